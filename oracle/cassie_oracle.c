@@ -1,0 +1,1037 @@
+/* cassie_oracle.c -- fp64 CPU ORACLE for the cassie_sim_step_pd hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (cassie-mujoco-sim_b200/, include/) may link,
+ * import or call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker / CPU baseline.
+ *
+ * What it restates (reference = osudrl/cassie-mujoco-sim @ /root/reference):
+ *   - glue and ordering of cassie_sim_step_pd        src/cassiemujoco.c:1115-1157
+ *   - robot I/O emulation (encoders, filters, motor) src/cassiemujoco.c:194-208, 558-664, 737-803
+ *   - init / reset state                             src/cassiemujoco.c:695-734, 979-1036, 2008-2033
+ *   - the physics the reference obtains from the un-vendored binary MuJoCo 2.1.0
+ *     (mj_step1/mj_step2, src/cassiemujoco.c:1132-1133): kinematics, comPos, CRB, L'DL,
+ *     collision (plane-sphere/capsule, capsule-capsule), constraint assembly (connect, joint
+ *     limit, pyramidal contact), PGS with warm start, sensors, implicit-damping Euler.
+ *     This is a restatement of MuJoCo's published algorithm (Computation chapter + the
+ *     open-sourced engine_*.c), specialised to the features the Cassie models use.
+ *   - the closed Agility blocks pd_input_step (motor-PD branch) and cassie_core_sim_step
+ *     (safety layer), include/pd_input.h:34, include/cassie_core_sim.h:34, from black-box
+ *     probing.  With -DORACLE_USE_AGILITY_REF the real archive
+ *     src/libagilitycassie.a is linked instead (oracle/_ref/liboracle_ref.so) and
+ *     state_output_step is the real one.
+ *
+ * PARITY STATUS: physics parity vs MuJoCo 2.1.0 is UNPINNED -- MuJoCo is absent from the build
+ * container, the reference ships no golden trajectories.  The Agility-block
+ * twins ARE pinned against the archive (tests/test_agility_twins.py).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/cassie_bus.h"
+
+#define MINVAL 1e-15
+#define MAXV 48
+#define MAXB 40
+#define MAXJ 40
+#define MAXG 48
+#define MAXCON 64
+#define MAXEFC 320
+#define MAXNM 512
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6 };
+enum { C_EQUALITY = 0, C_LIMIT = 3, C_FRICTIONLESS = 5, C_PYRAMIDAL = 6 };
+
+typedef struct {
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, neq, nM, nsensor, nhfield;
+  double timestep, gravity[3], magnetic[3], tolerance, impratio, meaninertia;
+  int iterations;
+  int body_parentid[MAXB], body_rootid[MAXB], body_weldid[MAXB], body_jntnum[MAXB], body_jntadr[MAXB],
+      body_dofnum[MAXB], body_dofadr[MAXB];
+  double body_pos[MAXB][3], body_quat[MAXB][4], body_ipos[MAXB][3], body_iquat[MAXB][4], body_mass[MAXB],
+      body_inertia[MAXB][3], body_invweight0[MAXB][2], body_subtreemass[MAXB];
+  int jnt_type[MAXJ], jnt_qposadr[MAXJ], jnt_dofadr[MAXJ], jnt_bodyid[MAXJ], jnt_limited[MAXJ];
+  double jnt_pos[MAXJ][3], jnt_axis[MAXJ][3], jnt_stiffness[MAXJ], jnt_range[MAXJ][2], jnt_margin[MAXJ],
+      jnt_solref[MAXJ][2], jnt_solimp[MAXJ][5];
+  int dof_bodyid[MAXV], dof_jntid[MAXV], dof_parentid[MAXV], dof_Madr[MAXV];
+  double dof_armature[MAXV], dof_damping[MAXV], dof_invweight0[MAXV];
+  double qpos0[MAXV + 8], qpos_spring[MAXV + 8];
+  int geom_type[MAXG], geom_bodyid[MAXG], geom_contype[MAXG], geom_conaffinity[MAXG], geom_condim[MAXG],
+      geom_priority[MAXG], geom_hfid[MAXG];
+  double geom_pos[MAXG][3], geom_quat[MAXG][4], geom_size[MAXG][3], geom_friction[MAXG][3], geom_solref[MAXG][2],
+      geom_solimp[MAXG][5], geom_rbound[MAXG], geom_solmix[MAXG], geom_margin[MAXG], geom_gap[MAXG];
+  int site_bodyid[32];
+  double site_pos[32][3], site_quat[32][4];
+  int eq_obj1id[8], eq_obj2id[8];
+  double eq_data[8][6], eq_solref[8][2], eq_solimp[8][5];
+  int actuator_jntid[16], actuator_ctrllimited[16];
+  double actuator_gear[16], actuator_ctrlrange[16][2], actuator_user[16];
+  int sensor_type[32], sensor_objid[32];
+  double sensor_user[32], sensor_cutoff[32];
+  int hfield_nrow, hfield_ncol;
+  double hfield_size[4];
+  float *hfield_data;
+  int imu_site;
+} OModel;
+
+typedef struct {
+  double pos[3], frame[9], dist, friction[5], solref[2], solimp[5], includemargin, mu;
+  int dim, geom1, geom2;
+} OContact;
+
+typedef struct {
+  double time;
+  double qpos[MAXV + 8], qvel[MAXV], qacc[MAXV], qacc_warmstart[MAXV], ctrl[16], xfrc_applied[MAXB][6],
+      qfrc_applied[MAXV];
+  /* position-dependent */
+  double xpos[MAXB][3], xquat[MAXB][4], xmat[MAXB][9], xipos[MAXB][3], ximat[MAXB][9], xanchor[MAXJ][3],
+      xaxis[MAXJ][3], geom_xpos[MAXG][3], geom_xmat[MAXG][9], site_xpos[32][3], site_xmat[32][9],
+      subtree_com[MAXB][3], cdof[MAXV][6], cinert[MAXB][10], crb[MAXB][10], qM[MAXNM], qLD[MAXNM],
+      qLDiagInv[MAXV], qLDiagSqrtInv[MAXV];
+  int ncon, nefc, ne, nl;
+  OContact contact[MAXCON];
+  int efc_type[MAXEFC], efc_id[MAXEFC];
+  double efc_J[MAXEFC][MAXV], efc_pos[MAXEFC], efc_margin[MAXEFC], efc_diagApprox[MAXEFC], efc_R[MAXEFC],
+      efc_D[MAXEFC], efc_KBIP[MAXEFC][4], efc_vel[MAXEFC], efc_aref[MAXEFC], efc_b[MAXEFC], efc_force[MAXEFC];
+  double *efc_AR; /* nefc x nefc */
+  /* velocity-dependent */
+  double cvel[MAXB][6], cdof_dot[MAXV][6], qfrc_bias[MAXV], qfrc_passive[MAXV], actuator_velocity[16],
+      actuator_length[16], actuator_force[16], qfrc_actuator[MAXV], qfrc_smooth[MAXV], qacc_smooth[MAXV],
+      qfrc_constraint[MAXV], cacc[MAXB][6];
+  double sensordata[40];
+  int solver_iter, unsupported_pairs, dropped_contacts;
+} OData;
+
+/* ------------------------------------------------------------------ small vector math */
+static void zero(double *x, int n) { memset(x, 0, sizeof(double) * n); }
+static void copyv(double *d, const double *s, int n) { memcpy(d, s, sizeof(double) * n); }
+static double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static double dotn(const double *a, const double *b, int n) { double s = 0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+static void cross(double *r, const double *a, const double *b) {
+  r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
+}
+static double normalize3(double *v) {
+  double n = sqrt(dot3(v, v));
+  if (n < MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; return 0; }
+  v[0] /= n; v[1] /= n; v[2] /= n; return n;
+}
+static double normalize4(double *q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return 0; }
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n; return n;
+}
+static void mulQuat(double *r, const double *a, const double *b) {
+  double t[4] = {a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                 a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]};
+  copyv(r, t, 4);
+}
+static void quat2Mat(double *m, const double *q) {
+  double q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3], q11 = q[1] * q[1], q12 = q[1] * q[2],
+         q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03);
+  m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
+}
+static void rotVecQuat(double *r, const double *v, const double *q) {
+  double m[9]; quat2Mat(m, q);
+  double t[3] = {m[0] * v[0] + m[1] * v[1] + m[2] * v[2], m[3] * v[0] + m[4] * v[1] + m[5] * v[2], m[6] * v[0] + m[7] * v[1] + m[8] * v[2]};
+  copyv(r, t, 3);
+}
+static void mulMatVec3(double *r, const double *m, const double *v) {
+  double t[3] = {m[0] * v[0] + m[1] * v[1] + m[2] * v[2], m[3] * v[0] + m[4] * v[1] + m[5] * v[2], m[6] * v[0] + m[7] * v[1] + m[8] * v[2]};
+  copyv(r, t, 3);
+}
+static void mulMatTVec3(double *r, const double *m, const double *v) {
+  double t[3] = {m[0] * v[0] + m[3] * v[1] + m[6] * v[2], m[1] * v[0] + m[4] * v[1] + m[7] * v[2], m[2] * v[0] + m[5] * v[1] + m[8] * v[2]};
+  copyv(r, t, 3);
+}
+static void mulMatMat3(double *r, const double *a, const double *b) {
+  double t[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+  copyv(r, t, 9);
+}
+static void axisAngle2Quat(double *q, const double *axis, double ang) {
+  if (ang == 0) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  double s = sin(ang * 0.5);
+  q[0] = cos(ang * 0.5); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+/* spatial algebra in MuJoCo's (angular; linear) layout, 10-number inertias */
+static void mulInertVec(double *r, const double *i, const double *v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+static void crossMotion(double *r, const double *vel, const double *v) {
+  cross(r, vel, v);
+  double t[3]; cross(r + 3, vel, v + 3); cross(t, vel + 3, v);
+  r[3] += t[0]; r[4] += t[1]; r[5] += t[2];
+}
+static void crossForce(double *r, const double *vel, const double *f) {
+  double t[3]; cross(r, vel, f); cross(t, vel + 3, f + 3);
+  r[0] += t[0]; r[1] += t[1]; r[2] += t[2];
+  cross(r + 3, vel, f + 3);
+}
+
+/* ------------------------------------------------------------------ model loading */
+static int rd_i(char *tok[], int n, int *dst, int cap) { if (n > cap) n = cap; for (int i = 0; i < n; i++) dst[i] = atoi(tok[i]); return n; }
+static int rd_f(char *tok[], int n, double *dst, int cap) { if (n > cap) n = cap; for (int i = 0; i < n; i++) dst[i] = strtod(tok[i], NULL); return n; }
+
+OModel *omodel_load(const char *path) {
+  FILE *f = fopen(path, "r");
+  if (!f) { fprintf(stderr, "oracle: cannot open %s\n", path); return NULL; }
+  OModel *m = calloc(1, sizeof(OModel));
+  size_t cap = 1 << 20; char *line = malloc(cap);
+  static char *tok[70000];
+  char site_names[32][64]; int nsn = 0;
+  while (fgets(line, cap, f)) {
+    if (line[0] == '#') continue;
+    char *key = strtok(line, " \n"); if (!key) continue;
+    char *ty = strtok(NULL, " \n"); int n = atoi(strtok(NULL, " \n")); (void)ty;
+    int nt = 0; char *t;
+    while ((t = strtok(NULL, " \n")) && nt < 70000) tok[nt++] = t;
+    if (nt < n) n = nt;
+#define KI(name, dst, cap_) else if (!strcmp(key, name)) rd_i(tok, n, (int *)(dst), cap_)
+#define KF(name, dst, cap_) else if (!strcmp(key, name)) rd_f(tok, n, (double *)(dst), cap_)
+    if (0) {}
+    KI("nq", &m->nq, 1); KI("nv", &m->nv, 1); KI("nu", &m->nu, 1); KI("nbody", &m->nbody, 1); KI("njnt", &m->njnt, 1);
+    KI("ngeom", &m->ngeom, 1); KI("nsite", &m->nsite, 1); KI("neq", &m->neq, 1); KI("nM", &m->nM, 1);
+    KI("nsensor", &m->nsensor, 1); KI("nhfield", &m->nhfield, 1);
+    KF("opt_timestep", &m->timestep, 1); KF("opt_gravity", m->gravity, 3); KF("opt_magnetic", m->magnetic, 3);
+    KF("opt_tolerance", &m->tolerance, 1); KF("opt_impratio", &m->impratio, 1); KI("opt_iterations", &m->iterations, 1);
+    KF("stat_meaninertia", &m->meaninertia, 1);
+    KI("body_parentid", m->body_parentid, MAXB); KI("body_rootid", m->body_rootid, MAXB); KI("body_weldid", m->body_weldid, MAXB);
+    KI("body_jntnum", m->body_jntnum, MAXB); KI("body_jntadr", m->body_jntadr, MAXB); KI("body_dofnum", m->body_dofnum, MAXB);
+    KI("body_dofadr", m->body_dofadr, MAXB);
+    KF("body_pos", m->body_pos, MAXB * 3); KF("body_quat", m->body_quat, MAXB * 4); KF("body_ipos", m->body_ipos, MAXB * 3);
+    KF("body_iquat", m->body_iquat, MAXB * 4); KF("body_mass", m->body_mass, MAXB); KF("body_inertia", m->body_inertia, MAXB * 3);
+    KF("body_invweight0", m->body_invweight0, MAXB * 2); KF("body_subtreemass", m->body_subtreemass, MAXB);
+    KI("jnt_type", m->jnt_type, MAXJ); KI("jnt_qposadr", m->jnt_qposadr, MAXJ); KI("jnt_dofadr", m->jnt_dofadr, MAXJ);
+    KI("jnt_bodyid", m->jnt_bodyid, MAXJ); KI("jnt_limited", m->jnt_limited, MAXJ);
+    KF("jnt_pos", m->jnt_pos, MAXJ * 3); KF("jnt_axis", m->jnt_axis, MAXJ * 3); KF("jnt_stiffness", m->jnt_stiffness, MAXJ);
+    KF("jnt_range", m->jnt_range, MAXJ * 2); KF("jnt_margin", m->jnt_margin, MAXJ); KF("jnt_solref", m->jnt_solref, MAXJ * 2);
+    KF("jnt_solimp", m->jnt_solimp, MAXJ * 5);
+    KI("dof_bodyid", m->dof_bodyid, MAXV); KI("dof_jntid", m->dof_jntid, MAXV); KI("dof_parentid", m->dof_parentid, MAXV);
+    KI("dof_Madr", m->dof_Madr, MAXV);
+    KF("dof_armature", m->dof_armature, MAXV); KF("dof_damping", m->dof_damping, MAXV); KF("dof_invweight0", m->dof_invweight0, MAXV);
+    KF("qpos0", m->qpos0, MAXV + 8); KF("qpos_spring", m->qpos_spring, MAXV + 8);
+    KI("geom_type", m->geom_type, MAXG); KI("geom_bodyid", m->geom_bodyid, MAXG); KI("geom_contype", m->geom_contype, MAXG);
+    KI("geom_conaffinity", m->geom_conaffinity, MAXG); KI("geom_condim", m->geom_condim, MAXG);
+    KI("geom_priority", m->geom_priority, MAXG); KI("geom_hfid", m->geom_hfid, MAXG);
+    KF("geom_pos", m->geom_pos, MAXG * 3); KF("geom_quat", m->geom_quat, MAXG * 4); KF("geom_size", m->geom_size, MAXG * 3);
+    KF("geom_friction", m->geom_friction, MAXG * 3); KF("geom_solref", m->geom_solref, MAXG * 2);
+    KF("geom_solimp", m->geom_solimp, MAXG * 5); KF("geom_rbound", m->geom_rbound, MAXG); KF("geom_solmix", m->geom_solmix, MAXG);
+    KF("geom_margin", m->geom_margin, MAXG); KF("geom_gap", m->geom_gap, MAXG);
+    KI("site_bodyid", m->site_bodyid, 32); KF("site_pos", m->site_pos, 96); KF("site_quat", m->site_quat, 128);
+    KI("eq_obj1id", m->eq_obj1id, 8); KI("eq_obj2id", m->eq_obj2id, 8); KF("eq_data", m->eq_data, 48);
+    KF("eq_solref", m->eq_solref, 16); KF("eq_solimp", m->eq_solimp, 40);
+    KI("actuator_jntid", m->actuator_jntid, 16); KI("actuator_ctrllimited", m->actuator_ctrllimited, 16);
+    KF("actuator_gear", m->actuator_gear, 16); KF("actuator_ctrlrange", m->actuator_ctrlrange, 32); KF("actuator_user", m->actuator_user, 16);
+    KI("sensor_type", m->sensor_type, 32); KI("sensor_objid", m->sensor_objid, 32);
+    KF("sensor_user", m->sensor_user, 32); KF("sensor_cutoff", m->sensor_cutoff, 32);
+    KI("hfield_nrow", &m->hfield_nrow, 1); KI("hfield_ncol", &m->hfield_ncol, 1); KF("hfield_size", m->hfield_size, 4);
+    else if (!strcmp(key, "names_site")) { for (int i = 0; i < n && i < 32; i++) { strncpy(site_names[i], tok[i], 63); site_names[i][63] = 0; } nsn = n < 32 ? n : 32; }
+  }
+  fclose(f); free(line);
+  m->imu_site = 0;
+  for (int i = 0; i < nsn; i++) if (!strcmp(site_names[i], "imu")) m->imu_site = i;
+  if (m->nhfield) m->hfield_data = calloc((size_t)m->hfield_nrow * m->hfield_ncol, sizeof(float));
+  if (m->nv > MAXV || m->nbody > MAXB || m->ngeom > MAXG || m->nM > MAXNM) { fprintf(stderr, "oracle: model too large\n"); free(m); return NULL; }
+  return m;
+}
+void omodel_free(OModel *m) { if (m) { free(m->hfield_data); free(m); } }
+
+/* ------------------------------------------------------------------ position stage (mj_fwdPosition) */
+static void o_kinematics(const OModel *m, OData *d) {
+  zero(d->xpos[0], 3); d->xquat[0][0] = 1; d->xquat[0][1] = d->xquat[0][2] = d->xquat[0][3] = 0;
+  quat2Mat(d->xmat[0], d->xquat[0]); zero(d->xipos[0], 3); copyv(d->ximat[0], d->xmat[0], 9);
+  for (int i = 1; i < m->nbody; i++) {
+    double xpos[3], xquat[4];
+    int jadr = m->body_jntadr[i];
+    if (m->body_jntnum[i] == 1 && m->jnt_type[jadr] == JNT_FREE) {
+      int qa = m->jnt_qposadr[jadr];
+      copyv(xpos, d->qpos + qa, 3); copyv(xquat, d->qpos + qa + 3, 4); normalize4(xquat);
+      copyv(d->xanchor[jadr], xpos, 3); copyv(d->xaxis[jadr], m->jnt_axis[jadr], 3);
+    } else {
+      int pid = m->body_parentid[i];
+      if (pid) {
+        double v[3]; mulMatVec3(v, d->xmat[pid], m->body_pos[i]);
+        for (int k = 0; k < 3; k++) xpos[k] = d->xpos[pid][k] + v[k];
+        mulQuat(xquat, d->xquat[pid], m->body_quat[i]);
+      } else { copyv(xpos, m->body_pos[i], 3); copyv(xquat, m->body_quat[i], 4); }
+      for (int j = 0; j < m->body_jntnum[i]; j++) {
+        int jid = jadr + j, qa = m->jnt_qposadr[jid];
+        rotVecQuat(d->xaxis[jid], m->jnt_axis[jid], xquat);
+        double v[3]; rotVecQuat(v, m->jnt_pos[jid], xquat);
+        for (int k = 0; k < 3; k++) d->xanchor[jid][k] = xpos[k] + v[k];
+        if (m->jnt_type[jid] == JNT_SLIDE) {
+          double s = d->qpos[qa] - m->qpos0[qa];
+          for (int k = 0; k < 3; k++) xpos[k] += d->xaxis[jid][k] * s;
+        } else {
+          double qloc[4];
+          if (m->jnt_type[jid] == JNT_BALL) { copyv(qloc, d->qpos + qa, 4); normalize4(qloc); }
+          else axisAngle2Quat(qloc, m->jnt_axis[jid], d->qpos[qa] - m->qpos0[qa]);
+          mulQuat(xquat, xquat, qloc);
+          rotVecQuat(v, m->jnt_pos[jid], xquat);
+          for (int k = 0; k < 3; k++) xpos[k] = d->xanchor[jid][k] - v[k];
+        }
+      }
+    }
+    normalize4(xquat);
+    copyv(d->xpos[i], xpos, 3); copyv(d->xquat[i], xquat, 4); quat2Mat(d->xmat[i], xquat);
+    double v[3], iq[4];
+    mulMatVec3(v, d->xmat[i], m->body_ipos[i]);
+    for (int k = 0; k < 3; k++) d->xipos[i][k] = xpos[k] + v[k];
+    mulQuat(iq, xquat, m->body_iquat[i]); quat2Mat(d->ximat[i], iq);
+  }
+  for (int g = 0; g < m->ngeom; g++) {
+    int b = m->geom_bodyid[g]; double v[3], q[4];
+    mulMatVec3(v, d->xmat[b], m->geom_pos[g]);
+    for (int k = 0; k < 3; k++) d->geom_xpos[g][k] = d->xpos[b][k] + v[k];
+    mulQuat(q, d->xquat[b], m->geom_quat[g]); quat2Mat(d->geom_xmat[g], q);
+  }
+  for (int s = 0; s < m->nsite; s++) {
+    int b = m->site_bodyid[s]; double v[3], q[4];
+    mulMatVec3(v, d->xmat[b], m->site_pos[s]);
+    for (int k = 0; k < 3; k++) d->site_xpos[s][k] = d->xpos[b][k] + v[k];
+    mulQuat(q, d->xquat[b], m->site_quat[s]); quat2Mat(d->site_xmat[s], q);
+  }
+}
+
+static void o_comPos(const OModel *m, OData *d) {
+  for (int i = 0; i < m->nbody; i++) zero(d->subtree_com[i], 3);
+  for (int i = m->nbody - 1; i >= 0; i--) {
+    for (int k = 0; k < 3; k++) d->subtree_com[i][k] += d->xipos[i][k] * m->body_mass[i];
+    if (i) for (int k = 0; k < 3; k++) d->subtree_com[m->body_parentid[i]][k] += d->subtree_com[i][k];
+    if (m->body_subtreemass[i] < MINVAL) copyv(d->subtree_com[i], d->xipos[i], 3);
+    else for (int k = 0; k < 3; k++) d->subtree_com[i][k] /= m->body_subtreemass[i];
+  }
+  zero(d->cinert[0], 10);
+  for (int i = 1; i < m->nbody; i++) {
+    double off[3]; const double *com = d->subtree_com[m->body_rootid[i]];
+    for (int k = 0; k < 3; k++) off[k] = d->xipos[i][k] - com[k];
+    const double *R = d->ximat[i], *I = m->body_inertia[i]; double mass = m->body_mass[i], *r = d->cinert[i];
+    /* R diag(I) R' in (xx yy zz xy xz yz) order, then parallel axis */
+    r[0] = R[0] * R[0] * I[0] + R[1] * R[1] * I[1] + R[2] * R[2] * I[2];
+    r[1] = R[3] * R[3] * I[0] + R[4] * R[4] * I[1] + R[5] * R[5] * I[2];
+    r[2] = R[6] * R[6] * I[0] + R[7] * R[7] * I[1] + R[8] * R[8] * I[2];
+    r[3] = R[0] * R[3] * I[0] + R[1] * R[4] * I[1] + R[2] * R[5] * I[2];
+    r[4] = R[0] * R[6] * I[0] + R[1] * R[7] * I[1] + R[2] * R[8] * I[2];
+    r[5] = R[3] * R[6] * I[0] + R[4] * R[7] * I[1] + R[5] * R[8] * I[2];
+    r[0] += mass * (off[1] * off[1] + off[2] * off[2]); r[1] += mass * (off[0] * off[0] + off[2] * off[2]);
+    r[2] += mass * (off[0] * off[0] + off[1] * off[1]);
+    r[3] -= mass * off[0] * off[1]; r[4] -= mass * off[0] * off[2]; r[5] -= mass * off[1] * off[2];
+    r[6] = mass * off[0]; r[7] = mass * off[1]; r[8] = mass * off[2]; r[9] = mass;
+  }
+  for (int j = 0; j < m->njnt; j++) {
+    int da = m->jnt_dofadr[j], bi = m->jnt_bodyid[j]; double off[3]; const double *com = d->subtree_com[m->body_rootid[bi]];
+    for (int k = 0; k < 3; k++) off[k] = com[k] - d->xanchor[j][k];
+    switch (m->jnt_type[j]) {
+      case JNT_FREE:
+        for (int k = 0; k < 3; k++) { zero(d->cdof[da + k], 6); d->cdof[da + k][3 + k] = 1; }
+        da += 3; /* fallthrough */
+      case JNT_BALL:
+        for (int k = 0; k < 3; k++) {
+          double ax[3] = {d->xmat[bi][k], d->xmat[bi][k + 3], d->xmat[bi][k + 6]};
+          copyv(d->cdof[da + k], ax, 3); cross(d->cdof[da + k] + 3, ax, off);
+        }
+        break;
+      case JNT_SLIDE: zero(d->cdof[da], 3); copyv(d->cdof[da] + 3, d->xaxis[j], 3); break;
+      case JNT_HINGE: copyv(d->cdof[da], d->xaxis[j], 3); cross(d->cdof[da] + 3, d->xaxis[j], off); break;
+    }
+  }
+}
+
+static void o_crb(const OModel *m, OData *d) {
+  memcpy(d->crb, d->cinert, sizeof(double) * 10 * m->nbody);
+  for (int i = m->nbody - 1; i > 0; i--) if (m->body_parentid[i] > 0)
+    for (int k = 0; k < 10; k++) d->crb[m->body_parentid[i]][k] += d->crb[i][k];
+  zero(d->qM, m->nM);
+  for (int i = 0; i < m->nv; i++) {
+    int adr = m->dof_Madr[i]; double buf[6];
+    d->qM[adr] = m->dof_armature[i];
+    mulInertVec(buf, d->crb[m->dof_bodyid[i]], d->cdof[i]);
+    for (int j = i; j >= 0; j = m->dof_parentid[j]) d->qM[adr++] += dotn(d->cdof[j], buf, 6);
+  }
+}
+
+static void factorI(const OModel *m, double *qLD, double *diaginv, double *sqrtinv) {
+  int nv = m->nv;
+  for (int k = nv - 1; k >= 0; k--) {
+    int kk = m->dof_Madr[k], ki = kk + 1;
+    for (int i = m->dof_parentid[k]; i >= 0; i = m->dof_parentid[i], ki++) {
+      double tmp = qLD[ki] / qLD[kk];
+      int cnt = (i < nv - 1 ? m->dof_Madr[i + 1] : m->nM) - m->dof_Madr[i];
+      for (int c = 0; c < cnt; c++) qLD[m->dof_Madr[i] + c] -= qLD[ki + c] * tmp;
+      qLD[ki] = tmp;
+    }
+  }
+  for (int i = 0; i < nv; i++) { diaginv[i] = 1.0 / qLD[m->dof_Madr[i]]; if (sqrtinv) sqrtinv[i] = 1.0 / sqrt(qLD[m->dof_Madr[i]]); }
+}
+static void solveLD(const OModel *m, double *x, const double *qLD, const double *diaginv) {
+  int nv = m->nv;
+  for (int i = nv - 1; i >= 0; i--) if (x[i] != 0) { int a = m->dof_Madr[i] + 1; for (int j = m->dof_parentid[i]; j >= 0; j = m->dof_parentid[j]) x[j] -= qLD[a++] * x[i]; }
+  for (int i = 0; i < nv; i++) x[i] *= diaginv[i];
+  for (int i = 0; i < nv; i++) { int a = m->dof_Madr[i] + 1; for (int j = m->dof_parentid[i]; j >= 0; j = m->dof_parentid[j]) x[i] -= qLD[a++] * x[j]; }
+}
+/* x <- sqrt(inv(D)) inv(L') x */
+static void solveM2(const OModel *m, const OData *d, double *x) {
+  int nv = m->nv;
+  for (int i = nv - 1; i >= 0; i--) if (x[i] != 0) { int a = m->dof_Madr[i] + 1; for (int j = m->dof_parentid[i]; j >= 0; j = m->dof_parentid[j]) x[j] -= d->qLD[a++] * x[i]; }
+  for (int i = 0; i < nv; i++) x[i] *= d->qLDiagSqrtInv[i];
+}
+
+/* jacobian of a world point attached to body (mj_jac) */
+static void o_jac(const OModel *m, const OData *d, double *jacp, double *jacr, const double *point, int body) {
+  int nv = m->nv; double off[3];
+  if (jacp) zero(jacp, 3 * nv); if (jacr) zero(jacr, 3 * nv);
+  for (int k = 0; k < 3; k++) off[k] = point[k] - d->subtree_com[m->body_rootid[body]][k];
+  while (body && !m->body_dofnum[body]) body = m->body_parentid[body];
+  if (!body) return;
+  for (int i = m->body_dofadr[body] + m->body_dofnum[body] - 1; i >= 0; i = m->dof_parentid[i]) {
+    if (jacr) for (int k = 0; k < 3; k++) jacr[k * nv + i] = d->cdof[i][k];
+    if (jacp) { double t[3]; cross(t, d->cdof[i], off); for (int k = 0; k < 3; k++) jacp[k * nv + i] = d->cdof[i][3 + k] + t[k]; }
+  }
+}
+
+/* ---------------- collision (mj_collision, specialised to the geom types the Cassie models use) */
+static void make_frame(double *f) {
+  normalize3(f);
+  if (sqrt(dot3(f + 3, f + 3)) < 0.5) { f[3] = f[4] = f[5] = 0; if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1; }
+  double s = dot3(f, f + 3);
+  for (int k = 0; k < 3; k++) f[3 + k] -= f[k] * s;
+  normalize3(f + 3); cross(f + 6, f, f + 3);
+}
+static int raw_plane_sphere(OContact *c, double margin, const double *ppos, const double *pmat, const double *spos, double r) {
+  double n[3] = {pmat[2], pmat[5], pmat[8]}, t[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
+  double cdist = dot3(t, n);
+  if (cdist > margin + r) return 0;
+  c->dist = cdist - r; copyv(c->frame, n, 3); zero(c->frame + 3, 6);
+  for (int k = 0; k < 3; k++) c->pos[k] = spos[k] - n[k] * (c->dist * 0.5 + r);
+  return 1;
+}
+static int raw_sphere_sphere(OContact *c, double margin, const double *p1, double r1, const double *p2, double r2) {
+  double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double cdist = sqrt(dot3(dif, dif));
+  if (cdist > margin + r1 + r2) return 0;
+  c->dist = cdist - r1 - r2;
+  if (cdist < MINVAL) { c->frame[0] = 1; c->frame[1] = c->frame[2] = 0; } else for (int k = 0; k < 3; k++) c->frame[k] = dif[k] / cdist;
+  zero(c->frame + 3, 6);
+  for (int k = 0; k < 3; k++) c->pos[k] = p1[k] + c->frame[k] * (r1 + c->dist * 0.5);
+  return 1;
+}
+static int col_plane_capsule(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
+  const double *mat2 = d->geom_xmat[g2]; double ax[3] = {mat2[2], mat2[5], mat2[8]}, p[3]; double hl = m->geom_size[g2][1];
+  for (int k = 0; k < 3; k++) p[k] = d->geom_xpos[g2][k] + ax[k] * hl;
+  int n1 = raw_plane_sphere(c, margin, d->geom_xpos[g1], d->geom_xmat[g1], p, m->geom_size[g2][0]);
+  for (int k = 0; k < 3; k++) p[k] = d->geom_xpos[g2][k] - ax[k] * hl;
+  int n2 = raw_plane_sphere(c + n1, margin, d->geom_xpos[g1], d->geom_xmat[g1], p, m->geom_size[g2][0]);
+  for (int i = 0; i < n1 + n2; i++) copyv(c[i].frame + 3, ax, 3);
+  return n1 + n2;
+}
+static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+static int col_capsule_capsule(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
+  const double *m1 = d->geom_xmat[g1], *m2 = d->geom_xmat[g2], *p1 = d->geom_xpos[g1], *p2 = d->geom_xpos[g2];
+  double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]}, dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  double s1 = m->geom_size[g1][1], s2 = m->geom_size[g2][1], r1 = m->geom_size[g1][0], r2 = m->geom_size[g2][0];
+  double ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif), det = ma * mc - mb * mb;
+  double v1[3], v2[3];
+  if (fabs(det) >= MINVAL) {
+    double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > s1) { x1 = s1; x2 = (v - mb * s1) / mc; } else if (x1 < -s1) { x1 = -s1; x2 = (v + mb * s1) / mc; }
+    if (x2 > s2) { x2 = s2; x1 = clampd((u - mb * s2) / ma, -s1, s1); } else if (x2 < -s2) { x2 = -s2; x1 = clampd((u + mb * s2) / ma, -s1, s1); }
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
+    return raw_sphere_sphere(c, margin, v1, r1, v2, r2);
+  }
+  /* parallel axes: test the segment ends of 1 against 2, then of 2 against 1; keep at most 2 */
+  int n = 0;
+  for (int e = 0; e < 2 && n < 2; e++) {
+    double x1 = e ? -s1 : s1, x2 = clampd((v - mb * x1) / mc, -s2, s2);
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
+    n += raw_sphere_sphere(c + n, margin, v1, r1, v2, r2);
+  }
+  for (int e = 0; e < 2 && n < 2; e++) {
+    double x2 = e ? -s2 : s2, x1 = clampd((u - mb * x2) / ma, -s1, s1);
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
+    n += raw_sphere_sphere(c + n, margin, v1, r1, v2, r2);
+  }
+  return n;
+}
+
+static void collide_geoms(const OModel *m, OData *d, int g1, int g2) {
+  if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+  if (!((m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]))) return;
+  double margin = fmax(m->geom_margin[g1], m->geom_margin[g2]), gap = fmax(m->geom_gap[g1], m->geom_gap[g2]);
+  int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  /* bounding-sphere filter */
+  if (m->geom_rbound[g1] > 0 && m->geom_rbound[g2] > 0) {
+    double dif[3]; for (int k = 0; k < 3; k++) dif[k] = d->geom_xpos[g1][k] - d->geom_xpos[g2][k];
+    double bound = m->geom_rbound[g1] + m->geom_rbound[g2] + margin;
+    if (dot3(dif, dif) > bound * bound) return;
+  } else if (t1 == G_PLANE && m->geom_rbound[g2] > 0) {
+    const double *pm = d->geom_xmat[g1]; double n[3] = {pm[2], pm[5], pm[8]}, dif[3];
+    for (int k = 0; k < 3; k++) dif[k] = d->geom_xpos[g2][k] - d->geom_xpos[g1][k];
+    if (dot3(dif, n) > m->geom_rbound[g2] + margin) return;
+  }
+  OContact con[4]; int num = 0;
+  if (t1 == G_PLANE && t2 == G_SPHERE) num = raw_plane_sphere(con, margin, d->geom_xpos[g1], d->geom_xmat[g1], d->geom_xpos[g2], m->geom_size[g2][0]);
+  else if (t1 == G_PLANE && t2 == G_CAPSULE) num = col_plane_capsule(m, d, con, g1, g2, margin);
+  else if (t1 == G_CAPSULE && t2 == G_CAPSULE) num = col_capsule_capsule(m, d, con, g1, g2, margin);
+  else { d->unsupported_pairs++; return; }
+  if (!num) return;
+  /* contact parameter mixing (mj_contactParam) */
+  int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2], dim; double fr[3], solref[2], solimp[5];
+  if (p1 != p2) {
+    int g = p1 > p2 ? g1 : g2; dim = m->geom_condim[g];
+    copyv(fr, m->geom_friction[g], 3); copyv(solref, m->geom_solref[g], 2); copyv(solimp, m->geom_solimp[g], 5);
+  } else {
+    dim = m->geom_condim[g1] > m->geom_condim[g2] ? m->geom_condim[g1] : m->geom_condim[g2];
+    double mix, s1 = m->geom_solmix[g1], s2 = m->geom_solmix[g2];
+    if (s1 >= MINVAL && s2 >= MINVAL) mix = s1 / (s1 + s2); else if (s1 < MINVAL && s2 < MINVAL) mix = 0.5; else mix = s1 < MINVAL ? 0.0 : 1.0;
+    if (m->geom_solref[g1][0] > 0 && m->geom_solref[g2][0] > 0) for (int k = 0; k < 2; k++) solref[k] = mix * m->geom_solref[g1][k] + (1 - mix) * m->geom_solref[g2][k];
+    else for (int k = 0; k < 2; k++) solref[k] = fmin(m->geom_solref[g1][k], m->geom_solref[g2][k]);
+    for (int k = 0; k < 5; k++) solimp[k] = mix * m->geom_solimp[g1][k] + (1 - mix) * m->geom_solimp[g2][k];
+    for (int k = 0; k < 3; k++) fr[k] = fmax(m->geom_friction[g1][k], m->geom_friction[g2][k]);
+  }
+  for (int i = 0; i < num; i++) {
+    if (con[i].dist >= margin) continue; /* only penetrating (dist < margin) contacts are kept */
+    if (d->ncon >= MAXCON) { d->dropped_contacts++; continue; }
+    OContact *c = &d->contact[d->ncon++];
+    *c = con[i]; c->geom1 = g1; c->geom2 = g2; c->dim = dim; c->includemargin = margin - gap;
+    c->friction[0] = c->friction[1] = fr[0]; c->friction[2] = fr[1]; c->friction[3] = c->friction[4] = fr[2];
+    copyv(c->solref, solref, 2); copyv(c->solimp, solimp, 5);
+    make_frame(c->frame);
+  }
+}
+
+static void o_collision(const OModel *m, OData *d) {
+  d->ncon = 0;
+  /* body pairs in ascending (b1,b2) order == MuJoCo's sorted broadphase output; the AABB sweep itself only
+     prunes pairs that the bounding-sphere / narrow phase would reject anyway */
+  for (int b1 = 0; b1 < m->nbody; b1++) for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
+    int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
+    if (w1 == w2) continue;
+    if (w1 && w2 && (m->body_weldid[m->body_parentid[w1]] == w2 || m->body_weldid[m->body_parentid[w2]] == w1)) continue;
+    for (int g1 = 0; g1 < m->ngeom; g1++) if (m->geom_bodyid[g1] == b1)
+      for (int g2 = 0; g2 < m->ngeom; g2++) if (m->geom_bodyid[g2] == b2) collide_geoms(m, d, g1, g2);
+  }
+}
+
+/* ---------------- constraints (mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint) */
+static int add_row(OData *d, const double *J, int nv, double pos, double margin, int type, int id) {
+  if (d->nefc >= MAXEFC) return -1;
+  int r = d->nefc++;
+  copyv(d->efc_J[r], J, nv); d->efc_pos[r] = pos; d->efc_margin[r] = margin; d->efc_type[r] = type; d->efc_id[r] = id;
+  return r;
+}
+static void get_impedance(const double *solimp, double pos, double margin, double *imp) {
+  if (solimp[0] == solimp[1] || solimp[2] <= MINVAL) { *imp = 0.5 * (solimp[0] + solimp[1]); return; }
+  double x = fabs((pos - margin) / solimp[2]);
+  if (x >= 1) { *imp = solimp[1]; return; }
+  if (x <= 0) { *imp = solimp[0]; return; }
+  double y, p = solimp[4], mid = solimp[3];
+  if (p == 1) y = x;
+  else if (x <= mid) y = pow(x, p) / pow(mid, p - 1);
+  else y = 1 - pow(1 - x, p) / pow(1 - mid, p - 1);
+  *imp = solimp[0] + y * (solimp[1] - solimp[0]);
+}
+static void o_makeConstraint(const OModel *m, OData *d) {
+  int nv = m->nv; double jp1[3 * MAXV], jp2[3 * MAXV], J[4][MAXV];
+  d->nefc = d->ne = d->nl = 0;
+  /* equality: connect */
+  for (int e = 0; e < m->neq; e++) {
+    int b1 = m->eq_obj1id[e], b2 = m->eq_obj2id[e]; double p1[3], p2[3], v[3];
+    mulMatVec3(v, d->xmat[b1], m->eq_data[e]); for (int k = 0; k < 3; k++) p1[k] = d->xpos[b1][k] + v[k];
+    mulMatVec3(v, d->xmat[b2], m->eq_data[e] + 3); for (int k = 0; k < 3; k++) p2[k] = d->xpos[b2][k] + v[k];
+    o_jac(m, d, jp1, NULL, p1, b1); o_jac(m, d, jp2, NULL, p2, b2);
+    for (int k = 0; k < 3; k++) {
+      for (int i = 0; i < nv; i++) J[0][i] = jp1[k * nv + i] - jp2[k * nv + i];
+      add_row(d, J[0], nv, p1[k] - p2[k], 0, C_EQUALITY, e);
+    }
+    d->ne += 3;
+  }
+  /* joint limits */
+  for (int j = 0; j < m->njnt; j++) if (m->jnt_limited[j] && (m->jnt_type[j] == JNT_HINGE || m->jnt_type[j] == JNT_SLIDE)) {
+    double value = d->qpos[m->jnt_qposadr[j]], margin = m->jnt_margin[j];
+    for (int side = -1; side <= 1; side += 2) {
+      double dist = side * (m->jnt_range[j][(side + 1) / 2] - value);
+      if (dist < margin) { zero(J[0], nv); J[0][m->jnt_dofadr[j]] = -(double)side; add_row(d, J[0], nv, dist, margin, C_LIMIT, j); d->nl++; }
+    }
+  }
+  /* contacts */
+  for (int c = 0; c < d->ncon; c++) {
+    OContact *con = &d->contact[c]; int b1 = m->geom_bodyid[con->geom1], b2 = m->geom_bodyid[con->geom2];
+    o_jac(m, d, jp1, NULL, con->pos, b1); o_jac(m, d, jp2, NULL, con->pos, b2);
+    int nr = con->dim > 1 ? 3 : 1;
+    for (int r = 0; r < nr; r++) for (int i = 0; i < nv; i++) {
+      double s = 0; for (int k = 0; k < 3; k++) s += con->frame[3 * r + k] * (jp2[k * nv + i] - jp1[k * nv + i]);
+      J[r][i] = s;
+    }
+    if (con->dim == 1) add_row(d, J[0], nv, con->dist, con->includemargin, C_FRICTIONLESS, c);
+    else for (int k = 1; k < con->dim; k++) {
+      double row[MAXV];
+      for (int i = 0; i < nv; i++) row[i] = J[0][i] + con->friction[k - 1] * J[k][i];
+      add_row(d, row, nv, con->dist, con->includemargin, C_PYRAMIDAL, c);
+      for (int i = 0; i < nv; i++) row[i] = J[0][i] - con->friction[k - 1] * J[k][i];
+      add_row(d, row, nv, con->dist, con->includemargin, C_PYRAMIDAL, c);
+    }
+  }
+  /* diagApprox, impedance, R, KBIP (mj_makeImpedance) */
+  for (int i = 0; i < d->nefc; i++) {
+    const double *solref, *solimp; int id = d->efc_id[i];
+    switch (d->efc_type[i]) {
+      case C_EQUALITY: d->efc_diagApprox[i] = m->body_invweight0[m->eq_obj1id[id]][0] + m->body_invweight0[m->eq_obj2id[id]][0];
+        solref = m->eq_solref[id]; solimp = m->eq_solimp[id]; break;
+      case C_LIMIT: d->efc_diagApprox[i] = m->dof_invweight0[m->jnt_dofadr[id]]; solref = m->jnt_solref[id]; solimp = m->jnt_solimp[id]; break;
+      default: {
+        OContact *con = &d->contact[id];
+        double tran = m->body_invweight0[m->geom_bodyid[con->geom1]][0] + m->body_invweight0[m->geom_bodyid[con->geom2]][0];
+        if (d->efc_type[i] == C_FRICTIONLESS) d->efc_diagApprox[i] = tran;
+        else { /* which of the 2*(dim-1) pyramid rows is this? rows of one contact are contiguous */
+          int first = i; while (first > 0 && d->efc_type[first - 1] == C_PYRAMIDAL && d->efc_id[first - 1] == id) first--;
+          double fri = con->friction[(i - first) / 2];
+          d->efc_diagApprox[i] = tran + fri * fri * tran;
+        }
+        solref = con->solref; solimp = con->solimp;
+      }
+    }
+    double sr0 = solref[0], sr1 = solref[1];
+    if (sr0 > 0) sr0 = fmax(sr0, 2 * m->timestep); /* refsafe */
+    double imp; get_impedance(solimp, d->efc_pos[i], d->efc_margin[i], &imp);
+    d->efc_R[i] = fmax(MINVAL, (1 - imp) * d->efc_diagApprox[i] / imp);
+    if (sr0 > 0) { d->efc_KBIP[i][0] = 1 / fmax(MINVAL, solimp[1] * solimp[1] * sr0 * sr0 * sr1 * sr1); d->efc_KBIP[i][1] = 2 / fmax(MINVAL, solimp[1] * sr0); }
+    else { d->efc_KBIP[i][0] = -sr0 / fmax(MINVAL, solimp[1] * solimp[1]); d->efc_KBIP[i][1] = -sr1 / fmax(MINVAL, solimp[1]); }
+    d->efc_KBIP[i][2] = imp; d->efc_KBIP[i][3] = 0;
+  }
+  /* pyramidal contacts: all rows of a contact share R = 2 mu^2 R[first] */
+  for (int i = 0; i < d->nefc; i++) if (d->efc_type[i] == C_PYRAMIDAL) {
+    OContact *con = &d->contact[d->efc_id[i]]; int n = 2 * (con->dim - 1);
+    con->mu = con->friction[0] / sqrt(m->impratio);
+    double Rpy = 2 * con->mu * con->mu * d->efc_R[i];
+    for (int j = 0; j < n; j++) d->efc_R[i + j] = Rpy;
+    i += n - 1;
+  }
+  for (int i = 0; i < d->nefc; i++) d->efc_D[i] = 1 / d->efc_R[i];
+}
+static void o_projectConstraint(const OModel *m, OData *d) {
+  int n = d->nefc, nv = m->nv;
+  free(d->efc_AR); d->efc_AR = NULL; if (!n) return;
+  double *JM2 = malloc(sizeof(double) * n * nv);
+  for (int i = 0; i < n; i++) { copyv(JM2 + i * nv, d->efc_J[i], nv); solveM2(m, d, JM2 + i * nv); }
+  d->efc_AR = malloc(sizeof(double) * n * n);
+  for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { double s = dotn(JM2 + i * nv, JM2 + j * nv, nv); d->efc_AR[i * n + j] = d->efc_AR[j * n + i] = s; }
+  for (int i = 0; i < n; i++) d->efc_AR[i * n + i] += d->efc_R[i];
+  free(JM2);
+}
+
+/* ---------------- sensors: the 29-number Cassie layout (model/cassie.xml:272-292) */
+static void o_sensor(const OModel *m, OData *d, int stage) {
+  int adr = 0;
+  for (int s = 0; s < m->nsensor; s++) {
+    int t = m->sensor_type[s], obj = m->sensor_objid[s], dim = (t <= 1) ? 1 : (t == 2 ? 4 : 3);
+    double *out = d->sensordata + adr; int st = (t == 3) ? 1 : (t == 4 ? 2 : 0);
+    if (st == stage) {
+      if (t == 0) out[0] = d->actuator_length[obj];
+      else if (t == 1) out[0] = d->qpos[m->jnt_qposadr[obj]];
+      else if (t == 2) { mulQuat(out, d->xquat[m->site_bodyid[obj]], m->site_quat[obj]); }
+      else if (t == 5) mulMatTVec3(out, d->site_xmat[obj], m->magnetic);
+      else {
+        int b = m->site_bodyid[obj]; const double *com = d->subtree_com[m->body_rootid[b]]; double dif[3], vel[6], t3[3];
+        for (int k = 0; k < 3; k++) dif[k] = d->site_xpos[obj][k] - com[k];
+        copyv(vel, d->cvel[b], 6); cross(t3, dif, d->cvel[b]); for (int k = 0; k < 3; k++) vel[3 + k] -= t3[k];
+        if (t == 3) mulMatTVec3(out, d->site_xmat[obj], vel);
+        else {
+          double acc[6], la[3], lv[3], lw[3], corr[3];
+          copyv(acc, d->cacc[b], 6); cross(t3, dif, d->cacc[b]); for (int k = 0; k < 3; k++) acc[3 + k] -= t3[k];
+          mulMatTVec3(la, d->site_xmat[obj], acc + 3); mulMatTVec3(lw, d->site_xmat[obj], vel); mulMatTVec3(lv, d->site_xmat[obj], vel + 3);
+          cross(corr, lw, lv);
+          for (int k = 0; k < 3; k++) out[k] = la[k] + corr[k];
+        }
+      }
+      if (m->sensor_cutoff[s] > 0) for (int k = 0; k < dim; k++) out[k] = clampd(out[k], -m->sensor_cutoff[s], m->sensor_cutoff[s]);
+    }
+    adr += dim;
+  }
+}
+
+/* ---------------- velocity stage */
+static void o_comVel(const OModel *m, OData *d) {
+  zero(d->cvel[0], 6);
+  for (int i = 1; i < m->nbody; i++) {
+    double cvel[6]; copyv(cvel, d->cvel[m->body_parentid[i]], 6);
+    int bda = m->body_dofadr[i];
+    for (int j = 0; j < m->body_dofnum[i]; j++) {
+      int jt = m->jnt_type[m->dof_jntid[bda + j]];
+      if (jt == JNT_FREE) {
+        for (int k = 0; k < 3; k++) { zero(d->cdof_dot[bda + k], 6); for (int c = 0; c < 6; c++) cvel[c] += d->cdof[bda + k][c] * d->qvel[bda + k]; }
+        j += 3; jt = JNT_BALL;
+      }
+      if (jt == JNT_BALL) {
+        for (int k = 0; k < 3; k++) crossMotion(d->cdof_dot[bda + j + k], cvel, d->cdof[bda + j + k]);
+        for (int k = 0; k < 3; k++) for (int c = 0; c < 6; c++) cvel[c] += d->cdof[bda + j + k][c] * d->qvel[bda + j + k];
+        j += 2;
+      } else {
+        crossMotion(d->cdof_dot[bda + j], cvel, d->cdof[bda + j]);
+        for (int c = 0; c < 6; c++) cvel[c] += d->cdof[bda + j][c] * d->qvel[bda + j];
+      }
+    }
+    copyv(d->cvel[i], cvel, 6);
+  }
+}
+static void o_passive(const OModel *m, OData *d) {
+  zero(d->qfrc_passive, m->nv);
+  for (int j = 0; j < m->njnt; j++) if (m->jnt_stiffness[j] != 0 && (m->jnt_type[j] == JNT_HINGE || m->jnt_type[j] == JNT_SLIDE))
+    d->qfrc_passive[m->jnt_dofadr[j]] = -m->jnt_stiffness[j] * (d->qpos[m->jnt_qposadr[j]] - m->qpos_spring[m->jnt_qposadr[j]]);
+  for (int i = 0; i < m->nv; i++) d->qfrc_passive[i] -= m->dof_damping[i] * d->qvel[i];
+}
+static void o_rne_bias(const OModel *m, OData *d) {
+  static double cacc[MAXB][6], cfrc[MAXB][6];
+  zero(cacc[0], 3); for (int k = 0; k < 3; k++) cacc[0][3 + k] = -m->gravity[k];
+  zero(cfrc[0], 6);
+  for (int i = 1; i < m->nbody; i++) {
+    int bda = m->body_dofadr[i]; double t[6], t1[6];
+    copyv(cacc[i], cacc[m->body_parentid[i]], 6);
+    for (int j = 0; j < m->body_dofnum[i]; j++) for (int c = 0; c < 6; c++) cacc[i][c] += d->cdof_dot[bda + j][c] * d->qvel[bda + j];
+    mulInertVec(cfrc[i], d->cinert[i], cacc[i]); mulInertVec(t, d->cinert[i], d->cvel[i]); crossForce(t1, d->cvel[i], t);
+    for (int c = 0; c < 6; c++) cfrc[i][c] += t1[c];
+  }
+  for (int i = m->nbody - 1; i > 0; i--) if (m->body_parentid[i]) for (int c = 0; c < 6; c++) cfrc[m->body_parentid[i]][c] += cfrc[i][c];
+  for (int i = 0; i < m->nv; i++) d->qfrc_bias[i] = dotn(d->cdof[i], cfrc[m->dof_bodyid[i]], 6);
+}
+
+/* ---------------- acceleration stage */
+static void o_fwdActuation(const OModel *m, OData *d) {
+  zero(d->qfrc_actuator, m->nv);
+  for (int i = 0; i < m->nu; i++) {
+    double c = d->ctrl[i];
+    if (m->actuator_ctrllimited[i]) c = clampd(c, m->actuator_ctrlrange[i][0], m->actuator_ctrlrange[i][1]);
+    d->actuator_force[i] = c;
+    d->qfrc_actuator[m->jnt_dofadr[m->actuator_jntid[i]]] += m->actuator_gear[i] * c;
+  }
+}
+static void o_fwdAcceleration(const OModel *m, OData *d) {
+  int nv = m->nv; double jp[3 * MAXV], jr[3 * MAXV];
+  for (int i = 0; i < nv; i++) d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_applied[i] + d->qfrc_actuator[i];
+  for (int b = 1; b < m->nbody; b++) {
+    const double *x = d->xfrc_applied[b]; int nz = 0; for (int k = 0; k < 6; k++) if (x[k] != 0) nz = 1;
+    if (!nz) continue;
+    o_jac(m, d, jp, jr, d->xipos[b], b);
+    for (int i = 0; i < nv; i++) for (int k = 0; k < 3; k++) d->qfrc_smooth[i] += jp[k * nv + i] * x[k] + jr[k * nv + i] * x[3 + k];
+  }
+  copyv(d->qacc_smooth, d->qfrc_smooth, nv); solveLD(m, d->qacc_smooth, d->qLD, d->qLDiagInv);
+}
+static void mulJacVec(const OModel *m, const OData *d, double *res, const double *v) { for (int i = 0; i < d->nefc; i++) res[i] = dotn(d->efc_J[i], v, m->nv); }
+static int is_ineq(int t) { return t == C_LIMIT || t == C_FRICTIONLESS || t == C_PYRAMIDAL; }
+static void o_fwdConstraint(const OModel *m, OData *d) {
+  int nv = m->nv, n = d->nefc; d->solver_iter = 0;
+  if (!n) { copyv(d->qacc, d->qacc_smooth, nv); zero(d->qfrc_constraint, nv); return; }
+  /* reference acceleration and b */
+  mulJacVec(m, d, d->efc_vel, d->qvel);
+  for (int i = 0; i < n; i++) d->efc_aref[i] = -d->efc_KBIP[i][1] * d->efc_vel[i] - d->efc_KBIP[i][0] * d->efc_KBIP[i][2] * (d->efc_pos[i] - d->efc_margin[i]);
+  mulJacVec(m, d, d->efc_b, d->qacc_smooth);
+  for (int i = 0; i < n; i++) d->efc_b[i] -= d->efc_aref[i];
+  /* warm start: forces implied by qacc_warmstart, kept only if their dual cost is negative */
+  double *f = d->efc_force, *AR = d->efc_AR; static double jar[MAXEFC];
+  mulJacVec(m, d, jar, d->qacc_warmstart);
+  for (int i = 0; i < n; i++) { jar[i] -= d->efc_aref[i]; f[i] = -d->efc_D[i] * jar[i]; if (is_ineq(d->efc_type[i]) && jar[i] >= 0) f[i] = 0; }
+  double cost = dotn(f, d->efc_b, n);
+  for (int i = 0; i < n; i++) cost += 0.5 * f[i] * dotn(AR + i * n, f, n);
+  if (cost > 0) zero(f, n);
+  /* PGS */
+  double scale = 1 / (m->meaninertia * (nv > 1 ? nv : 1));
+  int iter = 0;
+  while (iter < m->iterations) {
+    double improvement = 0;
+    for (int i = 0; i < n; i++) {
+      double res = d->efc_b[i] + dotn(AR + i * n, f, n), old = f[i];
+      f[i] -= res / AR[i * n + i];
+      if (is_ineq(d->efc_type[i]) && f[i] < 0) f[i] = 0;
+      double delta = f[i] - old, change = 0.5 * delta * delta * AR[i * n + i] + delta * res;
+      if (change > 1e-10) { f[i] = old; change = 0; }
+      improvement -= change;
+    }
+    improvement *= scale; iter++;
+    if (improvement < m->tolerance) break;
+  }
+  d->solver_iter = iter;
+  for (int j = 0; j < nv; j++) { double s = 0; for (int i = 0; i < n; i++) s += d->efc_J[i][j] * f[i]; d->qfrc_constraint[j] = s; }
+  copyv(d->qacc, d->qfrc_constraint, nv); solveLD(m, d->qacc, d->qLD, d->qLDiagInv);
+  for (int j = 0; j < nv; j++) d->qacc[j] += d->qacc_smooth[j];
+}
+static void o_cacc(const OModel *m, OData *d) { /* the part of mj_rnePostConstraint the accelerometer needs */
+  zero(d->cacc[0], 3); for (int k = 0; k < 3; k++) d->cacc[0][3 + k] = -m->gravity[k];
+  for (int i = 1; i < m->nbody; i++) {
+    int bda = m->body_dofadr[i]; copyv(d->cacc[i], d->cacc[m->body_parentid[i]], 6);
+    for (int j = 0; j < m->body_dofnum[i]; j++) for (int c = 0; c < 6; c++) d->cacc[i][c] += d->cdof_dot[bda + j][c] * d->qvel[bda + j] + d->cdof[bda + j][c] * d->qacc[bda + j];
+  }
+}
+static void quatIntegrate(double *q, const double *w, double h) {
+  double ax[3] = {w[0], w[1], w[2]}, ang = h * normalize3(ax), qr[4];
+  axisAngle2Quat(qr, ax, ang); normalize4(q); mulQuat(q, q, qr);
+}
+static void o_euler(const OModel *m, OData *d) {
+  int nv = m->nv; static double MhB[MAXNM], dinv[MAXV], qacc[MAXV];
+  copyv(MhB, d->qM, m->nM);
+  for (int i = 0; i < nv; i++) MhB[m->dof_Madr[i]] += m->timestep * m->dof_damping[i];
+  factorI(m, MhB, dinv, NULL);
+  for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+  solveLD(m, qacc, MhB, dinv);
+  for (int i = 0; i < nv; i++) d->qvel[i] += m->timestep * qacc[i];
+  for (int j = 0; j < m->njnt; j++) {
+    int qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+    switch (m->jnt_type[j]) {
+      case JNT_FREE: for (int k = 0; k < 3; k++) d->qpos[qa + k] += m->timestep * d->qvel[da + k]; quatIntegrate(d->qpos + qa + 3, d->qvel + da + 3, m->timestep); break;
+      case JNT_BALL: quatIntegrate(d->qpos + qa, d->qvel + da, m->timestep); break;
+      default: d->qpos[qa] += m->timestep * d->qvel[da];
+    }
+  }
+  d->time += m->timestep;
+  copyv(d->qacc_warmstart, d->qacc, nv);
+}
+
+void o_forward(const OModel *m, OData *d) {
+  o_kinematics(m, d); o_comPos(m, d); o_crb(m, d);
+  copyv(d->qLD, d->qM, m->nM); factorI(m, d->qLD, d->qLDiagInv, d->qLDiagSqrtInv);
+  o_collision(m, d); o_makeConstraint(m, d); o_projectConstraint(m, d);
+  for (int i = 0; i < m->nu; i++) { int j = m->actuator_jntid[i]; d->actuator_length[i] = m->actuator_gear[i] * d->qpos[m->jnt_qposadr[j]]; }
+  o_sensor(m, d, 0);
+  for (int i = 0; i < m->nu; i++) d->actuator_velocity[i] = m->actuator_gear[i] * d->qvel[m->jnt_dofadr[m->actuator_jntid[i]]];
+  o_comVel(m, d); o_passive(m, d); o_rne_bias(m, d);
+  o_sensor(m, d, 1);
+  o_fwdActuation(m, d); o_fwdAcceleration(m, d); o_fwdConstraint(m, d);
+  o_cacc(m, d); o_sensor(m, d, 2);
+}
+void o_step(const OModel *m, OData *d) { o_forward(m, d); o_euler(m, d); }
+
+/* ================================================================== Cassie glue (src/cassiemujoco.c) */
+#define NUM_DRIVES 10
+#define NUM_JOINTS 6
+#define DELAY 6
+static const int drive_b[9] = {2727, 534, -2658, -795, 72, 110, 19, -6, -3};       /* :198-200 */
+static const double joint_b[4] = {12.348, 12.348, -12.348, -12.348};                /* :202-204 */
+static const double joint_a[3] = {1.0, -1.7658, 0.79045};                           /* :206-208 */
+
+#ifdef ORACLE_USE_AGILITY_REF
+typedef struct CassieCoreSim cassie_core_sim_t; typedef struct StateOutput state_output_t; typedef struct PdInput pd_input_t;
+cassie_core_sim_t *cassie_core_sim_alloc(void); void cassie_core_sim_setup(cassie_core_sim_t *); void cassie_core_sim_free(cassie_core_sim_t *);
+void cassie_core_sim_step(cassie_core_sim_t *, const cassie_user_in_t *, const cassie_out_t *, cassie_in_t *);
+state_output_t *state_output_alloc(void); void state_output_setup(state_output_t *); void state_output_free(state_output_t *);
+void state_output_step(state_output_t *, const cassie_out_t *, state_out_t *);
+pd_input_t *pd_input_alloc(void); void pd_input_setup(pd_input_t *); void pd_input_free(pd_input_t *);
+void pd_input_step(pd_input_t *, const pd_in_t *, const cassie_out_t *, cassie_user_in_t *);
+#endif
+
+typedef struct {
+  OModel *m; OData *d;
+  cassie_out_t cassie_out;
+  int drive_filter[NUM_DRIVES][9];
+  double joint_filter_x[NUM_JOINTS][4], joint_filter_y[NUM_JOINTS][3];
+  double torque_delay[NUM_DRIVES][DELAY];
+#ifdef ORACLE_USE_AGILITY_REF
+  cassie_core_sim_t *core; state_output_t *est; pd_input_t *pd;
+#endif
+} OSim;
+
+static elmo_out_t *drive_ptr(cassie_out_t *o, int i) {
+  cassie_leg_out_t *leg = i < 5 ? &o->leftLeg : &o->rightLeg;
+  elmo_out_t *t[5] = {&leg->hipRollDrive, &leg->hipYawDrive, &leg->hipPitchDrive, &leg->kneeDrive, &leg->footDrive};
+  return t[i % 5];
+}
+static cassie_joint_out_t *joint_ptr(cassie_out_t *o, int i) {
+  cassie_leg_out_t *leg = i < 3 ? &o->leftLeg : &o->rightLeg;
+  cassie_joint_out_t *t[3] = {&leg->shinJoint, &leg->tarsusJoint, &leg->footJoint};
+  return t[i % 3];
+}
+static void cassie_out_init_(cassie_out_t *o) { /* :695-734 and :666-692 */
+  static const double tl[5] = {140.63, 140.63, 216.16, 216.16, 45.14}, gr[5] = {25, 25, 16, 16, 50};
+  memset(o, 0, sizeof *o);
+  o->isCalibrated = true;
+  o->pelvis.medullaCounter = 1; o->pelvis.medullaCpuLoad = 159; o->pelvis.vtmTemperature = 40;
+  o->pelvis.targetPc.etherCatStatus[1] = 8; o->pelvis.targetPc.etherCatStatus[4] = 1;
+  o->pelvis.targetPc.taskExecutionTime = 2e-4; o->pelvis.targetPc.cpuTemperature = 60;
+  o->pelvis.battery.dataGood = true; o->pelvis.battery.stateOfCharge = 1;
+  for (int i = 0; i < 4; i++) o->pelvis.battery.temperature[i] = 30;
+  for (int i = 0; i < 12; i++) o->pelvis.battery.voltage[i] = 4.2;
+  o->pelvis.radio.radioReceiverSignalGood = true; o->pelvis.radio.receiverMedullaSignalGood = true; o->pelvis.radio.channel[8] = 1;
+  o->pelvis.vectorNav.dataGood = true; o->pelvis.vectorNav.pressure = 101.325; o->pelvis.vectorNav.temperature = 25;
+  for (int l = 0; l < 2; l++) {
+    cassie_leg_out_t *leg = l ? &o->rightLeg : &o->leftLeg; leg->medullaCounter = 1; leg->medullaCpuLoad = 94;
+    for (int i = 0; i < 5; i++) { elmo_out_t *e = drive_ptr(o, 5 * l + i); e->statusWord = 0x0637; e->dcLinkVoltage = 48; e->driveTemperature = 30; e->torqueLimit = tl[i]; e->gearRatio = gr[i]; }
+  }
+}
+
+/* ---- Agility-block twins (closed source in the reference; semantics from SURVEY.md 8a-2 / 8a-3) */
+void o_pd_input_step(const pd_in_t *u, const cassie_out_t *o, double torque[10]) {
+  for (int i = 0; i < 10; i++) {
+    const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; int k = i % 5;
+    const elmo_out_t *e = drive_ptr((cassie_out_t *)o, i);
+    torque[i] = p->torque[k] + p->pGain[k] * (p->pTarget[k] - e->position) + p->dGain[k] * (p->dTarget[k] - e->velocity);
+  }
+}
+/* soft joint limits (rad), lower / upper, for hipRoll hipYaw hipPitch knee foot; left then right leg */
+static const double core_lo[10] = {-0.111799, -0.233972, -0.722665, -2.572714, -2.293461, -0.199066, -0.233972, -0.722665, -2.572714, -2.293461};
+static const double core_hi[10] = {0.199066, 0.233972, 1.246263, -0.883038, -0.760865, 0.111799, 0.233972, 1.246263, -0.883038, -0.760865};
+static const double core_K[5] = {800, 800, 1200, 1200, 100}, core_C[5] = {12, 12, 36, 36, 7};
+void o_core_sim_step(const double u[10], const cassie_out_t *o, double out[10]) {
+  double pos[10], vel[10], lim[10], add[10] = {0}, scale = 1.0; const double W = 0.15;
+  for (int i = 0; i < 10; i++) { const elmo_out_t *e = drive_ptr((cassie_out_t *)o, i); pos[i] = e->position; vel[i] = e->velocity; lim[i] = e->torqueLimit; }
+  for (int i = 0; i < 10; i++) {
+    int k = i % 5; double dhi = pos[i] - core_hi[i], dlo = core_lo[i] - pos[i];
+    if (dhi > 0) { add[i] += -(core_K[k] * dhi * (1 + dhi / W) + core_C[k] * (dhi / W) * vel[i]); scale *= fmax(0.0, 1 - dhi / W); }
+    if (dlo > 0) { add[i] += (core_K[k] * dlo * (1 + dlo / W) + core_C[k] * (dlo / W) * (-vel[i])); scale *= fmax(0.0, 1 - dlo / W); }
+  }
+  for (int l = 0; l < 2; l++) { /* coupled hipPitch + knee >= -3pi/4 */
+    double dsum = -2.356194 - (pos[5 * l + 2] + pos[5 * l + 3]);
+    if (dsum > 0) { double t = 1200 * dsum * (1 + dsum / W); add[5 * l + 2] += t; add[5 * l + 3] += t; scale *= fmax(0.0, 1 - dsum / W); }
+  }
+  int sto = !(o->pelvis.radio.channel[8] >= 1);
+  for (int i = 0; i < 10; i++) { double t = sto ? 0.0 : u[i] * scale + add[i]; out[i] = clampd(t, -lim[i], lim[i]); }
+}
+
+OSim *osim_new(const char *model_path) {
+  OSim *c = calloc(1, sizeof(OSim));
+  c->m = omodel_load(model_path); if (!c->m) { free(c); return NULL; }
+  c->d = calloc(1, sizeof(OData));
+  cassie_out_init_(&c->cassie_out);
+  copyv(c->d->qpos, c->m->qpos0, c->m->nq);
+  static const double qi[28] = {0.0045, 0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968,
+                                -0.0045, 0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968}; /* :1023-1027 */
+  copyv(c->d->qpos + 7, qi, 28);
+  o_forward(c->m, c->d); /* mj_forward at :1029 */
+#ifdef ORACLE_USE_AGILITY_REF
+  c->core = cassie_core_sim_alloc(); c->est = state_output_alloc(); c->pd = pd_input_alloc();
+  cassie_core_sim_setup(c->core); state_output_setup(c->est); pd_input_setup(c->pd);
+#endif
+  return c;
+}
+void osim_free(OSim *c) {
+  if (!c) return;
+#ifdef ORACLE_USE_AGILITY_REF
+  cassie_core_sim_free(c->core); state_output_free(c->est); pd_input_free(c->pd);
+#endif
+  free(c->d->efc_AR); free(c->d); omodel_free(c->m); free(c);
+}
+
+static double motor_(OSim *c, int i, double u, int sto) { /* :638-664 */
+  const OModel *m = c->m; OData *d = c->d;
+  double ratio = m->actuator_gear[i], tmax = m->actuator_ctrlrange[i][1], w = d->actuator_velocity[i], wmax = m->actuator_user[i] * 2 * M_PI / 60;
+  double tlim = 2 * tmax * (1 - fabs(w) / wmax); tlim = fmax(fmin(tlim, tmax), 0);
+  if (sto) u = 0;
+  double tau = copysign(fmin(fabs(u / ratio), tlim), u);
+  d->ctrl[i] = c->torque_delay[i][DELAY - 1];
+  for (int k = DELAY - 1; k > 0; k--) c->torque_delay[i][k] = c->torque_delay[i][k - 1];
+  c->torque_delay[i][0] = tau;
+  return d->ctrl[i] * ratio;
+}
+static void sensor_data_(OSim *c) { /* :737-774, 558-635 */
+  static const int dsid[10] = {0, 1, 2, 3, 4, 8, 9, 10, 11, 12}, jsid[6] = {5, 6, 7, 13, 14, 15};
+  const OModel *m = c->m; const double *sd = c->d->sensordata;
+  for (int i = 0; i < NUM_DRIVES; i++) {
+    elmo_out_t *dr = drive_ptr(&c->cassie_out, i); int s = dsid[i], bits = (int)m->sensor_user[s], *x = c->drive_filter[i];
+    int enc = (int)(sd[s] / (2 * M_PI) * (1 << bits));
+    double ratio = m->actuator_gear[m->sensor_objid[s]], scale = (2 * M_PI) / (1 << bits) / ratio;
+    dr->position = enc * scale;
+    int allzero = 1; for (int k = 0; k < 9; k++) allzero &= x[k] == 0;
+    if (allzero) for (int k = 0; k < 9; k++) x[k] = enc;
+    for (int k = 8; k > 0; k--) x[k] = x[k - 1];
+    x[0] = enc;
+    int y = 0; for (int k = 0; k < 9; k++) y += x[k] * drive_b[k];
+    dr->velocity = y * scale / M_PI;
+  }
+  for (int i = 0; i < NUM_JOINTS; i++) {
+    cassie_joint_out_t *jn = joint_ptr(&c->cassie_out, i); int s = jsid[i], bits = (int)m->sensor_user[s]; double *x = c->joint_filter_x[i], *y = c->joint_filter_y[i];
+    int enc = (int)(sd[s] / (2 * M_PI) * (1 << bits)); double scale = (2 * M_PI) / (1 << bits);
+    jn->position = enc * scale;
+    int allzero = 1; for (int k = 0; k < 4; k++) allzero &= x[k] == 0;
+    if (allzero) for (int k = 0; k < 4; k++) x[k] = jn->position;
+    for (int k = 3; k > 0; k--) x[k] = x[k - 1];
+    x[0] = jn->position;
+    for (int k = 2; k > 0; k--) y[k] = y[k - 1];
+    y[0] = 0;
+    for (int k = 0; k < 4; k++) y[0] += x[k] * joint_b[k];
+    for (int k = 1; k < 3; k++) y[0] -= y[k] * joint_a[k];
+    jn->velocity = y[0];
+  }
+  vectornav_out_t *vn = &c->cassie_out.pelvis.vectorNav;
+  copyv(vn->orientation, sd + 16, 4); copyv(vn->angularVelocity, sd + 20, 3); copyv(vn->linearAcceleration, sd + 23, 3); copyv(vn->magneticField, sd + 26, 3);
+}
+
+/* cassie_sim_step_pd, src/cassiemujoco.c:1147-1157 (with :1137-1145 and :1115-1135 inlined).
+ * y may be NULL.  cassie_out_copy (optional) receives the cassie_out_t the reference hands to the estimator. */
+void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassie_out_copy) {
+  double tq_user[10], tq_in[10];
+#ifdef ORACLE_USE_AGILITY_REF
+  cassie_user_in_t ui; cassie_in_t ci;
+  pd_input_step(c->pd, u, &c->cassie_out, &ui);
+  cassie_core_sim_step(c->core, &ui, &c->cassie_out, &ci);
+  for (int i = 0; i < 10; i++) { const cassie_leg_in_t *leg = i < 5 ? &ci.leftLeg : &ci.rightLeg; const elmo_in_t *t[5] = {&leg->hipRollDrive, &leg->hipYawDrive, &leg->hipPitchDrive, &leg->kneeDrive, &leg->footDrive}; tq_in[i] = t[i % 5]->torque; }
+  (void)tq_user;
+#else
+  o_pd_input_step(u, &c->cassie_out, tq_user);
+  o_core_sim_step(tq_user, &c->cassie_out, tq_in);
+#endif
+  int sto = c->cassie_out.pelvis.radio.channel[8] < 1;
+  for (int i = 0; i < NUM_DRIVES; i++) drive_ptr(&c->cassie_out, i)->torque = motor_(c, i, tq_in[i], sto);
+  sensor_data_(c);
+  cassie_out_t out = c->cassie_out;
+  if (cassie_out_copy) *cassie_out_copy = out;
+  int mjsteps = (int)round(5e-4 / c->m->timestep);
+  for (int i = 0; i < mjsteps; i++) o_step(c->m, c->d);
+  if (y) {
+#ifdef ORACLE_USE_AGILITY_REF
+    state_output_step(c->est, &out, y);
+#else
+    memset(y, 0, sizeof *y); /* pass-through subset only */
+    for (int i = 0; i < 10; i++) { elmo_out_t *e = drive_ptr(&out, i); y->motor.position[i] = e->position; y->motor.velocity[i] = e->velocity; y->motor.torque[i] = e->torque; }
+    for (int i = 0; i < 6; i++) { cassie_joint_out_t *j = joint_ptr(&out, i); y->joint.position[i] = j->position; y->joint.velocity[i] = j->velocity; }
+    copyv(y->pelvis.orientation, out.pelvis.vectorNav.orientation, 4); copyv(y->pelvis.rotationalVelocity, out.pelvis.vectorNav.angularVelocity, 3);
+    copyv(y->radio.channel, out.pelvis.radio.channel, 16); y->radio.signalGood = true; y->battery.stateOfCharge = out.pelvis.battery.stateOfCharge;
+#endif
+  }
+}
+
+/* ---------------- accessors for the test harness (ctypes) */
+OModel *osim_model(OSim *c) { return c->m; }
+OData *osim_data(OSim *c) { return c->d; }
+cassie_out_t *osim_cassie_out(OSim *c) { return &c->cassie_out; }
+int *osim_drive_filter(OSim *c) { return &c->drive_filter[0][0]; }
+double *osim_joint_filter_x(OSim *c) { return &c->joint_filter_x[0][0]; }
+double *osim_joint_filter_y(OSim *c) { return &c->joint_filter_y[0][0]; }
+double *osim_torque_delay(OSim *c) { return &c->torque_delay[0][0]; }
+float *osim_hfield_data(OSim *c) { return c->m->hfield_data; }
+void osim_forward(OSim *c) { o_forward(c->m, c->d); }
+void osim_mj_step(OSim *c) { o_step(c->m, c->d); }
+#define ARR(name, ptr, cnt) if (!strcmp(key, name)) { *n = (cnt); return (double *)(ptr); }
+double *osim_array(OSim *c, const char *key, int *n) {
+  OData *d = c->d; OModel *m = c->m; int nv = m->nv, nb = m->nbody;
+  ARR("qpos", d->qpos, m->nq) ARR("qvel", d->qvel, nv) ARR("qacc", d->qacc, nv) ARR("qacc_warmstart", d->qacc_warmstart, nv)
+  ARR("ctrl", d->ctrl, m->nu) ARR("xfrc_applied", d->xfrc_applied, 6 * nb) ARR("qfrc_applied", d->qfrc_applied, nv) ARR("time", &d->time, 1)
+  ARR("xpos", d->xpos, 3 * nb) ARR("xquat", d->xquat, 4 * nb) ARR("xmat", d->xmat, 9 * nb) ARR("xipos", d->xipos, 3 * nb)
+  ARR("ximat", d->ximat, 9 * nb) ARR("xanchor", d->xanchor, 3 * m->njnt) ARR("xaxis", d->xaxis, 3 * m->njnt)
+  ARR("geom_xpos", d->geom_xpos, 3 * m->ngeom) ARR("geom_xmat", d->geom_xmat, 9 * m->ngeom) ARR("subtree_com", d->subtree_com, 3 * nb)
+  ARR("cdof", d->cdof, 6 * nv) ARR("cinert", d->cinert, 10 * nb) ARR("crb", d->crb, 10 * nb) ARR("qM", d->qM, m->nM) ARR("qLD", d->qLD, m->nM)
+  ARR("qLDiagInv", d->qLDiagInv, nv) ARR("cvel", d->cvel, 6 * nb) ARR("cdof_dot", d->cdof_dot, 6 * nv) ARR("qfrc_bias", d->qfrc_bias, nv)
+  ARR("qfrc_passive", d->qfrc_passive, nv) ARR("qfrc_actuator", d->qfrc_actuator, nv) ARR("qfrc_smooth", d->qfrc_smooth, nv)
+  ARR("qacc_smooth", d->qacc_smooth, nv) ARR("qfrc_constraint", d->qfrc_constraint, nv) ARR("actuator_velocity", d->actuator_velocity, m->nu)
+  ARR("sensordata", d->sensordata, 29) ARR("efc_pos", d->efc_pos, d->nefc) ARR("efc_R", d->efc_R, d->nefc) ARR("efc_D", d->efc_D, d->nefc)
+  ARR("efc_aref", d->efc_aref, d->nefc) ARR("efc_b", d->efc_b, d->nefc) ARR("efc_force", d->efc_force, d->nefc) ARR("efc_vel", d->efc_vel, d->nefc)
+  ARR("efc_diagApprox", d->efc_diagApprox, d->nefc) ARR("efc_J", d->efc_J, d->nefc * MAXV) ARR("efc_AR", d->efc_AR, d->nefc * d->nefc)
+  ARR("cacc", d->cacc, 6 * nb)
+  *n = 0; return NULL;
+}
+int osim_int(OSim *c, const char *key) {
+  OData *d = c->d;
+  if (!strcmp(key, "nefc")) return d->nefc; if (!strcmp(key, "ncon")) return d->ncon; if (!strcmp(key, "ne")) return d->ne; if (!strcmp(key, "nl")) return d->nl;
+  if (!strcmp(key, "solver_iter")) return d->solver_iter; if (!strcmp(key, "unsupported_pairs")) return d->unsupported_pairs;
+  if (!strcmp(key, "dropped_contacts")) return d->dropped_contacts; if (!strcmp(key, "MAXV")) return MAXV;
+  if (!strcmp(key, "nq")) return c->m->nq; if (!strcmp(key, "nv")) return c->m->nv; if (!strcmp(key, "nbody")) return c->m->nbody;
+  return -1;
+}
+int osim_contact(OSim *c, int i, double *out /* pos3 frame9 dist */, int *geoms) {
+  if (i >= c->d->ncon) return 0; OContact *k = &c->d->contact[i];
+  copyv(out, k->pos, 3); copyv(out + 3, k->frame, 9); out[12] = k->dist; geoms[0] = k->geom1; geoms[1] = k->geom2; geoms[2] = k->dim; return 1;
+}
+/* CPU-baseline helper: run `ticks` step_pd ticks on `nsim` private sims in this thread, return 0 */
+int osim_run(OSim **sims, int nsim, const pd_in_t *u, int ticks) { for (int t = 0; t < ticks; t++) for (int i = 0; i < nsim; i++) osim_step_pd(sims[i], u, NULL, NULL); return 0; }
