@@ -870,21 +870,27 @@ void o_pd_input_step(const pd_in_t *u, const cassie_out_t *o, double torque[10])
     torque[i] = p->torque[k] + p->pGain[k] * (p->pTarget[k] - e->position) + p->dGain[k] * (p->dTarget[k] - e->velocity);
   }
 }
-/* soft joint limits (rad), lower / upper, for hipRoll hipYaw hipPitch knee foot; left then right leg */
-static const double core_lo[10] = {-0.111799, -0.233972, -0.722665, -2.572714, -2.293461, -0.199066, -0.233972, -0.722665, -2.572714, -2.293461};
-static const double core_hi[10] = {0.199066, 0.233972, 1.246263, -0.883038, -0.760865, 0.111799, 0.233972, 1.246263, -0.883038, -0.760865};
-static const double core_K[5] = {800, 800, 1200, 1200, 100}, core_C[5] = {12, 12, 36, 36, 7};
+/* soft joint limits = hard limits shrunk by W = 0.15 rad; order hipRoll hipYaw hipPitch knee foot, left leg then right.
+ * Values recovered by bisection on the archive (tests/golden/make_golden.py documents the probe): hard limits in degrees are
+ * hipRoll [-15, 20] (mirrored on the right), hipYaw +-22, hipPitch [-50, 80], knee [-156, -42], foot [-140, -35]. */
+#define DEG (M_PI / 180.0)
+static const double core_lo_deg[10] = {-15, -22, -50, -156, -140, -20, -22, -50, -156, -140};
+static const double core_hi_deg[10] = {20, 22, 80, -42, -35, 15, 22, 80, -42, -35};
+static const double core_K[5] = {1000, 800, 1200, 1200, 100}, core_C[5] = {12, 12, 36, 36, 7};
 void o_core_sim_step(const double u[10], const cassie_out_t *o, double out[10]) {
   double pos[10], vel[10], lim[10], add[10] = {0}, scale = 1.0; const double W = 0.15;
   for (int i = 0; i < 10; i++) { const elmo_out_t *e = drive_ptr((cassie_out_t *)o, i); pos[i] = e->position; vel[i] = e->velocity; lim[i] = e->torqueLimit; }
   for (int i = 0; i < 10; i++) {
-    int k = i % 5; double dhi = pos[i] - core_hi[i], dlo = core_lo[i] - pos[i];
-    if (dhi > 0) { add[i] += -(core_K[k] * dhi * (1 + dhi / W) + core_C[k] * (dhi / W) * vel[i]); scale *= fmax(0.0, 1 - dhi / W); }
-    if (dlo > 0) { add[i] += (core_K[k] * dlo * (1 + dlo / W) + core_C[k] * (dlo / W) * (-vel[i])); scale *= fmax(0.0, 1 - dlo / W); }
+    int k = i % 5; double dhi = pos[i] - (core_hi_deg[i] * DEG - W), dlo = (core_lo_deg[i] * DEG + W) - pos[i];
+    if (dhi > 0) { add[i] -= core_K[k] * dhi * (1 + dhi / W) + core_C[k] * fmin(dhi / W, 1.0) * vel[i]; scale *= fmax(0.0, 1 - dhi / W); }
+    if (dlo > 0) { add[i] += core_K[k] * dlo * (1 + dlo / W) - core_C[k] * fmin(dlo / W, 1.0) * vel[i]; scale *= fmax(0.0, 1 - dlo / W); }
   }
-  for (int l = 0; l < 2; l++) { /* coupled hipPitch + knee >= -3pi/4 */
-    double dsum = -2.356194 - (pos[5 * l + 2] + pos[5 * l + 3]);
-    if (dsum > 0) { double t = 1200 * dsum * (1 + dsum / W); add[5 * l + 2] += t; add[5 * l + 3] += t; scale *= fmax(0.0, 1 - dsum / W); }
+  for (int l = 0; l < 2; l++) { /* coupled row: hipPitch + knee >= -135 deg; each joint damped by its own velocity */
+    int a = 5 * l + 2, b = 5 * l + 3; double dsum = -135 * DEG - (pos[a] + pos[b]);
+    if (dsum > 0) {
+      double t = 1200 * dsum * (1 + dsum / W);
+      double r = fmin(dsum / W, 1.0); add[a] += t - 36 * r * vel[a]; add[b] += t - 36 * r * vel[b]; scale *= fmax(0.0, 1 - dsum / W);
+    }
   }
   int sto = !(o->pelvis.radio.channel[8] >= 1);
   for (int i = 0; i < 10; i++) { double t = sto ? 0.0 : u[i] * scale + add[i]; out[i] = clampd(t, -lim[i], lim[i]); }
