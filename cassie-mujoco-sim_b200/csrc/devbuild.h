@@ -1,0 +1,175 @@
+// devbuild.h -- host code that turns a HostModel into the DevModel<real> constant block, and the initial per-env state rows.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include "devmodel.h"
+#include "model.h"
+
+namespace cassie {
+
+namespace detail {
+inline void q2m_d(double *m, const double *q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+}  // namespace detail
+
+struct BuildInfo { int unsupported_pairs = 0; int collision_geoms = 0; };
+
+template <typename real>
+bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, BuildInfo *info = nullptr) {
+  std::memset(&d, 0, sizeof d);
+  if (m.nv > MV || m.nbody > MB || m.njnt > MJ || m.nM > NM_MAX || m.neq > ME || m.nu != MU) { err = "model exceeds the one-warp-per-env limits (nv<=32, nbody<=32, neq<=4, nu==10)"; return false; }
+  for (int j = 0; j < m.njnt; j++) if (m.jnt_type[j] == JNT_FREE) { err = "free joints are not supported by the batched stepper yet"; return false; }
+  for (int b = 1; b < m.nbody; b++) if (m.body_rootid[b] != 1) { err = "a single kinematic tree rooted at body 1 is required"; return false; }
+  d.nq = m.nq; d.nv = m.nv; d.nbody = m.nbody; d.njnt = m.njnt; d.neq = m.neq; d.nu = m.nu; d.nM = m.nM; d.iterations = m.iterations;
+  d.timestep = (real)m.timestep; d.tolerance = (real)m.tolerance; d.pgs_scale = (real)(1.0 / (m.meaninertia * std::max(1, m.nv)));
+  d.nsub = (int)std::lround(5e-4 / m.timestep); if (d.nsub < 1) d.nsub = 1;
+  double mass = 0; for (int b = 1; b < m.nbody; b++) mass += m.body_mass[b];
+  d.root_mass_inv = (real)(1.0 / mass);
+  for (int k = 0; k < 3; k++) { d.gravity[k] = (real)m.gravity[k]; d.magnetic[k] = (real)m.magnetic[k]; }
+  // bodies
+  for (int b = 0; b < m.nbody; b++) {
+    d.body_parent[b] = m.body_parentid[b]; d.body_depth[b] = b ? d.body_depth[m.body_parentid[b]] + 1 : 0;
+    if (d.body_depth[b] > d.maxdepth) d.maxdepth = d.body_depth[b];
+    d.body_jntadr[b] = m.body_jntadr[b]; d.body_jntnum[b] = m.body_jntnum[b];
+    int p = b; while (p > 0 && m.body_dofnum[p] == 0) p = m.body_parentid[p];
+    d.body_lastdof[b] = p > 0 ? m.body_dofadr[p] + m.body_dofnum[p] - 1 : -1;
+    uint32_t mask = 0; for (int k = d.body_lastdof[b]; k >= 0; k = m.dof_parentid[k]) mask |= 1u << k;
+    d.body_dofmask[b] = mask;
+    int end = b + 1; while (end < m.nbody) { int a = end; while (a > b) a = m.body_parentid[a]; if (a != b) break; end++; }
+    d.body_subtree_end[b] = b == 0 ? m.nbody : end;
+    double R[9]; detail::q2m_d(R, &m.body_iquat[4 * b]);
+    for (int k = 0; k < 3; k++) { d.body_pos[b][k] = (real)m.body_pos[3 * b + k]; d.body_ipos[b][k] = (real)m.body_ipos[3 * b + k]; d.body_inertia[b][k] = (real)m.body_inertia[3 * b + k]; }
+    for (int k = 0; k < 4; k++) d.body_quat[b][k] = (real)m.body_quat[4 * b + k];
+    for (int k = 0; k < 9; k++) d.body_imat[b][k] = (real)R[k];
+    d.body_mass[b] = (real)m.body_mass[b]; d.body_invw[b] = (real)m.body_invweight0[2 * b];
+  }
+  // joints
+  for (int j = 0; j < m.njnt; j++) {
+    d.jnt_type[j] = m.jnt_type[j]; d.jnt_qposadr[j] = m.jnt_qposadr[j]; d.jnt_dofadr[j] = m.jnt_dofadr[j]; d.jnt_body[j] = m.jnt_bodyid[j];
+    d.jnt_limited[j] = (m.jnt_limited[j] && (m.jnt_type[j] == JNT_HINGE || m.jnt_type[j] == JNT_SLIDE)) ? 1 : 0;
+    for (int k = 0; k < 3; k++) { d.jnt_pos[j][k] = (real)m.jnt_pos[3 * j + k]; d.jnt_axis[j][k] = (real)m.jnt_axis[3 * j + k]; }
+    d.jnt_stiffness[j] = (real)m.jnt_stiffness[j]; d.jnt_range[j][0] = (real)m.jnt_range[2 * j]; d.jnt_range[j][1] = (real)m.jnt_range[2 * j + 1];
+    d.jnt_qpos0[j] = (real)m.qpos0[m.jnt_qposadr[j]]; d.jnt_qspring[j] = (real)m.qpos_spring[m.jnt_qposadr[j]];
+    for (int k = 0; k < 2; k++) d.jnt_solref[j][k] = (real)m.jnt_solref[2 * j + k];
+    for (int k = 0; k < 5; k++) d.jnt_solimp[j][k] = (real)m.jnt_solimp[5 * j + k];
+    if (m.jnt_margin[j] != 0) { err = "joint margins are not supported"; return false; }
+  }
+  // dofs
+  d.ntri = 0;
+  for (int i = 0; i < m.nv; i++) {
+    d.dof_body[i] = m.dof_bodyid[i]; d.dof_jnt[i] = m.dof_jntid[i]; d.dof_parent[i] = m.dof_parentid[i]; d.dof_Madr[i] = m.dof_Madr[i];
+    d.dof_armature[i] = (real)m.dof_armature[i]; d.dof_damping[i] = (real)m.dof_damping[i]; d.dof_invweight0[i] = (real)m.dof_invweight0[i];
+    uint32_t mask = 0; int depth = 0; for (int k = m.dof_parentid[i]; k >= 0; k = m.dof_parentid[k]) { mask |= 1u << k; depth++; }
+    d.dof_ancmask[i] = mask; d.dof_depth[i] = depth;
+    int j = m.dof_jntid[i];
+    d.dof_cvelsrc[i] = (m.jnt_type[j] == JNT_BALL) ? m.dof_parentid[m.jnt_dofadr[j]] : m.dof_parentid[i];
+  }
+  for (int i = m.nv - 1; i >= 0; i--) { int a = m.dof_Madr[i] + 1; for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) { if (d.ntri >= NTRI_MAX) { err = "too many factor entries"; return false; } d.tri[d.ntri++] = ((uint32_t)i << 24) | ((uint32_t)j << 16) | (uint32_t)a; a++; } }
+  // IMU site and its sensors
+  int imu = m.site_id("imu");
+  if (imu < 0) { err = "site 'imu' not found"; return false; }
+  d.imu_body = m.site_bodyid[imu];
+  double Rs[9]; detail::q2m_d(Rs, &m.site_quat[4 * imu]);
+  for (int k = 0; k < 3; k++) d.imu_pos[k] = (real)m.site_pos[3 * imu + k];
+  for (int k = 0; k < 4; k++) d.imu_quat[k] = (real)m.site_quat[4 * imu + k];
+  for (int k = 0; k < 9; k++) d.imu_mat[k] = (real)Rs[k];
+  // sensor layout must be the Cassie one: 16 encoders, framequat, gyro, accelerometer, magnetometer (model/cassie.xml:272-292)
+  if (m.nsensor < 20) { err = "unexpected sensor layout"; return false; }
+  for (int s = 0; s < 16; s++) {
+    if (m.sensor_type[s] == SENS_ACTUATORPOS) { int a = m.sensor_objid[s], j = m.actuator_jntid[a]; d.enc_qposadr[s] = m.jnt_qposadr[j]; d.enc_scale[s] = (real)m.actuator_gear[a]; }
+    else if (m.sensor_type[s] == SENS_JOINTPOS) { d.enc_qposadr[s] = m.jnt_qposadr[m.sensor_objid[s]]; d.enc_scale[s] = 1; }
+    else { err = "unexpected sensor layout"; return false; }
+    d.enc_bits[s] = (int)m.sensor_user[s];
+  }
+  if (m.sensor_type[16] != SENS_FRAMEQUAT || m.sensor_type[17] != SENS_GYRO || m.sensor_type[18] != SENS_ACCEL || m.sensor_type[19] != SENS_MAG) { err = "unexpected sensor layout"; return false; }
+  d.gyro_cutoff = (real)m.sensor_cutoff[17]; d.accel_cutoff = (real)m.sensor_cutoff[18];
+  // motors
+  static const double torque_limit[5] = {140.63, 140.63, 216.16, 216.16, 45.14};  // elmo torqueLimit, src/cassiemujoco.c:687-691
+  for (int i = 0; i < m.nu; i++) {
+    int j = m.actuator_jntid[i];
+    d.act_dof[i] = m.jnt_dofadr[j]; d.act_qposadr[i] = m.jnt_qposadr[j]; d.act_gear[i] = (real)m.actuator_gear[i];
+    bool lim = m.actuator_ctrllimited[i] != 0;
+    d.act_ctrl_lo[i] = lim ? (real)m.actuator_ctrlrange[2 * i] : -std::numeric_limits<real>::max();
+    d.act_ctrl_hi[i] = lim ? (real)m.actuator_ctrlrange[2 * i + 1] : std::numeric_limits<real>::max();
+    d.act_wmax[i] = (real)(m.actuator_user[i] * 2 * M_PI / 60); d.act_torque_limit[i] = (real)torque_limit[i % 5];
+  }
+  // equality
+  for (int e = 0; e < m.neq; e++) {
+    d.eq_b1[e] = m.eq_obj1id[e]; d.eq_b2[e] = m.eq_obj2id[e];
+    for (int k = 0; k < 6; k++) d.eq_data[e][k] = (real)m.eq_data[6 * e + k];
+    for (int k = 0; k < 2; k++) d.eq_solref[e][k] = (real)m.eq_solref[2 * e + k];
+    for (int k = 0; k < 5; k++) d.eq_solimp[e][k] = (real)m.eq_solimp[5 * e + k];
+  }
+  // candidate pairs in MuJoCo's order: body pairs ascending, geoms in id order; then type-sorted
+  int gmap[256]; for (int g = 0; g < 256; g++) gmap[g] = -1;
+  auto dev_geom = [&](int g) -> int {
+    if (gmap[g] >= 0) return gmap[g];
+    if (d.ngeom >= MG) return -1;
+    int k = d.ngeom++; gmap[g] = k; d.geom_body[k] = m.geom_bodyid[g]; d.geom_type[k] = m.geom_type[g];
+    double R[9]; detail::q2m_d(R, &m.geom_quat[4 * g]);
+    for (int c = 0; c < 3; c++) { d.geom_pos[k][c] = (real)m.geom_pos[3 * g + c]; d.geom_zaxis[k][c] = (real)R[3 * c + 2]; }
+    d.geom_size[k][0] = (real)m.geom_size[3 * g]; d.geom_size[k][1] = (real)m.geom_size[3 * g + 1];
+    return k;
+  };
+  int unsupported = 0;
+  for (int b1 = 0; b1 < m.nbody; b1++) for (int b2 = b1 + 1; b2 < m.nbody; b2++) {
+    int w1 = m.body_weldid[b1], w2 = m.body_weldid[b2];
+    if (w1 == w2) continue;
+    if (w1 && w2 && (m.body_weldid[m.body_parentid[w1]] == w2 || m.body_weldid[m.body_parentid[w2]] == w1)) continue;
+    for (int ga = 0; ga < m.ngeom; ga++) if (m.geom_bodyid[ga] == b1) for (int gb = 0; gb < m.ngeom; gb++) if (m.geom_bodyid[gb] == b2) {
+      int g1 = ga, g2 = gb; if (m.geom_type[g1] > m.geom_type[g2]) std::swap(g1, g2);
+      if (!((m.geom_contype[g1] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g1]))) continue;
+      int t1 = m.geom_type[g1], t2 = m.geom_type[g2], kind;
+      if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) kind = PAIR_PLANE_SPHERE;
+      else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) kind = PAIR_PLANE_CAPSULE;
+      else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) kind = PAIR_CAPSULE_CAPSULE;
+      else { unsupported++; continue; }
+      if (d.npair >= MP) { err = "too many candidate geom pairs"; return false; }
+      int k1 = dev_geom(g1), k2 = dev_geom(g2); if (k1 < 0 || k2 < 0) { err = "too many collision geoms"; return false; }
+      int p = d.npair++; d.pair_g1[p] = k1; d.pair_g2[p] = k2; d.pair_kind[p] = kind;
+      // contact parameter mixing (mj_contactParam)
+      double fr, solref[2], solimp[5]; int dim;
+      if (m.geom_priority[g1] != m.geom_priority[g2]) {
+        int g = m.geom_priority[g1] > m.geom_priority[g2] ? g1 : g2; dim = m.geom_condim[g]; fr = m.geom_friction[3 * g];
+        for (int k = 0; k < 2; k++) solref[k] = m.geom_solref[2 * g + k]; for (int k = 0; k < 5; k++) solimp[k] = m.geom_solimp[5 * g + k];
+      } else {
+        dim = std::max(m.geom_condim[g1], m.geom_condim[g2]); fr = std::max(m.geom_friction[3 * g1], m.geom_friction[3 * g2]);
+        double s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2], mix;
+        if (s1 >= 1e-15 && s2 >= 1e-15) mix = s1 / (s1 + s2); else if (s1 < 1e-15 && s2 < 1e-15) mix = 0.5; else mix = s1 < 1e-15 ? 0.0 : 1.0;
+        if (m.geom_solref[2 * g1] > 0 && m.geom_solref[2 * g2] > 0) for (int k = 0; k < 2; k++) solref[k] = mix * m.geom_solref[2 * g1 + k] + (1 - mix) * m.geom_solref[2 * g2 + k];
+        else for (int k = 0; k < 2; k++) solref[k] = std::min(m.geom_solref[2 * g1 + k], m.geom_solref[2 * g2 + k]);
+        for (int k = 0; k < 5; k++) solimp[k] = mix * m.geom_solimp[5 * g1 + k] + (1 - mix) * m.geom_solimp[5 * g2 + k];
+      }
+      if (dim != 1 && dim != 3) { err = "only condim 1 and 3 contacts are supported"; return false; }
+      d.pair_condim[p] = dim; d.pair_mu[p] = (real)(fr / std::sqrt(m.impratio));
+      d.pair_margin[p] = (real)std::max(m.geom_margin[g1], m.geom_margin[g2]); d.pair_gap[p] = (real)std::max(m.geom_gap[g1], m.geom_gap[g2]);
+      for (int k = 0; k < 2; k++) d.pair_solref[p][k] = (real)solref[k];
+      for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = (real)solimp[k];
+    }
+  }
+  if (info) { info->unsupported_pairs = unsupported; info->collision_geoms = d.ngeom; }
+  return true;
+}
+
+// initial per-env rows: what cassie_sim_init leaves behind before its mj_forward (src/cassiemujoco.c:989-1027)
+template <typename real>
+void init_env_rows(const HostModel &m, real *qpos, real *qvel, real *qacc_ws, real *cst, int *dfilt, real *xfrc) {
+  static const double qi[28] = {0.0045, 0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968,
+                                -0.0045, 0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968};
+  for (int i = 0; i < QPOS_W; i++) qpos[i] = 0;
+  for (int i = 0; i < m.nq; i++) qpos[i] = (real)m.qpos0[i];
+  for (int i = 0; i < 28 && 7 + i < m.nq; i++) qpos[7 + i] = (real)qi[i];
+  for (int i = 0; i < QVEL_W; i++) { qvel[i] = 0; qacc_ws[i] = 0; }
+  for (int i = 0; i < CST_W; i++) cst[i] = 0;
+  cst[CS_STO] = 1;  // radio channel 8 = 1 (cassie_out_init, :724)
+  for (int i = 0; i < DFILT_W; i++) dfilt[i] = 0;
+  for (int i = 0; i < XFRC_W; i++) xfrc[i] = 0;
+}
+
+}  // namespace cassie

@@ -1,0 +1,108 @@
+// devmodel.h -- the per-model constant block the stepper reads (one copy per CTA in shared memory, staged with a
+// TMA bulk copy), the HBM state layout, and the per-warp scratch layout.  Shared by the CUDA build (kernels.cu) and
+// by the test-only host emulation of the same source (tests/emu/).
+#pragma once
+#include <cstdint>
+
+namespace cassie {
+
+constexpr int MB = 32;        // bodies (nbody <= 32: one lane per body)
+constexpr int MJ = 32;        // joints
+constexpr int MV = 32;        // dofs   (nv <= 32: one lane per dof)
+constexpr int MG = 16;        // collision geoms
+constexpr int MP = 32;        // candidate geom pairs (one lane per pair)
+constexpr int ME = 4;         // connect equalities
+constexpr int MU = 10;        // motors
+constexpr int NM_MAX = 320;   // sparse mass-matrix entries (307 for Cassie)
+constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 for Cassie)
+constexpr int NEFC = 64;      // constraint rows per env (12 equality + limits + 4 per floor contact)
+constexpr int MAXCON = 16;    // contacts per env
+constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
+
+// pair kinds handled by the narrow phase
+enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2 };
+
+template <typename real>
+struct DevModel {
+  // ---- sizes / options
+  int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, pad0, pad1;
+  real timestep, tolerance, pgs_scale, root_mass_inv;
+  real gravity[3], magnetic[3], imu_pos[3], imu_quat[4], imu_mat[9], gyro_cutoff, accel_cutoff;
+  // ---- bodies
+  int body_parent[MB], body_depth[MB], body_jntadr[MB], body_jntnum[MB], body_lastdof[MB], body_subtree_end[MB];
+  uint32_t body_dofmask[MB];
+  real body_pos[MB][3], body_quat[MB][4], body_ipos[MB][3], body_imat[MB][9], body_mass[MB], body_inertia[MB][3], body_invw[MB];
+  // ---- joints
+  int jnt_type[MJ], jnt_qposadr[MJ], jnt_dofadr[MJ], jnt_body[MJ], jnt_limited[MJ];
+  real jnt_pos[MJ][3], jnt_axis[MJ][3], jnt_stiffness[MJ], jnt_range[MJ][2], jnt_qpos0[MJ], jnt_qspring[MJ], jnt_solref[MJ][2], jnt_solimp[MJ][5];
+  // ---- dofs
+  int dof_body[MV], dof_jnt[MV], dof_parent[MV], dof_Madr[MV], dof_depth[MV], dof_cvelsrc[MV];
+  uint32_t dof_ancmask[MV];
+  real dof_armature[MV], dof_damping[MV], dof_invweight0[MV];
+  uint32_t tri[NTRI_MAX];     // (i << 24) | (j << 16) | qLD address of L(i,j); i descending, ancestors nearest first
+  // ---- collision geoms and pairs
+  int geom_body[MG], geom_type[MG];
+  real geom_pos[MG][3], geom_zaxis[MG][3], geom_size[MG][2];
+  int pair_g1[MP], pair_g2[MP], pair_kind[MP], pair_condim[MP];
+  real pair_mu[MP], pair_margin[MP], pair_gap[MP], pair_solref[MP][2], pair_solimp[MP][5];
+  // ---- equality
+  int eq_b1[ME], eq_b2[ME];
+  real eq_data[ME][6], eq_solref[ME][2], eq_solimp[ME][5];
+  // ---- motors and encoders (model/cassie.xml:258-287)
+  int act_dof[MU], act_qposadr[MU], enc_bits[16], enc_qposadr[16], pad2[2];
+  real act_gear[MU], act_ctrl_lo[MU], act_ctrl_hi[MU], act_wmax[MU], act_torque_limit[MU], enc_scale[16];
+};
+
+// ---- HBM state: one row per environment in each array (row-major, env index slowest)
+constexpr int QPOS_W = 36;      // qpos[35] padded
+constexpr int QVEL_W = 32;
+constexpr int CST_W = 192;      // controller / sensor state, layout below
+constexpr int DFILT_W = 96;     // int32 drive FIR taps [10][9] padded
+constexpr int PD_W = 52;        // torque, pTarget, dTarget, pGain, dGain for the 10 motors (+2 pad)
+constexpr int XFRC_W = 8;       // force xyz, torque xyz, body id (as real), pad
+constexpr int OBS_W = 64;       // the dynamic subset of cassie_out_t copied out at src/cassiemujoco.c:1127
+// CST offsets
+constexpr int CS_SENSOR = 0;    // sensordata[29]
+constexpr int CS_ACTVEL = 32;   // actuator_velocity[10]
+constexpr int CS_DPOS = 42, CS_DVEL = 52, CS_DTORQUE = 62;   // cassie_out drive position / velocity / torque
+constexpr int CS_JPOS = 72, CS_JVEL = 78;                    // cassie_out joint position / velocity
+constexpr int CS_DELAY = 84;    // torque_delay[10][6]
+constexpr int CS_JFX = 144;     // joint filter x[6][4]
+constexpr int CS_JFY = 168;     // joint filter y[6][3]
+constexpr int CS_TIME = 186;
+constexpr int CS_STO = 187;     // radio channel 8 (safe-torque-off when < 1)
+// OBS offsets
+constexpr int OB_MPOS = 0, OB_MVEL = 10, OB_MTORQUE = 20, OB_JPOS = 30, OB_JVEL = 36, OB_QUAT = 42, OB_GYRO = 46, OB_ACCEL = 49, OB_MAG = 52, OB_TIME = 55;
+
+// ---- per-warp scratch (in units of `real`)
+constexpr int S_XPOS = 0;                       // [32][3]
+constexpr int S_XQUAT = S_XPOS + 96;            // [32][4]
+constexpr int S_XMAT = S_XQUAT + 128;           // [32][9]
+constexpr int S_CDOF = S_XMAT + 288;            // [32][6]
+constexpr int S_CDOFD = S_CDOF + 192;           // [32][6]
+constexpr int S_CINERT = S_CDOFD + 192;         // [32][10]
+constexpr int S_CRB = S_CINERT + 320;           // [32][10]; during FK: xanchor[32][3], xaxis[32][3], qloc[32][4]
+constexpr int S_QM = S_CRB + 320;               // [320]
+constexpr int S_QLD = S_QM + NM_MAX;            // [320]
+constexpr int S_DINV = S_QLD + NM_MAX;          // [32]
+constexpr int S_DSQI = S_DINV + 32;             // [32]
+constexpr int S_QPOS = S_DSQI + 32;             // [40]
+constexpr int S_VEC = S_QPOS + 40;              // [4][32] general vectors
+constexpr int S_GEOM = S_VEC + 128;             // [16][6] world pos + z axis
+constexpr int S_CON = S_GEOM + 96;              // [MAXCON][16]
+constexpr int S_CST = S_CON + MAXCON * 16;      // [192]
+constexpr int S_EFC = S_CST + CST_W;            // [7][NEFC]
+constexpr int S_Y = S_EFC + 7 * NEFC;           // [NEFC][33]; before the constraint stage: temporaries
+constexpr int S_REALS = S_Y + NEFC * YSTRIDE;
+constexpr int S_INTS = DFILT_W;                 // int region after the reals
+// row-scalar slots inside S_EFC
+constexpr int E_B = 0, E_R = 1, E_ADINV = 2, E_F = 3, E_INEQ = 4, E_POS = 5, E_SRC = 6;
+
+template <typename real> constexpr size_t scratch_bytes() { return (size_t)S_REALS * sizeof(real) + (size_t)S_INTS * sizeof(int); }
+
+// ---- debug dump (tests only; one block per env, in `real`)
+constexpr int D_XPOS = 0, D_XQUAT = 96, D_CDOF = 224, D_QM = 416, D_QLD = 736, D_BIAS = 1056, D_PASSIVE = 1088, D_SMOOTH = 1120,
+              D_QACCS = 1152, D_QACC = 1184, D_QFRCC = 1216, D_COUNTS = 1248, D_EFC_B = 1252, D_EFC_F = 1316, D_EFC_R = 1380,
+              D_EFC_AREF = 1444, D_SENS = 1508, D_J = 1540, D_SIZE = 3600;
+
+}  // namespace cassie

@@ -1,0 +1,834 @@
+// step_core.inl -- the batched Cassie stepper: one WARP per environment, lanes = dofs / bodies / constraint rows.
+//
+// This file is the hot path named by BASELINE.json: everything cassie_sim_step_pd does for one environment
+// (/root/reference/src/cassiemujoco.c:1147-1157 -> :1137-1145 -> :1115-1135), i.e.
+//   pd_input_step (motor-PD branch)  ->  cassie_core_sim_step (safety layer)  ->  motor model + 6-tick torque delay (:638-664)
+//   ->  encoder / filter emulation (:558-635, 737-774)  ->  mj_step1 + mj_step2 (MuJoCo 2.1.0 semantics: kinematics, comPos, CRB,
+//   sparse L'DL, collision, constraint assembly, PGS with warm start, sensors, implicit-damping Euler)
+// fused so that a launch advances every environment `nticks` control ticks with no host round trip.
+//
+// The code is written as warp-synchronous PHASES: `LANES { ... } ENDL` runs the body once per lane with lane index `l`, and
+// all cross-lane traffic happens between phases (shared-memory scratch `sm`, warp shuffles via ALLSUM / BCAST / EXSCAN_INT).
+// On the GPU (kernels.cu) a phase is straight-line code followed by __syncwarp().  With -DCASSIE_EMU (tests/emu only, never
+// linked into the product) a phase is a `for (l = 0..31)` loop and lane variables are arrays, which lets the exact same
+// source be executed and diffed against the oracle on a machine without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "devmodel.h"
+
+#ifdef CASSIE_EMU
+#define CFN inline
+#define DECL_LANE
+#define LANES for (int l = 0; l < 32; ++l) {
+#define ENDL }
+#define LV(T, name) T name[32]
+#define L(name) name[l]
+#define LP(T, name) T(&name)[32]
+#define LANE0(v) v[0]
+#define ALLSUM(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ += v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
+#define BCAST(dst, src, lane) do { auto s_ = src[lane]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = s_; } while (0)
+#define EXSCAN_INT(v, total) do { int a_ = 0; for (int i_ = 0; i_ < 32; ++i_) { int t_ = v[i_]; v[i_] = a_; a_ += t_; } total = a_; } while (0)
+#else
+#define CFN __device__ __forceinline__
+#define DECL_LANE const int l = threadIdx.x & 31;
+#define LANES {
+#define ENDL } __syncwarp();
+#define LV(T, name) T name
+#define L(name) name
+#define LP(T, name) T &name
+#define LANE0(v) v
+#define ALLSUM(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o_); } while (0)
+#define BCAST(dst, src, lane) dst = __shfl_sync(0xffffffffu, src, lane)
+#define EXSCAN_INT(v, total) do { int x_ = v; for (int o_ = 1; o_ < 32; o_ <<= 1) { int y_ = __shfl_up_sync(0xffffffffu, x_, o_); if (l >= o_) x_ += y_; } total = __shfl_sync(0xffffffffu, x_, 31); v = x_ - v; } while (0)
+#endif
+
+namespace cassie {
+
+// ------------------------------------------------------------------ scalar math on float / double
+CFN float msqrt(float x) { return sqrtf(x); }
+CFN double msqrt(double x) { return sqrt(x); }
+CFN float mabs(float x) { return fabsf(x); }
+CFN double mabs(double x) { return fabs(x); }
+CFN float mmax(float a, float b) { return fmaxf(a, b); }
+CFN double mmax(double a, double b) { return fmax(a, b); }
+CFN float mmin(float a, float b) { return fminf(a, b); }
+CFN double mmin(double a, double b) { return fmin(a, b); }
+CFN float mpow(float a, float b) { return powf(a, b); }
+CFN double mpow(double a, double b) { return pow(a, b); }
+CFN void msincos(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+CFN void msincos(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
+template <typename real> CFN real minval();
+template <> CFN float minval<float>() { return 1e-15f; }
+template <> CFN double minval<double>() { return 1e-15; }
+
+template <typename real> CFN real dot3(const real *a, const real *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename real> CFN void cross3(real *r, const real *a, const real *b) {
+  real t0 = a[1] * b[2] - a[2] * b[1], t1 = a[2] * b[0] - a[0] * b[2], t2 = a[0] * b[1] - a[1] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2;
+}
+template <typename real> CFN real normalize3(real *v) {
+  real n = msqrt(dot3(v, v));
+  if (n < minval<real>()) { v[0] = 1; v[1] = 0; v[2] = 0; return 0; }
+  real inv = real(1) / n; v[0] *= inv; v[1] *= inv; v[2] *= inv; return n;
+}
+template <typename real> CFN void normalize4(real *q) {
+  real n = msqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < minval<real>()) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  real inv = real(1) / n; q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+template <typename real> CFN void mul_quat(real *r, const real *a, const real *b) {
+  real t0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], t1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  real t2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], t3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+template <typename real> CFN void quat2mat(real *m, const real *q) {
+  real q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3], q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3],
+       q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03); m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
+}
+template <typename real> CFN void mat_vec(real *r, const real *m, const real *v) {
+  real t0 = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], t1 = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], t2 = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = t0; r[1] = t1; r[2] = t2;
+}
+template <typename real> CFN void matT_vec(real *r, const real *m, const real *v) {
+  real t0 = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], t1 = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], t2 = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = t0; r[1] = t1; r[2] = t2;
+}
+// 10-number spatial inertia times (angular; linear) motion vector, MuJoCo's c-frame convention
+template <typename real> CFN void mul_inert_vec(real *r, const real *i, const real *v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+template <typename real> CFN void cross_motion(real *r, const real *vel, const real *v) {
+  real t[3]; cross3(r, vel, v); cross3(r + 3, vel, v + 3); cross3(t, vel + 3, v);
+  r[3] += t[0]; r[4] += t[1]; r[5] += t[2];
+}
+template <typename real> CFN void cross_force(real *r, const real *vel, const real *f) {
+  real t[3]; cross3(r, vel, f); cross3(t, vel + 3, f + 3);
+  r[0] += t[0]; r[1] += t[1]; r[2] += t[2];
+  cross3(r + 3, vel, f + 3);
+}
+template <typename real> CFN real clampr(real x, real lo, real hi) { return mmin(mmax(x, lo), hi); }
+// MuJoCo's impedance sigmoid (solimp = dmin dmax width midpoint power)
+template <typename real> CFN real impedance(const real *solimp, real pos, real margin) {
+  if (solimp[0] == solimp[1] || solimp[2] <= minval<real>()) return real(0.5) * (solimp[0] + solimp[1]);
+  real x = mabs((pos - margin) / solimp[2]);
+  if (x >= 1) return solimp[1];
+  if (x <= 0) return solimp[0];
+  real y, p = solimp[4], mid = solimp[3];
+  if (p == 1) y = x;
+  else if (p == 2) y = (x <= mid) ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else if (x <= mid) y = mpow(x, p) / mpow(mid, p - 1);
+  else y = 1 - mpow(1 - x, p) / mpow(1 - mid, p - 1);
+  return solimp[0] + y * (solimp[1] - solimp[0]);
+}
+// contact frame from a normal and an optional tangent hint (zero hint -> canonical choice)
+template <typename real> CFN void make_frame(real *f) {
+  normalize3(f);
+  if (msqrt(dot3(f + 3, f + 3)) < real(0.5)) { f[3] = f[4] = f[5] = 0; if (f[1] < real(0.5) && f[1] > real(-0.5)) f[4] = 1; else f[5] = 1; }
+  real s = dot3(f, f + 3);
+  f[3] -= f[0] * s; f[4] -= f[1] * s; f[5] -= f[2] * s;
+  normalize3(f + 3); cross3(f + 6, f, f + 3);
+}
+
+// ------------------------------------------------------------------ sparse L'DL on the dof tree (lane = dof where it matters)
+// in-place factorisation of sm[S_QLD..] (already holding M); writes 1/D and 1/sqrt(D)
+template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm) {
+  DECL_LANE
+  real *qLD = sm + S_QLD;
+  LV(real, tmp);
+  for (int k = cm.nv - 1; k >= 0; --k) {
+    const int kk = cm.dof_Madr[k], depth = cm.dof_depth[k];
+    if (depth == 0) continue;
+    LANES  // lane t (1..depth) owns the t-th ancestor i of k: row_i -= row_k[t..] * (M(k,i)/M(k,k))
+      L(tmp) = 0;
+      if (l >= 1 && l <= depth) {
+        int i = k; for (int t = 0; t < l; ++t) i = cm.dof_parent[i];
+        const real f = qLD[kk + l] / qLD[kk];
+        const int cnt = cm.dof_depth[i] + 1, ia = cm.dof_Madr[i];
+        for (int c = 0; c < cnt; ++c) qLD[ia + c] -= qLD[kk + l + c] * f;
+        L(tmp) = f;
+      }
+    ENDL
+    LANES if (l >= 1 && l <= depth) qLD[kk + l] = L(tmp); ENDL
+  }
+  LANES if (l < cm.nv) { real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = real(1) / d; sm[S_DSQI + l] = real(1) / msqrt(d); } ENDL
+}
+// x <- inv(L') x   (x: one value per lane = dof)
+template <typename real> CFN void solve_lt(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+  DECL_LANE
+  LV(real, xi);
+  for (int i = cm.nv - 1; i >= 0; --i) {
+    if (cm.dof_depth[i] == 0) continue;
+    BCAST(xi, x, i);
+    const uint32_t anc = cm.dof_ancmask[i]; const int base = S_QLD + cm.dof_Madr[i] + cm.dof_depth[i];
+    LANES if ((anc >> l) & 1u) L(x) -= sm[base - cm.dof_depth[l]] * L(xi); ENDL
+  }
+}
+// x <- inv(L) x
+template <typename real> CFN void solve_l(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+  DECL_LANE
+  LV(real, xj);
+  for (int j = 0; j < cm.nv; ++j) {
+    BCAST(xj, x, j);
+    const int dj = cm.dof_depth[j];
+    LANES if (l < cm.nv && ((cm.dof_ancmask[l] >> j) & 1u)) L(x) -= sm[S_QLD + cm.dof_Madr[l] + cm.dof_depth[l] - dj] * L(xj); ENDL
+  }
+}
+// x <- inv(M) x
+template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+  DECL_LANE
+  solve_lt(cm, sm, x);
+  LANES if (l < cm.nv) L(x) *= sm[S_DINV + l]; ENDL
+  solve_l(cm, sm, x);
+}
+// y <- L' x  (used for J'f = L' D^{1/2} z)
+template <typename real> CFN void mul_lt(const DevModel<real> &cm, const real *sm, LP(real, x), LP(real, y)) {
+  DECL_LANE
+  LV(real, xi);
+  LANES L(y) = L(x); ENDL
+  for (int i = cm.nv - 1; i >= 0; --i) {
+    if (cm.dof_depth[i] == 0) continue;
+    BCAST(xi, x, i);
+    const uint32_t anc = cm.dof_ancmask[i]; const int base = S_QLD + cm.dof_Madr[i] + cm.dof_depth[i];
+    LANES if ((anc >> l) & 1u) L(y) += sm[base - cm.dof_depth[l]] * L(xi); ENDL
+  }
+}
+
+// translational Jacobian column of dof l for a world point attached to `body` (zero when l is not in the body's chain)
+template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int body, const real *cd, const real *point, const real *com, real *out) {
+  if ((cm.body_dofmask[body] >> l) & 1u) {
+    real off[3] = {point[0] - com[0], point[1] - com[1], point[2] - com[2]}, t[3];
+    cross3(t, cd, off);
+    out[0] = cd[3] + t[0]; out[1] = cd[4] + t[1]; out[2] = cd[5] + t[2];
+  } else { out[0] = out[1] = out[2] = 0; }
+}
+
+// ------------------------------------------------------------------ one MuJoCo sub-step (mj_step1 + mj_step2)
+// state in: sm[S_QPOS], lane vars qvel / qacc_ws, ctrl in sm[S_CST..] (via ctrl lane var), xfrc.  state out: same + sensordata.
+template <typename real>
+CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real, qacc_ws), LP(real, ctrl), const real *xfrc, real *dbg, int *counters, bool advance) {
+  DECL_LANE
+  const int nv = cm.nv, nb = cm.nbody;
+  real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF, *cdofd = sm + S_CDOFD, *cinert = sm + S_CINERT;
+  real *qpos = sm + S_QPOS, *qM = sm + S_QM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
+  real *xanchor = sm + S_CRB, *xaxis = sm + S_CRB + 96, *qloc = sm + S_CRB + 192;
+  LV(real, com0); LV(real, com1); LV(real, com2);
+
+  // ================= kinematics (mj_kinematics) =================
+  LANES  // lane = joint: local joint rotation
+    if (l < cm.njnt) {
+      const int t = cm.jnt_type[l], qa = cm.jnt_qposadr[l];
+      if (t == 3) {  // hinge
+        real s, c; msincos(real(0.5) * (qpos[qa] - cm.jnt_qpos0[l]), &s, &c);
+        qloc[4 * l] = c; qloc[4 * l + 1] = cm.jnt_axis[l][0] * s; qloc[4 * l + 2] = cm.jnt_axis[l][1] * s; qloc[4 * l + 3] = cm.jnt_axis[l][2] * s;
+      } else if (t == 1) {  // ball: normalised copy
+        real q[4] = {qpos[qa], qpos[qa + 1], qpos[qa + 2], qpos[qa + 3]}; normalize4(q);
+        qloc[4 * l] = q[0]; qloc[4 * l + 1] = q[1]; qloc[4 * l + 2] = q[2]; qloc[4 * l + 3] = q[3];
+      }
+    }
+    if (l == 0) { xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0; for (int k = 0; k < 9; ++k) xmat[k] = (k % 4 == 0) ? real(1) : real(0); }
+  ENDL
+  for (int lev = 1; lev <= cm.maxdepth; ++lev) {
+    LANES  // lane = body at this tree level
+      if (l < nb && cm.body_depth[l] == lev) {
+        const int p = cm.body_parent[l];
+        real pos[3], quat[4], v[3], R[9];
+        mat_vec(v, xmat + 9 * p, cm.body_pos[l]);
+        pos[0] = xpos[3 * p] + v[0]; pos[1] = xpos[3 * p + 1] + v[1]; pos[2] = xpos[3 * p + 2] + v[2];
+        mul_quat(quat, xquat + 4 * p, cm.body_quat[l]);
+        for (int jj = 0; jj < cm.body_jntnum[l]; ++jj) {
+          const int j = cm.body_jntadr[l] + jj;
+          quat2mat(R, quat);
+          mat_vec(xaxis + 3 * j, R, cm.jnt_axis[j]);
+          mat_vec(v, R, cm.jnt_pos[j]);
+          xanchor[3 * j] = pos[0] + v[0]; xanchor[3 * j + 1] = pos[1] + v[1]; xanchor[3 * j + 2] = pos[2] + v[2];
+          if (cm.jnt_type[j] == 2) {
+            const real s = qpos[cm.jnt_qposadr[j]] - cm.jnt_qpos0[j];
+            pos[0] += xaxis[3 * j] * s; pos[1] += xaxis[3 * j + 1] * s; pos[2] += xaxis[3 * j + 2] * s;
+          } else {
+            mul_quat(quat, quat, qloc + 4 * j);
+            quat2mat(R, quat); mat_vec(v, R, cm.jnt_pos[j]);
+            pos[0] = xanchor[3 * j] - v[0]; pos[1] = xanchor[3 * j + 1] - v[1]; pos[2] = xanchor[3 * j + 2] - v[2];
+          }
+        }
+        normalize4(quat);
+        xpos[3 * l] = pos[0]; xpos[3 * l + 1] = pos[1]; xpos[3 * l + 2] = pos[2];
+        xquat[4 * l] = quat[0]; xquat[4 * l + 1] = quat[1]; xquat[4 * l + 2] = quat[2]; xquat[4 * l + 3] = quat[3];
+        quat2mat(xmat + 9 * l, quat);
+      }
+    ENDL
+  }
+
+  // ================= comPos: subtree com of the root, cinert, cdof =================
+  LV(real, t0); LV(real, t1); LV(real, t2);
+  LANES  // lane = body
+    L(t0) = L(t1) = L(t2) = 0;
+    if (l >= 1 && l < nb) {
+      real v[3]; mat_vec(v, xmat + 9 * l, cm.body_ipos[l]);
+      const real m = cm.body_mass[l];
+      L(t0) = m * (xpos[3 * l] + v[0]); L(t1) = m * (xpos[3 * l + 1] + v[1]); L(t2) = m * (xpos[3 * l + 2] + v[2]);
+    }
+  ENDL
+  ALLSUM(t0); ALLSUM(t1); ALLSUM(t2);
+  LANES L(com0) = L(t0) * cm.root_mass_inv; L(com1) = L(t1) * cm.root_mass_inv; L(com2) = L(t2) * cm.root_mass_inv; ENDL
+  LANES  // lane = body: cinert about the com, world orientation
+    if (l < nb) {
+      real *r = cinert + 10 * l;
+      if (l == 0) { for (int k = 0; k < 10; ++k) r[k] = 0; }
+      else {
+        real v[3], off[3], R[9]; const real *X = xmat + 9 * l, *B = cm.body_imat[l], *I = cm.body_inertia[l]; const real m = cm.body_mass[l];
+        mat_vec(v, X, cm.body_ipos[l]);
+        off[0] = xpos[3 * l] + v[0] - L(com0); off[1] = xpos[3 * l + 1] + v[1] - L(com1); off[2] = xpos[3 * l + 2] + v[2] - L(com2);
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[3 * a + b] = X[3 * a] * B[b] + X[3 * a + 1] * B[3 + b] + X[3 * a + 2] * B[6 + b];
+        r[0] = R[0] * R[0] * I[0] + R[1] * R[1] * I[1] + R[2] * R[2] * I[2] + m * (off[1] * off[1] + off[2] * off[2]);
+        r[1] = R[3] * R[3] * I[0] + R[4] * R[4] * I[1] + R[5] * R[5] * I[2] + m * (off[0] * off[0] + off[2] * off[2]);
+        r[2] = R[6] * R[6] * I[0] + R[7] * R[7] * I[1] + R[8] * R[8] * I[2] + m * (off[0] * off[0] + off[1] * off[1]);
+        r[3] = R[0] * R[3] * I[0] + R[1] * R[4] * I[1] + R[2] * R[5] * I[2] - m * off[0] * off[1];
+        r[4] = R[0] * R[6] * I[0] + R[1] * R[7] * I[1] + R[2] * R[8] * I[2] - m * off[0] * off[2];
+        r[5] = R[3] * R[6] * I[0] + R[4] * R[7] * I[1] + R[5] * R[8] * I[2] - m * off[1] * off[2];
+        r[6] = m * off[0]; r[7] = m * off[1]; r[8] = m * off[2]; r[9] = m;
+      }
+    }
+  ENDL
+  LV(real, cd0); LV(real, cd1); LV(real, cd2); LV(real, cd3); LV(real, cd4); LV(real, cd5);  // this lane's cdof (angular; linear)
+  LANES  // lane = dof
+    L(cd0) = L(cd1) = L(cd2) = L(cd3) = L(cd4) = L(cd5) = 0;
+    if (l < nv) {
+      const int j = cm.dof_jnt[l], t = cm.jnt_type[j], b = cm.dof_body[l];
+      real off[3] = {L(com0) - xanchor[3 * j], L(com1) - xanchor[3 * j + 1], L(com2) - xanchor[3 * j + 2]}, ax[3], c[3];
+      if (t == 2) { L(cd3) = xaxis[3 * j]; L(cd4) = xaxis[3 * j + 1]; L(cd5) = xaxis[3 * j + 2]; }
+      else {
+        if (t == 3) { ax[0] = xaxis[3 * j]; ax[1] = xaxis[3 * j + 1]; ax[2] = xaxis[3 * j + 2]; }
+        else { const int k = l - cm.jnt_dofadr[j]; ax[0] = xmat[9 * b + k]; ax[1] = xmat[9 * b + 3 + k]; ax[2] = xmat[9 * b + 6 + k]; }
+        cross3(c, ax, off);
+        L(cd0) = ax[0]; L(cd1) = ax[1]; L(cd2) = ax[2]; L(cd3) = c[0]; L(cd4) = c[1]; L(cd5) = c[2];
+      }
+      real *o = cdof + 6 * l; o[0] = L(cd0); o[1] = L(cd1); o[2] = L(cd2); o[3] = L(cd3); o[4] = L(cd4); o[5] = L(cd5);
+    }
+  ENDL
+
+  // ================= CRB -> sparse qM (mj_crb); crb overwrites the xanchor/xaxis/qloc temporaries =================
+  {
+    real *crb = sm + S_CRB;
+    LANES  // lane = body: composite inertia = sum of cinert over the (contiguous, depth-first) subtree
+      if (l < nb) {
+        real acc[10]; for (int k = 0; k < 10; ++k) acc[k] = 0;
+        if (l >= 1) for (int b = l; b < cm.body_subtree_end[l]; ++b) for (int k = 0; k < 10; ++k) acc[k] += cinert[10 * b + k];
+        for (int k = 0; k < 10; ++k) crb[10 * l + k] = acc[k];
+      }
+    ENDL
+    LANES  // lane = dof i: M(i, ancestors)
+      if (l < nv) {
+        real buf[6], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)};
+        mul_inert_vec(buf, crb + 10 * cm.dof_body[l], cd);
+        int a = cm.dof_Madr[l];
+        for (int j = l; j >= 0; j = cm.dof_parent[j]) {
+          const real *cj = cdof + 6 * j;
+          real s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+          if (j == l) s += cm.dof_armature[l];
+          qM[a] = s; qLD[a] = s; ++a;
+        }
+      }
+    ENDL
+  }
+  factor_ld(cm, sm);
+
+  // ================= velocity stage: comVel, passive, RNE bias =================
+  real *S = sm + S_CRB;          // chain sums [32][6] (crb is dead)
+  real *cvel = Y;                // [32][6]
+  real *cfrc = Y + 192;          // [32][6]
+  real *vecs = sm + S_VEC;
+  LANES if (l < nv) vecs[l] = L(qvel); ENDL
+  LANES  // lane = dof: S_d = sum over the chain root..d of cdof_a * qvel_a
+    if (l < nv) {
+      real acc[6] = {0, 0, 0, 0, 0, 0};
+      for (int a = l; a >= 0; a = cm.dof_parent[a]) { const real q = vecs[a]; const real *c = cdof + 6 * a; for (int k = 0; k < 6; ++k) acc[k] += c[k] * q; }
+      for (int k = 0; k < 6; ++k) S[6 * l + k] = acc[k];
+    }
+  ENDL
+  LANES  // cdof_dot = (velocity before this joint) x cdof ; body velocities
+    if (l < nv) {
+      real vb[6] = {0, 0, 0, 0, 0, 0}, cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, r[6];
+      const int src = cm.dof_cvelsrc[l];
+      if (src >= 0) for (int k = 0; k < 6; ++k) vb[k] = S[6 * src + k];
+      cross_motion(r, vb, cd);
+      for (int k = 0; k < 6; ++k) cdofd[6 * l + k] = r[k];
+    }
+    if (l < nb) { const int ld = cm.body_lastdof[l]; for (int k = 0; k < 6; ++k) cvel[6 * l + k] = (ld >= 0) ? S[6 * ld + k] : real(0); }
+  ENDL
+  LANES  // T_d = chain sums of cdof_dot * qvel (overwrites S; nobody reads S in this phase)
+    if (l < nv) {
+      real acc[6] = {0, 0, 0, 0, 0, 0};
+      for (int a = l; a >= 0; a = cm.dof_parent[a]) { const real q = vecs[a]; const real *c = cdofd + 6 * a; for (int k = 0; k < 6; ++k) acc[k] += c[k] * q; }
+      for (int k = 0; k < 6; ++k) S[6 * l + k] = acc[k];
+    }
+  ENDL
+  LANES  // lane = body: cfrc = cinert * cacc + cvel x* (cinert * cvel), cacc = (0; -g) + T[lastdof]
+    if (l < nb) {
+      real f[6] = {0, 0, 0, 0, 0, 0};
+      if (l >= 1) {
+        real acc[6] = {0, 0, 0, -cm.gravity[0], -cm.gravity[1], -cm.gravity[2]}, tmp[6], tmp1[6];
+        const int ld = cm.body_lastdof[l];
+        if (ld >= 0) for (int k = 0; k < 6; ++k) acc[k] += S[6 * ld + k];
+        mul_inert_vec(f, cinert + 10 * l, acc);
+        mul_inert_vec(tmp, cinert + 10 * l, cvel + 6 * l);
+        cross_force(tmp1, cvel + 6 * l, tmp);
+        for (int k = 0; k < 6; ++k) f[k] += tmp1[k];
+      }
+      for (int k = 0; k < 6; ++k) cfrc[6 * l + k] = f[k];
+    }
+  ENDL
+  LV(real, qfrc_smooth); LV(real, qacc_smooth); LV(real, bias);
+  LANES  // lane = dof: bias = cdof . (sum of cfrc over the subtree of the dof's body); passive; actuation; applied
+    L(qfrc_smooth) = 0; L(bias) = 0;
+    if (l < nv) {
+      const int b = cm.dof_body[l];
+      real acc[6] = {0, 0, 0, 0, 0, 0};
+      for (int d = b; d < cm.body_subtree_end[b]; ++d) for (int k = 0; k < 6; ++k) acc[k] += cfrc[6 * d + k];
+      const real bs = L(cd0) * acc[0] + L(cd1) * acc[1] + L(cd2) * acc[2] + L(cd3) * acc[3] + L(cd4) * acc[4] + L(cd5) * acc[5];
+      const int j = cm.dof_jnt[l];
+      real passive = -cm.dof_damping[l] * L(qvel);
+      if (cm.jnt_stiffness[j] != 0 && cm.jnt_type[j] >= 2) passive -= cm.jnt_stiffness[j] * (qpos[cm.jnt_qposadr[j]] - cm.jnt_qspring[j]);
+      real f = passive - bs;
+      // xfrc_applied on one body: J(xipos)' [force; torque]
+      const int xb = (int)xfrc[6];
+      if (xb > 0 && ((cm.body_dofmask[xb] >> l) & 1u)) {
+        real v[3], pt[3], jc[3], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, cm3[3] = {L(com0), L(com1), L(com2)};
+        mat_vec(v, xmat + 9 * xb, cm.body_ipos[xb]);
+        pt[0] = xpos[3 * xb] + v[0]; pt[1] = xpos[3 * xb + 1] + v[1]; pt[2] = xpos[3 * xb + 2] + v[2];
+        jac_col(cm, l, xb, cd, pt, cm3, jc);
+        f += jc[0] * xfrc[0] + jc[1] * xfrc[1] + jc[2] * xfrc[2] + cd[0] * xfrc[3] + cd[1] * xfrc[4] + cd[2] * xfrc[5];
+      }
+      L(bias) = bs;
+      L(qfrc_smooth) = f;
+      if (dbg) { dbg[D_BIAS + l] = bs; dbg[D_PASSIVE + l] = passive; }
+    }
+  ENDL
+  LANES  // motors: lane = actuator; clamp ctrl, scatter gear * ctrl to the dof through shared memory
+    vecs[32 + l] = 0;
+  ENDL
+  LANES if (l < cm.nu) vecs[32 + cm.act_dof[l]] = cm.act_gear[l] * clampr(L(ctrl), cm.act_ctrl_lo[l], cm.act_ctrl_hi[l]); ENDL
+  LANES if (l < nv) { L(qfrc_smooth) += vecs[32 + l]; L(qacc_smooth) = L(qfrc_smooth); } else L(qacc_smooth) = 0; ENDL
+  solve_m(cm, sm, qacc_smooth);
+  if (dbg) {
+    LANES
+      if (l < nv) { dbg[D_SMOOTH + l] = L(qfrc_smooth); dbg[D_QACCS + l] = L(qacc_smooth); for (int k = 0; k < 6; ++k) dbg[D_CDOF + 6 * l + k] = cdof[6 * l + k]; }
+      if (l < nb) { for (int k = 0; k < 3; ++k) dbg[D_XPOS + 3 * l + k] = xpos[3 * l + k]; for (int k = 0; k < 4; ++k) dbg[D_XQUAT + 4 * l + k] = xquat[4 * l + k]; }
+      for (int a = l; a < cm.nM; a += 32) { dbg[D_QM + a] = qM[a]; dbg[D_QLD + a] = qLD[a]; }
+    ENDL
+  }
+
+  // ================= collision (lane = candidate geom pair) =================
+  real *geom = sm + S_GEOM;
+  LANES
+    if (l < cm.ngeom) {
+      const int b = cm.geom_body[l]; real v[3];
+      mat_vec(v, xmat + 9 * b, cm.geom_pos[l]);
+      geom[6 * l] = xpos[3 * b] + v[0]; geom[6 * l + 1] = xpos[3 * b + 1] + v[1]; geom[6 * l + 2] = xpos[3 * b + 2] + v[2];
+      mat_vec(v, xmat + 9 * b, cm.geom_zaxis[l]);
+      geom[6 * l + 3] = v[0]; geom[6 * l + 4] = v[1]; geom[6 * l + 5] = v[2];
+    }
+  ENDL
+  LV(int, ccount); LV(int, coff);
+  LV(real, c0p0); LV(real, c0p1); LV(real, c0p2); LV(real, c0n0); LV(real, c0n1); LV(real, c0n2); LV(real, c0d);
+  LV(real, c1p0); LV(real, c1p1); LV(real, c1p2); LV(real, c1n0); LV(real, c1n1); LV(real, c1n2); LV(real, c1d);
+  LV(real, ch0); LV(real, ch1); LV(real, ch2);
+  LANES
+    L(ccount) = 0; L(ch0) = L(ch1) = L(ch2) = 0;
+    L(c0p0) = L(c0p1) = L(c0p2) = L(c0n0) = L(c0n1) = L(c0n2) = L(c0d) = 0; L(c1p0) = L(c1p1) = L(c1p2) = L(c1n0) = L(c1n1) = L(c1n2) = L(c1d) = 0;
+    if (l < cm.npair) {
+      const int g1 = cm.pair_g1[l], g2 = cm.pair_g2[l], kind = cm.pair_kind[l]; const real margin = cm.pair_margin[l];
+      const real *p1 = geom + 6 * g1, *a1 = p1 + 3, *p2 = geom + 6 * g2, *a2 = p2 + 3;
+      real cp[2][3], cn[2][3], cdst[2]; int n = 0;
+      if (kind == PAIR_PLANE_SPHERE || kind == PAIR_PLANE_CAPSULE) {
+        const real r = cm.geom_size[g2][0], hl = (kind == PAIR_PLANE_CAPSULE) ? cm.geom_size[g2][1] : real(0);
+        const int ne = (kind == PAIR_PLANE_CAPSULE) ? 2 : 1;
+        for (int e = 0; e < ne; ++e) {
+          const real sgn = e ? real(-1) : real(1);
+          real sp[3] = {p2[0] + sgn * hl * a2[0], p2[1] + sgn * hl * a2[1], p2[2] + sgn * hl * a2[2]};
+          real dd[3] = {sp[0] - p1[0], sp[1] - p1[1], sp[2] - p1[2]};
+          const real cdist = dot3(dd, a1);
+          if (cdist <= margin + r && cdist - r < margin) {
+            cdst[n] = cdist - r; cn[n][0] = a1[0]; cn[n][1] = a1[1]; cn[n][2] = a1[2];
+            const real s = cdst[n] * real(0.5) + r;
+            cp[n][0] = sp[0] - a1[0] * s; cp[n][1] = sp[1] - a1[1] * s; cp[n][2] = sp[2] - a1[2] * s; ++n;
+          }
+        }
+        if (kind == PAIR_PLANE_CAPSULE) { L(ch0) = a2[0]; L(ch1) = a2[1]; L(ch2) = a2[2]; }
+      } else {  // capsule - capsule
+        const real s1 = cm.geom_size[g1][1], s2 = cm.geom_size[g2][1], r1 = cm.geom_size[g1][0], r2 = cm.geom_size[g2][0];
+        real dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+        const real ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif), det = ma * mc - mb * mb;
+        real x1c[2], x2c[2]; int nc = 0;
+        if (mabs(det) >= minval<real>()) {
+          real x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+          if (x1 > s1) { x1 = s1; x2 = (v - mb * s1) / mc; } else if (x1 < -s1) { x1 = -s1; x2 = (v + mb * s1) / mc; }
+          if (x2 > s2) { x2 = s2; x1 = clampr((u - mb * s2) / ma, -s1, s1); } else if (x2 < -s2) { x2 = -s2; x1 = clampr((u + mb * s2) / ma, -s1, s1); }
+          x1c[0] = x1; x2c[0] = x2; nc = 1;
+        } else {  // parallel axes: segment ends of 1 against 2 (at most two contacts are kept)
+          x1c[0] = s1; x2c[0] = clampr((v - mb * s1) / mc, -s2, s2); x1c[1] = -s1; x2c[1] = clampr((v + mb * s1) / mc, -s2, s2); nc = 2;
+        }
+        for (int e = 0; e < nc; ++e) {
+          real v1[3] = {p1[0] + a1[0] * x1c[e], p1[1] + a1[1] * x1c[e], p1[2] + a1[2] * x1c[e]}, v2[3] = {p2[0] + a2[0] * x2c[e], p2[1] + a2[1] * x2c[e], p2[2] + a2[2] * x2c[e]};
+          real dd[3] = {v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2]}; const real cdist = msqrt(dot3(dd, dd));
+          if (cdist <= margin + r1 + r2 && cdist - r1 - r2 < margin) {
+            cdst[n] = cdist - r1 - r2;
+            if (cdist < minval<real>()) { cn[n][0] = 1; cn[n][1] = cn[n][2] = 0; } else { cn[n][0] = dd[0] / cdist; cn[n][1] = dd[1] / cdist; cn[n][2] = dd[2] / cdist; }
+            const real s = r1 + cdst[n] * real(0.5);
+            cp[n][0] = v1[0] + cn[n][0] * s; cp[n][1] = v1[1] + cn[n][1] * s; cp[n][2] = v1[2] + cn[n][2] * s; ++n;
+          }
+        }
+      }
+      L(ccount) = n;
+      if (n > 0) { L(c0p0) = cp[0][0]; L(c0p1) = cp[0][1]; L(c0p2) = cp[0][2]; L(c0n0) = cn[0][0]; L(c0n1) = cn[0][1]; L(c0n2) = cn[0][2]; L(c0d) = cdst[0]; }
+      if (n > 1) { L(c1p0) = cp[1][0]; L(c1p1) = cp[1][1]; L(c1p2) = cp[1][2]; L(c1n0) = cn[1][0]; L(c1n1) = cn[1][1]; L(c1n2) = cn[1][2]; L(c1d) = cdst[1]; }
+    }
+    L(coff) = L(ccount);
+  ENDL
+  int ncon_total = 0;
+  EXSCAN_INT(coff, ncon_total);
+  LANES  // write contacts in pair order: [pos3 frame9 dist pair]
+    for (int e = 0; e < L(ccount); ++e) {
+      const int c = L(coff) + e;
+      if (c < MAXCON) {
+        real *o = con + 16 * c;
+        o[0] = e ? L(c1p0) : L(c0p0); o[1] = e ? L(c1p1) : L(c0p1); o[2] = e ? L(c1p2) : L(c0p2);
+        real f[9] = {e ? L(c1n0) : L(c0n0), e ? L(c1n1) : L(c0n1), e ? L(c1n2) : L(c0n2), L(ch0), L(ch1), L(ch2), 0, 0, 0};
+        make_frame(f);
+        for (int k = 0; k < 9; ++k) o[3 + k] = f[k];
+        o[12] = e ? L(c1d) : L(c0d); o[13] = (real)l;
+      }
+    }
+  ENDL
+  int ncon = ncon_total < MAXCON ? ncon_total : MAXCON;
+
+  // ================= constraint rows: J (into Y), pos, source; order = equality, limits, contacts =================
+  int nefc = 0;
+  for (int e = 0; e < cm.neq; ++e) {
+    const int b1 = cm.eq_b1[e], b2 = cm.eq_b2[e];
+    LANES  // lane = dof
+      real p1[3], p2[3], v[3], j1[3], j2[3], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, cm3[3] = {L(com0), L(com1), L(com2)};
+      mat_vec(v, xmat + 9 * b1, cm.eq_data[e]); p1[0] = xpos[3 * b1] + v[0]; p1[1] = xpos[3 * b1 + 1] + v[1]; p1[2] = xpos[3 * b1 + 2] + v[2];
+      mat_vec(v, xmat + 9 * b2, cm.eq_data[e] + 3); p2[0] = xpos[3 * b2] + v[0]; p2[1] = xpos[3 * b2 + 1] + v[1]; p2[2] = xpos[3 * b2 + 2] + v[2];
+      jac_col(cm, l, b1, cd, p1, cm3, j1); jac_col(cm, l, b2, cd, p2, cm3, j2);
+      for (int k = 0; k < 3; ++k) {
+        Y[(nefc + k) * YSTRIDE + l] = j1[k] - j2[k];
+        if (l == 0) { efc[E_POS * NEFC + nefc + k] = p1[k] - p2[k]; efc[E_SRC * NEFC + nefc + k] = (real)e; efc[E_INEQ * NEFC + nefc + k] = 0; }
+      }
+    ENDL
+    nefc += 3;
+  }
+  LV(int, lcount); LV(int, loff);
+  LANES  // lane = joint: violated limits
+    L(lcount) = 0;
+    if (l < cm.njnt && cm.jnt_limited[l]) { const real q = qpos[cm.jnt_qposadr[l]]; L(lcount) = (q - cm.jnt_range[l][0] < 0 ? 1 : 0) + (cm.jnt_range[l][1] - q < 0 ? 1 : 0); }
+    L(loff) = L(lcount);
+  ENDL
+  int nlim = 0;
+  EXSCAN_INT(loff, nlim);
+  LANES
+    if (L(lcount) > 0) {
+      const real q = qpos[cm.jnt_qposadr[l]]; int r = nefc + L(loff);
+      for (int side = 0; side < 2; ++side) {
+        const real dist = side ? cm.jnt_range[l][1] - q : q - cm.jnt_range[l][0];
+        if (dist < 0 && r < NEFC) {
+          for (int d = 0; d < 32; ++d) Y[r * YSTRIDE + d] = 0;
+          Y[r * YSTRIDE + cm.jnt_dofadr[l]] = side ? real(-1) : real(1);
+          efc[E_POS * NEFC + r] = dist; efc[E_SRC * NEFC + r] = (real)(64 + l); efc[E_INEQ * NEFC + r] = 1; ++r;
+        }
+      }
+    }
+  ENDL
+  nefc += nlim; if (nefc > NEFC) nefc = NEFC;
+  const int nefc_before_contacts = nefc;
+  int ncon_used = 0;
+  for (int c = 0; c < ncon; ++c) {
+    const real *o = con + 16 * c; const int p = (int)o[13]; const int rows = cm.pair_condim[p] > 1 ? 4 : 1;
+    if (nefc + rows > NEFC) break;
+    const int b1 = cm.geom_body[cm.pair_g1[p]], b2 = cm.geom_body[cm.pair_g2[p]];
+    LANES  // lane = dof
+      real j1[3], j2[3], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, cm3[3] = {L(com0), L(com1), L(com2)};
+      jac_col(cm, l, b1, cd, o, cm3, j1); jac_col(cm, l, b2, cd, o, cm3, j2);
+      real dj[3] = {j2[0] - j1[0], j2[1] - j1[1], j2[2] - j1[2]};
+      const real jn = dot3(o + 3, dj);
+      if (rows == 1) Y[nefc * YSTRIDE + l] = jn;
+      else {
+        const real mu = cm.pair_mu[p], jt1 = dot3(o + 6, dj), jt2 = dot3(o + 9, dj);
+        Y[nefc * YSTRIDE + l] = jn + mu * jt1; Y[(nefc + 1) * YSTRIDE + l] = jn - mu * jt1;
+        Y[(nefc + 2) * YSTRIDE + l] = jn + mu * jt2; Y[(nefc + 3) * YSTRIDE + l] = jn - mu * jt2;
+      }
+      if (l < rows) { efc[E_POS * NEFC + nefc + l] = o[12]; efc[E_SRC * NEFC + nefc + l] = (real)(128 + p); efc[E_INEQ * NEFC + nefc + l] = 1; }
+    ENDL
+    nefc += rows; ++ncon_used;
+  }
+  if (counters) { LANES if (l == 0) { counters[0] = nefc; counters[1] = ncon_used; counters[2] = nlim; if (ncon_total > ncon_used) counters[4] += ncon_total - ncon_used; } ENDL }
+  (void)nefc_before_contacts;
+
+  LV(real, qacc); LV(real, qfrc_con);
+  int iters = 0;
+  if (nefc == 0) {
+    LANES L(qacc) = L(qacc_smooth); L(qfrc_con) = 0; ENDL
+  } else {
+    // ---- per-row: impedance, R, aref, b, warm-start force (lane = row)
+    LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc_smooth); vecs[64 + l] = L(qacc_ws); } ENDL
+    if (dbg) { LANES for (int r = 0; r < nefc; ++r) dbg[D_J + 32 * r + l] = Y[r * YSTRIDE + l]; ENDL }
+    for (int pass = 0; pass * 32 < nefc; ++pass) {
+      LANES
+        const int r = l + 32 * pass;
+        if (r < nefc) {
+          const real *y = Y + r * YSTRIDE; real jv = 0, ja = 0, jw = 0;
+          for (int d = 0; d < nv; ++d) { const real yy = y[d]; jv += yy * vecs[d]; ja += yy * vecs[32 + d]; jw += yy * vecs[64 + d]; }
+          const int src = (int)efc[E_SRC * NEFC + r]; const real pos = efc[E_POS * NEFC + r];
+          const real *solref, *solimp; real dA, margin = 0, rscale = 1;
+          if (src < 64) { solref = cm.eq_solref[src]; solimp = cm.eq_solimp[src]; dA = cm.body_invw[cm.eq_b1[src]] + cm.body_invw[cm.eq_b2[src]]; }
+          else if (src < 128) { const int j = src - 64; solref = cm.jnt_solref[j]; solimp = cm.jnt_solimp[j]; dA = cm.dof_invweight0[cm.jnt_dofadr[j]]; }
+          else {
+            const int p = src - 128; solref = cm.pair_solref[p]; solimp = cm.pair_solimp[p]; margin = cm.pair_margin[p] - cm.pair_gap[p];
+            dA = cm.body_invw[cm.geom_body[cm.pair_g1[p]]] + cm.body_invw[cm.geom_body[cm.pair_g2[p]]];
+            if (cm.pair_condim[p] > 1) { const real mu = cm.pair_mu[p]; dA += mu * mu * dA; rscale = 2 * mu * mu; }
+          }
+          const real imp = impedance(solimp, pos, margin);
+          const real Rr = rscale * mmax(minval<real>(), (1 - imp) * dA / imp);
+          real K, B;
+          if (solref[0] > 0) { const real tc = mmax(solref[0], 2 * cm.timestep); K = 1 / mmax(minval<real>(), solimp[1] * solimp[1] * tc * tc * solref[1] * solref[1]); B = 2 / mmax(minval<real>(), solimp[1] * tc); }
+          else { K = -solref[0] / mmax(minval<real>(), solimp[1] * solimp[1]); B = -solref[1] / mmax(minval<real>(), solimp[1]); }
+          const real aref = -B * jv - K * imp * (pos - margin);
+          const real jar = jw - aref; real f = -jar / Rr;
+          if (efc[E_INEQ * NEFC + r] != 0 && jar >= 0) f = 0;
+          efc[E_B * NEFC + r] = ja - aref; efc[E_R * NEFC + r] = Rr; efc[E_F * NEFC + r] = f;
+          if (dbg) { dbg[D_EFC_AREF + r] = aref; dbg[D_EFC_R + r] = Rr; dbg[D_EFC_B + r] = ja - aref; }
+          // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place
+          real *yy = Y + r * YSTRIDE;
+          for (int k = 0; k < cm.ntri; ++k) { const uint32_t t = cm.tri[k]; yy[(t >> 16) & 255u] -= qLD[t & 0xffffu] * yy[t >> 24]; }
+          real ad = 0;
+          for (int d = 0; d < nv; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
+          efc[E_ADINV * NEFC + r] = real(1) / (ad + Rr);
+        }
+      ENDL
+    }
+    // ---- warm start: keep f only if its dual cost 0.5 f'(YY'+R)f + f'b is not positive
+    LV(real, z);
+    LANES real s = 0; if (l < nv) for (int r = 0; r < nefc; ++r) s += Y[r * YSTRIDE + l] * efc[E_F * NEFC + r]; L(z) = s; L(t0) = real(0.5) * s * s; ENDL
+    LANES
+      real s = 0;
+      for (int r = l; r < nefc; r += 32) { const real f = efc[E_F * NEFC + r]; s += f * (efc[E_B * NEFC + r] + real(0.5) * efc[E_R * NEFC + r] * f); }
+      L(t0) += s;
+    ENDL
+    ALLSUM(t0);
+    if (LANE0(t0) > 0) { LANES L(z) = 0; for (int r = l; r < nefc; r += 32) efc[E_F * NEFC + r] = 0; ENDL }
+    // ---- projected Gauss-Seidel, rows strictly in order; z = Y'f is carried one entry per lane
+    LV(real, acc); LV(real, impr);
+    while (iters < cm.iterations) {
+      LANES L(impr) = 0; ENDL
+      for (int r = 0; r < nefc; ++r) {
+        LANES L(acc) = (l < nv) ? Y[r * YSTRIDE + l] * L(z) : real(0); ENDL
+        ALLSUM(acc);
+        LANES
+          const real fold = efc[E_F * NEFC + r], Rr = efc[E_R * NEFC + r], adinv = efc[E_ADINV * NEFC + r];
+          const real res = efc[E_B * NEFC + r] + L(acc) + Rr * fold;
+          real fnew = fold - res * adinv;
+          if (efc[E_INEQ * NEFC + r] != 0 && fnew < 0) fnew = 0;
+          real delta = fnew - fold;
+          real change = real(0.5) * delta * delta / adinv + delta * res;
+          if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+          L(impr) -= change;
+          if (l < nv) L(z) += Y[r * YSTRIDE + l] * delta;
+          L(t1) = fnew;
+        ENDL
+        LANES if (l == 0) efc[E_F * NEFC + r] = L(t1); ENDL
+      }
+      ++iters;
+      if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
+    }
+    // ---- qacc = qacc_smooth + inv(L) D^-1/2 z ;  qfrc_constraint = J'f = L' D^1/2 z
+    LV(real, w);
+    LANES L(w) = (l < nv) ? L(z) * sm[S_DSQI + l] : real(0); ENDL
+    solve_l(cm, sm, w);
+    LANES L(qacc) = L(qacc_smooth) + L(w); L(w) = (l < nv) ? L(z) / sm[S_DSQI + l] : real(0); ENDL
+    mul_lt(cm, sm, w, qfrc_con);
+  }
+  if (counters) { LANES if (l == 0) counters[3] = iters; ENDL }
+  if (dbg) {
+    LANES
+      if (l < nv) { dbg[D_QACC + l] = L(qacc); dbg[D_QFRCC + l] = L(qfrc_con); }
+      for (int r = l; r < nefc; r += 32) dbg[D_EFC_F + r] = efc[E_F * NEFC + r];
+      if (l == 0) { dbg[D_COUNTS] = (real)nefc; dbg[D_COUNTS + 1] = (real)ncon_used; dbg[D_COUNTS + 2] = (real)nlim; dbg[D_COUNTS + 3] = (real)iters; }
+    ENDL
+  }
+
+  // ================= sensors (mj_sensorPos / Vel / Acc for the Cassie layout) =================
+  real *cst = sm + S_CST;
+  LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc); } ENDL
+  LANES
+    if (l < 16) cst[CS_SENSOR + l] = cm.enc_scale[l] * qpos[cm.enc_qposadr[l]];   // actuatorpos = gear * q, jointpos = q
+    if (l < cm.nu) cst[CS_ACTVEL + l] = cm.act_gear[l] * vecs[cm.act_dof[l]];
+    if (l == 16) {  // IMU: framequat, gyro, accelerometer, magnetometer on site `imu`
+      const int b = cm.imu_body; real q[4], Rs[9], sp[3], v[3];
+      mul_quat(q, xquat + 4 * b, cm.imu_quat);
+      for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Rs[3 * a + c] = xmat[9 * b + 3 * a] * cm.imu_mat[c] + xmat[9 * b + 3 * a + 1] * cm.imu_mat[3 + c] + xmat[9 * b + 3 * a + 2] * cm.imu_mat[6 + c];
+      mat_vec(v, xmat + 9 * b, cm.imu_pos); sp[0] = xpos[3 * b] + v[0]; sp[1] = xpos[3 * b + 1] + v[1]; sp[2] = xpos[3 * b + 2] + v[2];
+      real dif[3] = {sp[0] - L(com0), sp[1] - L(com1), sp[2] - L(com2)};
+      // body spatial velocity / acceleration in the c-frame: chain sums over the body's dofs
+      real cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, -cm.gravity[0], -cm.gravity[1], -cm.gravity[2]};
+      for (int a = cm.body_lastdof[b]; a >= 0; a = cm.dof_parent[a]) for (int k = 0; k < 6; ++k) { cv[k] += cdof[6 * a + k] * vecs[a]; ca[k] += cdofd[6 * a + k] * vecs[a] + cdof[6 * a + k] * vecs[32 + a]; }
+      real t3[3], vl[3], al[3], lw[3], lv[3], la[3], corr[3];
+      cross3(t3, dif, cv); vl[0] = cv[3] - t3[0]; vl[1] = cv[4] - t3[1]; vl[2] = cv[5] - t3[2];
+      cross3(t3, dif, ca); al[0] = ca[3] - t3[0]; al[1] = ca[4] - t3[1]; al[2] = ca[5] - t3[2];
+      matT_vec(lw, Rs, cv); matT_vec(lv, Rs, vl); matT_vec(la, Rs, al); cross3(corr, lw, lv);
+      for (int k = 0; k < 4; ++k) cst[CS_SENSOR + 16 + k] = q[k];
+      for (int k = 0; k < 3; ++k) {
+        real g = lw[k], a = la[k] + corr[k];
+        if (cm.gyro_cutoff > 0) g = clampr(g, -cm.gyro_cutoff, cm.gyro_cutoff);
+        if (cm.accel_cutoff > 0) a = clampr(a, -cm.accel_cutoff, cm.accel_cutoff);
+        cst[CS_SENSOR + 20 + k] = g; cst[CS_SENSOR + 23 + k] = a;
+      }
+      real mg[3]; matT_vec(mg, Rs, cm.magnetic);
+      for (int k = 0; k < 3; ++k) cst[CS_SENSOR + 26 + k] = mg[k];
+    }
+  ENDL
+  if (dbg) { LANES if (l < 29) dbg[D_SENS + l] = cst[CS_SENSOR + l]; ENDL }
+
+  if (!advance) return;   // mj_forward only (used once at init / reset to populate sensordata, src/cassiemujoco.c:1029)
+  // ================= Euler with implicit joint damping (mj_Euler) + mj_advance =================
+  LANES  // MhB = M + h diag(damping), refactor in the qLD buffer
+    for (int a = l; a < cm.nM; a += 32) qLD[a] = qM[a];
+  ENDL
+  LANES if (l < nv) qLD[cm.dof_Madr[l]] += cm.timestep * cm.dof_damping[l]; ENDL
+  factor_ld(cm, sm);
+  LV(real, a);
+  LANES L(a) = (l < nv) ? L(qfrc_smooth) + L(qfrc_con) : real(0); ENDL
+  solve_m(cm, sm, a);
+  LANES if (l < nv) { L(qvel) += cm.timestep * L(a); vecs[l] = L(qvel); L(qacc_ws) = L(qacc); } ENDL
+  LANES  // lane = joint: integrate positions with the NEW velocity
+    if (l < cm.njnt) {
+      const int t = cm.jnt_type[l], qa = cm.jnt_qposadr[l], da = cm.jnt_dofadr[l]; const real h = cm.timestep;
+      if (t >= 2) qpos[qa] += h * vecs[da];
+      else if (t == 1) {
+        real wv[3] = {vecs[da], vecs[da + 1], vecs[da + 2]}, q[4] = {qpos[qa], qpos[qa + 1], qpos[qa + 2], qpos[qa + 3]}, qr[4], s, c;
+        const real ang = h * normalize3(wv);
+        msincos(real(0.5) * ang, &s, &c); qr[0] = c; qr[1] = wv[0] * s; qr[2] = wv[1] * s; qr[3] = wv[2] * s;
+        if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
+        normalize4(q); mul_quat(q, q, qr);
+        qpos[qa] = q[0]; qpos[qa + 1] = q[1]; qpos[qa + 2] = q[2]; qpos[qa + 3] = q[3];
+      }
+    }
+    if (l == 0) cst[CS_TIME] += cm.timestep;
+  ENDL
+}
+
+// ------------------------------------------------------------------ one control tick (cassie_sim_step_pd)
+// soft-limit tables of the safety layer (cassie_core_sim_step), degrees; left leg then right leg
+template <typename real> CFN real core_lo_deg(int i) { const real t[10] = {-15, -22, -50, -156, -140, -20, -22, -50, -156, -140}; return t[i]; }
+template <typename real> CFN real core_hi_deg(int i) { const real t[10] = {20, 22, 80, -42, -35, 15, 22, 80, -42, -35}; return t[i]; }
+template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 1200, 1200, 100}; return t[k]; }
+template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
+
+template <typename real>
+CFN void step_env(const DevModel<real> &cm, real *sm, int *ism, LP(real, qvel), LP(real, qacc_ws), const real *pd, const real *xfrc, real *obs,
+                  int nticks, real *dbg, int *counters) {
+  DECL_LANE
+  real *cst = sm + S_CST, *vecs = sm + S_VEC;
+  LV(real, ctrl); LV(real, tq); LV(real, scale_part);
+  for (int tick = 0; tick < nticks; ++tick) {
+    // ---- pd_input_step (motor-PD branch) + cassie_core_sim_step, lane = motor; both read LAST tick's cassie_out
+    const real W = real(0.15), DEG = real(0.017453292519943295);
+    LANES
+      L(tq) = 0; L(scale_part) = 1;
+      if (l < 10) {
+        const real pos = cst[CS_DPOS + l], vel = cst[CS_DVEL + l]; const int k = l % 5;
+        const real u = pd[l] + pd[30 + l] * (pd[10 + l] - pos) + pd[40 + l] * (pd[20 + l] - vel);
+        real add = 0, sc = 1;
+        const real dhi = pos - (core_hi_deg<real>(l) * DEG - W), dlo = (core_lo_deg<real>(l) * DEG + W) - pos;
+        if (dhi > 0) { add -= core_K<real>(k) * dhi * (1 + dhi / W) + core_C<real>(k) * mmin(dhi / W, real(1)) * vel; sc *= mmax(real(0), 1 - dhi / W); }
+        if (dlo > 0) { add += core_K<real>(k) * dlo * (1 + dlo / W) - core_C<real>(k) * mmin(dlo / W, real(1)) * vel; sc *= mmax(real(0), 1 - dlo / W); }
+        if (k == 2 || k == 3) {  // coupled row hipPitch + knee >= -135 deg, evaluated by both lanes of the pair
+          const int a = l - k + 2; const real dsum = -135 * DEG - (cst[CS_DPOS + a] + cst[CS_DPOS + a + 1]);
+          if (dsum > 0) { add += 1200 * dsum * (1 + dsum / W) - 36 * mmin(dsum / W, real(1)) * vel; if (k == 2) sc *= mmax(real(0), 1 - dsum / W); }
+        }
+        L(tq) = u; L(ctrl) = add; L(scale_part) = sc;
+      }
+    ENDL
+    // product of the per-row scale factors over all 10 motors (log-free: multiply through shared memory)
+    LANES vecs[l] = L(scale_part); ENDL
+    LANES
+      if (l < 10) {
+        real sc = 1; for (int i = 0; i < 10; ++i) sc *= vecs[i];
+        const bool sto = !(cst[CS_STO] >= 1);
+        real t = sto ? real(0) : L(tq) * sc + L(ctrl);
+        const real lim = cm.act_torque_limit[l];
+        t = clampr(t, -lim, lim);
+        // ---- motor(): torque-speed curve, STO, 6-tick delay line (src/cassiemujoco.c:638-664)
+        const real ratio = cm.act_gear[l], tmax = cm.act_ctrl_hi[l], w = cst[CS_ACTVEL + l];
+        real tlim = 2 * tmax * (1 - mabs(w) / cm.act_wmax[l]); tlim = mmax(mmin(tlim, tmax), real(0));
+        if (sto) t = 0;
+        real tau = mmin(mabs(t / ratio), tlim); if (t < 0) tau = -tau;
+        real *dl = cst + CS_DELAY + 6 * l;
+        const real c = dl[5];
+        for (int k = 5; k > 0; --k) dl[k] = dl[k - 1];
+        dl[0] = tau;
+        L(ctrl) = c;
+        cst[CS_DTORQUE + l] = c * ratio;
+      } else L(ctrl) = 0;
+    ENDL
+    // ---- cassie_sensor_data(): encoders + filters from the sensordata of the PREVIOUS physics step (:737-774)
+    LANES
+      if (l < 10) {  // drive encoder, integer FIR (:558-593)
+        const int s = l < 5 ? l : l + 3, bits = cm.enc_bits[s]; int *x = ism + 9 * l;
+        const double TWO_PI = 6.283185307179586;
+        const int enc = (int)((double)cst[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
+        const double scale = TWO_PI / (double)(1 << bits) / (double)cm.act_gear[l];
+        cst[CS_DPOS + l] = (real)(enc * scale);
+        bool allzero = true; for (int k = 0; k < 9; ++k) allzero &= (x[k] == 0);
+        if (allzero) for (int k = 0; k < 9; ++k) x[k] = enc;
+        for (int k = 8; k > 0; --k) x[k] = x[k - 1];
+        x[0] = enc;
+        const int b[9] = {2727, 534, -2658, -795, 72, 110, 19, -6, -3};
+        int y = 0; for (int k = 0; k < 9; ++k) y += x[k] * b[k];
+        cst[CS_DVEL + l] = (real)(y * scale / 3.141592653589793);
+      } else if (l < 16) {  // joint encoder, IIR (:596-635)
+        const int i = l - 10, s = i < 3 ? 5 + i : 10 + i, bits = cm.enc_bits[s]; real *x = cst + CS_JFX + 4 * i, *y = cst + CS_JFY + 3 * i;
+        const double TWO_PI = 6.283185307179586;
+        const int enc = (int)((double)cst[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
+        const real p = (real)(enc * (TWO_PI / (double)(1 << bits)));
+        cst[CS_JPOS + i] = p;
+        bool allzero = true; for (int k = 0; k < 4; ++k) allzero &= (x[k] == 0);
+        if (allzero) for (int k = 0; k < 4; ++k) x[k] = p;
+        for (int k = 3; k > 0; --k) x[k] = x[k - 1];
+        x[0] = p;
+        for (int k = 2; k > 0; --k) y[k] = y[k - 1];
+        real y0 = real(12.348) * (x[0] + x[1] - x[2] - x[3]);
+        y0 -= y[1] * real(-1.7658) + y[2] * real(0.79045);
+        y[0] = y0; cst[CS_JVEL + i] = y0;
+      }
+    ENDL
+    // ---- *y = cassie_out (:1127): the observation of this tick
+    if (obs && tick == nticks - 1) {
+      LANES
+        if (l < 10) { obs[OB_MPOS + l] = cst[CS_DPOS + l]; obs[OB_MVEL + l] = cst[CS_DVEL + l]; obs[OB_MTORQUE + l] = cst[CS_DTORQUE + l]; }
+        if (l < 6) { obs[OB_JPOS + l] = cst[CS_JPOS + l]; obs[OB_JVEL + l] = cst[CS_JVEL + l]; }
+        if (l < 13) obs[OB_QUAT + l] = cst[CS_SENSOR + 16 + l];
+        if (l == 13) obs[OB_TIME] = cst[CS_TIME];
+      ENDL
+    }
+    // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
+    for (int s = 0; s < cm.nsub; ++s) mj_substep(cm, sm, qvel, qacc_ws, ctrl, xfrc, (tick == nticks - 1 && s == cm.nsub - 1) ? dbg : (real *)0, counters, true);
+  }
+}
+
+// mj_forward on the current state with zero ctrl: fills sensordata / actuator_velocity (cassie_sim_init, :1029)
+template <typename real>
+CFN void forward_env(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real, qacc_ws), const real *xfrc, real *dbg, int *counters) {
+  DECL_LANE
+  LV(real, ctrl);
+  LANES L(ctrl) = 0; ENDL
+  mj_substep(cm, sm, qvel, qacc_ws, ctrl, xfrc, dbg, counters, false);
+}
+
+}  // namespace cassie

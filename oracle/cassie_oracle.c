@@ -445,15 +445,10 @@ static int col_capsule_capsule(const OModel *m, const OData *d, OContact *c, int
     for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
     return raw_sphere_sphere(c, margin, v1, r1, v2, r2);
   }
-  /* parallel axes: test the segment ends of 1 against 2, then of 2 against 1; keep at most 2 */
+  /* parallel axes: the segment ends of 1 against 2 (at most 2 contacts) */
   int n = 0;
   for (int e = 0; e < 2 && n < 2; e++) {
     double x1 = e ? -s1 : s1, x2 = clampd((v - mb * x1) / mc, -s2, s2);
-    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
-    n += raw_sphere_sphere(c + n, margin, v1, r1, v2, r2);
-  }
-  for (int e = 0; e < 2 && n < 2; e++) {
-    double x2 = e ? -s2 : s2, x1 = clampd((u - mb * x2) / ma, -s1, s1);
     for (int k = 0; k < 3; k++) { v1[k] = p1[k] + a1[k] * x1; v2[k] = p2[k] + a2[k] * x2; }
     n += raw_sphere_sphere(c + n, margin, v1, r1, v2, r2);
   }

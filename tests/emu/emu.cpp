@@ -1,0 +1,70 @@
+// emu.cpp -- TEST-ONLY host execution of the product's stepper source (cassie-mujoco-sim_b200/csrc/step_core.inl compiled with
+// -DCASSIE_EMU: every warp phase becomes a loop over 32 lanes).  It exists so the kernel logic can be diffed against the oracle
+// on a machine without a GPU.  It is never linked into, loaded by, or reachable from the product library.
+#define CASSIE_EMU 1
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../cassie-mujoco-sim_b200/csrc/devbuild.h"
+#include "../../cassie-mujoco-sim_b200/csrc/step_core.inl"
+
+using namespace cassie;
+
+template <typename real> struct Emu {
+  HostModel hm; DevModel<real> dm; std::vector<real> sm; std::vector<int> ism;
+  real qvel[32], qacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE]; int counters[8];
+  bool init(const char *path, std::string &err) {
+    if (!load_model_any(path, hm, err)) return false;
+    if (!build_dev_model(hm, dm, err)) return false;
+    sm.assign(S_REALS, 0); ism.assign(S_INTS, 0);
+    std::vector<real> qpos(QPOS_W);
+    init_env_rows(hm, qpos.data(), qvel, qacc_ws, sm.data() + S_CST, ism.data(), xfrc);
+    for (int i = 0; i < QPOS_W; i++) sm[S_QPOS + i] = qpos[i];
+    std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters);
+    forward();
+    return true;
+  }
+  void forward() { forward_env(dm, sm.data(), qvel, qacc_ws, xfrc, dbg, counters); }
+  void step(int nticks) { step_env(dm, sm.data(), ism.data(), qvel, qacc_ws, pd, xfrc, obs, nticks, dbg, counters); }
+};
+
+struct Handle { int fp32; Emu<float> f; Emu<double> d; };
+
+extern "C" {
+void *emu_new(const char *path, int fp32) {
+  Handle *h = new Handle(); h->fp32 = fp32; std::string err;
+  bool ok = fp32 ? h->f.init(path, err) : h->d.init(path, err);
+  if (!ok) { fprintf(stderr, "emu: %s\n", err.c_str()); delete h; return nullptr; }
+  return h;
+}
+void emu_free(void *p) { delete (Handle *)p; }
+void emu_step(void *p, const double *pd50, int nticks) {
+  Handle *h = (Handle *)p;
+  if (h->fp32) { for (int i = 0; i < 50; i++) h->f.pd[i] = (float)pd50[i]; h->f.step(nticks); }
+  else { for (int i = 0; i < 50; i++) h->d.pd[i] = pd50[i]; h->d.step(nticks); }
+}
+void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward(); else h->d.forward(); }
+// generic get/set of named state as doubles.  names: qpos qvel qacc_ws cst obs dbg xfrc ; ints: dfilt counters
+int emu_get(void *p, const char *name, double *out, int n) {
+  Handle *h = (Handle *)p; std::string k(name);
+#define GET(T, E) { const T *src = nullptr; int cnt = 0; \
+  if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
+  else if (k == "cst") { src = E.sm.data() + S_CST; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
+  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } \
+  if (src) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) out[i] = (double)src[i]; return cnt; } \
+  if (k == "dfilt") { int c2 = DFILT_W < n ? DFILT_W : n; for (int i = 0; i < c2; i++) out[i] = E.ism[i]; return c2; } \
+  if (k == "counters") { int c2 = 8 < n ? 8 : n; for (int i = 0; i < c2; i++) out[i] = E.counters[i]; return c2; } }
+  if (h->fp32) GET(float, h->f) else GET(double, h->d)
+  return -1;
+}
+int emu_set(void *p, const char *name, const double *in, int n) {
+  Handle *h = (Handle *)p; std::string k(name);
+#define SET(T, E) { T *dst = nullptr; int cnt = 0; \
+  if (k == "qpos") { dst = E.sm.data() + S_QPOS; cnt = QPOS_W; } else if (k == "qvel") { dst = E.qvel; cnt = 32; } else if (k == "qacc_ws") { dst = E.qacc_ws; cnt = 32; } \
+  else if (k == "cst") { dst = E.sm.data() + S_CST; cnt = CST_W; } else if (k == "xfrc") { dst = E.xfrc; cnt = XFRC_W; } \
+  if (dst) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) dst[i] = (T)in[i]; return cnt; } }
+  if (h->fp32) SET(float, h->f) else SET(double, h->d)
+  return -1;
+}
+}

@@ -1,0 +1,67 @@
+"""ctypes wrapper of the TEST-ONLY host emulation of the product stepper (tests/emu/emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+CSRC = os.path.join(REPO, 'cassie-mujoco-sim_b200', 'csrc')
+LIB = os.path.join(HERE, 'emu', '_build', 'libcassie_emu.so')
+
+# debug-dump offsets (devmodel.h)
+D = dict(XPOS=0, XQUAT=96, CDOF=224, QM=416, QLD=736, BIAS=1056, PASSIVE=1088, SMOOTH=1120, QACCS=1152, QACC=1184, QFRCC=1216,
+         COUNTS=1248, EFC_B=1252, EFC_F=1316, EFC_R=1380, EFC_AREF=1444, SENS=1508, J=1540, SIZE=3600)
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, 'emu', 'emu.cpp'), os.path.join(CSRC, 'mjcf.cpp'), os.path.join(CSRC, 'step_core.inl'),
+            os.path.join(CSRC, 'devmodel.h'), os.path.join(CSRC, 'devbuild.h'), os.path.join(CSRC, 'model.h')]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.check_call(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-o', LIB, srcs[0], srcs[1]])
+
+
+def load():
+    build()
+    L = C.CDLL(LIB)
+    L.emu_new.restype = C.c_void_p
+    L.emu_new.argtypes = [C.c_char_p, C.c_int]
+    L.emu_free.argtypes = [C.c_void_p]
+    L.emu_step.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    L.emu_forward.argtypes = [C.c_void_p]
+    L.emu_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+    L.emu_set.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+    return L
+
+
+class EmuSim:
+    def __init__(self, model_path, fp32=False):
+        self.L = load()
+        self.h = self.L.emu_new(model_path.encode(), 1 if fp32 else 0)
+        if not self.h:
+            raise RuntimeError('emu could not load ' + model_path)
+
+    def close(self):
+        if self.h:
+            self.L.emu_free(self.h)
+            self.h = None
+
+    def get(self, name, n=4096):
+        buf = np.zeros(n)
+        k = self.L.emu_get(self.h, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_double)), n)
+        assert k >= 0, name
+        return buf[:k]
+
+    def set(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        assert self.L.emu_set(self.h, name.encode(), a.ctypes.data_as(C.POINTER(C.c_double)), a.size) >= 0
+
+    def step(self, pd50, nticks=1):
+        a = np.ascontiguousarray(pd50, dtype=np.float64)
+        assert a.size == 50
+        self.L.emu_step(self.h, a.ctypes.data_as(C.POINTER(C.c_double)), nticks)
+
+    def forward(self):
+        self.L.emu_forward(self.h)
