@@ -1,0 +1,348 @@
+"""cassie-mujoco-sim_b200 -- Python host side of the B200-native batched Cassie stepper.
+
+Mirrors the reference's Python surface for the one path this repo accelerates
+(/root/reference/example/cassiemujoco.py:31-173: CassieSim.step_pd / qpos / qvel / set_qpos / apply_force ...)
+on top of the C-ABI in include/cassie_b200.h, and adds CassieBatch for the batched entry points.
+There is no CPU fallback: loading fails loudly if the CUDA library is missing, and cassie_batch_init fails if no GPU is visible.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcassie_b200.so')
+MODEL_DIR = os.path.join(_HERE, 'models')
+FP32, FP64 = 0, 1
+PD_WIDTH, OBS_WIDTH = 52, 64
+# observation row layout (cassie_batch_get_obs)
+OBS = dict(motor_pos=slice(0, 10), motor_vel=slice(10, 20), motor_torque=slice(20, 30), joint_pos=slice(30, 36), joint_vel=slice(36, 42),
+           quat=slice(42, 46), gyro=slice(46, 49), accel=slice(49, 52), mag=slice(52, 55), time=55)
+
+
+# ---------------------------------------------------------------- ctypes mirrors of the bus structs (include/cassie_bus.h)
+class pd_motor_in_t(C.Structure):
+    _fields_ = [(n, C.c_double * 5) for n in ('torque', 'pTarget', 'dTarget', 'pGain', 'dGain')]
+
+
+class pd_task_in_t(C.Structure):
+    _fields_ = [(n, C.c_double * 6) for n in ('torque', 'pTarget', 'dTarget', 'pGain', 'dGain')]
+
+
+class pd_leg_in_t(C.Structure):
+    _fields_ = [('taskPd', pd_task_in_t), ('motorPd', pd_motor_in_t)]
+
+
+class pd_in_t(C.Structure):
+    _fields_ = [('leftLeg', pd_leg_in_t), ('rightLeg', pd_leg_in_t), ('telemetry', C.c_double * 9)]
+
+
+class state_battery_out_t(C.Structure):
+    _fields_ = [('stateOfCharge', C.c_double), ('current', C.c_double)]
+
+
+class state_foot_out_t(C.Structure):
+    _fields_ = [('position', C.c_double * 3), ('orientation', C.c_double * 4), ('footRotationalVelocity', C.c_double * 3),
+                ('footTranslationalVelocity', C.c_double * 3), ('toeForce', C.c_double * 3), ('heelForce', C.c_double * 3)]
+
+
+class state_joint_out_t(C.Structure):
+    _fields_ = [('position', C.c_double * 6), ('velocity', C.c_double * 6)]
+
+
+class state_motor_out_t(C.Structure):
+    _fields_ = [('position', C.c_double * 10), ('velocity', C.c_double * 10), ('torque', C.c_double * 10)]
+
+
+class state_pelvis_out_t(C.Structure):
+    _fields_ = [('position', C.c_double * 3), ('orientation', C.c_double * 4), ('rotationalVelocity', C.c_double * 3),
+                ('translationalVelocity', C.c_double * 3), ('translationalAcceleration', C.c_double * 3),
+                ('externalMoment', C.c_double * 3), ('externalForce', C.c_double * 3)]
+
+
+class state_radio_out_t(C.Structure):
+    _fields_ = [('channel', C.c_double * 16), ('signalGood', C.c_bool)]
+
+
+class state_terrain_out_t(C.Structure):
+    _fields_ = [('height', C.c_double), ('slope', C.c_double * 2)]
+
+
+class state_out_t(C.Structure):
+    _fields_ = [('pelvis', state_pelvis_out_t), ('leftFoot', state_foot_out_t), ('rightFoot', state_foot_out_t),
+                ('terrain', state_terrain_out_t), ('motor', state_motor_out_t), ('joint', state_joint_out_t),
+                ('radio', state_radio_out_t), ('battery', state_battery_out_t)]
+
+
+assert C.sizeof(pd_in_t) == 952 and C.sizeof(state_out_t) == 992
+
+_lib = None
+
+
+def build(force=False, verbose=False):
+    """compile libcassie_b200.so in-tree (nvcc, sm_100a)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('_cassie_b200_build', os.path.join(_HERE, 'build.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+def lib():
+    """the loaded C-ABI library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('libcassie_b200.so is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). '
+                           'The batched stepper has no CPU fallback.')
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cd = C.c_void_p, C.c_int, C.POINTER(C.c_double)
+    L.cassie_b200_last_error.restype = C.c_char_p
+    L.cassie_batch_init.restype = vp
+    L.cassie_batch_init.argtypes = [C.c_char_p, ci, ci, ci]
+    L.cassie_batch_free.argtypes = [vp]
+    for n in ('cassie_batch_nenv', 'cassie_batch_nq', 'cassie_batch_nv', 'cassie_batch_precision'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = ci
+    L.cassie_batch_launch_count.argtypes = [vp]
+    L.cassie_batch_launch_count.restype = C.c_long
+    L.cassie_batch_reset.argtypes = [vp, C.c_void_p]
+    L.cassie_sim_step_pd_batch.argtypes = [vp, C.c_void_p, C.c_void_p]
+    L.cassie_batch_set_pd.argtypes = [vp, cd]
+    L.cassie_batch_step.argtypes = [vp, ci]
+    for n in ('cassie_batch_sync', 'cassie_batch_forward', 'cassie_batch_clear_forces', 'cassie_batch_integrate_pos'):
+        getattr(L, n).argtypes = [vp]
+    for n in ('cassie_batch_get_qpos', 'cassie_batch_set_qpos', 'cassie_batch_get_qvel', 'cassie_batch_set_qvel', 'cassie_batch_get_time',
+              'cassie_batch_get_obs'):
+        getattr(L, n).argtypes = [vp, cd]
+    L.cassie_batch_apply_force.argtypes = [vp, cd, C.c_char_p]
+    L.cassie_batch_apply_force.restype = ci
+    L.cassie_batch_device_ptr.argtypes = [vp, C.c_char_p]
+    L.cassie_batch_device_ptr.restype = vp
+    L.cassie_batch_set_stream.argtypes = [vp, vp]
+    L.cassie_batch_get_stream.argtypes = [vp]
+    L.cassie_batch_get_stream.restype = vp
+    L.cassie_batch_get_counters.argtypes = [vp, C.POINTER(ci)]
+    L.cassie_batch_debug_dump.argtypes = [vp, ci, cd, ci]
+    L.cassie_batch_debug_dump.restype = ci
+    # legacy verbs
+    L.cassie_mujoco_init.argtypes = [C.c_char_p]
+    L.cassie_mujoco_init.restype = C.c_bool
+    L.cassie_sim_init.argtypes = [C.c_char_p, C.c_bool]
+    L.cassie_sim_init.restype = vp
+    L.cassie_sim_free.argtypes = [vp]
+    L.cassie_sim_step_pd.argtypes = [vp, C.POINTER(state_out_t), C.POINTER(pd_in_t)]
+    for n in ('cassie_sim_time', 'cassie_sim_qpos', 'cassie_sim_qvel'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = cd
+    for n in ('cassie_sim_nv', 'cassie_sim_nq'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = ci
+    L.cassie_sim_apply_force.argtypes = [vp, cd, C.c_char_p]
+    L.cassie_sim_clear_forces.argtypes = [vp]
+    L.cassie_sim_full_reset.argtypes = [vp]
+    L.cassie_sim_radio.argtypes = [vp, cd]
+    _lib = L
+    return L
+
+
+def model_path(name='cassie'):
+    """compiled model table shipped with the package (used where the reference's MJCF checkout is absent)."""
+    return os.path.join(MODEL_DIR, name + '.cmodel')
+
+
+def pd_rows(n, torque=None, pTarget=None, dTarget=None, pGain=None, dGain=None):
+    """[n][52] compact motor-PD rows from 10-vectors (broadcast over envs) or [n][10] arrays."""
+    rows = np.zeros((n, PD_WIDTH))
+    for k, v in enumerate((torque, pTarget, dTarget, pGain, dGain)):
+        if v is not None:
+            rows[:, 10 * k:10 * k + 10] = np.asarray(v, dtype=np.float64)
+    return rows
+
+
+def _last_error():
+    return lib().cassie_b200_last_error().decode()
+
+
+class CassieBatch:
+    """n_env independent Cassie simulators advanced in lock-step on one GPU."""
+
+    def __init__(self, n_env, modelfile=None, device=0, precision=FP32):
+        self.L = lib()
+        self.n = int(n_env)
+        path = modelfile or model_path()
+        self.h = self.L.cassie_batch_init(path.encode(), self.n, int(device), int(precision))
+        if not self.h:
+            raise RuntimeError('cassie_batch_init failed: ' + _last_error())
+        self.nq, self.nv = self.L.cassie_batch_nq(self.h), self.L.cassie_batch_nv(self.h)
+        self.precision = precision
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.cassie_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    # ---- stepping
+    def set_pd(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        assert rows.shape == (self.n, PD_WIDTH)
+        self.L.cassie_batch_set_pd(self.h, self._dp(rows))
+
+    def step(self, nticks=1):
+        self.L.cassie_batch_step(self.h, int(nticks))
+
+    def sync(self):
+        self.L.cassie_batch_sync(self.h)
+
+    def step_pd(self, pd_in_array, want_state=True):
+        """AoS compatibility path: (pd_in_t * n) in, (state_out_t * n) out (cassie_sim_step_pd_batch)."""
+        out = (state_out_t * self.n)() if want_state else None
+        self.L.cassie_sim_step_pd_batch(self.h, C.byref(pd_in_array), C.byref(out) if want_state else None)
+        return out
+
+    def reset(self, mask=None):
+        if mask is None:
+            self.L.cassie_batch_reset(self.h, None)
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            self.L.cassie_batch_reset(self.h, m.ctypes.data_as(C.c_void_p))
+
+    def forward(self):
+        self.L.cassie_batch_forward(self.h)
+
+    def integrate_pos(self):
+        self.L.cassie_batch_integrate_pos(self.h)
+
+    # ---- state
+    def _get(self, fn, w):
+        out = np.zeros((self.n, w))
+        fn(self.h, self._dp(out))
+        return out
+
+    def qpos(self):
+        return self._get(self.L.cassie_batch_get_qpos, self.nq)
+
+    def qvel(self):
+        return self._get(self.L.cassie_batch_get_qvel, self.nv)
+
+    def time(self):
+        return self._get(self.L.cassie_batch_get_time, 1)[:, 0]
+
+    def obs(self):
+        return self._get(self.L.cassie_batch_get_obs, OBS_WIDTH)
+
+    def set_qpos(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape == (self.n, self.nq)
+        self.L.cassie_batch_set_qpos(self.h, self._dp(q))
+
+    def set_qvel(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.shape == (self.n, self.nv)
+        self.L.cassie_batch_set_qvel(self.h, self._dp(v))
+
+    def apply_force(self, xfrc, body_name='cassie-pelvis'):
+        x = np.ascontiguousarray(np.broadcast_to(np.asarray(xfrc, dtype=np.float64), (self.n, 6)))
+        return self.L.cassie_batch_apply_force(self.h, self._dp(x), body_name.encode())
+
+    def clear_forces(self):
+        self.L.cassie_batch_clear_forces(self.h)
+
+    def counters(self):
+        out = np.zeros((self.n, 8), dtype=np.int32)
+        self.L.cassie_batch_get_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
+    def debug_dump(self, env=0):
+        out = np.zeros(3600)
+        k = self.L.cassie_batch_debug_dump(self.h, env, self._dp(out), out.size)
+        return out if k > 0 else None
+
+    def launch_count(self):
+        return int(self.L.cassie_batch_launch_count(self.h))
+
+    def device_ptr(self, field):
+        return self.L.cassie_batch_device_ptr(self.h, field.encode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self.L.cassie_batch_set_stream(self.h, C.c_void_p(cuda_stream_ptr))
+
+    def torch_view(self, field):
+        """zero-copy torch tensor over a device state array (qpos [n,36], qvel [n,32], pd [n,52], obs [n,64])."""
+        import torch
+        width = dict(qpos=36, qvel=32, pd=PD_WIDTH, obs=OBS_WIDTH, xfrc=8)[field]
+        dt, isz, ts = (np.float32, 4, '<f4') if self.precision == FP32 else (np.float64, 8, '<f8')
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = dict(shape=(self.n, width), typestr=ts, data=(self.device_ptr(field), False), version=2)
+        return torch.as_tensor(a, device='cuda')
+
+
+class CassieSim:
+    """Legacy single-environment object (reference: example/cassiemujoco.py:31-173), stepped by the same CUDA kernels."""
+
+    def __init__(self, modelfile=None, reinit=False):
+        self.L = lib()
+        path = modelfile or model_path()
+        self.c = self.L.cassie_sim_init(path.encode(), bool(reinit))
+        if not self.c:
+            raise RuntimeError('cassie_sim_init failed: ' + _last_error())
+        self.nq, self.nv = self.L.cassie_sim_nq(self.c), self.L.cassie_sim_nv(self.c)
+
+    def step_pd(self, u):
+        y = state_out_t()
+        self.L.cassie_sim_step_pd(self.c, C.byref(y), C.byref(u))
+        return y
+
+    def time(self):
+        return self.L.cassie_sim_time(self.c)[0]
+
+    def qpos(self):
+        return np.array(self.L.cassie_sim_qpos(self.c)[:self.nq])
+
+    def qvel(self):
+        return np.array(self.L.cassie_sim_qvel(self.c)[:self.nv])
+
+    def set_time(self, t):
+        self.L.cassie_sim_time(self.c)[0] = t
+
+    def set_qpos(self, qpos):
+        p = self.L.cassie_sim_qpos(self.c)
+        for i in range(min(len(qpos), self.nq)):
+            p[i] = qpos[i]
+
+    def set_qvel(self, qvel):
+        p = self.L.cassie_sim_qvel(self.c)
+        for i in range(min(len(qvel), self.nv)):
+            p[i] = qvel[i]
+
+    def apply_force(self, xfrc, body_name='cassie-pelvis'):
+        a = (C.c_double * 6)(*[float(x) for x in xfrc])
+        self.L.cassie_sim_apply_force(self.c, a, body_name.encode())
+
+    def clear_forces(self):
+        self.L.cassie_sim_clear_forces(self.c)
+
+    def full_reset(self):
+        self.L.cassie_sim_full_reset(self.c)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'c', None):
+                self.L.cassie_sim_free(self.c)
+                self.c = None
+        except Exception:
+            pass

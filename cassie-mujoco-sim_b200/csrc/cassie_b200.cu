@@ -1,0 +1,409 @@
+// cassie_b200.cu -- CUDA kernels (sm_100a) and the C-ABI of the batched Cassie stepper.  See include/cassie_b200.h.
+//
+// Kernel shape: one warp per environment; a CTA of WPB warps first stages the model constant block into shared memory with
+// a TMA bulk copy (cp.async.bulk + mbarrier, SASS: UBLKCP), then every warp loads its environment's state rows from HBM
+// (coalesced, one row per array), advances `nticks` control ticks entirely on chip (step_core.inl) and writes the rows back.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cassie_b200.h"
+#include "devbuild.h"
+#include "step_core.inl"
+
+namespace cassie {
+
+static thread_local std::string g_err;
+static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b200: %s\n", e.c_str()); }
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
+
+template <typename real> struct EnvArrays {
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg; int *dfilt, *counters; int n;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy; all threads of the CTA return after it landed
+__device__ __forceinline__ void tma_stage(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  const uint32_t bar_a = smem_u32(bar), dst_a = smem_u32(dst_smem);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a), "l"(src_gmem), "r"(bytes), "r"(bar_a) : "memory");
+  }
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(bar_a), "r"(0) : "memory");
+}
+
+template <typename real> __host__ __device__ constexpr size_t model_bytes() { return (sizeof(DevModel<real>) + 127) / 128 * 128; }
+template <typename real> __host__ __device__ constexpr size_t warp_bytes() { return ((size_t)S_REALS * sizeof(real) + (size_t)S_INTS * sizeof(int) + 127) / 128 * 128; }
+
+template <typename real>
+__device__ __forceinline__ void load_env(const EnvArrays<real> &A, int env, real *sm, int *ism, real &qvel, real &qacc_ws) {
+  const int l = threadIdx.x & 31;
+  for (int i = l; i < QPOS_W; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * QPOS_W + i];
+  for (int i = l; i < CST_W; i += 32) sm[S_CST + i] = A.cst[(size_t)env * CST_W + i];
+  for (int i = l; i < PD_W; i += 32) sm[S_PD + i] = A.pd[(size_t)env * PD_W + i];
+  if (l < XFRC_W) sm[S_XFRC + l] = A.xfrc[(size_t)env * XFRC_W + l];
+  for (int i = l; i < DFILT_W; i += 32) ism[i] = A.dfilt[(size_t)env * DFILT_W + i];
+  qvel = A.qvel[(size_t)env * QVEL_W + l]; qacc_ws = A.qacc_ws[(size_t)env * QVEL_W + l];
+  __syncwarp();
+}
+template <typename real>
+__device__ __forceinline__ void store_env(const EnvArrays<real> &A, int env, const real *sm, const int *ism, real qvel, real qacc_ws) {
+  const int l = threadIdx.x & 31;
+  __syncwarp();
+  for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
+  for (int i = l; i < CST_W; i += 32) A.cst[(size_t)env * CST_W + i] = sm[S_CST + i];
+  for (int i = l; i < DFILT_W; i += 32) A.dfilt[(size_t)env * DFILT_W + i] = ism[i];
+  A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;
+}
+
+// mode 0: step nticks; mode 1: mj_forward only
+template <typename real>
+__global__ void __launch_bounds__(288) cassie_step_kernel(const DevModel<real> *__restrict__ gmodel, EnvArrays<real> A, int nticks, int mode) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
+  tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
+  const int warp = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= A.n) return;
+  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>());
+  int *ism = reinterpret_cast<int *>(sm + S_REALS);
+  const DevModel<real> &cm = *cmp;
+  real qvel, qacc_ws;
+  load_env(A, env, sm, ism, qvel, qacc_ws);
+  real *dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr;
+  int *counters = A.counters + (size_t)env * 8;
+  if (mode == 0) step_env(cm, sm, ism, qvel, qacc_ws, sm + S_PD, sm + S_XFRC, A.obs + (size_t)env * OBS_W, nticks, dbg, counters);
+  else forward_env(cm, sm, qvel, qacc_ws, sm + S_XFRC, dbg, counters);
+  store_env(A, env, sm, ism, qvel, qacc_ws);
+}
+
+// cassie_integrate_pos for the whole batch (mj_integratePos): the HBM-bound kernel.  One thread per (env, joint).
+template <typename real>
+__global__ void cassie_integrate_kernel(const DevModel<real> *__restrict__ gmodel, real *__restrict__ qpos, const real *__restrict__ qvel, int n) {
+  __shared__ int jt[MJ], jq[MJ], jd[MJ];
+  __shared__ int njnt; __shared__ real h;
+  if (threadIdx.x < MJ) { jt[threadIdx.x] = gmodel->jnt_type[threadIdx.x]; jq[threadIdx.x] = gmodel->jnt_qposadr[threadIdx.x]; jd[threadIdx.x] = gmodel->jnt_dofadr[threadIdx.x]; }
+  if (threadIdx.x == 0) { njnt = gmodel->njnt; h = gmodel->timestep; }
+  __syncthreads();
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = (int)(gid >> 5), j = (int)(gid & 31);
+  if (env >= n || j >= njnt) return;
+  real *q = qpos + (size_t)env * QPOS_W + jq[j]; const real *v = qvel + (size_t)env * QVEL_W + jd[j];
+  if (jt[j] >= 2) q[0] += h * v[0];
+  else if (jt[j] == 1) {
+    real wv[3] = {v[0], v[1], v[2]}, qq[4] = {q[0], q[1], q[2], q[3]}, qr[4], s, c;
+    const real ang = h * normalize3(wv);
+    msincos(real(0.5) * ang, &s, &c); qr[0] = c; qr[1] = wv[0] * s; qr[2] = wv[1] * s; qr[3] = wv[2] * s;
+    if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
+    normalize4(qq); mul_quat(qq, qq, qr);
+    q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct BatchBase {
+  virtual ~BatchBase() {}
+  HostModel hm; int n = 0, device = 0, precision = 0, wpb = 4; cudaStream_t stream = nullptr; bool own_stream = false; long launches = 0; bool debug = false;
+  virtual bool init() = 0;
+  virtual bool reset(const unsigned char *mask) = 0;
+  virtual bool set_pd(const double *pd) = 0;
+  virtual bool step(int nticks, int mode) = 0;
+  virtual bool integrate() = 0;
+  virtual bool get(const char *field, double *out) = 0;   // qpos[n][35] qvel[n][32] time[n] obs[n][64]
+  virtual bool set(const char *field, const double *in) = 0;
+  virtual bool set_xfrc(const double *xfrc, int body) = 0;
+  virtual void *dev_ptr(const char *field) = 0;
+  virtual bool get_counters(int *out) = 0;
+  virtual int debug_dump(int env, double *out, int cnt) = 0;
+  bool sync() { CUDA_OK(cudaStreamSynchronize(stream)); return true; }
+};
+
+template <typename real> struct Batch : BatchBase {
+  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0;
+  std::vector<real> h_tmp;
+  ~Batch() override {
+    cudaSetDevice(device);
+    cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
+    cudaFree(A.dfilt); cudaFree(A.counters);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+  bool init() override {
+    CUDA_OK(cudaSetDevice(device));
+    DevModel<real> *hmodel = (DevModel<real> *)calloc(1, model_bytes<real>()); std::string err; BuildInfo info;
+    if (!build_dev_model(hm, *hmodel, err, &info)) { free(hmodel); set_err(err); return false; }
+    if (info.unsupported_pairs) fprintf(stderr, "cassie_b200: note: %d candidate geom pairs involve box/hfield geoms that this build does not collide (skipped)\n", info.unsupported_pairs);
+    CUDA_OK(cudaMalloc(&d_model, model_bytes<real>()));
+    CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice)); free(hmodel);
+    A.n = n;
+    CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QPOS_W)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * QVEL_W)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * QVEL_W));
+    CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
+    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8));
+    CUDA_OK(cudaMemset(A.pd, 0, sizeof(real) * n * PD_W)); CUDA_OK(cudaMemset(A.obs, 0, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMemset(A.counters, 0, sizeof(int) * n * 8));
+    if (debug) { CUDA_OK(cudaMalloc(&A.dbg, sizeof(real) * n * D_SIZE)); CUDA_OK(cudaMemset(A.dbg, 0, sizeof(real) * n * D_SIZE)); }
+    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true;
+    // warps per CTA: as many as fit twice per SM, else once (fp64)
+    int dev_smem = 0; CUDA_OK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const char *w = getenv("CASSIE_B200_WPB");
+    wpb = w ? atoi(w) : (int)((dev_smem - model_bytes<real>()) / warp_bytes<real>());
+    if (wpb > 9) wpb = 9; if (wpb < 1) { set_err("not enough shared memory per block"); return false; }
+    if (!w && sizeof(real) == 4 && wpb >= 8) wpb = 4;   // two CTAs of 4 warps per SM
+    smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>();
+    CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return reset(nullptr);
+  }
+  bool reset(const unsigned char *mask) override {
+    CUDA_OK(cudaSetDevice(device));
+    std::vector<real> qpos(QPOS_W), qvel(QVEL_W), qa(QVEL_W), cst(CST_W), xf(XFRC_W); std::vector<int> df(DFILT_W);
+    init_env_rows(hm, qpos.data(), qvel.data(), qa.data(), cst.data(), df.data(), xf.data());
+    if (!mask) {
+      std::vector<real> buf((size_t)n * CST_W); std::vector<int> ibuf((size_t)n * DFILT_W, 0);
+      auto fill = [&](real *dst, const std::vector<real> &row, int w) -> bool { for (int e = 0; e < n; e++) memcpy(&buf[(size_t)e * w], row.data(), sizeof(real) * w); CUDA_OK(cudaMemcpyAsync(dst, buf.data(), sizeof(real) * n * w, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream)); return true; };
+      if (!fill(A.qpos, qpos, QPOS_W) || !fill(A.qvel, qvel, QVEL_W) || !fill(A.qacc_ws, qa, QVEL_W) || !fill(A.cst, cst, CST_W) || !fill(A.xfrc, xf, XFRC_W)) return false;
+      CUDA_OK(cudaMemcpyAsync(A.dfilt, ibuf.data(), sizeof(int) * n * DFILT_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+      return step(0, 1);
+    }
+    // masked reset: rewrite the selected rows, then forward everything (forward is idempotent for untouched envs except
+    // that their sensordata is refreshed from their current state, which is what mj_forward would give)
+    for (int e = 0; e < n; e++) if (mask[e]) {
+      CUDA_OK(cudaMemcpyAsync(A.qpos + (size_t)e * QPOS_W, qpos.data(), sizeof(real) * QPOS_W, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.qvel + (size_t)e * QVEL_W, qvel.data(), sizeof(real) * QVEL_W, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.qacc_ws + (size_t)e * QVEL_W, qa.data(), sizeof(real) * QVEL_W, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.cst + (size_t)e * CST_W, cst.data(), sizeof(real) * CST_W, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.xfrc + (size_t)e * XFRC_W, xf.data(), sizeof(real) * XFRC_W, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.dfilt + (size_t)e * DFILT_W, df.data(), sizeof(int) * DFILT_W, cudaMemcpyHostToDevice, stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    return step(0, 1);
+  }
+  bool set_pd(const double *pd) override {
+    h_tmp.resize((size_t)n * PD_W);
+    for (size_t i = 0; i < (size_t)n * PD_W; i++) h_tmp[i] = (real)pd[i];
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaMemcpyAsync(A.pd, h_tmp.data(), sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));   // h_tmp is pageable and reused
+    return true;
+  }
+  bool step(int nticks, int mode) override {
+    CUDA_OK(cudaSetDevice(device));
+    const int grid = (n + wpb - 1) / wpb;
+    cassie_step_kernel<real><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);
+    launches++;
+    CUDA_OK(cudaGetLastError());
+    return true;
+  }
+  bool integrate() override {
+    CUDA_OK(cudaSetDevice(device));
+    const long threads = (long)n * 32; const int bs = 256;
+    cassie_integrate_kernel<real><<<(unsigned)((threads + bs - 1) / bs), bs, 0, stream>>>(d_model, A.qpos, A.qvel, n);
+    launches++;
+    CUDA_OK(cudaGetLastError());
+    return true;
+  }
+  bool d2h(const real *src, int w, int take, int off, double *out) {
+    h_tmp.resize((size_t)n * w);
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaMemcpyAsync(h_tmp.data(), src, sizeof(real) * n * w, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    for (int e = 0; e < n; e++) for (int i = 0; i < take; i++) out[(size_t)e * take + i] = (double)h_tmp[(size_t)e * w + off + i];
+    return true;
+  }
+  bool get(const char *f, double *out) override {
+    if (!strcmp(f, "qpos")) return d2h(A.qpos, QPOS_W, hm.nq, 0, out);
+    if (!strcmp(f, "qvel")) return d2h(A.qvel, QVEL_W, hm.nv, 0, out);
+    if (!strcmp(f, "qacc_ws")) return d2h(A.qacc_ws, QVEL_W, hm.nv, 0, out);
+    if (!strcmp(f, "time")) return d2h(A.cst, CST_W, 1, CS_TIME, out);
+    if (!strcmp(f, "obs")) return d2h(A.obs, OBS_W, OBS_W, 0, out);
+    if (!strcmp(f, "cst")) return d2h(A.cst, CST_W, CST_W, 0, out);
+    set_err(std::string("unknown field ") + f); return false;
+  }
+  bool h2d(real *dst, int w, int take, int off, const double *in) {
+    h_tmp.resize((size_t)n * w);
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaMemcpyAsync(h_tmp.data(), dst, sizeof(real) * n * w, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    for (int e = 0; e < n; e++) for (int i = 0; i < take; i++) h_tmp[(size_t)e * w + off + i] = (real)in[(size_t)e * take + i];
+    CUDA_OK(cudaMemcpyAsync(dst, h_tmp.data(), sizeof(real) * n * w, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  bool set(const char *f, const double *in) override {
+    if (!strcmp(f, "qpos")) return h2d(A.qpos, QPOS_W, hm.nq, 0, in);
+    if (!strcmp(f, "qvel")) return h2d(A.qvel, QVEL_W, hm.nv, 0, in);
+    if (!strcmp(f, "time")) return h2d(A.cst, CST_W, 1, CS_TIME, in);
+    if (!strcmp(f, "sto")) return h2d(A.cst, CST_W, 1, CS_STO, in);
+    if (!strcmp(f, "cst")) return h2d(A.cst, CST_W, CST_W, 0, in);
+    set_err(std::string("unknown field ") + f); return false;
+  }
+  bool set_xfrc(const double *xfrc, int body) override {
+    h_tmp.assign((size_t)n * XFRC_W, 0);
+    if (xfrc) for (int e = 0; e < n; e++) { for (int i = 0; i < 6; i++) h_tmp[(size_t)e * XFRC_W + i] = (real)xfrc[(size_t)e * 6 + i]; h_tmp[(size_t)e * XFRC_W + 6] = (real)body; }
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaMemcpyAsync(A.xfrc, h_tmp.data(), sizeof(real) * n * XFRC_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  void *dev_ptr(const char *f) override {
+    if (!strcmp(f, "qpos")) return A.qpos; if (!strcmp(f, "qvel")) return A.qvel; if (!strcmp(f, "pd")) return A.pd; if (!strcmp(f, "obs")) return A.obs;
+    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws;
+    return nullptr;
+  }
+  bool get_counters(int *out) override {
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaMemcpyAsync(out, A.counters, sizeof(int) * n * 8, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  int debug_dump(int env, double *out, int cnt) override {
+    if (!A.dbg || env < 0 || env >= n) return -1;
+    std::vector<real> t(D_SIZE);
+    cudaSetDevice(device);
+    if (cudaMemcpyAsync(t.data(), A.dbg + (size_t)env * D_SIZE, sizeof(real) * D_SIZE, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return -1;
+    if (cnt > D_SIZE) cnt = D_SIZE;
+    for (int i = 0; i < cnt; i++) out[i] = (double)t[i];
+    return cnt;
+  }
+};
+
+}  // namespace cassie
+
+// ====================================================================== C-ABI
+using namespace cassie;
+struct cassie_batch { BatchBase *impl; std::vector<double> obs, radio; };
+struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev; };
+
+static std::mutex g_model_mutex;
+static std::string g_model_path;   // what cassie_mujoco_init cached (the reference caches the parsed model, src/cassiemujoco.c:48-59)
+
+extern "C" {
+
+const char *cassie_b200_last_error(void) { return g_err.c_str(); }
+
+cassie_batch_t *cassie_batch_init(const char *modelfile, int n_env, int device, int precision) {
+  g_err.clear();
+  if (!modelfile || n_env <= 0) { set_err("cassie_batch_init: bad arguments"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device: the batched stepper has no CPU fallback"); return nullptr; }
+  if (device < 0 || device >= ndev) { set_err("bad device index"); return nullptr; }
+  BatchBase *impl = precision == CASSIE_B200_FP64 ? (BatchBase *)new Batch<double>() : (BatchBase *)new Batch<float>();
+  std::string err;
+  if (!load_model_any(modelfile, impl->hm, err)) { set_err("Load model error: " + err); delete impl; return nullptr; }
+  impl->n = n_env; impl->device = device; impl->precision = precision; impl->debug = getenv("CASSIE_B200_DEBUG") != nullptr;
+  if (!impl->init() || !impl->sync()) { delete impl; return nullptr; }
+  cassie_batch *b = new cassie_batch(); b->impl = impl; b->radio.assign((size_t)n_env * 16, 0.0);
+  for (int e = 0; e < n_env; e++) b->radio[(size_t)e * 16 + 8] = 1.0;
+  return b;
+}
+void cassie_batch_free(cassie_batch_t *b) { if (!b) return; delete b->impl; delete b; }
+int cassie_batch_nenv(const cassie_batch_t *b) { return b->impl->n; }
+int cassie_batch_nq(const cassie_batch_t *b) { return b->impl->hm.nq; }
+int cassie_batch_nv(const cassie_batch_t *b) { return b->impl->hm.nv; }
+int cassie_batch_precision(const cassie_batch_t *b) { return b->impl->precision; }
+long cassie_batch_launch_count(const cassie_batch_t *b) { return b->impl->launches; }
+void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); }
+void cassie_batch_set_pd(cassie_batch_t *b, const double *pd) { b->impl->set_pd(pd); }
+void cassie_batch_step(cassie_batch_t *b, int nticks) { if (nticks > 0) b->impl->step(nticks, 0); }
+void cassie_batch_forward(cassie_batch_t *b) { b->impl->step(0, 1); }
+void cassie_batch_sync(cassie_batch_t *b) { b->impl->sync(); }
+void cassie_batch_get_qpos(cassie_batch_t *b, double *out) { b->impl->get("qpos", out); }
+void cassie_batch_set_qpos(cassie_batch_t *b, const double *in) { b->impl->set("qpos", in); }
+void cassie_batch_get_qvel(cassie_batch_t *b, double *out) { b->impl->get("qvel", out); }
+void cassie_batch_set_qvel(cassie_batch_t *b, const double *in) { b->impl->set("qvel", in); }
+void cassie_batch_get_time(cassie_batch_t *b, double *out) { b->impl->get("time", out); }
+void cassie_batch_get_obs(cassie_batch_t *b, double *out) { b->impl->get("obs", out); }
+int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *body_name) {
+  int id = body_name ? b->impl->hm.body_id(body_name) : -1;
+  if (id <= 0) { set_err("cassie_batch_apply_force: unknown body (no-op)"); return -1; }
+  return b->impl->set_xfrc(xfrc, id) ? 0 : -1;
+}
+void cassie_batch_clear_forces(cassie_batch_t *b) { b->impl->set_xfrc(nullptr, 0); }
+void cassie_batch_integrate_pos(cassie_batch_t *b) { b->impl->integrate(); }
+void *cassie_batch_device_ptr(cassie_batch_t *b, const char *field) { return b->impl->dev_ptr(field); }
+void cassie_batch_set_stream(cassie_batch_t *b, void *s) { b->impl->sync(); if (b->impl->own_stream && b->impl->stream) cudaStreamDestroy(b->impl->stream); b->impl->stream = (cudaStream_t)s; b->impl->own_stream = false; }
+void *cassie_batch_get_stream(cassie_batch_t *b) { return (void *)b->impl->stream; }
+void cassie_batch_get_counters(cassie_batch_t *b, int *out) { b->impl->get_counters(out); }
+int cassie_batch_debug_dump(cassie_batch_t *b, int env, double *out, int n) { return b->impl->debug_dump(env, out, n); }
+
+static void pd_to_row(const pd_in_t *u, double *row) {
+  for (int i = 0; i < 10; i++) {
+    const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; int k = i % 5;
+    row[i] = p->torque[k]; row[10 + i] = p->pTarget[k]; row[20 + i] = p->dTarget[k]; row[30 + i] = p->pGain[k]; row[40 + i] = p->dGain[k];
+  }
+  row[50] = row[51] = 0;
+}
+static void obs_to_state_out(const double *o, const double *radio, state_out_t *y) {
+  memset(y, 0, sizeof *y);
+  for (int i = 0; i < 10; i++) { y->motor.position[i] = o[OB_MPOS + i]; y->motor.velocity[i] = o[OB_MVEL + i]; y->motor.torque[i] = o[OB_MTORQUE + i]; }
+  for (int i = 0; i < 6; i++) { y->joint.position[i] = o[OB_JPOS + i]; y->joint.velocity[i] = o[OB_JVEL + i]; }
+  for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_QUAT + i];
+  for (int i = 0; i < 3; i++) { y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_ACCEL + i]; }
+  for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[i];
+  y->radio.signalGood = true; y->battery.stateOfCharge = 1;
+}
+void cassie_sim_step_pd_batch(cassie_batch_t *b, const pd_in_t *pd_in, state_out_t *state_out) {
+  const int n = b->impl->n;
+  std::vector<double> rows((size_t)n * PD_W);
+  for (int e = 0; e < n; e++) pd_to_row(&pd_in[e], &rows[(size_t)e * PD_W]);
+  b->impl->set_pd(rows.data());
+  b->impl->step(1, 0);
+  if (state_out) {
+    b->obs.resize((size_t)n * OBS_W); b->impl->get("obs", b->obs.data());
+    for (int e = 0; e < n; e++) obs_to_state_out(&b->obs[(size_t)e * OBS_W], &b->radio[(size_t)e * 16], &state_out[e]);
+  } else b->impl->sync();
+}
+
+// ---------------- legacy single-environment verbs
+bool cassie_mujoco_init(const char *modelfile) {
+  std::lock_guard<std::mutex> g(g_model_mutex);
+  if (!g_model_path.empty()) return true;
+  if (!modelfile) { set_err("cassie_mujoco_init: model file required"); return false; }
+  HostModel hm; std::string err;
+  if (!load_model_any(modelfile, hm, err)) { fprintf(stderr, "Load model error: %s\n", err.c_str()); g_err = err; return false; }
+  g_model_path = modelfile; return true;
+}
+void cassie_cleanup(void) { std::lock_guard<std::mutex> g(g_model_mutex); g_model_path.clear(); }
+static void sim_pull(cassie_sim_t *c) {
+  c->b->impl->get("qpos", c->qpos); c->b->impl->get("qvel", c->qvel); c->b->impl->get("time", &c->time);
+  memcpy(c->qpos_dev, c->qpos, sizeof c->qpos); memcpy(c->qvel_dev, c->qvel, sizeof c->qvel); c->time_dev = c->time;
+}
+static void sim_push(cassie_sim_t *c) {  // upload whatever the caller wrote through the borrowed pointers
+  if (memcmp(c->qpos_dev, c->qpos, sizeof c->qpos)) c->b->impl->set("qpos", c->qpos);
+  if (memcmp(c->qvel_dev, c->qvel, sizeof c->qvel)) c->b->impl->set("qvel", c->qvel);
+  if (c->time_dev != c->time) c->b->impl->set("time", &c->time);
+}
+cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
+  std::string path;
+  { std::lock_guard<std::mutex> g(g_model_mutex); if (reinit || g_model_path.empty()) { if (!modelfile) { set_err("cassie_sim_init: model file required"); return nullptr; } path = modelfile; if (g_model_path.empty()) g_model_path = modelfile; } else path = g_model_path; }
+  cassie_batch_t *b = cassie_batch_init(path.c_str(), 1, 0, CASSIE_B200_FP64);
+  if (!b) return nullptr;
+  cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); c->b = b; sim_pull(c);
+  return c;
+}
+void cassie_sim_free(cassie_sim_t *c) { if (!c) return; cassie_batch_free(c->b); delete c; }
+void cassie_sim_step_pd(cassie_sim_t *c, state_out_t *y, const pd_in_t *u) { sim_push(c); cassie_sim_step_pd_batch(c->b, u, y); sim_pull(c); }
+double *cassie_sim_time(cassie_sim_t *c) { return &c->time; }
+double *cassie_sim_qpos(cassie_sim_t *c) { return c->qpos; }
+double *cassie_sim_qvel(cassie_sim_t *c) { return c->qvel; }
+int cassie_sim_nv(const cassie_sim_t *c) { return c->b->impl->hm.nv; }
+int cassie_sim_nq(const cassie_sim_t *c) { return c->b->impl->hm.nq; }
+void cassie_sim_apply_force(cassie_sim_t *c, double xfrc[6], const char *name) { cassie_batch_apply_force(c->b, xfrc, name); }
+void cassie_sim_clear_forces(cassie_sim_t *c) { cassie_batch_clear_forces(c->b); }
+void cassie_sim_radio(cassie_sim_t *c, double channels[16]) { for (int i = 0; i < 16; i++) c->b->radio[i] = channels[i]; double s = channels[8]; c->b->impl->set("sto", &s); }
+void cassie_sim_full_reset(cassie_sim_t *c) {
+  // src/cassiemujoco.c:2008-2033: qpos <- 35 constants, zero qvel / ctrl / applied forces / qacc, zero the torque delay line.
+  // It does NOT touch time, the encoder filters or cassie_out, and does not call mj_forward.
+  static const double q[35] = {0, 0, 1.01, 1, 0, 0, 0, 0.0045, 0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968,
+                               -0.0045, 0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968};
+  std::vector<double> cst(CST_W); c->b->impl->get("cst", cst.data());
+  for (int i = 0; i < 60; i++) cst[CS_DELAY + i] = 0;
+  c->b->impl->set("cst", cst.data());
+  memset(c->qpos, 0, sizeof c->qpos); memcpy(c->qpos, q, sizeof q); memset(c->qvel, 0, sizeof c->qvel);
+  c->b->impl->set("qpos", c->qpos); c->b->impl->set("qvel", c->qvel); cassie_batch_clear_forces(c->b);
+  sim_pull(c);
+}
+}  // extern "C"

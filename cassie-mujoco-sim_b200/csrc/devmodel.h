@@ -91,7 +91,9 @@ constexpr int S_VEC = S_QPOS + 40;              // [4][32] general vectors
 constexpr int S_GEOM = S_VEC + 128;             // [16][6] world pos + z axis
 constexpr int S_CON = S_GEOM + 96;              // [MAXCON][16]
 constexpr int S_CST = S_CON + MAXCON * 16;      // [192]
-constexpr int S_EFC = S_CST + CST_W;            // [7][NEFC]
+constexpr int S_PD = S_CST + CST_W;             // [56] motor-PD row held for the launch
+constexpr int S_XFRC = S_PD + 56;               // [8]
+constexpr int S_EFC = S_XFRC + 8;               // [7][NEFC]
 constexpr int S_Y = S_EFC + 7 * NEFC;           // [NEFC][33]; before the constraint stage: temporaries
 constexpr int S_REALS = S_Y + NEFC * YSTRIDE;
 constexpr int S_INTS = DFILT_W;                 // int region after the reals

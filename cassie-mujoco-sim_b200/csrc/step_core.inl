@@ -825,7 +825,6 @@ CFN void step_env(const DevModel<real> &cm, real *sm, int *ism, LP(real, qvel), 
 // mj_forward on the current state with zero ctrl: fills sensordata / actuator_velocity (cassie_sim_init, :1029)
 template <typename real>
 CFN void forward_env(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real, qacc_ws), const real *xfrc, real *dbg, int *counters) {
-  DECL_LANE
   LV(real, ctrl);
   LANES L(ctrl) = 0; ENDL
   mj_substep(cm, sm, qvel, qacc_ws, ctrl, xfrc, dbg, counters, false);

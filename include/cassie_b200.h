@@ -1,0 +1,113 @@
+/* cassie_b200.h -- C-ABI of the B200-native batched Cassie stepper (libcassie_b200.so).
+ *
+ * Drop-in boundary for ONE path of osudrl/cassie-mujoco-sim: cassie_sim_step_pd and the few lifecycle / state verbs a caller
+ * needs around it.  Every entry point cites the reference interface it replaces (paths relative to /root/reference).
+ * Plain pointers and sizes only; no CUDA or torch types appear in any signature (device pointers travel as void*).
+ *
+ * Two groups:
+ *   (1) legacy single-environment verbs with the reference's exact names and signatures (include/cassiemujoco.h) --
+ *       a cassie_sim_t is a batch of one environment stepped by the same CUDA kernels (there is no CPU backend);
+ *   (2) the new batched verbs (cassie_batch_*, cassie_sim_step_pd_batch) named by BASELINE.json's north_star.
+ */
+#ifndef CASSIE_B200_H
+#define CASSIE_B200_H
+#include <stdbool.h>
+#include "cassie_bus.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cassie_sim cassie_sim_t;     /* include/cassiemujoco.h:31 */
+typedef struct cassie_batch cassie_batch_t; /* new */
+
+/* ------------------------------------------------------------------ (1) legacy single-environment verbs */
+/* include/cassiemujoco.h:45  (src/cassiemujoco.c:820-879): loads and caches the model; here: compiles the MJCF (or .cmodel) */
+bool cassie_mujoco_init(const char *modelfile);
+/* include/cassiemujoco.h:49  (src/cassiemujoco.c:881-...): drops the cached model */
+void cassie_cleanup(void);
+/* include/cassiemujoco.h:67  (src/cassiemujoco.c:979-1036): NULL on failure, message on stderr */
+cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit);
+/* include/cassiemujoco.h:77  (src/cassiemujoco.c:1102-1113): NULL is a no-op */
+void cassie_sim_free(cassie_sim_t *sim);
+/* include/cassiemujoco.h:95  (src/cassiemujoco.c:1147-1157): THE hot path, one environment, one 0.5 ms tick */
+void cassie_sim_step_pd(cassie_sim_t *sim, state_out_t *y, const pd_in_t *u);
+/* include/cassiemujoco.h:104,147,183 (src/cassiemujoco.c:1191-1214): borrowed read-write pointers (35 / 32 / 1 doubles) into a
+ * host mirror; writes are uploaded before the next step, the mirror is refreshed after every step */
+double *cassie_sim_time(cassie_sim_t *sim);
+double *cassie_sim_qpos(cassie_sim_t *sim);
+double *cassie_sim_qvel(cassie_sim_t *sim);
+/* src/cassiemujoco.c:1038-1052 */
+int cassie_sim_nv(const cassie_sim_t *sim);
+int cassie_sim_nq(const cassie_sim_t *sim);
+/* include/cassiemujoco.h:263 (src/cassiemujoco.c:1963-1967): xfrc = force xyz, torque xyz in the world frame; unknown name: no-op */
+void cassie_sim_apply_force(cassie_sim_t *sim, double xfrc[6], const char *name);
+/* include/cassiemujoco.h:268 (src/cassiemujoco.c:1969-1972) */
+void cassie_sim_clear_forces(cassie_sim_t *sim);
+/* include/cassiemujoco.h:281 (src/cassiemujoco.c:2008-2033) */
+void cassie_sim_full_reset(cassie_sim_t *sim);
+/* src/cassiemujoco.c:2002-2006: the 16 radio channels; channel 8 < 1 engages safe-torque-off */
+void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
+
+/* ------------------------------------------------------------------ (2) batched verbs (new; north_star) */
+#define CASSIE_B200_FP32 0 /* throughput build: state and arithmetic in fp32 */
+#define CASSIE_B200_FP64 1 /* parity build: state and arithmetic in fp64 */
+#define CASSIE_PD_WIDTH 52  /* compact motor-PD row: torque[10] pTarget[10] dTarget[10] pGain[10] dGain[10] pad[2] */
+#define CASSIE_OBS_WIDTH 64 /* compact observation row, see cassie_batch_get_obs */
+
+/* n_env environments on CUDA device `device`, all in the state cassie_sim_init leaves (src/cassiemujoco.c:979-1036).
+ * modelfile: MJCF (.xml) or a compiled table (.cmodel).  NULL + stderr message on failure (no GPU, bad model, ...). */
+cassie_batch_t *cassie_batch_init(const char *modelfile, int n_env, int device, int precision);
+void cassie_batch_free(cassie_batch_t *b);
+int cassie_batch_nenv(const cassie_batch_t *b);
+int cassie_batch_nq(const cassie_batch_t *b);
+int cassie_batch_nv(const cassie_batch_t *b);
+/* back to the cassie_sim_init state (mask == NULL: all envs; else mask[i] != 0 selects env i) */
+void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask);
+
+/* cassie_sim_step_pd for every environment: pd_in[n_env] host AoS in, state_out[n_env] host AoS out (may be NULL).
+ * Replaces n_env calls of src/cassiemujoco.c:1147-1157.  Synchronous.  state_out carries the pass-through fields of the
+ * reference's state_output_step (motor/joint position+velocity+torque, IMU orientation/gyro/accel, radio, battery);
+ * the estimator-only fields are zero (scope). */
+void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_out_t *state_out);
+
+/* throughput path: compact rows.  pd: host [n_env][CASSIE_PD_WIDTH] doubles, copied to the device (and converted to the batch
+ * precision) on the batch stream; step: `nticks` control ticks per launch with the PD rows held; asynchronous. */
+void cassie_batch_set_pd(cassie_batch_t *b, const double *pd);
+void cassie_batch_step(cassie_batch_t *b, int nticks);
+void cassie_batch_sync(cassie_batch_t *b);
+/* host copies (synchronous): qpos [n][35], qvel [n][32], time [n], obs [n][CASSIE_OBS_WIDTH] =
+ * motor pos[10] vel[10] torque[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3] mag[3], time, pad */
+void cassie_batch_get_qpos(cassie_batch_t *b, double *out);
+void cassie_batch_set_qpos(cassie_batch_t *b, const double *in);
+void cassie_batch_get_qvel(cassie_batch_t *b, double *out);
+void cassie_batch_set_qvel(cassie_batch_t *b, const double *in);
+void cassie_batch_get_time(cassie_batch_t *b, double *out);
+void cassie_batch_get_obs(cassie_batch_t *b, double *out);
+/* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
+void cassie_batch_forward(cassie_batch_t *b);
+/* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */
+int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *body_name);
+void cassie_batch_clear_forces(cassie_batch_t *b);
+/* batched cassie_integrate_pos (src/cassiemujoco.c:1183-1189 -> mj_integratePos): qpos <- qpos (+) h * qvel, the HBM-bound kernel */
+void cassie_batch_integrate_pos(cassie_batch_t *b);
+
+/* zero-copy access for a PyTorch / DLPack caller: device pointer of a state array ("qpos" [n][36], "qvel" [n][32],
+ * "pd" [n][52], "obs" [n][64], "xfrc" [n][8]) in the batch precision; the stream all work is enqueued on (cudaStream_t). */
+void *cassie_batch_device_ptr(cassie_batch_t *b, const char *field);
+void cassie_batch_set_stream(cassie_batch_t *b, void *cuda_stream);
+void *cassie_batch_get_stream(cassie_batch_t *b);
+int cassie_batch_precision(const cassie_batch_t *b);
+/* per-env solver statistics of the last sub-step: int [n][8] = nefc, ncon, nlimit, PGS iterations, dropped contacts, 0,0,0 */
+void cassie_batch_get_counters(cassie_batch_t *b, int *out);
+/* launches issued since init (bench.py's gpu_launches) */
+long cassie_batch_launch_count(const cassie_batch_t *b);
+/* test hook: stage-by-stage intermediates of env `env` from the last sub-step (DevModel debug layout, doubles) */
+int cassie_batch_debug_dump(cassie_batch_t *b, int env, double *out, int n);
+/* last error message of this thread ("" if none) */
+const char *cassie_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASSIE_B200_H */
