@@ -1,0 +1,274 @@
+#!/usr/bin/env python3
+"""bench.py -- Cassie env-steps/s for the cassie_sim_step_pd hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one control tick (one cassie_sim_step_pd, 0.5 ms of simulated time, 1 physics sub-step) for EVERY environment of the
+batch, i.e. one launch of the fused step kernel.  Workload at N=1 = BASELINE config 2: 4096 envs, cassie.xml flat floor, fixed
+motor-PD targets, initial pelvis height/yaw jitter U(-0.01, 0.01) seed 0.  N>1: the same 4096 envs on
+every GPU (weak scaling, environments are independent; no data-path collective).
+
+value     kernel-only throughput: PD rows and state resident in HBM, CUDA events around each launch on the launching stream,
+          L2 flushed (256 MiB memset) between launches, max over ranks.
+e2e       the same metric through the reference-shaped C-ABI call cassie_sim_step_pd_batch(envs, pd_in_t[] host, state_out_t[] host):
+          host->device copy of every env's PD input and device->host read of every env's observation inside the timed region.
+roofline  for the dominant kernel (cassie_step_kernel<float>), algorithmic bytes = persistent state in + out per env-step.
+cpu_baseline / --impl reference: the CPU restatement in oracle/ (physics restated from MuJoCo 2.1.0 semantics + the reference's real
+          closed Agility blocks when oracle/_ref/liboracle_ref.so exists) on all host cores.  The reference's own libcassiemujoco.so
+          cannot be built: MuJoCo 2.1.0 is not available.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'oracle'))
+
+PD_TARGET = [0.0045, 0, 0.4973, -1.1997, -1.5968, -0.0045, 0, 0.4973, -1.1997, -1.5968]
+PD_PGAIN = [70, 70, 100, 100, 50] * 2
+PD_DGAIN = [7, 7, 8, 8, 5] * 2
+STATE_BYTES_FP32 = 4 * ((36 + 32 + 32 + 192 + 52 + 8 + 96) + (36 + 32 + 32 + 192 + 96 + 64))   # rows read + rows written per env per launch
+WORKLOAD = 'config2: 4096 envs/GPU cassie.xml flat floor, fixed motor-PD targets, pelvis z/yaw jitter U(-0.01,0.01) seed 0'
+
+
+def jittered_qpos(q0, n, seed=0):
+    rng = np.random.default_rng(seed)
+    q = np.repeat(q0[None, :], n, axis=0).copy()
+    q[:, 2] += rng.uniform(-0.01, 0.01, n)
+    yaw = rng.uniform(-0.01, 0.01, n)
+    q[:, 3] = np.cos(yaw / 2); q[:, 4] = 0; q[:, 5] = 0; q[:, 6] = np.sin(yaw / 2)
+    return q
+
+
+# ------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_arm(n_threads, envs_per_thread, ticks, warm_ticks=0):
+    """aggregate env-steps/s of the CPU oracle with one thread per core, each owning private sims."""
+    import oracle as O
+    ref = os.path.exists(O.lib_path(ref=True))
+    L = O.load(ref=ref)
+    model = os.path.join(REPO, 'tests', 'golden', 'cassie.omodel')
+    u = O.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    groups = []
+    for _ in range(n_threads):
+        sims = (C.c_void_p * envs_per_thread)(*[L.osim_new(model.encode()) for _ in range(envs_per_thread)])
+        groups.append(sims)
+
+    def run(sims, t):
+        L.osim_run(sims, envs_per_thread, C.byref(u), t)
+
+    def run_all(t):
+        th = [threading.Thread(target=run, args=(g, t)) for g in groups]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+    if warm_ticks:
+        run_all(warm_ticks)
+    dt = run_all(ticks)
+    for g in groups:
+        for s in g:
+            L.osim_free(s)
+    return n_threads * envs_per_thread * ticks / dt, dt, ref
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ept = 16 if args.steps >= 100 else 64           # private sims per thread; enough work that thread start-up does not dominate
+    val, dt, ref = cpu_arm(cores, ept, args.steps, warm_ticks=args.warmup)
+    kind = 'port'
+    sample = '%d envs (%d threads x %d private sims) x %d ticks of %s; physics = oracle/cassie_oracle.c (fp64 restatement of MuJoCo 2.1.0 semantics), Agility blocks = %s' % (
+        cores * ept, cores, ept, args.steps, WORKLOAD, 'the reference archive libagilitycassie.a incl. state_output_step' if ref else 'oracle twins')
+    line = {'impl': 'reference', 'metric': 'Cassie env-steps/s', 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'parallelism': 'cpu x%d threads' % cores},
+            'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
+            'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+                                          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ''
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons)}
+
+
+def gpu_arm(args, rank, local_rank, world):
+    import torch
+    P = importlib.import_module('cassie-mujoco-sim_b200')
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    n = args.envs
+    b = P.CassieBatch(n, device=local_rank, precision=P.FP32)
+    b.set_stream(torch.cuda.current_stream().cuda_stream)
+    q0 = b.qpos()[0]
+    b.set_qpos(jittered_qpos(q0, n, seed=rank))
+    b.forward()
+    rows = P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    b.set_pd(rows)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks['hbm_gbs'], 'measured (MEASURED_PEAKS.json)') if 'hbm_gbs' in peaks else (6650.0, 'fallback (B200_PROFILING.md)')
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only: warm-up, then K timed launches, each bracketed by its own events, L2 flushed in between
+    for _ in range(args.warmup):
+        b.step(1)
+    launches0 = b.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record(); b.step(1); e1.record()
+    barrier()
+    launches = b.launch_count() - launches0
+    ms_kernel = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    # ---- end to end through the AoS C-ABI: pd_in_t[n] host -> step -> state_out_t[n] host, every step
+    pd = (P.pd_in_t * n)()
+    for e in range(n):
+        for i in range(5):
+            for leg, off in ((pd[e].leftLeg, 0), (pd[e].rightLeg, 5)):
+                leg.motorPd.pTarget[i] = PD_TARGET[off + i]; leg.motorPd.pGain[i] = PD_PGAIN[i]; leg.motorPd.dGain[i] = PD_DGAIN[i]
+    out = (P.state_out_t * n)()
+    obs_t = b.torch_view('obs') if dist else None
+    gathered = torch.empty((world * n, P.OBS_WIDTH), dtype=torch.float32, device='cuda') if dist else None
+    e2e_steps = max(10, min(args.steps, 100))
+    for _ in range(3):
+        b.L.cassie_sim_step_pd_batch(b.h, C.byref(pd), C.byref(out))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        b.L.cassie_sim_step_pd_batch(b.h, C.byref(pd), C.byref(out))
+        if dist:   # the optional batched observation copy-out: one all-gather of the fp32 observation block
+            dist.all_gather_into_tensor(gathered, obs_t)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    # ---- the HBM-bound integrate kernel (cassie_batch_integrate_pos) on a state larger than L2
+    integ = None
+    if rank == 0:
+        nb = 1 << 20
+        bi = P.CassieBatch(nb, device=local_rank, precision=P.FP32)
+        bi.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            bi.integrate_pos()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            bi.integrate_pos()
+        e1.record(); torch.cuda.synchronize()
+        ms_i = e0.elapsed_time(e1) / reps
+        bytes_i = nb * 4 * (35 + 32 + 35)
+        integ = {'kernel': 'cassie_integrate_kernel<float>', 'bound': 'hbm', 'achieved': bytes_i / (ms_i * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                 'frac': bytes_i / (ms_i * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'envs': nb, 'bytes_per_env': 4 * (35 + 32 + 35), 'ms': ms_i}
+        bi.close()
+    # ---- reduce over ranks
+    t = torch.tensor([ms_kernel, t_e2e], dtype=torch.float64, device='cuda')
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_kernel, t_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        try:
+            cpu_val, cpu_dt, ref = cpu_arm(cores, 16, 1500, warm_ticks=50)
+            cpu = {'value': cpu_val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                   'sample': '%d envs (%d threads x 16 private sims) x 1500 ticks of the same workload (~1 s per core); oracle/cassie_oracle.c fp64 + %s' % (
+                       16 * cores, cores, 'reference Agility archive' if ref else 'Agility twins')}
+        except Exception as ex:   # the oracle is a checker; its absence must not void the GPU number
+            cpu = {'value': None, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': 'unavailable: %r' % (ex,)}
+        ms_step = ms_kernel / args.steps
+        value = world * n * args.steps / (ms_kernel * 1e-3)
+        ach = STATE_BYTES_FP32 * n / (ms_step * 1e-3) / 1e9
+        line = {'metric': 'Cassie env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'envs_per_gpu': n, 'ticks_per_step': 1, 'parallelism': 'env-sharded x%d (no data-path collective)' % world,
+                           'l2': 'flushed between timed launches (256 MiB memset); per-launch CUDA events summed', 'model': 'compiled table of model/cassie.xml'},
+                'clocks': clocks,
+                'e2e': {'value': world * n * e2e_steps / t_e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * P.PD_WIDTH * 4, 'd2h_bytes_per_step': n * P.OBS_WIDTH * 4,
+                        'api': 'cassie_sim_step_pd_batch(envs, pd_in_t[n] host, state_out_t[n] host), %d steps, host AoS pack/unpack included%s' % (
+                            e2e_steps, '; + one NCCL all-gather of the observation block per step' if dist else '')},
+                'gpu_launches': launches,
+                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None,
+                             'peak_source': peak_src, 'bytes_per_env_step': STATE_BYTES_FP32,
+                             'note': 'latency/issue-bound by design (SURVEY 8d): algorithmic HBM traffic is only the persistent state rows in+out'},
+                'roofline_integrate': integ, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--envs', type=int, default=4096)
+    args = ap.parse_args()
+    rank, local_rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        reference_arm(args, rank, world)
+    else:
+        gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -346,3 +346,33 @@ class CassieSim:
                 self.c = None
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------- multi-GPU: environments are independent, shard them by index
+def env_shard(n_total, rank, world):
+    """contiguous env-index range [start, start+count) owned by `rank`: sizes differ by at most one."""
+    base, rem = divmod(int(n_total), int(world))
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def gather_observations(local_obs, group=None):
+    """the one optional collective of the path: all-gather of every rank's [n_local, OBS_WIDTH] observation block
+    (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).  Ranks may own different env counts."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = [torch.zeros(1, dtype=torch.int64, device=local_obs.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([local_obs.shape[0]], dtype=torch.int64, device=local_obs.device), group=group)
+    counts = [int(c.item()) for c in counts]
+    if len(set(counts)) == 1:
+        out = torch.empty((world * counts[0],) + tuple(local_obs.shape[1:]), dtype=local_obs.dtype, device=local_obs.device)
+        dist.all_gather_into_tensor(out, local_obs.contiguous(), group=group)
+        return out
+    mx = max(counts)
+    pad = torch.zeros((mx,) + tuple(local_obs.shape[1:]), dtype=local_obs.dtype, device=local_obs.device)
+    pad[:local_obs.shape[0]] = local_obs
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)

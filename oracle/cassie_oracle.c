@@ -36,7 +36,7 @@
 #define MAXJ 40
 #define MAXG 48
 #define MAXCON 64
-#define MAXEFC 320
+#define MAXEFC 160
 #define MAXNM 512
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6 };
@@ -93,7 +93,7 @@ typedef struct {
   int efc_type[MAXEFC], efc_id[MAXEFC];
   double efc_J[MAXEFC][MAXV], efc_pos[MAXEFC], efc_margin[MAXEFC], efc_diagApprox[MAXEFC], efc_R[MAXEFC],
       efc_D[MAXEFC], efc_KBIP[MAXEFC][4], efc_vel[MAXEFC], efc_aref[MAXEFC], efc_b[MAXEFC], efc_force[MAXEFC];
-  double *efc_AR; /* nefc x nefc */
+  double *efc_AR, *efc_JM2; /* nefc x nefc, nefc x nv (allocated once) */
   /* velocity-dependent */
   double cvel[MAXB][6], cdof_dot[MAXV][6], qfrc_bias[MAXV], qfrc_passive[MAXV], actuator_velocity[16],
       actuator_length[16], actuator_force[16], qfrc_actuator[MAXV], qfrc_smooth[MAXV], qacc_smooth[MAXV],
@@ -612,13 +612,12 @@ static void o_makeConstraint(const OModel *m, OData *d) {
 }
 static void o_projectConstraint(const OModel *m, OData *d) {
   int n = d->nefc, nv = m->nv;
-  free(d->efc_AR); d->efc_AR = NULL; if (!n) return;
-  double *JM2 = malloc(sizeof(double) * n * nv);
+  if (!n) return;
+  if (!d->efc_AR) { d->efc_AR = malloc(sizeof(double) * MAXEFC * MAXEFC); d->efc_JM2 = malloc(sizeof(double) * MAXEFC * MAXV); }
+  double *JM2 = d->efc_JM2;
   for (int i = 0; i < n; i++) { copyv(JM2 + i * nv, d->efc_J[i], nv); solveM2(m, d, JM2 + i * nv); }
-  d->efc_AR = malloc(sizeof(double) * n * n);
   for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { double s = dotn(JM2 + i * nv, JM2 + j * nv, nv); d->efc_AR[i * n + j] = d->efc_AR[j * n + i] = s; }
   for (int i = 0; i < n; i++) d->efc_AR[i * n + i] += d->efc_R[i];
-  free(JM2);
 }
 
 /* ---------------- sensors: the 29-number Cassie layout (model/cassie.xml:272-292) */
@@ -682,7 +681,7 @@ static void o_passive(const OModel *m, OData *d) {
   for (int i = 0; i < m->nv; i++) d->qfrc_passive[i] -= m->dof_damping[i] * d->qvel[i];
 }
 static void o_rne_bias(const OModel *m, OData *d) {
-  static double cacc[MAXB][6], cfrc[MAXB][6];
+  double cacc[MAXB][6], cfrc[MAXB][6];
   zero(cacc[0], 3); for (int k = 0; k < 3; k++) cacc[0][3 + k] = -m->gravity[k];
   zero(cfrc[0], 6);
   for (int i = 1; i < m->nbody; i++) {
@@ -728,7 +727,7 @@ static void o_fwdConstraint(const OModel *m, OData *d) {
   mulJacVec(m, d, d->efc_b, d->qacc_smooth);
   for (int i = 0; i < n; i++) d->efc_b[i] -= d->efc_aref[i];
   /* warm start: forces implied by qacc_warmstart, kept only if their dual cost is negative */
-  double *f = d->efc_force, *AR = d->efc_AR; static double jar[MAXEFC];
+  double *f = d->efc_force, *AR = d->efc_AR; double jar[MAXEFC];
   mulJacVec(m, d, jar, d->qacc_warmstart);
   for (int i = 0; i < n; i++) { jar[i] -= d->efc_aref[i]; f[i] = -d->efc_D[i] * jar[i]; if (is_ineq(d->efc_type[i]) && jar[i] >= 0) f[i] = 0; }
   double cost = dotn(f, d->efc_b, n);
@@ -767,7 +766,7 @@ static void quatIntegrate(double *q, const double *w, double h) {
   axisAngle2Quat(qr, ax, ang); normalize4(q); mulQuat(q, q, qr);
 }
 static void o_euler(const OModel *m, OData *d) {
-  int nv = m->nv; static double MhB[MAXNM], dinv[MAXV], qacc[MAXV];
+  int nv = m->nv; double MhB[MAXNM], dinv[MAXV], qacc[MAXV];
   copyv(MhB, d->qM, m->nM);
   for (int i = 0; i < nv; i++) MhB[m->dof_Madr[i]] += m->timestep * m->dof_damping[i];
   factorI(m, MhB, dinv, NULL);
@@ -912,7 +911,7 @@ void osim_free(OSim *c) {
 #ifdef ORACLE_USE_AGILITY_REF
   cassie_core_sim_free(c->core); state_output_free(c->est); pd_input_free(c->pd);
 #endif
-  free(c->d->efc_AR); free(c->d); omodel_free(c->m); free(c);
+  free(c->d->efc_AR); free(c->d->efc_JM2); free(c->d); omodel_free(c->m); free(c);
 }
 
 static double motor_(OSim *c, int i, double u, int sto) { /* :638-664 */
@@ -1035,4 +1034,4 @@ int osim_contact(OSim *c, int i, double *out /* pos3 frame9 dist */, int *geoms)
   copyv(out, k->pos, 3); copyv(out + 3, k->frame, 9); out[12] = k->dist; geoms[0] = k->geom1; geoms[1] = k->geom2; geoms[2] = k->dim; return 1;
 }
 /* CPU-baseline helper: run `ticks` step_pd ticks on `nsim` private sims in this thread, return 0 */
-int osim_run(OSim **sims, int nsim, const pd_in_t *u, int ticks) { for (int t = 0; t < ticks; t++) for (int i = 0; i < nsim; i++) osim_step_pd(sims[i], u, NULL, NULL); return 0; }
+int osim_run(OSim **sims, int nsim, const pd_in_t *u, int ticks) { state_out_t y; for (int t = 0; t < ticks; t++) for (int i = 0; i < nsim; i++) osim_step_pd(sims[i], u, &y, NULL); return 0; }

@@ -1,0 +1,95 @@
+"""The product stepper source executed on the host (tests/emu, -DCASSIE_EMU) against the oracle: the no-GPU parity gate."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PD_DGAIN, PD_PGAIN, PD_TARGET, REPO
+
+OMODEL = os.path.join(GOLDEN, 'cassie.omodel')
+CMODEL = os.path.join(REPO, 'cassie-mujoco-sim_b200', 'models', 'cassie.cmodel')
+PD_ROW = np.concatenate([np.zeros(10), PD_TARGET, np.zeros(10), PD_PGAIN, PD_DGAIN])
+
+
+def test_forward_stages(oracle_mod):
+    import emu_harness as E
+    D = E.D
+    o, e = oracle_mod.OracleSim(OMODEL), E.EmuSim(CMODEL)
+    dbg, n = e.get('dbg'), o.get_int('nefc')
+    for key, cnt, name in (('XPOS', 78, 'xpos'), ('XQUAT', 104, 'xquat'), ('CDOF', 192, 'cdof'), ('QM', 307, 'qM'), ('QLD', 307, 'qLD'), ('BIAS', 32, 'qfrc_bias'),
+                           ('QACCS', 32, 'qacc_smooth'), ('EFC_R', n, 'efc_R'), ('EFC_AREF', n, 'efc_aref'), ('EFC_F', n, 'efc_force'), ('QACC', 32, 'qacc'),
+                           ('QFRCC', 32, 'qfrc_constraint'), ('SENS', 29, 'sensordata')):
+        want = o.arr(name)[:cnt]
+        assert np.abs(dbg[D[key]:D[key] + cnt] - want).max() <= 1e-9 * max(1, np.abs(want).max()), name
+    assert np.abs(dbg[D['J']:D['J'] + 32 * n].reshape(n, 32) - o.efc_J()).max() < 1e-13
+
+
+@pytest.mark.parametrize('cfg', ['zero_pd', 'fixed_pd'])
+def test_trajectory_fp64(oracle_mod, cfg):
+    import emu_harness as E
+    u = oracle_mod.make_pd() if cfg == 'zero_pd' else oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    pd = np.zeros(50) if cfg == 'zero_pd' else PD_ROW
+    o, e = oracle_mod.OracleSim(OMODEL), E.EmuSim(CMODEL)
+    for k in range(1000):
+        o.step_pd(u)
+        e.step(pd)
+        if k % 20 == 0 or k == 999:
+            assert np.abs(e.get('qpos')[:35] - o.arr('qpos')).max() < 1e-10, k
+            c = e.get('counters')
+            assert int(c[0]) == o.get_int('nefc') and int(c[3]) == o.get_int('solver_iter'), k   # same rows, same PGS iteration count
+    assert np.abs(e.get('qvel') - o.arr('qvel')).max() < 1e-8
+
+
+@pytest.mark.parametrize('cfg', ['zero_pd', 'fixed_pd'])
+def test_trajectory_fp32_within_north_star_tolerance(oracle_mod, cfg):
+    """fp32 instance of the same source: max|dqpos| <= 1e-4 vs the fp64 oracle over 1000 ticks"""
+    import emu_harness as E
+    u = oracle_mod.make_pd() if cfg == 'zero_pd' else oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    pd = np.zeros(50) if cfg == 'zero_pd' else PD_ROW
+    o, e = oracle_mod.OracleSim(OMODEL), E.EmuSim(CMODEL, fp32=True)
+    worst = 0.0
+    for k in range(1000):
+        o.step_pd(u)
+        e.step(pd)
+        worst = max(worst, np.abs(e.get('qpos')[:35] - o.arr('qpos')).max())
+    assert worst < 1e-4, worst
+
+
+def test_multitick_and_observation_row(oracle_mod):
+    import ctypes as C
+    import emu_harness as E
+    P = __import__('conftest').product()
+    o, a, b = oracle_mod.OracleSim(OMODEL), E.EmuSim(CMODEL), E.EmuSim(CMODEL)
+    u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    y = P.state_out_t()
+    for _ in range(30):
+        oracle_mod.load().osim_step_pd(o.h, C.byref(u), C.byref(y), None)
+        a.step(PD_ROW)
+    b.step(PD_ROW, nticks=30)
+    assert np.array_equal(a.get('qpos'), b.get('qpos')) and np.array_equal(a.get('obs'), b.get('obs'))
+    obs = b.get('obs')
+    assert np.abs(obs[0:10] - np.array(y.motor.position)).max() < 1e-12 and np.abs(obs[10:20] - np.array(y.motor.velocity)).max() < 1e-9
+    assert np.abs(obs[20:30] - np.array(y.motor.torque)).max() < 1e-9 and np.abs(obs[30:36] - np.array(y.joint.position)).max() < 1e-12
+    assert np.abs(obs[42:46] - np.array(y.pelvis.orientation)).max() < 1e-12
+
+
+def test_torque_delay_and_encoder_quantisation(oracle_mod):
+    """a torque step reaches ctrl exactly 6 ticks later (src/cassiemujoco.c:658-661); drive positions sit on the encoder grid"""
+    import emu_harness as E
+    e = E.EmuSim(CMODEL)
+    pd = np.zeros(50)
+    pd[1] = 20.0          # left hip-yaw feed-forward torque, output side
+    seen = []
+    for k in range(9):
+        e.step(pd)
+        seen.append(e.get('obs')[20 + 1])
+    # tick 0 still sees the all-zero cassie_out (calloc, src/cassiemujoco.c:989): knee and foot "positions" of 0 rad violate the safety
+    # layer's soft limits by more than 0.15 rad, so every commanded torque is scaled to zero on that tick; the command of tick 1 is the
+    # first to pass and reaches the joint 6 ticks later
+    assert all(abs(x) < 1e-12 for x in seen[:7]) and abs(seen[7] - 20.0) < 1e-9, seen
+    pos = e.get('obs')[0:10]
+    bits = [13, 13, 13, 13, 18] * 2
+    gear = [25, 25, 16, 16, 50] * 2
+    for p, b, g in zip(pos, bits, gear):
+        counts = p * g / (2 * np.pi) * (1 << b)
+        assert abs(counts - round(counts)) < 1e-6

@@ -1,0 +1,154 @@
+"""The oracle itself: physics invariants (no MuJoCo is available to pin it -- SURVEY.md section 8c) and committed golden trajectories."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PD_DGAIN, PD_PGAIN, PD_TARGET, REPO
+
+OMODEL = os.path.join(GOLDEN, 'cassie.omodel')
+
+
+def table(path):
+    d = {}
+    for line in open(path):
+        if line[0] == '#':
+            continue
+        t = line.split()
+        if t[1] != 'S':
+            d[t[0]] = np.array([float(x) for x in t[3:3 + int(t[2])]])
+    return d
+
+
+def dense_M(o, T):
+    nv = 32
+    qM, par, adr = o.arr('qM'), T['dof_parentid'].astype(int), T['dof_Madr'].astype(int)
+    D = np.zeros((nv, nv))
+    for i in range(nv):
+        a, j = adr[i], i
+        while j >= 0:
+            D[i, j] = D[j, i] = qM[a]
+            a += 1
+            j = par[j]
+    return D
+
+
+def write_table(T, path, **over):
+    with open(path, 'w') as f:
+        for line in open(OMODEL):
+            k = line.split()[0]
+            if k in over:
+                v = np.asarray(over[k])
+                ty = 'I' if v.dtype.kind in 'iu' else 'F'
+                f.write('%s %s %d %s\n' % (k, ty, v.size, ' '.join(('%d' if ty == 'I' else '%.17g') % x for x in v.ravel())))
+            else:
+                f.write(line)
+
+
+def test_mass_matrix_is_spd_and_total_mass(oracle_mod):
+    o = oracle_mod.OracleSim(OMODEL)
+    T = table(OMODEL)
+    M = dense_M(o, T)
+    assert np.linalg.eigvalsh(M).min() > 0
+    assert abs(M[0, 0] - T['body_mass'].sum()) < 1e-9 and abs(M[0, 0] - 33.312) < 2e-3
+    # sparse L'DL solve == dense solve
+    b = o.arr('qfrc_smooth').copy()
+    assert np.abs(np.linalg.solve(M, b) - o.arr('qacc_smooth')).max() < 1e-8
+
+
+def test_gravity_bias_is_potential_gradient(oracle_mod):
+    o = oracle_mod.OracleSim(OMODEL)
+    T = table(OMODEL)
+    q0 = o.arr('qpos').copy()
+    o.arr('qvel')[:] = 0
+    o.forward()
+    bias = o.arr('qfrc_bias').copy()
+
+    def V(q):
+        o.arr('qpos')[:] = q
+        o.forward()
+        return 9.81 * np.dot(T['body_mass'], o.arr('xipos').reshape(-1, 3)[:, 2])
+    for j in range(26):
+        if int(T['jnt_type'][j]) in (2, 3):
+            qa, da, e = int(T['jnt_qposadr'][j]), int(T['jnt_dofadr'][j]), 1e-6
+            qp, qm = q0.copy(), q0.copy()
+            qp[qa] += e
+            qm[qa] -= e
+            assert abs((V(qp) - V(qm)) / (2 * e) - bias[da]) < 1e-5
+
+
+def test_energy_drift_is_first_order_in_h(oracle_mod, tmp_path):
+    """unconstrained, undamped tumbling tree: total energy error over a fixed horizon halves when h halves"""
+    T = table(OMODEL)
+
+    def drift(h):
+        p = str(tmp_path / ('free_%g.omodel' % h))
+        write_table(T, p, neq=np.array([0]), dof_damping=np.zeros(32), jnt_limited=np.zeros(26, dtype=int), geom_contype=np.zeros(25, dtype=int),
+                    geom_conaffinity=np.zeros(25, dtype=int), opt_timestep=np.array([h]), eq_obj1id=np.zeros(0, dtype=int), eq_obj2id=np.zeros(0, dtype=int))
+        o = oracle_mod.OracleSim(p)
+        o.arr('qvel')[:] = np.random.default_rng(0).normal(size=32)
+
+        def E():
+            o.forward()
+            v = o.arr('qvel')
+            ke = 0.5 * v @ dense_M(o, T) @ v
+            pe = 9.81 * np.dot(T['body_mass'], o.arr('xipos').reshape(-1, 3)[:, 2])
+            q = o.arr('qpos')
+            for j in range(26):
+                if T['jnt_stiffness'][j] > 0:
+                    pe += 0.5 * T['jnt_stiffness'][j] * q[int(T['jnt_qposadr'][j])] ** 2
+            return ke + pe
+        e0 = E()
+        for _ in range(int(round(0.2 / h))):
+            o.mj_step()
+        return E() - e0
+    d1, d2 = drift(5e-4), drift(2.5e-4)
+    assert abs(d1) < 0.5 and 1.7 < d1 / d2 < 2.3, (d1, d2)
+
+
+def test_pd_stance_contact_forces_carry_the_weight(oracle_mod):
+    o = oracle_mod.OracleSim(OMODEL)
+    u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    forces = []
+    for k in range(1000):
+        o.step_pd(u)
+        if k >= 300 and o.get_int('ncon') > 0:
+            n, ne = o.get_int('nefc'), 12 + o.get_int('nl')
+            forces.append(o.arr('efc_force')[ne:n].sum())
+    assert abs(np.mean(forces) - 33.312 * 9.81) < 0.15 * 33.312 * 9.81     # normal force ~ weight while (quasi) standing
+    assert np.abs(o.arr("efc_pos")[:12]).max() < 5e-3                       # loop closures hold
+    q = o.arr('qpos')
+    for a in (3, 10, 24):
+        assert abs(np.linalg.norm(q[a:a + 4]) - 1) < 1e-12
+    assert o.get_int('unsupported_pairs') == 0 and o.get_int('dropped_contacts') == 0
+
+
+def test_left_right_symmetry(oracle_mod):
+    """mirror-symmetric model + symmetric input: left and right motor joints move identically (up to the slightly asymmetric qpos_init)"""
+    o = oracle_mod.OracleSim(OMODEL)
+    q = o.arr('qpos')
+    q[21:35] = q[7:21]
+    q[21] = -q[7]; q[22] = -q[8]                      # roll / yaw mirror
+    q[24] = q[10]; q[25] = -q[11]; q[26] = -q[12]; q[27] = q[13]     # achilles quaternion reflected in the leg's local xy plane: (w, -x, -y, z)
+    o.forward()
+    u = oracle_mod.make_pd()
+    for _ in range(200):
+        o.step_pd(u)
+    q = o.arr('qpos')
+    assert abs(q[9] - q[23]) < 1e-4 and abs(q[14] - q[28]) < 1e-4 and abs(q[20] - q[34]) < 1e-4   # hip pitch, knee, foot
+    assert abs(q[1]) < 1e-4                                                                        # no lateral drift
+
+
+@pytest.mark.parametrize('name', ['traj_zero_pd', 'traj_fixed_pd'])
+def test_golden_trajectory(oracle_mod, name):
+    """regression pin: committed fp64 oracle trajectories (tests/golden/make_golden.py)"""
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    u = oracle_mod.make_pd() if name == 'traj_zero_pd' else oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    o = oracle_mod.OracleSim(OMODEL)
+    ticks = list(g['ticks'])
+    for k in range(1, int(max(ticks)) + 1):
+        o.step_pd(u)
+        if k in ticks:
+            i = ticks.index(k)
+            assert np.abs(o.arr('qpos') - g['qpos'][i]).max() < 1e-7, k
+            assert np.abs(o.arr('qvel') - g['qvel'][i]).max() < 1e-5, k
