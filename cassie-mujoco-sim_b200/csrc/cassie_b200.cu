@@ -22,7 +22,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg; int *dfilt, *counters; int n;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters; int n;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -44,48 +44,31 @@ __device__ __forceinline__ void tma_stage(void *dst_smem, const void *src_gmem, 
 }
 
 template <typename real> __host__ __device__ constexpr size_t model_bytes() { return (sizeof(DevModel<real>) + 127) / 128 * 128; }
-template <typename real> __host__ __device__ constexpr size_t warp_bytes() { return ((size_t)S_REALS * sizeof(real) + (size_t)S_INTS * sizeof(int) + 127) / 128 * 128; }
-
-template <typename real>
-__device__ __forceinline__ void load_env(const EnvArrays<real> &A, int env, real *sm, int *ism, real &qvel, real &qacc_ws) {
-  const int l = threadIdx.x & 31;
-  for (int i = l; i < QPOS_W; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * QPOS_W + i];
-  for (int i = l; i < CST_W; i += 32) sm[S_CST + i] = A.cst[(size_t)env * CST_W + i];
-  for (int i = l; i < PD_W; i += 32) sm[S_PD + i] = A.pd[(size_t)env * PD_W + i];
-  if (l < XFRC_W) sm[S_XFRC + l] = A.xfrc[(size_t)env * XFRC_W + l];
-  for (int i = l; i < DFILT_W; i += 32) ism[i] = A.dfilt[(size_t)env * DFILT_W + i];
-  qvel = A.qvel[(size_t)env * QVEL_W + l]; qacc_ws = A.qacc_ws[(size_t)env * QVEL_W + l];
-  __syncwarp();
-}
-template <typename real>
-__device__ __forceinline__ void store_env(const EnvArrays<real> &A, int env, const real *sm, const int *ism, real qvel, real qacc_ws) {
-  const int l = threadIdx.x & 31;
-  __syncwarp();
-  for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
-  for (int i = l; i < CST_W; i += 32) A.cst[(size_t)env * CST_W + i] = sm[S_CST + i];
-  for (int i = l; i < DFILT_W; i += 32) A.dfilt[(size_t)env * DFILT_W + i] = ism[i];
-  A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;
-}
+template <typename real> __host__ __device__ constexpr size_t warp_bytes() { return ((size_t)S_REALS * sizeof(real) + 127) / 128 * 128; }
 
 // mode 0: step nticks; mode 1: mj_forward only
 template <typename real>
-__global__ void __launch_bounds__(288) cassie_step_kernel(const DevModel<real> *__restrict__ gmodel, EnvArrays<real> A, int nticks, int mode) {
+__global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *__restrict__ gmodel, EnvArrays<real> A, int nticks, int mode) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
   tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
-  const int warp = threadIdx.x >> 5, env = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int warp = threadIdx.x >> 5, l = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + warp;
   if (env >= A.n) return;
   real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>());
-  int *ism = reinterpret_cast<int *>(sm + S_REALS);
   const DevModel<real> &cm = *cmp;
-  real qvel, qacc_ws;
-  load_env(A, env, sm, ism, qvel, qacc_ws);
-  real *dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr;
-  int *counters = A.counters + (size_t)env * 8;
-  if (mode == 0) step_env(cm, sm, ism, qvel, qacc_ws, sm + S_PD, sm + S_XFRC, A.obs + (size_t)env * OBS_W, nticks, dbg, counters);
-  else forward_env(cm, sm, qvel, qacc_ws, sm + S_XFRC, dbg, counters);
-  store_env(A, env, sm, ism, qvel, qacc_ws);
+  // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
+  for (int i = l; i < QPOS_W; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * QPOS_W + i];
+  real qvel = A.qvel[(size_t)env * QVEL_W + l], qacc_ws = A.qacc_ws[(size_t)env * QVEL_W + l];
+  __syncwarp();
+  EnvPtrs<real> E;
+  E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
+  E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
+  if (mode == 0) step_env(cm, sm, E, qvel, qacc_ws, nticks);
+  else forward_env(cm, sm, E, qvel, qacc_ws);
+  __syncwarp();
+  for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
+  A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;
 }
 
 // cassie_integrate_pos for the whole batch (mj_integratePos): the HBM-bound kernel.  One thread per (env, joint).
@@ -135,7 +118,7 @@ template <typename real> struct Batch : BatchBase {
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
   bool init() override {
@@ -148,16 +131,27 @@ template <typename real> struct Batch : BatchBase {
     A.n = n;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QPOS_W)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * QVEL_W)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * QVEL_W));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
-    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8));
+    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * NM_MAX));
     CUDA_OK(cudaMemset(A.pd, 0, sizeof(real) * n * PD_W)); CUDA_OK(cudaMemset(A.obs, 0, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMemset(A.counters, 0, sizeof(int) * n * 8));
     if (debug) { CUDA_OK(cudaMalloc(&A.dbg, sizeof(real) * n * D_SIZE)); CUDA_OK(cudaMemset(A.dbg, 0, sizeof(real) * n * D_SIZE)); }
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true;
-    // warps per CTA: as many as fit twice per SM, else once (fp64)
-    int dev_smem = 0; CUDA_OK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // warps per CTA: maximise resident warps per SM over 1..4 CTAs per SM (each CTA carries its own copy of the model block)
+    int dev_smem = 0, sm_smem = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     const char *w = getenv("CASSIE_B200_WPB");
-    wpb = w ? atoi(w) : (int)((dev_smem - model_bytes<real>()) / warp_bytes<real>());
-    if (wpb > 9) wpb = 9; if (wpb < 1) { set_err("not enough shared memory per block"); return false; }
-    if (!w && sizeof(real) == 4 && wpb >= 8) wpb = 4;   // two CTAs of 4 warps per SM
+    if (w) wpb = atoi(w);
+    else {
+      int best = 0, kk[5] = {0, 0, 0, 0, 0}; wpb = 1;
+      for (int ctas = 4; ctas >= 1; --ctas) {
+        long per_cta = (long)sm_smem / ctas - 1024; if (per_cta > dev_smem) per_cta = dev_smem;
+        int k = (int)((per_cta - (long)model_bytes<real>()) / (long)warp_bytes<real>()); if (k > 16) k = 16; if (k < 0) k = 0;
+        kk[ctas] = k; if (k * ctas > best) best = k * ctas;
+      }
+      // several small CTAs refill an SM more smoothly than one big one: take the most CTAs within 15 % of the best residency
+      for (int ctas = 4; ctas >= 1; --ctas) if (kk[ctas] >= 1 && kk[ctas] * ctas * 100 >= best * 85) { wpb = kk[ctas]; break; }
+    }
+    if (wpb < 1 || wpb > 16 || model_bytes<real>() + (size_t)wpb * warp_bytes<real>() > (size_t)dev_smem) { set_err("not enough shared memory per block"); return false; }
     smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>();
     CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return reset(nullptr);

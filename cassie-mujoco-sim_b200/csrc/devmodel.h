@@ -15,8 +15,8 @@ constexpr int ME = 4;         // connect equalities
 constexpr int MU = 10;        // motors
 constexpr int NM_MAX = 320;   // sparse mass-matrix entries (307 for Cassie)
 constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 for Cassie)
-constexpr int NEFC = 64;      // constraint rows per env (12 equality + limits + 4 per floor contact)
-constexpr int MAXCON = 16;    // contacts per env
+constexpr int NEFC = 48;      // constraint rows per env (12 equality + limits + 4 per floor contact); excess contacts are dropped and counted
+constexpr int MAXCON = 12;    // contacts per env
 constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
 
 // pair kinds handled by the narrow phase
@@ -79,28 +79,27 @@ constexpr int S_XPOS = 0;                       // [32][3]
 constexpr int S_XQUAT = S_XPOS + 96;            // [32][4]
 constexpr int S_XMAT = S_XQUAT + 128;           // [32][9]
 constexpr int S_CDOF = S_XMAT + 288;            // [32][6]
-constexpr int S_CDOFD = S_CDOF + 192;           // [32][6]
-constexpr int S_CINERT = S_CDOFD + 192;         // [32][10]
-constexpr int S_CRB = S_CINERT + 320;           // [32][10]; during FK: xanchor[32][3], xaxis[32][3], qloc[32][4]
-constexpr int S_QM = S_CRB + 320;               // [320]
-constexpr int S_QLD = S_QM + NM_MAX;            // [320]
+constexpr int S_QLD = S_CDOF + 192;             // [320] (qM itself lives in a global scratch row)
 constexpr int S_DINV = S_QLD + NM_MAX;          // [32]
 constexpr int S_DSQI = S_DINV + 32;             // [32]
 constexpr int S_QPOS = S_DSQI + 32;             // [40]
-constexpr int S_VEC = S_QPOS + 40;              // [4][32] general vectors
+constexpr int S_VEC = S_QPOS + 40;              // [4][32] general vectors ([96..101]: cdof_dot*qvel chain sum of the IMU body)
 constexpr int S_GEOM = S_VEC + 128;             // [16][6] world pos + z axis
 constexpr int S_CON = S_GEOM + 96;              // [MAXCON][16]
-constexpr int S_CST = S_CON + MAXCON * 16;      // [192]
-constexpr int S_PD = S_CST + CST_W;             // [56] motor-PD row held for the launch
-constexpr int S_XFRC = S_PD + 56;               // [8]
-constexpr int S_EFC = S_XFRC + 8;               // [7][NEFC]
-constexpr int S_Y = S_EFC + 7 * NEFC;           // [NEFC][33]; before the constraint stage: temporaries
+constexpr int S_EFC = S_CON + MAXCON * 16;               // [NEFC][4]: row-build scalars {.., pos, src, ineq} then solver constants {b, 1/A, A, +-R}
+constexpr int S_Y = S_EFC + 4 * NEFC;           // [NEFC][33] constraint matrix; before the constraint stage it holds the temporaries below
 constexpr int S_REALS = S_Y + NEFC * YSTRIDE;
-constexpr int S_INTS = DFILT_W;                 // int region after the reals
-// row-scalar slots inside S_EFC
-constexpr int E_B = 0, E_R = 1, E_ADINV = 2, E_F = 3, E_INEQ = 4, E_POS = 5, E_SRC = 6;
+// temporaries inside the S_Y region (dead before the first constraint row is written)
+constexpr int T_CINERT = 0;                     // [32][10]
+constexpr int T_CRB = 320;                      // [32][10]; during kinematics: xanchor[32][3], xaxis[32][3], qloc[32][4]; later chain sums [32][6]
+constexpr int T_CVEL = 640;                     // [32][6]
+constexpr int T_CFRC = 832;                     // [32][6]
+constexpr int T_CDOFD = 1024;                   // [32][6]
+static_assert(T_CDOFD + 192 <= NEFC * YSTRIDE, "temporaries must fit in the constraint-matrix region");
+// slots of a row's 4 scalars while the rows are being built (overwritten by the solver constants afterwards)
+constexpr int E_POS = 0, E_SRC = 1, E_INEQ = 2;
 
-template <typename real> constexpr size_t scratch_bytes() { return (size_t)S_REALS * sizeof(real) + (size_t)S_INTS * sizeof(int); }
+template <typename real> constexpr size_t scratch_bytes() { return (size_t)S_REALS * sizeof(real); }
 
 // ---- debug dump (tests only; one block per env, in `real`)
 constexpr int D_XPOS = 0, D_XQUAT = 96, D_CDOF = 224, D_QM = 416, D_QLD = 736, D_BIAS = 1056, D_PASSIVE = 1088, D_SMOOTH = 1120,

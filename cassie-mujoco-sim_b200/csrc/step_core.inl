@@ -22,6 +22,8 @@
 #define DECL_LANE
 #define LANES for (int l = 0; l < 32; ++l) {
 #define ENDL }
+#define LANES_NS for (int l = 0; l < 32; ++l) {
+#define ENDL_NS }
 #define LV(T, name) T name[32]
 #define L(name) name[l]
 #define LP(T, name) T(&name)[32]
@@ -34,6 +36,8 @@
 #define DECL_LANE const int l = threadIdx.x & 31;
 #define LANES {
 #define ENDL } __syncwarp();
+#define LANES_NS {
+#define ENDL_NS }
 #define LV(T, name) T name
 #define L(name) name
 #define LP(T, name) T &name
@@ -44,6 +48,18 @@
 #endif
 
 namespace cassie {
+
+// per-environment rows that stay in global memory (L1/L2 resident; only the owning warp touches them)
+template <typename real> struct EnvPtrs {
+  real *cst;          // [CST_W] controller / sensor state
+  int *dfilt;         // [DFILT_W] drive FIR taps
+  const real *pd;     // [PD_W] motor-PD row held for the launch
+  const real *xfrc;   // [XFRC_W]
+  real *obs;          // [OBS_W] or null
+  real *qM;           // [NM_MAX] mass-matrix scratch (written by CRB, read back by the Euler stage)
+  real *dbg;          // [D_SIZE] or null
+  int *counters;      // [8]
+};
 
 // ------------------------------------------------------------------ scalar math on float / double
 CFN float msqrt(float x) { return sqrtf(x); }
@@ -144,19 +160,20 @@ template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm) 
   real *qLD = sm + S_QLD;
   LV(real, tmp);
   for (int k = cm.nv - 1; k >= 0; --k) {
-    const int kk = cm.dof_Madr[k], depth = cm.dof_depth[k];
-    if (depth == 0) continue;
-    LANES  // lane t (1..depth) owns the t-th ancestor i of k: row_i -= row_k[t..] * (M(k,i)/M(k,k))
+    const int dk = cm.dof_depth[k];
+    if (dk == 0) continue;
+    const int kk = cm.dof_Madr[k]; const uint32_t anc = cm.dof_ancmask[k];
+    LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
       L(tmp) = 0;
-      if (l >= 1 && l <= depth) {
-        int i = k; for (int t = 0; t < l; ++t) i = cm.dof_parent[i];
-        const real f = qLD[kk + l] / qLD[kk];
-        const int cnt = cm.dof_depth[i] + 1, ia = cm.dof_Madr[i];
-        for (int c = 0; c < cnt; ++c) qLD[ia + c] -= qLD[kk + l + c] * f;
+      if ((anc >> l) & 1u) {
+        const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
+        const real f = qLD[kk + t] / qLD[kk];
+        const real *rk = qLD + kk + t; real *ri = qLD + ia;
+        for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
         L(tmp) = f;
       }
     ENDL
-    LANES if (l >= 1 && l <= depth) qLD[kk + l] = L(tmp); ENDL
+    LANES if ((anc >> l) & 1u) qLD[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
   }
   LANES if (l < cm.nv) { real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = real(1) / d; sm[S_DSQI + l] = real(1) / msqrt(d); } ENDL
 }
@@ -213,12 +230,15 @@ template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int b
 // ------------------------------------------------------------------ one MuJoCo sub-step (mj_step1 + mj_step2)
 // state in: sm[S_QPOS], lane vars qvel / qacc_ws, ctrl in sm[S_CST..] (via ctrl lane var), xfrc.  state out: same + sensordata.
 template <typename real>
-CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real, qacc_ws), LP(real, ctrl), const real *xfrc, real *dbg, int *counters, bool advance) {
+CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, ctrl), real *dbg, bool advance) {
   DECL_LANE
   const int nv = cm.nv, nb = cm.nbody;
-  real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF, *cdofd = sm + S_CDOFD, *cinert = sm + S_CINERT;
-  real *qpos = sm + S_QPOS, *qM = sm + S_QM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
-  real *xanchor = sm + S_CRB, *xaxis = sm + S_CRB + 96, *qloc = sm + S_CRB + 192;
+  real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
+  real *qpos = sm + S_QPOS, *qM = E.qM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
+  const real *xfrc = E.xfrc; int *counters = E.counters;
+  // temporaries of the smooth-dynamics stages live in the (not yet used) constraint-matrix region
+  real *cinert = sm + S_Y + T_CINERT, *cdofd = sm + S_Y + T_CDOFD;
+  real *xanchor = sm + S_Y + T_CRB, *xaxis = sm + S_Y + T_CRB + 96, *qloc = sm + S_Y + T_CRB + 192;
   LV(real, com0); LV(real, com1); LV(real, com2);
 
   // ================= kinematics (mj_kinematics) =================
@@ -316,7 +336,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
 
   // ================= CRB -> sparse qM (mj_crb); crb overwrites the xanchor/xaxis/qloc temporaries =================
   {
-    real *crb = sm + S_CRB;
+    real *crb = sm + S_Y + T_CRB;
     LANES  // lane = body: composite inertia = sum of cinert over the (contiguous, depth-first) subtree
       if (l < nb) {
         real acc[10]; for (int k = 0; k < 10; ++k) acc[k] = 0;
@@ -341,9 +361,9 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
   factor_ld(cm, sm);
 
   // ================= velocity stage: comVel, passive, RNE bias =================
-  real *S = sm + S_CRB;          // chain sums [32][6] (crb is dead)
-  real *cvel = Y;                // [32][6]
-  real *cfrc = Y + 192;          // [32][6]
+  real *S = sm + S_Y + T_CRB;      // chain sums [32][6] (crb is dead)
+  real *cvel = sm + S_Y + T_CVEL;  // [32][6]
+  real *cfrc = sm + S_Y + T_CFRC;  // [32][6]
   real *vecs = sm + S_VEC;
   LANES if (l < nv) vecs[l] = L(qvel); ENDL
   LANES  // lane = dof: S_d = sum over the chain root..d of cdof_a * qvel_a
@@ -385,6 +405,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
       for (int k = 0; k < 6; ++k) cfrc[6 * l + k] = f[k];
     }
   ENDL
+  LANES { const int ld = cm.body_lastdof[cm.imu_body]; if (l < 6) vecs[96 + l] = (ld >= 0) ? S[6 * ld + l] : real(0); } ENDL
   LV(real, qfrc_smooth); LV(real, qacc_smooth); LV(real, bias);
   LANES  // lane = dof: bias = cdof . (sum of cfrc over the subtree of the dof's body); passive; actuation; applied
     L(qfrc_smooth) = 0; L(bias) = 0;
@@ -520,7 +541,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
       jac_col(cm, l, b1, cd, p1, cm3, j1); jac_col(cm, l, b2, cd, p2, cm3, j2);
       for (int k = 0; k < 3; ++k) {
         Y[(nefc + k) * YSTRIDE + l] = j1[k] - j2[k];
-        if (l == 0) { efc[E_POS * NEFC + nefc + k] = p1[k] - p2[k]; efc[E_SRC * NEFC + nefc + k] = (real)e; efc[E_INEQ * NEFC + nefc + k] = 0; }
+        if (l == 0) { efc[4 * (nefc + k) + E_POS] = p1[k] - p2[k]; efc[4 * (nefc + k) + E_SRC] = (real)e; efc[4 * (nefc + k) + E_INEQ] = 0; }
       }
     ENDL
     nefc += 3;
@@ -541,7 +562,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
         if (dist < 0 && r < NEFC) {
           for (int d = 0; d < 32; ++d) Y[r * YSTRIDE + d] = 0;
           Y[r * YSTRIDE + cm.jnt_dofadr[l]] = side ? real(-1) : real(1);
-          efc[E_POS * NEFC + r] = dist; efc[E_SRC * NEFC + r] = (real)(64 + l); efc[E_INEQ * NEFC + r] = 1; ++r;
+          efc[4 * r + E_POS] = dist; efc[4 * r + E_SRC] = (real)(64 + l); efc[4 * r + E_INEQ] = 1; ++r;
         }
       }
     }
@@ -564,7 +585,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
         Y[nefc * YSTRIDE + l] = jn + mu * jt1; Y[(nefc + 1) * YSTRIDE + l] = jn - mu * jt1;
         Y[(nefc + 2) * YSTRIDE + l] = jn + mu * jt2; Y[(nefc + 3) * YSTRIDE + l] = jn - mu * jt2;
       }
-      if (l < rows) { efc[E_POS * NEFC + nefc + l] = o[12]; efc[E_SRC * NEFC + nefc + l] = (real)(128 + p); efc[E_INEQ * NEFC + nefc + l] = 1; }
+      if (l < rows) { efc[4 * (nefc + l) + E_POS] = o[12]; efc[4 * (nefc + l) + E_SRC] = (real)(128 + p); efc[4 * (nefc + l) + E_INEQ] = 1; }
     ENDL
     nefc += rows; ++ncon_used;
   }
@@ -572,20 +593,21 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
   (void)nefc_before_contacts;
 
   LV(real, qacc); LV(real, qfrc_con);
+  LV(real, f0); LV(real, f1);    // constraint forces: lane (r & 31) owns rows r and r + 32
   int iters = 0;
   if (nefc == 0) {
-    LANES L(qacc) = L(qacc_smooth); L(qfrc_con) = 0; ENDL
+    LANES L(qacc) = L(qacc_smooth); L(qfrc_con) = 0; L(f0) = L(f1) = 0; ENDL
   } else {
     // ---- per-row: impedance, R, aref, b, warm-start force (lane = row)
-    LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc_smooth); vecs[64 + l] = L(qacc_ws); } ENDL
+    LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc_smooth); vecs[64 + l] = L(qacc_ws); } L(f0) = L(f1) = 0; ENDL
     if (dbg) { LANES for (int r = 0; r < nefc; ++r) dbg[D_J + 32 * r + l] = Y[r * YSTRIDE + l]; ENDL }
     for (int pass = 0; pass * 32 < nefc; ++pass) {
       LANES
         const int r = l + 32 * pass;
         if (r < nefc) {
-          const real *y = Y + r * YSTRIDE; real jv = 0, ja = 0, jw = 0;
-          for (int d = 0; d < nv; ++d) { const real yy = y[d]; jv += yy * vecs[d]; ja += yy * vecs[32 + d]; jw += yy * vecs[64 + d]; }
-          const int src = (int)efc[E_SRC * NEFC + r]; const real pos = efc[E_POS * NEFC + r];
+          real *yy = Y + r * YSTRIDE; real jv = 0, ja = 0, jw = 0;
+          for (int d = 0; d < nv; ++d) { const real y = yy[d]; jv += y * vecs[d]; ja += y * vecs[32 + d]; jw += y * vecs[64 + d]; }
+          const int src = (int)efc[4 * r + E_SRC]; const real pos = efc[4 * r + E_POS]; const bool ineq = efc[4 * r + E_INEQ] != 0;
           const real *solref, *solimp; real dA, margin = 0, rscale = 1;
           if (src < 64) { solref = cm.eq_solref[src]; solimp = cm.eq_solimp[src]; dA = cm.body_invw[cm.eq_b1[src]] + cm.body_invw[cm.eq_b2[src]]; }
           else if (src < 128) { const int j = src - 64; solref = cm.jnt_solref[j]; solimp = cm.jnt_solimp[j]; dA = cm.dof_invweight0[cm.jnt_dofadr[j]]; }
@@ -601,48 +623,56 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
           else { K = -solref[0] / mmax(minval<real>(), solimp[1] * solimp[1]); B = -solref[1] / mmax(minval<real>(), solimp[1]); }
           const real aref = -B * jv - K * imp * (pos - margin);
           const real jar = jw - aref; real f = -jar / Rr;
-          if (efc[E_INEQ * NEFC + r] != 0 && jar >= 0) f = 0;
-          efc[E_B * NEFC + r] = ja - aref; efc[E_R * NEFC + r] = Rr; efc[E_F * NEFC + r] = f;
+          if (ineq && jar >= 0) f = 0;
+          if (pass == 0) L(f0) = f; else L(f1) = f;
           if (dbg) { dbg[D_EFC_AREF + r] = aref; dbg[D_EFC_R + r] = Rr; dbg[D_EFC_B + r] = ja - aref; }
           // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place
-          real *yy = Y + r * YSTRIDE;
-          for (int k = 0; k < cm.ntri; ++k) { const uint32_t t = cm.tri[k]; yy[(t >> 16) & 255u] -= qLD[t & 0xffffu] * yy[t >> 24]; }
+          { int ci = -1; real xi = 0;
+            for (int k = 0; k < cm.ntri; ++k) { const uint32_t t = cm.tri[k]; const int i = (int)(t >> 24); if (i != ci) { ci = i; xi = yy[i]; } yy[(t >> 16) & 255u] -= qLD[t & 0xffffu] * xi; } }
           real ad = 0;
           for (int d = 0; d < nv; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
-          efc[E_ADINV * NEFC + r] = real(1) / (ad + Rr);
+          // packed row constants for the solver: b, 1/A, A, +-R (sign bit set = inequality row)
+          real *rc = efc + 4 * r; const real Ad = ad + Rr;
+          rc[0] = ja - aref; rc[1] = real(1) / Ad; rc[2] = Ad; rc[3] = ineq ? -Rr : Rr;
         }
       ENDL
     }
     // ---- warm start: keep f only if its dual cost 0.5 f'(YY'+R)f + f'b is not positive
-    LV(real, z);
-    LANES real s = 0; if (l < nv) for (int r = 0; r < nefc; ++r) s += Y[r * YSTRIDE + l] * efc[E_F * NEFC + r]; L(z) = s; L(t0) = real(0.5) * s * s; ENDL
+    LV(real, z); LV(real, fb);
+    LANES L(z) = 0; ENDL
+    for (int r = 0; r < nefc; ++r) {
+      if (r < 32) { BCAST(fb, f0, r); } else { BCAST(fb, f1, r - 32); }
+      LANES if (l < nv) L(z) += Y[r * YSTRIDE + l] * L(fb); ENDL
+    }
     LANES
-      real s = 0;
-      for (int r = l; r < nefc; r += 32) { const real f = efc[E_F * NEFC + r]; s += f * (efc[E_B * NEFC + r] + real(0.5) * efc[E_R * NEFC + r] * f); }
-      L(t0) += s;
+      real s = real(0.5) * L(z) * L(z);
+      if (l < nefc) { const real f = L(f0); s += f * (efc[4 * l] + real(0.5) * mabs(efc[4 * l + 3]) * f); }
+      if (l + 32 < nefc) { const real f = L(f1); s += f * (efc[4 * (l + 32)] + real(0.5) * mabs(efc[4 * (l + 32) + 3]) * f); }
+      L(t0) = s;
     ENDL
     ALLSUM(t0);
-    if (LANE0(t0) > 0) { LANES L(z) = 0; for (int r = l; r < nefc; r += 32) efc[E_F * NEFC + r] = 0; ENDL }
+    if (LANE0(t0) > 0) { LANES L(z) = 0; L(f0) = L(f1) = 0; ENDL }
     // ---- projected Gauss-Seidel, rows strictly in order; z = Y'f is carried one entry per lane
-    LV(real, acc); LV(real, impr);
+    LV(real, acc); LV(real, impr); LV(real, yr);
     while (iters < cm.iterations) {
       LANES L(impr) = 0; ENDL
       for (int r = 0; r < nefc; ++r) {
-        LANES L(acc) = (l < nv) ? Y[r * YSTRIDE + l] * L(z) : real(0); ENDL
+        if (r < 32) { BCAST(fb, f0, r); } else { BCAST(fb, f1, r - 32); }
+        LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
         ALLSUM(acc);
-        LANES
-          const real fold = efc[E_F * NEFC + r], Rr = efc[E_R * NEFC + r], adinv = efc[E_ADINV * NEFC + r];
-          const real res = efc[E_B * NEFC + r] + L(acc) + Rr * fold;
-          real fnew = fold - res * adinv;
-          if (efc[E_INEQ * NEFC + r] != 0 && fnew < 0) fnew = 0;
+        LANES_NS
+          const real *rc = efc + 4 * r;
+          const real b = rc[0], ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb);
+          const real res = b + L(acc) + mabs(Rs) * fold;
+          real fnew = fold - res * ainv;
+          if (Rs < 0) fnew = mmax(fnew, real(0));
           real delta = fnew - fold;
-          real change = real(0.5) * delta * delta / adinv + delta * res;
+          real change = delta * (real(0.5) * delta * Ad + res);
           if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
           L(impr) -= change;
-          if (l < nv) L(z) += Y[r * YSTRIDE + l] * delta;
-          L(t1) = fnew;
-        ENDL
-        LANES if (l == 0) efc[E_F * NEFC + r] = L(t1); ENDL
+          L(z) += L(yr) * delta;
+          if (l == (r & 31)) { if (r < 32) L(f0) = fnew; else L(f1) = fnew; }
+        ENDL_NS
       }
       ++iters;
       if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
@@ -658,13 +688,14 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
   if (dbg) {
     LANES
       if (l < nv) { dbg[D_QACC + l] = L(qacc); dbg[D_QFRCC + l] = L(qfrc_con); }
-      for (int r = l; r < nefc; r += 32) dbg[D_EFC_F + r] = efc[E_F * NEFC + r];
+      if (l < nefc) dbg[D_EFC_F + l] = L(f0);
+      if (l + 32 < nefc) dbg[D_EFC_F + l + 32] = L(f1);
       if (l == 0) { dbg[D_COUNTS] = (real)nefc; dbg[D_COUNTS + 1] = (real)ncon_used; dbg[D_COUNTS + 2] = (real)nlim; dbg[D_COUNTS + 3] = (real)iters; }
     ENDL
   }
 
   // ================= sensors (mj_sensorPos / Vel / Acc for the Cassie layout) =================
-  real *cst = sm + S_CST;
+  real *cst = E.cst;
   LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc); } ENDL
   LANES
     if (l < 16) cst[CS_SENSOR + l] = cm.enc_scale[l] * qpos[cm.enc_qposadr[l]];   // actuatorpos = gear * q, jointpos = q
@@ -677,7 +708,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real,
       real dif[3] = {sp[0] - L(com0), sp[1] - L(com1), sp[2] - L(com2)};
       // body spatial velocity / acceleration in the c-frame: chain sums over the body's dofs
       real cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, -cm.gravity[0], -cm.gravity[1], -cm.gravity[2]};
-      for (int a = cm.body_lastdof[b]; a >= 0; a = cm.dof_parent[a]) for (int k = 0; k < 6; ++k) { cv[k] += cdof[6 * a + k] * vecs[a]; ca[k] += cdofd[6 * a + k] * vecs[a] + cdof[6 * a + k] * vecs[32 + a]; }
+      for (int k = 0; k < 6; ++k) ca[k] += vecs[96 + k];
+      for (int a = cm.body_lastdof[b]; a >= 0; a = cm.dof_parent[a]) for (int k = 0; k < 6; ++k) { cv[k] += cdof[6 * a + k] * vecs[a]; ca[k] += cdof[6 * a + k] * vecs[32 + a]; }
       real t3[3], vl[3], al[3], lw[3], lv[3], la[3], corr[3];
       cross3(t3, dif, cv); vl[0] = cv[3] - t3[0]; vl[1] = cv[4] - t3[1]; vl[2] = cv[5] - t3[2];
       cross3(t3, dif, ca); al[0] = ca[3] - t3[0]; al[1] = ca[4] - t3[1]; al[2] = ca[5] - t3[2];
@@ -731,10 +763,9 @@ template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
 template <typename real>
-CFN void step_env(const DevModel<real> &cm, real *sm, int *ism, LP(real, qvel), LP(real, qacc_ws), const real *pd, const real *xfrc, real *obs,
-                  int nticks, real *dbg, int *counters) {
+CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), int nticks) {
   DECL_LANE
-  real *cst = sm + S_CST, *vecs = sm + S_VEC;
+  real *cst = E.cst, *vecs = sm + S_VEC, *obs = E.obs; const real *pd = E.pd; int *ism = E.dfilt;
   LV(real, ctrl); LV(real, tq); LV(real, scale_part);
   for (int tick = 0; tick < nticks; ++tick) {
     // ---- pd_input_step (motor-PD branch) + cassie_core_sim_step, lane = motor; both read LAST tick's cassie_out
@@ -818,16 +849,16 @@ CFN void step_env(const DevModel<real> &cm, real *sm, int *ism, LP(real, qvel), 
       ENDL
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
-    for (int s = 0; s < cm.nsub; ++s) mj_substep(cm, sm, qvel, qacc_ws, ctrl, xfrc, (tick == nticks - 1 && s == cm.nsub - 1) ? dbg : (real *)0, counters, true);
+    for (int s = 0; s < cm.nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, ctrl, (tick == nticks - 1 && s == cm.nsub - 1) ? E.dbg : (real *)0, true);
   }
 }
 
 // mj_forward on the current state with zero ctrl: fills sensordata / actuator_velocity (cassie_sim_init, :1029)
 template <typename real>
-CFN void forward_env(const DevModel<real> &cm, real *sm, LP(real, qvel), LP(real, qacc_ws), const real *xfrc, real *dbg, int *counters) {
+CFN void forward_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws)) {
   LV(real, ctrl);
   LANES L(ctrl) = 0; ENDL
-  mj_substep(cm, sm, qvel, qacc_ws, ctrl, xfrc, dbg, counters, false);
+  mj_substep(cm, sm, E, qvel, qacc_ws, ctrl, E.dbg, false);
 }
 
 }  // namespace cassie

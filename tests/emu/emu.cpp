@@ -13,20 +13,21 @@ using namespace cassie;
 
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE]; int counters[8];
+  real qvel[32], qacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX]; int counters[8];
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; return E; }
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
     if (!build_dev_model(hm, dm, err)) return false;
-    sm.assign(S_REALS, 0); ism.assign(S_INTS, 0);
+    sm.assign(S_REALS, 0); ism.assign(DFILT_W, 0);
     std::vector<real> qpos(QPOS_W);
-    init_env_rows(hm, qpos.data(), qvel, qacc_ws, sm.data() + S_CST, ism.data(), xfrc);
+    init_env_rows(hm, qpos.data(), qvel, qacc_ws, cst, ism.data(), xfrc);
     for (int i = 0; i < QPOS_W; i++) sm[S_QPOS + i] = qpos[i];
     std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters);
     forward();
     return true;
   }
-  void forward() { forward_env(dm, sm.data(), qvel, qacc_ws, xfrc, dbg, counters); }
-  void step(int nticks) { step_env(dm, sm.data(), ism.data(), qvel, qacc_ws, pd, xfrc, obs, nticks, dbg, counters); }
+  void forward() { forward_env(dm, sm.data(), ptrs(), qvel, qacc_ws); }
+  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, nticks); }
 };
 
 struct Handle { int fp32; Emu<float> f; Emu<double> d; };
@@ -50,7 +51,7 @@ int emu_get(void *p, const char *name, double *out, int n) {
   Handle *h = (Handle *)p; std::string k(name);
 #define GET(T, E) { const T *src = nullptr; int cnt = 0; \
   if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
-  else if (k == "cst") { src = E.sm.data() + S_CST; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
+  else if (k == "cst") { src = E.cst; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
   else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } \
   if (src) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) out[i] = (double)src[i]; return cnt; } \
   if (k == "dfilt") { int c2 = DFILT_W < n ? DFILT_W : n; for (int i = 0; i < c2; i++) out[i] = E.ism[i]; return c2; } \
@@ -62,7 +63,7 @@ int emu_set(void *p, const char *name, const double *in, int n) {
   Handle *h = (Handle *)p; std::string k(name);
 #define SET(T, E) { T *dst = nullptr; int cnt = 0; \
   if (k == "qpos") { dst = E.sm.data() + S_QPOS; cnt = QPOS_W; } else if (k == "qvel") { dst = E.qvel; cnt = 32; } else if (k == "qacc_ws") { dst = E.qacc_ws; cnt = 32; } \
-  else if (k == "cst") { dst = E.sm.data() + S_CST; cnt = CST_W; } else if (k == "xfrc") { dst = E.xfrc; cnt = XFRC_W; } \
+  else if (k == "cst") { dst = E.cst; cnt = CST_W; } else if (k == "xfrc") { dst = E.xfrc; cnt = XFRC_W; } \
   if (dst) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) dst[i] = (T)in[i]; return cnt; } }
   if (h->fp32) SET(float, h->f) else SET(double, h->d)
   return -1;
