@@ -29,6 +29,7 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
   d.nq = m.nq; d.nv = m.nv; d.nbody = m.nbody; d.njnt = m.njnt; d.neq = m.neq; d.nu = m.nu; d.nM = m.nM; d.iterations = m.iterations;
   d.timestep = (real)m.timestep; d.tolerance = (real)m.tolerance; d.pgs_scale = (real)(1.0 / (m.meaninertia * std::max(1, m.nv)));
   d.nsub = (int)std::lround(5e-4 / m.timestep); if (d.nsub < 1) d.nsub = 1;
+  d.euler_eps = (real)(4 * std::numeric_limits<real>::epsilon());
   double mass = 0; for (int b = 1; b < m.nbody; b++) mass += m.body_mass[b];
   d.root_mass_inv = (real)(1.0 / mass);
   for (int k = 0; k < 3; k++) { d.gravity[k] = (real)m.gravity[k]; d.magnetic[k] = (real)m.magnetic[k]; }
@@ -66,11 +67,26 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     d.dof_body[i] = m.dof_bodyid[i]; d.dof_jnt[i] = m.dof_jntid[i]; d.dof_parent[i] = m.dof_parentid[i]; d.dof_Madr[i] = m.dof_Madr[i];
     d.dof_armature[i] = (real)m.dof_armature[i]; d.dof_damping[i] = (real)m.dof_damping[i]; d.dof_invweight0[i] = (real)m.dof_invweight0[i];
     uint32_t mask = 0; int depth = 0; for (int k = m.dof_parentid[i]; k >= 0; k = m.dof_parentid[k]) { mask |= 1u << k; depth++; }
-    d.dof_ancmask[i] = mask; d.dof_depth[i] = depth;
+    d.dof_ancmask[i] = mask; d.dof_depth[i] = depth; d.dof_Mrow[i] = m.dof_Madr[i] + depth;
+    if (depth > 15) { err = "dof tree deeper than 15"; return false; }
+    { int t = 1; for (int k = m.dof_parentid[i]; k >= 0; k = m.dof_parentid[k]) d.dof_anc[i][t++] = (unsigned char)k; }
+    { int end = i + 1; while (end < m.nv) { int a = end; while (a > i) a = m.dof_parentid[a]; if (a != i) break; end++; } d.dof_subtree_end[i] = end; }
+    if (m.dof_damping[i] > 0) d.has_damping = 1;
     int j = m.dof_jntid[i];
     d.dof_cvelsrc[i] = (m.jnt_type[j] == JNT_BALL) ? m.dof_parentid[m.jnt_dofadr[j]] : m.dof_parentid[i];
   }
   for (int i = m.nv - 1; i >= 0; i--) { int a = m.dof_Madr[i] + 1; for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) { if (d.ntri >= NTRI_MAX) { err = "too many factor entries"; return false; } d.tri[d.ntri++] = ((uint32_t)i << 24) | ((uint32_t)j << 16) | (uint32_t)a; a++; } }
+  // balanced factorisation schedule (falls back to the per-ancestor loop when the table would not fit)
+  { int total = 0; for (int k = 0; k < m.nv; k++) total += d.dof_depth[k] * (d.dof_depth[k] + 1) / 2;
+    d.nfac = 0;
+    if (total <= NFAC_MAX) {
+      int n = 0;
+      for (int k = 0; k < m.nv; k++) {
+        d.fac_start[k] = n; int dk = d.dof_depth[k], kk = m.dof_Madr[k];
+        for (int t = 1; t <= dk; t++) { int i = d.dof_anc[k][t], ia = m.dof_Madr[i]; for (int c = 0; c <= dk - t; c++) d.fac_pairs[n++] = ((uint32_t)t << 24) | ((uint32_t)(kk + t + c) << 12) | (uint32_t)(ia + c); }
+      }
+      d.fac_start[m.nv] = n; d.nfac = n;
+    } }
   // IMU site and its sensors
   int imu = m.site_id("imu");
   if (imu < 0) { err = "site 'imu' not found"; return false; }

@@ -15,6 +15,7 @@ constexpr int ME = 4;         // connect equalities
 constexpr int MU = 10;        // motors
 constexpr int NM_MAX = 320;   // sparse mass-matrix entries (307 for Cassie)
 constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 for Cassie)
+constexpr int NFAC_MAX = 1600; // rank-1 update pairs of the factorisation schedule (1519 for Cassie)
 constexpr int NEFC = 48;      // constraint rows per env (12 equality + limits + 4 per floor contact); excess contacts are dropped and counted
 constexpr int MAXCON = 12;    // contacts per env
 constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
@@ -25,8 +26,8 @@ enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPS
 template <typename real>
 struct DevModel {
   // ---- sizes / options
-  int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, pad0, pad1;
-  real timestep, tolerance, pgs_scale, root_mass_inv;
+  int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, has_damping, pad1;
+  real timestep, tolerance, pgs_scale, root_mass_inv, euler_eps, padr[3];
   real gravity[3], magnetic[3], imu_pos[3], imu_quat[4], imu_mat[9], gyro_cutoff, accel_cutoff;
   // ---- bodies
   int body_parent[MB], body_depth[MB], body_jntadr[MB], body_jntnum[MB], body_lastdof[MB], body_subtree_end[MB];
@@ -36,10 +37,13 @@ struct DevModel {
   int jnt_type[MJ], jnt_qposadr[MJ], jnt_dofadr[MJ], jnt_body[MJ], jnt_limited[MJ];
   real jnt_pos[MJ][3], jnt_axis[MJ][3], jnt_stiffness[MJ], jnt_range[MJ][2], jnt_qpos0[MJ], jnt_qspring[MJ], jnt_solref[MJ][2], jnt_solimp[MJ][5];
   // ---- dofs
-  int dof_body[MV], dof_jnt[MV], dof_parent[MV], dof_Madr[MV], dof_depth[MV], dof_cvelsrc[MV];
+  int dof_body[MV], dof_jnt[MV], dof_parent[MV], dof_Madr[MV], dof_depth[MV], dof_cvelsrc[MV], dof_Mrow[MV], dof_subtree_end[MV];
+  unsigned char dof_anc[MV][16];  // t-th ancestor of a dof (t = 1: parent)
   uint32_t dof_ancmask[MV];
   real dof_armature[MV], dof_damping[MV], dof_invweight0[MV];
   uint32_t tri[NTRI_MAX];     // (i << 24) | (j << 16) | qLD address of L(i,j); i descending, ancestors nearest first
+  int nfac, fac_start[MV + 1], padf[2];
+  uint32_t fac_pairs[NFAC_MAX];  // (t << 24) | (src << 12) | dst: qLD[dst] -= qLD[src] * f_t, grouped by eliminated dof k
   // ---- collision geoms and pairs
   int geom_body[MG], geom_type[MG];
   real geom_pos[MG][3], geom_zaxis[MG][3], geom_size[MG][2];
@@ -83,8 +87,8 @@ constexpr int S_QLD = S_CDOF + 192;             // [320] (qM itself lives in a g
 constexpr int S_DINV = S_QLD + NM_MAX;          // [32]
 constexpr int S_DSQI = S_DINV + 32;             // [32]
 constexpr int S_QPOS = S_DSQI + 32;             // [40]
-constexpr int S_VEC = S_QPOS + 40;              // [4][32] general vectors ([96..101]: cdof_dot*qvel chain sum of the IMU body)
-constexpr int S_GEOM = S_VEC + 128;             // [16][6] world pos + z axis
+constexpr int S_VEC = S_QPOS + 40;              // [5][32] general vectors ([96..101]: cdof_dot*qvel chain sum of the IMU body; [128..159]: exchange buffer)
+constexpr int S_GEOM = S_VEC + 160;             // [16][6] world pos + z axis
 constexpr int S_CON = S_GEOM + 96;              // [MAXCON][16]
 constexpr int S_EFC = S_CON + MAXCON * 16;               // [NEFC][4]: row-build scalars {.., pos, src, ineq} then solver constants {b, 1/A, A, +-R}
 constexpr int S_Y = S_EFC + 4 * NEFC;           // [NEFC][33] constraint matrix; before the constraint stage it holds the temporaries below

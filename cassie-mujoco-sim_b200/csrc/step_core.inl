@@ -29,6 +29,7 @@
 #define LP(T, name) T(&name)[32]
 #define LANE0(v) v[0]
 #define ALLSUM(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ += v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
+#define ALLMAX(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ = s_ > v[i_] ? s_ : v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
 #define BCAST(dst, src, lane) do { auto s_ = src[lane]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = s_; } while (0)
 #define EXSCAN_INT(v, total) do { int a_ = 0; for (int i_ = 0; i_ < 32; ++i_) { int t_ = v[i_]; v[i_] = a_; a_ += t_; } total = a_; } while (0)
 #else
@@ -43,6 +44,7 @@
 #define LP(T, name) T &name
 #define LANE0(v) v
 #define ALLSUM(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o_); } while (0)
+#define ALLMAX(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v = mmax(v, __shfl_xor_sync(0xffffffffu, v, o_)); } while (0)
 #define BCAST(dst, src, lane) dst = __shfl_sync(0xffffffffu, src, lane)
 #define EXSCAN_INT(v, total) do { int x_ = v; for (int o_ = 1; o_ < 32; o_ <<= 1) { int y_ = __shfl_up_sync(0xffffffffu, x_, o_); if (l >= o_) x_ += y_; } total = __shfl_sync(0xffffffffu, x_, 31); v = x_ - v; } while (0)
 #endif
@@ -72,8 +74,16 @@ CFN float mmin(float a, float b) { return fminf(a, b); }
 CFN double mmin(double a, double b) { return fmin(a, b); }
 CFN float mpow(float a, float b) { return powf(a, b); }
 CFN double mpow(double a, double b) { return pow(a, b); }
-CFN void msincos(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
-CFN void msincos(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
+CFN void msincos(float x, float *s, float *c) { sincosf(x, s, c); }
+CFN void msincos(double x, double *s, double *c) { sincos(x, s, c); }
+CFN float mrcp(float x) {
+#ifdef CASSIE_EMU
+  return 1.0f / x;
+#else
+  return __frcp_rn(x);
+#endif
+}
+CFN double mrcp(double x) { return 1.0 / x; }
 template <typename real> CFN real minval();
 template <> CFN float minval<float>() { return 1e-15f; }
 template <> CFN double minval<double>() { return 1e-15; }
@@ -157,65 +167,67 @@ template <typename real> CFN void make_frame(real *f) {
 // in-place factorisation of sm[S_QLD..] (already holding M); writes 1/D and 1/sqrt(D)
 template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm) {
   DECL_LANE
-  real *qLD = sm + S_QLD;
+  real *qLD = sm + S_QLD, *ftmp = sm + S_VEC + 128;
   LV(real, tmp);
   for (int k = cm.nv - 1; k >= 0; --k) {
     const int dk = cm.dof_depth[k];
     if (dk == 0) continue;
-    const int kk = cm.dof_Madr[k]; const uint32_t anc = cm.dof_ancmask[k];
-    LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
-      L(tmp) = 0;
-      if ((anc >> l) & 1u) {
-        const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
-        const real f = qLD[kk + t] / qLD[kk];
-        const real *rk = qLD + kk + t; real *ri = qLD + ia;
-        for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
-        L(tmp) = f;
-      }
-    ENDL
-    LANES if ((anc >> l) & 1u) qLD[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
+    const int kk = cm.dof_Madr[k];
+    if (cm.nfac > 0) {
+      // balanced schedule: the dk(dk+1)/2 independent updates  M(anc_t, .)[c] -= M(k, .)[t+c] * f_t  are dealt round-robin to the lanes
+      LANES L(tmp) = 0; if (l >= 1 && l <= dk) { L(tmp) = qLD[kk + l] * mrcp(qLD[kk]); ftmp[l] = L(tmp); } ENDL
+      const int p0 = cm.fac_start[k], p1 = cm.fac_start[k + 1];
+      LANES
+        for (int p = p0 + l; p < p1; p += 32) { const uint32_t e = cm.fac_pairs[p]; qLD[e & 0xfffu] -= qLD[(e >> 12) & 0xfffu] * ftmp[e >> 24]; }
+      ENDL
+      LANES if (l >= 1 && l <= dk) qLD[kk + l] = L(tmp); ENDL
+    } else {
+      const uint32_t anc = cm.dof_ancmask[k];
+      LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
+        L(tmp) = 0;
+        if ((anc >> l) & 1u) {
+          const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
+          const real f = qLD[kk + t] / qLD[kk];
+          const real *rk = qLD + kk + t; real *ri = qLD + ia;
+          for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
+          L(tmp) = f;
+        }
+      ENDL
+      LANES if ((anc >> l) & 1u) qLD[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
+    }
   }
-  LANES if (l < cm.nv) { real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = real(1) / d; sm[S_DSQI + l] = real(1) / msqrt(d); } ENDL
+  LANES if (l < cm.nv) { const real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = mrcp(d); sm[S_DSQI + l] = mrcp(msqrt(d)); } ENDL
 }
-// x <- inv(L') x   (x: one value per lane = dof)
-template <typename real> CFN void solve_lt(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+// triangular sweeps on the factorisation in sm[S_QLD..] (one value per lane = dof); each is nv broadcast steps
+// x <- inv(L') x
+template <typename real> CFN void sweep_lt(const DevModel<real> &cm, const real *sm, LP(real, x)) {
   DECL_LANE
-  LV(real, xi);
+  LV(real, xi); LV(int, dl);
+  LANES_NS L(dl) = (l < cm.nv) ? cm.dof_depth[l] : 0; ENDL_NS
   for (int i = cm.nv - 1; i >= 0; --i) {
     if (cm.dof_depth[i] == 0) continue;
     BCAST(xi, x, i);
-    const uint32_t anc = cm.dof_ancmask[i]; const int base = S_QLD + cm.dof_Madr[i] + cm.dof_depth[i];
-    LANES if ((anc >> l) & 1u) L(x) -= sm[base - cm.dof_depth[l]] * L(xi); ENDL
+    const uint32_t anc = cm.dof_ancmask[i]; const int base = S_QLD + cm.dof_Mrow[i];
+    LANES_NS if ((anc >> l) & 1u) L(x) -= sm[base - L(dl)] * L(xi); ENDL_NS
   }
 }
 // x <- inv(L) x
-template <typename real> CFN void solve_l(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+template <typename real> CFN void sweep_l(const DevModel<real> &cm, const real *sm, LP(real, x)) {
   DECL_LANE
-  LV(real, xj);
+  LV(real, xi); LV(int, ptr); LV(uint32_t, ancl);
+  // lane l walks its row of L from the root-most ancestor entry towards the diagonal: ancestors arrive in increasing dof order
+  LANES_NS L(ptr) = (l < cm.nv) ? S_QLD + cm.dof_Mrow[l] : 0; L(ancl) = (l < cm.nv) ? cm.dof_ancmask[l] : 0u; ENDL_NS
   for (int j = 0; j < cm.nv; ++j) {
-    BCAST(xj, x, j);
-    const int dj = cm.dof_depth[j];
-    LANES if (l < cm.nv && ((cm.dof_ancmask[l] >> j) & 1u)) L(x) -= sm[S_QLD + cm.dof_Madr[l] + cm.dof_depth[l] - dj] * L(xj); ENDL
+    BCAST(xi, x, j);
+    LANES_NS if ((L(ancl) >> j) & 1u) { L(x) -= sm[L(ptr)] * L(xi); L(ptr) -= 1; } ENDL_NS
   }
 }
-// x <- inv(M) x
+// x <- inv(L'DL) x
 template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *sm, LP(real, x)) {
   DECL_LANE
-  solve_lt(cm, sm, x);
-  LANES if (l < cm.nv) L(x) *= sm[S_DINV + l]; ENDL
-  solve_l(cm, sm, x);
-}
-// y <- L' x  (used for J'f = L' D^{1/2} z)
-template <typename real> CFN void mul_lt(const DevModel<real> &cm, const real *sm, LP(real, x), LP(real, y)) {
-  DECL_LANE
-  LV(real, xi);
-  LANES L(y) = L(x); ENDL
-  for (int i = cm.nv - 1; i >= 0; --i) {
-    if (cm.dof_depth[i] == 0) continue;
-    BCAST(xi, x, i);
-    const uint32_t anc = cm.dof_ancmask[i]; const int base = S_QLD + cm.dof_Madr[i] + cm.dof_depth[i];
-    LANES if ((anc >> l) & 1u) L(y) += sm[base - cm.dof_depth[l]] * L(xi); ENDL
-  }
+  sweep_lt(cm, sm, x);
+  LANES_NS if (l < cm.nv) L(x) *= sm[S_DINV + l]; ENDL_NS
+  sweep_l(cm, sm, x);
 }
 
 // translational Jacobian column of dof l for a world point attached to `body` (zero when l is not in the body's chain)
@@ -359,6 +371,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
   factor_ld(cm, sm);
+  if (dbg) { LANES for (int a = l; a < cm.nM; a += 32) { dbg[D_QM + a] = qM[a]; dbg[D_QLD + a] = qLD[a]; } ENDL }
 
   // ================= velocity stage: comVel, passive, RNE bias =================
   real *S = sm + S_Y + T_CRB;      // chain sums [32][6] (crb is dead)
@@ -442,7 +455,6 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     LANES
       if (l < nv) { dbg[D_SMOOTH + l] = L(qfrc_smooth); dbg[D_QACCS + l] = L(qacc_smooth); for (int k = 0; k < 6; ++k) dbg[D_CDOF + 6 * l + k] = cdof[6 * l + k]; }
       if (l < nb) { for (int k = 0; k < 3; ++k) dbg[D_XPOS + 3 * l + k] = xpos[3 * l + k]; for (int k = 0; k < 4; ++k) dbg[D_XQUAT + 4 * l + k] = xquat[4 * l + k]; }
-      for (int a = l; a < cm.nM; a += 32) { dbg[D_QM + a] = qM[a]; dbg[D_QLD + a] = qLD[a]; }
     ENDL
   }
 
@@ -626,9 +638,12 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (ineq && jar >= 0) f = 0;
           if (pass == 0) L(f0) = f; else L(f1) = f;
           if (dbg) { dbg[D_EFC_AREF + r] = aref; dbg[D_EFC_R + r] = Rr; dbg[D_EFC_B + r] = ja - aref; }
-          // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place
-          { int ci = -1; real xi = 0;
-            for (int k = 0; k < cm.ntri; ++k) { const uint32_t t = cm.tri[k]; const int i = (int)(t >> 24); if (i != ci) { ci = i; xi = yy[i]; } yy[(t >> 16) & 255u] -= qLD[t & 0xffffu] * xi; } }
+          // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place; all lanes (rows) walk the same (i, ancestor) sequence
+          for (int i = nv - 1; i > 0; --i) {
+            const int di = cm.dof_depth[i]; if (di == 0) continue;
+            const real xi = yy[i]; const real *Li = qLD + cm.dof_Madr[i]; const unsigned char *an = cm.dof_anc[i];
+            for (int t = 1; t <= di; ++t) yy[an[t]] -= Li[t] * xi;
+          }
           real ad = 0;
           for (int d = 0; d < nv; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
           // packed row constants for the solver: b, 1/A, A, +-R (sign bit set = inequality row)
@@ -656,8 +671,9 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     LV(real, acc); LV(real, impr); LV(real, yr);
     while (iters < cm.iterations) {
       LANES L(impr) = 0; ENDL
-      for (int r = 0; r < nefc; ++r) {
-        if (r < 32) { BCAST(fb, f0, r); } else { BCAST(fb, f1, r - 32); }
+      const int n0 = nefc < 32 ? nefc : 32;
+      for (int r = 0; r < n0; ++r) {
+        BCAST(fb, f0, r);
         LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
         ALLSUM(acc);
         LANES_NS
@@ -671,7 +687,25 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
           L(impr) -= change;
           L(z) += L(yr) * delta;
-          if (l == (r & 31)) { if (r < 32) L(f0) = fnew; else L(f1) = fnew; }
+          if (l == r) L(f0) = fnew;
+        ENDL_NS
+      }
+      for (int r = 32; r < nefc; ++r) {
+        BCAST(fb, f1, r - 32);
+        LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
+        ALLSUM(acc);
+        LANES_NS
+          const real *rc = efc + 4 * r;
+          const real b = rc[0], ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb);
+          const real res = b + L(acc) + mabs(Rs) * fold;
+          real fnew = fold - res * ainv;
+          if (Rs < 0) fnew = mmax(fnew, real(0));
+          real delta = fnew - fold;
+          real change = delta * (real(0.5) * delta * Ad + res);
+          if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+          L(impr) -= change;
+          L(z) += L(yr) * delta;
+          if (l == r - 32) L(f1) = fnew;
         ENDL_NS
       }
       ++iters;
@@ -680,9 +714,19 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     // ---- qacc = qacc_smooth + inv(L) D^-1/2 z ;  qfrc_constraint = J'f = L' D^1/2 z
     LV(real, w);
     LANES L(w) = (l < nv) ? L(z) * sm[S_DSQI + l] : real(0); ENDL
-    solve_l(cm, sm, w);
-    LANES L(qacc) = L(qacc_smooth) + L(w); L(w) = (l < nv) ? L(z) / sm[S_DSQI + l] : real(0); ENDL
-    mul_lt(cm, sm, w, qfrc_con);
+    sweep_l(cm, sm, w);
+    LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; ENDL
+    if (dbg) {  // qfrc_constraint = M (qacc - qacc_smooth); only the debug dump wants it (the Euler stage below does not)
+      LANES vecs[128 + l] = L(w); ENDL
+      LANES
+        if (l < nv) {
+          real sacc = 0; int a = cm.dof_Madr[l];
+          for (int j = l; j >= 0; j = cm.dof_parent[j]) sacc += qM[a++] * vecs[128 + j];
+          for (int i = l + 1; i < cm.dof_subtree_end[l]; ++i) sacc += qM[cm.dof_Madr[i] + cm.dof_depth[i] - cm.dof_depth[l]] * vecs[128 + i];
+          L(qfrc_con) = sacc;
+        }
+      ENDL
+    }
   }
   if (counters) { LANES if (l == 0) counters[3] = iters; ENDL }
   if (dbg) {
@@ -729,14 +773,16 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
 
   if (!advance) return;   // mj_forward only (used once at init / reset to populate sensordata, src/cassiemujoco.c:1029)
   // ================= Euler with implicit joint damping (mj_Euler) + mj_advance =================
-  LANES  // MhB = M + h diag(damping), refactor in the qLD buffer
-    for (int a = l; a < cm.nM; a += 32) qLD[a] = qM[a];
-  ENDL
-  LANES if (l < nv) qLD[cm.dof_Madr[l]] += cm.timestep * cm.dof_damping[l]; ENDL
-  factor_ld(cm, sm);
+  // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
-  LANES L(a) = (l < nv) ? L(qfrc_smooth) + L(qfrc_con) : real(0); ENDL
-  solve_m(cm, sm, a);
+  if (cm.has_damping) {
+    LANES for (int k = l; k < cm.nM; k += 32) qLD[k] = qM[k]; ENDL          // the inverse factor of M is dead: reuse its buffer
+    LANES if (l < nv) qLD[cm.dof_Madr[l]] += cm.timestep * cm.dof_damping[l]; ENDL
+    factor_ld(cm, sm);
+    LANES L(a) = (l < nv) ? cm.timestep * cm.dof_damping[l] * L(qacc) : real(0); ENDL
+    solve_m(cm, sm, a);
+    LANES L(a) = L(qacc) - L(a); ENDL
+  } else { LANES L(a) = L(qacc); ENDL }
   LANES if (l < nv) { L(qvel) += cm.timestep * L(a); vecs[l] = L(qvel); L(qacc_ws) = L(qacc); } ENDL
   LANES  // lane = joint: integrate positions with the NEW velocity
     if (l < cm.njnt) {
