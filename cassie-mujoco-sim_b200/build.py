@@ -21,7 +21,7 @@ def nvcc():
 def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS):
         return LIB
-    cmd = [nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
+    cmd = [nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-shared', '-Xcompiler', '-fPIC,-fopenmp', '-lgomp',
            '-Xptxas', '-v' if verbose else '-O3', '-o', LIB] + SRCS
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/cassie_b200.h"
@@ -22,7 +23,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters; int n;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters, *ticket; int n;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,45 +54,104 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   __shared__ __align__(8) uint64_t bar;
   DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
   tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
-  const int warp = threadIdx.x >> 5, l = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (env >= A.n) return;
+  const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
   real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>());
   const DevModel<real> &cm = *cmp;
-  // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
-  for (int i = l; i < QPOS_W; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * QPOS_W + i];
-  real qvel = A.qvel[(size_t)env * QVEL_W + l], qacc_ws = A.qacc_ws[(size_t)env * QVEL_W + l];
-  __syncwarp();
-  EnvPtrs<real> E;
-  E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
-  E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-  if (mode == 0) step_env(cm, sm, E, qvel, qacc_ws, nticks);
-  else forward_env(cm, sm, E, qvel, qacc_ws);
-  __syncwarp();
-  for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
-  A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;
+  // persistent warps: every warp pulls environment indices from a global ticket counter until the batch is exhausted, so a warp
+  // that drew a cheap environment (few contacts, few solver sweeps) immediately starts another one
+  for (;;) {
+    int env = 0;
+    if (l == 0) env = atomicAdd(A.ticket, 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= A.n) break;
+    // warm the L2/L1 path of the rows that are addressed in place later (controller state, PD row, FIR taps)
+    if (l < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cst + (size_t)env * CST_W + 32 * l));
+    else if (l < 9) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dfilt + (size_t)env * DFILT_W + 32 * (l - 6)));
+    else if (l < 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pd + (size_t)env * PD_W + 32 * (l - 9)));
+    else if (l == 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.xfrc + (size_t)env * XFRC_W));
+    // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
+    for (int i = l; i < QPOS_W; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * QPOS_W + i];
+    real qvel = A.qvel[(size_t)env * QVEL_W + l], qacc_ws = A.qacc_ws[(size_t)env * QVEL_W + l];
+    __syncwarp();
+    EnvPtrs<real> E;
+    E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
+    E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
+    if (mode == 0) step_env(cm, sm, E, qvel, qacc_ws, nticks);
+    else forward_env(cm, sm, E, qvel, qacc_ws);
+    __syncwarp();
+    for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
+    A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;
+    __syncwarp();
+  }
 }
 
-// cassie_integrate_pos for the whole batch (mj_integratePos): the HBM-bound kernel.  One thread per (env, joint).
+// cassie_integrate_pos for the whole batch (mj_integratePos, src/cassiemujoco.c:1183-1189): the HBM-bound kernel.
+// A tile of ITILE consecutive environments is one contiguous chunk of the qpos array and one of the qvel array.  Persistent CTAs
+// stream tiles through an ISTAGES-deep shared-memory ring: TMA bulk loads (cp.async.bulk -> mbarrier), in-place arithmetic,
+// TMA bulk store of the qpos chunk.  Algorithmic traffic per env: read qpos + qvel, write qpos = (36 + 32 + 36) reals.
+constexpr int ITILE = 64, ISTAGES = 4;
+template <typename real> __host__ __device__ constexpr size_t itile_bytes() { return (size_t)ITILE * (QPOS_W + QVEL_W) * sizeof(real); }
 template <typename real>
-__global__ void cassie_integrate_kernel(const DevModel<real> *__restrict__ gmodel, real *__restrict__ qpos, const real *__restrict__ qvel, int n) {
-  __shared__ int jt[MJ], jq[MJ], jd[MJ];
-  __shared__ int njnt; __shared__ real h;
-  if (threadIdx.x < MJ) { jt[threadIdx.x] = gmodel->jnt_type[threadIdx.x]; jq[threadIdx.x] = gmodel->jnt_qposadr[threadIdx.x]; jd[threadIdx.x] = gmodel->jnt_dofadr[threadIdx.x]; }
-  if (threadIdx.x == 0) { njnt = gmodel->njnt; h = gmodel->timestep; }
-  __syncthreads();
-  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int env = (int)(gid >> 5), j = (int)(gid & 31);
-  if (env >= n || j >= njnt) return;
-  real *q = qpos + (size_t)env * QPOS_W + jq[j]; const real *v = qvel + (size_t)env * QVEL_W + jd[j];
-  if (jt[j] >= 2) q[0] += h * v[0];
-  else if (jt[j] == 1) {
-    real wv[3] = {v[0], v[1], v[2]}, qq[4] = {q[0], q[1], q[2], q[3]}, qr[4], s, c;
-    const real ang = h * normalize3(wv);
-    msincos(real(0.5) * ang, &s, &c); qr[0] = c; qr[1] = wv[0] * s; qr[2] = wv[1] * s; qr[3] = wv[2] * s;
-    if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
-    normalize4(qq); mul_quat(qq, qq, qr);
-    q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+__global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<real> *__restrict__ gmodel, real *__restrict__ qpos, const real *__restrict__ qvel, int n) {
+  extern __shared__ __align__(128) unsigned char ibuf[];
+  __shared__ __align__(8) uint64_t bar[ISTAGES];
+  __shared__ int ns, nb, sq_adr[MJ], sd_adr[MJ], bq_adr[MJ], bd_adr[MJ];
+  __shared__ real h;
+  const int ntiles = (n + ITILE - 1) / ITILE;
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int j = 0; j < gmodel->njnt; ++j) {
+      const int t = gmodel->jnt_type[j];
+      if (t >= 2) { sq_adr[a] = gmodel->jnt_qposadr[j]; sd_adr[a] = gmodel->jnt_dofadr[j]; ++a; } else if (t == 1) { bq_adr[b] = gmodel->jnt_qposadr[j]; bd_adr[b] = gmodel->jnt_dofadr[j]; ++b; }
+    }
+    ns = a; nb = b; h = gmodel->timestep;
+    for (int s = 0; s < ISTAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  auto issue_load = [&](int stage, int tile) {   // thread 0 only
+    const int cnt = min(ITILE, n - tile * ITILE);
+    const uint32_t bq = (uint32_t)(cnt * QPOS_W * sizeof(real)), bv = (uint32_t)(cnt * QVEL_W * sizeof(real));
+    unsigned char *dst = ibuf + (size_t)stage * itile_bytes<real>();
+    const uint32_t bar_a = smem_u32(&bar[stage]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bq + bv) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(qpos + (size_t)tile * ITILE * QPOS_W), "r"(bq), "r"(bar_a) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst + (size_t)ITILE * QPOS_W * sizeof(real))), "l"(qvel + (size_t)tile * ITILE * QVEL_W), "r"(bv), "r"(bar_a) : "memory");
+  };
+  if (threadIdx.x == 0) for (int s = 0; s < ISTAGES; ++s) { const int tile = blockIdx.x + s * gridDim.x; if (tile < ntiles) issue_load(s, tile); }
+  for (int i = 0;; ++i) {
+    const int tile = blockIdx.x + i * gridDim.x;
+    if (tile >= ntiles) break;
+    const int stage = i % ISTAGES; const uint32_t parity = (uint32_t)((i / ISTAGES) & 1), bar_a = smem_u32(&bar[stage]);
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(bar_a), "r"(parity) : "memory");
+    real *sq = reinterpret_cast<real *>(ibuf + (size_t)stage * itile_bytes<real>()); const real *sv = sq + ITILE * QPOS_W;
+    const int cnt = min(ITILE, n - tile * ITILE);
+    // scalar joints: lane = joint, warps stride over the tile's environments (a row's 36 entries sit in distinct banks);
+    // ball joints: thread = (env, ball joint), dense, no divergence
+    {
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      if (lane < ns) { const int qa = sq_adr[lane], da = sd_adr[lane]; for (int e = wid; e < cnt; e += nw) sq[e * QPOS_W + qa] += h * sv[e * QVEL_W + da]; }
+      for (int w = threadIdx.x; w < cnt * nb; w += blockDim.x) {
+        const int e = w / nb, k = w - e * nb;
+        real *q = sq + e * QPOS_W + bq_adr[k]; const real *v = sv + e * QVEL_W + bd_adr[k];
+        real wv[3] = {v[0], v[1], v[2]}, qq[4] = {q[0], q[1], q[2], q[3]}, qr[4], s, c;
+        const real ang = h * normalize3(wv);
+        msincos(real(0.5) * ang, &s, &c); qr[0] = c; qr[1] = wv[0] * s; qr[2] = wv[1] * s; qr[3] = wv[2] * s;
+        if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
+        normalize4(qq); mul_quat(qq, qq, qr);
+        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(qpos + (size_t)tile * ITILE * QPOS_W), "r"(smem_u32(sq)), "r"((uint32_t)(cnt * QPOS_W * sizeof(real))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      const int next = tile + ISTAGES * gridDim.x;
+      if (next < ntiles) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); issue_load(stage, next); }
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ host side
@@ -109,16 +169,19 @@ struct BatchBase {
   virtual void *dev_ptr(const char *field) = 0;
   virtual bool get_counters(int *out) = 0;
   virtual int debug_dump(int env, double *out, int cnt) = 0;
+  virtual bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) = 0;
   bool sync() { CUDA_OK(cudaStreamSynchronize(stream)); return true; }
 };
 
 template <typename real> struct Batch : BatchBase {
-  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0;
+  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0; int resident_ctas = 1;
   std::vector<real> h_tmp;
+  real *pin_pd = nullptr, *pin_obs = nullptr;   // pinned staging for the AoS entry point
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket);
+    if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
   bool init() override {
@@ -131,7 +194,7 @@ template <typename real> struct Batch : BatchBase {
     A.n = n;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QPOS_W)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * QVEL_W)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * QVEL_W));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
-    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * NM_MAX));
+    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * NM_MAX)); CUDA_OK(cudaMalloc(&A.ticket, sizeof(int)));
     CUDA_OK(cudaMemset(A.pd, 0, sizeof(real) * n * PD_W)); CUDA_OK(cudaMemset(A.obs, 0, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMemset(A.counters, 0, sizeof(int) * n * 8));
     if (debug) { CUDA_OK(cudaMalloc(&A.dbg, sizeof(real) * n * D_SIZE)); CUDA_OK(cudaMemset(A.dbg, 0, sizeof(real) * n * D_SIZE)); }
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true;
@@ -154,6 +217,8 @@ template <typename real> struct Batch : BatchBase {
     if (wpb < 1 || wpb > 16 || model_bytes<real>() + (size_t)wpb * warp_bytes<real>() > (size_t)dev_smem) { set_err("not enough shared memory per block"); return false; }
     smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>();
     CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int per_sm = 0, sms = 0; CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real>, 32 * wpb, smem));
+      CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)); resident_ctas = per_sm * sms; if (resident_ctas < 1) resident_ctas = 1; }
     return reset(nullptr);
   }
   bool reset(const unsigned char *mask) override {
@@ -188,9 +253,41 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaStreamSynchronize(stream));   // h_tmp is pageable and reused
     return true;
   }
+  // cassie_sim_step_pd for every env with host AoS buffers: pack pd_in_t[] -> pinned rows -> H2D, one tick, D2H rows -> state_out_t[]
+  bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (!pin_pd) { CUDA_OK(cudaMallocHost(&pin_pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMallocHost(&pin_obs, sizeof(real) * n * OBS_W)); }
+#pragma omp parallel for schedule(static) num_threads(8) if (n >= 512)
+    for (int e = 0; e < n; e++) {
+      real *row = pin_pd + (size_t)e * PD_W; const pd_in_t *u = pd_in + e;
+      for (int i = 0; i < 10; i++) {
+        const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; const int k = i % 5;
+        row[i] = (real)p->torque[k]; row[10 + i] = (real)p->pTarget[k]; row[20 + i] = (real)p->dTarget[k]; row[30 + i] = (real)p->pGain[k]; row[40 + i] = (real)p->dGain[k];
+      }
+      row[50] = row[51] = 0;
+    }
+    CUDA_OK(cudaMemcpyAsync(A.pd, pin_pd, sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));
+    if (!step(1, 0)) return false;
+    if (!state_out) return sync();
+    CUDA_OK(cudaMemcpyAsync(pin_obs, A.obs, sizeof(real) * n * OBS_W, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+#pragma omp parallel for schedule(static) num_threads(8) if (n >= 512)
+    for (int e = 0; e < n; e++) {
+      const real *o = pin_obs + (size_t)e * OBS_W; state_out_t *y = state_out + e;
+      memset(y, 0, sizeof *y);
+      for (int i = 0; i < 10; i++) { y->motor.position[i] = o[OB_MPOS + i]; y->motor.velocity[i] = o[OB_MVEL + i]; y->motor.torque[i] = o[OB_MTORQUE + i]; }
+      for (int i = 0; i < 6; i++) { y->joint.position[i] = o[OB_JPOS + i]; y->joint.velocity[i] = o[OB_JVEL + i]; }
+      for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_QUAT + i];
+      for (int i = 0; i < 3; i++) { y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_ACCEL + i]; }
+      for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
+      y->radio.signalGood = true; y->battery.stateOfCharge = 1;
+    }
+    return true;
+  }
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
-    const int grid = (n + wpb - 1) / wpb;
+    int grid = (n + wpb - 1) / wpb; if (grid > resident_ctas) grid = resident_ctas;
+    CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
     cassie_step_kernel<real><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);
     launches++;
     CUDA_OK(cudaGetLastError());
@@ -198,8 +295,13 @@ template <typename real> struct Batch : BatchBase {
   }
   bool integrate() override {
     CUDA_OK(cudaSetDevice(device));
-    const long threads = (long)n * 32; const int bs = 256;
-    cassie_integrate_kernel<real><<<(unsigned)((threads + bs - 1) / bs), bs, 0, stream>>>(d_model, A.qpos, A.qvel, n);
+    const int ntiles = (n + ITILE - 1) / ITILE; int sms = 0; CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const size_t ib = ISTAGES * itile_bytes<real>();
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(cassie_integrate_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ib)); attr_set = true; }
+    const int per_sm = sizeof(real) == 4 ? 3 : 1;
+    const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
+    cassie_integrate_kernel<real><<<grid, 256, ib, stream>>>(d_model, A.qpos, A.qvel, n);
     launches++;
     CUDA_OK(cudaGetLastError());
     return true;
@@ -323,32 +425,8 @@ void *cassie_batch_get_stream(cassie_batch_t *b) { return (void *)b->impl->strea
 void cassie_batch_get_counters(cassie_batch_t *b, int *out) { b->impl->get_counters(out); }
 int cassie_batch_debug_dump(cassie_batch_t *b, int env, double *out, int n) { return b->impl->debug_dump(env, out, n); }
 
-static void pd_to_row(const pd_in_t *u, double *row) {
-  for (int i = 0; i < 10; i++) {
-    const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; int k = i % 5;
-    row[i] = p->torque[k]; row[10 + i] = p->pTarget[k]; row[20 + i] = p->dTarget[k]; row[30 + i] = p->pGain[k]; row[40 + i] = p->dGain[k];
-  }
-  row[50] = row[51] = 0;
-}
-static void obs_to_state_out(const double *o, const double *radio, state_out_t *y) {
-  memset(y, 0, sizeof *y);
-  for (int i = 0; i < 10; i++) { y->motor.position[i] = o[OB_MPOS + i]; y->motor.velocity[i] = o[OB_MVEL + i]; y->motor.torque[i] = o[OB_MTORQUE + i]; }
-  for (int i = 0; i < 6; i++) { y->joint.position[i] = o[OB_JPOS + i]; y->joint.velocity[i] = o[OB_JVEL + i]; }
-  for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_QUAT + i];
-  for (int i = 0; i < 3; i++) { y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_ACCEL + i]; }
-  for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[i];
-  y->radio.signalGood = true; y->battery.stateOfCharge = 1;
-}
 void cassie_sim_step_pd_batch(cassie_batch_t *b, const pd_in_t *pd_in, state_out_t *state_out) {
-  const int n = b->impl->n;
-  std::vector<double> rows((size_t)n * PD_W);
-  for (int e = 0; e < n; e++) pd_to_row(&pd_in[e], &rows[(size_t)e * PD_W]);
-  b->impl->set_pd(rows.data());
-  b->impl->step(1, 0);
-  if (state_out) {
-    b->obs.resize((size_t)n * OBS_W); b->impl->get("obs", b->obs.data());
-    for (int e = 0; e < n; e++) obs_to_state_out(&b->obs[(size_t)e * OBS_W], &b->radio[(size_t)e * 16], &state_out[e]);
-  } else b->impl->sync();
+  b->impl->step_pd_aos(pd_in, state_out, b->radio.data());
 }
 
 // ---------------- legacy single-environment verbs

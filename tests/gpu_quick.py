@@ -11,7 +11,9 @@ if len(sys.argv) > 1:
     cfgs = [(P.FP32, 4096, 1), (P.FP32, 4096, 50)]
 for prec, n, nt in cfgs:
     b = P.CassieBatch(n, precision=prec)
-    b.set_pd(P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
+    rng = np.random.default_rng(0)
+    jit = 0.05 if os.environ.get('JITTER') else 0.0
+    b.set_pd(P.pd_rows(n, pTarget=np.array(PD_TARGET) + rng.uniform(-jit, jit, (n, 10)), pGain=PD_PGAIN, dGain=PD_DGAIN))
     b.set_stream(torch.cuda.current_stream().cuda_stream)
     for _ in range(3): b.step(nt)
     b.sync()
