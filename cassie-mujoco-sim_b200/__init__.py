@@ -118,6 +118,11 @@ def lib():
         getattr(L, n).argtypes = [vp, cd]
     L.cassie_batch_apply_force.argtypes = [vp, cd, C.c_char_p]
     L.cassie_batch_apply_force.restype = ci
+    L.cassie_batch_set_hfielddata.argtypes = [vp, C.POINTER(C.c_float), ci]
+    L.cassie_batch_set_hfielddata.restype = ci
+    for n in ('cassie_batch_hfield_nrow', 'cassie_batch_hfield_ncol'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = ci
     L.cassie_batch_device_ptr.argtypes = [vp, C.c_char_p]
     L.cassie_batch_device_ptr.restype = vp
     L.cassie_batch_set_stream.argtypes = [vp, vp]
@@ -258,6 +263,14 @@ class CassieBatch:
 
     def clear_forces(self):
         self.L.cassie_batch_clear_forces(self.h)
+
+    def set_hfield_data(self, data):
+        """data: [K, nrow, ncol] (or [nrow, ncol]) normalised elevations; env e uses terrain e % K."""
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        nrow, ncol = self.L.cassie_batch_hfield_nrow(self.h), self.L.cassie_batch_hfield_ncol(self.h)
+        a = a.reshape(-1, nrow, ncol)
+        if self.L.cassie_batch_set_hfielddata(self.h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0]) != 0:
+            raise RuntimeError(_last_error())
 
     def counters(self):
         out = np.zeros((self.n, 8), dtype=np.int32)

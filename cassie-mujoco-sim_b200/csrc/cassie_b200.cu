@@ -23,7 +23,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters, *ticket; int n;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters, *ticket; const float *hfield; int n, n_terrain; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     __syncwarp();
     EnvPtrs<real> E;
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
+    E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
     if (mode == 0) step_env(cm, sm, E, qvel, qacc_ws, nticks);
     else forward_env(cm, sm, E, qvel, qacc_ws);
@@ -170,6 +171,7 @@ struct BatchBase {
   virtual bool get_counters(int *out) = 0;
   virtual int debug_dump(int env, double *out, int cnt) = 0;
   virtual bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) = 0;
+  virtual bool set_hfield(const float *data, int n_terrains) = 0;
   bool sync() { CUDA_OK(cudaStreamSynchronize(stream)); return true; }
 };
 
@@ -177,11 +179,12 @@ template <typename real> struct Batch : BatchBase {
   DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0; int resident_ctas = 1;
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr;   // pinned staging for the AoS entry point
+  float *d_hfield = nullptr;
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
     cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket);
-    if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs);
+    if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
   bool init() override {
@@ -191,7 +194,8 @@ template <typename real> struct Batch : BatchBase {
     if (info.unsupported_pairs) fprintf(stderr, "cassie_b200: note: %d candidate geom pairs involve box/hfield geoms that this build does not collide (skipped)\n", info.unsupported_pairs);
     CUDA_OK(cudaMalloc(&d_model, model_bytes<real>()));
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice)); free(hmodel);
-    A.n = n;
+    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0;
+    if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QPOS_W)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * QVEL_W)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * QVEL_W));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
     CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * NM_MAX)); CUDA_OK(cudaMalloc(&A.ticket, sizeof(int)));
@@ -284,6 +288,19 @@ template <typename real> struct Batch : BatchBase {
     }
     return true;
   }
+  // K terrains of nrow*ncol normalised elevations; environment e stands on terrain e % K (cassie_sim_set_hfielddata, src/cassiemujoco.c:2076-2080)
+  bool set_hfield(const float *data, int n_terrains) override {
+    if (hm.nhfield != 1 || n_terrains < 1) { set_err("this model has no height field"); return false; }
+    CUDA_OK(cudaSetDevice(device));
+    const size_t cells = (size_t)hm.hfield_nrow[0] * hm.hfield_ncol[0];
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (d_hfield) CUDA_OK(cudaFree(d_hfield));
+    CUDA_OK(cudaMalloc(&d_hfield, sizeof(float) * cells * n_terrains));
+    if (data) CUDA_OK(cudaMemcpy(d_hfield, data, sizeof(float) * cells * n_terrains, cudaMemcpyHostToDevice));
+    else CUDA_OK(cudaMemset(d_hfield, 0, sizeof(float) * cells * n_terrains));
+    A.hfield = d_hfield; A.n_terrain = n_terrains; A.hfield_stride = cells;
+    return true;
+  }
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
     int grid = (n + wpb - 1) / wpb; if (grid > resident_ctas) grid = resident_ctas;
@@ -371,7 +388,7 @@ template <typename real> struct Batch : BatchBase {
 // ====================================================================== C-ABI
 using namespace cassie;
 struct cassie_batch { BatchBase *impl; std::vector<double> obs, radio; };
-struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev; };
+struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev; std::vector<float> hfield, hfield_dev; };
 
 static std::mutex g_model_mutex;
 static std::string g_model_path;   // what cassie_mujoco_init cached (the reference caches the parsed model, src/cassiemujoco.c:48-59)
@@ -419,6 +436,9 @@ int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *
 }
 void cassie_batch_clear_forces(cassie_batch_t *b) { b->impl->set_xfrc(nullptr, 0); }
 void cassie_batch_integrate_pos(cassie_batch_t *b) { b->impl->integrate(); }
+int cassie_batch_set_hfielddata(cassie_batch_t *b, const float *data, int n_terrains) { return b->impl->set_hfield(data, n_terrains) ? 0 : -1; }
+int cassie_batch_hfield_nrow(const cassie_batch_t *b) { return b->impl->hm.nhfield ? b->impl->hm.hfield_nrow[0] : 0; }
+int cassie_batch_hfield_ncol(const cassie_batch_t *b) { return b->impl->hm.nhfield ? b->impl->hm.hfield_ncol[0] : 0; }
 void *cassie_batch_device_ptr(cassie_batch_t *b, const char *field) { return b->impl->dev_ptr(field); }
 void cassie_batch_set_stream(cassie_batch_t *b, void *s) { b->impl->sync(); if (b->impl->own_stream && b->impl->stream) cudaStreamDestroy(b->impl->stream); b->impl->stream = (cudaStream_t)s; b->impl->own_stream = false; }
 void *cassie_batch_get_stream(cassie_batch_t *b) { return (void *)b->impl->stream; }
@@ -447,6 +467,7 @@ static void sim_push(cassie_sim_t *c) {  // upload whatever the caller wrote thr
   if (memcmp(c->qpos_dev, c->qpos, sizeof c->qpos)) c->b->impl->set("qpos", c->qpos);
   if (memcmp(c->qvel_dev, c->qvel, sizeof c->qvel)) c->b->impl->set("qvel", c->qvel);
   if (c->time_dev != c->time) c->b->impl->set("time", &c->time);
+  if (!c->hfield.empty() && c->hfield != c->hfield_dev) { c->b->impl->set_hfield(c->hfield.data(), 1); c->hfield_dev = c->hfield; }
 }
 cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   std::string path;
@@ -454,6 +475,7 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   cassie_batch_t *b = cassie_batch_init(path.c_str(), 1, 0, CASSIE_B200_FP64);
   if (!b) return nullptr;
   cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); c->b = b; sim_pull(c);
+  if (b->impl->hm.nhfield) { c->hfield.assign((size_t)b->impl->hm.hfield_nrow[0] * b->impl->hm.hfield_ncol[0], 0.0f); c->hfield_dev = c->hfield; }
   return c;
 }
 void cassie_sim_free(cassie_sim_t *c) { if (!c) return; cassie_batch_free(c->b); delete c; }
@@ -466,6 +488,11 @@ int cassie_sim_nq(const cassie_sim_t *c) { return c->b->impl->hm.nq; }
 void cassie_sim_apply_force(cassie_sim_t *c, double xfrc[6], const char *name) { cassie_batch_apply_force(c->b, xfrc, name); }
 void cassie_sim_clear_forces(cassie_sim_t *c) { cassie_batch_clear_forces(c->b); }
 void cassie_sim_radio(cassie_sim_t *c, double channels[16]) { for (int i = 0; i < 16; i++) c->b->radio[i] = channels[i]; double s = channels[8]; c->b->impl->set("sto", &s); }
+int cassie_sim_get_hfield_nrow(cassie_sim_t *c) { return cassie_batch_hfield_nrow(c->b); }
+int cassie_sim_get_hfield_ncol(cassie_sim_t *c) { return cassie_batch_hfield_ncol(c->b); }
+int cassie_sim_get_nhfielddata(cassie_sim_t *c) { return (int)c->hfield.size(); }
+float *cassie_sim_hfielddata(cassie_sim_t *c) { return c->hfield.empty() ? nullptr : c->hfield.data(); }
+void cassie_sim_set_hfielddata(cassie_sim_t *c, float *data) { for (size_t i = 0; i < c->hfield.size(); i++) c->hfield[i] = data[i]; }
 void cassie_sim_full_reset(cassie_sim_t *c) {
   // src/cassiemujoco.c:2008-2033: qpos <- 35 constants, zero qvel / ctrl / applied forces / qacc, zero the torque delay line.
   // It does NOT touch time, the encoder filters or cassie_out, and does not call mj_forward.

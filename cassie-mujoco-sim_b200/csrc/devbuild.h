@@ -25,7 +25,10 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
   std::memset(&d, 0, sizeof d);
   if (m.nv > MV || m.nbody > MB || m.njnt > MJ || m.nM > NM_MAX || m.neq > ME || m.nu != MU) { err = "model exceeds the one-warp-per-env limits (nv<=32, nbody<=32, neq<=4, nu==10)"; return false; }
   for (int j = 0; j < m.njnt; j++) if (m.jnt_type[j] == JNT_FREE) { err = "free joints are not supported by the batched stepper yet"; return false; }
-  for (int b = 1; b < m.nbody; b++) if (m.body_rootid[b] != 1) { err = "a single kinematic tree rooted at body 1 is required"; return false; }
+  { int root = -1;   // one moving tree; other bodies must be static (welded to the world, e.g. the 'floor' body of cassie_hfield.xml)
+    for (int b = 1; b < m.nbody; b++) { if (m.body_weldid[b] == 0) continue; if (root < 0) root = m.body_rootid[b]; if (m.body_rootid[b] != root) { err = "a single moving kinematic tree is required"; return false; } } }
+  if (m.nhfield > 1) { err = "at most one height field is supported"; return false; }
+  if (m.nhfield == 1) { d.hf_nrow = m.hfield_nrow[0]; d.hf_ncol = m.hfield_ncol[0]; for (int k = 0; k < 4; k++) d.hf_size[k] = (real)m.hfield_size[k]; }
   d.nq = m.nq; d.nv = m.nv; d.nbody = m.nbody; d.njnt = m.njnt; d.neq = m.neq; d.nu = m.nu; d.nM = m.nM; d.iterations = m.iterations;
   d.timestep = (real)m.timestep; d.tolerance = (real)m.tolerance; d.pgs_scale = (real)(1.0 / (m.meaninertia * std::max(1, m.nv)));
   d.nsub = (int)std::lround(5e-4 / m.timestep); if (d.nsub < 1) d.nsub = 1;
@@ -145,8 +148,12 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) kind = PAIR_PLANE_SPHERE;
       else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) kind = PAIR_PLANE_CAPSULE;
       else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) kind = PAIR_CAPSULE_CAPSULE;
+      else if (t1 == GEOM_HFIELD && t2 == GEOM_SPHERE) kind = PAIR_HFIELD_SPHERE;
+      else if (t1 == GEOM_HFIELD && t2 == GEOM_CAPSULE) kind = PAIR_HFIELD_CAPSULE;
       else { unsupported++; continue; }
       if (d.npair >= MP) { err = "too many candidate geom pairs"; return false; }
+      if (t1 == GEOM_HFIELD) { const double *q = &m.geom_quat[4 * g1], *bq = &m.body_quat[4 * m.geom_bodyid[g1]];
+        if (std::fabs(q[0]) < 1 - 1e-12 || std::fabs(bq[0]) < 1 - 1e-12 || m.body_weldid[m.geom_bodyid[g1]] != 0) { err = "the height field must be axis aligned and static"; return false; } }
       int k1 = dev_geom(g1), k2 = dev_geom(g2); if (k1 < 0 || k2 < 0) { err = "too many collision geoms"; return false; }
       int p = d.npair++; d.pair_g1[p] = k1; d.pair_g2[p] = k2; d.pair_kind[p] = kind;
       // contact parameter mixing (mj_contactParam)

@@ -21,7 +21,7 @@ constexpr int MAXCON = 12;    // contacts per env
 constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
 
 // pair kinds handled by the narrow phase
-enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2 };
+enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2, PAIR_HFIELD_SPHERE = 3, PAIR_HFIELD_CAPSULE = 4 };
 
 template <typename real>
 struct DevModel {
@@ -29,6 +29,8 @@ struct DevModel {
   int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, has_damping, pad1;
   real timestep, tolerance, pgs_scale, root_mass_inv, euler_eps, padr[3];
   real gravity[3], magnetic[3], imu_pos[3], imu_quat[4], imu_mat[9], gyro_cutoff, accel_cutoff;
+  int hf_nrow, hf_ncol, padh[2];
+  real hf_size[4];           // height field: x half-size, y half-size, elevation scale, base thickness
   // ---- bodies
   int body_parent[MB], body_depth[MB], body_jntadr[MB], body_jntnum[MB], body_lastdof[MB], body_subtree_end[MB];
   uint32_t body_dofmask[MB];

@@ -403,6 +403,8 @@ bool compile_mjcf(const std::string &xml_path, HostModel &m, std::string &err) {
   // inertia inferred from geoms (inertiafromgeom='auto'): boxes only
   for (size_t b = 1; b < C.bodies.size(); b++) if (!C.bodies[b].explicit_inertial) {
     Body &B = C.bodies[b]; double tot = 0, com[3] = {0, 0, 0};
+    { bool is_static = B.joints.empty(); for (int a = B.parent; a > 0 && is_static; a = C.bodies[a].parent) if (!C.bodies[a].joints.empty()) is_static = false;
+      if (is_static) { B.mass = 0; B.inertia[0] = B.inertia[1] = B.inertia[2] = 0; B.ipos[0] = B.ipos[1] = B.ipos[2] = 0; B.iquat[0] = 1; B.iquat[1] = B.iquat[2] = B.iquat[3] = 0; continue; } }
     for (int gi : B.geoms) { Geom &G = C.geoms[gi]; if (G.type != GEOM_BOX) { err = "geom-inferred inertia implemented for boxes only"; return false; }
       if (!G.has_mass) G.mass = 1000.0 * 8 * G.size[0] * G.size[1] * G.size[2]; tot += G.mass; for (int i = 0; i < 3; i++) com[i] += G.mass * G.pos[i]; }
     if (tot <= 0) { err = "body '" + B.name + "' has no inertia"; return false; }

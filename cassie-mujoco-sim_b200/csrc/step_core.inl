@@ -59,6 +59,7 @@ template <typename real> struct EnvPtrs {
   const real *xfrc;   // [XFRC_W]
   real *obs;          // [OBS_W] or null
   real *qM;           // [NM_MAX] mass-matrix scratch (written by CRB, read back by the Euler stage)
+  const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
   real *dbg;          // [D_SIZE] or null
   int *counters;      // [8]
 };
@@ -228,6 +229,60 @@ template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *
   sweep_lt(cm, sm, x);
   LANES_NS if (l < cm.nv) L(x) *= sm[S_DINV + l]; ENDL_NS
   sweep_l(cm, sm, x);
+}
+
+// closest point on triangle abc to p (Ericson, Real-Time Collision Detection 5.1.5); true when it lies strictly inside the face
+template <typename real> CFN bool closest_pt_tri(const real *p, const real *a, const real *b, const real *c, real *q) {
+  real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+  const real d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+  if (d1 <= 0 && d2 <= 0) { q[0] = a[0]; q[1] = a[1]; q[2] = a[2]; return false; }
+  real bp[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
+  const real d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+  if (d3 >= 0 && d4 <= d3) { q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; return false; }
+  const real vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { const real v = d1 / (d1 - d3); q[0] = a[0] + v * ab[0]; q[1] = a[1] + v * ab[1]; q[2] = a[2] + v * ab[2]; return false; }
+  real cp[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+  const real d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  if (d6 >= 0 && d5 <= d6) { q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; return false; }
+  const real vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { const real w = d2 / (d2 - d6); q[0] = a[0] + w * ac[0]; q[1] = a[1] + w * ac[1]; q[2] = a[2] + w * ac[2]; return false; }
+  const real va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { const real w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); q[0] = b[0] + w * (c[0] - b[0]); q[1] = b[1] + w * (c[1] - b[1]); q[2] = b[2] + w * (c[2] - b[2]); return false; }
+  const real den = real(1) / (va + vb + vc), v = vb * den, w = vc * den;
+  q[0] = a[0] + ab[0] * v + ac[0] * w; q[1] = a[1] + ab[1] * v + ac[1] * w; q[2] = a[2] + ab[2] * v + ac[2] * w;
+  return true;
+}
+// height field vs sphere: the deepest analytic contact against the triangulated surface under the sphere (own definition);
+// hf = normalised elevations [nrow][ncol] in global memory; the hfield frame is axis aligned at hpos
+template <typename real> CFN bool hfield_sphere(const DevModel<real> &cm, const float *hf, const real *hpos, const real *sp, real r, real margin, real *dist, real *nrm) {
+  const real sx = cm.hf_size[0], sy = cm.hf_size[1], sz = cm.hf_size[2]; const int nrow = cm.hf_nrow, ncol = cm.hf_ncol;
+  real pl[3] = {sp[0] - hpos[0], sp[1] - hpos[1], sp[2] - hpos[2]};
+  if (mabs(pl[0]) > sx + r || mabs(pl[1]) > sy + r || pl[2] - r > sz + margin) return false;
+  const real dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1);
+  int c0 = (int)floor((pl[0] - r + sx) / dx), c1 = (int)floor((pl[0] + r + sx) / dx), r0 = (int)floor((pl[1] - r + sy) / dy), r1 = (int)floor((pl[1] + r + sy) / dy);
+  c0 = c0 < 0 ? 0 : (c0 > ncol - 2 ? ncol - 2 : c0); c1 = c1 < 0 ? 0 : (c1 > ncol - 2 ? ncol - 2 : c1);
+  r0 = r0 < 0 ? 0 : (r0 > nrow - 2 ? nrow - 2 : r0); r1 = r1 < 0 ? 0 : (r1 > nrow - 2 ? nrow - 2 : r1);
+  real best = real(1e30), bn0 = 0, bn1 = 0, bn2 = 1;
+  for (int rr = r0; rr <= r1; ++rr) for (int cc = c0; cc <= c1; ++cc) {
+    const real x0 = -sx + cc * dx, y0 = -sy + rr * dy;
+    const real h00 = (real)hf[rr * ncol + cc] * sz, h10 = (real)hf[rr * ncol + cc + 1] * sz, h01 = (real)hf[(rr + 1) * ncol + cc] * sz, h11 = (real)hf[(rr + 1) * ncol + cc + 1] * sz;
+    const real v00[3] = {x0, y0, h00}, v10[3] = {x0 + dx, y0, h10}, v01[3] = {x0, y0 + dy, h01}, v11[3] = {x0 + dx, y0 + dy, h11};
+    for (int t = 0; t < 2; ++t) {
+      const real *a = t ? v10 : v00, *b = t ? v11 : v10, *c = v01;
+      real e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, n[3], q[3], dd, nn[3];
+      cross3(n, e1, e2); normalize3(n);
+      if (closest_pt_tri(pl, a, b, c, q)) { real d[3] = {pl[0] - a[0], pl[1] - a[1], pl[2] - a[2]}; dd = dot3(n, d) - r; nn[0] = n[0]; nn[1] = n[1]; nn[2] = n[2]; }
+      else {
+        real v[3] = {pl[0] - q[0], pl[1] - q[1], pl[2] - q[2]}; const real len = msqrt(dot3(v, v));
+        if (dot3(v, n) < 0 || len < real(1e-12)) continue;
+        dd = len - r; nn[0] = v[0] / len; nn[1] = v[1] / len; nn[2] = v[2] / len;
+      }
+      if (dd < margin && dd < best) { best = dd; bn0 = nn[0]; bn1 = nn[1]; bn2 = nn[2]; }
+    }
+  }
+  if (best > real(1e29)) return false;
+  *dist = best; nrm[0] = bn0; nrm[1] = bn1; nrm[2] = bn2;
+  return true;
 }
 
 // translational Jacobian column of dof l for a world point attached to `body` (zero when l is not in the body's chain)
@@ -495,6 +550,19 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           }
         }
         if (kind == PAIR_PLANE_CAPSULE) { L(ch0) = a2[0]; L(ch1) = a2[1]; L(ch2) = a2[2]; }
+      } else if (kind == PAIR_HFIELD_SPHERE || kind == PAIR_HFIELD_CAPSULE) {
+        const real r = cm.geom_size[g2][0], hl = (kind == PAIR_HFIELD_CAPSULE) ? cm.geom_size[g2][1] : real(0);
+        const int ne = (kind == PAIR_HFIELD_CAPSULE) ? 2 : 1;
+        if (E.hfield) for (int e = 0; e < ne; ++e) {
+          const real sgn = e ? real(-1) : real(1);
+          real sp[3] = {p2[0] + sgn * hl * a2[0], p2[1] + sgn * hl * a2[1], p2[2] + sgn * hl * a2[2]}, dd, nn[3];
+          if (hfield_sphere(cm, E.hfield, p1, sp, r, margin, &dd, nn)) {
+            cdst[n] = dd; cn[n][0] = nn[0]; cn[n][1] = nn[1]; cn[n][2] = nn[2];
+            const real s = dd * real(0.5) + r;
+            cp[n][0] = sp[0] - nn[0] * s; cp[n][1] = sp[1] - nn[1] * s; cp[n][2] = sp[2] - nn[2] * s; ++n;
+          }
+        }
+        if (kind == PAIR_HFIELD_CAPSULE) { L(ch0) = a2[0]; L(ch1) = a2[1]; L(ch2) = a2[2]; }
       } else {  // capsule - capsule
         const real s1 = cm.geom_size[g1][1], s2 = cm.geom_size[g2][1], r1 = cm.geom_size[g1][0], r2 = cm.geom_size[g2][0];
         real dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};

@@ -46,6 +46,13 @@ void cassie_sim_apply_force(cassie_sim_t *sim, double xfrc[6], const char *name)
 void cassie_sim_clear_forces(cassie_sim_t *sim);
 /* include/cassiemujoco.h:281 (src/cassiemujoco.c:2008-2033) */
 void cassie_sim_full_reset(cassie_sim_t *sim);
+/* include/cassiemujoco.h:317-329 (src/cassiemujoco.c:2050-2080): height-field terrain of cassie_hfield.xml; nrow*ncol floats in [0,1],
+ * row-major, row <-> y, column <-> x.  cassie_sim_hfielddata returns a borrowed read-write host mirror uploaded before the next step. */
+int cassie_sim_get_hfield_nrow(cassie_sim_t *sim);
+int cassie_sim_get_hfield_ncol(cassie_sim_t *sim);
+int cassie_sim_get_nhfielddata(cassie_sim_t *sim);
+float *cassie_sim_hfielddata(cassie_sim_t *sim);
+void cassie_sim_set_hfielddata(cassie_sim_t *sim, float *data);
 /* src/cassiemujoco.c:2002-2006: the 16 radio channels; channel 8 < 1 engages safe-torque-off */
 void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
 
@@ -91,6 +98,12 @@ int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *
 void cassie_batch_clear_forces(cassie_batch_t *b);
 /* batched cassie_integrate_pos (src/cassiemujoco.c:1183-1189 -> mj_integratePos): qpos <- qpos (+) h * qvel, the HBM-bound kernel */
 void cassie_batch_integrate_pos(cassie_batch_t *b);
+
+/* batched cassie_sim_set_hfielddata: `n_terrains` height fields of nrow*ncol floats; environment e stands on terrain e % n_terrains
+ * (BASELINE config 4: a few dozen terrains shared round-robin).  0 on success, -1 if the model has no height field. */
+int cassie_batch_set_hfielddata(cassie_batch_t *b, const float *data, int n_terrains);
+int cassie_batch_hfield_nrow(const cassie_batch_t *b);
+int cassie_batch_hfield_ncol(const cassie_batch_t *b);
 
 /* zero-copy access for a PyTorch / DLPack caller: device pointer of a state array ("qpos" [n][36], "qvel" [n][32],
  * "pd" [n][52], "obs" [n][64], "xfrc" [n][8]) in the batch precision; the stream all work is enqueued on (cudaStream_t). */

@@ -432,6 +432,72 @@ static int col_plane_capsule(const OModel *m, const OData *d, OContact *c, int g
   return n1 + n2;
 }
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* closest point on triangle abc to p (Ericson, Real-Time Collision Detection 5.1.5); returns 1 when it lies strictly inside the face */
+static int closest_pt_tri(const double *p, const double *a, const double *b, const double *c, double *q) {
+  double ab[3], ac[3], ap[3], bp[3], cp[3];
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+  double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+  if (d1 <= 0 && d2 <= 0) { copyv(q, a, 3); return 0; }
+  for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
+  double d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+  if (d3 >= 0 && d4 <= d3) { copyv(q, b, 3); return 0; }
+  double vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { double v = d1 / (d1 - d3); for (int k = 0; k < 3; k++) q[k] = a[k] + v * ab[k]; return 0; }
+  for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
+  double d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  if (d6 >= 0 && d5 <= d6) { copyv(q, c, 3); return 0; }
+  double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { double w = d2 / (d2 - d6); for (int k = 0; k < 3; k++) q[k] = a[k] + w * ac[k]; return 0; }
+  double va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { double w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); for (int k = 0; k < 3; k++) q[k] = b[k] + w * (c[k] - b[k]); return 0; }
+  double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+  for (int k = 0; k < 3; k++) q[k] = a[k] + ab[k] * v + ac[k] * w;
+  return 1;
+}
+/* Height field vs sphere.  NOT MuJoCo's prism + MPR scheme (that iterative convex solver cannot be restated bit for bit, SURVEY.md hard
+ * part 6): the surface is the same triangulation MuJoCo uses (cell diagonal from (r,c+1) to (r+1,c)), every triangle under the sphere's
+ * xy box is tested analytically and the single deepest contact is kept.  hfield frame = geom frame, axis aligned. */
+static int raw_hfield_sphere(const OModel *m, OContact *c, double margin, const double *hpos, const double *sp, double r) {
+  const double sx = m->hfield_size[0], sy = m->hfield_size[1], sz = m->hfield_size[2]; const int nrow = m->hfield_nrow, ncol = m->hfield_ncol;
+  double pl[3] = {sp[0] - hpos[0], sp[1] - hpos[1], sp[2] - hpos[2]};
+  if (fabs(pl[0]) > sx + r || fabs(pl[1]) > sy + r || pl[2] - r > sz + margin) return 0;
+  double dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1);
+  int c0 = (int)floor((pl[0] - r + sx) / dx), c1 = (int)floor((pl[0] + r + sx) / dx), r0 = (int)floor((pl[1] - r + sy) / dy), r1 = (int)floor((pl[1] + r + sy) / dy);
+  c0 = c0 < 0 ? 0 : (c0 > ncol - 2 ? ncol - 2 : c0); c1 = c1 < 0 ? 0 : (c1 > ncol - 2 ? ncol - 2 : c1);
+  r0 = r0 < 0 ? 0 : (r0 > nrow - 2 ? nrow - 2 : r0); r1 = r1 < 0 ? 0 : (r1 > nrow - 2 ? nrow - 2 : r1);
+  double best = 1e30, bn[3] = {0, 0, 1};
+  for (int rr = r0; rr <= r1; rr++) for (int cc = c0; cc <= c1; cc++) {
+    double x0 = -sx + cc * dx, y0 = -sy + rr * dy;
+    double h00 = m->hfield_data[rr * ncol + cc] * sz, h10 = m->hfield_data[rr * ncol + cc + 1] * sz, h01 = m->hfield_data[(rr + 1) * ncol + cc] * sz, h11 = m->hfield_data[(rr + 1) * ncol + cc + 1] * sz;
+    double v00[3] = {x0, y0, h00}, v10[3] = {x0 + dx, y0, h10}, v01[3] = {x0, y0 + dy, h01}, v11[3] = {x0 + dx, y0 + dy, h11};
+    const double *tri[2][3] = {{v00, v10, v01}, {v10, v11, v01}};
+    for (int t = 0; t < 2; t++) {
+      const double *a = tri[t][0], *b = tri[t][1], *cc3 = tri[t][2]; double e1[3], e2[3], n[3], q[3], dist, nrm[3];
+      for (int k = 0; k < 3; k++) { e1[k] = b[k] - a[k]; e2[k] = cc3[k] - a[k]; }
+      cross(n, e1, e2); normalize3(n);
+      if (closest_pt_tri(pl, a, b, cc3, q)) { double d[3] = {pl[0] - a[0], pl[1] - a[1], pl[2] - a[2]}; dist = dot3(n, d) - r; copyv(nrm, n, 3); }
+      else {
+        double v[3] = {pl[0] - q[0], pl[1] - q[1], pl[2] - q[2]}, dd = sqrt(dot3(v, v));
+        if (dot3(v, n) < 0 || dd < 1e-12) continue;
+        dist = dd - r; for (int k = 0; k < 3; k++) nrm[k] = v[k] / dd;
+      }
+      if (dist < margin && dist < best) { best = dist; copyv(bn, nrm, 3); }
+    }
+  }
+  if (best > 1e29) return 0;
+  c->dist = best; copyv(c->frame, bn, 3); zero(c->frame + 3, 6);
+  for (int k = 0; k < 3; k++) c->pos[k] = sp[k] - bn[k] * (r + best * 0.5);
+  return 1;
+}
+static int col_hfield_capsule(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
+  const double *mat2 = d->geom_xmat[g2]; double ax[3] = {mat2[2], mat2[5], mat2[8]}, p[3]; double hl = m->geom_size[g2][1];
+  for (int k = 0; k < 3; k++) p[k] = d->geom_xpos[g2][k] + ax[k] * hl;
+  int n1 = raw_hfield_sphere(m, c, margin, d->geom_xpos[g1], p, m->geom_size[g2][0]);
+  for (int k = 0; k < 3; k++) p[k] = d->geom_xpos[g2][k] - ax[k] * hl;
+  int n2 = raw_hfield_sphere(m, c + n1, margin, d->geom_xpos[g1], p, m->geom_size[g2][0]);
+  for (int i = 0; i < n1 + n2; i++) copyv(c[i].frame + 3, ax, 3);
+  return n1 + n2;
+}
 static int col_capsule_capsule(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
   const double *m1 = d->geom_xmat[g1], *m2 = d->geom_xmat[g2], *p1 = d->geom_xpos[g1], *p2 = d->geom_xpos[g2];
   double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]}, dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
@@ -474,6 +540,8 @@ static void collide_geoms(const OModel *m, OData *d, int g1, int g2) {
   if (t1 == G_PLANE && t2 == G_SPHERE) num = raw_plane_sphere(con, margin, d->geom_xpos[g1], d->geom_xmat[g1], d->geom_xpos[g2], m->geom_size[g2][0]);
   else if (t1 == G_PLANE && t2 == G_CAPSULE) num = col_plane_capsule(m, d, con, g1, g2, margin);
   else if (t1 == G_CAPSULE && t2 == G_CAPSULE) num = col_capsule_capsule(m, d, con, g1, g2, margin);
+  else if (t1 == G_HFIELD && t2 == G_SPHERE && m->hfield_data) num = raw_hfield_sphere(m, con, margin, d->geom_xpos[g1], d->geom_xpos[g2], m->geom_size[g2][0]);
+  else if (t1 == G_HFIELD && t2 == G_CAPSULE && m->hfield_data) num = col_hfield_capsule(m, d, con, g1, g2, margin);
   else { d->unsupported_pairs++; return; }
   if (!num) return;
   /* contact parameter mixing (mj_contactParam) */

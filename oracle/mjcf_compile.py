@@ -273,9 +273,21 @@ def compile_mjcf(path):
     wb = root.find('worldbody')
     walk(wb, 0, None)
 
+    def ancestors(b):
+        out = []
+        b = bodies[b]['parent']
+        while b > 0:
+            out.append(b)
+            b = bodies[b]['parent']
+        return out
+
     # bodies without <inertial>: infer from geoms (inertiafromgeom='auto'); only boxes needed (tray, cup_box)
     for bid, bd in enumerate(bodies):
         if bid == 0 or bd.get('explicit_inertial'):
+            continue
+        if not bd['joints'] and all(not bodies[a]['joints'] for a in ancestors(bid)):
+            # static body welded to the world (e.g. the 'floor' body carrying the height field): its inertia never enters the dynamics
+            bd['mass'], bd['ipos'], bd['inertia'], bd['iquat'] = 0.0, np.zeros(3), np.zeros(3), np.array([1.0, 0, 0, 0])
             continue
         tot, com, parts = 0.0, np.zeros(3), []
         for gi in bd['geoms']:

@@ -14,11 +14,13 @@ using namespace cassie;
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; std::vector<real> sm; std::vector<int> ism;
   real qvel[32], qacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX]; int counters[8];
-  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; return E; }
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
+  std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
     if (!build_dev_model(hm, dm, err)) return false;
     sm.assign(S_REALS, 0); ism.assign(DFILT_W, 0);
+    if (hm.nhfield) hfield.assign((size_t)hm.hfield_nrow[0] * hm.hfield_ncol[0], 0.0f);
     std::vector<real> qpos(QPOS_W);
     init_env_rows(hm, qpos.data(), qvel, qacc_ws, cst, ism.data(), xfrc);
     for (int i = 0; i < QPOS_W; i++) sm[S_QPOS + i] = qpos[i];
@@ -45,6 +47,7 @@ void emu_step(void *p, const double *pd50, int nticks) {
   if (h->fp32) { for (int i = 0; i < 50; i++) h->f.pd[i] = (float)pd50[i]; h->f.step(nticks); }
   else { for (int i = 0; i < 50; i++) h->d.pd[i] = pd50[i]; h->d.step(nticks); }
 }
+void emu_set_hfield(void *p, const float *data, int n) { Handle *h = (Handle *)p; std::vector<float> &dst = h->fp32 ? h->f.hfield : h->d.hfield; for (int i = 0; i < n && i < (int)dst.size(); i++) dst[i] = data[i]; }
 void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward(); else h->d.forward(); }
 // generic get/set of named state as doubles.  names: qpos qvel qacc_ws cst obs dbg xfrc ; ints: dfilt counters
 int emu_get(void *p, const char *name, double *out, int n) {

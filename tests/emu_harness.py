@@ -65,3 +65,12 @@ class EmuSim:
 
     def forward(self):
         self.L.emu_forward(self.h)
+
+
+def _emu_set_hfield(self, data):
+    a = np.ascontiguousarray(data, dtype=np.float32)
+    self.L.emu_set_hfield.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+    self.L.emu_set_hfield(self.h, a.ctypes.data_as(C.POINTER(C.c_float)), a.size)
+
+
+EmuSim.set_hfield = _emu_set_hfield
