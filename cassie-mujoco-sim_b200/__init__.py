@@ -307,7 +307,7 @@ class CassieBatch:
 class CassieSim:
     """Legacy single-environment object (reference: example/cassiemujoco.py:31-173), stepped by the same CUDA kernels."""
 
-    def __init__(self, modelfile=None, reinit=False):
+    def __init__(self, modelfile=None, reinit=True):   # the reference wrapper always passes reinit=True (example/cassiemujoco.py:44)
         self.L = lib()
         path = modelfile or model_path()
         self.c = self.L.cassie_sim_init(path.encode(), bool(reinit))

@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    if (mode == 0) step_env(cm, sm, E, qvel, qacc_ws, nticks);
-    else forward_env(cm, sm, E, qvel, qacc_ws);
+    step_env(cm, sm, E, qvel, qacc_ws, nticks, mode != 0);
     __syncwarp();
     for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
     A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;

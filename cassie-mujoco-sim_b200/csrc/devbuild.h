@@ -1,6 +1,7 @@
 // devbuild.h -- host code that turns a HostModel into the DevModel<real> constant block, and the initial per-env state rows.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -33,6 +34,7 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
   d.timestep = (real)m.timestep; d.tolerance = (real)m.tolerance; d.pgs_scale = (real)(1.0 / (m.meaninertia * std::max(1, m.nv)));
   d.nsub = (int)std::lround(5e-4 / m.timestep); if (d.nsub < 1) d.nsub = 1;
   d.euler_eps = (real)(4 * std::numeric_limits<real>::epsilon());
+  d.force_zpath = std::getenv("CASSIE_B200_ZPATH") ? 1 : 0;   // test hook: force the reduction-based solver path used when nefc > 32
   double mass = 0; for (int b = 1; b < m.nbody; b++) mass += m.body_mass[b];
   d.root_mass_inv = (real)(1.0 / mass);
   for (int k = 0; k < 3; k++) { d.gravity[k] = (real)m.gravity[k]; d.magnetic[k] = (real)m.magnetic[k]; }

@@ -18,6 +18,7 @@ constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 
 constexpr int NFAC_MAX = 1600; // rank-1 update pairs of the factorisation schedule (1519 for Cassie)
 constexpr int NEFC = 48;      // constraint rows per env (12 equality + limits + 4 per floor contact); excess contacts are dropped and counted
 constexpr int MAXCON = 12;    // contacts per env
+constexpr int NEFC_DENSE = 24; // up to this many rows the dense A = YY'+R fits in the unused tail of the constraint-matrix region
 constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
 
 // pair kinds handled by the narrow phase
@@ -26,7 +27,7 @@ enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPS
 template <typename real>
 struct DevModel {
   // ---- sizes / options
-  int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, has_damping, pad1;
+  int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, has_damping, force_zpath;
   real timestep, tolerance, pgs_scale, root_mass_inv, euler_eps, padr[3];
   real gravity[3], magnetic[3], imu_pos[3], imu_quat[4], imu_mat[9], gyro_cutoff, accel_cutoff;
   int hf_nrow, hf_ncol, padh[2];

@@ -27,6 +27,8 @@
 #define LV(T, name) T name[32]
 #define L(name) name[l]
 #define LP(T, name) T(&name)[32]
+#define LVA(T, name, N) T name[N][32]
+#define LA(name, i) name[i][l]
 #define LANE0(v) v[0]
 #define ALLSUM(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ += v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
 #define ALLMAX(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ = s_ > v[i_] ? s_ : v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
@@ -42,6 +44,8 @@
 #define LV(T, name) T name
 #define L(name) name
 #define LP(T, name) T &name
+#define LVA(T, name, N) T name[N]
+#define LA(name, i) name[i]
 #define LANE0(v) v
 #define ALLSUM(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o_); } while (0)
 #define ALLMAX(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v = mmax(v, __shfl_xor_sync(0xffffffffu, v, o_)); } while (0)
@@ -720,64 +724,120 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         }
       ENDL
     }
-    // ---- warm start: keep f only if its dual cost 0.5 f'(YY'+R)f + f'b is not positive
-    LV(real, z); LV(real, fb);
-    LANES L(z) = 0; ENDL
-    for (int r = 0; r < nefc; ++r) {
-      if (r < 32) { BCAST(fb, f0, r); } else { BCAST(fb, f1, r - 32); }
-      LANES if (l < nv) L(z) += Y[r * YSTRIDE + l] * L(fb); ENDL
-    }
-    LANES
-      real s = real(0.5) * L(z) * L(z);
-      if (l < nefc) { const real f = L(f0); s += f * (efc[4 * l] + real(0.5) * mabs(efc[4 * l + 3]) * f); }
-      if (l + 32 < nefc) { const real f = L(f1); s += f * (efc[4 * (l + 32)] + real(0.5) * mabs(efc[4 * (l + 32) + 3]) * f); }
-      L(t0) = s;
-    ENDL
-    ALLSUM(t0);
-    if (LANE0(t0) > 0) { LANES L(z) = 0; L(f0) = L(f1) = 0; ENDL }
-    // ---- projected Gauss-Seidel, rows strictly in order; z = Y'f is carried one entry per lane
-    LV(real, acc); LV(real, impr); LV(real, yr);
-    while (iters < cm.iterations) {
-      LANES L(impr) = 0; ENDL
-      const int n0 = nefc < 32 ? nefc : 32;
-      for (int r = 0; r < n0; ++r) {
-        BCAST(fb, f0, r);
-        LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
-        ALLSUM(acc);
+    LV(real, z); LV(real, fb); LV(real, impr);
+    if (nefc <= NEFC_DENSE && !cm.force_zpath) {
+      // ---- dense path (nefc <= 24, e.g. standing on two contacts): A = Y Y' + R is formed explicitly in the unused tail of the Y region
+      // (rows NEFC_DENSE.. of it), and the solver carries the residual res = b + A f one entry per lane: a Gauss-Seidel row update is two
+      // broadcasts, ~10 scalar ops, one shared load and one FMA per lane, with no warp reduction on the critical path
+      real *Am = Y + NEFC_DENSE * YSTRIDE;     // Am[c * YSTRIDE + r] = A(r, c) (symmetric)
+      {
+        LVA(real, yreg, 32);
         LANES_NS
-          const real *rc = efc + 4 * r;
-          const real b = rc[0], ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb);
-          const real res = b + L(acc) + mabs(Rs) * fold;
-          real fnew = fold - res * ainv;
-          if (Rs < 0) fnew = mmax(fnew, real(0));
-          real delta = fnew - fold;
-          real change = delta * (real(0.5) * delta * Ad + res);
-          if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
-          L(impr) -= change;
-          L(z) += L(yr) * delta;
-          if (l == r) L(f0) = fnew;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) LA(yreg, d) = (l < nefc) ? Y[l * YSTRIDE + d] : real(0);
         ENDL_NS
+        for (int c = 0; c < nefc; ++c) {
+          LANES_NS
+            const real *yc = Y + c * YSTRIDE; real sacc = 0;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) sacc += LA(yreg, d) * yc[d];
+            if (c == l) sacc += mabs(efc[4 * c + 3]);
+            Am[c * YSTRIDE + l] = sacc;
+          ENDL_NS
+        }
       }
-      for (int r = 32; r < nefc; ++r) {
-        BCAST(fb, f1, r - 32);
-        LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
-        ALLSUM(acc);
-        LANES_NS
-          const real *rc = efc + 4 * r;
-          const real b = rc[0], ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb);
-          const real res = b + L(acc) + mabs(Rs) * fold;
-          real fnew = fold - res * ainv;
-          if (Rs < 0) fnew = mmax(fnew, real(0));
-          real delta = fnew - fold;
-          real change = delta * (real(0.5) * delta * Ad + res);
-          if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
-          L(impr) -= change;
-          L(z) += L(yr) * delta;
-          if (l == r - 32) L(f1) = fnew;
-        ENDL_NS
+      // warm start: res = b + A f; keep f only if its dual cost f'(b + 0.5 A f) is not positive
+      LV(real, res); LV(real, ri);
+      LANES L(res) = 0; ENDL
+      for (int c = 0; c < nefc; ++c) { BCAST(fb, f0, c); LANES_NS L(res) += Am[c * YSTRIDE + l] * L(fb); ENDL_NS }
+      LANES_NS
+        const real bl = (l < nefc) ? efc[4 * l] : real(0);
+        L(t0) = (l < nefc) ? L(f0) * (bl + real(0.5) * L(res)) : real(0);
+        L(res) += bl; L(t1) = bl;
+      ENDL_NS
+      ALLSUM(t0);
+      if (LANE0(t0) > 0) { LANES_NS L(f0) = 0; L(res) = L(t1); ENDL_NS }
+      while (iters < cm.iterations) {
+        LANES_NS L(impr) = 0; ENDL_NS
+        for (int i = 0; i < nefc; ++i) {
+          BCAST(ri, res, i); BCAST(fb, f0, i);
+          LANES_NS
+            const real *rc = efc + 4 * i;
+            const real ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb), resi = L(ri);
+            real fnew = fold - resi * ainv;
+            if (Rs < 0) fnew = mmax(fnew, real(0));
+            real delta = fnew - fold;
+            real change = delta * (real(0.5) * delta * Ad + resi);
+            if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+            L(impr) -= change;
+            L(res) += Am[i * YSTRIDE + l] * delta;
+            if (l == i) L(f0) = fnew;
+          ENDL_NS
+        }
+        ++iters;
+        if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
       }
-      ++iters;
-      if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
+      LANES_NS L(z) = 0; ENDL_NS
+      for (int r = 0; r < nefc; ++r) { BCAST(fb, f0, r); LANES_NS if (l < nv) L(z) += Y[r * YSTRIDE + l] * L(fb); ENDL_NS }
+    } else {
+      // ---- warm start: keep f only if its dual cost 0.5 f'(YY'+R)f + f'b is not positive
+      LANES L(z) = 0; ENDL
+      for (int r = 0; r < nefc; ++r) {
+        if (r < 32) { BCAST(fb, f0, r); } else { BCAST(fb, f1, r - 32); }
+        LANES if (l < nv) L(z) += Y[r * YSTRIDE + l] * L(fb); ENDL
+      }
+      LANES
+        real s = real(0.5) * L(z) * L(z);
+        if (l < nefc) { const real f = L(f0); s += f * (efc[4 * l] + real(0.5) * mabs(efc[4 * l + 3]) * f); }
+        if (l + 32 < nefc) { const real f = L(f1); s += f * (efc[4 * (l + 32)] + real(0.5) * mabs(efc[4 * (l + 32) + 3]) * f); }
+        L(t0) = s;
+      ENDL
+      ALLSUM(t0);
+      if (LANE0(t0) > 0) { LANES L(z) = 0; L(f0) = L(f1) = 0; ENDL }
+      // ---- projected Gauss-Seidel, rows strictly in order; z = Y'f is carried one entry per lane
+      LV(real, acc); LV(real, yr);
+      while (iters < cm.iterations) {
+        LANES L(impr) = 0; ENDL
+        const int n0 = nefc < 32 ? nefc : 32;
+        for (int r = 0; r < n0; ++r) {
+          BCAST(fb, f0, r);
+          LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
+          ALLSUM(acc);
+          LANES_NS
+            const real *rc = efc + 4 * r;
+            const real b = rc[0], ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb);
+            const real res = b + L(acc) + mabs(Rs) * fold;
+            real fnew = fold - res * ainv;
+            if (Rs < 0) fnew = mmax(fnew, real(0));
+            real delta = fnew - fold;
+            real change = delta * (real(0.5) * delta * Ad + res);
+            if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+            L(impr) -= change;
+            L(z) += L(yr) * delta;
+            if (l == r) L(f0) = fnew;
+          ENDL_NS
+        }
+        for (int r = 32; r < nefc; ++r) {
+          BCAST(fb, f1, r - 32);
+          LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
+          ALLSUM(acc);
+          LANES_NS
+            const real *rc = efc + 4 * r;
+            const real b = rc[0], ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb);
+            const real res = b + L(acc) + mabs(Rs) * fold;
+            real fnew = fold - res * ainv;
+            if (Rs < 0) fnew = mmax(fnew, real(0));
+            real delta = fnew - fold;
+            real change = delta * (real(0.5) * delta * Ad + res);
+            if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+            L(impr) -= change;
+            L(z) += L(yr) * delta;
+            if (l == r - 32) L(f1) = fnew;
+          ENDL_NS
+        }
+        ++iters;
+        if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
+      }
     }
     // ---- qacc = qacc_smooth + inv(L) D^-1/2 z ;  qfrc_constraint = J'f = L' D^1/2 z
     LV(real, w);
@@ -877,11 +937,16 @@ template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
 template <typename real>
-CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), int nticks) {
+CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), int nticks, bool forward_only) {
   DECL_LANE
   real *cst = E.cst, *vecs = sm + S_VEC, *obs = E.obs; const real *pd = E.pd; int *ism = E.dfilt;
   LV(real, ctrl); LV(real, tq); LV(real, scale_part);
+  // forward_only: a single mj_forward with zero ctrl (cassie_sim_init / reset, src/cassiemujoco.c:1029); it shares the one inlined copy of
+  // mj_substep with the stepping path so the kernel's instruction footprint stays small
+  if (forward_only) nticks = 1;
   for (int tick = 0; tick < nticks; ++tick) {
+    if (forward_only) { LANES L(ctrl) = 0; ENDL }
+    else {
     // ---- pd_input_step (motor-PD branch) + cassie_core_sim_step, lane = motor; both read LAST tick's cassie_out
     const real W = real(0.15), DEG = real(0.017453292519943295);
     LANES
@@ -962,17 +1027,11 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         if (l == 13) obs[OB_TIME] = cst[CS_TIME];
       ENDL
     }
+    }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
-    for (int s = 0; s < cm.nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, ctrl, (tick == nticks - 1 && s == cm.nsub - 1) ? E.dbg : (real *)0, true);
+    const int nsub = forward_only ? 1 : cm.nsub;
+    for (int s = 0; s < nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, !forward_only);
   }
-}
-
-// mj_forward on the current state with zero ctrl: fills sensordata / actuator_velocity (cassie_sim_init, :1029)
-template <typename real>
-CFN void forward_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws)) {
-  LV(real, ctrl);
-  LANES L(ctrl) = 0; ENDL
-  mj_substep(cm, sm, E, qvel, qacc_ws, ctrl, E.dbg, false);
 }
 
 }  // namespace cassie

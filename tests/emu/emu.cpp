@@ -28,8 +28,8 @@ template <typename real> struct Emu {
     forward();
     return true;
   }
-  void forward() { forward_env(dm, sm.data(), ptrs(), qvel, qacc_ws); }
-  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, nticks); }
+  void forward() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, 1, true); }
+  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, nticks, false); }
 };
 
 struct Handle { int fp32; Emu<float> f; Emu<double> d; };
