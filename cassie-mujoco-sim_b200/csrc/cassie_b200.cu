@@ -281,7 +281,7 @@ template <typename real> struct Batch : BatchBase {
       for (int i = 0; i < 10; i++) { y->motor.position[i] = o[OB_MPOS + i]; y->motor.velocity[i] = o[OB_MVEL + i]; y->motor.torque[i] = o[OB_MTORQUE + i]; }
       for (int i = 0; i < 6; i++) { y->joint.position[i] = o[OB_JPOS + i]; y->joint.velocity[i] = o[OB_JVEL + i]; }
       for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_QUAT + i];
-      for (int i = 0; i < 3; i++) { y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_ACCEL + i]; }
+      for (int i = 0; i < 3; i++) y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i];   // translationalAcceleration is an estimator output (not a copy of the accelerometer)
       for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
       y->radio.signalGood = true; y->battery.stateOfCharge = 1;
     }

@@ -96,6 +96,8 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
   int imu = m.site_id("imu");
   if (imu < 0) { err = "site 'imu' not found"; return false; }
   d.imu_body = m.site_bodyid[imu];
+  { int n = 0; int pb = d.imu_body; while (pb > 0 && m.body_dofnum[pb] == 0) pb = m.body_parentid[pb]; for (int k = pb > 0 ? m.body_dofadr[pb] + m.body_dofnum[pb] - 1 : -1; k >= 0; k = m.dof_parentid[k]) n++;
+    if (n > 7) { err = "the IMU body must have at most 7 dofs in its chain"; return false; } }
   double Rs[9]; detail::q2m_d(Rs, &m.site_quat[4 * imu]);
   for (int k = 0; k < 3; k++) d.imu_pos[k] = (real)m.site_pos[3 * imu + k];
   for (int k = 0; k < 4; k++) d.imu_quat[k] = (real)m.site_quat[4 * imu + k];

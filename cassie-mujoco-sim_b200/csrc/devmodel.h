@@ -18,7 +18,6 @@ constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 
 constexpr int NFAC_MAX = 1600; // rank-1 update pairs of the factorisation schedule (1519 for Cassie)
 constexpr int NEFC = 48;      // constraint rows per env (12 equality + limits + 4 per floor contact); excess contacts are dropped and counted
 constexpr int MAXCON = 12;    // contacts per env
-constexpr int NEFC_DENSE = 24; // up to this many rows the dense A = YY'+R fits in the unused tail of the constraint-matrix region
 constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
 
 // pair kinds handled by the narrow phase
@@ -103,6 +102,7 @@ constexpr int T_CVEL = 640;                     // [32][6]
 constexpr int T_CFRC = 832;                     // [32][6]
 constexpr int T_CDOFD = 1024;                   // [32][6]
 static_assert(T_CDOFD + 192 <= NEFC * YSTRIDE, "temporaries must fit in the constraint-matrix region");
+static_assert(NEFC >= 48 && 16 * YSTRIDE <= S_QLD - S_XPOS, "the dense solver path keeps A in rows 32..47 of Y and in the kinematics buffers");
 // slots of a row's 4 scalars while the rows are being built (overwritten by the solver constants afterwards)
 constexpr int E_POS = 0, E_SRC = 1, E_INEQ = 2;
 

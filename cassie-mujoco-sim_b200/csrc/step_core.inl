@@ -517,6 +517,48 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
+  // ================= sensors that do not need qacc (mj_sensorPos / mj_sensorVel for the Cassie layout) =================
+  // done here because the constraint stage below reuses the kinematics buffers; the accelerometer is finished after the solve from
+  // a small stash: vecs[102..104] = qacc-independent part, vecs[105..] = 3 x nchain gain matrix over the IMU body's dof chain
+  {
+    real *cst = E.cst;
+    LANES
+      if (l < 16) cst[CS_SENSOR + l] = cm.enc_scale[l] * qpos[cm.enc_qposadr[l]];   // actuatorpos = gear * q, jointpos = q
+      if (l < cm.nu) cst[CS_ACTVEL + l] = cm.act_gear[l] * vecs[cm.act_dof[l]];
+      if (l == 16) {  // IMU: framequat, gyro, magnetometer on site `imu`
+        const int b = cm.imu_body; real q[4], Rs[9], sp[3], v[3];
+        mul_quat(q, xquat + 4 * b, cm.imu_quat);
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Rs[3 * a + c] = xmat[9 * b + 3 * a] * cm.imu_mat[c] + xmat[9 * b + 3 * a + 1] * cm.imu_mat[3 + c] + xmat[9 * b + 3 * a + 2] * cm.imu_mat[6 + c];
+        mat_vec(v, xmat + 9 * b, cm.imu_pos); sp[0] = xpos[3 * b] + v[0]; sp[1] = xpos[3 * b + 1] + v[1]; sp[2] = xpos[3 * b + 2] + v[2];
+        real dif[3] = {sp[0] - L(com0), sp[1] - L(com1), sp[2] - L(com2)};
+        // body spatial velocity in the c-frame and the qacc-independent part of its acceleration (chain sums over the body's dofs)
+        real cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, -cm.gravity[0], -cm.gravity[1], -cm.gravity[2]};
+        for (int k = 0; k < 6; ++k) ca[k] += vecs[96 + k];
+        int nchain = 0;
+        for (int a = cm.body_lastdof[b]; a >= 0; a = cm.dof_parent[a], ++nchain) {
+          const real *cd_ = cdof + 6 * a; real t3[3], gl[3], gloc[3];
+          for (int k = 0; k < 6; ++k) cv[k] += cd_[k] * vecs[a];
+          cross3(t3, dif, cd_); gl[0] = cd_[3] - t3[0]; gl[1] = cd_[4] - t3[1]; gl[2] = cd_[5] - t3[2];
+          matT_vec(gloc, Rs, gl);
+          vecs[105 + 3 * nchain] = gloc[0]; vecs[105 + 3 * nchain + 1] = gloc[1]; vecs[105 + 3 * nchain + 2] = gloc[2];
+        }
+        vecs[127] = (real)nchain;
+        real t3[3], vl[3], al[3], lw[3], lv[3], la[3], corr[3];
+        cross3(t3, dif, cv); vl[0] = cv[3] - t3[0]; vl[1] = cv[4] - t3[1]; vl[2] = cv[5] - t3[2];
+        cross3(t3, dif, ca); al[0] = ca[3] - t3[0]; al[1] = ca[4] - t3[1]; al[2] = ca[5] - t3[2];
+        matT_vec(lw, Rs, cv); matT_vec(lv, Rs, vl); matT_vec(la, Rs, al); cross3(corr, lw, lv);
+        for (int k = 0; k < 4; ++k) cst[CS_SENSOR + 16 + k] = q[k];
+        for (int k = 0; k < 3; ++k) {
+          real g = lw[k];
+          if (cm.gyro_cutoff > 0) g = clampr(g, -cm.gyro_cutoff, cm.gyro_cutoff);
+          cst[CS_SENSOR + 20 + k] = g; vecs[102 + k] = la[k] + corr[k];
+        }
+        real mg[3]; matT_vec(mg, Rs, cm.magnetic);
+        for (int k = 0; k < 3; ++k) cst[CS_SENSOR + 26 + k] = mg[k];
+      }
+    ENDL
+  }
+
   // ================= collision (lane = candidate geom pair) =================
   real *geom = sm + S_GEOM;
   LANES
@@ -725,11 +767,12 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       ENDL
     }
     LV(real, z); LV(real, fb); LV(real, impr);
-    if (nefc <= NEFC_DENSE && !cm.force_zpath) {
-      // ---- dense path (nefc <= 24, e.g. standing on two contacts): A = Y Y' + R is formed explicitly in the unused tail of the Y region
-      // (rows NEFC_DENSE.. of it), and the solver carries the residual res = b + A f one entry per lane: a Gauss-Seidel row update is two
+    if (nefc <= 32 && !cm.force_zpath) {
+      // ---- dense path (nefc <= 32: standing / walking contact states): A = Y Y' + R is formed explicitly in scratch that is idle during the
+      // solve, and the solver carries the residual res = b + A f one entry per lane: a Gauss-Seidel row update is two
       // broadcasts, ~10 scalar ops, one shared load and one FMA per lane, with no warp reduction on the critical path
-      real *Am = Y + NEFC_DENSE * YSTRIDE;     // Am[c * YSTRIDE + r] = A(r, c) (symmetric)
+      // A(., c) for c < 16 lives in rows 32..47 of the Y region, for c >= 16 in the (now dead) kinematics buffers xpos/xquat/xmat/cdof
+#define AM(c) (((c) < 16 ? Y + (32 + (c)) * YSTRIDE : sm + S_XPOS + ((c) - 16) * YSTRIDE))
       {
         LVA(real, yreg, 32);
         LANES_NS
@@ -742,14 +785,14 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
 #pragma unroll
             for (int d = 0; d < 32; ++d) sacc += LA(yreg, d) * yc[d];
             if (c == l) sacc += mabs(efc[4 * c + 3]);
-            Am[c * YSTRIDE + l] = sacc;
+            AM(c)[l] = sacc;
           ENDL_NS
         }
       }
       // warm start: res = b + A f; keep f only if its dual cost f'(b + 0.5 A f) is not positive
       LV(real, res); LV(real, ri);
       LANES L(res) = 0; ENDL
-      for (int c = 0; c < nefc; ++c) { BCAST(fb, f0, c); LANES_NS L(res) += Am[c * YSTRIDE + l] * L(fb); ENDL_NS }
+      for (int c = 0; c < nefc; ++c) { BCAST(fb, f0, c); LANES_NS L(res) += AM(c)[l] * L(fb); ENDL_NS }
       LANES_NS
         const real bl = (l < nefc) ? efc[4 * l] : real(0);
         L(t0) = (l < nefc) ? L(f0) * (bl + real(0.5) * L(res)) : real(0);
@@ -759,20 +802,39 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       if (LANE0(t0) > 0) { LANES_NS L(f0) = 0; L(res) = L(t1); ENDL_NS }
       while (iters < cm.iterations) {
         LANES_NS L(impr) = 0; ENDL_NS
-        for (int i = 0; i < nefc; ++i) {
+        {
+          const real *Ac = Y + 32 * YSTRIDE; const int n0 = nefc < 16 ? nefc : 16;
+          for (int i = 0; i < n0; ++i, Ac += YSTRIDE) {
           BCAST(ri, res, i); BCAST(fb, f0, i);
-          LANES_NS
-            const real *rc = efc + 4 * i;
-            const real ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb), resi = L(ri);
-            real fnew = fold - resi * ainv;
-            if (Rs < 0) fnew = mmax(fnew, real(0));
-            real delta = fnew - fold;
-            real change = delta * (real(0.5) * delta * Ad + resi);
-            if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
-            L(impr) -= change;
-            L(res) += Am[i * YSTRIDE + l] * delta;
-            if (l == i) L(f0) = fnew;
-          ENDL_NS
+            LANES_NS
+              const real *rc = efc + 4 * i;
+              const real ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb), resi = L(ri);
+              real fnew = fold - resi * ainv;
+              if (Rs < 0) fnew = mmax(fnew, real(0));
+              real delta = fnew - fold;
+              real change = delta * (real(0.5) * delta * Ad + resi);
+              if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+              L(impr) -= change;
+              L(res) += Ac[l] * delta;
+              if (l == i) L(f0) = fnew;
+            ENDL_NS
+          }
+          Ac = sm + S_XPOS;
+          for (int i = 16; i < nefc; ++i, Ac += YSTRIDE) {
+          BCAST(ri, res, i); BCAST(fb, f0, i);
+            LANES_NS
+              const real *rc = efc + 4 * i;
+              const real ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb), resi = L(ri);
+              real fnew = fold - resi * ainv;
+              if (Rs < 0) fnew = mmax(fnew, real(0));
+              real delta = fnew - fold;
+              real change = delta * (real(0.5) * delta * Ad + resi);
+              if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
+              L(impr) -= change;
+              L(res) += Ac[l] * delta;
+              if (l == i) L(f0) = fnew;
+            ENDL_NS
+          }
         }
         ++iters;
         if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
@@ -866,35 +928,19 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
-  // ================= sensors (mj_sensorPos / Vel / Acc for the Cassie layout) =================
   real *cst = E.cst;
-  LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc); } ENDL
+  // ================= accelerometer (mj_sensorAcc): the position / velocity sensors and the qacc-independent part were prepared before
+  // the constraint stage (which recycles the kinematics buffers); accel = g0 + G qacc over the IMU body's dof chain
+  LANES if (l < nv) vecs[32 + l] = L(qacc); ENDL
   LANES
-    if (l < 16) cst[CS_SENSOR + l] = cm.enc_scale[l] * qpos[cm.enc_qposadr[l]];   // actuatorpos = gear * q, jointpos = q
-    if (l < cm.nu) cst[CS_ACTVEL + l] = cm.act_gear[l] * vecs[cm.act_dof[l]];
-    if (l == 16) {  // IMU: framequat, gyro, accelerometer, magnetometer on site `imu`
-      const int b = cm.imu_body; real q[4], Rs[9], sp[3], v[3];
-      mul_quat(q, xquat + 4 * b, cm.imu_quat);
-      for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Rs[3 * a + c] = xmat[9 * b + 3 * a] * cm.imu_mat[c] + xmat[9 * b + 3 * a + 1] * cm.imu_mat[3 + c] + xmat[9 * b + 3 * a + 2] * cm.imu_mat[6 + c];
-      mat_vec(v, xmat + 9 * b, cm.imu_pos); sp[0] = xpos[3 * b] + v[0]; sp[1] = xpos[3 * b + 1] + v[1]; sp[2] = xpos[3 * b + 2] + v[2];
-      real dif[3] = {sp[0] - L(com0), sp[1] - L(com1), sp[2] - L(com2)};
-      // body spatial velocity / acceleration in the c-frame: chain sums over the body's dofs
-      real cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, -cm.gravity[0], -cm.gravity[1], -cm.gravity[2]};
-      for (int k = 0; k < 6; ++k) ca[k] += vecs[96 + k];
-      for (int a = cm.body_lastdof[b]; a >= 0; a = cm.dof_parent[a]) for (int k = 0; k < 6; ++k) { cv[k] += cdof[6 * a + k] * vecs[a]; ca[k] += cdof[6 * a + k] * vecs[32 + a]; }
-      real t3[3], vl[3], al[3], lw[3], lv[3], la[3], corr[3];
-      cross3(t3, dif, cv); vl[0] = cv[3] - t3[0]; vl[1] = cv[4] - t3[1]; vl[2] = cv[5] - t3[2];
-      cross3(t3, dif, ca); al[0] = ca[3] - t3[0]; al[1] = ca[4] - t3[1]; al[2] = ca[5] - t3[2];
-      matT_vec(lw, Rs, cv); matT_vec(lv, Rs, vl); matT_vec(la, Rs, al); cross3(corr, lw, lv);
-      for (int k = 0; k < 4; ++k) cst[CS_SENSOR + 16 + k] = q[k];
+    if (l == 16) {
+      const int nchain = (int)vecs[127];
       for (int k = 0; k < 3; ++k) {
-        real g = lw[k], a = la[k] + corr[k];
-        if (cm.gyro_cutoff > 0) g = clampr(g, -cm.gyro_cutoff, cm.gyro_cutoff);
-        if (cm.accel_cutoff > 0) a = clampr(a, -cm.accel_cutoff, cm.accel_cutoff);
-        cst[CS_SENSOR + 20 + k] = g; cst[CS_SENSOR + 23 + k] = a;
+        real acc = vecs[102 + k]; int a = cm.body_lastdof[cm.imu_body];
+        for (int c = 0; c < nchain; ++c, a = cm.dof_parent[a]) acc += vecs[105 + 3 * c + k] * vecs[32 + a];
+        if (cm.accel_cutoff > 0) acc = clampr(acc, -cm.accel_cutoff, cm.accel_cutoff);
+        cst[CS_SENSOR + 23 + k] = acc;
       }
-      real mg[3]; matT_vec(mg, Rs, cm.magnetic);
-      for (int k = 0; k < 3; ++k) cst[CS_SENSOR + 26 + k] = mg[k];
     }
   ENDL
   if (dbg) { LANES if (l < 29) dbg[D_SENS + l] = cst[CS_SENSOR + l]; ENDL }

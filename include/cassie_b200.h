@@ -74,7 +74,8 @@ void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask);
 
 /* cassie_sim_step_pd for every environment: pd_in[n_env] host AoS in, state_out[n_env] host AoS out (may be NULL).
  * Replaces n_env calls of src/cassiemujoco.c:1147-1157.  Synchronous.  state_out carries the pass-through fields of the
- * reference's state_output_step (motor/joint position+velocity+torque, IMU orientation/gyro/accel, radio, battery);
+ * reference's state_output_step (motor/joint position+velocity+torque, IMU orientation and gyro, radio, battery; verified equal
+ * to the real estimator's outputs for these fields); the raw accelerometer / magnetometer are in the compact observation row;
  * the estimator-only fields are zero (scope). */
 void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_out_t *state_out);
 
