@@ -294,7 +294,8 @@ class CassieBatch:
     def torch_view(self, field):
         """zero-copy torch tensor over a device state array (qpos [n,36], qvel [n,32], pd [n,52], obs [n,64])."""
         import torch
-        width = dict(qpos=36, qvel=32, pd=PD_WIDTH, obs=OBS_WIDTH, xfrc=8)[field]
+        self.L.cassie_batch_row_width.argtypes = [C.c_void_p, C.c_char_p]
+        width = self.L.cassie_batch_row_width(self.h, field.encode())
         dt, isz, ts = (np.float32, 4, '<f4') if self.precision == FP32 else (np.float64, 8, '<f8')
 
         class _Arr:

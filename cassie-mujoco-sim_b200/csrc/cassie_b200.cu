@@ -23,7 +23,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters, *ticket; const float *hfield; int n, n_terrain; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters, *ticket; const float *hfield; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,7 +45,7 @@ __device__ __forceinline__ void tma_stage(void *dst_smem, const void *src_gmem, 
 }
 
 template <typename real> __host__ __device__ constexpr size_t model_bytes() { return (sizeof(DevModel<real>) + 127) / 128 * 128; }
-template <typename real> __host__ __device__ constexpr size_t warp_bytes() { return ((size_t)S_REALS * sizeof(real) + 127) / 128 * 128; }
+template <typename real> __host__ __device__ constexpr size_t warp_bytes(int ystride) { return ((size_t)scratch_reals(ystride) * sizeof(real) + 127) / 128 * 128; }
 
 // mode 0: step nticks; mode 1: mj_forward only
 template <typename real>
@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
   tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
   const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
-  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>());
+  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>(A.ystride));
+  const int qw = A.qpos_w, vw = A.qvel_w;
   const DevModel<real> &cm = *cmp;
   // persistent warps: every warp pulls environment indices from a global ticket counter until the batch is exhausted, so a warp
   // that drew a cheap environment (few contacts, few solver sweeps) immediately starts another one
@@ -70,17 +71,19 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     else if (l < 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pd + (size_t)env * PD_W + 32 * (l - 9)));
     else if (l == 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.xfrc + (size_t)env * XFRC_W));
     // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
-    for (int i = l; i < QPOS_W; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * QPOS_W + i];
-    real qvel = A.qvel[(size_t)env * QVEL_W + l], qacc_ws = A.qacc_ws[(size_t)env * QVEL_W + l];
+    for (int i = l; i < qw; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * qw + i];
+    real qvel = A.qvel[(size_t)env * vw + l], qacc_ws = A.qacc_ws[(size_t)env * vw + l], xqvel = 0, xqacc_ws = 0;
+    if (A.xb >= 0 && l < 6) { xqvel = A.qvel[(size_t)env * vw + 32 + l]; xqacc_ws = A.qacc_ws[(size_t)env * vw + 32 + l]; }
     __syncwarp();
     EnvPtrs<real> E;
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    step_env(cm, sm, E, qvel, qacc_ws, nticks, mode != 0);
+    step_env(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode != 0);
     __syncwarp();
-    for (int i = l; i < QPOS_W; i += 32) A.qpos[(size_t)env * QPOS_W + i] = sm[S_QPOS + i];
-    A.qvel[(size_t)env * QVEL_W + l] = qvel; A.qacc_ws[(size_t)env * QVEL_W + l] = qacc_ws;
+    for (int i = l; i < qw; i += 32) A.qpos[(size_t)env * qw + i] = sm[S_QPOS + i];
+    A.qvel[(size_t)env * vw + l] = qvel; A.qacc_ws[(size_t)env * vw + l] = qacc_ws;
+    if (A.xb >= 0 && l < 6) { A.qvel[(size_t)env * vw + 32 + l] = xqvel; A.qacc_ws[(size_t)env * vw + 32 + l] = xqacc_ws; }
     __syncwarp();
   }
 }
@@ -90,12 +93,12 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
 // stream tiles through an ISTAGES-deep shared-memory ring: TMA bulk loads (cp.async.bulk -> mbarrier), in-place arithmetic,
 // TMA bulk store of the qpos chunk.  Algorithmic traffic per env: read qpos + qvel, write qpos = (36 + 32 + 36) reals.
 constexpr int ITILE = 64, ISTAGES = 4;
-template <typename real> __host__ __device__ constexpr size_t itile_bytes() { return (size_t)ITILE * (QPOS_W + QVEL_W) * sizeof(real); }
+template <typename real> __host__ __device__ constexpr size_t itile_bytes(int qw, int vw) { return (size_t)ITILE * (qw + vw) * sizeof(real); }
 template <typename real>
-__global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<real> *__restrict__ gmodel, real *__restrict__ qpos, const real *__restrict__ qvel, int n) {
+__global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<real> *__restrict__ gmodel, real *__restrict__ qpos, const real *__restrict__ qvel, int n, int QPOS_W, int QVEL_W) {
   extern __shared__ __align__(128) unsigned char ibuf[];
   __shared__ __align__(8) uint64_t bar[ISTAGES];
-  __shared__ int ns, nb, sq_adr[MJ], sd_adr[MJ], bq_adr[MJ], bd_adr[MJ];
+  __shared__ int ns, nb, sq_adr[MJ + 4], sd_adr[MJ + 4], bq_adr[MJ], bd_adr[MJ];
   __shared__ real h;
   const int ntiles = (n + ITILE - 1) / ITILE;
   if (threadIdx.x == 0) {
@@ -103,6 +106,10 @@ __global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<re
     for (int j = 0; j < gmodel->njnt; ++j) {
       const int t = gmodel->jnt_type[j];
       if (t >= 2) { sq_adr[a] = gmodel->jnt_qposadr[j]; sd_adr[a] = gmodel->jnt_dofadr[j]; ++a; } else if (t == 1) { bq_adr[b] = gmodel->jnt_qposadr[j]; bd_adr[b] = gmodel->jnt_dofadr[j]; ++b; }
+      else {   // free joint: three translations like slides, the quaternion like a ball joint
+        for (int k = 0; k < 3; ++k) { sq_adr[a] = gmodel->jnt_qposadr[j] + k; sd_adr[a] = gmodel->jnt_dofadr[j] + k; ++a; }
+        bq_adr[b] = gmodel->jnt_qposadr[j] + 3; bd_adr[b] = gmodel->jnt_dofadr[j] + 3; ++b;
+      }
     }
     ns = a; nb = b; h = gmodel->timestep;
     for (int s = 0; s < ISTAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(1));
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<re
   auto issue_load = [&](int stage, int tile) {   // thread 0 only
     const int cnt = min(ITILE, n - tile * ITILE);
     const uint32_t bq = (uint32_t)(cnt * QPOS_W * sizeof(real)), bv = (uint32_t)(cnt * QVEL_W * sizeof(real));
-    unsigned char *dst = ibuf + (size_t)stage * itile_bytes<real>();
+    unsigned char *dst = ibuf + (size_t)stage * itile_bytes<real>(QPOS_W, QVEL_W);
     const uint32_t bar_a = smem_u32(&bar[stage]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bq + bv) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(qpos + (size_t)tile * ITILE * QPOS_W), "r"(bq), "r"(bar_a) : "memory");
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<re
     if (tile >= ntiles) break;
     const int stage = i % ISTAGES; const uint32_t parity = (uint32_t)((i / ISTAGES) & 1), bar_a = smem_u32(&bar[stage]);
     asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(bar_a), "r"(parity) : "memory");
-    real *sq = reinterpret_cast<real *>(ibuf + (size_t)stage * itile_bytes<real>()); const real *sv = sq + ITILE * QPOS_W;
+    real *sq = reinterpret_cast<real *>(ibuf + (size_t)stage * itile_bytes<real>(QPOS_W, QVEL_W)); const real *sv = sq + ITILE * QPOS_W;
     const int cnt = min(ITILE, n - tile * ITILE);
     // scalar joints: lane = joint, warps stride over the tile's environments (a row's 36 entries sit in distinct banks);
     // ball joints: thread = (env, ball joint), dense, no divergence
@@ -175,7 +182,7 @@ struct BatchBase {
 };
 
 template <typename real> struct Batch : BatchBase {
-  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0; int resident_ctas = 1;
+  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0; int resident_ctas = 1, QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr;   // pinned staging for the AoS entry point
   float *d_hfield = nullptr;
@@ -192,10 +199,11 @@ template <typename real> struct Batch : BatchBase {
     if (!build_dev_model(hm, *hmodel, err, &info)) { free(hmodel); set_err(err); return false; }
     if (info.unsupported_pairs) fprintf(stderr, "cassie_b200: note: %d candidate geom pairs involve box/hfield geoms that this build does not collide (skipped)\n", info.unsupported_pairs);
     CUDA_OK(cudaMalloc(&d_model, model_bytes<real>()));
-    CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice)); free(hmodel);
+    CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
+    const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
     A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0;
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
-    CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QPOS_W)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * QVEL_W)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * QVEL_W));
+    CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QW)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * VW)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * VW));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
     CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * NM_MAX)); CUDA_OK(cudaMalloc(&A.ticket, sizeof(int)));
     CUDA_OK(cudaMemset(A.pd, 0, sizeof(real) * n * PD_W)); CUDA_OK(cudaMemset(A.obs, 0, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMemset(A.counters, 0, sizeof(int) * n * 8));
@@ -211,14 +219,14 @@ template <typename real> struct Batch : BatchBase {
       int best = 0, kk[5] = {0, 0, 0, 0, 0}; wpb = 1;
       for (int ctas = 4; ctas >= 1; --ctas) {
         long per_cta = (long)sm_smem / ctas - 1024; if (per_cta > dev_smem) per_cta = dev_smem;
-        int k = (int)((per_cta - (long)model_bytes<real>()) / (long)warp_bytes<real>()); if (k > 16) k = 16; if (k < 0) k = 0;
+        int k = (int)((per_cta - (long)model_bytes<real>()) / (long)warp_bytes<real>(hmodel_ystride)); if (k > 16) k = 16; if (k < 0) k = 0;
         kk[ctas] = k; if (k * ctas > best) best = k * ctas;
       }
       // several small CTAs refill an SM more smoothly than one big one: take the most CTAs within 15 % of the best residency
       for (int ctas = 4; ctas >= 1; --ctas) if (kk[ctas] >= 1 && kk[ctas] * ctas * 100 >= best * 85) { wpb = kk[ctas]; break; }
     }
-    if (wpb < 1 || wpb > 16 || model_bytes<real>() + (size_t)wpb * warp_bytes<real>() > (size_t)dev_smem) { set_err("not enough shared memory per block"); return false; }
-    smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>();
+    if (wpb < 1 || wpb > 16 || model_bytes<real>() + (size_t)wpb * warp_bytes<real>(hmodel_ystride) > (size_t)dev_smem) { set_err("not enough shared memory per block"); return false; }
+    smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>(hmodel_ystride);
     CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { int per_sm = 0, sms = 0; CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real>, 32 * wpb, smem));
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)); resident_ctas = per_sm * sms; if (resident_ctas < 1) resident_ctas = 1; }
@@ -226,21 +234,21 @@ template <typename real> struct Batch : BatchBase {
   }
   bool reset(const unsigned char *mask) override {
     CUDA_OK(cudaSetDevice(device));
-    std::vector<real> qpos(QPOS_W), qvel(QVEL_W), qa(QVEL_W), cst(CST_W), xf(XFRC_W); std::vector<int> df(DFILT_W);
+    std::vector<real> qpos(QPOS_W_XB), qvel(QVEL_W_XB), qa(QVEL_W_XB), cst(CST_W), xf(XFRC_W); std::vector<int> df(DFILT_W);
     init_env_rows(hm, qpos.data(), qvel.data(), qa.data(), cst.data(), df.data(), xf.data());
     if (!mask) {
       std::vector<real> buf((size_t)n * CST_W); std::vector<int> ibuf((size_t)n * DFILT_W, 0);
       auto fill = [&](real *dst, const std::vector<real> &row, int w) -> bool { for (int e = 0; e < n; e++) memcpy(&buf[(size_t)e * w], row.data(), sizeof(real) * w); CUDA_OK(cudaMemcpyAsync(dst, buf.data(), sizeof(real) * n * w, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream)); return true; };
-      if (!fill(A.qpos, qpos, QPOS_W) || !fill(A.qvel, qvel, QVEL_W) || !fill(A.qacc_ws, qa, QVEL_W) || !fill(A.cst, cst, CST_W) || !fill(A.xfrc, xf, XFRC_W)) return false;
+      if (!fill(A.qpos, qpos, QW) || !fill(A.qvel, qvel, VW) || !fill(A.qacc_ws, qa, VW) || !fill(A.cst, cst, CST_W) || !fill(A.xfrc, xf, XFRC_W)) return false;
       CUDA_OK(cudaMemcpyAsync(A.dfilt, ibuf.data(), sizeof(int) * n * DFILT_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
       return step(0, 1);
     }
     // masked reset: rewrite the selected rows, then forward everything (forward is idempotent for untouched envs except
     // that their sensordata is refreshed from their current state, which is what mj_forward would give)
     for (int e = 0; e < n; e++) if (mask[e]) {
-      CUDA_OK(cudaMemcpyAsync(A.qpos + (size_t)e * QPOS_W, qpos.data(), sizeof(real) * QPOS_W, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.qvel + (size_t)e * QVEL_W, qvel.data(), sizeof(real) * QVEL_W, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.qacc_ws + (size_t)e * QVEL_W, qa.data(), sizeof(real) * QVEL_W, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.qpos + (size_t)e * QW, qpos.data(), sizeof(real) * QW, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.qvel + (size_t)e * VW, qvel.data(), sizeof(real) * VW, cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaMemcpyAsync(A.qacc_ws + (size_t)e * VW, qa.data(), sizeof(real) * VW, cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaMemcpyAsync(A.cst + (size_t)e * CST_W, cst.data(), sizeof(real) * CST_W, cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaMemcpyAsync(A.xfrc + (size_t)e * XFRC_W, xf.data(), sizeof(real) * XFRC_W, cudaMemcpyHostToDevice, stream));
       CUDA_OK(cudaMemcpyAsync(A.dfilt + (size_t)e * DFILT_W, df.data(), sizeof(int) * DFILT_W, cudaMemcpyHostToDevice, stream));
@@ -312,12 +320,11 @@ template <typename real> struct Batch : BatchBase {
   bool integrate() override {
     CUDA_OK(cudaSetDevice(device));
     const int ntiles = (n + ITILE - 1) / ITILE; int sms = 0; CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const size_t ib = ISTAGES * itile_bytes<real>();
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_OK(cudaFuncSetAttribute(cassie_integrate_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ib)); attr_set = true; }
-    const int per_sm = sizeof(real) == 4 ? 3 : 1;
+    const size_t ib = ISTAGES * itile_bytes<real>(A.qpos_w, A.qvel_w);
+    CUDA_OK(cudaFuncSetAttribute(cassie_integrate_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ib));
+    const int per_sm = (int)(220000 / ib) < 1 ? 1 : (int)(220000 / ib);
     const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
-    cassie_integrate_kernel<real><<<grid, 256, ib, stream>>>(d_model, A.qpos, A.qvel, n);
+    cassie_integrate_kernel<real><<<grid, 256, ib, stream>>>(d_model, A.qpos, A.qvel, n, A.qpos_w, A.qvel_w);
     launches++;
     CUDA_OK(cudaGetLastError());
     return true;
@@ -330,9 +337,9 @@ template <typename real> struct Batch : BatchBase {
     return true;
   }
   bool get(const char *f, double *out) override {
-    if (!strcmp(f, "qpos")) return d2h(A.qpos, QPOS_W, hm.nq, 0, out);
-    if (!strcmp(f, "qvel")) return d2h(A.qvel, QVEL_W, hm.nv, 0, out);
-    if (!strcmp(f, "qacc_ws")) return d2h(A.qacc_ws, QVEL_W, hm.nv, 0, out);
+    if (!strcmp(f, "qpos")) return d2h(A.qpos, QW, hm.nq, 0, out);
+    if (!strcmp(f, "qvel")) return d2h(A.qvel, VW, hm.nv, 0, out);
+    if (!strcmp(f, "qacc_ws")) return d2h(A.qacc_ws, VW, hm.nv, 0, out);
     if (!strcmp(f, "time")) return d2h(A.cst, CST_W, 1, CS_TIME, out);
     if (!strcmp(f, "obs")) return d2h(A.obs, OBS_W, OBS_W, 0, out);
     if (!strcmp(f, "cst")) return d2h(A.cst, CST_W, CST_W, 0, out);
@@ -347,8 +354,8 @@ template <typename real> struct Batch : BatchBase {
     return true;
   }
   bool set(const char *f, const double *in) override {
-    if (!strcmp(f, "qpos")) return h2d(A.qpos, QPOS_W, hm.nq, 0, in);
-    if (!strcmp(f, "qvel")) return h2d(A.qvel, QVEL_W, hm.nv, 0, in);
+    if (!strcmp(f, "qpos")) return h2d(A.qpos, QW, hm.nq, 0, in);
+    if (!strcmp(f, "qvel")) return h2d(A.qvel, VW, hm.nv, 0, in);
     if (!strcmp(f, "time")) return h2d(A.cst, CST_W, 1, CS_TIME, in);
     if (!strcmp(f, "sto")) return h2d(A.cst, CST_W, 1, CS_STO, in);
     if (!strcmp(f, "cst")) return h2d(A.cst, CST_W, CST_W, 0, in);
@@ -416,6 +423,10 @@ int cassie_batch_nenv(const cassie_batch_t *b) { return b->impl->n; }
 int cassie_batch_nq(const cassie_batch_t *b) { return b->impl->hm.nq; }
 int cassie_batch_nv(const cassie_batch_t *b) { return b->impl->hm.nv; }
 int cassie_batch_precision(const cassie_batch_t *b) { return b->impl->precision; }
+int cassie_batch_row_width(const cassie_batch_t *b, const char *field) {
+  if (!strcmp(field, "qpos")) return b->impl->hm.nq > 36 ? QPOS_W_XB : QPOS_W_MAIN; if (!strcmp(field, "qvel")) return b->impl->hm.nv > 32 ? QVEL_W_XB : QVEL_W_MAIN;
+  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; return -1;
+}
 long cassie_batch_launch_count(const cassie_batch_t *b) { return b->impl->launches; }
 void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); }
 void cassie_batch_set_pd(cassie_batch_t *b, const double *pd) { b->impl->set_pd(pd); }

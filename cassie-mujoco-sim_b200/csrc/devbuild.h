@@ -24,18 +24,33 @@ struct BuildInfo { int unsupported_pairs = 0; int collision_geoms = 0; };
 template <typename real>
 bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, BuildInfo *info = nullptr) {
   std::memset(&d, 0, sizeof d);
-  if (m.nv > MV || m.nbody > MB || m.njnt > MJ || m.nM > NM_MAX || m.neq > ME || m.nu != MU) { err = "model exceeds the one-warp-per-env limits (nv<=32, nbody<=32, neq<=4, nu==10)"; return false; }
-  for (int j = 0; j < m.njnt; j++) if (m.jnt_type[j] == JNT_FREE) { err = "free joints are not supported by the batched stepper yet"; return false; }
+  // at most one extra free body (cassie_tray_box.xml's cup): it must be the last joint / last 6 dofs, a child of the world, with its inertial
+  // frame equal to its body frame; its dofs live beside the main tree's (one lane per main-tree dof)
+  int xb = -1;
+  for (int j = 0; j < m.njnt; j++) if (m.jnt_type[j] == JNT_FREE) {
+    int b = m.jnt_bodyid[j];
+    if (xb >= 0 || j != m.njnt - 1 || m.jnt_dofadr[j] != m.nv - 6 || m.body_parentid[b] != 0 || b != m.nbody - 1) { err = "only one free body, defined last and attached to the world, is supported"; return false; }
+    if (std::fabs(m.body_ipos[3 * b]) + std::fabs(m.body_ipos[3 * b + 1]) + std::fabs(m.body_ipos[3 * b + 2]) > 1e-12 || std::fabs(m.body_iquat[4 * b]) < 1 - 1e-12) { err = "the free body's inertial frame must coincide with its body frame"; return false; }
+    xb = b;
+  }
+  const int nvm = m.nv - (xb >= 0 ? 6 : 0);   // dofs of the main tree
+  if (nvm > MV || m.nbody > MB || m.njnt > MJ || m.nM > NM_MAX + 21 || m.neq > ME || m.nu != MU) { err = "model exceeds the one-warp-per-env limits (main-tree nv<=32, nbody<=32, neq<=4, nu==10)"; return false; }
   { int root = -1;   // one moving tree; other bodies must be static (welded to the world, e.g. the 'floor' body of cassie_hfield.xml)
-    for (int b = 1; b < m.nbody; b++) { if (m.body_weldid[b] == 0) continue; if (root < 0) root = m.body_rootid[b]; if (m.body_rootid[b] != root) { err = "a single moving kinematic tree is required"; return false; } } }
+    for (int b = 1; b < m.nbody; b++) { if (m.body_weldid[b] == 0 || b == xb) continue; if (root < 0) root = m.body_rootid[b]; if (m.body_rootid[b] != root) { err = "a single articulated tree (plus at most one free body) is required"; return false; } } }
   if (m.nhfield > 1) { err = "at most one height field is supported"; return false; }
   if (m.nhfield == 1) { d.hf_nrow = m.hfield_nrow[0]; d.hf_ncol = m.hfield_ncol[0]; for (int k = 0; k < 4; k++) d.hf_size[k] = (real)m.hfield_size[k]; }
-  d.nq = m.nq; d.nv = m.nv; d.nbody = m.nbody; d.njnt = m.njnt; d.neq = m.neq; d.nu = m.nu; d.nM = m.nM; d.iterations = m.iterations;
+  d.nq = m.nq; d.nv = nvm; d.nbody = m.nbody; d.njnt = m.njnt; d.neq = m.neq; d.nu = m.nu; d.iterations = m.iterations;
+  d.nM = 0; for (int i = 0; i < nvm; i++) d.nM = m.dof_Madr[i] + 1; { int last = nvm - 1, dep = 0; for (int k = m.dof_parentid[last]; k >= 0; k = m.dof_parentid[k]) dep++; d.nM = m.dof_Madr[last] + dep + 1; }
+  d.xb = xb; d.qpos_w = xb >= 0 ? QPOS_W_XB : QPOS_W_MAIN; d.qvel_w = xb >= 0 ? QVEL_W_XB : QVEL_W_MAIN; d.ystride = xb >= 0 ? YSTRIDE_MAX : YSTRIDE_MAIN;
+  if (xb >= 0) {
+    d.xb_jnt = m.njnt - 1; d.xb_qadr = m.jnt_qposadr[d.xb_jnt]; d.xb_dadr = m.jnt_dofadr[d.xb_jnt];
+    d.xb_mass = (real)m.body_mass[xb]; for (int k = 0; k < 3; k++) { d.xb_inertia[k] = (real)m.body_inertia[3 * xb + k]; d.xb_dsqi[k] = (real)(1.0 / std::sqrt(m.body_mass[xb])); d.xb_dsqi[3 + k] = (real)(1.0 / std::sqrt(m.body_inertia[3 * xb + k])); }
+  }
   d.timestep = (real)m.timestep; d.tolerance = (real)m.tolerance; d.pgs_scale = (real)(1.0 / (m.meaninertia * std::max(1, m.nv)));
   d.nsub = (int)std::lround(5e-4 / m.timestep); if (d.nsub < 1) d.nsub = 1;
   d.euler_eps = (real)(4 * std::numeric_limits<real>::epsilon());
   d.force_zpath = std::getenv("CASSIE_B200_ZPATH") ? 1 : 0;   // test hook: force the reduction-based solver path used when nefc > 32
-  double mass = 0; for (int b = 1; b < m.nbody; b++) mass += m.body_mass[b];
+  double mass = 0; for (int b = 1; b < m.nbody; b++) if (b != xb) mass += m.body_mass[b];
   d.root_mass_inv = (real)(1.0 / mass);
   for (int k = 0; k < 3; k++) { d.gravity[k] = (real)m.gravity[k]; d.magnetic[k] = (real)m.magnetic[k]; }
   // bodies
@@ -44,7 +59,7 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     if (d.body_depth[b] > d.maxdepth) d.maxdepth = d.body_depth[b];
     d.body_jntadr[b] = m.body_jntadr[b]; d.body_jntnum[b] = m.body_jntnum[b];
     int p = b; while (p > 0 && m.body_dofnum[p] == 0) p = m.body_parentid[p];
-    d.body_lastdof[b] = p > 0 ? m.body_dofadr[p] + m.body_dofnum[p] - 1 : -1;
+    d.body_lastdof[b] = (p > 0 && b != xb) ? m.body_dofadr[p] + m.body_dofnum[p] - 1 : -1;
     uint32_t mask = 0; for (int k = d.body_lastdof[b]; k >= 0; k = m.dof_parentid[k]) mask |= 1u << k;
     d.body_dofmask[b] = mask;
     int end = b + 1; while (end < m.nbody) { int a = end; while (a > b) a = m.body_parentid[a]; if (a != b) break; end++; }
@@ -68,29 +83,29 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
   }
   // dofs
   d.ntri = 0;
-  for (int i = 0; i < m.nv; i++) {
+  for (int i = 0; i < nvm; i++) {
     d.dof_body[i] = m.dof_bodyid[i]; d.dof_jnt[i] = m.dof_jntid[i]; d.dof_parent[i] = m.dof_parentid[i]; d.dof_Madr[i] = m.dof_Madr[i];
     d.dof_armature[i] = (real)m.dof_armature[i]; d.dof_damping[i] = (real)m.dof_damping[i]; d.dof_invweight0[i] = (real)m.dof_invweight0[i];
     uint32_t mask = 0; int depth = 0; for (int k = m.dof_parentid[i]; k >= 0; k = m.dof_parentid[k]) { mask |= 1u << k; depth++; }
     d.dof_ancmask[i] = mask; d.dof_depth[i] = depth; d.dof_Mrow[i] = m.dof_Madr[i] + depth;
     if (depth > 15) { err = "dof tree deeper than 15"; return false; }
     { int t = 1; for (int k = m.dof_parentid[i]; k >= 0; k = m.dof_parentid[k]) d.dof_anc[i][t++] = (unsigned char)k; }
-    { int end = i + 1; while (end < m.nv) { int a = end; while (a > i) a = m.dof_parentid[a]; if (a != i) break; end++; } d.dof_subtree_end[i] = end; }
+    { int end = i + 1; while (end < nvm) { int a = end; while (a > i) a = m.dof_parentid[a]; if (a != i) break; end++; } d.dof_subtree_end[i] = end; }
     if (m.dof_damping[i] > 0) d.has_damping = 1;
     int j = m.dof_jntid[i];
     d.dof_cvelsrc[i] = (m.jnt_type[j] == JNT_BALL) ? m.dof_parentid[m.jnt_dofadr[j]] : m.dof_parentid[i];
   }
-  for (int i = m.nv - 1; i >= 0; i--) { int a = m.dof_Madr[i] + 1; for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) { if (d.ntri >= NTRI_MAX) { err = "too many factor entries"; return false; } d.tri[d.ntri++] = ((uint32_t)i << 24) | ((uint32_t)j << 16) | (uint32_t)a; a++; } }
+  for (int i = nvm - 1; i >= 0; i--) { int a = m.dof_Madr[i] + 1; for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) { if (d.ntri >= NTRI_MAX) { err = "too many factor entries"; return false; } d.tri[d.ntri++] = ((uint32_t)i << 24) | ((uint32_t)j << 16) | (uint32_t)a; a++; } }
   // balanced factorisation schedule (falls back to the per-ancestor loop when the table would not fit)
-  { int total = 0; for (int k = 0; k < m.nv; k++) total += d.dof_depth[k] * (d.dof_depth[k] + 1) / 2;
+  { int total = 0; for (int k = 0; k < nvm; k++) total += d.dof_depth[k] * (d.dof_depth[k] + 1) / 2;
     d.nfac = 0;
     if (total <= NFAC_MAX) {
       int n = 0;
-      for (int k = 0; k < m.nv; k++) {
+      for (int k = 0; k < nvm; k++) {
         d.fac_start[k] = n; int dk = d.dof_depth[k], kk = m.dof_Madr[k];
         for (int t = 1; t <= dk; t++) { int i = d.dof_anc[k][t], ia = m.dof_Madr[i]; for (int c = 0; c <= dk - t; c++) d.fac_pairs[n++] = ((uint32_t)t << 24) | ((uint32_t)(kk + t + c) << 12) | (uint32_t)(ia + c); }
       }
-      d.fac_start[m.nv] = n; d.nfac = n;
+      d.fac_start[nvm] = n; d.nfac = n;
     } }
   // IMU site and its sensors
   int imu = m.site_id("imu");
@@ -136,8 +151,8 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     if (d.ngeom >= MG) return -1;
     int k = d.ngeom++; gmap[g] = k; d.geom_body[k] = m.geom_bodyid[g]; d.geom_type[k] = m.geom_type[g];
     double R[9]; detail::q2m_d(R, &m.geom_quat[4 * g]);
-    for (int c = 0; c < 3; c++) { d.geom_pos[k][c] = (real)m.geom_pos[3 * g + c]; d.geom_zaxis[k][c] = (real)R[3 * c + 2]; }
-    d.geom_size[k][0] = (real)m.geom_size[3 * g]; d.geom_size[k][1] = (real)m.geom_size[3 * g + 1];
+    for (int c = 0; c < 3; c++) { d.geom_pos[k][c] = (real)m.geom_pos[3 * g + c]; d.geom_size[k][c] = (real)m.geom_size[3 * g + c]; }
+    for (int c = 0; c < 9; c++) d.geom_mat[k][c] = (real)R[c];
     return k;
   };
   int unsupported = 0;
@@ -149,11 +164,17 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       int g1 = ga, g2 = gb; if (m.geom_type[g1] > m.geom_type[g2]) std::swap(g1, g2);
       if (!((m.geom_contype[g1] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g1]))) continue;
       int t1 = m.geom_type[g1], t2 = m.geom_type[g2], kind;
+      { int gw = m.geom_bodyid[g1] == 0 ? g1 : (m.geom_bodyid[g2] == 0 ? g2 : -1);   // the 15 stair boxes of cassie.xml are parked 20 m away: not collided
+        if (gw >= 0 && m.geom_type[gw] == GEOM_BOX && std::fabs(m.geom_pos[3 * gw + 1]) > 10.0) { unsupported++; continue; } }
       if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) kind = PAIR_PLANE_SPHERE;
       else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) kind = PAIR_PLANE_CAPSULE;
       else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) kind = PAIR_CAPSULE_CAPSULE;
       else if (t1 == GEOM_HFIELD && t2 == GEOM_SPHERE) kind = PAIR_HFIELD_SPHERE;
       else if (t1 == GEOM_HFIELD && t2 == GEOM_CAPSULE) kind = PAIR_HFIELD_CAPSULE;
+      else if (t1 == GEOM_PLANE && t2 == GEOM_BOX) kind = PAIR_PLANE_BOX;
+      else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) kind = PAIR_SPHERE_BOX;
+      else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) kind = PAIR_CAPSULE_BOX;
+      else if (t1 == GEOM_BOX && t2 == GEOM_BOX) kind = PAIR_BOX_BOX;
       else { unsupported++; continue; }
       if (d.npair >= MP) { err = "too many candidate geom pairs"; return false; }
       if (t1 == GEOM_HFIELD) { const double *q = &m.geom_quat[4 * g1], *bq = &m.body_quat[4 * m.geom_bodyid[g1]];
@@ -189,10 +210,10 @@ template <typename real>
 void init_env_rows(const HostModel &m, real *qpos, real *qvel, real *qacc_ws, real *cst, int *dfilt, real *xfrc) {
   static const double qi[28] = {0.0045, 0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968,
                                 -0.0045, 0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968};
-  for (int i = 0; i < QPOS_W; i++) qpos[i] = 0;
+  for (int i = 0; i < QPOS_W_XB; i++) qpos[i] = 0;
   for (int i = 0; i < m.nq; i++) qpos[i] = (real)m.qpos0[i];
   for (int i = 0; i < 28 && 7 + i < m.nq; i++) qpos[7 + i] = (real)qi[i];
-  for (int i = 0; i < QVEL_W; i++) { qvel[i] = 0; qacc_ws[i] = 0; }
+  for (int i = 0; i < QVEL_W_XB; i++) { qvel[i] = 0; qacc_ws[i] = 0; }
   for (int i = 0; i < CST_W; i++) cst[i] = 0;
   cst[CS_STO] = 1;  // radio channel 8 = 1 (cassie_out_init, :724)
   for (int i = 0; i < DFILT_W; i++) dfilt[i] = 0;

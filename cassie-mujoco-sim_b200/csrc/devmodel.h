@@ -3,6 +3,11 @@
 // by the test-only host emulation of the same source (tests/emu/).
 #pragma once
 #include <cstdint>
+#ifdef __CUDACC__
+#define CASSIE_HD __host__ __device__
+#else
+#define CASSIE_HD
+#endif
 
 namespace cassie {
 
@@ -18,19 +23,24 @@ constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 
 constexpr int NFAC_MAX = 1600; // rank-1 update pairs of the factorisation schedule (1519 for Cassie)
 constexpr int NEFC = 48;      // constraint rows per env (12 equality + limits + 4 per floor contact); excess contacts are dropped and counted
 constexpr int MAXCON = 12;    // contacts per env
-constexpr int YSTRIDE = 33;   // row stride of the constraint matrix in shared memory (bank-conflict free both ways)
+constexpr int YSTRIDE_MAIN = 33;  // row stride of the constraint matrix in shared memory: dofs + 1 (odd: bank-conflict free both ways)
+constexpr int YSTRIDE_MAX = 39;   // with the 6 dofs of an extra free body (cassie_tray_box.xml)
 
 // pair kinds handled by the narrow phase
-enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2, PAIR_HFIELD_SPHERE = 3, PAIR_HFIELD_CAPSULE = 4 };
+enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2, PAIR_HFIELD_SPHERE = 3, PAIR_HFIELD_CAPSULE = 4,
+                PAIR_PLANE_BOX = 5, PAIR_SPHERE_BOX = 6, PAIR_CAPSULE_BOX = 7, PAIR_BOX_BOX = 8 };
 
 template <typename real>
 struct DevModel {
   // ---- sizes / options
+  int qpos_w, qvel_w, ystride, xb;   // HBM row widths, constraint-matrix row stride, id of the extra free body (or -1)
+  int xb_qadr, xb_dadr, xb_jnt, padx;
   int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, has_damping, force_zpath;
   real timestep, tolerance, pgs_scale, root_mass_inv, euler_eps, padr[3];
   real gravity[3], magnetic[3], imu_pos[3], imu_quat[4], imu_mat[9], gyro_cutoff, accel_cutoff;
   int hf_nrow, hf_ncol, padh[2];
   real hf_size[4];           // height field: x half-size, y half-size, elevation scale, base thickness
+  real xb_mass, xb_inertia[3], xb_dsqi[6], padxb[2];  // extra free body: mass, principal inertia (inertial frame = body frame), 1/sqrt of its diagonal mass matrix
   // ---- bodies
   int body_parent[MB], body_depth[MB], body_jntadr[MB], body_jntnum[MB], body_lastdof[MB], body_subtree_end[MB];
   uint32_t body_dofmask[MB];
@@ -48,7 +58,7 @@ struct DevModel {
   uint32_t fac_pairs[NFAC_MAX];  // (t << 24) | (src << 12) | dst: qLD[dst] -= qLD[src] * f_t, grouped by eliminated dof k
   // ---- collision geoms and pairs
   int geom_body[MG], geom_type[MG];
-  real geom_pos[MG][3], geom_zaxis[MG][3], geom_size[MG][2];
+  real geom_pos[MG][3], geom_mat[MG][9], geom_size[MG][3];   // geom frame in its body (row-major rotation), sizes
   int pair_g1[MP], pair_g2[MP], pair_kind[MP], pair_condim[MP];
   real pair_mu[MP], pair_margin[MP], pair_gap[MP], pair_solref[MP][2], pair_solimp[MP][5];
   // ---- equality
@@ -60,8 +70,8 @@ struct DevModel {
 };
 
 // ---- HBM state: one row per environment in each array (row-major, env index slowest)
-constexpr int QPOS_W = 36;      // qpos[35] padded
-constexpr int QVEL_W = 32;
+constexpr int QPOS_W_MAIN = 36, QVEL_W_MAIN = 32;   // row widths for the nq 35 / nv 32 models (runtime values live in DevModel::qpos_w / qvel_w)
+constexpr int QPOS_W_XB = 44, QVEL_W_XB = 40;       // with an extra free body (nq 42 / nv 38)
 constexpr int CST_W = 192;      // controller / sensor state, layout below
 constexpr int DFILT_W = 96;     // int32 drive FIR taps [10][9] padded
 constexpr int PD_W = 52;        // torque, pTarget, dTarget, pGain, dGain for the 10 motors (+2 pad)
@@ -88,25 +98,24 @@ constexpr int S_CDOF = S_XMAT + 288;            // [32][6]
 constexpr int S_QLD = S_CDOF + 192;             // [320] (qM itself lives in a global scratch row)
 constexpr int S_DINV = S_QLD + NM_MAX;          // [32]
 constexpr int S_DSQI = S_DINV + 32;             // [32]
-constexpr int S_QPOS = S_DSQI + 32;             // [40]
-constexpr int S_VEC = S_QPOS + 40;              // [5][32] general vectors ([96..101]: cdof_dot*qvel chain sum of the IMU body; [128..159]: exchange buffer)
-constexpr int S_GEOM = S_VEC + 160;             // [16][6] world pos + z axis
-constexpr int S_CON = S_GEOM + 96;              // [MAXCON][16]
+constexpr int S_QPOS = S_DSQI + 32;             // [44]
+constexpr int S_VEC = S_QPOS + 44;              // [6][32] general vectors ([96..127]: IMU stash; [128..159]: exchange buffer; [160..183]: extra-body qvel / qacc_smooth / qacc_ws / qacc)
+constexpr int S_GEOM = S_VEC + 192;             // [16][12] world pos + rotation matrix (column 2 = z axis)
+constexpr int S_CON = S_GEOM + 192;             // [MAXCON][16]
 constexpr int S_EFC = S_CON + MAXCON * 16;               // [NEFC][4]: row-build scalars {.., pos, src, ineq} then solver constants {b, 1/A, A, +-R}
-constexpr int S_Y = S_EFC + 4 * NEFC;           // [NEFC][33] constraint matrix; before the constraint stage it holds the temporaries below
-constexpr int S_REALS = S_Y + NEFC * YSTRIDE;
+constexpr int S_Y = S_EFC + 4 * NEFC;           // [NEFC][ystride] constraint matrix; before the constraint stage it holds the temporaries below
+CASSIE_HD inline constexpr int scratch_reals(int ystride) { return S_Y + NEFC * ystride; }
 // temporaries inside the S_Y region (dead before the first constraint row is written)
 constexpr int T_CINERT = 0;                     // [32][10]
 constexpr int T_CRB = 320;                      // [32][10]; during kinematics: xanchor[32][3], xaxis[32][3], qloc[32][4]; later chain sums [32][6]
 constexpr int T_CVEL = 640;                     // [32][6]
 constexpr int T_CFRC = 832;                     // [32][6]
 constexpr int T_CDOFD = 1024;                   // [32][6]
-static_assert(T_CDOFD + 192 <= NEFC * YSTRIDE, "temporaries must fit in the constraint-matrix region");
-static_assert(NEFC >= 48 && 16 * YSTRIDE <= S_QLD - S_XPOS, "the dense solver path keeps A in rows 32..47 of Y and in the kinematics buffers");
+static_assert(T_CDOFD + 192 <= NEFC * YSTRIDE_MAIN, "temporaries must fit in the constraint-matrix region");
+static_assert(NEFC >= 48 && 16 * YSTRIDE_MAX <= S_QLD - S_XPOS, "the dense solver path keeps A in rows 32..47 of Y and in the kinematics buffers");
 // slots of a row's 4 scalars while the rows are being built (overwritten by the solver constants afterwards)
 constexpr int E_POS = 0, E_SRC = 1, E_INEQ = 2;
 
-template <typename real> constexpr size_t scratch_bytes() { return (size_t)S_REALS * sizeof(real); }
 
 // ---- debug dump (tests only; one block per env, in `real`)
 constexpr int D_XPOS = 0, D_XQUAT = 96, D_CDOF = 224, D_QM = 416, D_QLD = 736, D_BIAS = 1056, D_PASSIVE = 1088, D_SMOOTH = 1120,

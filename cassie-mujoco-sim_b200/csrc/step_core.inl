@@ -289,6 +289,83 @@ template <typename real> CFN bool hfield_sphere(const DevModel<real> &cm, const 
   return true;
 }
 
+// ---- box primitives (cassie_tray_box.xml): analytic definitions of our own; the CPU checker restates the same rules.
+// geom record g = [pos3, z-axis3, x-axis3, y-axis3] (world); local -> world: v = x*vx + y*vy + z*vz
+template <typename real> CFN void box_to_world(const real *g, const real *l3, real *w) {
+  w[0] = g[6] * l3[0] + g[9] * l3[1] + g[3] * l3[2]; w[1] = g[7] * l3[0] + g[10] * l3[1] + g[4] * l3[2]; w[2] = g[8] * l3[0] + g[11] * l3[1] + g[5] * l3[2];
+}
+template <typename real> CFN void box_to_local(const real *g, const real *w, real *l3) {
+  l3[0] = g[6] * w[0] + g[7] * w[1] + g[8] * w[2]; l3[1] = g[9] * w[0] + g[10] * w[1] + g[11] * w[2]; l3[2] = g[3] * w[0] + g[4] * w[1] + g[5] * w[2];
+}
+template <typename real> CFN void box_corner(const real *g, const real *s, int i, real *out) {
+  real l3[3] = {(i & 1) ? s[0] : -s[0], (i & 2) ? s[1] : -s[1], (i & 4) ? s[2] : -s[2]}, w[3];
+  box_to_world(g, l3, w); out[0] = g[0] + w[0]; out[1] = g[1] + w[1]; out[2] = g[2] + w[2];
+}
+// sphere (geom1) vs box (geom2): 0 or 1 contact; normal from the sphere to the box
+template <typename real> CFN int sphere_box(real margin, const real *sc, real r, const real *gb, const real *s, real *pos, real *nrm, real *dist) {
+  real t[3] = {sc[0] - gb[0], sc[1] - gb[1], sc[2] - gb[2]}, cl[3], q[3], nl[3], dd; bool inside = true;
+  box_to_local(gb, t, cl);
+  for (int k = 0; k < 3; ++k) { q[k] = clampr(cl[k], -s[k], s[k]); if (q[k] != cl[k]) inside = false; }
+  if (inside) {
+    int ax = 0; real best = real(1e30);
+    for (int k = 0; k < 3; ++k) { const real pen = s[k] - mabs(cl[k]); if (pen < best) { best = pen; ax = k; } }
+    nl[0] = nl[1] = nl[2] = 0; nl[ax] = cl[ax] >= 0 ? real(1) : real(-1); q[ax] = nl[ax] * s[ax]; dd = -best - r;
+  } else {
+    real dv[3] = {cl[0] - q[0], cl[1] - q[1], cl[2] - q[2]}; const real len = msqrt(dot3(dv, dv));
+    if (len - r >= margin) return 0;
+    nl[0] = dv[0] / len; nl[1] = dv[1] / len; nl[2] = dv[2] / len; dd = len - r;
+  }
+  if (dd >= margin) return 0;
+  real nw[3], qw[3]; box_to_world(gb, nl, nw); box_to_world(gb, q, qw);
+  *dist = dd;
+  for (int k = 0; k < 3; ++k) { nrm[k] = -nw[k]; pos[k] = gb[k] + qw[k] + nw[k] * dd * real(0.5); }
+  return 1;
+}
+// all box pair kinds; g1 / g2 = geom records, s1 / s2 = geom sizes; returns the contact count (<= 4)
+template <typename real> CFN int box_pair(int kind, real margin, const real *g1, const real *g2, const real *s1, const real *s2, real (*cp)[3], real (*cn)[3], real *cdst) {
+  int cnt = 0;
+  if (kind == PAIR_PLANE_BOX) {            // every corner below the plane, at most 4, in corner order
+    const real *n = g1 + 3;
+    for (int i = 0; i < 8 && cnt < 4; ++i) {
+      real v[3]; box_corner(g2, s2, i, v);
+      real t[3] = {v[0] - g1[0], v[1] - g1[1], v[2] - g1[2]}; const real dd = dot3(t, n);
+      if (dd >= margin) continue;
+      cdst[cnt] = dd; for (int k = 0; k < 3; ++k) { cn[cnt][k] = n[k]; cp[cnt][k] = v[k] - n[k] * dd * real(0.5); }
+      ++cnt;
+    }
+  } else if (kind == PAIR_SPHERE_BOX) {
+    cnt = sphere_box(margin, g1, s1[0], g2, s2, cp[0], cn[0], cdst);
+  } else if (kind == PAIR_CAPSULE_BOX) {   // closest point of the capsule axis to the box by alternating projections, then sphere vs box
+    const real *ax = g1 + 3; const real hl = s1[1]; real t, p[3], pl[3], q[3], qw[3], tmp[3];
+    for (int k = 0; k < 3; ++k) tmp[k] = g2[k] - g1[k];
+    t = clampr(dot3(tmp, ax), -hl, hl);
+    for (int it = 0; it < 4; ++it) {
+      for (int k = 0; k < 3; ++k) { p[k] = g1[k] + ax[k] * t; tmp[k] = p[k] - g2[k]; }
+      box_to_local(g2, tmp, pl); for (int k = 0; k < 3; ++k) q[k] = clampr(pl[k], -s2[k], s2[k]);
+      box_to_world(g2, q, qw); for (int k = 0; k < 3; ++k) tmp[k] = g2[k] + qw[k] - g1[k];
+      t = clampr(dot3(tmp, ax), -hl, hl);
+    }
+    for (int k = 0; k < 3; ++k) p[k] = g1[k] + ax[k] * t;
+    cnt = sphere_box(margin, p, s1[0], g2, s2, cp[0], cn[0], cdst);
+  } else {                                 // box - box: corners of g2 inside g1, then corners of g1 inside g2
+    for (int pass = 0; pass < 2 && cnt < 4; ++pass) {
+      const real *ga = pass ? g2 : g1, *gb = pass ? g1 : g2, *as = pass ? s2 : s1, *bs = pass ? s1 : s2;
+      for (int i = 0; i < 8 && cnt < 4; ++i) {
+        real v[3], vl[3]; box_corner(gb, bs, i, v);
+        real t[3] = {v[0] - ga[0], v[1] - ga[1], v[2] - ga[2]}; box_to_local(ga, t, vl);
+        int ax = -1; real best = real(1e30);
+        for (int k = 0; k < 3; ++k) { const real pen = as[k] - mabs(vl[k]); if (pen <= -margin) { ax = -1; break; } if (pen < best) { best = pen; ax = k; } }
+        if (ax < 0) continue;
+        real nl[3] = {0, 0, 0}, nw[3]; nl[ax] = vl[ax] >= 0 ? real(1) : real(-1); box_to_world(ga, nl, nw);
+        const real sgn = pass ? real(-1) : real(1);
+        cdst[cnt] = -best; for (int k = 0; k < 3; ++k) { cn[cnt][k] = sgn * nw[k]; cp[cnt][k] = v[k] + nw[k] * best * real(0.5); }
+        ++cnt;
+      }
+    }
+  }
+  return cnt;
+}
+
 // translational Jacobian column of dof l for a world point attached to `body` (zero when l is not in the body's chain)
 template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int body, const real *cd, const real *point, const real *com, real *out) {
   if ((cm.body_dofmask[body] >> l) & 1u) {
@@ -301,9 +378,9 @@ template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int b
 // ------------------------------------------------------------------ one MuJoCo sub-step (mj_step1 + mj_step2)
 // state in: sm[S_QPOS], lane vars qvel / qacc_ws, ctrl in sm[S_CST..] (via ctrl lane var), xfrc.  state out: same + sensordata.
 template <typename real>
-CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, ctrl), real *dbg, bool advance) {
+CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), LP(real, ctrl), real *dbg, bool advance) {
   DECL_LANE
-  const int nv = cm.nv, nb = cm.nbody;
+  const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
   real *qpos = sm + S_QPOS, *qM = E.qM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
   const real *xfrc = E.xfrc; int *counters = E.counters;
@@ -328,7 +405,13 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   ENDL
   for (int lev = 1; lev <= cm.maxdepth; ++lev) {
     LANES  // lane = body at this tree level
-      if (l < nb && cm.body_depth[l] == lev) {
+      if (l < nb && cm.body_depth[l] == lev && l == xb) {   // free joint: pose straight from qpos (position, quaternion)
+        const int qa = cm.xb_qadr; real quat[4] = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
+        normalize4(quat);
+        xpos[3 * l] = qpos[qa]; xpos[3 * l + 1] = qpos[qa + 1]; xpos[3 * l + 2] = qpos[qa + 2];
+        xquat[4 * l] = quat[0]; xquat[4 * l + 1] = quat[1]; xquat[4 * l + 2] = quat[2]; xquat[4 * l + 3] = quat[3];
+        quat2mat(xmat + 9 * l, quat);
+      } else if (l < nb && cm.body_depth[l] == lev) {
         const int p = cm.body_parent[l];
         real pos[3], quat[4], v[3], R[9];
         mat_vec(v, xmat + 9 * p, cm.body_pos[l]);
@@ -361,7 +444,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   LV(real, t0); LV(real, t1); LV(real, t2);
   LANES  // lane = body
     L(t0) = L(t1) = L(t2) = 0;
-    if (l >= 1 && l < nb) {
+    if (l >= 1 && l < nb && l != xb) {
       real v[3]; mat_vec(v, xmat + 9 * l, cm.body_ipos[l]);
       const real m = cm.body_mass[l];
       L(t0) = m * (xpos[3 * l] + v[0]); L(t1) = m * (xpos[3 * l + 1] + v[1]); L(t2) = m * (xpos[3 * l + 2] + v[2]);
@@ -510,6 +593,20 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   LANES if (l < cm.nu) vecs[32 + cm.act_dof[l]] = cm.act_gear[l] * clampr(L(ctrl), cm.act_ctrl_lo[l], cm.act_ctrl_hi[l]); ENDL
   LANES if (l < nv) { L(qfrc_smooth) += vecs[32 + l]; L(qacc_smooth) = L(qfrc_smooth); } else L(qacc_smooth) = 0; ENDL
   solve_m(cm, sm, qacc_smooth);
+  // ---- extra free body (cassie_tray_box.xml: the cup): its mass matrix is the constant diag(m, m, m, I1, I2, I3) (translation in the
+  // world frame, rotation in the body frame, inertial frame = body frame), so its smooth acceleration is closed form; lanes 0..5 = its dofs
+  LV(real, xqacc_smooth); LV(real, xz); LV(real, xqacc);
+  LANES L(xqacc_smooth) = 0; L(xz) = 0; L(xqacc) = 0; if (xb >= 0 && l < 6) vecs[160 + l] = L(xqvel); ENDL
+  if (xb >= 0) {
+    LANES
+      if (l < 3) L(xqacc_smooth) = cm.gravity[l];
+      else if (l < 6) {
+        const real w[3] = {vecs[163], vecs[164], vecs[165]}, Iw[3] = {cm.xb_inertia[0] * w[0], cm.xb_inertia[1] * w[1], cm.xb_inertia[2] * w[2]}; real t3[3];
+        cross3(t3, w, Iw);
+        L(xqacc_smooth) = -t3[l - 3] / cm.xb_inertia[l - 3];
+      }
+    ENDL
+  }
   if (dbg) {
     LANES
       if (l < nv) { dbg[D_SMOOTH + l] = L(qfrc_smooth); dbg[D_QACCS + l] = L(qacc_smooth); for (int k = 0; k < 6; ++k) dbg[D_CDOF + 6 * l + k] = cdof[6 * l + k]; }
@@ -565,22 +662,21 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     if (l < cm.ngeom) {
       const int b = cm.geom_body[l]; real v[3];
       mat_vec(v, xmat + 9 * b, cm.geom_pos[l]);
-      geom[6 * l] = xpos[3 * b] + v[0]; geom[6 * l + 1] = xpos[3 * b + 1] + v[1]; geom[6 * l + 2] = xpos[3 * b + 2] + v[2];
-      mat_vec(v, xmat + 9 * b, cm.geom_zaxis[l]);
-      geom[6 * l + 3] = v[0]; geom[6 * l + 4] = v[1]; geom[6 * l + 5] = v[2];
+      geom[12 * l] = xpos[3 * b] + v[0]; geom[12 * l + 1] = xpos[3 * b + 1] + v[1]; geom[12 * l + 2] = xpos[3 * b + 2] + v[2];
+      // world rotation of the geom, stored by columns: z axis, then x and y (capsules / planes only need z; boxes need all three)
+      for (int c = 0; c < 3; ++c) { real col[3] = {cm.geom_mat[l][c], cm.geom_mat[l][3 + c], cm.geom_mat[l][6 + c]}; mat_vec(v, xmat + 9 * b, col);
+        const int o = c == 2 ? 3 : (c == 0 ? 6 : 9); geom[12 * l + o] = v[0]; geom[12 * l + o + 1] = v[1]; geom[12 * l + o + 2] = v[2]; }
     }
   ENDL
   LV(int, ccount); LV(int, coff);
-  LV(real, c0p0); LV(real, c0p1); LV(real, c0p2); LV(real, c0n0); LV(real, c0n1); LV(real, c0n2); LV(real, c0d);
-  LV(real, c1p0); LV(real, c1p1); LV(real, c1p2); LV(real, c1n0); LV(real, c1n1); LV(real, c1n2); LV(real, c1d);
+  LVA(real, cb, 28);   // up to 4 contacts of this lane's pair: [pos3 normal3 dist] each
   LV(real, ch0); LV(real, ch1); LV(real, ch2);
   LANES
     L(ccount) = 0; L(ch0) = L(ch1) = L(ch2) = 0;
-    L(c0p0) = L(c0p1) = L(c0p2) = L(c0n0) = L(c0n1) = L(c0n2) = L(c0d) = 0; L(c1p0) = L(c1p1) = L(c1p2) = L(c1n0) = L(c1n1) = L(c1n2) = L(c1d) = 0;
     if (l < cm.npair) {
       const int g1 = cm.pair_g1[l], g2 = cm.pair_g2[l], kind = cm.pair_kind[l]; const real margin = cm.pair_margin[l];
-      const real *p1 = geom + 6 * g1, *a1 = p1 + 3, *p2 = geom + 6 * g2, *a2 = p2 + 3;
-      real cp[2][3], cn[2][3], cdst[2]; int n = 0;
+      const real *p1 = geom + 12 * g1, *a1 = p1 + 3, *p2 = geom + 12 * g2, *a2 = p2 + 3;
+      real cp[4][3], cn[4][3], cdst[4]; int n = 0;
       if (kind == PAIR_PLANE_SPHERE || kind == PAIR_PLANE_CAPSULE) {
         const real r = cm.geom_size[g2][0], hl = (kind == PAIR_PLANE_CAPSULE) ? cm.geom_size[g2][1] : real(0);
         const int ne = (kind == PAIR_PLANE_CAPSULE) ? 2 : 1;
@@ -609,6 +705,9 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           }
         }
         if (kind == PAIR_HFIELD_CAPSULE) { L(ch0) = a2[0]; L(ch1) = a2[1]; L(ch2) = a2[2]; }
+      } else if (kind >= PAIR_PLANE_BOX) {
+        n = box_pair(kind, margin, p1, p2, cm.geom_size[g1], cm.geom_size[g2], cp, cn, cdst);
+        if (kind == PAIR_CAPSULE_BOX && n) { L(ch0) = a1[0]; L(ch1) = a1[1]; L(ch2) = a1[2]; }
       } else {  // capsule - capsule
         const real s1 = cm.geom_size[g1][1], s2 = cm.geom_size[g2][1], r1 = cm.geom_size[g1][0], r2 = cm.geom_size[g2][0];
         real dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
@@ -634,8 +733,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         }
       }
       L(ccount) = n;
-      if (n > 0) { L(c0p0) = cp[0][0]; L(c0p1) = cp[0][1]; L(c0p2) = cp[0][2]; L(c0n0) = cn[0][0]; L(c0n1) = cn[0][1]; L(c0n2) = cn[0][2]; L(c0d) = cdst[0]; }
-      if (n > 1) { L(c1p0) = cp[1][0]; L(c1p1) = cp[1][1]; L(c1p2) = cp[1][2]; L(c1n0) = cn[1][0]; L(c1n1) = cn[1][1]; L(c1n2) = cn[1][2]; L(c1d) = cdst[1]; }
+      for (int e = 0; e < n; ++e) { LA(cb, 7 * e) = cp[e][0]; LA(cb, 7 * e + 1) = cp[e][1]; LA(cb, 7 * e + 2) = cp[e][2]; LA(cb, 7 * e + 3) = cn[e][0]; LA(cb, 7 * e + 4) = cn[e][1]; LA(cb, 7 * e + 5) = cn[e][2]; LA(cb, 7 * e + 6) = cdst[e]; }
     }
     L(coff) = L(ccount);
   ENDL
@@ -646,11 +744,11 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       const int c = L(coff) + e;
       if (c < MAXCON) {
         real *o = con + 16 * c;
-        o[0] = e ? L(c1p0) : L(c0p0); o[1] = e ? L(c1p1) : L(c0p1); o[2] = e ? L(c1p2) : L(c0p2);
-        real f[9] = {e ? L(c1n0) : L(c0n0), e ? L(c1n1) : L(c0n1), e ? L(c1n2) : L(c0n2), L(ch0), L(ch1), L(ch2), 0, 0, 0};
+        o[0] = LA(cb, 7 * e); o[1] = LA(cb, 7 * e + 1); o[2] = LA(cb, 7 * e + 2);
+        real f[9] = {LA(cb, 7 * e + 3), LA(cb, 7 * e + 4), LA(cb, 7 * e + 5), L(ch0), L(ch1), L(ch2), 0, 0, 0};
         make_frame(f);
         for (int k = 0; k < 9; ++k) o[3 + k] = f[k];
-        o[12] = e ? L(c1d) : L(c0d); o[13] = (real)l;
+        o[12] = LA(cb, 7 * e + 6); o[13] = (real)l;
       }
     }
   ENDL
@@ -666,7 +764,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       mat_vec(v, xmat + 9 * b2, cm.eq_data[e] + 3); p2[0] = xpos[3 * b2] + v[0]; p2[1] = xpos[3 * b2 + 1] + v[1]; p2[2] = xpos[3 * b2 + 2] + v[2];
       jac_col(cm, l, b1, cd, p1, cm3, j1); jac_col(cm, l, b2, cd, p2, cm3, j2);
       for (int k = 0; k < 3; ++k) {
-        Y[(nefc + k) * YSTRIDE + l] = j1[k] - j2[k];
+        Y[(nefc + k) * ys + l] = j1[k] - j2[k];
+        if (xb >= 0 && l < 6) Y[(nefc + k) * ys + 32 + l] = 0;
         if (l == 0) { efc[4 * (nefc + k) + E_POS] = p1[k] - p2[k]; efc[4 * (nefc + k) + E_SRC] = (real)e; efc[4 * (nefc + k) + E_INEQ] = 0; }
       }
     ENDL
@@ -686,8 +785,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       for (int side = 0; side < 2; ++side) {
         const real dist = side ? cm.jnt_range[l][1] - q : q - cm.jnt_range[l][0];
         if (dist < 0 && r < NEFC) {
-          for (int d = 0; d < 32; ++d) Y[r * YSTRIDE + d] = 0;
-          Y[r * YSTRIDE + cm.jnt_dofadr[l]] = side ? real(-1) : real(1);
+          for (int d = 0; d < ys - 1; ++d) Y[r * ys + d] = 0;
+          Y[r * ys + cm.jnt_dofadr[l]] = side ? real(-1) : real(1);
           efc[4 * r + E_POS] = dist; efc[4 * r + E_SRC] = (real)(64 + l); efc[4 * r + E_INEQ] = 1; ++r;
         }
       }
@@ -705,11 +804,26 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       jac_col(cm, l, b1, cd, o, cm3, j1); jac_col(cm, l, b2, cd, o, cm3, j2);
       real dj[3] = {j2[0] - j1[0], j2[1] - j1[1], j2[2] - j1[2]};
       const real jn = dot3(o + 3, dj);
-      if (rows == 1) Y[nefc * YSTRIDE + l] = jn;
+      if (rows == 1) Y[nefc * ys + l] = jn;
       else {
         const real mu = cm.pair_mu[p], jt1 = dot3(o + 6, dj), jt2 = dot3(o + 9, dj);
-        Y[nefc * YSTRIDE + l] = jn + mu * jt1; Y[(nefc + 1) * YSTRIDE + l] = jn - mu * jt1;
-        Y[(nefc + 2) * YSTRIDE + l] = jn + mu * jt2; Y[(nefc + 3) * YSTRIDE + l] = jn - mu * jt2;
+        Y[nefc * ys + l] = jn + mu * jt1; Y[(nefc + 1) * ys + l] = jn - mu * jt1;
+        Y[(nefc + 2) * ys + l] = jn + mu * jt2; Y[(nefc + 3) * ys + l] = jn - mu * jt2;
+      }
+      if (xb >= 0 && l < 6) {   // columns of the extra free body's dofs: translation = world axes, rotation = body axes about its origin
+        real col[3] = {0, 0, 0};
+        if (b1 == xb || b2 == xb) {
+          if (l < 3) col[l] = 1;
+          else { const real axv[3] = {xmat[9 * xb + (l - 3)], xmat[9 * xb + 3 + (l - 3)], xmat[9 * xb + 6 + (l - 3)]}, off[3] = {o[0] - xpos[3 * xb], o[1] - xpos[3 * xb + 1], o[2] - xpos[3 * xb + 2]}; cross3(col, axv, off); }
+          if (b1 == xb) { col[0] = -col[0]; col[1] = -col[1]; col[2] = -col[2]; }
+        }
+        const real xn = dot3(o + 3, col);
+        if (rows == 1) Y[nefc * ys + 32 + l] = xn;
+        else {
+          const real mu = cm.pair_mu[p], xt1 = dot3(o + 6, col), xt2 = dot3(o + 9, col);
+          Y[nefc * ys + 32 + l] = xn + mu * xt1; Y[(nefc + 1) * ys + 32 + l] = xn - mu * xt1;
+          Y[(nefc + 2) * ys + 32 + l] = xn + mu * xt2; Y[(nefc + 3) * ys + 32 + l] = xn - mu * xt2;
+        }
       }
       if (l < rows) { efc[4 * (nefc + l) + E_POS] = o[12]; efc[4 * (nefc + l) + E_SRC] = (real)(128 + p); efc[4 * (nefc + l) + E_INEQ] = 1; }
     ENDL
@@ -722,17 +836,19 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   LV(real, f0); LV(real, f1);    // constraint forces: lane (r & 31) owns rows r and r + 32
   int iters = 0;
   if (nefc == 0) {
-    LANES L(qacc) = L(qacc_smooth); L(qfrc_con) = 0; L(f0) = L(f1) = 0; ENDL
+    LANES L(qacc) = L(qacc_smooth); L(qfrc_con) = 0; L(f0) = L(f1) = 0; L(xqacc) = L(xqacc_smooth); ENDL
   } else {
     // ---- per-row: impedance, R, aref, b, warm-start force (lane = row)
-    LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc_smooth); vecs[64 + l] = L(qacc_ws); } L(f0) = L(f1) = 0; ENDL
-    if (dbg) { LANES for (int r = 0; r < nefc; ++r) dbg[D_J + 32 * r + l] = Y[r * YSTRIDE + l]; ENDL }
+    LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc_smooth); vecs[64 + l] = L(qacc_ws); } L(f0) = L(f1) = 0;
+      if (xb >= 0 && l < 6) { vecs[160 + l] = L(xqvel); vecs[166 + l] = L(xqacc_smooth); vecs[172 + l] = L(xqacc_ws); } ENDL
+    if (dbg) { LANES for (int r = 0; r < nefc; ++r) dbg[D_J + 32 * r + l] = Y[r * ys + l]; ENDL }
     for (int pass = 0; pass * 32 < nefc; ++pass) {
       LANES
         const int r = l + 32 * pass;
         if (r < nefc) {
-          real *yy = Y + r * YSTRIDE; real jv = 0, ja = 0, jw = 0;
+          real *yy = Y + r * ys; real jv = 0, ja = 0, jw = 0;
           for (int d = 0; d < nv; ++d) { const real y = yy[d]; jv += y * vecs[d]; ja += y * vecs[32 + d]; jw += y * vecs[64 + d]; }
+          if (xb >= 0) for (int d = 0; d < 6; ++d) { const real y = yy[32 + d]; jv += y * vecs[160 + d]; ja += y * vecs[166 + d]; jw += y * vecs[172 + d]; }
           const int src = (int)efc[4 * r + E_SRC]; const real pos = efc[4 * r + E_POS]; const bool ineq = efc[4 * r + E_INEQ] != 0;
           const real *solref, *solimp; real dA, margin = 0, rscale = 1;
           if (src < 64) { solref = cm.eq_solref[src]; solimp = cm.eq_solimp[src]; dA = cm.body_invw[cm.eq_b1[src]] + cm.body_invw[cm.eq_b2[src]]; }
@@ -760,6 +876,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           }
           real ad = 0;
           for (int d = 0; d < nv; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
+          if (xb >= 0) for (int d = 0; d < 6; ++d) { const real v = yy[32 + d] * cm.xb_dsqi[d]; yy[32 + d] = v; ad += v * v; }
           // packed row constants for the solver: b, 1/A, A, +-R (sign bit set = inequality row)
           real *rc = efc + 4 * r; const real Ad = ad + Rr;
           rc[0] = ja - aref; rc[1] = real(1) / Ad; rc[2] = Ad; rc[3] = ineq ? -Rr : Rr;
@@ -772,18 +889,19 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       // solve, and the solver carries the residual res = b + A f one entry per lane: a Gauss-Seidel row update is two
       // broadcasts, ~10 scalar ops, one shared load and one FMA per lane, with no warp reduction on the critical path
       // A(., c) for c < 16 lives in rows 32..47 of the Y region, for c >= 16 in the (now dead) kinematics buffers xpos/xquat/xmat/cdof
-#define AM(c) (((c) < 16 ? Y + (32 + (c)) * YSTRIDE : sm + S_XPOS + ((c) - 16) * YSTRIDE))
+#define AM(c) (((c) < 16 ? Y + (32 + (c)) * ys : sm + S_XPOS + ((c) - 16) * ys))
       {
         LVA(real, yreg, 32);
         LANES_NS
 #pragma unroll
-          for (int d = 0; d < 32; ++d) LA(yreg, d) = (l < nefc) ? Y[l * YSTRIDE + d] : real(0);
+          for (int d = 0; d < 32; ++d) LA(yreg, d) = (l < nefc) ? Y[l * ys + d] : real(0);
         ENDL_NS
         for (int c = 0; c < nefc; ++c) {
           LANES_NS
-            const real *yc = Y + c * YSTRIDE; real sacc = 0;
+            const real *yc = Y + c * ys; real sacc = 0;
 #pragma unroll
             for (int d = 0; d < 32; ++d) sacc += LA(yreg, d) * yc[d];
+            if (xb >= 0 && l < nefc) for (int d = 32; d < 38; ++d) sacc += Y[l * ys + d] * yc[d];
             if (c == l) sacc += mabs(efc[4 * c + 3]);
             AM(c)[l] = sacc;
           ENDL_NS
@@ -803,8 +921,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       while (iters < cm.iterations) {
         LANES_NS L(impr) = 0; ENDL_NS
         {
-          const real *Ac = Y + 32 * YSTRIDE; const int n0 = nefc < 16 ? nefc : 16;
-          for (int i = 0; i < n0; ++i, Ac += YSTRIDE) {
+          const real *Ac = Y + 32 * ys; const int n0 = nefc < 16 ? nefc : 16;
+          for (int i = 0; i < n0; ++i, Ac += ys) {
           BCAST(ri, res, i); BCAST(fb, f0, i);
             LANES_NS
               const real *rc = efc + 4 * i;
@@ -820,7 +938,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
             ENDL_NS
           }
           Ac = sm + S_XPOS;
-          for (int i = 16; i < nefc; ++i, Ac += YSTRIDE) {
+          for (int i = 16; i < nefc; ++i, Ac += ys) {
           BCAST(ri, res, i); BCAST(fb, f0, i);
             LANES_NS
               const real *rc = efc + 4 * i;
@@ -840,30 +958,30 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
       }
       LANES_NS L(z) = 0; ENDL_NS
-      for (int r = 0; r < nefc; ++r) { BCAST(fb, f0, r); LANES_NS if (l < nv) L(z) += Y[r * YSTRIDE + l] * L(fb); ENDL_NS }
+      for (int r = 0; r < nefc; ++r) { BCAST(fb, f0, r); LANES_NS if (l < nv) L(z) += Y[r * ys + l] * L(fb); if (xb >= 0 && l < 6) L(xz) += Y[r * ys + 32 + l] * L(fb); ENDL_NS }
     } else {
       // ---- warm start: keep f only if its dual cost 0.5 f'(YY'+R)f + f'b is not positive
       LANES L(z) = 0; ENDL
       for (int r = 0; r < nefc; ++r) {
         if (r < 32) { BCAST(fb, f0, r); } else { BCAST(fb, f1, r - 32); }
-        LANES if (l < nv) L(z) += Y[r * YSTRIDE + l] * L(fb); ENDL
+        LANES if (l < nv) L(z) += Y[r * ys + l] * L(fb); if (xb >= 0 && l < 6) L(xz) += Y[r * ys + 32 + l] * L(fb); ENDL
       }
       LANES
-        real s = real(0.5) * L(z) * L(z);
+        real s = real(0.5) * (L(z) * L(z) + L(xz) * L(xz));
         if (l < nefc) { const real f = L(f0); s += f * (efc[4 * l] + real(0.5) * mabs(efc[4 * l + 3]) * f); }
         if (l + 32 < nefc) { const real f = L(f1); s += f * (efc[4 * (l + 32)] + real(0.5) * mabs(efc[4 * (l + 32) + 3]) * f); }
         L(t0) = s;
       ENDL
       ALLSUM(t0);
-      if (LANE0(t0) > 0) { LANES L(z) = 0; L(f0) = L(f1) = 0; ENDL }
+      if (LANE0(t0) > 0) { LANES L(z) = 0; L(xz) = 0; L(f0) = L(f1) = 0; ENDL }
       // ---- projected Gauss-Seidel, rows strictly in order; z = Y'f is carried one entry per lane
-      LV(real, acc); LV(real, yr);
+      LV(real, acc); LV(real, yr); LV(real, yx);
       while (iters < cm.iterations) {
         LANES L(impr) = 0; ENDL
         const int n0 = nefc < 32 ? nefc : 32;
         for (int r = 0; r < n0; ++r) {
           BCAST(fb, f0, r);
-          LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
+          LANES_NS L(yr) = (l < nv) ? Y[r * ys + l] : real(0); L(yx) = (xb >= 0 && l < 6) ? Y[r * ys + 32 + l] : real(0); L(acc) = L(yr) * L(z) + L(yx) * L(xz); ENDL_NS
           ALLSUM(acc);
           LANES_NS
             const real *rc = efc + 4 * r;
@@ -875,13 +993,13 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
             real change = delta * (real(0.5) * delta * Ad + res);
             if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
             L(impr) -= change;
-            L(z) += L(yr) * delta;
+            L(z) += L(yr) * delta; L(xz) += L(yx) * delta;
             if (l == r) L(f0) = fnew;
           ENDL_NS
         }
         for (int r = 32; r < nefc; ++r) {
           BCAST(fb, f1, r - 32);
-          LANES_NS L(yr) = (l < nv) ? Y[r * YSTRIDE + l] : real(0); L(acc) = L(yr) * L(z); ENDL_NS
+          LANES_NS L(yr) = (l < nv) ? Y[r * ys + l] : real(0); L(yx) = (xb >= 0 && l < 6) ? Y[r * ys + 32 + l] : real(0); L(acc) = L(yr) * L(z) + L(yx) * L(xz); ENDL_NS
           ALLSUM(acc);
           LANES_NS
             const real *rc = efc + 4 * r;
@@ -893,7 +1011,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
             real change = delta * (real(0.5) * delta * Ad + res);
             if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
             L(impr) -= change;
-            L(z) += L(yr) * delta;
+            L(z) += L(yr) * delta; L(xz) += L(yx) * delta;
             if (l == r - 32) L(f1) = fnew;
           ENDL_NS
         }
@@ -905,7 +1023,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     LV(real, w);
     LANES L(w) = (l < nv) ? L(z) * sm[S_DSQI + l] : real(0); ENDL
     sweep_l(cm, sm, w);
-    LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; ENDL
+    LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; if (xb >= 0 && l < 6) L(xqacc) = L(xqacc_smooth) + L(xz) * cm.xb_dsqi[l]; ENDL
     if (dbg) {  // qfrc_constraint = M (qacc - qacc_smooth); only the debug dump wants it (the Euler stage below does not)
       LANES vecs[128 + l] = L(w); ENDL
       LANES
@@ -957,18 +1075,22 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     solve_m(cm, sm, a);
     LANES L(a) = L(qacc) - L(a); ENDL
   } else { LANES L(a) = L(qacc); ENDL }
-  LANES if (l < nv) { L(qvel) += cm.timestep * L(a); vecs[l] = L(qvel); L(qacc_ws) = L(qacc); } ENDL
+  LANES if (l < nv) { L(qvel) += cm.timestep * L(a); vecs[l] = L(qvel); L(qacc_ws) = L(qacc); }
+    if (xb >= 0 && l < 6) { L(xqvel) += cm.timestep * L(xqacc); vecs[160 + l] = L(xqvel); L(xqacc_ws) = L(xqacc); } ENDL
   LANES  // lane = joint: integrate positions with the NEW velocity
     if (l < cm.njnt) {
       const int t = cm.jnt_type[l], qa = cm.jnt_qposadr[l], da = cm.jnt_dofadr[l]; const real h = cm.timestep;
       if (t >= 2) qpos[qa] += h * vecs[da];
-      else if (t == 1) {
-        real wv[3] = {vecs[da], vecs[da + 1], vecs[da + 2]}, q[4] = {qpos[qa], qpos[qa + 1], qpos[qa + 2], qpos[qa + 3]}, qr[4], s, c;
+      else {
+        const real *vv = (t == 1) ? vecs + da : vecs + 160 + 3;     // ball: main-tree velocities; free: the extra body's angular velocity
+        const int qq = (t == 1) ? qa : qa + 3;
+        if (t == 0) { qpos[qa] += h * vecs[160]; qpos[qa + 1] += h * vecs[161]; qpos[qa + 2] += h * vecs[162]; }
+        real wv[3] = {vv[0], vv[1], vv[2]}, q[4] = {qpos[qq], qpos[qq + 1], qpos[qq + 2], qpos[qq + 3]}, qr[4], s, c;
         const real ang = h * normalize3(wv);
         msincos(real(0.5) * ang, &s, &c); qr[0] = c; qr[1] = wv[0] * s; qr[2] = wv[1] * s; qr[3] = wv[2] * s;
         if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
         normalize4(q); mul_quat(q, q, qr);
-        qpos[qa] = q[0]; qpos[qa + 1] = q[1]; qpos[qa + 2] = q[2]; qpos[qa + 3] = q[3];
+        qpos[qq] = q[0]; qpos[qq + 1] = q[1]; qpos[qq + 2] = q[2]; qpos[qq + 3] = q[3];
       }
     }
     if (l == 0) cst[CS_TIME] += cm.timestep;
@@ -983,7 +1105,7 @@ template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
 template <typename real>
-CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), int nticks, bool forward_only) {
+CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), int nticks, bool forward_only) {
   DECL_LANE
   real *cst = E.cst, *vecs = sm + S_VEC, *obs = E.obs; const real *pd = E.pd; int *ism = E.dfilt;
   LV(real, ctrl); LV(real, tq); LV(real, scale_part);
@@ -1076,7 +1198,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
     const int nsub = forward_only ? 1 : cm.nsub;
-    for (int s = 0; s < nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, !forward_only);
+    for (int s = 0; s < nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, !forward_only);
   }
 }
 

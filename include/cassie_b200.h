@@ -112,6 +112,8 @@ void *cassie_batch_device_ptr(cassie_batch_t *b, const char *field);
 void cassie_batch_set_stream(cassie_batch_t *b, void *cuda_stream);
 void *cassie_batch_get_stream(cassie_batch_t *b);
 int cassie_batch_precision(const cassie_batch_t *b);
+/* row width (in elements) of a device array named as in cassie_batch_device_ptr: qpos 36 (44 with the extra free body of cassie_tray_box.xml), qvel 32 (40) */
+int cassie_batch_row_width(const cassie_batch_t *b, const char *field);
 /* per-env solver statistics of the last sub-step: int [n][8] = nefc, ncon, nlimit, PGS iterations, dropped contacts, 0,0,0 */
 void cassie_batch_get_counters(cassie_batch_t *b, int *out);
 /* launches issued since init (bench.py's gpu_launches) */

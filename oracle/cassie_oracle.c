@@ -498,6 +498,85 @@ static int col_hfield_capsule(const OModel *m, const OData *d, OContact *c, int 
   for (int i = 0; i < n1 + n2; i++) copyv(c[i].frame + 3, ax, 3);
   return n1 + n2;
 }
+/* ---- box primitives (cassie_tray_box.xml).  These are analytic definitions of our own, NOT restatements of MuJoCo's mjc_PlaneBox /
+ * mjc_SphereBox / mjc_CapsuleBox / mjc_BoxBox (the latter two are long special-case routines that cannot be recalled line by line);
+ * DESIGN.md states the rules.  Normals point from geom1 to geom2 like every MuJoCo contact. */
+static void box_corner(const double *bpos, const double *bmat, const double *s, int i, double *out) {
+  double l[3] = {(i & 1) ? s[0] : -s[0], (i & 2) ? s[1] : -s[1], (i & 4) ? s[2] : -s[2]}, w[3];
+  mulMatVec3(w, bmat, l); for (int k = 0; k < 3; k++) out[k] = bpos[k] + w[k];
+}
+/* plane (g1) vs box (g2): every corner below the plane is a contact, at most 4, in corner order */
+static int col_plane_box(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
+  const double *pm = d->geom_xmat[g1], *pp = d->geom_xpos[g1]; double n[3] = {pm[2], pm[5], pm[8]}; int cnt = 0;
+  for (int i = 0; i < 8 && cnt < 4; i++) {
+    double v[3], t[3]; box_corner(d->geom_xpos[g2], d->geom_xmat[g2], m->geom_size[g2], i, v);
+    for (int k = 0; k < 3; k++) t[k] = v[k] - pp[k];
+    double dist = dot3(t, n);
+    if (dist >= margin) continue;
+    c[cnt].dist = dist; copyv(c[cnt].frame, n, 3); zero(c[cnt].frame + 3, 6);
+    for (int k = 0; k < 3; k++) c[cnt].pos[k] = v[k] - n[k] * dist * 0.5;
+    cnt++;
+  }
+  return cnt;
+}
+/* sphere (centre sc, radius r) as geom1 vs box as geom2 */
+static int raw_sphere_box(OContact *c, double margin, const double *sc, double r, const double *bpos, const double *bmat, const double *s) {
+  double t[3] = {sc[0] - bpos[0], sc[1] - bpos[1], sc[2] - bpos[2]}, cl[3], q[3], nl[3], dist; int inside = 1;
+  mulMatTVec3(cl, bmat, t);
+  for (int k = 0; k < 3; k++) { q[k] = clampd(cl[k], -s[k], s[k]); if (q[k] != cl[k]) inside = 0; }
+  if (inside) { /* centre inside the box: leave through the nearest face */
+    int ax = 0; double best = 1e30; for (int k = 0; k < 3; k++) { double pen = s[k] - fabs(cl[k]); if (pen < best) { best = pen; ax = k; } }
+    nl[0] = nl[1] = nl[2] = 0; nl[ax] = cl[ax] >= 0 ? 1 : -1; q[ax] = nl[ax] * s[ax]; dist = -best - r;
+  } else {
+    double dv[3] = {cl[0] - q[0], cl[1] - q[1], cl[2] - q[2]}, len = sqrt(dot3(dv, dv));
+    if (len - r >= margin) return 0;
+    for (int k = 0; k < 3; k++) nl[k] = dv[k] / len;
+    dist = len - r;
+  }
+  if (dist >= margin) return 0;
+  double nw[3], qw[3]; mulMatVec3(nw, bmat, nl); mulMatVec3(qw, bmat, q);     /* nw: box -> sphere */
+  c->dist = dist; for (int k = 0; k < 3; k++) { c->frame[k] = -nw[k]; c->pos[k] = bpos[k] + qw[k] + nw[k] * dist * 0.5; }
+  zero(c->frame + 3, 6);
+  return 1;
+}
+/* capsule (g1) vs box (g2): the point of the capsule axis closest to the box (alternating projections), then sphere vs box there */
+static int col_capsule_box(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
+  const double *m1 = d->geom_xmat[g1], *p1 = d->geom_xpos[g1], *bpos = d->geom_xpos[g2], *bmat = d->geom_xmat[g2], *s = m->geom_size[g2];
+  double ax[3] = {m1[2], m1[5], m1[8]}, hl = m->geom_size[g1][1], t = 0, p[3], pl[3], q[3], qw[3], tmp[3];
+  for (int k = 0; k < 3; k++) tmp[k] = bpos[k] - p1[k];
+  t = clampd(dot3(tmp, ax), -hl, hl);
+  for (int it = 0; it < 4; it++) {
+    for (int k = 0; k < 3; k++) { p[k] = p1[k] + ax[k] * t; tmp[k] = p[k] - bpos[k]; }
+    mulMatTVec3(pl, bmat, tmp); for (int k = 0; k < 3; k++) q[k] = clampd(pl[k], -s[k], s[k]);
+    mulMatVec3(qw, bmat, q); for (int k = 0; k < 3; k++) tmp[k] = bpos[k] + qw[k] - p1[k];
+    t = clampd(dot3(tmp, ax), -hl, hl);
+  }
+  for (int k = 0; k < 3; k++) p[k] = p1[k] + ax[k] * t;
+  int n = raw_sphere_box(c, margin, p, m->geom_size[g1][0], bpos, bmat, s);
+  if (n) copyv(c->frame + 3, ax, 3);
+  return n;
+}
+/* box (g1) vs box (g2): corners of g2 inside g1, then corners of g1 inside g2; at most 4 contacts */
+static int col_box_box(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
+  int cnt = 0;
+  for (int pass = 0; pass < 2 && cnt < 4; pass++) {
+    int ga = pass ? g2 : g1, gb = pass ? g1 : g2;    /* corners of gb tested against the volume of ga */
+    const double *apos = d->geom_xpos[ga], *amat = d->geom_xmat[ga], *as = m->geom_size[ga];
+    for (int i = 0; i < 8 && cnt < 4; i++) {
+      double v[3], t[3], vl[3]; box_corner(d->geom_xpos[gb], d->geom_xmat[gb], m->geom_size[gb], i, v);
+      for (int k = 0; k < 3; k++) t[k] = v[k] - apos[k];
+      mulMatTVec3(vl, amat, t);
+      int ax = -1; double best = 1e30, pen;
+      for (int k = 0; k < 3; k++) { pen = as[k] - fabs(vl[k]); if (pen <= -margin) { ax = -1; best = -1; break; } if (pen < best) { best = pen; ax = k; } }
+      if (ax < 0) continue;
+      double nl[3] = {0, 0, 0}, nw[3]; nl[ax] = vl[ax] >= 0 ? 1 : -1; mulMatVec3(nw, amat, nl);   /* outward normal of ga's face */
+      double sgn = pass ? -1.0 : 1.0;   /* pass 0: ga = g1, outward normal already points g1 -> g2; pass 1: ga = g2, flip */
+      c[cnt].dist = -best; for (int k = 0; k < 3; k++) { c[cnt].frame[k] = sgn * nw[k]; c[cnt].pos[k] = v[k] + nw[k] * best * 0.5; }
+      zero(c[cnt].frame + 3, 6); cnt++;
+    }
+  }
+  return cnt;
+}
 static int col_capsule_capsule(const OModel *m, const OData *d, OContact *c, int g1, int g2, double margin) {
   const double *m1 = d->geom_xmat[g1], *m2 = d->geom_xmat[g2], *p1 = d->geom_xpos[g1], *p2 = d->geom_xpos[g2];
   double a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]}, dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
@@ -536,10 +615,14 @@ static void collide_geoms(const OModel *m, OData *d, int g1, int g2) {
     for (int k = 0; k < 3; k++) dif[k] = d->geom_xpos[g2][k] - d->geom_xpos[g1][k];
     if (dot3(dif, n) > m->geom_rbound[g2] + margin) return;
   }
-  OContact con[4]; int num = 0;
+  OContact con[8]; int num = 0;
   if (t1 == G_PLANE && t2 == G_SPHERE) num = raw_plane_sphere(con, margin, d->geom_xpos[g1], d->geom_xmat[g1], d->geom_xpos[g2], m->geom_size[g2][0]);
   else if (t1 == G_PLANE && t2 == G_CAPSULE) num = col_plane_capsule(m, d, con, g1, g2, margin);
   else if (t1 == G_CAPSULE && t2 == G_CAPSULE) num = col_capsule_capsule(m, d, con, g1, g2, margin);
+  else if (t1 == G_PLANE && t2 == G_BOX) num = col_plane_box(m, d, con, g1, g2, margin);
+  else if (t1 == G_SPHERE && t2 == G_BOX) num = raw_sphere_box(con, margin, d->geom_xpos[g1], m->geom_size[g1][0], d->geom_xpos[g2], d->geom_xmat[g2], m->geom_size[g2]);
+  else if (t1 == G_CAPSULE && t2 == G_BOX) num = col_capsule_box(m, d, con, g1, g2, margin);
+  else if (t1 == G_BOX && t2 == G_BOX) num = col_box_box(m, d, con, g1, g2, margin);
   else if (t1 == G_HFIELD && t2 == G_SPHERE && m->hfield_data) num = raw_hfield_sphere(m, con, margin, d->geom_xpos[g1], d->geom_xpos[g2], m->geom_size[g2][0]);
   else if (t1 == G_HFIELD && t2 == G_CAPSULE && m->hfield_data) num = col_hfield_capsule(m, d, con, g1, g2, margin);
   else { d->unsupported_pairs++; return; }

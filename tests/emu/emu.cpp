@@ -13,23 +13,24 @@ using namespace cassie;
 
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX]; int counters[8];
+  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX]; int counters[8];
   EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
     if (!build_dev_model(hm, dm, err)) return false;
-    sm.assign(S_REALS, 0); ism.assign(DFILT_W, 0);
+    sm.assign(scratch_reals(dm.ystride), 0); ism.assign(DFILT_W, 0);
     if (hm.nhfield) hfield.assign((size_t)hm.hfield_nrow[0] * hm.hfield_ncol[0], 0.0f);
-    std::vector<real> qpos(QPOS_W);
-    init_env_rows(hm, qpos.data(), qvel, qacc_ws, cst, ism.data(), xfrc);
-    for (int i = 0; i < QPOS_W; i++) sm[S_QPOS + i] = qpos[i];
+    std::vector<real> qpos(QPOS_W_XB), qv(QVEL_W_XB), qa(QVEL_W_XB);
+    init_env_rows(hm, qpos.data(), qv.data(), qa.data(), cst, ism.data(), xfrc);
+    for (int i = 0; i < 32; i++) { qvel[i] = qv[i]; qacc_ws[i] = qa[i]; xqvel[i] = 0; xqacc_ws[i] = 0; }
+    for (int i = 0; i < QPOS_W_XB; i++) sm[S_QPOS + i] = qpos[i];
     std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters);
     forward();
     return true;
   }
-  void forward() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, 1, true); }
-  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, nticks, false); }
+  void forward() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, 1, true); }
+  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, false); }
 };
 
 struct Handle { int fp32; Emu<float> f; Emu<double> d; };
@@ -53,7 +54,7 @@ void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward()
 int emu_get(void *p, const char *name, double *out, int n) {
   Handle *h = (Handle *)p; std::string k(name);
 #define GET(T, E) { const T *src = nullptr; int cnt = 0; \
-  if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
+  if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W_XB; } else if (k == "xqvel") { src = E.xqvel; cnt = 6; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
   else if (k == "cst") { src = E.cst; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
   else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } \
   if (src) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) out[i] = (double)src[i]; return cnt; } \
@@ -65,7 +66,7 @@ int emu_get(void *p, const char *name, double *out, int n) {
 int emu_set(void *p, const char *name, const double *in, int n) {
   Handle *h = (Handle *)p; std::string k(name);
 #define SET(T, E) { T *dst = nullptr; int cnt = 0; \
-  if (k == "qpos") { dst = E.sm.data() + S_QPOS; cnt = QPOS_W; } else if (k == "qvel") { dst = E.qvel; cnt = 32; } else if (k == "qacc_ws") { dst = E.qacc_ws; cnt = 32; } \
+  if (k == "qpos") { dst = E.sm.data() + S_QPOS; cnt = QPOS_W_XB; } else if (k == "xqvel") { dst = E.xqvel; cnt = 6; } else if (k == "qvel") { dst = E.qvel; cnt = 32; } else if (k == "qacc_ws") { dst = E.qacc_ws; cnt = 32; } \
   else if (k == "cst") { dst = E.cst; cnt = CST_W; } else if (k == "xfrc") { dst = E.xfrc; cnt = XFRC_W; } \
   if (dst) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) dst[i] = (T)in[i]; return cnt; } }
   if (h->fp32) SET(float, h->f) else SET(double, h->d)
