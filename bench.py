@@ -177,6 +177,16 @@ def gpu_arm(args, rank, local_rank, world):
     barrier()
     launches = b.launch_count() - launches0
     ms_kernel = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    # ---- same kernel, 50 control ticks per launch (cassie_batch_step(b, 50): one 40 Hz policy step of the reference's demos)
+    for _ in range(2):
+        b.step(50)
+    barrier()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(4):
+        b.step(50)
+    m1.record(); barrier()
+    ms_multi = m0.elapsed_time(m1)
     # ---- end to end through the AoS C-ABI: pd_in_t[n] host -> step -> state_out_t[n] host, every step
     pd = (P.pd_in_t * n)()
     for e in range(n):
@@ -216,8 +226,52 @@ def gpu_arm(args, rank, local_rank, world):
         ms_i = e0.elapsed_time(e1) / reps
         bytes_i = nb * 4 * (35 + 32 + 35)
         integ = {'kernel': 'cassie_integrate_kernel<float>', 'bound': 'hbm', 'achieved': bytes_i / (ms_i * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                 'frac': bytes_i / (ms_i * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'envs': nb, 'bytes_per_env': 4 * (35 + 32 + 35), 'ms': ms_i}
+                 'frac': bytes_i / (ms_i * 1e-3) / 1e9 / hbm_peak, 'traffic': 3.857e8,   # profiles/r1_integrate_kernel_ncu_summary.md
+                 'envs': nb, 'bytes_per_env': 4 * (35 + 32 + 35), 'ms': ms_i}
         bi.close()
+    # ---- the other BASELINE configs (parity-test cases, not the bench line): per-GPU slices, kernel-only, short runs
+    others = None
+    if rank == 0 and not args.no_extra:
+        others = {}
+
+        def timed(bb, nsteps, pre=None):
+            bb.set_stream(torch.cuda.current_stream().cuda_stream)
+            bb.step(300); bb.sync()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(nsteps):
+                if pre:
+                    pre(i)
+                bb.step(1)
+            a1.record(); torch.cuda.synchronize()
+            c = bb.counters()
+            return {'env_steps_per_s': bb.n * nsteps / (a0.elapsed_time(a1) * 1e-3), 'ms_per_tick': a0.elapsed_time(a1) / nsteps,
+                    'mean_rows': float(c[:, 0].mean()), 'mean_pgs_sweeps': float(c[:, 3].mean()), 'dropped_contacts': int(c[:, 4].sum())}
+        try:
+            n3 = 16384
+            b3 = P.CassieBatch(n3, device=local_rank, precision=P.FP32)
+            b3.set_pd(P.pd_rows(n3, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
+            rng = np.random.default_rng(1234)
+            push = np.zeros((n3, 6)); push[:, :2] = rng.uniform(-100, 100, (n3, 2))
+
+            def pushes(i):          # every 400 ticks: U(-100,100) N xy push on the pelvis held for 100 ticks, scaled to the short run
+                if i % 40 == 0:
+                    b3.apply_force(push, 'cassie-pelvis')
+                elif i % 40 == 10:
+                    b3.clear_forces()
+            others['config3_16384_envs_pelvis_pushes'] = timed(b3, 80, pushes); b3.close()
+            n4 = 8192
+            b4 = P.CassieBatch(n4, modelfile=P.model_path('cassie_hfield'), device=local_rank, precision=P.FP32)
+            T = (np.random.default_rng(7).uniform(0, 1, (64, 200, 200)) * 0.25).astype(np.float32); T[:, 95:105, 95:105] = 0
+            b4.set_hfield_data(T); b4.set_pd(P.pd_rows(n4, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
+            others['config4_8192_envs_per_gpu_hfield_64_terrains_amp0.05m'] = timed(b4, 80); b4.close()
+            b5 = P.CassieBatch(n4, modelfile=P.model_path('cassie_tray_box'), device=local_rank, precision=P.FP32)
+            ph = np.random.default_rng(99).uniform(0, 2 * np.pi, (n4, 1)); amp = np.array([0.05, 0.05, 0.3, 0.4, 0.3] * 2) * 0.2
+            rows5 = P.pd_rows(n4, pTarget=np.array(PD_TARGET) + amp * np.sin(ph + np.array([0] * 5 + [np.pi] * 5)), pGain=PD_PGAIN, dGain=PD_DGAIN)
+            b5.set_pd(rows5)
+            others['config5_8192_envs_per_gpu_tray_box'] = timed(b5, 80); b5.close()
+        except Exception as ex:
+            others['error'] = repr(ex)
     # ---- reduce over ranks
     t = torch.tensor([ms_kernel, t_e2e], dtype=torch.float64, device='cuda')
     if dist:
@@ -244,10 +298,12 @@ def gpu_arm(args, rank, local_rank, world):
                         'api': 'cassie_sim_step_pd_batch(envs, pd_in_t[n] host, state_out_t[n] host), %d steps, host AoS pack/unpack included%s' % (
                             e2e_steps, '; + one NCCL all-gather of the observation block per step' if dist else '')},
                 'gpu_launches': launches,
-                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None,
+                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': 8.62e6,   # dram__bytes_read.sum + write.sum per launch, profiles/r1_step_kernel_final_ncu_summary.md
+                            
                              'peak_source': peak_src, 'bytes_per_env_step': STATE_BYTES_FP32,
                              'note': 'latency/issue-bound by design (SURVEY 8d): algorithmic HBM traffic is only the persistent state rows in+out'},
-                'roofline_integrate': integ, 'cpu_baseline': cpu}
+                'multitick': {'ticks_per_launch': 50, 'env_steps_per_s_this_rank': n * 200 / (ms_multi * 1e-3)},
+                'roofline_integrate': integ, 'cpu_baseline': cpu, 'other_configs': others}
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -260,6 +316,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--envs', type=int, default=4096)
+    ap.add_argument('--no-extra', dest='no_extra', action='store_true', help='skip the short runs of BASELINE configs 3-5')
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     if args.warmup < 3:
