@@ -80,7 +80,12 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     for (int k = 0; k < 2; k++) d.jnt_solref[j][k] = (real)m.jnt_solref[2 * j + k];
     for (int k = 0; k < 5; k++) d.jnt_solimp[j][k] = (real)m.jnt_solimp[5 * j + k];
     if (m.jnt_margin[j] != 0) { err = "joint margins are not supported"; return false; }
+    if (std::fabs(m.jnt_pos[3 * j]) + std::fabs(m.jnt_pos[3 * j + 1]) + std::fabs(m.jnt_pos[3 * j + 2]) > 0) d.any_jnt_pos = 1;
   }
+  // joint arrangement the kinematics stage relies on: per body, slides first, then at most one hinge or ball joint
+  for (int b = 1; b < m.nbody; b++) { int rot = 0; for (int jj = 0; jj < m.body_jntnum[b]; jj++) { int t = m.jnt_type[m.body_jntadr[b] + jj];
+      if (t == JNT_SLIDE && rot) { err = "a slide joint after a rotational joint in the same body is not supported"; return false; } if (t == JNT_HINGE || t == JNT_BALL) rot++; }
+    if (rot > 1) { err = "more than one rotational joint per body is not supported"; return false; } }
   // dofs
   d.ntri = 0;
   for (int i = 0; i < nvm; i++) {

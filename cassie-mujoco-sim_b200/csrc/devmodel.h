@@ -34,7 +34,7 @@ template <typename real>
 struct DevModel {
   // ---- sizes / options
   int qpos_w, qvel_w, ystride, xb;   // HBM row widths, constraint-matrix row stride, id of the extra free body (or -1)
-  int xb_qadr, xb_dadr, xb_jnt, padx;
+  int xb_qadr, xb_dadr, xb_jnt, any_jnt_pos;   // any_jnt_pos: some joint anchor is not at its body origin
   int nq, nv, nbody, njnt, ngeom, npair, neq, nu, maxdepth, nM, ntri, nsub, iterations, imu_body, has_damping, force_zpath;
   real timestep, tolerance, pgs_scale, root_mass_inv, euler_eps, padr[3];
   real gravity[3], magnetic[3], imu_pos[3], imu_quat[4], imu_mat[9], gyro_cutoff, accel_cutoff;

@@ -390,47 +390,47 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   LV(real, com0); LV(real, com1); LV(real, com2);
 
   // ================= kinematics (mj_kinematics) =================
-  LANES  // lane = joint: local joint rotation
-    if (l < cm.njnt) {
-      const int t = cm.jnt_type[l], qa = cm.jnt_qposadr[l];
-      if (t == 3) {  // hinge
-        real s, c; msincos(real(0.5) * (qpos[qa] - cm.jnt_qpos0[l]), &s, &c);
-        qloc[4 * l] = c; qloc[4 * l + 1] = cm.jnt_axis[l][0] * s; qloc[4 * l + 2] = cm.jnt_axis[l][1] * s; qloc[4 * l + 3] = cm.jnt_axis[l][2] * s;
-      } else if (t == 1) {  // ball: normalised copy
-        real q[4] = {qpos[qa], qpos[qa + 1], qpos[qa + 2], qpos[qa + 3]}; normalize4(q);
-        qloc[4 * l] = q[0]; qloc[4 * l + 1] = q[1]; qloc[4 * l + 2] = q[2]; qloc[4 * l + 3] = q[3];
+  // (A) every body in parallel: its transform relative to the parent frame from its own joints (slides first, then at most one hinge /
+  //     ball -- checked when the model block is built); (B) tree levels: compose with the parent; anchors / axes follow in the cdof phase
+  real *prel = xanchor, *qrel = qloc, *sax = xaxis;   // [32][3] position, [32][4] rotation, [32][3] slide axes in the parent frame
+  LANES
+    if (l >= 1 && l < nb && l != xb) {
+      real p[3] = {cm.body_pos[l][0], cm.body_pos[l][1], cm.body_pos[l][2]}, q[4] = {cm.body_quat[l][0], cm.body_quat[l][1], cm.body_quat[l][2], cm.body_quat[l][3]};
+      for (int jj = 0; jj < cm.body_jntnum[l]; ++jj) {
+        const int j = cm.body_jntadr[l] + jj, t = cm.jnt_type[j], qa = cm.jnt_qposadr[j];
+        if (t == 2) {          // slide along its axis in the (not yet rotated) body frame
+          real R[9], ax[3]; quat2mat(R, q); mat_vec(ax, R, cm.jnt_axis[j]);
+          sax[3 * j] = ax[0]; sax[3 * j + 1] = ax[1]; sax[3 * j + 2] = ax[2];
+          const real d = qpos[qa] - cm.jnt_qpos0[j];
+          p[0] += ax[0] * d; p[1] += ax[1] * d; p[2] += ax[2] * d;
+        } else {               // hinge / ball about the joint anchor
+          real ql[4];
+          if (t == 3) { real sn, cs; msincos(real(0.5) * (qpos[qa] - cm.jnt_qpos0[j]), &sn, &cs); ql[0] = cs; ql[1] = cm.jnt_axis[j][0] * sn; ql[2] = cm.jnt_axis[j][1] * sn; ql[3] = cm.jnt_axis[j][2] * sn; }
+          else { ql[0] = qpos[qa]; ql[1] = qpos[qa + 1]; ql[2] = qpos[qa + 2]; ql[3] = qpos[qa + 3]; normalize4(ql); }
+          if (cm.any_jnt_pos) {  // off-centre joint: the anchor stays fixed while the body turns about it
+            real R[9], v0[3], v1[3]; quat2mat(R, q); mat_vec(v0, R, cm.jnt_pos[j]); mul_quat(q, q, ql); quat2mat(R, q); mat_vec(v1, R, cm.jnt_pos[j]);
+            p[0] += v0[0] - v1[0]; p[1] += v0[1] - v1[1]; p[2] += v0[2] - v1[2];
+          } else mul_quat(q, q, ql);
+        }
       }
+      prel[3 * l] = p[0]; prel[3 * l + 1] = p[1]; prel[3 * l + 2] = p[2];
+      qrel[4 * l] = q[0]; qrel[4 * l + 1] = q[1]; qrel[4 * l + 2] = q[2]; qrel[4 * l + 3] = q[3];
     }
     if (l == 0) { xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0; for (int k = 0; k < 9; ++k) xmat[k] = (k % 4 == 0) ? real(1) : real(0); }
   ENDL
   for (int lev = 1; lev <= cm.maxdepth; ++lev) {
     LANES  // lane = body at this tree level
-      if (l < nb && cm.body_depth[l] == lev && l == xb) {   // free joint: pose straight from qpos (position, quaternion)
-        const int qa = cm.xb_qadr; real quat[4] = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
-        normalize4(quat);
-        xpos[3 * l] = qpos[qa]; xpos[3 * l + 1] = qpos[qa + 1]; xpos[3 * l + 2] = qpos[qa + 2];
-        xquat[4 * l] = quat[0]; xquat[4 * l + 1] = quat[1]; xquat[4 * l + 2] = quat[2]; xquat[4 * l + 3] = quat[3];
-        quat2mat(xmat + 9 * l, quat);
-      } else if (l < nb && cm.body_depth[l] == lev) {
-        const int p = cm.body_parent[l];
-        real pos[3], quat[4], v[3], R[9];
-        mat_vec(v, xmat + 9 * p, cm.body_pos[l]);
-        pos[0] = xpos[3 * p] + v[0]; pos[1] = xpos[3 * p + 1] + v[1]; pos[2] = xpos[3 * p + 2] + v[2];
-        mul_quat(quat, xquat + 4 * p, cm.body_quat[l]);
-        for (int jj = 0; jj < cm.body_jntnum[l]; ++jj) {
-          const int j = cm.body_jntadr[l] + jj;
-          quat2mat(R, quat);
-          mat_vec(xaxis + 3 * j, R, cm.jnt_axis[j]);
-          mat_vec(v, R, cm.jnt_pos[j]);
-          xanchor[3 * j] = pos[0] + v[0]; xanchor[3 * j + 1] = pos[1] + v[1]; xanchor[3 * j + 2] = pos[2] + v[2];
-          if (cm.jnt_type[j] == 2) {
-            const real s = qpos[cm.jnt_qposadr[j]] - cm.jnt_qpos0[j];
-            pos[0] += xaxis[3 * j] * s; pos[1] += xaxis[3 * j + 1] * s; pos[2] += xaxis[3 * j + 2] * s;
-          } else {
-            mul_quat(quat, quat, qloc + 4 * j);
-            quat2mat(R, quat); mat_vec(v, R, cm.jnt_pos[j]);
-            pos[0] = xanchor[3 * j] - v[0]; pos[1] = xanchor[3 * j + 1] - v[1]; pos[2] = xanchor[3 * j + 2] - v[2];
-          }
+      if (l < nb && cm.body_depth[l] == lev) {
+        real pos[3], quat[4];
+        if (l == xb) {   // free joint: pose straight from qpos (position, quaternion)
+          const int qa = cm.xb_qadr;
+          pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
+          quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
+        } else {
+          const int p = cm.body_parent[l]; real v[3];
+          mat_vec(v, xmat + 9 * p, prel + 3 * l);
+          pos[0] = xpos[3 * p] + v[0]; pos[1] = xpos[3 * p + 1] + v[1]; pos[2] = xpos[3 * p + 2] + v[2];
+          mul_quat(quat, xquat + 4 * p, qrel + 4 * l);
         }
         normalize4(quat);
         xpos[3 * l] = pos[0]; xpos[3 * l + 1] = pos[1]; xpos[3 * l + 2] = pos[2];
@@ -476,10 +476,15 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     L(cd0) = L(cd1) = L(cd2) = L(cd3) = L(cd4) = L(cd5) = 0;
     if (l < nv) {
       const int j = cm.dof_jnt[l], t = cm.jnt_type[j], b = cm.dof_body[l];
-      real off[3] = {L(com0) - xanchor[3 * j], L(com1) - xanchor[3 * j + 1], L(com2) - xanchor[3 * j + 2]}, ax[3], c[3];
-      if (t == 2) { L(cd3) = xaxis[3 * j]; L(cd4) = xaxis[3 * j + 1]; L(cd5) = xaxis[3 * j + 2]; }
-      else {
-        if (t == 3) { ax[0] = xaxis[3 * j]; ax[1] = xaxis[3 * j + 1]; ax[2] = xaxis[3 * j + 2]; }
+      real ax[3], c[3];
+      if (t == 2) {  // slide: axis fixed in the parent frame
+        mat_vec(ax, xmat + 9 * cm.body_parent[b], sax + 3 * j);
+        L(cd3) = ax[0]; L(cd4) = ax[1]; L(cd5) = ax[2];
+      } else {
+        real an[3] = {xpos[3 * b], xpos[3 * b + 1], xpos[3 * b + 2]};
+        if (cm.any_jnt_pos) { real v[3]; mat_vec(v, xmat + 9 * b, cm.jnt_pos[j]); an[0] += v[0]; an[1] += v[1]; an[2] += v[2]; }
+        real off[3] = {L(com0) - an[0], L(com1) - an[1], L(com2) - an[2]};
+        if (t == 3) mat_vec(ax, xmat + 9 * b, cm.jnt_axis[j]);
         else { const int k = l - cm.jnt_dofadr[j]; ax[0] = xmat[9 * b + k]; ax[1] = xmat[9 * b + 3 + k]; ax[2] = xmat[9 * b + 6 + k]; }
         cross3(c, ax, off);
         L(cd0) = ax[0]; L(cd1) = ax[1]; L(cd2) = ax[2]; L(cd3) = c[0]; L(cd4) = c[1]; L(cd5) = c[2];
