@@ -14,7 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcassie_b200.so')
 MODEL_DIR = os.path.join(_HERE, 'models')
 FP32, FP64 = 0, 1
-PD_WIDTH, OBS_WIDTH = 52, 64
+PD_WIDTH, OBS_WIDTH, AUX_WIDTH = 52, 64, 64
+# slices of a derived-quantity row (CASSIE_AUX_* in include/cassie_b200.h)
+AUX = dict(foot_force=slice(0, 12), toe_force=slice(12, 18), heel_force=slice(18, 24), foot_pos=slice(24, 30), foot_vel=slice(30, 42),
+           cm_pos=slice(42, 45), cm_vel=slice(45, 48), angmom=slice(48, 51), obstacle=51, self_collision=52, group_mask=53, ncon=54)
 # observation row layout (cassie_batch_get_obs)
 OBS = dict(motor_pos=slice(0, 10), motor_vel=slice(10, 20), motor_torque=slice(20, 30), joint_pos=slice(30, 36), joint_vel=slice(36, 42),
            quat=slice(42, 46), gyro=slice(46, 49), accel=slice(49, 52), mag=slice(52, 55), time=55)
@@ -148,6 +151,26 @@ def lib():
     L.cassie_sim_clear_forces.argtypes = [vp]
     L.cassie_sim_full_reset.argtypes = [vp]
     L.cassie_sim_radio.argtypes = [vp, cd]
+    for n in ('cassie_batch_enable_aux',):
+        getattr(L, n).argtypes = [vp, ci]
+        getattr(L, n).restype = ci
+    L.cassie_batch_get_aux.argtypes = [vp, cd]
+    L.cassie_batch_get_aux.restype = ci
+    L.cassie_batch_query.argtypes = [vp]
+    L.cassie_batch_query.restype = ci
+    L.cassie_batch_row_width.argtypes = [vp, C.c_char_p]
+    L.cassie_batch_row_width.restype = ci
+    for n in ('cassie_sim_foot_forces', 'cassie_sim_foot_positions', 'cassie_sim_foot_velocities', 'cassie_sim_cm_position', 'cassie_sim_cm_velocity',
+              'cassie_sim_angular_momentum'):
+        getattr(L, n).argtypes = [vp, cd]
+        getattr(L, n).restype = None
+    L.cassie_sim_heeltoe_forces.argtypes = [vp, cd, cd]
+    L.cassie_sim_heeltoe_forces.restype = None
+    for n in ('cassie_sim_check_obstacle_collision', 'cassie_sim_check_self_collision'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = C.c_bool
+    L.cassie_sim_geom_collision.argtypes = [vp, ci]
+    L.cassie_sim_geom_collision.restype = C.c_bool
     _lib = L
     return L
 
@@ -246,6 +269,23 @@ class CassieBatch:
 
     def obs(self):
         return self._get(self.L.cassie_batch_get_obs, OBS_WIDTH)
+
+    # ---- derived quantities (reference: the read-only queries of example/cassiemujoco.py:214-306, 815-819), one row per environment
+    def enable_aux(self, on=True):
+        if self.L.cassie_batch_enable_aux(self.h, 1 if on else 0) != 0:
+            raise RuntimeError(_last_error())
+
+    def aux(self):
+        """[n, AUX_WIDTH] rows; slices are named in AUX (e.g. rows[:, AUX['foot_force']])."""
+        out = np.zeros((self.n, AUX_WIDTH))
+        if self.L.cassie_batch_get_aux(self.h, self._dp(out)) != 0:
+            raise RuntimeError(_last_error())
+        return out
+
+    def query(self):
+        """refresh the centre-of-mass slots of the aux rows for the CURRENT state (nothing else is written)."""
+        if self.L.cassie_batch_query(self.h) != 0:
+            raise RuntimeError(_last_error())
 
     def set_qpos(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64)
@@ -352,6 +392,48 @@ class CassieSim:
 
     def full_reset(self):
         self.L.cassie_sim_full_reset(self.c)
+
+    # ---- read-only queries, named as in the reference wrapper (example/cassiemujoco.py:214-306, 815-819)
+    def _vec(self, fn, n):
+        a = (C.c_double * n)()
+        fn(self.c, a)
+        return np.array(a[:])
+
+    def foot_forces_raw(self):
+        return self._vec(self.L.cassie_sim_foot_forces, 12)
+
+    def get_foot_forces(self):
+        f = self.foot_forces_raw()
+        return float(np.sqrt((f[0:3] ** 2).sum())), float(np.sqrt((f[6:9] ** 2).sum()))
+
+    def get_heeltoe_forces(self):
+        t, h = (C.c_double * 6)(), (C.c_double * 6)()
+        self.L.cassie_sim_heeltoe_forces(self.c, t, h)
+        return np.array(t[:]), np.array(h[:])
+
+    def check_collision(self, geom_group):
+        return bool(self.L.cassie_sim_geom_collision(self.c, int(geom_group)))
+
+    def foot_pos(self):
+        return list(self._vec(self.L.cassie_sim_foot_positions, 6))
+
+    def foot_vel(self, vel):
+        vel[:12] = self._vec(self.L.cassie_sim_foot_velocities, 12)
+
+    def center_of_mass_position(self):
+        return list(self._vec(self.L.cassie_sim_cm_position, 3))
+
+    def center_of_mass_velocity(self):
+        return list(self._vec(self.L.cassie_sim_cm_velocity, 3))
+
+    def angular_momentum(self):
+        return list(self._vec(self.L.cassie_sim_angular_momentum, 3))
+
+    def check_self_collision(self):
+        return bool(self.L.cassie_sim_check_self_collision(self.c))
+
+    def check_obstacle_collision(self):
+        return bool(self.L.cassie_sim_check_obstacle_collision(self.c))
 
     def __del__(self):
         try:

@@ -23,7 +23,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM; int *dfilt, *counters, *ticket; const float *hfield; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux; int *dfilt, *counters, *ticket; const float *hfield; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    step_env(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode != 0);
+    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr;
+    step_env(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
+    if (mode == 2) continue;   // query: nothing but the aux row is written
     for (int i = l; i < qw; i += 32) A.qpos[(size_t)env * qw + i] = sm[S_QPOS + i];
     A.qvel[(size_t)env * vw + l] = qvel; A.qacc_ws[(size_t)env * vw + l] = qacc_ws;
     if (A.xb >= 0 && l < 6) { A.qvel[(size_t)env * vw + 32 + l] = xqvel; A.qacc_ws[(size_t)env * vw + 32 + l] = xqacc_ws; }
@@ -178,6 +180,8 @@ struct BatchBase {
   virtual int debug_dump(int env, double *out, int cnt) = 0;
   virtual bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) = 0;
   virtual bool set_hfield(const float *data, int n_terrains) = 0;
+  virtual bool enable_aux(bool on) = 0;
+  virtual bool has_aux() const = 0;
   bool sync() { CUDA_OK(cudaStreamSynchronize(stream)); return true; }
 };
 
@@ -189,7 +193,7 @@ template <typename real> struct Batch : BatchBase {
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux);
     if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -308,8 +312,17 @@ template <typename real> struct Batch : BatchBase {
     A.hfield = d_hfield; A.n_terrain = n_terrains; A.hfield_stride = cells;
     return true;
   }
+  // derived-quantity rows [n][AUX_W]: allocated on first use; while present every launch fills them (a few percent of a step)
+  bool enable_aux(bool on) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (on && !A.aux) { CUDA_OK(cudaMalloc(&A.aux, sizeof(real) * n * AUX_W)); CUDA_OK(cudaMemsetAsync(A.aux, 0, sizeof(real) * n * AUX_W, stream)); }
+    if (!on && A.aux) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.aux)); A.aux = nullptr; }
+    return true;
+  }
+  bool has_aux() const override { return A.aux != nullptr; }
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
+    if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
     int grid = (n + wpb - 1) / wpb; if (grid > resident_ctas) grid = resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
     cassie_step_kernel<real><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);
@@ -343,6 +356,7 @@ template <typename real> struct Batch : BatchBase {
     if (!strcmp(f, "time")) return d2h(A.cst, CST_W, 1, CS_TIME, out);
     if (!strcmp(f, "obs")) return d2h(A.obs, OBS_W, OBS_W, 0, out);
     if (!strcmp(f, "cst")) return d2h(A.cst, CST_W, CST_W, 0, out);
+    if (!strcmp(f, "aux")) { if (!A.aux) { set_err("derived quantities are not enabled (cassie_batch_enable_aux)"); return false; } return d2h(A.aux, AUX_W, AUX_W, 0, out); }
     set_err(std::string("unknown field ") + f); return false;
   }
   bool h2d(real *dst, int w, int take, int off, const double *in) {
@@ -370,7 +384,7 @@ template <typename real> struct Batch : BatchBase {
   }
   void *dev_ptr(const char *f) override {
     if (!strcmp(f, "qpos")) return A.qpos; if (!strcmp(f, "qvel")) return A.qvel; if (!strcmp(f, "pd")) return A.pd; if (!strcmp(f, "obs")) return A.obs;
-    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws;
+    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux;
     return nullptr;
   }
   bool get_counters(int *out) override {
@@ -394,7 +408,7 @@ template <typename real> struct Batch : BatchBase {
 // ====================================================================== C-ABI
 using namespace cassie;
 struct cassie_batch { BatchBase *impl; std::vector<double> obs, radio; };
-struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev; std::vector<float> hfield, hfield_dev; };
+struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev, aux[AUX_W]; std::vector<float> hfield, hfield_dev; };
 
 static std::mutex g_model_mutex;
 static std::string g_model_path;   // what cassie_mujoco_init cached (the reference caches the parsed model, src/cassiemujoco.c:48-59)
@@ -425,7 +439,7 @@ int cassie_batch_nv(const cassie_batch_t *b) { return b->impl->hm.nv; }
 int cassie_batch_precision(const cassie_batch_t *b) { return b->impl->precision; }
 int cassie_batch_row_width(const cassie_batch_t *b, const char *field) {
   if (!strcmp(field, "qpos")) return b->impl->hm.nq > 36 ? QPOS_W_XB : QPOS_W_MAIN; if (!strcmp(field, "qvel")) return b->impl->hm.nv > 32 ? QVEL_W_XB : QVEL_W_MAIN;
-  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; return -1;
+  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; if (!strcmp(field, "aux")) return AUX_W; return -1;
 }
 long cassie_batch_launch_count(const cassie_batch_t *b) { return b->impl->launches; }
 void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); }
@@ -439,6 +453,9 @@ void cassie_batch_get_qvel(cassie_batch_t *b, double *out) { b->impl->get("qvel"
 void cassie_batch_set_qvel(cassie_batch_t *b, const double *in) { b->impl->set("qvel", in); }
 void cassie_batch_get_time(cassie_batch_t *b, double *out) { b->impl->get("time", out); }
 void cassie_batch_get_obs(cassie_batch_t *b, double *out) { b->impl->get("obs", out); }
+int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
+int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
+int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }
 int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *body_name) {
   int id = body_name ? b->impl->hm.body_id(body_name) : -1;
   if (id <= 0) { set_err("cassie_batch_apply_force: unknown body (no-op)"); return -1; }
@@ -470,7 +487,7 @@ bool cassie_mujoco_init(const char *modelfile) {
 }
 void cassie_cleanup(void) { std::lock_guard<std::mutex> g(g_model_mutex); g_model_path.clear(); }
 static void sim_pull(cassie_sim_t *c) {
-  c->b->impl->get("qpos", c->qpos); c->b->impl->get("qvel", c->qvel); c->b->impl->get("time", &c->time);
+  c->b->impl->get("qpos", c->qpos); c->b->impl->get("qvel", c->qvel); c->b->impl->get("time", &c->time); if (c->b->impl->has_aux()) c->b->impl->get("aux", c->aux);
   memcpy(c->qpos_dev, c->qpos, sizeof c->qpos); memcpy(c->qvel_dev, c->qvel, sizeof c->qvel); c->time_dev = c->time;
 }
 static void sim_push(cassie_sim_t *c) {  // upload whatever the caller wrote through the borrowed pointers
@@ -484,7 +501,9 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   { std::lock_guard<std::mutex> g(g_model_mutex); if (reinit || g_model_path.empty()) { if (!modelfile) { set_err("cassie_sim_init: model file required"); return nullptr; } path = modelfile; if (g_model_path.empty()) g_model_path = modelfile; } else path = g_model_path; }
   cassie_batch_t *b = cassie_batch_init(path.c_str(), 1, 0, CASSIE_B200_FP64);
   if (!b) return nullptr;
-  cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); c->b = b; sim_pull(c);
+  cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b;
+  b->impl->enable_aux(true); b->impl->step(0, 1);   // a single environment always carries the derived-quantity row; populate it like the sensordata
+  sim_pull(c);
   if (b->impl->hm.nhfield) { c->hfield.assign((size_t)b->impl->hm.hfield_nrow[0] * b->impl->hm.hfield_ncol[0], 0.0f); c->hfield_dev = c->hfield; }
   return c;
 }
@@ -503,6 +522,23 @@ int cassie_sim_get_hfield_ncol(cassie_sim_t *c) { return cassie_batch_hfield_nco
 int cassie_sim_get_nhfielddata(cassie_sim_t *c) { return (int)c->hfield.size(); }
 float *cassie_sim_hfielddata(cassie_sim_t *c) { return c->hfield.empty() ? nullptr : c->hfield.data(); }
 void cassie_sim_set_hfielddata(cassie_sim_t *c, float *data) { for (size_t i = 0; i < c->hfield.size(); i++) c->hfield[i] = data[i]; }
+// ---- read-only derived quantities (include/cassiemujoco.h:200-240).  Contact forces, flags, foot positions / velocities are by-products of
+// the last step (the reference reads the same stale mjData arrays); the centre-of-mass group recomputes the kinematics of the CURRENT
+// state first, as the reference does with mj_fwdPosition, through a query launch that writes nothing else.
+static const double *sim_aux(const cassie_sim_t *c) { return c->aux; }
+static void sim_query(const cassie_sim_t *cc) { cassie_sim_t *c = const_cast<cassie_sim_t *>(cc); sim_push(c); double keep[AUX_W]; memcpy(keep, c->aux, sizeof keep);
+  cassie_batch_query(c->b); c->b->impl->get("aux", c->aux);
+  for (int i = 0; i < AUX_W; i++) if (i < AX_CM_POS || i >= AX_ANGMOM + 3) c->aux[i] = keep[i]; }
+void cassie_sim_foot_forces(const cassie_sim_t *c, double cfrc[12]) { memcpy(cfrc, sim_aux(c) + AX_FOOT_FORCE, 12 * sizeof(double)); }
+void cassie_sim_heeltoe_forces(const cassie_sim_t *c, double toe_force[6], double heel_force[6]) { memcpy(toe_force, sim_aux(c) + AX_TOE_FORCE, 6 * sizeof(double)); memcpy(heel_force, sim_aux(c) + AX_HEEL_FORCE, 6 * sizeof(double)); }
+void cassie_sim_foot_positions(const cassie_sim_t *c, double cpos[6]) { memcpy(cpos, sim_aux(c) + AX_FOOT_POS, 6 * sizeof(double)); }
+void cassie_sim_foot_velocities(const cassie_sim_t *c, double cvel[12]) { memcpy(cvel, sim_aux(c) + AX_FOOT_VEL, 12 * sizeof(double)); }
+void cassie_sim_cm_position(const cassie_sim_t *c, double cm_pos[3]) { sim_query(c); memcpy(cm_pos, sim_aux(c) + AX_CM_POS, 3 * sizeof(double)); }
+void cassie_sim_cm_velocity(const cassie_sim_t *c, double cm_vel[3]) { sim_query(c); memcpy(cm_vel, sim_aux(c) + AX_CM_VEL, 3 * sizeof(double)); }
+void cassie_sim_angular_momentum(const cassie_sim_t *c, double Lcm[3]) { sim_query(c); memcpy(Lcm, sim_aux(c) + AX_ANGMOM, 3 * sizeof(double)); }
+bool cassie_sim_check_obstacle_collision(const cassie_sim_t *c) { return sim_aux(c)[AX_OBSTACLE] != 0; }
+bool cassie_sim_check_self_collision(const cassie_sim_t *c) { return sim_aux(c)[AX_SELF] != 0; }
+bool cassie_sim_geom_collision(const cassie_sim_t *c, int geom_group) { return geom_group >= 0 && geom_group < 16 && (((int)sim_aux(c)[AX_GROUPMASK] >> geom_group) & 1); }
 void cassie_sim_full_reset(cassie_sim_t *c) {
   // src/cassiemujoco.c:2008-2033: qpos <- 35 constants, zero qvel / ctrl / applied forces / qacc, zero the torque delay line.
   // It does NOT touch time, the encoder filters or cassie_out, and does not call mj_forward.

@@ -186,6 +186,12 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
         if (std::fabs(q[0]) < 1 - 1e-12 || std::fabs(bq[0]) < 1 - 1e-12 || m.body_weldid[m.geom_bodyid[g1]] != 0) { err = "the height field must be axis aligned and static"; return false; } }
       int k1 = dev_geom(g1), k2 = dev_geom(g2); if (k1 < 0 || k2 < 0) { err = "too many collision geoms"; return false; }
       int p = d.npair++; d.pair_g1[p] = k1; d.pair_g2[p] = k2; d.pair_kind[p] = kind;
+      { const int u1 = m.geom_user[g1], u2 = m.geom_user[g2], r1 = m.geom_group[g1], r2 = m.geom_group[g2]; int fl = 0;
+        if (u1 == 1 || u2 == 1) fl |= 1;
+        if (u1 == 2 && u2 == 2) fl |= 2;
+        if (r1 == 1 && r2 >= 0 && r2 < 16) fl |= 256 << r2;
+        if (r2 == 1 && r1 >= 0 && r1 < 16) fl |= 256 << r1;
+        d.pair_flags[p] = fl; }
       // contact parameter mixing (mj_contactParam)
       double fr, solref[2], solimp[5]; int dim;
       if (m.geom_priority[g1] != m.geom_priority[g2]) {
@@ -204,6 +210,21 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       d.pair_margin[p] = (real)std::max(m.geom_margin[g1], m.geom_margin[g2]); d.pair_gap[p] = (real)std::max(m.geom_gap[g1], m.geom_gap[g2]);
       for (int k = 0; k < 2; k++) d.pair_solref[p][k] = (real)solref[k];
       for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = (real)solimp[k];
+    }
+  }
+  // feet: bodies `left-foot` / `right-foot`; toe and heel points = the named sites when the model has them (model/cassie.xml:153-154,
+  // 219-220), else the end points of the foot capsule (where cassie.xml puts those sites; cassie_hfield.xml / cassie_tray_box.xml lack them)
+  d.foot_offset = (real)std::sqrt(0.01762 * 0.01762 + 0.05219 * 0.05219);   // src/cassiemujoco.c:1618
+  { double mt = 0; for (int b = 1; b < m.nbody; b++) mt += m.body_mass[b]; d.total_mass_inv = (real)(mt > 0 ? 1.0 / mt : 0.0); }
+  for (int s = 0; s < 2; s++) {
+    const int fb = m.body_id(s ? "right-foot" : "left-foot"), toe = m.site_id(s ? "right-toe" : "left-toe"), heel = m.site_id(s ? "right-heel" : "left-heel");
+    d.foot_body[s] = fb;
+    for (int k = 0; k < 3; k++) { d.toe_local[s][k] = 0; d.heel_local[s][k] = 0; }
+    if (fb < 0) continue;
+    if (toe >= 0 && heel >= 0) { for (int k = 0; k < 3; k++) { d.toe_local[s][k] = (real)m.site_pos[3 * toe + k]; d.heel_local[s][k] = (real)m.site_pos[3 * heel + k]; } continue; }
+    for (int g = 0; g < m.ngeom; g++) if (m.geom_bodyid[g] == fb && m.geom_type[g] == GEOM_CAPSULE && m.geom_contype[g]) {
+      double R[9]; detail::q2m_d(R, &m.geom_quat[4 * g]);
+      for (int k = 0; k < 3; k++) { d.toe_local[s][k] = (real)(m.geom_pos[3 * g + k] + R[3 * k + 2] * m.geom_size[3 * g + 1]); d.heel_local[s][k] = (real)(m.geom_pos[3 * g + k] - R[3 * k + 2] * m.geom_size[3 * g + 1]); }
     }
   }
   if (info) { info->unsupported_pairs = unsupported; info->collision_geoms = d.ngeom; }

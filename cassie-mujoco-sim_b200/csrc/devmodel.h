@@ -61,6 +61,11 @@ struct DevModel {
   real geom_pos[MG][3], geom_mat[MG][9], geom_size[MG][3];   // geom frame in its body (row-major rotation), sizes
   int pair_g1[MP], pair_g2[MP], pair_kind[MP], pair_condim[MP];
   real pair_mu[MP], pair_margin[MP], pair_gap[MP], pair_solref[MP][2], pair_solimp[MP][5];
+  int pair_flags[MP];   // derived-quantity flags of a pair: bit 0 obstacle geom involved (geom user == 1), bit 1 robot-robot (both user == 2),
+                        // bits 8.. : geom groups g met by a group-1 geom (cassie_sim_geom_collision, src/cassiemujoco.c:1944-1961)
+  // ---- feet (src/cassiemujoco.c:861-866): body ids, toe / heel points in the foot frames, total mass including the extra free body
+  int foot_body[2], padfb[2];
+  real toe_local[2][3], heel_local[2][3], foot_offset, total_mass_inv, padft[2];
   // ---- equality
   int eq_b1[ME], eq_b2[ME];
   real eq_data[ME][6], eq_solref[ME][2], eq_solimp[ME][5];
@@ -89,6 +94,16 @@ constexpr int CS_TIME = 186;
 constexpr int CS_STO = 187;     // radio channel 8 (safe-torque-off when < 1)
 // OBS offsets
 constexpr int OB_MPOS = 0, OB_MVEL = 10, OB_MTORQUE = 20, OB_JPOS = 30, OB_JVEL = 36, OB_QUAT = 42, OB_GYRO = 46, OB_ACCEL = 49, OB_MAG = 52, OB_TIME = 55;
+
+// derived-quantity row (optional, cassie_batch_enable_aux): the reference's read-only queries (src/cassiemujoco.c:1586-1961) as by-products
+constexpr int AUX_W = 64;
+constexpr int AX_FOOT_FORCE = 0;                    // [12] cassie_sim_foot_forces: left xyz, 3 zeros, right xyz, 3 zeros
+constexpr int AX_TOE_FORCE = 12, AX_HEEL_FORCE = 18; // [6] [6] cassie_sim_heeltoe_forces: left xyz, right xyz
+constexpr int AX_FOOT_POS = 24;                     // [6]  cassie_sim_foot_positions
+constexpr int AX_FOOT_VEL = 30;                     // [12] cassie_sim_foot_velocities
+constexpr int AX_CM_POS = 42, AX_CM_VEL = 45, AX_ANGMOM = 48;   // [3] each: centre of mass, its velocity, angular momentum about it
+constexpr int AX_OBSTACLE = 51, AX_SELF = 52, AX_GROUPMASK = 53, AX_NCON = 54;
+constexpr int AX_TMP = 56;                          // [8] toe / heel world xy of both feet, carried between stages of one sub-step
 
 // ---- per-warp scratch (in units of `real`)
 constexpr int S_XPOS = 0;                       // [32][3]

@@ -174,7 +174,7 @@ void orientation(const Attrs &a, double q[4]) {
 
 struct Body { std::string name; int parent; double pos[3], quat[4], ipos[3], iquat[4], mass, inertia[3]; bool explicit_inertial; std::vector<int> joints, geoms; };
 struct Joint { std::string name; int type, body, limited; double pos[3], axis[3], range[2], ref, springref, stiffness, damping, armature, margin, solref[2], solimp[5]; int qposadr, dofadr; };
-struct Geom { std::string name; int type, body, contype, conaffinity, condim, priority, hfid; double pos[3], quat[4], size[3], rbound, friction[3], solmix, solref[2], solimp[5], margin, gap, mass; bool has_mass; };
+struct Geom { std::string name; int type, body, contype, conaffinity, condim, priority, hfid, user, group; double pos[3], quat[4], size[3], rbound, friction[3], solmix, solref[2], solimp[5], margin, gap, mass; bool has_mass; };
 struct Site { std::string name; int body; double pos[3], quat[4]; };
 void solimp5(const Attrs &a, const char *key, double out[5]) { vec v = Av(a, key, "0.9 0.95 0.001"); double d[5] = {0.9, 0.95, 0.001, 0.5, 2}; for (size_t i = 0; i < v.size() && i < 5; i++) d[i] = v[i]; memcpy(out, d, sizeof d); }
 
@@ -213,6 +213,7 @@ struct Compiler {
     else if (G.type == GEOM_HFIELD) { const double *h = &hf_size[4 * G.hfid]; double t[3] = {h[0], h[1], std::max(h[2], h[3])}; G.rbound = norm3(t); }
     else G.rbound = 0;
     G.condim = Ai(a, "condim", 3); G.priority = Ai(a, "priority", 0);
+    { vec u = Av(a, "user", "0"); G.user = u.empty() ? 0 : (int)u[0]; G.group = Ai(a, "group", 0); }
     vec fr = Av(a, "friction", "1 0.005 0.0001"); double f3[3] = {1, 0.005, 0.0001}; for (size_t i = 0; i < fr.size() && i < 3; i++) f3[i] = fr[i]; memcpy(G.friction, f3, sizeof f3);
     G.solmix = Ad(a, "solmix", 1); vec sr = Av(a, "solref", "0.02 1"); G.solref[0] = sr[0]; G.solref[1] = sr[1]; solimp5(a, "solimp", G.solimp);
     G.margin = Ad(a, "margin", 0); G.gap = Ad(a, "gap", 0); G.has_mass = A(a, "mass") != nullptr; G.mass = Ad(a, "mass", 0);
@@ -455,7 +456,7 @@ bool compile_mjcf(const std::string &xml_path, HostModel &m, std::string &err) {
   m.nM = 0; for (int d = 0; d < m.nv; d++) { m.dof_Madr[d] = m.nM; for (int k = d; k >= 0; k = m.dof_parentid[k]) m.nM++; }
   for (const Geom &G : C.geoms) {
     m.geom_type.push_back(G.type); m.geom_bodyid.push_back(G.body); m.geom_contype.push_back(G.contype); m.geom_conaffinity.push_back(G.conaffinity);
-    m.geom_condim.push_back(G.condim); m.geom_priority.push_back(G.priority); m.geom_hfid.push_back(G.hfid);
+    m.geom_condim.push_back(G.condim); m.geom_priority.push_back(G.priority); m.geom_hfid.push_back(G.hfid); m.geom_user.push_back(G.user); m.geom_group.push_back(G.group);
     m.geom_pos.insert(m.geom_pos.end(), G.pos, G.pos + 3); m.geom_quat.insert(m.geom_quat.end(), G.quat, G.quat + 4); m.geom_size.insert(m.geom_size.end(), G.size, G.size + 3);
     m.geom_friction.insert(m.geom_friction.end(), G.friction, G.friction + 3); m.geom_solref.insert(m.geom_solref.end(), G.solref, G.solref + 2);
     m.geom_solimp.insert(m.geom_solimp.end(), G.solimp, G.solimp + 5); m.geom_rbound.push_back(G.rbound); m.geom_solmix.push_back(G.solmix);
@@ -529,7 +530,7 @@ bool save_cmodel(const HostModel &m, const std::string &path) {
   PVI(jnt_type); PVI(jnt_qposadr); PVI(jnt_dofadr); PVI(jnt_bodyid); PVI(jnt_limited);
   PVF(jnt_pos); PVF(jnt_axis); PVF(jnt_stiffness); PVF(jnt_range); PVF(jnt_margin); PVF(jnt_solref); PVF(jnt_solimp);
   PVI(dof_bodyid); PVI(dof_jntid); PVI(dof_parentid); PVI(dof_Madr); PVF(dof_armature); PVF(dof_damping); PVF(dof_invweight0); PVF(qpos0); PVF(qpos_spring);
-  PVI(geom_type); PVI(geom_bodyid); PVI(geom_contype); PVI(geom_conaffinity); PVI(geom_condim); PVI(geom_priority); PVI(geom_hfid);
+  PVI(geom_type); PVI(geom_bodyid); PVI(geom_contype); PVI(geom_conaffinity); PVI(geom_condim); PVI(geom_priority); PVI(geom_hfid); PVI(geom_user); PVI(geom_group);
   PVF(geom_pos); PVF(geom_quat); PVF(geom_size); PVF(geom_friction); PVF(geom_solref); PVF(geom_solimp); PVF(geom_rbound); PVF(geom_solmix); PVF(geom_margin); PVF(geom_gap);
   PVI(site_bodyid); PVF(site_pos); PVF(site_quat); PVI(eq_obj1id); PVI(eq_obj2id); PVF(eq_data); PVF(eq_solref); PVF(eq_solimp);
   PVI(actuator_jntid); PVI(actuator_ctrllimited); PVF(actuator_gear); PVF(actuator_ctrlrange); PVF(actuator_user);
@@ -559,7 +560,7 @@ bool load_cmodel(const std::string &path, HostModel &m, std::string &err) {
     LVI(jnt_type); LVI(jnt_qposadr); LVI(jnt_dofadr); LVI(jnt_bodyid); LVI(jnt_limited);
     LVF(jnt_pos); LVF(jnt_axis); LVF(jnt_stiffness); LVF(jnt_range); LVF(jnt_margin); LVF(jnt_solref); LVF(jnt_solimp);
     LVI(dof_bodyid); LVI(dof_jntid); LVI(dof_parentid); LVI(dof_Madr); LVF(dof_armature); LVF(dof_damping); LVF(dof_invweight0); LVF(qpos0); LVF(qpos_spring);
-    LVI(geom_type); LVI(geom_bodyid); LVI(geom_contype); LVI(geom_conaffinity); LVI(geom_condim); LVI(geom_priority); LVI(geom_hfid);
+    LVI(geom_type); LVI(geom_bodyid); LVI(geom_contype); LVI(geom_conaffinity); LVI(geom_condim); LVI(geom_priority); LVI(geom_hfid); LVI(geom_user); LVI(geom_group);
     LVF(geom_pos); LVF(geom_quat); LVF(geom_size); LVF(geom_friction); LVF(geom_solref); LVF(geom_solimp); LVF(geom_rbound); LVF(geom_solmix); LVF(geom_margin); LVF(geom_gap);
     LVI(site_bodyid); LVF(site_pos); LVF(site_quat); LVI(eq_obj1id); LVI(eq_obj2id); LVF(eq_data); LVF(eq_solref); LVF(eq_solimp);
     LVI(actuator_jntid); LVI(actuator_ctrllimited); LVF(actuator_gear); LVF(actuator_ctrlrange); LVF(actuator_user);
@@ -568,6 +569,7 @@ bool load_cmodel(const std::string &path, HostModel &m, std::string &err) {
     else if (key == "names_geom") m.names_geom = vs; else if (key == "names_joint") m.names_joint = vs;
   }
   if (m.nv <= 0 || (int)m.dof_parentid.size() != m.nv || (int)m.body_parentid.size() != m.nbody) { err = "malformed model table " + path; return false; }
+  m.geom_user.resize(m.ngeom, 0); m.geom_group.resize(m.ngeom, 0);   // tables written before these columns existed
   return true;
 }
 bool load_model_any(const std::string &path, HostModel &out, std::string &err) {

@@ -31,7 +31,7 @@ struct HostModel {
   std::vector<double> dof_armature, dof_damping, dof_invweight0;
   std::vector<double> qpos0, qpos_spring;
   // geoms (mesh geoms are dropped: in every Cassie model they have contype = conaffinity = 0)
-  std::vector<int> geom_type, geom_bodyid, geom_contype, geom_conaffinity, geom_condim, geom_priority, geom_hfid;
+  std::vector<int> geom_type, geom_bodyid, geom_contype, geom_conaffinity, geom_condim, geom_priority, geom_hfid, geom_user, geom_group;
   std::vector<double> geom_pos, geom_quat, geom_size, geom_friction, geom_solref, geom_solimp, geom_rbound, geom_solmix,
       geom_margin, geom_gap;
   // sites

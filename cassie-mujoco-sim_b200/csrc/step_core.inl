@@ -65,6 +65,7 @@ template <typename real> struct EnvPtrs {
   real *qM;           // [NM_MAX] mass-matrix scratch (written by CRB, read back by the Euler stage)
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
   real *dbg;          // [D_SIZE] or null
+  real *aux;          // [AUX_W] derived-quantity row or null
   int *counters;      // [8]
 };
 
@@ -375,10 +376,29 @@ template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int b
   } else { out[0] = out[1] = out[2] = 0; }
 }
 
+// cassie_sim_foot_velocities (src/cassiemujoco.c:1623-1631): mj_comVel of the two foot bodies = sum over the dof chain, root first, of
+// cdof * qvel; qvel is read from vecs[0..nv), cdof from the copy the derived-quantity stage left in the geom buffer
+template <typename real>
+CFN void aux_foot_velocities(const DevModel<real> &cm, real *sm, real *aux) {
+  DECL_LANE
+  const real *vecs = sm + S_VEC, *cdofs = sm + S_GEOM;
+  LANES
+    if (l < 12) {
+      const int fb = cm.foot_body[l / 6], k = l % 6; real acc = 0;
+      if (fb >= 0) {
+        const int ld = cm.body_lastdof[fb];
+        if (ld >= 0) { for (int t = cm.dof_depth[ld]; t >= 1; --t) { const int a = cm.dof_anc[ld][t]; acc += cdofs[6 * a + k] * vecs[a]; } acc += cdofs[6 * ld + k] * vecs[ld]; }
+      }
+      aux[AX_FOOT_VEL + l] = acc;
+    }
+  ENDL
+}
+
 // ------------------------------------------------------------------ one MuJoCo sub-step (mj_step1 + mj_step2)
 // state in: sm[S_QPOS], lane vars qvel / qacc_ws, ctrl in sm[S_CST..] (via ctrl lane var), xfrc.  state out: same + sensordata.
 template <typename real>
-CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), LP(real, ctrl), real *dbg, bool advance) {
+CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), LP(real, ctrl), real *dbg, int mode) {
+  const bool advance = (mode == 0);   // mode: 0 step, 1 mj_forward only, 2 query (kinematics + velocities -> centre-of-mass slots of the aux row, nothing else written)
   DECL_LANE
   const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
@@ -619,6 +639,35 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
+  // ================= derived quantities, part 1: centre of mass, its velocity, angular momentum about it =================
+  // (cassie_sim_cm_position / cm_velocity / angular_momentum, src/cassiemujoco.c:1633-1646,1693-1699 -> subtree_com, mj_subtreeVel of the
+  // world body).  Sum over bodies of cinert * cvel is the spatial momentum about the main tree's com; the extra free body is folded in.
+  if (E.aux) {
+    LV(real, m0); LV(real, m1); LV(real, m2); LV(real, m3); LV(real, m4); LV(real, m5);
+    LANES
+      real h6[6] = {0, 0, 0, 0, 0, 0};
+      if (l >= 1 && l < nb && l != xb) mul_inert_vec(h6, cinert + 10 * l, cvel + 6 * l);
+      L(m0) = h6[0]; L(m1) = h6[1]; L(m2) = h6[2]; L(m3) = h6[3]; L(m4) = h6[4]; L(m5) = h6[5];
+    ENDL
+    ALLSUM(m0); ALLSUM(m1); ALLSUM(m2); ALLSUM(m3); ALLSUM(m4); ALLSUM(m5);
+    LANES
+      if (l == 0) {
+        real C[3] = {L(com0), L(com1), L(com2)}, P[3] = {L(m3), L(m4), L(m5)}, Lc[3] = {L(m0), L(m1), L(m2)}, V[3];
+        if (xb >= 0) {
+          const real mc = cm.xb_mass, Mr = real(1) / cm.root_mass_inv, *xc = xpos + 3 * xb, *R = xmat + 9 * xb;
+          real Ct[3], d1[3], d2[3], t3[3], pc[3] = {mc * vecs[160], mc * vecs[161], mc * vecs[162]}, Iw[3] = {cm.xb_inertia[0] * vecs[163], cm.xb_inertia[1] * vecs[164], cm.xb_inertia[2] * vecs[165]}, Lx[3];
+          for (int k = 0; k < 3; ++k) { Ct[k] = (Mr * C[k] + mc * xc[k]) * cm.total_mass_inv; d1[k] = C[k] - Ct[k]; d2[k] = xc[k] - Ct[k]; }
+          mat_vec(Lx, R, Iw);
+          cross3(t3, d1, P); for (int k = 0; k < 3; ++k) Lc[k] += t3[k] + Lx[k];
+          cross3(t3, d2, pc); for (int k = 0; k < 3; ++k) { Lc[k] += t3[k]; P[k] += pc[k]; C[k] = Ct[k]; }
+        }
+        for (int k = 0; k < 3; ++k) V[k] = P[k] * cm.total_mass_inv;
+        for (int k = 0; k < 3; ++k) { E.aux[AX_CM_POS + k] = C[k]; E.aux[AX_CM_VEL + k] = V[k]; E.aux[AX_ANGMOM + k] = Lc[k]; }
+      }
+    ENDL
+    if (mode == 2) return;
+  }
+
   // ================= sensors that do not need qacc (mj_sensorPos / mj_sensorVel for the Cassie layout) =================
   // done here because the constraint stage below reuses the kinematics buffers; the accelerometer is finished after the solve from
   // a small stash: vecs[102..104] = qacc-independent part, vecs[105..] = 3 x nchain gain matrix over the IMU body's dof chain
@@ -831,11 +880,25 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         }
       }
       if (l < rows) { efc[4 * (nefc + l) + E_POS] = o[12]; efc[4 * (nefc + l) + E_SRC] = (real)(128 + p); efc[4 * (nefc + l) + E_INEQ] = 1; }
+      if (l == 0) con[16 * c + 14] = (real)nefc;   // first row of this contact (read back by the contact-force stage)
     ENDL
     nefc += rows; ++ncon_used;
   }
   if (counters) { LANES if (l == 0) { counters[0] = nefc; counters[1] = ncon_used; counters[2] = nlim; if (ncon_total > ncon_used) counters[4] += ncon_total - ncon_used; } ENDL }
   (void)nefc_before_contacts;
+  // ================= derived quantities, part 2 (while the kinematics buffers are alive): foot positions, toe / heel points, a copy of
+  // cdof for the foot velocities (cassie_sim_foot_positions :1608-1621; site_xpos of the toe / heel sites :1888-1889)
+  if (E.aux) {
+    real *cdofs = geom;   // the geom poses are dead once the contacts are listed
+    LANES
+      if (l < nv) for (int k = 0; k < 6; ++k) cdofs[6 * l + k] = cdof[6 * l + k];
+      if (l < 6) { const int fb = cm.foot_body[l / 3], k = l % 3; real v = fb >= 0 ? xpos[3 * fb + k] : real(0); if (k == 2) v -= cm.foot_offset; E.aux[AX_FOOT_POS + l] = v; }
+      if (l >= 8 && l < 16) {
+        const int i = l - 8, sd = i >> 2, k = i & 1, fb = cm.foot_body[sd]; const real *loc = ((i >> 1) & 1) ? cm.heel_local[sd] : cm.toe_local[sd];
+        E.aux[AX_TMP + i] = fb >= 0 ? xpos[3 * fb + k] + (xmat[9 * fb + 3 * k] * loc[0] + xmat[9 * fb + 3 * k + 1] * loc[1] + xmat[9 * fb + 3 * k + 2] * loc[2]) : real(0);
+      }
+    ENDL
+  }
 
   LV(real, qacc); LV(real, qfrc_con);
   LV(real, f0); LV(real, f1);    // constraint forces: lane (r & 31) owns rows r and r + 32
@@ -1042,6 +1105,47 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     }
   }
   if (counters) { LANES if (l == 0) counters[3] = iters; ENDL }
+  // ================= derived quantities, part 3: contact forces (mj_contactForce -> world frame), foot / toe / heel sums, collision flags
+  // (cassie_sim_foot_forces :1812-1854, cassie_sim_heeltoe_forces :1856-1898, check_*_collision :1586-1606, geom_collision :1944-1961)
+  if (E.aux) {
+    real *aux = E.aux;
+    if (nefc > 0) { LANES if (l < nefc) efc[4 * l] = L(f0); if (l + 32 < nefc) efc[4 * (l + 32)] = L(f1); ENDL }   // slot 0 (b) is dead: keep the row forces
+    LANES  // lane = contact: decode the pyramid, rotate into the world frame, classify
+      if (l < ncon_used) {
+        real *o = con + 16 * l; const int p = (int)o[13], r0 = (int)o[14];
+        real fn, t1 = 0, t2 = 0;
+        if (cm.pair_condim[p] == 1) fn = efc[4 * r0];
+        else { const real a = efc[4 * r0], b = efc[4 * (r0 + 1)], c = efc[4 * (r0 + 2)], d = efc[4 * (r0 + 3)], mu = cm.pair_mu[p]; fn = a + b + c + d; t1 = (a - b) * mu; t2 = (c - d) * mu; }
+        real F[3]; for (int k = 0; k < 3; ++k) F[k] = o[3 + k] * fn + o[6 + k] * t1 + o[9 + k] * t2;
+        const int b1 = cm.geom_body[cm.pair_g1[p]], b2 = cm.geom_body[cm.pair_g2[p]], lf = cm.foot_body[0], rf = cm.foot_body[1];
+        const bool f1 = (b1 == lf || b1 == rf), anyf = f1 || b2 == lf || b2 == rf; const int id = (b1 == rf || b2 == rf) ? 1 : 0;
+        real toe = 0;
+        if (anyf) {
+          const real td0 = aux[AX_TMP + 4 * id] - o[0], td1 = aux[AX_TMP + 4 * id + 1] - o[1], hd0 = aux[AX_TMP + 4 * id + 2] - o[0], hd1 = aux[AX_TMP + 4 * id + 3] - o[1];
+          toe = (msqrt(td0 * td0 + td1 * td1) < msqrt(hd0 * hd0 + hd1 * hd1)) ? real(1) : real(0);
+        }
+        o[3] = F[0]; o[4] = F[1]; o[5] = F[2];
+        o[6] = b1 == lf ? real(-1) : (b2 == lf ? real(1) : real(0));   // sign with which this contact enters the left / right foot force
+        o[7] = b1 == rf ? real(-1) : (b2 == rf ? real(1) : real(0));
+        o[8] = anyf ? (f1 ? real(-1) : real(1)) : real(0); o[9] = (real)id; o[10] = toe;   // heel / toe split: sign, foot, toe-or-heel
+      }
+    ENDL
+    LANES  // lane = output slot
+      if (l < 18) {
+        real acc = 0;
+        for (int c = 0; c < ncon_used; ++c) {
+          const real *o = con + 16 * c;
+          if (l < 6) { const real sg = o[6 + l / 3]; if (sg != 0) acc += sg * o[3 + l % 3]; }
+          else { const int i = l - 6, j = i % 6; if (o[8] != 0 && (int)o[9] == j / 3 && (o[10] != 0) == (i < 6)) acc += o[8] * o[3 + j % 3]; }
+        }
+        if (l < 6) { aux[AX_FOOT_FORCE + 6 * (l / 3) + l % 3] = acc; aux[AX_FOOT_FORCE + 6 * (l / 3) + 3 + l % 3] = 0; }
+        else aux[AX_TOE_FORCE + (l - 6)] = acc;
+      } else if (l == 18) {
+        int fl = 0; for (int c = 0; c < ncon_used; ++c) fl |= cm.pair_flags[(int)con[16 * c + 13]];
+        aux[AX_OBSTACLE] = (fl & 1) ? real(1) : real(0); aux[AX_SELF] = (fl & 2) ? real(1) : real(0); aux[AX_GROUPMASK] = (real)(fl >> 8); aux[AX_NCON] = (real)ncon_used;
+      }
+    ENDL
+  }
   if (dbg) {
     LANES
       if (l < nv) { dbg[D_QACC + l] = L(qacc); dbg[D_QFRCC + l] = L(qfrc_con); }
@@ -1068,7 +1172,10 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   ENDL
   if (dbg) { LANES if (l < 29) dbg[D_SENS + l] = cst[CS_SENSOR + l]; ENDL }
 
-  if (!advance) return;   // mj_forward only (used once at init / reset to populate sensordata, src/cassiemujoco.c:1029)
+  if (!advance) {   // mj_forward only (used once at init / reset to populate sensordata, src/cassiemujoco.c:1029)
+    if (E.aux) { LANES if (l < nv) vecs[l] = L(qvel); ENDL aux_foot_velocities(cm, sm, E.aux); }
+    return;
+  }
   // ================= Euler with implicit joint damping (mj_Euler) + mj_advance =================
   // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
@@ -1082,6 +1189,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   } else { LANES L(a) = L(qacc); ENDL }
   LANES if (l < nv) { L(qvel) += cm.timestep * L(a); vecs[l] = L(qvel); L(qacc_ws) = L(qacc); }
     if (xb >= 0 && l < 6) { L(xqvel) += cm.timestep * L(xqacc); vecs[160 + l] = L(xqvel); L(xqacc_ws) = L(xqacc); } ENDL
+  if (E.aux) aux_foot_velocities(cm, sm, E.aux);   // with the NEW qvel and the cdof of this sub-step's kinematics, as the reference's query does
   LANES  // lane = joint: integrate positions with the NEW velocity
     if (l < cm.njnt) {
       const int t = cm.jnt_type[l], qa = cm.jnt_qposadr[l], da = cm.jnt_dofadr[l]; const real h = cm.timestep;
@@ -1110,7 +1218,8 @@ template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
 template <typename real>
-CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), int nticks, bool forward_only) {
+CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), int nticks, int mode) {
+  const bool forward_only = (mode != 0);
   DECL_LANE
   real *cst = E.cst, *vecs = sm + S_VEC, *obs = E.obs; const real *pd = E.pd; int *ism = E.dfilt;
   LV(real, ctrl); LV(real, tq); LV(real, scale_part);
@@ -1203,7 +1312,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
     const int nsub = forward_only ? 1 : cm.nsub;
-    for (int s = 0; s < nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, !forward_only);
+    for (int s = 0; s < nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, mode);
   }
 }
 

@@ -53,6 +53,20 @@ int cassie_sim_get_hfield_ncol(cassie_sim_t *sim);
 int cassie_sim_get_nhfielddata(cassie_sim_t *sim);
 float *cassie_sim_hfielddata(cassie_sim_t *sim);
 void cassie_sim_set_hfielddata(cassie_sim_t *sim, float *data);
+/* read-only derived quantities.  include/cassiemujoco.h:200-240 (src/cassiemujoco.c:1586-1699, 1812-1898, 1944-1961).
+ * Like the reference, the contact / foot group reads what the LAST step left behind (contact list and forces of the state that step
+ * started from); the centre-of-mass group first recomputes the kinematics of the current state (the reference calls mj_fwdPosition).
+ * cm_velocity / angular_momentum use velocities consistent with that state (the reference mixes them with the previous step's cvel). */
+bool cassie_sim_check_obstacle_collision(const cassie_sim_t *sim);
+bool cassie_sim_check_self_collision(const cassie_sim_t *sim);
+void cassie_sim_foot_forces(const cassie_sim_t *c, double cfrc[12]);
+void cassie_sim_heeltoe_forces(const cassie_sim_t *c, double toe_force[6], double heel_force[6]);
+bool cassie_sim_geom_collision(const cassie_sim_t *c, int geom_group);
+void cassie_sim_foot_positions(const cassie_sim_t *c, double cpos[6]);   /* src/cassiemujoco.c:1608-1621 (defined there, not in the header) */
+void cassie_sim_foot_velocities(const cassie_sim_t *c, double cvel[12]);
+void cassie_sim_cm_position(const cassie_sim_t *c, double cm_pos[3]);
+void cassie_sim_cm_velocity(const cassie_sim_t *c, double cm_vel[3]);
+void cassie_sim_angular_momentum(const cassie_sim_t *c, double Lcm[3]);
 /* src/cassiemujoco.c:2002-2006: the 16 radio channels; channel 8 < 1 engages safe-torque-off */
 void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
 
@@ -61,6 +75,20 @@ void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
 #define CASSIE_B200_FP64 1 /* parity build: state and arithmetic in fp64 */
 #define CASSIE_PD_WIDTH 52  /* compact motor-PD row: torque[10] pTarget[10] dTarget[10] pGain[10] dGain[10] pad[2] */
 #define CASSIE_OBS_WIDTH 64 /* compact observation row, see cassie_batch_get_obs */
+#define CASSIE_AUX_WIDTH 64 /* derived-quantity row, see cassie_batch_get_aux */
+/* offsets inside a derived-quantity row */
+#define CASSIE_AUX_FOOT_FORCE 0   /* [12] cassie_sim_foot_forces layout: left xyz, 3 zeros, right xyz, 3 zeros */
+#define CASSIE_AUX_TOE_FORCE 12   /* [6]  cassie_sim_heeltoe_forces toe_force: left xyz, right xyz */
+#define CASSIE_AUX_HEEL_FORCE 18  /* [6]  ... heel_force */
+#define CASSIE_AUX_FOOT_POS 24    /* [6]  cassie_sim_foot_positions */
+#define CASSIE_AUX_FOOT_VEL 30    /* [12] cassie_sim_foot_velocities */
+#define CASSIE_AUX_CM_POS 42      /* [3]  centre of mass of everything (cassie_sim_cm_position) */
+#define CASSIE_AUX_CM_VEL 45      /* [3]  its velocity (cassie_sim_cm_velocity) */
+#define CASSIE_AUX_ANGMOM 48      /* [3]  angular momentum about it (cassie_sim_angular_momentum) */
+#define CASSIE_AUX_OBSTACLE 51    /* 1 if a contact involves an obstacle geom (cassie_sim_check_obstacle_collision) */
+#define CASSIE_AUX_SELF 52        /* 1 if two robot geoms touch (cassie_sim_check_self_collision) */
+#define CASSIE_AUX_GROUPMASK 53   /* bit g set: a group-1 geom touches a geom of group g (cassie_sim_geom_collision) */
+#define CASSIE_AUX_NCON 54        /* contacts that entered the solve */
 
 /* n_env environments on CUDA device `device`, all in the state cassie_sim_init leaves (src/cassiemujoco.c:979-1036).
  * modelfile: MJCF (.xml) or a compiled table (.cmodel).  NULL + stderr message on failure (no GPU, bad model, ...). */
@@ -92,6 +120,15 @@ void cassie_batch_get_qvel(cassie_batch_t *b, double *out);
 void cassie_batch_set_qvel(cassie_batch_t *b, const double *in);
 void cassie_batch_get_time(cassie_batch_t *b, double *out);
 void cassie_batch_get_obs(cassie_batch_t *b, double *out);
+/* derived quantities for every environment, as by-products of the step kernel (no second pass over the state).
+ * enable_aux(b, 1) allocates [n][CASSIE_AUX_WIDTH] rows in the batch precision; from then on every step / forward launch fills them:
+ * contact-derived slots and foot positions / velocities exactly as the reference's queries would return right after that step; the
+ * centre-of-mass slots describe the state the last sub-step STARTED from (one 0.5 ms tick old).  cassie_batch_query recomputes only the
+ * centre-of-mass slots for the CURRENT state and writes nothing else (state, sensors and the other slots are untouched).
+ * get_aux: synchronous host copy [n][CASSIE_AUX_WIDTH] doubles; device pointer: cassie_batch_device_ptr(b, "aux").  0 / -1. */
+int cassie_batch_enable_aux(cassie_batch_t *b, int on);
+int cassie_batch_get_aux(cassie_batch_t *b, double *out);
+int cassie_batch_query(cassie_batch_t *b);
 /* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
 void cassie_batch_forward(cassie_batch_t *b);
 /* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */

@@ -57,7 +57,7 @@ typedef struct {
   double dof_armature[MAXV], dof_damping[MAXV], dof_invweight0[MAXV];
   double qpos0[MAXV + 8], qpos_spring[MAXV + 8];
   int geom_type[MAXG], geom_bodyid[MAXG], geom_contype[MAXG], geom_conaffinity[MAXG], geom_condim[MAXG],
-      geom_priority[MAXG], geom_hfid[MAXG];
+      geom_priority[MAXG], geom_hfid[MAXG], geom_user[MAXG], geom_group[MAXG];
   double geom_pos[MAXG][3], geom_quat[MAXG][4], geom_size[MAXG][3], geom_friction[MAXG][3], geom_solref[MAXG][2],
       geom_solimp[MAXG][5], geom_rbound[MAXG], geom_solmix[MAXG], geom_margin[MAXG], geom_gap[MAXG];
   int site_bodyid[32];
@@ -72,11 +72,14 @@ typedef struct {
   double hfield_size[4];
   float *hfield_data;
   int imu_site;
+  /* ids looked up by name at init (src/cassiemujoco.c:861-866); -1 when the model has no such site */
+  int left_foot_body, right_foot_body, left_heel, left_toe, right_heel, right_toe;
+  double toe_local[2][3], heel_local[2][3]; /* toe / heel points in the foot body frames (sites, else the foot capsule's end points) */
 } OModel;
 
 typedef struct {
   double pos[3], frame[9], dist, friction[5], solref[2], solimp[5], includemargin, mu;
-  int dim, geom1, geom2;
+  int dim, geom1, geom2, efc_address;
 } OContact;
 
 typedef struct {
@@ -97,7 +100,7 @@ typedef struct {
   /* velocity-dependent */
   double cvel[MAXB][6], cdof_dot[MAXV][6], qfrc_bias[MAXV], qfrc_passive[MAXV], actuator_velocity[16],
       actuator_length[16], actuator_force[16], qfrc_actuator[MAXV], qfrc_smooth[MAXV], qacc_smooth[MAXV],
-      qfrc_constraint[MAXV], cacc[MAXB][6];
+      qfrc_constraint[MAXV], cacc[MAXB][6], subtree_linvel[MAXB][3], subtree_angmom[MAXB][3];
   double sensordata[40];
   int solver_iter, unsupported_pairs, dropped_contacts;
 } OData;
@@ -185,7 +188,7 @@ OModel *omodel_load(const char *path) {
   OModel *m = calloc(1, sizeof(OModel));
   size_t cap = 1 << 20; char *line = malloc(cap);
   static char *tok[70000];
-  char site_names[32][64]; int nsn = 0;
+  char site_names[32][64], body_names[MAXB][64]; int nsn = 0, nbn = 0;
   while (fgets(line, cap, f)) {
     if (line[0] == '#') continue;
     char *key = strtok(line, " \n"); if (!key) continue;
@@ -220,6 +223,7 @@ OModel *omodel_load(const char *path) {
     KI("geom_type", m->geom_type, MAXG); KI("geom_bodyid", m->geom_bodyid, MAXG); KI("geom_contype", m->geom_contype, MAXG);
     KI("geom_conaffinity", m->geom_conaffinity, MAXG); KI("geom_condim", m->geom_condim, MAXG);
     KI("geom_priority", m->geom_priority, MAXG); KI("geom_hfid", m->geom_hfid, MAXG);
+    KI("geom_user", m->geom_user, MAXG); KI("geom_group", m->geom_group, MAXG);
     KF("geom_pos", m->geom_pos, MAXG * 3); KF("geom_quat", m->geom_quat, MAXG * 4); KF("geom_size", m->geom_size, MAXG * 3);
     KF("geom_friction", m->geom_friction, MAXG * 3); KF("geom_solref", m->geom_solref, MAXG * 2);
     KF("geom_solimp", m->geom_solimp, MAXG * 5); KF("geom_rbound", m->geom_rbound, MAXG); KF("geom_solmix", m->geom_solmix, MAXG);
@@ -232,11 +236,28 @@ OModel *omodel_load(const char *path) {
     KI("sensor_type", m->sensor_type, 32); KI("sensor_objid", m->sensor_objid, 32);
     KF("sensor_user", m->sensor_user, 32); KF("sensor_cutoff", m->sensor_cutoff, 32);
     KI("hfield_nrow", &m->hfield_nrow, 1); KI("hfield_ncol", &m->hfield_ncol, 1); KF("hfield_size", m->hfield_size, 4);
+    else if (!strcmp(key, "names_body")) { for (int i = 0; i < n && i < MAXB; i++) { strncpy(body_names[i], tok[i], 63); body_names[i][63] = 0; } nbn = n < MAXB ? n : MAXB; }
     else if (!strcmp(key, "names_site")) { for (int i = 0; i < n && i < 32; i++) { strncpy(site_names[i], tok[i], 63); site_names[i][63] = 0; } nsn = n < 32 ? n : 32; }
   }
   fclose(f); free(line);
   m->imu_site = 0;
   for (int i = 0; i < nsn; i++) if (!strcmp(site_names[i], "imu")) m->imu_site = i;
+  m->left_foot_body = m->right_foot_body = m->left_heel = m->left_toe = m->right_heel = m->right_toe = -1;
+  for (int i = 0; i < nbn; i++) { if (!strcmp(body_names[i], "left-foot")) m->left_foot_body = i; if (!strcmp(body_names[i], "right-foot")) m->right_foot_body = i; }
+  for (int i = 0; i < nsn; i++) {
+    if (!strcmp(site_names[i], "left-heel")) m->left_heel = i; if (!strcmp(site_names[i], "left-toe")) m->left_toe = i;
+    if (!strcmp(site_names[i], "right-heel")) m->right_heel = i; if (!strcmp(site_names[i], "right-toe")) m->right_toe = i;
+  }
+  for (int s = 0; s < 2; s++) { /* toe / heel points: the named sites; models without them (cassie_hfield.xml, cassie_tray_box.xml) fall back
+                                   to the end points of the foot capsule, which is where cassie.xml puts the sites (model/cassie.xml:151-154) */
+    int fb = s ? m->right_foot_body : m->left_foot_body, toe = s ? m->right_toe : m->left_toe, heel = s ? m->right_heel : m->left_heel;
+    if (toe >= 0 && heel >= 0) { for (int k = 0; k < 3; k++) { m->toe_local[s][k] = m->site_pos[toe][k]; m->heel_local[s][k] = m->site_pos[heel][k]; } continue; }
+    for (int g = 0; g < m->ngeom; g++) if (m->geom_bodyid[g] == fb && m->geom_type[g] == 3 /* capsule */ && m->geom_contype[g]) {
+      const double *q = m->geom_quat[g]; /* z axis of the geom frame */
+      double z[3] = {2 * (q[1] * q[3] + q[0] * q[2]), 2 * (q[2] * q[3] - q[0] * q[1]), 1 - 2 * (q[1] * q[1] + q[2] * q[2])};
+      for (int k = 0; k < 3; k++) { m->toe_local[s][k] = m->geom_pos[g][k] + z[k] * m->geom_size[g][1]; m->heel_local[s][k] = m->geom_pos[g][k] - z[k] * m->geom_size[g][1]; }
+    }
+  }
   if (m->nhfield) m->hfield_data = calloc((size_t)m->hfield_nrow * m->hfield_ncol, sizeof(float));
   if (m->nv > MAXV || m->nbody > MAXB || m->ngeom > MAXG || m->nM > MAXNM) { fprintf(stderr, "oracle: model too large\n"); free(m); return NULL; }
   return m;
@@ -709,6 +730,7 @@ static void o_makeConstraint(const OModel *m, OData *d) {
   /* contacts */
   for (int c = 0; c < d->ncon; c++) {
     OContact *con = &d->contact[c]; int b1 = m->geom_bodyid[con->geom1], b2 = m->geom_bodyid[con->geom2];
+    con->efc_address = d->nefc;
     o_jac(m, d, jp1, NULL, con->pos, b1); o_jac(m, d, jp2, NULL, con->pos, b2);
     int nr = con->dim > 1 ? 3 : 1;
     for (int r = 0; r < nr; r++) for (int i = 0; i < nv; i++) {
@@ -1143,6 +1165,116 @@ void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassi
   }
 }
 
+/* ------------------------------------------------------------------ derived-quantity queries (src/cassiemujoco.c:1586-1961)
+ * Each function restates the reference function of the same name, INCLUDING which arrays it recomputes and which it reads stale:
+ * after cassie_sim_step_pd the contact list, efc_force, xpos and cdof belong to the state the last sub-step started from, qvel / qpos are
+ * one step newer. */
+static void o_fwdPosition(const OModel *m, OData *d) { /* mj_fwdPosition [M] (camlight / tendon: nothing to do for these models) */
+  o_kinematics(m, d); o_comPos(m, d);
+  for (int i = 0; i < m->nu; i++) { int j = m->actuator_jntid[i]; d->actuator_length[i] = m->actuator_gear[i] * d->qpos[m->jnt_qposadr[j]]; }
+  o_crb(m, d); copyv(d->qLD, d->qM, m->nM); factorI(m, d->qLD, d->qLDiagInv, d->qLDiagSqrtInv);
+  o_collision(m, d); o_makeConstraint(m, d); o_projectConstraint(m, d);
+}
+static void o_subtreeVel(const OModel *m, OData *d) { /* mj_subtreeVel [M]; reads d->cvel as it stands */
+  double body_vel[MAXB][6], dx[3], dv[3], dp[3], dL[3];
+  for (int i = 0; i < m->nbody; i++) {
+    /* mj_objectVelocity(mjOBJ_BODY, world orientation): cvel moved from the c-frame origin to the body's inertial frame origin */
+    const double *cv = d->cvel[i]; double dif[3], cr[3];
+    for (int k = 0; k < 3; k++) dif[k] = d->xipos[i][k] - d->subtree_com[m->body_rootid[i]][k];
+    cross(cr, dif, cv);
+    for (int k = 0; k < 3; k++) { body_vel[i][k] = cv[k]; body_vel[i][3 + k] = cv[3 + k] - cr[k]; }
+    for (int k = 0; k < 3; k++) d->subtree_linvel[i][k] = body_vel[i][3 + k] * m->body_mass[i];
+    mulMatTVec3(dv, d->ximat[i], body_vel[i]);
+    for (int k = 0; k < 3; k++) dv[k] *= m->body_inertia[i][k];
+    mulMatVec3(d->subtree_angmom[i], d->ximat[i], dv);
+  }
+  for (int i = m->nbody - 1; i >= 0; i--) {
+    if (i) for (int k = 0; k < 3; k++) d->subtree_linvel[m->body_parentid[i]][k] += d->subtree_linvel[i][k];
+    double inv = 1 / fmax(MINVAL, m->body_subtreemass[i]);
+    for (int k = 0; k < 3; k++) d->subtree_linvel[i][k] *= inv;
+  }
+  for (int i = m->nbody - 1; i > 0; i--) {
+    int parent = m->body_parentid[i];
+    for (int k = 0; k < 3; k++) { dx[k] = d->xipos[i][k] - d->subtree_com[i][k]; dv[k] = body_vel[i][3 + k] - d->subtree_linvel[i][k]; dp[k] = dv[k] * m->body_mass[i]; }
+    cross(dL, dx, dp);
+    for (int k = 0; k < 3; k++) d->subtree_angmom[i][k] += dL[k];
+    for (int k = 0; k < 3; k++) d->subtree_angmom[parent][k] += d->subtree_angmom[i][k];
+    for (int k = 0; k < 3; k++) { dx[k] = d->subtree_com[i][k] - d->subtree_com[parent][k]; dv[k] = (d->subtree_linvel[i][k] - d->subtree_linvel[parent][k]) * m->body_subtreemass[i]; }
+    cross(dL, dx, dv);
+    for (int k = 0; k < 3; k++) d->subtree_angmom[parent][k] += dL[k];
+  }
+}
+static void o_contactForce(const OModel *m, const OData *d, int id, double result[6]) { /* mj_contactForce + mju_decodePyramid [M] */
+  (void)m; zero(result, 6);
+  const OContact *con = &d->contact[id];
+  if (con->efc_address < 0 || con->efc_address >= d->nefc) return;
+  const double *f = d->efc_force + con->efc_address;
+  if (con->dim == 1) { result[0] = f[0]; return; }
+  for (int i = 0; i < 2 * (con->dim - 1); i++) result[0] += f[i];
+  for (int i = 1; i < con->dim; i++) result[i] = (f[2 * (i - 1)] - f[2 * (i - 1) + 1]) * con->friction[i - 1];
+}
+void osim_foot_forces(OSim *c, double cfrc[12]) { /* :1812-1854 */
+  const OModel *m = c->m; const OData *d = c->d; double ft[6], fg[3];
+  zero(cfrc, 12);
+  for (int i = 0; i < d->ncon; i++) {
+    int body1 = m->geom_bodyid[d->contact[i].geom1], body2 = m->geom_bodyid[d->contact[i].geom2];
+    for (int s = 0; s < 2; s++) {
+      int fb = s ? m->right_foot_body : m->left_foot_body;
+      if (body1 == fb || body2 == fb) {
+        o_contactForce(m, d, i, ft); mulMatTVec3(fg, d->contact[i].frame, ft);
+        for (int j = 0; j < 3; j++) cfrc[6 * s + j] += (body1 == fb) ? -fg[j] : fg[j];
+      }
+    }
+  }
+}
+void osim_heeltoe_forces(OSim *c, double toe_force[6], double heel_force[6]) { /* :1856-1898 */
+  const OModel *m = c->m; const OData *d = c->d; double ft[6], fg[3];
+  zero(toe_force, 6); zero(heel_force, 6);
+  for (int i = 0; i < d->ncon; i++) {
+    int body1 = m->geom_bodyid[d->contact[i].geom1], body2 = m->geom_bodyid[d->contact[i].geom2];
+    int lf = m->left_foot_body, rf = m->right_foot_body;
+    if (body1 == lf || body2 == lf || body1 == rf || body2 == rf) {
+      int sign = (body1 == lf || body1 == rf) ? -1 : 1, id = (body1 == rf || body2 == rf) ? 1 : 0, fb = id ? rf : lf;
+      o_contactForce(m, d, i, ft); mulMatTVec3(fg, d->contact[i].frame, ft);
+      double tw[3], hw[3], v[3]; /* site_xpos of the toe / heel sites (kinematics of the last sub-step) */
+      mulMatVec3(v, d->xmat[fb], m->toe_local[id]); for (int k = 0; k < 3; k++) tw[k] = d->xpos[fb][k] + v[k];
+      mulMatVec3(v, d->xmat[fb], m->heel_local[id]); for (int k = 0; k < 3; k++) hw[k] = d->xpos[fb][k] + v[k];
+      double td[2] = {tw[0] - d->contact[i].pos[0], tw[1] - d->contact[i].pos[1]}, hd[2] = {hw[0] - d->contact[i].pos[0], hw[1] - d->contact[i].pos[1]};
+      if (sqrt(td[0] * td[0] + td[1] * td[1]) < sqrt(hd[0] * hd[0] + hd[1] * hd[1])) for (int j = 0; j < 3; j++) toe_force[j + 3 * id] += sign * fg[j];
+      else for (int j = 0; j < 3; j++) heel_force[j + 3 * id] += sign * fg[j];
+    }
+  }
+}
+void osim_foot_positions(OSim *c, double cpos[6]) { /* :1608-1621 */
+  const OModel *m = c->m; const OData *d = c->d;
+  copyv(cpos, d->xpos[m->left_foot_body], 3); copyv(cpos + 3, d->xpos[m->right_foot_body], 3);
+  double off = sqrt(pow(0.01762, 2) + pow(0.05219, 2));
+  cpos[2] -= off; cpos[5] -= off;
+}
+void osim_foot_velocities(OSim *c, double cvel[12]) { /* :1623-1631: mj_comVel on the CURRENT qvel with the cdof of the last kinematics */
+  o_comVel(c->m, c->d);
+  copyv(cvel, c->d->cvel[c->m->left_foot_body], 6); copyv(cvel + 6, c->d->cvel[c->m->right_foot_body], 6);
+}
+void osim_cm_position(OSim *c, double cm_pos[3]) { o_fwdPosition(c->m, c->d); copyv(cm_pos, c->d->subtree_com[0], 3); }          /* :1633-1638 */
+void osim_cm_velocity(OSim *c, double cm_vel[3]) { o_fwdPosition(c->m, c->d); o_subtreeVel(c->m, c->d); copyv(cm_vel, c->d->subtree_linvel[0], 3); } /* :1640-1646 */
+void osim_angular_momentum(OSim *c, double L[3]) { o_fwdPosition(c->m, c->d); o_subtreeVel(c->m, c->d); copyv(L, c->d->subtree_angmom[0], 3); }       /* :1693-1699 */
+int osim_check_obstacle_collision(OSim *c) { /* :1586-1595 */
+  for (int i = 0; i < c->d->ncon; i++) if (c->m->geom_user[c->d->contact[i].geom1] == 1 || c->m->geom_user[c->d->contact[i].geom2] == 1) return 1;
+  return 0;
+}
+int osim_check_self_collision(OSim *c) { /* :1597-1606 */
+  for (int i = 0; i < c->d->ncon; i++) if (c->m->geom_user[c->d->contact[i].geom1] == 2 && c->m->geom_user[c->d->contact[i].geom2] == 2) return 1;
+  return 0;
+}
+int osim_geom_collision(OSim *c, int geom_group) { /* :1944-1961 */
+  for (int i = 0; i < c->d->ncon; i++) {
+    int g1 = c->m->geom_group[c->d->contact[i].geom1], g2 = c->m->geom_group[c->d->contact[i].geom2];
+    if ((g1 == 1 && g2 == geom_group) || (g2 == 1 && g1 == geom_group)) return 1;
+  }
+  return 0;
+}
+void osim_comvel(OSim *c) { o_comVel(c->m, c->d); }
+
 /* ---------------- accessors for the test harness (ctypes) */
 OModel *osim_model(OSim *c) { return c->m; }
 OData *osim_data(OSim *c) { return c->d; }
@@ -1169,7 +1301,7 @@ double *osim_array(OSim *c, const char *key, int *n) {
   ARR("sensordata", d->sensordata, 29) ARR("efc_pos", d->efc_pos, d->nefc) ARR("efc_R", d->efc_R, d->nefc) ARR("efc_D", d->efc_D, d->nefc)
   ARR("efc_aref", d->efc_aref, d->nefc) ARR("efc_b", d->efc_b, d->nefc) ARR("efc_force", d->efc_force, d->nefc) ARR("efc_vel", d->efc_vel, d->nefc)
   ARR("efc_diagApprox", d->efc_diagApprox, d->nefc) ARR("efc_J", d->efc_J, d->nefc * MAXV) ARR("efc_AR", d->efc_AR, d->nefc * d->nefc)
-  ARR("cacc", d->cacc, 6 * nb)
+  ARR("cacc", d->cacc, 6 * nb) ARR("subtree_linvel", d->subtree_linvel, 3 * nb) ARR("subtree_angmom", d->subtree_angmom, 3 * nb)
   *n = 0; return NULL;
 }
 int osim_int(OSim *c, const char *key) {

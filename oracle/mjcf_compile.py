@@ -203,7 +203,8 @@ def compile_mjcf(path):
                           friction=fl(a.get('friction', '1 0.005 0.0001')), solmix=float(a.get('solmix', 1)),
                           solref=fl(a.get('solref', '0.02 1')), solimp=np.concatenate([fl(a.get('solimp', '0.9 0.95 0.001')), [0.5, 2.0]])[:5],
                           margin=float(a.get('margin', 0)), gap=float(a.get('gap', 0)),
-                          mass=float(a['mass']) if 'mass' in a else None, hfid=hfid, cls=cls))
+                          mass=float(a['mass']) if 'mass' in a else None, hfid=hfid, cls=cls,
+                          user=int(float(a.get('user', '0').split()[0])), group=int(a.get('group', 0))))
         bodies[bid]['geoms'].append(len(geoms) - 1)
 
     def walk(node, parent, childclass):
@@ -412,6 +413,8 @@ def compile_mjcf(path):
     M['geom_condim'] = np.array([g['condim'] for g in geoms], dtype=np.int32)
     M['geom_priority'] = np.array([g['priority'] for g in geoms], dtype=np.int32)
     M['geom_hfid'] = np.array([g['hfid'] for g in geoms], dtype=np.int32)
+    M['geom_user'] = np.array([g['user'] for g in geoms], dtype=np.int32)     # nuser_geom = 1: 1 obstacle, 2 robot collision geom
+    M['geom_group'] = np.array([g['group'] for g in geoms], dtype=np.int32)
     for k in ('pos', 'quat', 'size', 'friction', 'solref', 'solimp'):
         M['geom_' + k] = np.array([g[k] for g in geoms])
     for k in ('rbound', 'solmix', 'margin', 'gap'):

@@ -75,6 +75,14 @@ def load(ref=False):
     L.osim_hfield_data.restype = C.POINTER(C.c_float)
     L.osim_hfield_data.argtypes = [C.c_void_p]
     L.osim_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int]
+    for n in ('osim_foot_forces', 'osim_foot_positions', 'osim_foot_velocities', 'osim_cm_position', 'osim_cm_velocity', 'osim_angular_momentum'):
+        getattr(L, n).argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        getattr(L, n).restype = None
+    L.osim_heeltoe_forces.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.osim_heeltoe_forces.restype = None
+    L.osim_check_obstacle_collision.argtypes = [C.c_void_p]
+    L.osim_check_self_collision.argtypes = [C.c_void_p]
+    L.osim_geom_collision.argtypes = [C.c_void_p, C.c_int]
     L.o_pd_input_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
     L.o_core_sim_step.argtypes = [C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_double)]
     return L
@@ -131,6 +139,44 @@ class OracleSim:
             out.append(dict(pos=np.array(buf[0:3]), frame=np.array(buf[3:12]).reshape(3, 3), dist=buf[12], geom1=g[0], geom2=g[1], dim=g[2]))
             i += 1
         return out
+
+    # ---- derived-quantity queries, named like the reference functions they restate (src/cassiemujoco.c:1586-1961)
+    def _vec(self, fn, n):
+        buf = (C.c_double * n)()
+        getattr(self.L, fn)(self.h, buf)
+        return np.array(buf[:])
+
+    def foot_forces(self):
+        return self._vec('osim_foot_forces', 12)
+
+    def heeltoe_forces(self):
+        t, h = (C.c_double * 6)(), (C.c_double * 6)()
+        self.L.osim_heeltoe_forces(self.h, t, h)
+        return np.array(t[:]), np.array(h[:])
+
+    def foot_positions(self):
+        return self._vec('osim_foot_positions', 6)
+
+    def foot_velocities(self):
+        return self._vec('osim_foot_velocities', 12)
+
+    def cm_position(self):
+        return self._vec('osim_cm_position', 3)
+
+    def cm_velocity(self):
+        return self._vec('osim_cm_velocity', 3)
+
+    def angular_momentum(self):
+        return self._vec('osim_angular_momentum', 3)
+
+    def check_obstacle_collision(self):
+        return bool(self.L.osim_check_obstacle_collision(self.h))
+
+    def check_self_collision(self):
+        return bool(self.L.osim_check_self_collision(self.h))
+
+    def geom_collision(self, group):
+        return bool(self.L.osim_geom_collision(self.h, group))
 
     def efc_J(self):
         n, nv, mv = self.get_int('nefc'), self.nv, self.get_int('MAXV')

@@ -13,8 +13,8 @@ using namespace cassie;
 
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX]; int counters[8];
-  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
+  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX], aux[AUX_W]; int counters[8];
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.aux = aux; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
@@ -25,12 +25,13 @@ template <typename real> struct Emu {
     init_env_rows(hm, qpos.data(), qv.data(), qa.data(), cst, ism.data(), xfrc);
     for (int i = 0; i < 32; i++) { qvel[i] = qv[i]; qacc_ws[i] = qa[i]; xqvel[i] = 0; xqacc_ws[i] = 0; }
     for (int i = 0; i < QPOS_W_XB; i++) sm[S_QPOS + i] = qpos[i];
-    std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters);
+    std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters); std::memset(aux, 0, sizeof aux);
     forward();
     return true;
   }
-  void forward() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, 1, true); }
-  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, false); }
+  void forward() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, 1, 1); }
+  void query() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, 1, 2); }
+  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, 0); }
 };
 
 struct Handle { int fp32; Emu<float> f; Emu<double> d; };
@@ -49,6 +50,7 @@ void emu_step(void *p, const double *pd50, int nticks) {
   else { for (int i = 0; i < 50; i++) h->d.pd[i] = pd50[i]; h->d.step(nticks); }
 }
 void emu_set_hfield(void *p, const float *data, int n) { Handle *h = (Handle *)p; std::vector<float> &dst = h->fp32 ? h->f.hfield : h->d.hfield; for (int i = 0; i < n && i < (int)dst.size(); i++) dst[i] = data[i]; }
+void emu_query(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.query(); else h->d.query(); }
 void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward(); else h->d.forward(); }
 // generic get/set of named state as doubles.  names: qpos qvel qacc_ws cst obs dbg xfrc ; ints: dfilt counters
 int emu_get(void *p, const char *name, double *out, int n) {
@@ -56,7 +58,7 @@ int emu_get(void *p, const char *name, double *out, int n) {
 #define GET(T, E) { const T *src = nullptr; int cnt = 0; \
   if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W_XB; } else if (k == "xqvel") { src = E.xqvel; cnt = 6; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
   else if (k == "cst") { src = E.cst; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
-  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } \
+  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } else if (k == "aux") { src = E.aux; cnt = AUX_W; } \
   if (src) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) out[i] = (double)src[i]; return cnt; } \
   if (k == "dfilt") { int c2 = DFILT_W < n ? DFILT_W : n; for (int i = 0; i < c2; i++) out[i] = E.ism[i]; return c2; } \
   if (k == "counters") { int c2 = 8 < n ? 8 : n; for (int i = 0; i < c2; i++) out[i] = E.counters[i]; return c2; } }

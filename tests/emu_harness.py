@@ -31,6 +31,7 @@ def load():
     L.emu_free.argtypes = [C.c_void_p]
     L.emu_step.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
     L.emu_forward.argtypes = [C.c_void_p]
+    L.emu_query.argtypes = [C.c_void_p]
     L.emu_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
     L.emu_set.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
     return L
@@ -65,6 +66,9 @@ class EmuSim:
 
     def forward(self):
         self.L.emu_forward(self.h)
+
+    def query(self):
+        self.L.emu_query(self.h)
 
 
 def _emu_set_hfield(self, data):

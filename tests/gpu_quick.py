@@ -15,6 +15,7 @@ for prec, n, nt in cfgs:
     jit = 0.05 if os.environ.get('JITTER') else 0.0
     b.set_pd(P.pd_rows(n, pTarget=np.array(PD_TARGET) + rng.uniform(-jit, jit, (n, 10)), pGain=PD_PGAIN, dGain=PD_DGAIN))
     b.set_stream(torch.cuda.current_stream().cuda_stream)
+    if os.environ.get('AUX'): b.enable_aux()
     for _ in range(3): b.step(nt)
     b.sync()
     reps = max(4, 200 // nt)
