@@ -160,6 +160,38 @@ def lib():
     L.cassie_batch_query.restype = ci
     L.cassie_batch_row_width.argtypes = [vp, C.c_char_p]
     L.cassie_batch_row_width.restype = ci
+    for n in ('cassie_batch_nbody', 'cassie_batch_ngeom'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = ci
+    for what in ('body_mass', 'body_ipos', 'dof_damping', 'geom_friction'):
+        for op in ('set', 'get'):
+            f = getattr(L, 'cassie_batch_%s_%s' % (op, what))
+            f.argtypes = [vp, cd]
+            f.restype = ci
+    L.cassie_batch_set_const.argtypes = [vp, C.c_void_p, ci]
+    L.cassie_batch_set_const.restype = ci
+    L.cassie_sim_params.argtypes = [vp, C.POINTER(ci)]
+    for n in ('cassie_sim_dof_damping', 'cassie_sim_body_mass', 'cassie_sim_body_ipos', 'cassie_sim_geom_friction'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = cd
+    for n in ('cassie_sim_set_dof_damping', 'cassie_sim_set_body_mass', 'cassie_sim_set_body_ipos', 'cassie_sim_set_geom_friction'):
+        getattr(L, n).argtypes = [vp, cd]
+        getattr(L, n).restype = None
+    for n in ('cassie_sim_set_dof_name_damping', 'cassie_sim_set_body_name_ipos', 'cassie_sim_set_geom_name_friction'):
+        getattr(L, n).argtypes = [vp, C.c_char_p, cd]
+        getattr(L, n).restype = None
+    for n in ('cassie_sim_get_dof_name_damping', 'cassie_sim_get_body_name_ipos', 'cassie_sim_get_geom_name_friction'):
+        getattr(L, n).argtypes = [vp, C.c_char_p]
+        getattr(L, n).restype = cd
+    L.cassie_sim_get_joint_num_dof.argtypes = [vp, C.c_char_p]
+    L.cassie_sim_get_joint_num_dof.restype = ci
+    L.cassie_sim_set_body_name_mass.argtypes = [vp, C.c_char_p, C.c_double]
+    L.cassie_sim_set_body_name_mass.restype = None
+    L.cassie_sim_get_body_name_mass.argtypes = [vp, C.c_char_p]
+    L.cassie_sim_get_body_name_mass.restype = C.c_double
+    for n in ('cassie_sim_set_const', 'cassie_sim_just_set_const'):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = None
     for n in ('cassie_sim_foot_forces', 'cassie_sim_foot_positions', 'cassie_sim_foot_velocities', 'cassie_sim_cm_position', 'cassie_sim_cm_velocity',
               'cassie_sim_angular_momentum'):
         getattr(L, n).argtypes = [vp, cd]
@@ -282,6 +314,29 @@ class CassieBatch:
             raise RuntimeError(_last_error())
         return out
 
+    # ---- per-environment model constants (domain randomisation; reference: example/cassiemujoco.py:517-610 on one env)
+    def _model_width(self, what):
+        nb, ng = self.L.cassie_batch_nbody(self.h), self.L.cassie_batch_ngeom(self.h)
+        return dict(body_mass=nb, body_ipos=3 * nb, dof_damping=self.nv, geom_friction=3 * ng)[what]
+
+    def set_model(self, what, rows):
+        """what in body_mass [n, nbody], body_ipos [n, 3 nbody], dof_damping [n, nv], geom_friction [n, 3 ngeom] (reference numbering)."""
+        a = np.ascontiguousarray(rows, dtype=np.float64).reshape(self.n, self._model_width(what))
+        if getattr(self.L, 'cassie_batch_set_' + what)(self.h, self._dp(a)) != 0:
+            raise RuntimeError(_last_error())
+
+    def get_model(self, what):
+        out = np.zeros((self.n, self._model_width(what)))
+        if getattr(self.L, 'cassie_batch_get_' + what)(self.h, self._dp(out)) != 0:
+            raise RuntimeError(_last_error())
+        return out
+
+    def set_const(self, mask=None, reset_state=False):
+        """mj_setConst on the device for the masked environments (all if None); reset_state=True adds cassie_sim_set_const's state reset."""
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        if self.L.cassie_batch_set_const(self.h, None if m is None else m.ctypes.data_as(C.c_void_p), 1 if reset_state else 0) != 0:
+            raise RuntimeError(_last_error())
+
     def query(self):
         """refresh the centre-of-mass slots of the aux rows for the CURRENT state (nothing else is written)."""
         if self.L.cassie_batch_query(self.h) != 0:
@@ -392,6 +447,77 @@ class CassieSim:
 
     def full_reset(self):
         self.L.cassie_sim_full_reset(self.c)
+
+    # ---- model constants, named as in the reference wrapper (example/cassiemujoco.py:380-610)
+    def params(self):
+        p = (C.c_int * 6)()
+        self.L.cassie_sim_params(self.c, p)
+        return list(p)
+
+    def _marr(self, fn, n):
+        return np.array(fn(self.c)[:n])
+
+    def get_dof_damping(self, name=None):
+        if name:
+            return np.array(self.L.cassie_sim_get_dof_name_damping(self.c, name.encode())[:self.L.cassie_sim_get_joint_num_dof(self.c, name.encode())])
+        return self._marr(self.L.cassie_sim_dof_damping, self.nv)
+
+    def get_body_mass(self, name=None):
+        if name:
+            return self.L.cassie_sim_get_body_name_mass(self.c, name.encode())
+        return self._marr(self.L.cassie_sim_body_mass, self.params()[4])
+
+    def get_body_ipos(self, name=None):
+        if name:
+            return np.array(self.L.cassie_sim_get_body_name_ipos(self.c, name.encode())[:3])
+        return self._marr(self.L.cassie_sim_body_ipos, 3 * self.params()[4])
+
+    def get_geom_friction(self, name=None):
+        if name:
+            return np.array(self.L.cassie_sim_get_geom_name_friction(self.c, name.encode())[:3])
+        ng = self.params()[5]
+        return self._marr(self.L.cassie_sim_geom_friction, 3 * ng).reshape(ng, 3)
+
+    @staticmethod
+    def _carr(data):
+        a = np.ascontiguousarray(data, dtype=np.float64).ravel()
+        return (C.c_double * a.size)(*a)
+
+    def set_dof_damping(self, data, name=None):
+        if name:
+            self.L.cassie_sim_set_dof_name_damping(self.c, name.encode(), self._carr(np.atleast_1d(data)))
+        else:
+            assert len(data) == self.nv
+            self.L.cassie_sim_set_dof_damping(self.c, self._carr(data))
+
+    def set_body_mass(self, data, name=None):
+        if name is None:
+            assert len(data) == self.params()[4]
+            self.L.cassie_sim_set_body_mass(self.c, self._carr(data))
+        else:
+            self.L.cassie_sim_set_body_name_mass(self.c, name.encode(), float(data))
+
+    def set_body_ipos(self, data, name=None):
+        if name:
+            assert len(data) == 3
+            self.L.cassie_sim_set_body_name_ipos(self.c, name.encode(), self._carr(data))
+        else:
+            assert len(data) == 3 * self.params()[4]
+            self.L.cassie_sim_set_body_ipos(self.c, self._carr(data))
+
+    def set_geom_friction(self, data, name=None):
+        if name is None:
+            assert np.size(data) == 3 * self.params()[5]
+            self.L.cassie_sim_set_geom_friction(self.c, self._carr(data))
+        else:
+            assert len(data) == 3
+            self.L.cassie_sim_set_geom_name_friction(self.c, name.encode(), self._carr(data))
+
+    def set_const(self):
+        self.L.cassie_sim_set_const(self.c)
+
+    def just_set_const(self):
+        self.L.cassie_sim_just_set_const(self.c)
 
     # ---- read-only queries, named as in the reference wrapper (example/cassiemujoco.py:214-306, 815-819)
     def _vec(self, fn, n):

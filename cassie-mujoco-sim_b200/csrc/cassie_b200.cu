@@ -23,7 +23,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux; int *dfilt, *counters, *ticket; const float *hfield; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,7 +48,7 @@ template <typename real> __host__ __device__ constexpr size_t model_bytes() { re
 template <typename real> __host__ __device__ constexpr size_t warp_bytes(int ystride) { return ((size_t)scratch_reals(ystride) * sizeof(real) + 127) / 128 * 128; }
 
 // mode 0: step nticks; mode 1: mj_forward only
-template <typename real>
+template <typename real, bool DR>
 __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *__restrict__ gmodel, EnvArrays<real> A, int nticks, int mode) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
@@ -65,13 +65,14 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     if (l == 0) env = atomicAdd(A.ticket, 1);
     env = __shfl_sync(0xffffffffu, env, 0);
     if (env >= A.n) break;
+    if (A.mask && !A.mask[env]) continue;   // masked launches (reset / set_const of a subset)
     // warm the L2/L1 path of the rows that are addressed in place later (controller state, PD row, FIR taps)
     if (l < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cst + (size_t)env * CST_W + 32 * l));
     else if (l < 9) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dfilt + (size_t)env * DFILT_W + 32 * (l - 6)));
     else if (l < 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pd + (size_t)env * PD_W + 32 * (l - 9)));
     else if (l == 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.xfrc + (size_t)env * XFRC_W));
     // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
-    for (int i = l; i < qw; i += 32) sm[S_QPOS + i] = A.qpos[(size_t)env * qw + i];
+    for (int i = l; i < qw; i += 32) sm[S_QPOS + i] = (mode == 3) ? cm.qpos0[i] : A.qpos[(size_t)env * qw + i];   // set_const works at the reference configuration
     real qvel = A.qvel[(size_t)env * vw + l], qacc_ws = A.qacc_ws[(size_t)env * vw + l], xqvel = 0, xqacc_ws = 0;
     if (A.xb >= 0 && l < 6) { xqvel = A.qvel[(size_t)env * vw + 32 + l]; xqacc_ws = A.qacc_ws[(size_t)env * vw + 32 + l]; }
     __syncwarp();
@@ -79,10 +80,10 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr;
-    step_env(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
+    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr;
+    step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
-    if (mode == 2) continue;   // query: nothing but the aux row is written
+    if (mode >= 2) continue;   // query / set_const: only the aux row / the constant row is written
     for (int i = l; i < qw; i += 32) A.qpos[(size_t)env * qw + i] = sm[S_QPOS + i];
     A.qvel[(size_t)env * vw + l] = qvel; A.qacc_ws[(size_t)env * vw + l] = qacc_ws;
     if (A.xb >= 0 && l < 6) { A.qvel[(size_t)env * vw + 32 + l] = xqvel; A.qacc_ws[(size_t)env * vw + 32 + l] = xqacc_ws; }
@@ -163,6 +164,13 @@ __global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<re
   if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// rows of the selected environments <- one template row (masked reset / set_const)
+template <typename T>
+__global__ void fill_rows_kernel(T *__restrict__ dst, const T *__restrict__ row, int w, const unsigned char *__restrict__ mask, int n) {
+  const size_t total = (size_t)n * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) { const size_t e = i / w; if (!mask || mask[e]) dst[i] = row[i - e * w]; }
+}
+
 // ------------------------------------------------------------------ host side
 struct BatchBase {
   virtual ~BatchBase() {}
@@ -181,6 +189,9 @@ struct BatchBase {
   virtual bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) = 0;
   virtual bool set_hfield(const float *data, int n_terrains) = 0;
   virtual bool enable_aux(bool on) = 0;
+  virtual bool set_model_rows(const char *what, const double *rows, int width) = 0;   // per-env model constants (domain randomisation)
+  virtual bool get_model_rows(const char *what, double *rows, int width) = 0;
+  virtual bool set_const(const unsigned char *mask, bool reset_state) = 0;
   virtual bool has_aux() const = 0;
   bool sync() { CUDA_OK(cudaStreamSynchronize(stream)); return true; }
 };
@@ -189,11 +200,11 @@ template <typename real> struct Batch : BatchBase {
   DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0; int resident_ctas = 1, QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr;   // pinned staging for the AoS entry point
-  float *d_hfield = nullptr;
+  float *d_hfield = nullptr; unsigned char *d_mask = nullptr; DevModel<real> h_model_copy{}; int geom_dev[256]; void *d_row = nullptr;
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(d_mask); cudaFree(d_row);
     if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -204,6 +215,7 @@ template <typename real> struct Batch : BatchBase {
     if (info.unsupported_pairs) fprintf(stderr, "cassie_b200: note: %d candidate geom pairs involve box/hfield geoms that this build does not collide (skipped)\n", info.unsupported_pairs);
     CUDA_OK(cudaMalloc(&d_model, model_bytes<real>()));
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
+    h_model_copy = *hmodel; memcpy(geom_dev, info.geom_dev, sizeof geom_dev);
     const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
     A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0;
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
@@ -231,8 +243,10 @@ template <typename real> struct Batch : BatchBase {
     }
     if (wpb < 1 || wpb > 16 || model_bytes<real>() + (size_t)wpb * warp_bytes<real>(hmodel_ystride) > (size_t)dev_smem) { set_err("not enough shared memory per block"); return false; }
     smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>(hmodel_ystride);
-    CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { int per_sm = 0, sms = 0; CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real>, 32 * wpb, smem));
+    CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int per_sm = 0, per_sm_dr = 0, sms = 0; CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real, false>, 32 * wpb, smem));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dr, cassie_step_kernel<real, true>, 32 * wpb, smem)); if (per_sm_dr < per_sm) per_sm = per_sm_dr;
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)); resident_ctas = per_sm * sms; if (resident_ctas < 1) resident_ctas = 1; }
     return reset(nullptr);
   }
@@ -247,18 +261,73 @@ template <typename real> struct Batch : BatchBase {
       CUDA_OK(cudaMemcpyAsync(A.dfilt, ibuf.data(), sizeof(int) * n * DFILT_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
       return step(0, 1);
     }
-    // masked reset: rewrite the selected rows, then forward everything (forward is idempotent for untouched envs except
-    // that their sensordata is refreshed from their current state, which is what mj_forward would give)
-    for (int e = 0; e < n; e++) if (mask[e]) {
-      CUDA_OK(cudaMemcpyAsync(A.qpos + (size_t)e * QW, qpos.data(), sizeof(real) * QW, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.qvel + (size_t)e * VW, qvel.data(), sizeof(real) * VW, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.qacc_ws + (size_t)e * VW, qa.data(), sizeof(real) * VW, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.cst + (size_t)e * CST_W, cst.data(), sizeof(real) * CST_W, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.xfrc + (size_t)e * XFRC_W, xf.data(), sizeof(real) * XFRC_W, cudaMemcpyHostToDevice, stream));
-      CUDA_OK(cudaMemcpyAsync(A.dfilt + (size_t)e * DFILT_W, df.data(), sizeof(int) * DFILT_W, cudaMemcpyHostToDevice, stream));
-    }
-    CUDA_OK(cudaStreamSynchronize(stream));
-    return step(0, 1);
+    // masked reset: rewrite the selected rows, then mj_forward for exactly those environments
+    if (!upload_mask(mask)) return false;
+    if (!fill_masked(A.qpos, qpos.data(), QW) || !fill_masked(A.qvel, qvel.data(), VW) || !fill_masked(A.qacc_ws, qa.data(), VW) || !fill_masked(A.cst, cst.data(), CST_W) ||
+        !fill_masked(A.xfrc, xf.data(), XFRC_W) || !fill_masked(A.dfilt, df.data(), DFILT_W)) return false;
+    return step_masked(1);
+  }
+  bool upload_mask(const unsigned char *mask) {
+    if (!d_mask) CUDA_OK(cudaMalloc(&d_mask, n));
+    CUDA_OK(cudaMemcpyAsync(d_mask, mask, n, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  template <typename T> bool fill_masked(T *dst, const T *row, int w) {   // uses d_mask
+    if (!d_row) CUDA_OK(cudaMalloc(&d_row, 4096));
+    CUDA_OK(cudaMemcpyAsync(d_row, row, sizeof(T) * w, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    fill_rows_kernel<T><<<256, 256, 0, stream>>>(dst, (const T *)d_row, w, d_mask, n);
+    CUDA_OK(cudaGetLastError()); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  bool step_masked(int mode) { A.mask = d_mask; const bool ok = step(0, mode); A.mask = nullptr; return ok; }
+  // ---- per-environment model constants (domain randomisation; reference setters src/cassiemujoco.c:1303-1436)
+  bool ensure_cenv() {
+    if (A.cenv) return true;
+    CUDA_OK(cudaSetDevice(device));
+    std::vector<real> row(CE_W), all((size_t)n * CE_W); init_cenv_row(h_model_copy, row.data());
+    for (int e = 0; e < n; e++) memcpy(&all[(size_t)e * CE_W], row.data(), sizeof(real) * CE_W);
+    CUDA_OK(cudaMalloc(&A.cenv, sizeof(real) * n * CE_W));
+    CUDA_OK(cudaMemcpyAsync(A.cenv, all.data(), sizeof(real) * n * CE_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  int cenv_slot(const char *what, int i, int &width) const { return cassie::cenv_slot(hm, h_model_copy.nv, geom_dev, what, i, width); }
+  bool set_model_rows(const char *what, const double *rows, int width) override {
+    int w = 0; cenv_slot(what, 0, w);
+    if (w < 0 || w != width) { set_err(std::string("set_model_rows: unknown array or wrong width for ") + what); return false; }
+    if (!strcmp(what, "body_ipos") && h_model_copy.xb >= 0) for (int e = 0; e < n; e++) for (int k = 0; k < 3; k++)
+      if (rows[(size_t)e * w + 3 * h_model_copy.xb + k] != hm.body_ipos[3 * h_model_copy.xb + k]) { set_err("body_ipos of the extra free body cannot be changed (its inertial frame must stay its body frame)"); return false; }
+    if (!ensure_cenv()) return false;
+    std::vector<real> all((size_t)n * CE_W);
+    CUDA_OK(cudaMemcpyAsync(all.data(), A.cenv, sizeof(real) * n * CE_W, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    for (int e = 0; e < n; e++) for (int i = 0; i < w; i++) { int ww; const int sl = cenv_slot(what, i, ww); if (sl >= 0) all[(size_t)e * CE_W + sl] = (real)rows[(size_t)e * w + i]; }
+    CUDA_OK(cudaMemcpyAsync(A.cenv, all.data(), sizeof(real) * n * CE_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  bool get_model_rows(const char *what, double *rows, int width) override {
+    int w = 0; cenv_slot(what, 0, w);
+    if (w < 0 || w != width) { set_err(std::string("get_model_rows: unknown array or wrong width for ") + what); return false; }
+    if (!ensure_cenv()) return false;
+    std::vector<real> all((size_t)n * CE_W);
+    CUDA_OK(cudaMemcpyAsync(all.data(), A.cenv, sizeof(real) * n * CE_W, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    const std::vector<double> *src = !strcmp(what, "geom_friction") ? &hm.geom_friction : nullptr;
+    for (int e = 0; e < n; e++) for (int i = 0; i < w; i++) { int ww; const int sl = cenv_slot(what, i, ww); rows[(size_t)e * w + i] = sl >= 0 ? (double)all[(size_t)e * CE_W + sl] : (src ? (*src)[i] : 0.0); }
+    return true;
+  }
+  // mj_setConst for the selected environments on the device (mode 3), optionally followed by the state reset cassie_sim_set_const performs
+  bool set_const(const unsigned char *mask, bool reset_state) override {
+    if (!ensure_cenv()) return false;
+    std::vector<unsigned char> ones; if (!mask) { ones.assign(n, 1); mask = ones.data(); }
+    if (!upload_mask(mask) || !step_masked(3)) return false;
+    if (!reset_state) return sync();
+    // src/cassiemujoco.c:955-971: qpos <- the init constants, qvel <- 0, time <- 0, mj_forward (filters, delay line, cassie_out keep their values)
+    std::vector<real> qpos(QPOS_W_XB), qvel(QVEL_W_XB), qa(QVEL_W_XB), cst(CST_W), xf(XFRC_W); std::vector<int> df(DFILT_W);
+    init_env_rows(hm, qpos.data(), qvel.data(), qa.data(), cst.data(), df.data(), xf.data());
+    if (!fill_masked(A.qpos, qpos.data(), QW) || !fill_masked(A.qvel, qvel.data(), VW)) return false;
+    { std::vector<real> all((size_t)n * CST_W);
+      CUDA_OK(cudaMemcpyAsync(all.data(), A.cst, sizeof(real) * n * CST_W, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+      for (int e = 0; e < n; e++) if (mask[e]) all[(size_t)e * CST_W + CS_TIME] = 0;
+      CUDA_OK(cudaMemcpyAsync(A.cst, all.data(), sizeof(real) * n * CST_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream)); }
+    return step_masked(1) && sync();
   }
   bool set_pd(const double *pd) override {
     h_tmp.resize((size_t)n * PD_W);
@@ -325,7 +394,8 @@ template <typename real> struct Batch : BatchBase {
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
     int grid = (n + wpb - 1) / wpb; if (grid > resident_ctas) grid = resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
-    cassie_step_kernel<real><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);
+    if (A.cenv || A.aux) cassie_step_kernel<real, true><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
+    else cassie_step_kernel<real, false><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);
     launches++;
     CUDA_OK(cudaGetLastError());
     return true;
@@ -408,7 +478,8 @@ template <typename real> struct Batch : BatchBase {
 // ====================================================================== C-ABI
 using namespace cassie;
 struct cassie_batch { BatchBase *impl; std::vector<double> obs, radio; };
-struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev, aux[AUX_W]; std::vector<float> hfield, hfield_dev; };
+struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev, aux[AUX_W]; std::vector<float> hfield, hfield_dev;
+  std::vector<double> m_mass, m_ipos, m_damp, m_fric, m_mass_dev, m_ipos_dev, m_damp_dev, m_fric_dev; };   // host mirrors of the model arrays handed out as borrowed pointers
 
 static std::mutex g_model_mutex;
 static std::string g_model_path;   // what cassie_mujoco_init cached (the reference caches the parsed model, src/cassiemujoco.c:48-59)
@@ -453,6 +524,17 @@ void cassie_batch_get_qvel(cassie_batch_t *b, double *out) { b->impl->get("qvel"
 void cassie_batch_set_qvel(cassie_batch_t *b, const double *in) { b->impl->set("qvel", in); }
 void cassie_batch_get_time(cassie_batch_t *b, double *out) { b->impl->get("time", out); }
 void cassie_batch_get_obs(cassie_batch_t *b, double *out) { b->impl->get("obs", out); }
+int cassie_batch_nbody(const cassie_batch_t *b) { return b->impl->hm.nbody; }
+int cassie_batch_ngeom(const cassie_batch_t *b) { return b->impl->hm.ngeom; }
+int cassie_batch_set_body_mass(cassie_batch_t *b, const double *mass) { return b->impl->set_model_rows("body_mass", mass, b->impl->hm.nbody) ? 0 : -1; }
+int cassie_batch_set_body_ipos(cassie_batch_t *b, const double *ipos) { return b->impl->set_model_rows("body_ipos", ipos, 3 * b->impl->hm.nbody) ? 0 : -1; }
+int cassie_batch_set_dof_damping(cassie_batch_t *b, const double *damp) { return b->impl->set_model_rows("dof_damping", damp, b->impl->hm.nv) ? 0 : -1; }
+int cassie_batch_set_geom_friction(cassie_batch_t *b, const double *fric) { return b->impl->set_model_rows("geom_friction", fric, 3 * b->impl->hm.ngeom) ? 0 : -1; }
+int cassie_batch_get_body_mass(cassie_batch_t *b, double *mass) { return b->impl->get_model_rows("body_mass", mass, b->impl->hm.nbody) ? 0 : -1; }
+int cassie_batch_get_body_ipos(cassie_batch_t *b, double *ipos) { return b->impl->get_model_rows("body_ipos", ipos, 3 * b->impl->hm.nbody) ? 0 : -1; }
+int cassie_batch_get_dof_damping(cassie_batch_t *b, double *damp) { return b->impl->get_model_rows("dof_damping", damp, b->impl->hm.nv) ? 0 : -1; }
+int cassie_batch_get_geom_friction(cassie_batch_t *b, double *fric) { return b->impl->get_model_rows("geom_friction", fric, 3 * b->impl->hm.ngeom) ? 0 : -1; }
+int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int reset_state) { return b->impl->set_const(mask, reset_state != 0) ? 0 : -1; }
 int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
 int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
 int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }
@@ -495,6 +577,10 @@ static void sim_push(cassie_sim_t *c) {  // upload whatever the caller wrote thr
   if (memcmp(c->qvel_dev, c->qvel, sizeof c->qvel)) c->b->impl->set("qvel", c->qvel);
   if (c->time_dev != c->time) c->b->impl->set("time", &c->time);
   if (!c->hfield.empty() && c->hfield != c->hfield_dev) { c->b->impl->set_hfield(c->hfield.data(), 1); c->hfield_dev = c->hfield; }
+  if (c->m_mass != c->m_mass_dev) { cassie_batch_set_body_mass(c->b, c->m_mass.data()); c->m_mass_dev = c->m_mass; }
+  if (c->m_ipos != c->m_ipos_dev) { cassie_batch_set_body_ipos(c->b, c->m_ipos.data()); c->m_ipos_dev = c->m_ipos; }
+  if (c->m_damp != c->m_damp_dev) { cassie_batch_set_dof_damping(c->b, c->m_damp.data()); c->m_damp_dev = c->m_damp; }
+  if (c->m_fric != c->m_fric_dev) { cassie_batch_set_geom_friction(c->b, c->m_fric.data()); c->m_fric_dev = c->m_fric; }
 }
 cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   std::string path;
@@ -504,6 +590,8 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b;
   b->impl->enable_aux(true); b->impl->step(0, 1);   // a single environment always carries the derived-quantity row; populate it like the sensordata
   sim_pull(c);
+  { const HostModel &hm = b->impl->hm; c->m_mass = hm.body_mass; c->m_ipos = hm.body_ipos; c->m_damp = hm.dof_damping; c->m_fric = hm.geom_friction;
+    c->m_mass_dev = c->m_mass; c->m_ipos_dev = c->m_ipos; c->m_damp_dev = c->m_damp; c->m_fric_dev = c->m_fric; }
   if (b->impl->hm.nhfield) { c->hfield.assign((size_t)b->impl->hm.hfield_nrow[0] * b->impl->hm.hfield_ncol[0], 0.0f); c->hfield_dev = c->hfield; }
   return c;
 }
@@ -539,6 +627,30 @@ void cassie_sim_angular_momentum(const cassie_sim_t *c, double Lcm[3]) { sim_que
 bool cassie_sim_check_obstacle_collision(const cassie_sim_t *c) { return sim_aux(c)[AX_OBSTACLE] != 0; }
 bool cassie_sim_check_self_collision(const cassie_sim_t *c) { return sim_aux(c)[AX_SELF] != 0; }
 bool cassie_sim_geom_collision(const cassie_sim_t *c, int geom_group) { return geom_group >= 0 && geom_group < 16 && (((int)sim_aux(c)[AX_GROUPMASK] >> geom_group) & 1); }
+// ---- model constants (domain randomisation).  include/cassiemujoco.h / src/cassiemujoco.c:1303-1436: the reference hands out pointers into
+// its private mjModel copy; here they point into host mirrors that are uploaded before the next step / query / set_const.
+void cassie_sim_params(cassie_sim_t *c, int *params) { const HostModel &hm = c->b->impl->hm; params[0] = hm.nq; params[1] = hm.nv; params[2] = hm.nu; params[3] = 29; params[4] = hm.nbody; params[5] = hm.ngeom; }
+double *cassie_sim_dof_damping(cassie_sim_t *c) { return c->m_damp.data(); }
+double *cassie_sim_body_mass(cassie_sim_t *c) { return c->m_mass.data(); }
+double *cassie_sim_body_ipos(cassie_sim_t *c) { return c->m_ipos.data(); }
+double *cassie_sim_geom_friction(cassie_sim_t *c) { return c->m_fric.data(); }
+void cassie_sim_set_dof_damping(cassie_sim_t *c, double *damp) { for (size_t i = 0; i < c->m_damp.size(); i++) c->m_damp[i] = damp[i]; }
+void cassie_sim_set_body_mass(cassie_sim_t *c, double *mass) { for (size_t i = 0; i < c->m_mass.size(); i++) c->m_mass[i] = mass[i]; }
+void cassie_sim_set_body_ipos(cassie_sim_t *c, double *ipos) {   // the reference indexes its argument with [i + j], not [3 i + j] (:1386-1393); kept
+  const int nb = (int)c->m_mass.size(); for (int i = 0; i < nb; i++) for (int j = 0; j < 3; j++) c->m_ipos[3 * i + j] = ipos[i + j]; }
+void cassie_sim_set_geom_friction(cassie_sim_t *c, double *fric) { for (size_t i = 0; i < c->m_fric.size(); i++) c->m_fric[i] = fric[i]; }
+void cassie_sim_set_body_name_mass(cassie_sim_t *c, const char *name, double mass) { const int id = c->b->impl->hm.body_id(name ? name : ""); if (id >= 0) c->m_mass[id] = mass; }
+double cassie_sim_get_body_name_mass(cassie_sim_t *c, const char *name) { const int id = c->b->impl->hm.body_id(name ? name : ""); return id >= 0 ? c->m_mass[id] : 0.0; }
+void cassie_sim_set_body_name_ipos(cassie_sim_t *c, const char *name, double *ipos) { const int id = c->b->impl->hm.body_id(name ? name : ""); if (id >= 0) for (int k = 0; k < 3; k++) c->m_ipos[3 * id + k] = ipos[k]; }
+double *cassie_sim_get_body_name_ipos(cassie_sim_t *c, const char *name) { const int id = c->b->impl->hm.body_id(name ? name : ""); return id >= 0 ? &c->m_ipos[3 * id] : nullptr; }
+int cassie_sim_get_joint_num_dof(cassie_sim_t *c, const char *name) { const HostModel &hm = c->b->impl->hm; const int j = hm.joint_id(name ? name : ""); if (j < 0) return 0; return hm.jnt_type[j] == JNT_FREE ? 6 : (hm.jnt_type[j] == JNT_BALL ? 3 : 1); }
+void cassie_sim_set_dof_name_damping(cassie_sim_t *c, const char *name, double *damp) { const HostModel &hm = c->b->impl->hm; const int j = hm.joint_id(name ? name : ""); if (j < 0) return; const int nd = cassie_sim_get_joint_num_dof(c, name); for (int i = 0; i < nd; i++) c->m_damp[hm.jnt_dofadr[j] + i] = damp[i]; }
+double *cassie_sim_get_dof_name_damping(cassie_sim_t *c, const char *name) { const HostModel &hm = c->b->impl->hm; const int j = hm.joint_id(name ? name : ""); return j >= 0 ? &c->m_damp[hm.jnt_dofadr[j]] : nullptr; }
+// the reference copies 3 values to &geom_friction[geom_id] (:1417-1421, not 3 * geom_id); here the geom's own triple is addressed
+void cassie_sim_set_geom_name_friction(cassie_sim_t *c, const char *name, double *fric) { const int g = c->b->impl->hm.geom_id(name ? name : ""); if (g >= 0) for (int k = 0; k < 3; k++) c->m_fric[3 * g + k] = fric[k]; }
+double *cassie_sim_get_geom_name_friction(cassie_sim_t *c, const char *name) { const int g = c->b->impl->hm.geom_id(name ? name : ""); return g >= 0 ? &c->m_fric[3 * g] : nullptr; }
+void cassie_sim_just_set_const(cassie_sim_t *c) { sim_push(c); cassie_batch_set_const(c->b, nullptr, 0); }
+void cassie_sim_set_const(cassie_sim_t *c) { sim_push(c); cassie_batch_set_const(c->b, nullptr, 1); sim_pull(c); }
 void cassie_sim_full_reset(cassie_sim_t *c) {
   // src/cassiemujoco.c:2008-2033: qpos <- 35 constants, zero qvel / ctrl / applied forces / qacc, zero the torque delay line.
   // It does NOT touch time, the encoder filters or cassie_out, and does not call mj_forward.

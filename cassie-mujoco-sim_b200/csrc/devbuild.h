@@ -19,7 +19,7 @@ inline void q2m_d(double *m, const double *q) {
 }
 }  // namespace detail
 
-struct BuildInfo { int unsupported_pairs = 0; int collision_geoms = 0; };
+struct BuildInfo { int unsupported_pairs = 0; int collision_geoms = 0; int geom_dev[256]; BuildInfo() { for (int i = 0; i < 256; i++) geom_dev[i] = -1; } };   // geom_dev: host geom id -> collision geom slot of the device block
 
 template <typename real>
 bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, BuildInfo *info = nullptr) {
@@ -53,6 +53,8 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
   double mass = 0; for (int b = 1; b < m.nbody; b++) if (b != xb) mass += m.body_mass[b];
   d.root_mass_inv = (real)(1.0 / mass);
   for (int k = 0; k < 3; k++) { d.gravity[k] = (real)m.gravity[k]; d.magnetic[k] = (real)m.magnetic[k]; }
+  for (int k = 0; k < 44; k++) d.qpos0[k] = k < m.nq ? (real)m.qpos0[k] : real(0);
+  if (std::fabs(m.impratio - 1.0) > 1e-12) { err = "impratio != 1 is not supported"; return false; }
   // bodies
   for (int b = 0; b < m.nbody; b++) {
     d.body_parent[b] = m.body_parentid[b]; d.body_depth[b] = b ? d.body_depth[m.body_parentid[b]] + 1 : 0;
@@ -207,6 +209,8 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       }
       if (dim != 1 && dim != 3) { err = "only condim 1 and 3 contacts are supported"; return false; }
       d.pair_condim[p] = dim; d.pair_mu[p] = (real)(fr / std::sqrt(m.impratio));
+      d.pair_mu_src[p] = m.geom_priority[g1] == m.geom_priority[g2] ? 0 : (m.geom_priority[g1] > m.geom_priority[g2] ? 1 : 2);
+      d.geom_fric[k1] = (real)m.geom_friction[3 * g1]; d.geom_fric[k2] = (real)m.geom_friction[3 * g2];
       d.pair_margin[p] = (real)std::max(m.geom_margin[g1], m.geom_margin[g2]); d.pair_gap[p] = (real)std::max(m.geom_gap[g1], m.geom_gap[g2]);
       for (int k = 0; k < 2; k++) d.pair_solref[p][k] = (real)solref[k];
       for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = (real)solimp[k];
@@ -227,8 +231,30 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       for (int k = 0; k < 3; k++) { d.toe_local[s][k] = (real)(m.geom_pos[3 * g + k] + R[3 * k + 2] * m.geom_size[3 * g + 1]); d.heel_local[s][k] = (real)(m.geom_pos[3 * g + k] - R[3 * k + 2] * m.geom_size[3 * g + 1]); }
     }
   }
-  if (info) { info->unsupported_pairs = unsupported; info->collision_geoms = d.ngeom; }
+  if (info) { info->unsupported_pairs = unsupported; info->collision_geoms = d.ngeom; for (int g = 0; g < 256; g++) info->geom_dev[g] = gmap[g]; }
   return true;
+}
+
+// slot of entry i of a named per-env model array ("body_mass" [nbody], "body_ipos" [3 nbody], "dof_damping" [nv], "geom_friction" [3 ngeom],
+// all in the host model's numbering = the reference's) inside the constant row, or -1 for entries the stepper does not use (damping of the
+// extra free body, friction of non-colliding geoms, the torsional / rolling coefficients); width <- entries per env, -1 for an unknown name
+inline int cenv_slot(const HostModel &hm, int nv_main, const int *geom_dev, const char *what, int i, int &width) {
+  const std::string k(what);
+  if (k == "body_mass") { width = hm.nbody; return CE_MASS + i; }
+  if (k == "body_ipos") { width = 3 * hm.nbody; return CE_IPOS + i; }   // (the extra free body keeps its inertial frame: the setter rejects a change there)
+  if (k == "dof_damping") { width = hm.nv; return i < nv_main ? CE_DAMP + i : -1; }
+  if (k == "geom_friction") { width = 3 * hm.ngeom; const int g = i / 3; return (i % 3 == 0 && g < 256 && geom_dev[g] >= 0) ? CE_FRIC + geom_dev[g] : -1; }
+  width = -1; return -1;
+}
+
+// default row of per-environment model constants (CE_* layout): the shared model's own values
+template <typename real>
+void init_cenv_row(const DevModel<real> &d, real *row) {
+  for (int i = 0; i < CE_W; i++) row[i] = 0;
+  for (int b = 0; b < d.nbody; b++) { row[CE_MASS + b] = d.body_mass[b]; for (int k = 0; k < 3; k++) row[CE_IPOS + 3 * b + k] = d.body_ipos[b][k]; row[CE_BINVW + b] = d.body_invw[b]; }
+  for (int i = 0; i < d.nv; i++) { row[CE_DAMP + i] = d.dof_damping[i]; row[CE_DINVW + i] = d.dof_invweight0[i]; }
+  for (int g = 0; g < d.ngeom; g++) row[CE_FRIC + g] = d.geom_fric[g];
+  row[CE_ROOT_MINV] = d.root_mass_inv; row[CE_TOT_MINV] = d.total_mass_inv; row[CE_PGS_SCALE] = d.pgs_scale;
 }
 
 // initial per-env rows: what cassie_sim_init leaves behind before its mj_forward (src/cassiemujoco.c:989-1027)

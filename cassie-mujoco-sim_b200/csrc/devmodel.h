@@ -61,6 +61,8 @@ struct DevModel {
   real geom_pos[MG][3], geom_mat[MG][9], geom_size[MG][3];   // geom frame in its body (row-major rotation), sizes
   int pair_g1[MP], pair_g2[MP], pair_kind[MP], pair_condim[MP];
   real pair_mu[MP], pair_margin[MP], pair_gap[MP], pair_solref[MP][2], pair_solimp[MP][5];
+  int pair_mu_src[MP];  // how the pair's sliding friction follows from the geoms': 0 max of both (equal priority), 1 geom 1, 2 geom 2
+  real geom_fric[MG], qpos0[44];   // sliding friction per collision geom; the reference configuration (mj_setConst works there)
   int pair_flags[MP];   // derived-quantity flags of a pair: bit 0 obstacle geom involved (geom user == 1), bit 1 robot-robot (both user == 2),
                         // bits 8.. : geom groups g met by a group-1 geom (cassie_sim_geom_collision, src/cassiemujoco.c:1944-1961)
   // ---- feet (src/cassiemujoco.c:861-866): body ids, toe / heel points in the foot frames, total mass including the extra free body
@@ -104,6 +106,17 @@ constexpr int AX_FOOT_VEL = 30;                     // [12] cassie_sim_foot_velo
 constexpr int AX_CM_POS = 42, AX_CM_VEL = 45, AX_ANGMOM = 48;   // [3] each: centre of mass, its velocity, angular momentum about it
 constexpr int AX_OBSTACLE = 51, AX_SELF = 52, AX_GROUPMASK = 53, AX_NCON = 54;
 constexpr int AX_TMP = 56;                          // [8] toe / heel world xy of both feet, carried between stages of one sub-step
+
+// per-environment model constants (optional, domain randomisation: src/cassiemujoco.c:1303-1436 setters + mj_setConst :949-977).
+// When a batch carries these rows the step kernel reads the listed constants from the env's row instead of the shared model block.
+constexpr int CE_W = 256;
+constexpr int CE_MASS = 0;       // [32] body_mass
+constexpr int CE_IPOS = 32;      // [32][3] body_ipos
+constexpr int CE_DAMP = 128;     // [32] dof_damping (main tree)
+constexpr int CE_FRIC = 160;     // [16] sliding friction per collision geom (device geom order)
+constexpr int CE_BINVW = 176;    // [32] body_invweight0 (translational)  -- written by the set_const launch
+constexpr int CE_DINVW = 208;    // [32] dof_invweight0                    -- written by the set_const launch
+constexpr int CE_ROOT_MINV = 240, CE_TOT_MINV = 241, CE_PGS_SCALE = 242;   // 1 / main-tree mass, 1 / total mass, 1 / (meaninertia * nv)
 
 // ---- per-warp scratch (in units of `real`)
 constexpr int S_XPOS = 0;                       // [32][3]

@@ -192,14 +192,12 @@ struct Compiler {
     if (!types.count(ts)) { err = "unknown geom type " + ts; return false; }
     Geom G{}; G.type = types.at(ts); G.body = bid; G.name = A(a, "name") ? A(a, "name") : "";
     G.contype = Ai(a, "contype", 1); G.conaffinity = Ai(a, "conaffinity", 1);
-    if (G.type == GEOM_MESH) {
-      if (G.contype || G.conaffinity) { err = "colliding mesh geoms are not supported"; return false; }
-      return true;  // visual only
-    }
+    const bool mesh = G.type == GEOM_MESH;   // visual only: kept (zero size) so geom ids / per-geom arrays are numbered as in the reference's model
+    if (mesh && (G.contype || G.conaffinity)) { err = "colliding mesh geoms are not supported"; return false; }
     if (G.type == 4 || G.type == 5) { err = "ellipsoid/cylinder geoms are not supported"; return false; }
-    vec s = Av(a, "size", ""), pos = Av(a, "pos", "0 0 0");
+    vec s = mesh ? vec() : Av(a, "size", ""), pos = Av(a, "pos", "0 0 0");
     memcpy(G.pos, pos.data(), sizeof G.pos); orientation(a, G.quat);
-    if (A(a, "fromto")) {
+    if (!mesh && A(a, "fromto")) {
       vec ft = nums(A(a, "fromto")); double v[3] = {ft[0] - ft[3], ft[1] - ft[4], ft[2] - ft[5]};  // z axis points from 'to' to 'from'
       G.size[0] = s.size() ? s[0] : 0; G.size[1] = norm3(v) / 2;
       for (int i = 0; i < 3; i++) G.pos[i] = 0.5 * (ft[i] + ft[3 + i]);

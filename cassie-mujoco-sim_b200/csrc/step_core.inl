@@ -66,6 +66,7 @@ template <typename real> struct EnvPtrs {
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
   real *dbg;          // [D_SIZE] or null
   real *aux;          // [AUX_W] derived-quantity row or null
+  real *cenv;         // [CE_W] per-environment model constants (domain randomisation) or null: then the shared model block's values apply
   int *counters;      // [8]
 };
 
@@ -376,6 +377,28 @@ template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int b
   } else { out[0] = out[1] = out[2] = 0; }
 }
 
+// sliding friction of a candidate pair: the shared model's value, or mixed from the env's per-geom values (mj_contactParam: the geom of
+// higher priority wins, else the larger coefficient)
+template <typename real>
+CFN real pair_friction(const DevModel<real> &cm, const real *ce, int p) {
+  if (!ce) return cm.pair_mu[p];
+  const real f1 = ce[CE_FRIC + cm.pair_g1[p]], f2 = ce[CE_FRIC + cm.pair_g2[p]]; const int src = cm.pair_mu_src[p];
+  return src == 0 ? mmax(f1, f2) : (src == 1 ? f1 : f2);
+}
+// one row of J  ->  D^-1/2 L^-T J' in place (mj_solveM2 on a single vector, main-tree dofs); returns its squared norm = J inv(M) J'
+template <typename real>
+CFN real half_solve_row(const DevModel<real> &cm, const real *sm, real *yy, int nv) {
+  const real *qLD = sm + S_QLD;
+  for (int i = nv - 1; i > 0; --i) {
+    const int di = cm.dof_depth[i]; if (di == 0) continue;
+    const real xi = yy[i]; const real *Li = qLD + cm.dof_Madr[i]; const unsigned char *an = cm.dof_anc[i];
+    for (int t = 1; t <= di; ++t) yy[an[t]] -= Li[t] * xi;
+  }
+  real ad = 0;
+  for (int d = 0; d < nv; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
+  return ad;
+}
+
 // cassie_sim_foot_velocities (src/cassiemujoco.c:1623-1631): mj_comVel of the two foot bodies = sum over the dof chain, root first, of
 // cdof * qvel; qvel is read from vecs[0..nv), cdof from the copy the derived-quantity stage left in the geom buffer
 template <typename real>
@@ -396,9 +419,21 @@ CFN void aux_foot_velocities(const DevModel<real> &cm, real *sm, real *aux) {
 
 // ------------------------------------------------------------------ one MuJoCo sub-step (mj_step1 + mj_step2)
 // state in: sm[S_QPOS], lane vars qvel / qacc_ws, ctrl in sm[S_CST..] (via ctrl lane var), xfrc.  state out: same + sensordata.
-template <typename real>
-CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), LP(real, ctrl), real *dbg, int mode) {
-  const bool advance = (mode == 0);   // mode: 0 step, 1 mj_forward only, 2 query (kinematics + velocities -> centre-of-mass slots of the aux row, nothing else written)
+// DR ("extended" instance): the batch carries per-environment model constants (domain randomisation) and / or derived-quantity rows.  A
+// compile-time flag so that the plain instance keeps its constants in the shared model block with no indirection and contains neither the
+// set_const stage nor the derived-quantity stages.
+template <typename real, bool DR>
+CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), LP(real, ctrl), real *dbg, real *aux_row, int mode) {
+  const bool advance = (mode == 0);   // mode: 0 step, 1 mj_forward only, 2 query (kinematics + velocities -> centre-of-mass slots of the aux row, nothing else written),
+                                      //       3 set_const (invweights / masses / mean inertia at the reference configuration -> the env's constant row)
+  // model constants that may be env-private (domain randomisation): the env's row if the batch carries one, else the shared block
+  const real *ce = DR ? E.cenv : (const real *)0;
+  real *const auxr = DR ? aux_row : (real *)0;   // derived-quantity row: only the extended instance carries those stages, and only the last
+                                                 // sub-step of a launch fills it (what a query after the launch would see)
+  const real *bmass = ce ? ce + CE_MASS : cm.body_mass, *bipos = ce ? ce + CE_IPOS : &cm.body_ipos[0][0], *ddamp = ce ? ce + CE_DAMP : cm.dof_damping;
+  const real *binvw = ce ? ce + CE_BINVW : cm.body_invw, *dinvw = ce ? ce + CE_DINVW : cm.dof_invweight0;
+  const real root_mass_inv = ce ? ce[CE_ROOT_MINV] : cm.root_mass_inv, total_mass_inv = ce ? ce[CE_TOT_MINV] : cm.total_mass_inv, pgs_scale = ce ? ce[CE_PGS_SCALE] : cm.pgs_scale;
+  const real xb_dsqi_t = (ce && cm.xb >= 0) ? real(1) / msqrt(bmass[cm.xb]) : cm.xb_dsqi[0];   // the extra free body's mass acts at once, like every body_mass entry
   DECL_LANE
   const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
@@ -465,20 +500,20 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   LANES  // lane = body
     L(t0) = L(t1) = L(t2) = 0;
     if (l >= 1 && l < nb && l != xb) {
-      real v[3]; mat_vec(v, xmat + 9 * l, cm.body_ipos[l]);
-      const real m = cm.body_mass[l];
+      real v[3]; mat_vec(v, xmat + 9 * l, bipos + 3 * l);
+      const real m = bmass[l];
       L(t0) = m * (xpos[3 * l] + v[0]); L(t1) = m * (xpos[3 * l + 1] + v[1]); L(t2) = m * (xpos[3 * l + 2] + v[2]);
     }
   ENDL
   ALLSUM(t0); ALLSUM(t1); ALLSUM(t2);
-  LANES L(com0) = L(t0) * cm.root_mass_inv; L(com1) = L(t1) * cm.root_mass_inv; L(com2) = L(t2) * cm.root_mass_inv; ENDL
+  LANES L(com0) = L(t0) * root_mass_inv; L(com1) = L(t1) * root_mass_inv; L(com2) = L(t2) * root_mass_inv; ENDL
   LANES  // lane = body: cinert about the com, world orientation
     if (l < nb) {
       real *r = cinert + 10 * l;
       if (l == 0) { for (int k = 0; k < 10; ++k) r[k] = 0; }
       else {
-        real v[3], off[3], R[9]; const real *X = xmat + 9 * l, *B = cm.body_imat[l], *I = cm.body_inertia[l]; const real m = cm.body_mass[l];
-        mat_vec(v, X, cm.body_ipos[l]);
+        real v[3], off[3], R[9]; const real *X = xmat + 9 * l, *B = cm.body_imat[l], *I = cm.body_inertia[l]; const real m = bmass[l];
+        mat_vec(v, X, bipos + 3 * l);
         off[0] = xpos[3 * l] + v[0] - L(com0); off[1] = xpos[3 * l + 1] + v[1] - L(com1); off[2] = xpos[3 * l + 2] + v[2] - L(com2);
         for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[3 * a + b] = X[3 * a] * B[b] + X[3 * a + 1] * B[3 + b] + X[3 * a + 2] * B[6 + b];
         r[0] = R[0] * R[0] * I[0] + R[1] * R[1] * I[1] + R[2] * R[2] * I[2] + m * (off[1] * off[1] + off[2] * off[2]);
@@ -540,6 +575,53 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   factor_ld(cm, sm);
   if (dbg) { LANES for (int a = l; a < cm.nM; a += 32) { dbg[D_QM + a] = qM[a]; dbg[D_QLD + a] = qLD[a]; } ENDL }
 
+  // ================= mode 3: mj_setConst for this env (src/cassiemujoco.c:949-977 -> set0 / setStat [M]) =================
+  // the caller loaded qpos0; with M factored there: dof_invweight0 = diag(inv(M)) (averaged over a ball joint's three dofs),
+  // body_invweight0 = trace(Jp inv(M) Jp')/3 with Jp the translational Jacobian at the body's com, each entry the squared norm of a
+  // half-solved row (the same in-place transform the constraint stage applies to J); mean inertia = mean diagonal of M
+  if (DR && mode == 3) {
+    real *cew = E.cenv, *vecs3 = sm + S_VEC;
+    if (!cew) return;
+    LANES for (int d = 0; d < ys; ++d) Y[l * ys + d] = (d == l) ? real(1) : real(0); ENDL
+    LANES if (l < nv) vecs3[l] = half_solve_row(cm, sm, Y + l * ys, nv); ENDL
+    LANES
+      if (l < nv) {
+        const int j = cm.dof_jnt[l], da = cm.jnt_dofadr[j];
+        cew[CE_DINVW + l] = (cm.jnt_type[j] == 1) ? (vecs3[da] + vecs3[da + 1] + vecs3[da + 2]) / 3 : vecs3[l];
+      }
+    ENDL
+    for (int c0 = 1; c0 < nb; c0 += 16) {
+      const int nbc = (nb - c0) < 16 ? (nb - c0) : 16;
+      for (int i = 0; i < nbc; ++i) {
+        const int b = c0 + i;
+        LANES  // lane = dof: column of the translational Jacobian at the body's centre of mass
+          real v[3], pt[3], jc[3] = {0, 0, 0}, cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, cm3[3] = {L(com0), L(com1), L(com2)};
+          if (b != xb) { mat_vec(v, xmat + 9 * b, bipos + 3 * b); pt[0] = xpos[3 * b] + v[0]; pt[1] = xpos[3 * b + 1] + v[1]; pt[2] = xpos[3 * b + 2] + v[2]; jac_col(cm, l, b, cd, pt, cm3, jc); }
+          for (int k = 0; k < 3; ++k) Y[(3 * i + k) * ys + l] = jc[k];
+        ENDL
+      }
+      LANES  // lane = row
+        if (l < 3 * nbc) vecs3[l] = half_solve_row(cm, sm, Y + l * ys, nv);
+        if (l + 32 < 3 * nbc) vecs3[l + 32] = half_solve_row(cm, sm, Y + (l + 32) * ys, nv);
+      ENDL
+      LANES
+        if (l < nbc) { const int b = c0 + l; cew[CE_BINVW + b] = (b == xb) ? real(1) / bmass[b] : (cm.body_lastdof[b] >= 0 ? (vecs3[3 * l] + vecs3[3 * l + 1] + vecs3[3 * l + 2]) / 3 : real(0)); }
+      ENDL
+    }
+    LV(real, sm0); LV(real, sm1);
+    LANES L(sm0) = (l >= 1 && l < nb && l != xb) ? bmass[l] : real(0); L(sm1) = (l < nv) ? qM[cm.dof_Madr[l]] : real(0); ENDL
+    ALLSUM(sm0); ALLSUM(sm1);
+    LANES
+      if (l == 0) {
+        real mroot = L(sm0), mtot = mroot, tr = L(sm1); int nvt = nv;
+        if (xb >= 0) { mtot += bmass[xb]; tr += 3 * bmass[xb] + cm.xb_inertia[0] + cm.xb_inertia[1] + cm.xb_inertia[2]; nvt += 6; }
+        cew[CE_ROOT_MINV] = real(1) / mroot; cew[CE_TOT_MINV] = real(1) / mtot;
+        cew[CE_PGS_SCALE] = real(1) / ((tr / (real)nvt) * (real)nvt);
+      }
+    ENDL
+    return;
+  }
+
   // ================= velocity stage: comVel, passive, RNE bias =================
   real *S = sm + S_Y + T_CRB;      // chain sums [32][6] (crb is dead)
   real *cvel = sm + S_Y + T_CVEL;  // [32][6]
@@ -595,14 +677,14 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       for (int d = b; d < cm.body_subtree_end[b]; ++d) for (int k = 0; k < 6; ++k) acc[k] += cfrc[6 * d + k];
       const real bs = L(cd0) * acc[0] + L(cd1) * acc[1] + L(cd2) * acc[2] + L(cd3) * acc[3] + L(cd4) * acc[4] + L(cd5) * acc[5];
       const int j = cm.dof_jnt[l];
-      real passive = -cm.dof_damping[l] * L(qvel);
+      real passive = -ddamp[l] * L(qvel);
       if (cm.jnt_stiffness[j] != 0 && cm.jnt_type[j] >= 2) passive -= cm.jnt_stiffness[j] * (qpos[cm.jnt_qposadr[j]] - cm.jnt_qspring[j]);
       real f = passive - bs;
       // xfrc_applied on one body: J(xipos)' [force; torque]
       const int xb = (int)xfrc[6];
       if (xb > 0 && ((cm.body_dofmask[xb] >> l) & 1u)) {
         real v[3], pt[3], jc[3], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, cm3[3] = {L(com0), L(com1), L(com2)};
-        mat_vec(v, xmat + 9 * xb, cm.body_ipos[xb]);
+        mat_vec(v, xmat + 9 * xb, bipos + 3 * xb);
         pt[0] = xpos[3 * xb] + v[0]; pt[1] = xpos[3 * xb + 1] + v[1]; pt[2] = xpos[3 * xb + 2] + v[2];
         jac_col(cm, l, xb, cd, pt, cm3, jc);
         f += jc[0] * xfrc[0] + jc[1] * xfrc[1] + jc[2] * xfrc[2] + cd[0] * xfrc[3] + cd[1] * xfrc[4] + cd[2] * xfrc[5];
@@ -642,7 +724,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   // ================= derived quantities, part 1: centre of mass, its velocity, angular momentum about it =================
   // (cassie_sim_cm_position / cm_velocity / angular_momentum, src/cassiemujoco.c:1633-1646,1693-1699 -> subtree_com, mj_subtreeVel of the
   // world body).  Sum over bodies of cinert * cvel is the spatial momentum about the main tree's com; the extra free body is folded in.
-  if (E.aux) {
+  if (auxr) {
     LV(real, m0); LV(real, m1); LV(real, m2); LV(real, m3); LV(real, m4); LV(real, m5);
     LANES
       real h6[6] = {0, 0, 0, 0, 0, 0};
@@ -654,15 +736,15 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       if (l == 0) {
         real C[3] = {L(com0), L(com1), L(com2)}, P[3] = {L(m3), L(m4), L(m5)}, Lc[3] = {L(m0), L(m1), L(m2)}, V[3];
         if (xb >= 0) {
-          const real mc = cm.xb_mass, Mr = real(1) / cm.root_mass_inv, *xc = xpos + 3 * xb, *R = xmat + 9 * xb;
+          const real mc = bmass[xb], Mr = real(1) / root_mass_inv, *xc = xpos + 3 * xb, *R = xmat + 9 * xb;
           real Ct[3], d1[3], d2[3], t3[3], pc[3] = {mc * vecs[160], mc * vecs[161], mc * vecs[162]}, Iw[3] = {cm.xb_inertia[0] * vecs[163], cm.xb_inertia[1] * vecs[164], cm.xb_inertia[2] * vecs[165]}, Lx[3];
-          for (int k = 0; k < 3; ++k) { Ct[k] = (Mr * C[k] + mc * xc[k]) * cm.total_mass_inv; d1[k] = C[k] - Ct[k]; d2[k] = xc[k] - Ct[k]; }
+          for (int k = 0; k < 3; ++k) { Ct[k] = (Mr * C[k] + mc * xc[k]) * total_mass_inv; d1[k] = C[k] - Ct[k]; d2[k] = xc[k] - Ct[k]; }
           mat_vec(Lx, R, Iw);
           cross3(t3, d1, P); for (int k = 0; k < 3; ++k) Lc[k] += t3[k] + Lx[k];
           cross3(t3, d2, pc); for (int k = 0; k < 3; ++k) { Lc[k] += t3[k]; P[k] += pc[k]; C[k] = Ct[k]; }
         }
-        for (int k = 0; k < 3; ++k) V[k] = P[k] * cm.total_mass_inv;
-        for (int k = 0; k < 3; ++k) { E.aux[AX_CM_POS + k] = C[k]; E.aux[AX_CM_VEL + k] = V[k]; E.aux[AX_ANGMOM + k] = Lc[k]; }
+        for (int k = 0; k < 3; ++k) V[k] = P[k] * total_mass_inv;
+        for (int k = 0; k < 3; ++k) { auxr[AX_CM_POS + k] = C[k]; auxr[AX_CM_VEL + k] = V[k]; auxr[AX_ANGMOM + k] = Lc[k]; }
       }
     ENDL
     if (mode == 2) return;
@@ -860,7 +942,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       const real jn = dot3(o + 3, dj);
       if (rows == 1) Y[nefc * ys + l] = jn;
       else {
-        const real mu = cm.pair_mu[p], jt1 = dot3(o + 6, dj), jt2 = dot3(o + 9, dj);
+        const real mu = pair_friction(cm, ce, p), jt1 = dot3(o + 6, dj), jt2 = dot3(o + 9, dj);
         Y[nefc * ys + l] = jn + mu * jt1; Y[(nefc + 1) * ys + l] = jn - mu * jt1;
         Y[(nefc + 2) * ys + l] = jn + mu * jt2; Y[(nefc + 3) * ys + l] = jn - mu * jt2;
       }
@@ -874,7 +956,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         const real xn = dot3(o + 3, col);
         if (rows == 1) Y[nefc * ys + 32 + l] = xn;
         else {
-          const real mu = cm.pair_mu[p], xt1 = dot3(o + 6, col), xt2 = dot3(o + 9, col);
+          const real mu = pair_friction(cm, ce, p), xt1 = dot3(o + 6, col), xt2 = dot3(o + 9, col);
           Y[nefc * ys + 32 + l] = xn + mu * xt1; Y[(nefc + 1) * ys + 32 + l] = xn - mu * xt1;
           Y[(nefc + 2) * ys + 32 + l] = xn + mu * xt2; Y[(nefc + 3) * ys + 32 + l] = xn - mu * xt2;
         }
@@ -888,14 +970,14 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   (void)nefc_before_contacts;
   // ================= derived quantities, part 2 (while the kinematics buffers are alive): foot positions, toe / heel points, a copy of
   // cdof for the foot velocities (cassie_sim_foot_positions :1608-1621; site_xpos of the toe / heel sites :1888-1889)
-  if (E.aux) {
+  if (auxr) {
     real *cdofs = geom;   // the geom poses are dead once the contacts are listed
     LANES
       if (l < nv) for (int k = 0; k < 6; ++k) cdofs[6 * l + k] = cdof[6 * l + k];
-      if (l < 6) { const int fb = cm.foot_body[l / 3], k = l % 3; real v = fb >= 0 ? xpos[3 * fb + k] : real(0); if (k == 2) v -= cm.foot_offset; E.aux[AX_FOOT_POS + l] = v; }
+      if (l < 6) { const int fb = cm.foot_body[l / 3], k = l % 3; real v = fb >= 0 ? xpos[3 * fb + k] : real(0); if (k == 2) v -= cm.foot_offset; auxr[AX_FOOT_POS + l] = v; }
       if (l >= 8 && l < 16) {
         const int i = l - 8, sd = i >> 2, k = i & 1, fb = cm.foot_body[sd]; const real *loc = ((i >> 1) & 1) ? cm.heel_local[sd] : cm.toe_local[sd];
-        E.aux[AX_TMP + i] = fb >= 0 ? xpos[3 * fb + k] + (xmat[9 * fb + 3 * k] * loc[0] + xmat[9 * fb + 3 * k + 1] * loc[1] + xmat[9 * fb + 3 * k + 2] * loc[2]) : real(0);
+        auxr[AX_TMP + i] = fb >= 0 ? xpos[3 * fb + k] + (xmat[9 * fb + 3 * k] * loc[0] + xmat[9 * fb + 3 * k + 1] * loc[1] + xmat[9 * fb + 3 * k + 2] * loc[2]) : real(0);
       }
     ENDL
   }
@@ -919,12 +1001,12 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (xb >= 0) for (int d = 0; d < 6; ++d) { const real y = yy[32 + d]; jv += y * vecs[160 + d]; ja += y * vecs[166 + d]; jw += y * vecs[172 + d]; }
           const int src = (int)efc[4 * r + E_SRC]; const real pos = efc[4 * r + E_POS]; const bool ineq = efc[4 * r + E_INEQ] != 0;
           const real *solref, *solimp; real dA, margin = 0, rscale = 1;
-          if (src < 64) { solref = cm.eq_solref[src]; solimp = cm.eq_solimp[src]; dA = cm.body_invw[cm.eq_b1[src]] + cm.body_invw[cm.eq_b2[src]]; }
-          else if (src < 128) { const int j = src - 64; solref = cm.jnt_solref[j]; solimp = cm.jnt_solimp[j]; dA = cm.dof_invweight0[cm.jnt_dofadr[j]]; }
+          if (src < 64) { solref = cm.eq_solref[src]; solimp = cm.eq_solimp[src]; dA = binvw[cm.eq_b1[src]] + binvw[cm.eq_b2[src]]; }
+          else if (src < 128) { const int j = src - 64; solref = cm.jnt_solref[j]; solimp = cm.jnt_solimp[j]; dA = dinvw[cm.jnt_dofadr[j]]; }
           else {
             const int p = src - 128; solref = cm.pair_solref[p]; solimp = cm.pair_solimp[p]; margin = cm.pair_margin[p] - cm.pair_gap[p];
-            dA = cm.body_invw[cm.geom_body[cm.pair_g1[p]]] + cm.body_invw[cm.geom_body[cm.pair_g2[p]]];
-            if (cm.pair_condim[p] > 1) { const real mu = cm.pair_mu[p]; dA += mu * mu * dA; rscale = 2 * mu * mu; }
+            dA = binvw[cm.geom_body[cm.pair_g1[p]]] + binvw[cm.geom_body[cm.pair_g2[p]]];
+            if (cm.pair_condim[p] > 1) { const real mu = pair_friction(cm, ce, p); dA += mu * mu * dA; rscale = 2 * mu * mu; }
           }
           const real imp = impedance(solimp, pos, margin);
           const real Rr = rscale * mmax(minval<real>(), (1 - imp) * dA / imp);
@@ -937,14 +1019,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (pass == 0) L(f0) = f; else L(f1) = f;
           if (dbg) { dbg[D_EFC_AREF + r] = aref; dbg[D_EFC_R + r] = Rr; dbg[D_EFC_B + r] = ja - aref; }
           // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place; all lanes (rows) walk the same (i, ancestor) sequence
-          for (int i = nv - 1; i > 0; --i) {
-            const int di = cm.dof_depth[i]; if (di == 0) continue;
-            const real xi = yy[i]; const real *Li = qLD + cm.dof_Madr[i]; const unsigned char *an = cm.dof_anc[i];
-            for (int t = 1; t <= di; ++t) yy[an[t]] -= Li[t] * xi;
-          }
-          real ad = 0;
-          for (int d = 0; d < nv; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
-          if (xb >= 0) for (int d = 0; d < 6; ++d) { const real v = yy[32 + d] * cm.xb_dsqi[d]; yy[32 + d] = v; ad += v * v; }
+          real ad = half_solve_row(cm, sm, yy, nv);
+          if (xb >= 0) for (int d = 0; d < 6; ++d) { const real v = yy[32 + d] * (d < 3 ? xb_dsqi_t : cm.xb_dsqi[d]); yy[32 + d] = v; ad += v * v; }
           // packed row constants for the solver: b, 1/A, A, +-R (sign bit set = inequality row)
           real *rc = efc + 4 * r; const real Ad = ad + Rr;
           rc[0] = ja - aref; rc[1] = real(1) / Ad; rc[2] = Ad; rc[3] = ineq ? -Rr : Rr;
@@ -1023,7 +1099,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           }
         }
         ++iters;
-        if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
+        if (LANE0(impr) * pgs_scale < cm.tolerance) break;
       }
       LANES_NS L(z) = 0; ENDL_NS
       for (int r = 0; r < nefc; ++r) { BCAST(fb, f0, r); LANES_NS if (l < nv) L(z) += Y[r * ys + l] * L(fb); if (xb >= 0 && l < 6) L(xz) += Y[r * ys + 32 + l] * L(fb); ENDL_NS }
@@ -1084,14 +1160,14 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           ENDL_NS
         }
         ++iters;
-        if (LANE0(impr) * cm.pgs_scale < cm.tolerance) break;
+        if (LANE0(impr) * pgs_scale < cm.tolerance) break;
       }
     }
     // ---- qacc = qacc_smooth + inv(L) D^-1/2 z ;  qfrc_constraint = J'f = L' D^1/2 z
     LV(real, w);
     LANES L(w) = (l < nv) ? L(z) * sm[S_DSQI + l] : real(0); ENDL
     sweep_l(cm, sm, w);
-    LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; if (xb >= 0 && l < 6) L(xqacc) = L(xqacc_smooth) + L(xz) * cm.xb_dsqi[l]; ENDL
+    LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; if (xb >= 0 && l < 6) L(xqacc) = L(xqacc_smooth) + L(xz) * (l < 3 ? xb_dsqi_t : cm.xb_dsqi[l]); ENDL
     if (dbg) {  // qfrc_constraint = M (qacc - qacc_smooth); only the debug dump wants it (the Euler stage below does not)
       LANES vecs[128 + l] = L(w); ENDL
       LANES
@@ -1107,15 +1183,15 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   if (counters) { LANES if (l == 0) counters[3] = iters; ENDL }
   // ================= derived quantities, part 3: contact forces (mj_contactForce -> world frame), foot / toe / heel sums, collision flags
   // (cassie_sim_foot_forces :1812-1854, cassie_sim_heeltoe_forces :1856-1898, check_*_collision :1586-1606, geom_collision :1944-1961)
-  if (E.aux) {
-    real *aux = E.aux;
+  if (auxr) {
+    real *aux = auxr;
     if (nefc > 0) { LANES if (l < nefc) efc[4 * l] = L(f0); if (l + 32 < nefc) efc[4 * (l + 32)] = L(f1); ENDL }   // slot 0 (b) is dead: keep the row forces
     LANES  // lane = contact: decode the pyramid, rotate into the world frame, classify
       if (l < ncon_used) {
         real *o = con + 16 * l; const int p = (int)o[13], r0 = (int)o[14];
         real fn, t1 = 0, t2 = 0;
         if (cm.pair_condim[p] == 1) fn = efc[4 * r0];
-        else { const real a = efc[4 * r0], b = efc[4 * (r0 + 1)], c = efc[4 * (r0 + 2)], d = efc[4 * (r0 + 3)], mu = cm.pair_mu[p]; fn = a + b + c + d; t1 = (a - b) * mu; t2 = (c - d) * mu; }
+        else { const real a = efc[4 * r0], b = efc[4 * (r0 + 1)], c = efc[4 * (r0 + 2)], d = efc[4 * (r0 + 3)], mu = pair_friction(cm, ce, p); fn = a + b + c + d; t1 = (a - b) * mu; t2 = (c - d) * mu; }
         real F[3]; for (int k = 0; k < 3; ++k) F[k] = o[3 + k] * fn + o[6 + k] * t1 + o[9 + k] * t2;
         const int b1 = cm.geom_body[cm.pair_g1[p]], b2 = cm.geom_body[cm.pair_g2[p]], lf = cm.foot_body[0], rf = cm.foot_body[1];
         const bool f1 = (b1 == lf || b1 == rf), anyf = f1 || b2 == lf || b2 == rf; const int id = (b1 == rf || b2 == rf) ? 1 : 0;
@@ -1173,23 +1249,23 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   if (dbg) { LANES if (l < 29) dbg[D_SENS + l] = cst[CS_SENSOR + l]; ENDL }
 
   if (!advance) {   // mj_forward only (used once at init / reset to populate sensordata, src/cassiemujoco.c:1029)
-    if (E.aux) { LANES if (l < nv) vecs[l] = L(qvel); ENDL aux_foot_velocities(cm, sm, E.aux); }
+    if (auxr) { LANES if (l < nv) vecs[l] = L(qvel); ENDL aux_foot_velocities(cm, sm, auxr); }
     return;
   }
   // ================= Euler with implicit joint damping (mj_Euler) + mj_advance =================
   // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
-  if (cm.has_damping) {
+  if (cm.has_damping || ce) {
     LANES for (int k = l; k < cm.nM; k += 32) qLD[k] = qM[k]; ENDL          // the inverse factor of M is dead: reuse its buffer
-    LANES if (l < nv) qLD[cm.dof_Madr[l]] += cm.timestep * cm.dof_damping[l]; ENDL
+    LANES if (l < nv) qLD[cm.dof_Madr[l]] += cm.timestep * ddamp[l]; ENDL
     factor_ld(cm, sm);
-    LANES L(a) = (l < nv) ? cm.timestep * cm.dof_damping[l] * L(qacc) : real(0); ENDL
+    LANES L(a) = (l < nv) ? cm.timestep * ddamp[l] * L(qacc) : real(0); ENDL
     solve_m(cm, sm, a);
     LANES L(a) = L(qacc) - L(a); ENDL
   } else { LANES L(a) = L(qacc); ENDL }
   LANES if (l < nv) { L(qvel) += cm.timestep * L(a); vecs[l] = L(qvel); L(qacc_ws) = L(qacc); }
     if (xb >= 0 && l < 6) { L(xqvel) += cm.timestep * L(xqacc); vecs[160 + l] = L(xqvel); L(xqacc_ws) = L(xqacc); } ENDL
-  if (E.aux) aux_foot_velocities(cm, sm, E.aux);   // with the NEW qvel and the cdof of this sub-step's kinematics, as the reference's query does
+  if (auxr) aux_foot_velocities(cm, sm, auxr);   // with the NEW qvel and the cdof of this sub-step's kinematics, as the reference's query does
   LANES  // lane = joint: integrate positions with the NEW velocity
     if (l < cm.njnt) {
       const int t = cm.jnt_type[l], qa = cm.jnt_qposadr[l], da = cm.jnt_dofadr[l]; const real h = cm.timestep;
@@ -1217,7 +1293,7 @@ template <typename real> CFN real core_hi_deg(int i) { const real t[10] = {20, 2
 template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 1200, 1200, 100}; return t[k]; }
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
-template <typename real>
+template <typename real, bool DR>
 CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), int nticks, int mode) {
   const bool forward_only = (mode != 0);
   DECL_LANE
@@ -1312,7 +1388,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
     const int nsub = forward_only ? 1 : cm.nsub;
-    for (int s = 0; s < nsub; ++s) mj_substep(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, mode);
+    for (int s = 0; s < nsub; ++s) mj_substep<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, (tick == nticks - 1 && s == nsub - 1) ? E.aux : (real *)0, mode);
   }
 }
 

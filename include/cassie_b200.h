@@ -67,6 +67,32 @@ void cassie_sim_foot_velocities(const cassie_sim_t *c, double cvel[12]);
 void cassie_sim_cm_position(const cassie_sim_t *c, double cm_pos[3]);
 void cassie_sim_cm_velocity(const cassie_sim_t *c, double cm_vel[3]);
 void cassie_sim_angular_momentum(const cassie_sim_t *c, double Lcm[3]);
+/* model constants for domain randomisation.  src/cassiemujoco.c:1303-1436, 949-977 (most are defined there without a header
+ * declaration; example/cassiemujoco.py:517-610 calls them).  The pointer-returning verbs hand out borrowed read-write host mirrors
+ * ([nv], [nbody], [3 nbody], [3 ngeom] doubles, numbered like the reference's mjModel incl. its visual mesh geoms); writes are uploaded
+ * before the next step / query / set_const.  What the stepper uses: dof_damping of the 32 robot dofs, body_mass, body_ipos (not of the
+ * free `cup_box` body), the sliding coefficient geom_friction[3 g] of colliding geoms.  As in MuJoCo, a changed mass acts at once while
+ * the solver's reference weights (body/dof_invweight0, meaninertia, subtree masses) stay stale until (just_)set_const. */
+void cassie_sim_params(cassie_sim_t *c, int *params);                 /* :1566-1574: nq nv nu nsensordata nbody ngeom */
+double *cassie_sim_dof_damping(cassie_sim_t *c);                       /* :1303 */
+double *cassie_sim_body_mass(cassie_sim_t *c);                         /* :1308 */
+double *cassie_sim_body_ipos(cassie_sim_t *c);                         /* :1313 */
+double *cassie_sim_geom_friction(cassie_sim_t *c);                     /* :1318 */
+void cassie_sim_set_dof_damping(cassie_sim_t *c, double *damp);        /* :1330 */
+void cassie_sim_set_dof_name_damping(cassie_sim_t *c, const char *name, double *damp);   /* :1338 */
+double *cassie_sim_get_dof_name_damping(cassie_sim_t *c, const char *name);              /* :1347 */
+int cassie_sim_get_joint_num_dof(cassie_sim_t *c, const char *name);                     /* :1353 */
+void cassie_sim_set_body_mass(cassie_sim_t *c, double *mass);          /* :1366 */
+void cassie_sim_set_body_name_mass(cassie_sim_t *c, const char *name, double mass);      /* :1373 */
+double cassie_sim_get_body_name_mass(cassie_sim_t *c, const char *name);                 /* :1379 */
+void cassie_sim_set_body_ipos(cassie_sim_t *c, double *ipos);          /* :1385 (reads ipos[i + j], as the reference does) */
+void cassie_sim_set_body_name_ipos(cassie_sim_t *c, const char *name, double *ipos);     /* :1394 */
+double *cassie_sim_get_body_name_ipos(cassie_sim_t *c, const char *name);                /* :1402 */
+void cassie_sim_set_geom_friction(cassie_sim_t *c, double *fric);      /* :1420 */
+void cassie_sim_set_geom_name_friction(cassie_sim_t *c, const char *name, double *fric); /* :1427 (addresses the geom's own triple) */
+double *cassie_sim_get_geom_name_friction(cassie_sim_t *c, const char *name);            /* :1433 */
+void cassie_sim_set_const(cassie_sim_t *c);                            /* :949-972: mj_setConst, then qpos <- init, qvel <- 0, time <- 0, mj_forward */
+void cassie_sim_just_set_const(cassie_sim_t *c);                       /* :974-977: mj_setConst only */
 /* src/cassiemujoco.c:2002-2006: the 16 radio channels; channel 8 < 1 engages safe-torque-off */
 void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
 
@@ -129,6 +155,22 @@ void cassie_batch_get_obs(cassie_batch_t *b, double *out);
 int cassie_batch_enable_aux(cassie_batch_t *b, int on);
 int cassie_batch_get_aux(cassie_batch_t *b, double *out);
 int cassie_batch_query(cassie_batch_t *b);
+/* per-environment model constants (domain randomisation).  rows are host [n][width] doubles in the host model's numbering (= the
+ * reference's mjModel): body_mass [nbody], body_ipos [3 nbody], dof_damping [nv], geom_friction [3 ngeom].  The first call allocates a
+ * 1 KB (fp32) constant row per environment that the step kernel then reads instead of the shared model block.  set_const runs mj_setConst
+ * for the selected environments (mask == NULL: all) as one kernel launch at the reference configuration -- body/dof inverse weights, subtree
+ * masses, mean inertia -- and, with reset_state != 0, the state reset of cassie_sim_set_const (src/cassiemujoco.c:955-971).  0 / -1. */
+int cassie_batch_nbody(const cassie_batch_t *b);
+int cassie_batch_ngeom(const cassie_batch_t *b);
+int cassie_batch_set_body_mass(cassie_batch_t *b, const double *mass);
+int cassie_batch_set_body_ipos(cassie_batch_t *b, const double *ipos);
+int cassie_batch_set_dof_damping(cassie_batch_t *b, const double *damp);
+int cassie_batch_set_geom_friction(cassie_batch_t *b, const double *fric);
+int cassie_batch_get_body_mass(cassie_batch_t *b, double *mass);
+int cassie_batch_get_body_ipos(cassie_batch_t *b, double *ipos);
+int cassie_batch_get_dof_damping(cassie_batch_t *b, double *damp);
+int cassie_batch_get_geom_friction(cassie_batch_t *b, double *fric);
+int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int reset_state);
 /* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
 void cassie_batch_forward(cassie_batch_t *b);
 /* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */

@@ -34,7 +34,7 @@
 #define MAXV 48
 #define MAXB 40
 #define MAXJ 40
-#define MAXG 48
+#define MAXG 64
 #define MAXCON 64
 #define MAXEFC 160
 #define MAXNM 512
@@ -1275,6 +1275,60 @@ int osim_geom_collision(OSim *c, int geom_group) { /* :1944-1961 */
 }
 void osim_comvel(OSim *c) { o_comVel(c->m, c->d); }
 
+/* ------------------------------------------------------------------ model-constant setters' companion: mj_setConst (src/cassiemujoco.c:949-977)
+ * set0 [M]: subtree masses; at qpos0: kinematics, comPos, crb, factorM; body_invweight0 = {trace(Jp inv(M) Jp')/3, trace(Jr inv(M) Jr')/3}
+ * with the Jacobians at the body's centre of mass (zero for bodies welded to the world); dof_invweight0 = diag(inv(M)), averaged over the
+ * three dofs of a ball joint and over each half of a free joint; setStat [M]: meaninertia = mean diagonal of M(qpos0).
+ * The caller's qpos is put back afterwards (cassie_sim_set_const overwrites it anyway). */
+void o_setConst(OModel *m, OData *d) {
+  int nv = m->nv; double keep[MAXV + 8], jp[3 * MAXV], jr[3 * MAXV], row[MAXV];
+  for (int i = 0; i < m->nbody; i++) m->body_subtreemass[i] = m->body_mass[i];
+  for (int i = m->nbody - 1; i > 0; i--) m->body_subtreemass[m->body_parentid[i]] += m->body_subtreemass[i];
+  copyv(keep, d->qpos, m->nq); copyv(d->qpos, m->qpos0, m->nq);
+  o_kinematics(m, d); o_comPos(m, d); o_crb(m, d);
+  copyv(d->qLD, d->qM, m->nM); factorI(m, d->qLD, d->qLDiagInv, d->qLDiagSqrtInv);
+  for (int b = 1; b < m->nbody; b++) {
+    m->body_invweight0[b][0] = m->body_invweight0[b][1] = 0;
+    if (!m->body_weldid[b]) continue;
+    o_jac(m, d, jp, jr, d->xipos[b], b);
+    double tp = 0, tr = 0;
+    for (int k = 0; k < 3; k++) {
+      copyv(row, jp + k * nv, nv); solveM2(m, d, row); tp += dotn(row, row, nv);
+      copyv(row, jr + k * nv, nv); solveM2(m, d, row); tr += dotn(row, row, nv);
+    }
+    m->body_invweight0[b][0] = tp / 3; m->body_invweight0[b][1] = tr / 3;
+  }
+  double dg[MAXV];
+  for (int i = 0; i < nv; i++) { zero(row, nv); row[i] = 1; solveM2(m, d, row); dg[i] = dotn(row, row, nv); }
+  for (int j = 0; j < m->njnt; j++) {
+    int da = m->jnt_dofadr[j];
+    if (m->jnt_type[j] == JNT_FREE) { double a = (dg[da] + dg[da + 1] + dg[da + 2]) / 3, b = (dg[da + 3] + dg[da + 4] + dg[da + 5]) / 3; for (int k = 0; k < 3; k++) { m->dof_invweight0[da + k] = a; m->dof_invweight0[da + 3 + k] = b; } }
+    else if (m->jnt_type[j] == JNT_BALL) { double a = (dg[da] + dg[da + 1] + dg[da + 2]) / 3; for (int k = 0; k < 3; k++) m->dof_invweight0[da + k] = a; }
+    else m->dof_invweight0[da] = dg[da];
+  }
+  double tr = 0; for (int i = 0; i < nv; i++) tr += d->qM[m->dof_Madr[i]];
+  m->meaninertia = tr / nv;
+  copyv(d->qpos, keep, m->nq);
+}
+void osim_just_set_const(OSim *c) { o_setConst(c->m, c->d); }              /* :974-977 */
+void osim_set_const(OSim *c) {                                             /* :949-972 */
+  static const double qi[28] = {0.0045, 0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968,
+                                -0.0045, 0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968};
+  o_setConst(c->m, c->d);
+  copyv(c->d->qpos, c->m->qpos0, c->m->nq); copyv(c->d->qpos + 7, qi, 28);  /* the 35 constants at :953-958 = qpos0[0..6] ++ these */
+  zero(c->d->qvel, c->m->nv); zero(c->d->qacc, c->m->nv);
+  c->d->time = 0;
+  o_forward(c->m, c->d);
+}
+double *osim_model_array(OSim *c, const char *key, int *n) {
+  OModel *m = c->m;
+#define MARR(name, ptr, cnt) if (!strcmp(key, name)) { *n = (cnt); return (double *)(ptr); }
+  MARR("body_mass", m->body_mass, m->nbody) MARR("body_ipos", m->body_ipos, 3 * m->nbody) MARR("dof_damping", m->dof_damping, m->nv)
+  MARR("geom_friction", m->geom_friction, 3 * m->ngeom) MARR("body_invweight0", m->body_invweight0, 2 * m->nbody) MARR("dof_invweight0", m->dof_invweight0, m->nv)
+  MARR("body_subtreemass", m->body_subtreemass, m->nbody) MARR("meaninertia", &m->meaninertia, 1) MARR("body_pos", m->body_pos, 3 * m->nbody)
+  *n = 0; return NULL;
+}
+
 /* ---------------- accessors for the test harness (ctypes) */
 OModel *osim_model(OSim *c) { return c->m; }
 OData *osim_data(OSim *c) { return c->d; }
@@ -1309,6 +1363,7 @@ int osim_int(OSim *c, const char *key) {
   if (!strcmp(key, "nefc")) return d->nefc; if (!strcmp(key, "ncon")) return d->ncon; if (!strcmp(key, "ne")) return d->ne; if (!strcmp(key, "nl")) return d->nl;
   if (!strcmp(key, "solver_iter")) return d->solver_iter; if (!strcmp(key, "unsupported_pairs")) return d->unsupported_pairs;
   if (!strcmp(key, "dropped_contacts")) return d->dropped_contacts; if (!strcmp(key, "MAXV")) return MAXV;
+  if (!strcmp(key, "ngeom")) return c->m->ngeom;
   if (!strcmp(key, "nq")) return c->m->nq; if (!strcmp(key, "nv")) return c->m->nv; if (!strcmp(key, "nbody")) return c->m->nbody;
   return -1;
 }

@@ -167,9 +167,12 @@ def compile_mjcf(path):
         a.update(g.attrib)
         gtype = GEOM_TYPES[a.get('type', 'sphere')]
         if gtype == GEOM_MESH:
-            # visual only in every Cassie model (contype = conaffinity = 0); inertia always comes from <inertial>
+            # visual only in every Cassie model (contype = conaffinity = 0); inertia always comes from <inertial>.  Kept in the table
+            # (zero size, zero bounding radius) so geom ids and per-geom arrays are numbered as in the reference's model
             assert int(a.get('contype', 1)) == 0 and int(a.get('conaffinity', 1)) == 0
-            return
+            a = dict(a)
+            a.pop('size', None)
+            a.pop('fromto', None)
         size = np.zeros(3)
         s = fl(a['size']) if 'size' in a else np.zeros(0)
         pos = fl(a.get('pos', '0 0 0'))

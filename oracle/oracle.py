@@ -83,6 +83,10 @@ def load(ref=False):
     L.osim_check_obstacle_collision.argtypes = [C.c_void_p]
     L.osim_check_self_collision.argtypes = [C.c_void_p]
     L.osim_geom_collision.argtypes = [C.c_void_p, C.c_int]
+    L.osim_model_array.restype = C.POINTER(C.c_double)
+    L.osim_model_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+    L.osim_set_const.argtypes = [C.c_void_p]
+    L.osim_just_set_const.argtypes = [C.c_void_p]
     L.o_pd_input_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
     L.o_core_sim_step.argtypes = [C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_double)]
     return L
@@ -177,6 +181,21 @@ class OracleSim:
 
     def geom_collision(self, group):
         return bool(self.L.osim_geom_collision(self.h, group))
+
+    # ---- model constants (the reference hands out c->m->... pointers, src/cassiemujoco.c:1303-1321) and mj_setConst
+    def model_arr(self, key):
+        """live numpy VIEW of a model array: body_mass, body_ipos, dof_damping, geom_friction, body_invweight0, dof_invweight0, meaninertia."""
+        n = C.c_int()
+        p = self.L.osim_model_array(self.h, key.encode(), C.byref(n))
+        if not p or n.value == 0:
+            raise KeyError(key)
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def set_const(self):
+        self.L.osim_set_const(self.h)
+
+    def just_set_const(self):
+        self.L.osim_just_set_const(self.h)
 
     def efc_J(self):
         n, nv, mv = self.get_int('nefc'), self.nv, self.get_int('MAXV')

@@ -12,13 +12,13 @@
 using namespace cassie;
 
 template <typename real> struct Emu {
-  HostModel hm; DevModel<real> dm; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX], aux[AUX_W]; int counters[8];
-  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.aux = aux; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
+  HostModel hm; DevModel<real> dm; BuildInfo info; std::vector<real> sm; std::vector<int> ism;
+  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX], aux[AUX_W], cenv[CE_W]; int counters[8]; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
-    if (!build_dev_model(hm, dm, err)) return false;
+    if (!build_dev_model(hm, dm, err, &info)) return false;
     sm.assign(scratch_reals(dm.ystride), 0); ism.assign(DFILT_W, 0);
     if (hm.nhfield) hfield.assign((size_t)hm.hfield_nrow[0] * hm.hfield_ncol[0], 0.0f);
     std::vector<real> qpos(QPOS_W_XB), qv(QVEL_W_XB), qa(QVEL_W_XB);
@@ -29,9 +29,25 @@ template <typename real> struct Emu {
     forward();
     return true;
   }
-  void forward() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, 1, 1); }
-  void query() { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, 1, 2); }
-  void step(int nticks) { step_env(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, 0); }
+  void run(int nticks, int mode) { if (use_cenv || use_ext) step_env<real, true>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); else step_env<real, false>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); }
+  void forward() { run(1, 1); }
+  // per-environment model constants + mj_setConst (mode 3 works at the reference configuration, like the kernel wrapper does)
+  void enable_cenv() { if (!use_cenv) { init_cenv_row(dm, cenv); use_cenv = true; } }
+  int model_set(const char *what, const double *v, int n) {   // same slot mapping as the product's cassie_batch_set_* verbs
+    enable_cenv(); int w = 0; cenv_slot(hm, dm.nv, info.geom_dev, what, 0, w);
+    if (w < 0 || w != n) return -1;
+    for (int i = 0; i < w; i++) { int ww; const int sl = cenv_slot(hm, dm.nv, info.geom_dev, what, i, ww); if (sl >= 0) cenv[sl] = (real)v[i]; }
+    return 0;
+  }
+  void set_const() {
+    enable_cenv();
+    std::vector<real> keep(sm.begin() + S_QPOS, sm.begin() + S_QPOS + QPOS_W_XB);
+    for (int i = 0; i < QPOS_W_XB; i++) sm[S_QPOS + i] = dm.qpos0[i];
+    run(1, 3);
+    for (int i = 0; i < QPOS_W_XB; i++) sm[S_QPOS + i] = keep[i];
+  }
+  void query() { run(1, 2); }
+  void step(int nticks) { run(nticks, 0); }
 };
 
 struct Handle { int fp32; Emu<float> f; Emu<double> d; };
@@ -50,6 +66,10 @@ void emu_step(void *p, const double *pd50, int nticks) {
   else { for (int i = 0; i < 50; i++) h->d.pd[i] = pd50[i]; h->d.step(nticks); }
 }
 void emu_set_hfield(void *p, const float *data, int n) { Handle *h = (Handle *)p; std::vector<float> &dst = h->fp32 ? h->f.hfield : h->d.hfield; for (int i = 0; i < n && i < (int)dst.size(); i++) dst[i] = data[i]; }
+int emu_model_set(void *p, const char *what, const double *v, int n) { Handle *h = (Handle *)p; return h->fp32 ? h->f.model_set(what, v, n) : h->d.model_set(what, v, n); }
+void emu_set_const(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.set_const(); else h->d.set_const(); }
+void emu_plain(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.use_ext = false; else h->d.use_ext = false; }   // run the plain instance from now on
+void emu_enable_cenv(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.enable_cenv(); else h->d.enable_cenv(); }
 void emu_query(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.query(); else h->d.query(); }
 void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward(); else h->d.forward(); }
 // generic get/set of named state as doubles.  names: qpos qvel qacc_ws cst obs dbg xfrc ; ints: dfilt counters
@@ -58,7 +78,7 @@ int emu_get(void *p, const char *name, double *out, int n) {
 #define GET(T, E) { const T *src = nullptr; int cnt = 0; \
   if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W_XB; } else if (k == "xqvel") { src = E.xqvel; cnt = 6; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
   else if (k == "cst") { src = E.cst; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
-  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } else if (k == "aux") { src = E.aux; cnt = AUX_W; } \
+  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } else if (k == "aux") { src = E.aux; cnt = AUX_W; } else if (k == "cenv") { src = E.cenv; cnt = CE_W; } \
   if (src) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) out[i] = (double)src[i]; return cnt; } \
   if (k == "dfilt") { int c2 = DFILT_W < n ? DFILT_W : n; for (int i = 0; i < c2; i++) out[i] = E.ism[i]; return c2; } \
   if (k == "counters") { int c2 = 8 < n ? 8 : n; for (int i = 0; i < c2; i++) out[i] = E.counters[i]; return c2; } }
@@ -69,7 +89,7 @@ int emu_set(void *p, const char *name, const double *in, int n) {
   Handle *h = (Handle *)p; std::string k(name);
 #define SET(T, E) { T *dst = nullptr; int cnt = 0; \
   if (k == "qpos") { dst = E.sm.data() + S_QPOS; cnt = QPOS_W_XB; } else if (k == "xqvel") { dst = E.xqvel; cnt = 6; } else if (k == "qvel") { dst = E.qvel; cnt = 32; } else if (k == "qacc_ws") { dst = E.qacc_ws; cnt = 32; } \
-  else if (k == "cst") { dst = E.cst; cnt = CST_W; } else if (k == "xfrc") { dst = E.xfrc; cnt = XFRC_W; } \
+  else if (k == "cst") { dst = E.cst; cnt = CST_W; } else if (k == "xfrc") { dst = E.xfrc; cnt = XFRC_W; } else if (k == "cenv") { dst = E.cenv; cnt = CE_W; } \
   if (dst) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) dst[i] = (T)in[i]; return cnt; } }
   if (h->fp32) SET(float, h->f) else SET(double, h->d)
   return -1;

@@ -32,6 +32,10 @@ def load():
     L.emu_step.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
     L.emu_forward.argtypes = [C.c_void_p]
     L.emu_query.argtypes = [C.c_void_p]
+    L.emu_set_const.argtypes = [C.c_void_p]
+    L.emu_model_set.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+    L.emu_enable_cenv.argtypes = [C.c_void_p]
+    L.emu_plain.argtypes = [C.c_void_p]
     L.emu_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
     L.emu_set.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
     return L
@@ -69,6 +73,20 @@ class EmuSim:
 
     def query(self):
         self.L.emu_query(self.h)
+
+    def plain(self):
+        """switch to the plain kernel instance (no derived-quantity rows, no per-env constants), the one the throughput path runs."""
+        self.L.emu_plain(self.h)
+
+    def enable_cenv(self):
+        self.L.emu_enable_cenv(self.h)
+
+    def set_const(self):
+        self.L.emu_set_const(self.h)
+
+    def model_set(self, what, values):
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        assert self.L.emu_model_set(self.h, what.encode(), a.ctypes.data_as(C.POINTER(C.c_double)), a.size) == 0, what
 
 
 def _emu_set_hfield(self, data):
