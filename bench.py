@@ -270,6 +270,18 @@ def gpu_arm(args, rank, local_rank, world):
             rows5 = P.pd_rows(n4, pTarget=np.array(PD_TARGET) + amp * np.sin(ph + np.array([0] * 5 + [np.pi] * 5)), pGain=PD_PGAIN, dGain=PD_DGAIN)
             b5.set_pd(rows5)
             others['config5_8192_envs_per_gpu_tray_box'] = timed(b5, 80); b5.close()
+            # SURVEY 8f-2 / 8f-3 on the config-2 workload: derived-quantity rows on, then per-env randomised constants + set_const (extended kernel instance)
+            b6 = P.CassieBatch(n, device=local_rank, precision=P.FP32)
+            b6.set_pd(P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)); b6.set_qpos(jittered_qpos(b6.qpos()[0], n)); b6.forward()
+            b6.enable_aux()
+            others['config2_with_derived_quantity_rows'] = timed(b6, 80)
+            rng6 = np.random.default_rng(5)
+            b6.set_model('body_mass', b6.get_model('body_mass') * rng6.uniform(0.8, 1.2, (n, 1)))
+            b6.set_model('dof_damping', b6.get_model('dof_damping') * rng6.uniform(0.5, 2.0, (n, 32)))
+            fr = b6.get_model('geom_friction'); fr[:, 0::3] *= rng6.uniform(0.6, 1.1, (n, 1)); b6.set_model('geom_friction', fr)
+            t0 = time.time(); b6.set_const(reset_state=True); b6.sync(); t_sc = time.time() - t0
+            b6.set_qpos(jittered_qpos(b6.qpos()[0], n)); b6.forward()
+            others['config2_with_randomised_constants_and_rows'] = dict(timed(b6, 80), set_const_ms_for_all_envs=1e3 * t_sc); b6.close()
         except Exception as ex:
             others['error'] = repr(ex)
     # ---- reduce over ranks
