@@ -45,7 +45,7 @@ __device__ __forceinline__ void tma_stage(void *dst_smem, const void *src_gmem, 
 }
 
 template <typename real> __host__ __device__ constexpr size_t model_bytes() { return (sizeof(DevModel<real>) + 127) / 128 * 128; }
-template <typename real> __host__ __device__ constexpr size_t warp_bytes(int ystride) { return ((size_t)scratch_reals(ystride) * sizeof(real) + 127) / 128 * 128; }
+template <typename real> __host__ __device__ constexpr size_t warp_bytes(int ystride, bool ext) { return ((size_t)(ext ? scratch_reals_ext(ystride) : scratch_reals(ystride)) * sizeof(real) + 127) / 128 * 128; }
 
 // mode 0: step nticks; mode 1: mj_forward only
 template <typename real, bool DR>
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
   tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
   const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
-  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>(A.ystride));
+  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>(A.ystride, DR));
   const int qw = A.qpos_w, vw = A.qvel_w;
   const DevModel<real> &cm = *cmp;
   // persistent warps: every warp pulls environment indices from a global ticket counter until the batch is exhausted, so a warp
@@ -197,7 +197,8 @@ struct BatchBase {
 };
 
 template <typename real> struct Batch : BatchBase {
-  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; size_t smem = 0; int resident_ctas = 1, QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
+  DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; int QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
+  struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[2];   // [0] plain instance, [1] extended instance
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr;   // pinned staging for the AoS entry point
   float *d_hfield = nullptr; unsigned char *d_mask = nullptr; DevModel<real> h_model_copy{}; int geom_dev[256]; void *d_row = nullptr;
@@ -225,29 +226,36 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemset(A.pd, 0, sizeof(real) * n * PD_W)); CUDA_OK(cudaMemset(A.obs, 0, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMemset(A.counters, 0, sizeof(int) * n * 8));
     if (debug) { CUDA_OK(cudaMalloc(&A.dbg, sizeof(real) * n * D_SIZE)); CUDA_OK(cudaMemset(A.dbg, 0, sizeof(real) * n * D_SIZE)); }
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true;
-    // warps per CTA: maximise resident warps per SM over 1..4 CTAs per SM (each CTA carries its own copy of the model block)
-    int dev_smem = 0, sm_smem = 0;
+    // warps per CTA: maximise resident warps per SM over 1..4 CTAs per SM (each CTA carries its own copy of the model block); the two kernel
+    // instances have different scratch sizes, hence their own launch shapes
+    int dev_smem = 0, sm_smem = 0, sms = 0;
     CUDA_OK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    const char *w = getenv("CASSIE_B200_WPB");
-    if (w) wpb = atoi(w);
-    else {
-      int best = 0, kk[5] = {0, 0, 0, 0, 0}; wpb = 1;
-      for (int ctas = 4; ctas >= 1; --ctas) {
-        long per_cta = (long)sm_smem / ctas - 1024; if (per_cta > dev_smem) per_cta = dev_smem;
-        int k = (int)((per_cta - (long)model_bytes<real>()) / (long)warp_bytes<real>(hmodel_ystride)); if (k > 16) k = 16; if (k < 0) k = 0;
-        kk[ctas] = k; if (k * ctas > best) best = k * ctas;
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    for (int ext = 0; ext < 2; ++ext) {
+      const long wb = (long)warp_bytes<real>(hmodel_ystride, ext != 0), mb = (long)model_bytes<real>() + 256;   // + static shared (mbarrier) and alignment slack
+      const char *w = getenv("CASSIE_B200_WPB"); int k_sel = 1;
+      if (w) { k_sel = atoi(w); const int kmax = (int)(((long)dev_smem - mb) / wb); if (k_sel > kmax) k_sel = kmax; }
+      else {
+        int best = 0, kk[5] = {0, 0, 0, 0, 0};
+        for (int ctas = 4; ctas >= 1; --ctas) {
+          long per_cta = (long)sm_smem / ctas - 1024; if (per_cta > dev_smem) per_cta = dev_smem;
+          int k = (int)((per_cta - mb) / wb); if (k > 16) k = 16; if (k < 0) k = 0;
+          kk[ctas] = k; if (k * ctas > best) best = k * ctas;
+        }
+        // several small CTAs refill an SM more smoothly than one big one: take the most CTAs within 15 % of the best residency
+        for (int ctas = 4; ctas >= 1; --ctas) if (kk[ctas] >= 1 && kk[ctas] * ctas * 100 >= best * 85) { k_sel = kk[ctas]; break; }
       }
-      // several small CTAs refill an SM more smoothly than one big one: take the most CTAs within 15 % of the best residency
-      for (int ctas = 4; ctas >= 1; --ctas) if (kk[ctas] >= 1 && kk[ctas] * ctas * 100 >= best * 85) { wpb = kk[ctas]; break; }
+      if (k_sel < 1 || k_sel > 16 || (long)model_bytes<real>() + k_sel * wb > (long)dev_smem) { set_err("not enough shared memory per block"); return false; }
+      cfg[ext].wpb = k_sel; cfg[ext].smem = model_bytes<real>() + (size_t)k_sel * wb;
+      int per_sm = 0;
+      if (ext) { CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));
+                 CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real, true>, 32 * k_sel, cfg[ext].smem)); }
+      else { CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));
+             CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real, false>, 32 * k_sel, cfg[ext].smem)); }
+      cfg[ext].resident_ctas = per_sm * sms < 1 ? 1 : per_sm * sms;
     }
-    if (wpb < 1 || wpb > 16 || model_bytes<real>() + (size_t)wpb * warp_bytes<real>(hmodel_ystride) > (size_t)dev_smem) { set_err("not enough shared memory per block"); return false; }
-    smem = model_bytes<real>() + (size_t)wpb * warp_bytes<real>(hmodel_ystride);
-    CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { int per_sm = 0, per_sm_dr = 0, sms = 0; CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real, false>, 32 * wpb, smem));
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dr, cassie_step_kernel<real, true>, 32 * wpb, smem)); if (per_sm_dr < per_sm) per_sm = per_sm_dr;
-      CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)); resident_ctas = per_sm * sms; if (resident_ctas < 1) resident_ctas = 1; }
+    wpb = cfg[0].wpb;
     return reset(nullptr);
   }
   bool reset(const unsigned char *mask) override {
@@ -392,10 +400,11 @@ template <typename real> struct Batch : BatchBase {
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
-    int grid = (n + wpb - 1) / wpb; if (grid > resident_ctas) grid = resident_ctas;
+    const LaunchCfg &c = cfg[(A.cenv || A.aux) ? 1 : 0];
+    int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
-    if (A.cenv || A.aux) cassie_step_kernel<real, true><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
-    else cassie_step_kernel<real, false><<<grid, 32 * wpb, smem, stream>>>(d_model, A, nticks, mode);
+    if (A.cenv || A.aux) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
+    else cassie_step_kernel<real, false><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
     launches++;
     CUDA_OK(cudaGetLastError());
     return true;

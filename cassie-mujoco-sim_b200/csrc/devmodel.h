@@ -128,18 +128,20 @@ constexpr int S_DINV = S_QLD + NM_MAX;          // [32]
 constexpr int S_DSQI = S_DINV + 32;             // [32]
 constexpr int S_QPOS = S_DSQI + 32;             // [44]
 constexpr int S_VEC = S_QPOS + 44;              // [6][32] general vectors ([96..127]: IMU stash; [128..159]: exchange buffer; [160..183]: extra-body qvel / qacc_smooth / qacc_ws / qacc)
-constexpr int S_GEOM = S_VEC + 192;             // [16][12] world pos + rotation matrix (column 2 = z axis)
-constexpr int S_CON = S_GEOM + 192;             // [MAXCON][16]
+constexpr int S_CON = S_VEC + 192;              // [MAXCON][16]
 constexpr int S_EFC = S_CON + MAXCON * 16;               // [NEFC][4]: row-build scalars {.., pos, src, ineq} then solver constants {b, 1/A, A, +-R}
 constexpr int S_Y = S_EFC + 4 * NEFC;           // [NEFC][ystride] constraint matrix; before the constraint stage it holds the temporaries below
 CASSIE_HD inline constexpr int scratch_reals(int ystride) { return S_Y + NEFC * ystride; }
+// the extended instance (derived-quantity rows) appends a [32][6] copy of cdof that outlives the constraint stage
+CASSIE_HD inline constexpr int scratch_reals_ext(int ystride) { return scratch_reals(ystride) + 192; }
 // temporaries inside the S_Y region (dead before the first constraint row is written)
 constexpr int T_CINERT = 0;                     // [32][10]
 constexpr int T_CRB = 320;                      // [32][10]; during kinematics: xanchor[32][3], xaxis[32][3], qloc[32][4]; later chain sums [32][6]
 constexpr int T_CVEL = 640;                     // [32][6]
 constexpr int T_CFRC = 832;                     // [32][6]
 constexpr int T_CDOFD = 1024;                   // [32][6]
-static_assert(T_CDOFD + 192 <= NEFC * YSTRIDE_MAIN, "temporaries must fit in the constraint-matrix region");
+constexpr int T_GEOM = 1216;                    // [16][12] geom world poses (position + rotation by columns), live from the collision stage until the contact list is written
+static_assert(T_GEOM + 192 <= NEFC * YSTRIDE_MAIN, "temporaries must fit in the constraint-matrix region");
 static_assert(NEFC >= 48 && 16 * YSTRIDE_MAX <= S_QLD - S_XPOS, "the dense solver path keeps A in rows 32..47 of Y and in the kinematics buffers");
 // slots of a row's 4 scalars while the rows are being built (overwritten by the solver constants afterwards)
 constexpr int E_POS = 0, E_SRC = 1, E_INEQ = 2;

@@ -404,7 +404,7 @@ CFN real half_solve_row(const DevModel<real> &cm, const real *sm, real *yy, int 
 template <typename real>
 CFN void aux_foot_velocities(const DevModel<real> &cm, real *sm, real *aux) {
   DECL_LANE
-  const real *vecs = sm + S_VEC, *cdofs = sm + S_GEOM;
+  const real *vecs = sm + S_VEC, *cdofs = sm + scratch_reals(cm.ystride);   // the extended instance's tail
   LANES
     if (l < 12) {
       const int fb = cm.foot_body[l / 6], k = l % 6; real acc = 0;
@@ -793,7 +793,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   }
 
   // ================= collision (lane = candidate geom pair) =================
-  real *geom = sm + S_GEOM;
+  real *geom = sm + S_Y + T_GEOM;   // the smooth-dynamics temporaries below it are dead; the constraint rows are written after the contact list
   LANES
     if (l < cm.ngeom) {
       const int b = cm.geom_body[l]; real v[3];
@@ -971,7 +971,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   // ================= derived quantities, part 2 (while the kinematics buffers are alive): foot positions, toe / heel points, a copy of
   // cdof for the foot velocities (cassie_sim_foot_positions :1608-1621; site_xpos of the toe / heel sites :1888-1889)
   if (auxr) {
-    real *cdofs = geom;   // the geom poses are dead once the contacts are listed
+    real *cdofs = sm + scratch_reals(ys);   // the extended instance's tail
     LANES
       if (l < nv) for (int k = 0; k < 6; ++k) cdofs[6 * l + k] = cdof[6 * l + k];
       if (l < 6) { const int fb = cm.foot_body[l / 3], k = l % 3; real v = fb >= 0 ? xpos[3 * fb + k] : real(0); if (k == 2) v -= cm.foot_offset; auxr[AX_FOOT_POS + l] = v; }

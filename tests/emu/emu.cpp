@@ -19,7 +19,7 @@ template <typename real> struct Emu {
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
     if (!build_dev_model(hm, dm, err, &info)) return false;
-    sm.assign(scratch_reals(dm.ystride), 0); ism.assign(DFILT_W, 0);
+    sm.assign(scratch_reals_ext(dm.ystride), 0); ism.assign(DFILT_W, 0);
     if (hm.nhfield) hfield.assign((size_t)hm.hfield_nrow[0] * hm.hfield_ncol[0], 0.0f);
     std::vector<real> qpos(QPOS_W_XB), qv(QVEL_W_XB), qa(QVEL_W_XB);
     init_env_rows(hm, qpos.data(), qv.data(), qa.data(), cst, ism.data(), xfrc);
