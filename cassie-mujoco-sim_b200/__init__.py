@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcassie_b200.so')
 MODEL_DIR = os.path.join(_HERE, 'models')
 FP32, FP64 = 0, 1
-PD_WIDTH, OBS_WIDTH, AUX_WIDTH = 52, 64, 64
+PD_WIDTH, OBS_WIDTH, AUX_WIDTH = 52, 96, 64
 # slices of a derived-quantity row (CASSIE_AUX_* in include/cassie_b200.h)
 AUX = dict(foot_force=slice(0, 12), toe_force=slice(12, 18), heel_force=slice(18, 24), foot_pos=slice(24, 30), foot_vel=slice(30, 42),
            cm_pos=slice(42, 45), cm_vel=slice(45, 48), angmom=slice(48, 51), obstacle=51, self_collision=52, group_mask=53, ncon=54)
@@ -387,7 +387,7 @@ class CassieBatch:
         self.L.cassie_batch_set_stream(self.h, C.c_void_p(cuda_stream_ptr))
 
     def torch_view(self, field):
-        """zero-copy torch tensor over a device state array (qpos [n,36], qvel [n,32], pd [n,52], obs [n,64])."""
+        """zero-copy torch tensor over a device state array (qpos [n,36], qvel [n,32], pd [n,52], obs [n,96])."""
         import torch
         self.L.cassie_batch_row_width.argtypes = [C.c_void_p, C.c_char_p]
         width = self.L.cassie_batch_row_width(self.h, field.encode())

@@ -369,8 +369,13 @@ template <typename real> struct Batch : BatchBase {
       memset(y, 0, sizeof *y);
       for (int i = 0; i < 10; i++) { y->motor.position[i] = o[OB_MPOS + i]; y->motor.velocity[i] = o[OB_MVEL + i]; y->motor.torque[i] = o[OB_MTORQUE + i]; }
       for (int i = 0; i < 6; i++) { y->joint.position[i] = o[OB_JPOS + i]; y->joint.velocity[i] = o[OB_JVEL + i]; }
-      for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_QUAT + i];
-      for (int i = 0; i < 3; i++) y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i];   // translationalAcceleration is an estimator output (not a copy of the accelerometer)
+      for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_EST_QUAT + i];
+      for (int i = 0; i < 3; i++) { y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_EST_ACC + i]; }
+      for (int sd = 0; sd < 2; sd++) {   // decoded stateless part of the estimator: foot pose (pelvis frame) and velocities (foot frame)
+        state_foot_out_t *f = sd ? &y->rightFoot : &y->leftFoot; const real *fo = o + OB_FOOT + 13 * sd;
+        for (int i = 0; i < 3; i++) { f->position[i] = fo[i]; f->footRotationalVelocity[i] = fo[7 + i]; f->footTranslationalVelocity[i] = fo[10 + i]; }
+        for (int i = 0; i < 4; i++) f->orientation[i] = fo[3 + i];
+      }
       for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
       y->radio.signalGood = true; y->battery.stateOfCharge = 1;
     }

@@ -83,7 +83,7 @@ constexpr int CST_W = 192;      // controller / sensor state, layout below
 constexpr int DFILT_W = 96;     // int32 drive FIR taps [10][9] padded
 constexpr int PD_W = 52;        // torque, pTarget, dTarget, pGain, dGain for the 10 motors (+2 pad)
 constexpr int XFRC_W = 8;       // force xyz, torque xyz, body id (as real), pad
-constexpr int OBS_W = 64;       // the dynamic subset of cassie_out_t copied out at src/cassiemujoco.c:1127
+constexpr int OBS_W = 96;       // the dynamic subset of cassie_out_t copied out at src/cassiemujoco.c:1127 + the decoded estimator outputs
 // CST offsets
 constexpr int CS_SENSOR = 0;    // sensordata[29]
 constexpr int CS_ACTVEL = 32;   // actuator_velocity[10]
@@ -96,6 +96,10 @@ constexpr int CS_TIME = 186;
 constexpr int CS_STO = 187;     // radio channel 8 (safe-torque-off when < 1)
 // OBS offsets
 constexpr int OB_MPOS = 0, OB_MVEL = 10, OB_MTORQUE = 20, OB_JPOS = 30, OB_JVEL = 36, OB_QUAT = 42, OB_GYRO = 46, OB_ACCEL = 49, OB_MAG = 52, OB_TIME = 55;
+// stateless part of the reference's estimator (state_output_step, closed source; semantics recovered by probing the archive):
+constexpr int OB_EST_ACC = 56;    // [3] pelvis.translationalAcceleration
+constexpr int OB_FOOT = 60;       // [2][13] per foot: position 3, orientation 4 (pelvis frame), rotational velocity 3, translational velocity 3 (foot frame)
+constexpr int OB_EST_QUAT = 86;   // [4] pelvis.orientation (IMU quaternion with w >= 0)
 
 // derived-quantity row (optional, cassie_batch_enable_aux): the reference's read-only queries (src/cassiemujoco.c:1586-1961) as by-products
 constexpr int AUX_W = 64;

@@ -100,7 +100,7 @@ void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
 #define CASSIE_B200_FP32 0 /* throughput build: state and arithmetic in fp32 */
 #define CASSIE_B200_FP64 1 /* parity build: state and arithmetic in fp64 */
 #define CASSIE_PD_WIDTH 52  /* compact motor-PD row: torque[10] pTarget[10] dTarget[10] pGain[10] dGain[10] pad[2] */
-#define CASSIE_OBS_WIDTH 64 /* compact observation row, see cassie_batch_get_obs */
+#define CASSIE_OBS_WIDTH 96 /* compact observation row, see cassie_batch_get_obs */
 #define CASSIE_AUX_WIDTH 64 /* derived-quantity row, see cassie_batch_get_aux */
 /* offsets inside a derived-quantity row */
 #define CASSIE_AUX_FOOT_FORCE 0   /* [12] cassie_sim_foot_forces layout: left xyz, 3 zeros, right xyz, 3 zeros */
@@ -127,10 +127,11 @@ int cassie_batch_nv(const cassie_batch_t *b);
 void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask);
 
 /* cassie_sim_step_pd for every environment: pd_in[n_env] host AoS in, state_out[n_env] host AoS out (may be NULL).
- * Replaces n_env calls of src/cassiemujoco.c:1147-1157.  Synchronous.  state_out carries the pass-through fields of the
- * reference's state_output_step (motor/joint position+velocity+torque, IMU orientation and gyro, radio, battery; verified equal
- * to the real estimator's outputs for these fields); the raw accelerometer / magnetometer are in the compact observation row;
- * the estimator-only fields are zero (scope). */
+ * Replaces n_env calls of src/cassiemujoco.c:1147-1157.  Synchronous.  state_out carries the stateless part of the reference's
+ * state_output_step, decoded from the closed archive and checked equal to it to 1e-11: motor / joint position + velocity + torque,
+ * pelvis.orientation (w >= 0), rotationalVelocity, translationalAcceleration, both feet's position / orientation (pelvis frame) and
+ * footRotationalVelocity / footTranslationalVelocity (foot frame), radio, battery.  The stateful outputs (pelvis.position,
+ * translationalVelocity, externalForce / externalMoment, toe / heel forces, terrain) are zero (scope). */
 void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_out_t *state_out);
 
 /* throughput path: compact rows.  pd: host [n_env][CASSIE_PD_WIDTH] doubles, copied to the device (and converted to the batch
@@ -139,7 +140,9 @@ void cassie_batch_set_pd(cassie_batch_t *b, const double *pd);
 void cassie_batch_step(cassie_batch_t *b, int nticks);
 void cassie_batch_sync(cassie_batch_t *b);
 /* host copies (synchronous): qpos [n][35], qvel [n][32], time [n], obs [n][CASSIE_OBS_WIDTH] =
- * motor pos[10] vel[10] torque[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3] mag[3], time, pad */
+ * motor pos[10] vel[10] torque[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3] mag[3], time (0..55);
+ * estimator: translationalAcceleration[3] (56), pad, per foot {position 3, orientation 4, rotational velocity 3, translational
+ * velocity 3} left (60..72) right (73..85), pelvis.orientation[4] (86..89), pad */
 void cassie_batch_get_qpos(cassie_batch_t *b, double *out);
 void cassie_batch_set_qpos(cassie_batch_t *b, const double *in);
 void cassie_batch_get_qvel(cassie_batch_t *b, double *out);
@@ -186,7 +189,7 @@ int cassie_batch_hfield_nrow(const cassie_batch_t *b);
 int cassie_batch_hfield_ncol(const cassie_batch_t *b);
 
 /* zero-copy access for a PyTorch / DLPack caller: device pointer of a state array ("qpos" [n][36], "qvel" [n][32],
- * "pd" [n][52], "obs" [n][64], "xfrc" [n][8]) in the batch precision; the stream all work is enqueued on (cudaStream_t). */
+ * "pd" [n][52], "obs" [n][96], "xfrc" [n][8], "aux" [n][64]) in the batch precision; the stream all work is enqueued on (cudaStream_t). */
 void *cassie_batch_device_ptr(cassie_batch_t *b, const char *field);
 void cassie_batch_set_stream(cassie_batch_t *b, void *cuda_stream);
 void *cassie_batch_get_stream(cassie_batch_t *b);

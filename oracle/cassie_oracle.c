@@ -1063,6 +1063,73 @@ void o_core_sim_step(const double u[10], const cassie_out_t *o, double out[10]) 
   for (int i = 0; i < 10; i++) { double t = sto ? 0.0 : u[i] * scale + add[i]; out[i] = clampd(t, -lim[i], lim[i]); }
 }
 
+/* ---- state_output_step: the STATELESS part of the closed estimator, decoded by probing the archive (oracle/probe_estimator.c,
+ * oracle/probe_est_tools.py; agreement with the archive 1e-14 over random inputs, tests/test_agility_twins.py):
+ *  - pass-through: motor / joint position, velocity, torque, radio, battery, IMU gyro;
+ *  - pelvis.orientation = IMU quaternion with its sign chosen so that w >= 0;
+ *  - pelvis.translationalAcceleration = accelerometer - R(q)' (0, 0, 9.806) - w x (w x r)   (body frame, gravity removed, moved from the
+ *    IMU site to the pelvis origin without the angular-acceleration term);
+ *  - per foot: forward kinematics of a 7-link chain pelvis -> hipRoll -> hipYaw -> hipPitch -> knee -> shin -> tarsus -> foot with the MJCF's
+ *    offsets (model/cassie.xml:96-152) and EXACT quarter turns, driven by the MEASURED angles (motor encoders for the five drives, joint
+ *    encoders for shin and tarsus; the foot joint encoder is not used).  position = the point (0.01762, 0.05219, 0) of the foot frame in
+ *    the pelvis frame; orientation = foot frame turned by a fixed rotation (40 degrees), as a quaternion (mat2quat branches as MuJoCo's);
+ *    footRotationalVelocity / footTranslationalVelocity = Jacobian times the measured rates, expressed in THAT FOOT FRAME.
+ * Not decoded (left zero): pelvis.position / translationalVelocity / externalForce / externalMoment, toe / heel forces, terrain (stateful). */
+static void est_mat2quat(double *q, const double *R) { /* R row-major */
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) { double s = sqrt(t + 1) * 2; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { double s = sqrt(1 + R[0] - R[4] - R[8]) * 2; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { double s = sqrt(1 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { double s = sqrt(1 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+}
+void o_est_foot(int side, const double ang[7], const double rate[7], double pos[3], double quat[4], double rotvel[3], double linvel[3]) {
+  /* ang / rate: hipRoll, hipYaw, hipPitch, knee, shin, tarsus, foot */
+  const double sg = side ? -1.0 : 1.0;
+  const double off[7][3] = {{0.021, 0.135 * sg, 0}, {0, 0, -0.07}, {0, 0, -0.09}, {0.12, 0, 0.0045 * sg}, {0.06068, 0.04741, 0}, {0.43476, 0.02, 0}, {0.408, -0.04, 0}};
+  /* fixed frame of each link in its parent (columns = x, y, z axes): quarter turns for the three hip links, identity below */
+  static const double F[3][9] = {{0, 0, 1, 0, 1, 0, -1, 0, 0}, {0, 0, -1, 0, 1, 0, 1, 0, 0}, {0, 1, 0, 0, 0, -1, -1, 0, 0}};
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, anchor[7][3], axis[7][3];
+  for (int i = 0; i < 7; i++) {
+    double v[3], T[9], c = cos(ang[i]), s = sin(ang[i]);
+    mulMatVec3(v, R, off[i]); for (int k = 0; k < 3; k++) p[k] += v[k];
+    if (i < 3) { mulMatMat3(T, R, F[i]); copyv(R, T, 9); }
+    const double Z[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+    mulMatMat3(T, R, Z); copyv(R, T, 9);
+    copyv(anchor[i], p, 3); axis[i][0] = R[2]; axis[i][1] = R[5]; axis[i][2] = R[8];
+  }
+  const double c40 = cos(40 * M_PI / 180), s40 = sin(40 * M_PI / 180), Roff[9] = {-c40, 0, -s40, s40, 0, -c40, 0, -1, 0}, loc[3] = {0.01762, 0.05219, 0};
+  double Rf[9], v[3], w[3] = {0, 0, 0}, vl[3] = {0, 0, 0};
+  mulMatMat3(Rf, R, Roff); mulMatVec3(v, R, loc); for (int k = 0; k < 3; k++) pos[k] = p[k] + v[k];
+  est_mat2quat(quat, Rf);
+  for (int i = 0; i < 7; i++) {
+    double d[3] = {pos[0] - anchor[i][0], pos[1] - anchor[i][1], pos[2] - anchor[i][2]}, cr[3];
+    cross(cr, axis[i], d);
+    for (int k = 0; k < 3; k++) { w[k] += axis[i][k] * rate[i]; vl[k] += cr[k] * rate[i]; }
+  }
+  mulMatTVec3(rotvel, Rf, w); mulMatTVec3(linvel, Rf, vl);
+}
+void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
+  cassie_out_t out = *o;
+  memset(y, 0, sizeof *y);
+  for (int i = 0; i < 10; i++) { elmo_out_t *e = drive_ptr(&out, i); y->motor.position[i] = e->position; y->motor.velocity[i] = e->velocity; y->motor.torque[i] = e->torque; }
+  for (int i = 0; i < 6; i++) { cassie_joint_out_t *j = joint_ptr(&out, i); y->joint.position[i] = j->position; y->joint.velocity[i] = j->velocity; }
+  const double *q = out.pelvis.vectorNav.orientation, sgn = q[0] < 0 ? -1.0 : 1.0;
+  for (int k = 0; k < 4; k++) y->pelvis.orientation[k] = sgn * q[k];
+  copyv(y->pelvis.rotationalVelocity, out.pelvis.vectorNav.angularVelocity, 3);
+  { /* accelerometer moved from the IMU (r = (0.03155, 0, -0.079996) from the pelvis origin; the MJCF site has -0.07996, model/cassie.xml:87) to the pelvis origin, centripetal part only: a - w x (w x r) */
+    double R[9], wr[3], wwr[3]; const double r[3] = {0.03155, 0, -0.079996}, *w = out.pelvis.vectorNav.angularVelocity;
+    quat2Mat(R, q); cross(wr, w, r); cross(wwr, w, wr);
+    for (int k = 0; k < 3; k++) y->pelvis.translationalAcceleration[k] = out.pelvis.vectorNav.linearAcceleration[k] - R[6 + k] * 9.806 - wwr[k]; }
+  for (int s = 0; s < 2; s++) {
+    state_foot_out_t *f = s ? &y->rightFoot : &y->leftFoot; double ang[7], rate[7];
+    for (int i = 0; i < 4; i++) { ang[i] = y->motor.position[5 * s + i]; rate[i] = y->motor.velocity[5 * s + i]; }
+    ang[4] = y->joint.position[3 * s]; rate[4] = y->joint.velocity[3 * s]; ang[5] = y->joint.position[3 * s + 1]; rate[5] = y->joint.velocity[3 * s + 1];
+    ang[6] = y->motor.position[5 * s + 4]; rate[6] = y->motor.velocity[5 * s + 4];
+    o_est_foot(s, ang, rate, f->position, f->orientation, f->footRotationalVelocity, f->footTranslationalVelocity);
+  }
+  copyv(y->radio.channel, out.pelvis.radio.channel, 16); y->radio.signalGood = true; y->battery.stateOfCharge = out.pelvis.battery.stateOfCharge;
+}
+
 OSim *osim_new(const char *model_path) {
   OSim *c = calloc(1, sizeof(OSim));
   c->m = omodel_load(model_path); if (!c->m) { free(c); return NULL; }
@@ -1156,11 +1223,7 @@ void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassi
 #ifdef ORACLE_USE_AGILITY_REF
     state_output_step(c->est, &out, y);
 #else
-    memset(y, 0, sizeof *y); /* pass-through subset only */
-    for (int i = 0; i < 10; i++) { elmo_out_t *e = drive_ptr(&out, i); y->motor.position[i] = e->position; y->motor.velocity[i] = e->velocity; y->motor.torque[i] = e->torque; }
-    for (int i = 0; i < 6; i++) { cassie_joint_out_t *j = joint_ptr(&out, i); y->joint.position[i] = j->position; y->joint.velocity[i] = j->velocity; }
-    copyv(y->pelvis.orientation, out.pelvis.vectorNav.orientation, 4); copyv(y->pelvis.rotationalVelocity, out.pelvis.vectorNav.angularVelocity, 3);
-    copyv(y->radio.channel, out.pelvis.radio.channel, 16); y->radio.signalGood = true; y->battery.stateOfCharge = out.pelvis.battery.stateOfCharge;
+    o_state_output_step(&out, y); /* the decoded stateless subset */
 #endif
   }
 }

@@ -1,0 +1,47 @@
+/* Black-box probe of the reference's closed estimator block (state_output_step in src/libagilitycassie.a).  TEST INFRASTRUCTURE / study aid:
+ * built by `make -C oracle probe` into oracle/_ref/libprobe_est.so (needs /root/reference); never shipped, never on the product path.
+ * probe_est(in[45], ncalls, out[123]): in = motor pos[10] vel[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3], mag[3];
+ * a fresh estimator is fed the same cassie_out `ncalls` times; out = state_out_t flattened as 123 doubles (field order of the struct). */
+#include <string.h>
+#include <stdlib.h>
+#include "../include/cassie_bus.h"
+typedef struct StateOutput state_output_t;
+state_output_t *state_output_alloc(void); void state_output_setup(state_output_t *); void state_output_free(state_output_t *);
+void state_output_step(state_output_t *, const cassie_out_t *, state_out_t *);
+static elmo_out_t *drv(cassie_out_t *o, int i) { cassie_leg_out_t *l = i < 5 ? &o->leftLeg : &o->rightLeg; elmo_out_t *t[5] = {&l->hipRollDrive, &l->hipYawDrive, &l->hipPitchDrive, &l->kneeDrive, &l->footDrive}; return t[i % 5]; }
+static cassie_joint_out_t *jnt(cassie_out_t *o, int i) { cassie_leg_out_t *l = i < 3 ? &o->leftLeg : &o->rightLeg; cassie_joint_out_t *t[3] = {&l->shinJoint, &l->tarsusJoint, &l->footJoint}; return t[i % 3]; }
+static void fill(cassie_out_t *o, const double *in) {
+  static const double tl[5] = {140.63, 140.63, 216.16, 216.16, 45.14}, gr[5] = {25, 25, 16, 16, 50};
+  memset(o, 0, sizeof *o); o->isCalibrated = 1;
+  o->pelvis.battery.dataGood = 1; o->pelvis.battery.stateOfCharge = 1;
+  o->pelvis.radio.radioReceiverSignalGood = 1; o->pelvis.radio.receiverMedullaSignalGood = 1; o->pelvis.radio.channel[8] = 1;
+  o->pelvis.vectorNav.dataGood = 1; o->pelvis.vectorNav.pressure = 101.325; o->pelvis.vectorNav.temperature = 25;
+  for (int i = 0; i < 10; i++) { elmo_out_t *e = drv(o, i); e->statusWord = 0x0637; e->dcLinkVoltage = 48; e->driveTemperature = 30; e->torqueLimit = tl[i % 5]; e->gearRatio = gr[i % 5]; e->position = in[i]; e->velocity = in[10 + i]; }
+  for (int i = 0; i < 6; i++) { jnt(o, i)->position = in[20 + i]; jnt(o, i)->velocity = in[26 + i]; }
+  for (int k = 0; k < 4; k++) o->pelvis.vectorNav.orientation[k] = in[32 + k];
+  for (int k = 0; k < 3; k++) { o->pelvis.vectorNav.angularVelocity[k] = in[36 + k]; o->pelvis.vectorNav.linearAcceleration[k] = in[39 + k]; o->pelvis.vectorNav.magneticField[k] = in[42 + k]; }
+}
+static void flat(const state_out_t *y, double *out) {
+  int n = 0;
+#define PUT(a, c) do { for (int k_ = 0; k_ < (c); k_++) out[n++] = (a)[k_]; } while (0)
+  PUT(y->pelvis.position, 3); PUT(y->pelvis.orientation, 4); PUT(y->pelvis.rotationalVelocity, 3); PUT(y->pelvis.translationalVelocity, 3);
+  PUT(y->pelvis.translationalAcceleration, 3); PUT(y->pelvis.externalMoment, 3); PUT(y->pelvis.externalForce, 3);            /* 0..21 */
+  const state_foot_out_t *f[2] = {&y->leftFoot, &y->rightFoot};
+  for (int s = 0; s < 2; s++) { PUT(f[s]->position, 3); PUT(f[s]->orientation, 4); PUT(f[s]->footRotationalVelocity, 3); PUT(f[s]->footTranslationalVelocity, 3); PUT(f[s]->toeForce, 3); PUT(f[s]->heelForce, 3); } /* 22..40, 41..59 */
+  PUT(&y->terrain.height, 1); PUT(y->terrain.slope, 2);                                                                       /* 60..62 */
+  PUT(y->motor.position, 10); PUT(y->motor.velocity, 10); PUT(y->motor.torque, 10); PUT(y->joint.position, 6); PUT(y->joint.velocity, 6); /* 63..104 */
+  (void)n;
+}
+void probe_est(const double *in, int ncalls, double *out) {
+  cassie_out_t o; state_out_t y; fill(&o, in);
+  state_output_t *e = state_output_alloc(); state_output_setup(e);
+  for (int i = 0; i < ncalls; i++) state_output_step(e, &o, &y);
+  flat(&y, out); state_output_free(e);
+}
+/* a sequence: T inputs of 45, one persistent estimator, T outputs of 105 */
+void probe_est_seq(const double *in, int T, double *out) {
+  cassie_out_t o; state_out_t y;
+  state_output_t *e = state_output_alloc(); state_output_setup(e);
+  for (int t = 0; t < T; t++) { fill(&o, in + 45 * t); state_output_step(e, &o, &y); flat(&y, out + 105 * t); }
+  state_output_free(e);
+}

@@ -51,3 +51,46 @@ def test_product_controller_matches_archive_in_closed_loop(oracle_mod):
         assert worst < 1e-9, worst
         if not pd.any():
             assert safety > 50     # the safety layer really was exercised
+
+
+DECODED = ['pelvis.orientation', 'pelvis.rotationalVelocity', 'pelvis.translationalAcceleration', 'leftFoot.position', 'leftFoot.orientation',
+           'leftFoot.footRotationalVelocity', 'leftFoot.footTranslationalVelocity', 'rightFoot.position', 'rightFoot.orientation',
+           'rightFoot.footRotationalVelocity', 'rightFoot.footTranslationalVelocity', 'motor.position', 'motor.velocity', 'motor.torque',
+           'joint.position', 'joint.velocity']
+
+
+def field(y, path):
+    for p in path.split('.'):
+        y = getattr(y, p)
+    return np.array(y[:])
+
+
+def test_estimator_twin_matches_archive_in_closed_loop(oracle_mod, pkg):
+    """the decoded stateless subset of state_output_step (oracle o_state_output_step) against the REAL estimator, fed the same cassie_out
+    along a falling-and-catching trajectory (large joint excursions; an IMU quaternion with w < 0)"""
+    import ctypes as C
+    import oracle as O
+    _fuzz_binary()
+    if not os.path.exists(O.lib_path(ref=True)):
+        pytest.skip('oracle/_ref/liboracle_ref.so not available')
+    L = O.load(ref=True)
+    L.o_state_output_step.argtypes = [C.c_void_p, C.c_void_p]
+    L.osim_cassie_out.restype = C.c_void_p
+    worst = {k: 0.0 for k in DECODED}
+    for u, setup in ((O.make_pd(), None), (O.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN), 'spin')):
+        o = O.OracleSim(os.path.join(GOLDEN, 'cassie.omodel'), ref=True)
+        if setup == 'spin':
+            o.arr('qpos')[3:7] = [-0.995, 0.02, -0.03, 0.09]      # same kind of attitude, stored with w < 0: the estimator reports the w >= 0 twin
+            o.arr('qvel')[3:6] = [0.5, -0.4, 0.6]
+        y, y2, co = pkg.state_out_t(), pkg.state_out_t(), (C.c_char * 1336)()
+        saw_neg = False
+        for k in range(700):
+            o.step_pd(u, y, co)                         # y: real estimator on this tick's cassie_out (copied into co)
+            L.o_state_output_step(C.byref(co), C.byref(y2))
+            for f in DECODED:
+                worst[f] = max(worst[f], np.abs(field(y, f) - field(y2, f)).max())
+            saw_neg |= o.arr('sensordata')[16] < 0
+        if setup == 'spin':
+            assert saw_neg
+    for f, w in worst.items():
+        assert w < 1e-11, (f, w)
