@@ -94,3 +94,67 @@ def test_estimator_twin_matches_archive_in_closed_loop(oracle_mod, pkg):
             assert saw_neg
     for f, w in worst.items():
         assert w < 1e-11, (f, w)
+
+
+def _probe(O):
+    import ctypes as C
+    _fuzz_binary()
+    if not os.path.exists(O.lib_path(ref=True)):
+        pytest.skip('oracle/_ref/liboracle_ref.so not available')
+    L = O.load(ref=True)
+    L.probe_est.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+
+    def est(inp):
+        a, out = np.ascontiguousarray(inp, dtype=np.float64), np.zeros(123)
+        L.probe_est(a.ctypes.data_as(C.POINTER(C.c_double)), 1, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+    return est
+
+
+def test_estimator_twin_on_random_inputs(oracle_mod):
+    """o_est_foot against the archive on arbitrary angles / rates (far outside what a trajectory visits: all mat2quat branches)"""
+    import ctypes as C
+    est, L = _probe(oracle_mod), oracle_mod.load()
+    L.o_est_foot.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 6
+    rng, worst = np.random.default_rng(11), 0.0
+    for it in range(2000):
+        x = np.zeros(45)
+        x[32] = 1
+        x[0:10], x[10:20], x[20:26], x[26:32] = rng.uniform(-3, 3, 10), rng.uniform(-8, 8, 10), rng.uniform(-3, 3, 6), rng.uniform(-8, 8, 6)
+        e = est(x)
+        for sd in range(2):
+            ang = (C.c_double * 7)(*x[5 * sd:5 * sd + 4], x[20 + 3 * sd], x[21 + 3 * sd], x[5 * sd + 4])
+            rate = (C.c_double * 7)(*x[10 + 5 * sd:14 + 5 * sd], x[26 + 3 * sd], x[27 + 3 * sd], x[14 + 5 * sd])
+            out = [(C.c_double * n)() for n in (3, 4, 3, 3)]
+            L.o_est_foot(sd, ang, rate, *out)
+            got = np.concatenate([np.array(a[:]) for a in out])
+            worst = max(worst, np.abs(got - e[22 + 19 * sd:35 + 19 * sd]).max())
+    assert worst < 1e-12, worst
+
+
+def test_archive_kinematics_pin_the_mjcf_compiler(oracle_mod):
+    """an independent check of the model compiler's kinematic tables: the foot point computed by the oracle's mj_kinematics on the compiled
+    model/cassie.xml equals the closed estimator's own forward kinematics (which carries Agility's constants) to the MJCF's 5-digit rounding"""
+    est = _probe(oracle_mod)
+    o = oracle_mod.OracleSim(os.path.join(GOLDEN, 'cassie.omodel'))
+    names = open(os.path.join(GOLDEN, 'cassie.omodel')).read().split('names_body')[1].split('\n')[0].split()[2:]
+    pel, feet = names.index('cassie-pelvis'), (names.index('left-foot'), names.index('right-foot'))
+    rng, worst = np.random.default_rng(4), 0.0
+    lo, hi = np.array([-0.25, -0.35, -0.8, -2.7, -2.4]), np.array([0.3, 0.35, 1.3, -0.7, -0.6])
+    for it in range(50):
+        mL, mR, sh, ta = rng.uniform(lo, hi), rng.uniform(lo, hi), rng.uniform(-0.05, 0.05, 2), rng.uniform(0.9, 2.0, 2)
+        q = o.arr('qpos')
+        q[:] = 0
+        q[2], q[3], q[10], q[24] = 1.01, 1, 1, 1
+        q[[7, 8, 9, 14, 20]], q[15], q[16] = mL, sh[0], ta[0]
+        q[[21, 22, 23, 28, 34]], q[29], q[30] = mR, sh[1], ta[1]
+        o.forward()
+        xp, xm = o.arr('xpos').reshape(-1, 3), o.arr('xmat').reshape(-1, 3, 3)
+        x = np.zeros(45)
+        x[32] = 1
+        x[0:5], x[5:10], x[20], x[21], x[23], x[24] = mL, mR, sh[0], ta[0], sh[1], ta[1]
+        e = est(x)
+        for sd, fb in enumerate(feet):
+            p = xm[pel].T @ (xp[fb] + xm[fb] @ np.array([0.01762, 0.05219, 0]) - xp[pel])
+            worst = max(worst, np.abs(p - e[22 + 19 * sd:25 + 19 * sd]).max())
+    assert worst < 5e-7, worst
