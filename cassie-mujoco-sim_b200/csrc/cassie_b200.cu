@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <omp.h>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -348,8 +349,9 @@ template <typename real> struct Batch : BatchBase {
   // cassie_sim_step_pd for every env with host AoS buffers: pack pd_in_t[] -> pinned rows -> H2D, one tick, D2H rows -> state_out_t[]
   bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) override {
     CUDA_OK(cudaSetDevice(device));
+    static const int aos_threads = [] { const char *e = getenv("CASSIE_B200_AOS_THREADS"); int t = e ? atoi(e) : 32; const int hw = omp_get_num_procs(); if (t > hw) t = hw; return t < 1 ? 1 : t; }();   // host pack / unpack threads
     if (!pin_pd) { CUDA_OK(cudaMallocHost(&pin_pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMallocHost(&pin_obs, sizeof(real) * n * OBS_W)); }
-#pragma omp parallel for schedule(static) num_threads(8) if (n >= 512)
+#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
     for (int e = 0; e < n; e++) {
       real *row = pin_pd + (size_t)e * PD_W; const pd_in_t *u = pd_in + e;
       for (int i = 0; i < 10; i++) {
@@ -363,7 +365,7 @@ template <typename real> struct Batch : BatchBase {
     if (!state_out) return sync();
     CUDA_OK(cudaMemcpyAsync(pin_obs, A.obs, sizeof(real) * n * OBS_W, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
-#pragma omp parallel for schedule(static) num_threads(8) if (n >= 512)
+#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
     for (int e = 0; e < n; e++) {
       const real *o = pin_obs + (size_t)e * OBS_W; state_out_t *y = state_out + e;
       memset(y, 0, sizeof *y);
