@@ -176,6 +176,10 @@ def gpu_arm(args, rank, local_rank, world):
         bk.set_stream(torch.cuda.current_stream().cuda_stream)
         bk.set_qpos(jittered_qpos(q0, n, seed=1000 * k + rank)); bk.forward(); bk.set_pd(rows)
         copies.append(bk)
+    # untimed set-up: every copy lands and settles into standing under the PD controller (600 ticks = 0.3 s of simulated time), so that the
+    # timed region measures the steady workload (12 equality + 8 contact-pyramid rows, ~10 PGS sweeps) whatever K and W are
+    for bk in copies:
+        bk.step(600)
     for _ in range(args.warmup):
         for bk in copies:
             bk.step(1)
@@ -226,10 +230,20 @@ def gpu_arm(args, rank, local_rank, world):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         b.L.cassie_sim_step_pd_batch(b.h, C.byref(pd), C.byref(out))
-        if dist:   # the optional batched observation copy-out: one all-gather of the fp32 observation block
-            dist.all_gather_into_tensor(gathered, obs_t)
     barrier()
     t_e2e = time.perf_counter() - t0
+    # the one optional collective of the path: all-gather of every rank's fp32 observation block, timed on its own
+    ms_gather = None
+    if dist:
+        for _ in range(3):
+            dist.all_gather_into_tensor(gathered, obs_t)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(20):
+            dist.all_gather_into_tensor(gathered, obs_t)
+        g1.record(); barrier()
+        ms_gather = g0.elapsed_time(g1) / 20
     clocks = sampler.stop() if sampler else None
     # ---- the HBM-bound integrate kernel (cassie_batch_integrate_pos) on a state larger than L2
     integ = None
@@ -309,7 +323,11 @@ def gpu_arm(args, rank, local_rank, world):
             others['error'] = repr(ex)
     # ---- reduce over ranks
     t = torch.tensor([ms_kernel, t_e2e], dtype=torch.float64, device='cuda')
+    per_rank = None
     if dist:
+        allt = torch.empty((world, 2), dtype=torch.float64, device='cuda')
+        dist.all_gather_into_tensor(allt, t)
+        per_rank = {'kernel_ms_per_step': [float(x) / args.steps for x in allt[:, 0]], 'e2e_ms_per_step': [1e3 * float(x) / e2e_steps for x in allt[:, 1]]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_kernel, t_e2e = float(t[0]), float(t[1])
     if rank == 0:
@@ -333,10 +351,9 @@ def gpu_arm(args, rank, local_rank, world):
                 'clocks': clocks,
                 'e2e': {'value': world * n * e2e_steps / t_e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * P.PD_WIDTH * 4, 'd2h_bytes_per_step': n * P.OBS_WIDTH * 4,
                         'api': 'cassie_sim_step_pd_batch(envs, pd_in_t[n] host, state_out_t[n] host), %d steps, host AoS pack/unpack included%s' % (
-                            e2e_steps, '; + one NCCL all-gather of the observation block per step' if dist else '')},
-                'gpu_launches': launches,
-                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': 8.62e6,   # dram__bytes_read.sum + write.sum per launch, profiles/r1_step_kernel_final_ncu_summary.md
-                            
+                            e2e_steps, ''), 'obs_allgather_ms': ms_gather},
+                'gpu_launches': launches, 'per_rank': per_rank,
+                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': 9.07e6,   # dram__bytes_read.sum + write.sum per launch, profiles/r1_step_kernel_v3_ncu_summary.md
                              'peak_source': peak_src, 'bytes_per_env_step': STATE_BYTES_FP32,
                              'note': 'latency/issue-bound by design (SURVEY 8d): algorithmic HBM traffic is only the persistent state rows in+out'},
                 'multitick': {'ticks_per_launch': 50, 'env_steps_per_s_this_rank': n * 200 / (ms_multi * 1e-3)},
@@ -361,6 +378,9 @@ def main():
     if args.impl == 'reference':
         reference_arm(args, rank, world)
     else:
+        # host pack / unpack threads of the AoS entry point: share the host's cores between the ranks of this node (set before any
+        # OpenMP runtime is loaded); the roofline traffic figure cites the ncu capture under profiles/
+        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(max(2, min(32, (os.cpu_count() or 8) // (2 * max(1, world))))))
         gpu_arm(args, rank, local_rank, world)
 
 
