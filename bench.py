@@ -10,7 +10,8 @@ motor-PD targets, initial pelvis height/yaw jitter U(-0.0
 every GPU (weak scaling, environments are independent; no data-path collective).
 
 value     kernel-only throughput: PD rows and state resident in HBM; inputs larger than L2 (independent copies of the batch stepped
-          round-robin, > 1.5 x L2 in total), one contiguous CUDA-event region of K launches on the launching stream, max over ranks.
+          round-robin, > 1.5 x L2 in total), one contiguous CUDA-event region of K steps on the launching stream, max over ranks.  The K
+          steps run as K / T launches of T <= 50 ticks (cassie_batch_step(b, T), PD rows held); single_tick_launches = T = 1.
           (l2_memset_flush_mode: the same kernel on one copy with a 256 MiB memset between launches, per-launch events.)
 e2e       the same metric through the reference-shaped C-ABI call cassie_sim_step_pd_batch(envs, pd_in_t[] host, state_out_t[] host):
           host->device copy of every env's PD input and device->host read of every env's observation inside the timed region.
@@ -98,7 +99,7 @@ def reference_arm(args, rank, world):
             'config': {'workload': WORKLOAD, 'parallelism': 'cpu x%d threads' % cores},
             'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=lambda o: o.tolist() if hasattr(o, 'tolist') else str(o)), flush=True)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -186,14 +187,25 @@ def gpu_arm(args, rank, local_rank, world):
     launches0 = sum(bk.launch_count() for bk in copies)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
+    # K steps (control ticks of the whole batch) = K / T launches of T ticks each with the PD rows held (cassie_batch_step(b, T); config 2's
+    # targets are constant).  T = the largest divisor of K not above 50 (50 ticks = one 40 Hz policy step of the reference's demos).
+    T = max(t for t in range(1, 51) if args.steps % t == 0)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
-    for i in range(args.steps):
-        copies[i % nb_copies].step(1)
+    for i in range(args.steps // T):
+        copies[i % nb_copies].step(T)
     k1.record()
     barrier()
     launches = sum(bk.launch_count() for bk in copies) - launches0
     ms_kernel = k0.elapsed_time(k1)
+    # ---- the same K steps as K single-tick launches (reported beside the value)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(args.steps):
+        copies[i % nb_copies].step(1)
+    s1.record()
+    barrier()
+    ms_single = s0.elapsed_time(s1) / args.steps
     # ---- the same on ONE copy with a 256 MiB memset between launches (the other flush method; per-launch events; reported beside the value)
     nfl = min(args.steps, 50)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nfl)]
@@ -204,16 +216,6 @@ def gpu_arm(args, rank, local_rank, world):
     ms_flush = sum(e0.elapsed_time(e1) for e0, e1 in ev) / nfl
     for bk in copies[1:]:
         bk.close()
-    # ---- same kernel, 50 control ticks per launch (cassie_batch_step(b, 50): one 40 Hz policy step of the reference's demos)
-    for _ in range(2):
-        b.step(50)
-    barrier()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m0.record()
-    for _ in range(4):
-        b.step(50)
-    m1.record(); barrier()
-    ms_multi = m0.elapsed_time(m1)
     # ---- end to end through the AoS C-ABI: pd_in_t[n] host -> step -> state_out_t[n] host, every step
     pd = (P.pd_in_t * n)()
     for e in range(n):
@@ -299,8 +301,8 @@ def gpu_arm(args, rank, local_rank, world):
             others['config3_16384_envs_pelvis_pushes'] = timed(b3, 80, pushes); b3.close()
             n4 = 8192
             b4 = P.CassieBatch(n4, modelfile=P.model_path('cassie_hfield'), device=local_rank, precision=P.FP32)
-            T = (np.random.default_rng(7).uniform(0, 1, (64, 200, 200)) * 0.25).astype(np.float32); T[:, 95:105, 95:105] = 0
-            b4.set_hfield_data(T); b4.set_pd(P.pd_rows(n4, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
+            terr = (np.random.default_rng(7).uniform(0, 1, (64, 200, 200)) * 0.25).astype(np.float32); terr[:, 95:105, 95:105] = 0
+            b4.set_hfield_data(terr); b4.set_pd(P.pd_rows(n4, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
             others['config4_8192_envs_per_gpu_hfield_64_terrains_amp0.05m'] = timed(b4, 80); b4.close()
             b5 = P.CassieBatch(n4, modelfile=P.model_path('cassie_tray_box'), device=local_rank, precision=P.FP32)
             ph = np.random.default_rng(99).uniform(0, 2 * np.pi, (n4, 1)); amp = np.array([0.05, 0.05, 0.3, 0.4, 0.3] * 2) * 0.2
@@ -341,10 +343,10 @@ def gpu_arm(args, rank, local_rank, world):
             cpu = {'value': None, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': 'unavailable: %r' % (ex,)}
         ms_step = ms_kernel / args.steps
         value = world * n * args.steps / (ms_kernel * 1e-3)
-        ach = STATE_BYTES_FP32 * n / (ms_step * 1e-3) / 1e9
+        ach = STATE_BYTES_FP32 * n / (T * ms_step * 1e-3) / 1e9   # algorithmic bytes of one launch (state rows in + out, once per launch) / its duration
         line = {'metric': 'Cassie env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'envs_per_gpu': n, 'ticks_per_step': 1, 'parallelism': 'env-sharded x%d (no data-path collective)' % world,
+                'config': {'workload': WORKLOAD, 'envs_per_gpu': n, 'ticks_per_step': 1, 'ticks_per_launch': T, 'parallelism': 'env-sharded x%d (no data-path collective)' % world,
                            'l2': 'inputs larger than L2: %d independent copies of the batch (%.0f MB) stepped round-robin, one contiguous timed region' % (nb_copies, nb_copies * per_copy / 1e6),
                            'model': 'compiled table of model/cassie.xml'},
                 'l2_memset_flush_mode': {'ms_per_step': ms_flush, 'env_steps_per_s_this_rank': n / (ms_flush * 1e-3), 'note': 'one copy, 256 MiB memset between launches, per-launch events'},
@@ -354,11 +356,11 @@ def gpu_arm(args, rank, local_rank, world):
                             e2e_steps, ''), 'obs_allgather_ms': ms_gather},
                 'gpu_launches': launches, 'per_rank': per_rank,
                 'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': 9.07e6,   # dram__bytes_read.sum + write.sum per launch, profiles/r1_step_kernel_v3_ncu_summary.md
-                             'peak_source': peak_src, 'bytes_per_env_step': STATE_BYTES_FP32,
+                             'peak_source': peak_src, 'bytes_per_env_per_launch': STATE_BYTES_FP32, 'ticks_per_launch': T,
                              'note': 'latency/issue-bound by design (SURVEY 8d): algorithmic HBM traffic is only the persistent state rows in+out'},
-                'multitick': {'ticks_per_launch': 50, 'env_steps_per_s_this_rank': n * 200 / (ms_multi * 1e-3)},
+                'single_tick_launches': {'ms_per_step': ms_single, 'env_steps_per_s_this_rank': n / (ms_single * 1e-3), 'note': 'the same K steps as K launches of one tick'},
                 'roofline_integrate': integ, 'cpu_baseline': cpu, 'other_configs': others}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=lambda o: o.tolist() if hasattr(o, 'tolist') else str(o)), flush=True)
     if dist:
         dist.destroy_process_group()
 

@@ -4,6 +4,7 @@
 // a TMA bulk copy (cp.async.bulk + mbarrier, SASS: UBLKCP), then every warp loads its environment's state rows from HBM
 // (coalesced, one row per array), advances `nticks` control ticks entirely on chip (step_core.inl) and writes the rows back.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,7 +25,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,14 +60,22 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>(A.ystride, DR));
   const int qw = A.qpos_w, vw = A.qvel_w;
   const DevModel<real> &cm = *cmp;
-  // persistent warps: every warp pulls environment indices from a global ticket counter until the batch is exhausted, so a warp
-  // that drew a cheap environment (few contacts, few solver sweeps) immediately starts another one
+  // persistent CTAs: a CTA draws one environment per warp from a global ticket counter until the batch is exhausted; its warps walk the
+  // stages together (STAGE_SYNC) so that they share instruction-cache lines -- the kernel is ~250 KB of code, eight times the L1.5
+  __shared__ int cta_base;
+  const int nwarps = blockDim.x >> 5, sync_on = A.cta_sync && mode == 0 && nticks > 1;   // a single tick starts in step and stays close enough
   for (;;) {
-    int env = 0;
-    if (l == 0) env = atomicAdd(A.ticket, 1);
-    env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= A.n) break;
-    if (A.mask && !A.mask[env]) continue;   // masked launches (reset / set_const of a subset)
+    __syncthreads();
+    if (threadIdx.x == 0) cta_base = atomicAdd(A.ticket, nwarps);
+    __syncthreads();
+    const int base = cta_base;
+    if (base >= A.n) break;
+    const int env = base + warp;
+    const bool active = env < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
+    if (!active) {   // keep the rendezvous count of the working warps
+      if (sync_on) { for (int i = 0; i < nticks * cm.nsub * 5; ++i) __syncthreads(); }
+      continue;
+    }
     // warm the L2/L1 path of the rows that are addressed in place later (controller state, PD row, FIR taps)
     if (l < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cst + (size_t)env * CST_W + 32 * l));
     else if (l < 9) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dfilt + (size_t)env * DFILT_W + 32 * (l - 6)));
@@ -81,7 +90,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr;
+    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on;
     step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
     if (mode >= 2) continue;   // query / set_const: only the aux row / the constant row is written
@@ -219,7 +228,7 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
     h_model_copy = *hmodel; memcpy(geom_dev, info.geom_dev, sizeof geom_dev);
     const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
-    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0;
+    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : 1;
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QW)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * VW)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * VW));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
@@ -248,6 +257,11 @@ template <typename real> struct Batch : BatchBase {
         for (int ctas = 4; ctas >= 1; --ctas) if (kk[ctas] >= 1 && kk[ctas] * ctas * 100 >= best * 85) { k_sel = kk[ctas]; break; }
       }
       if (k_sel < 1 || k_sel > 16 || (long)model_bytes<real>() + k_sel * wb > (long)dev_smem) { set_err("not enough shared memory per block"); return false; }
+      if (!w && sms > 0) {   // balance the rounds: with one resident CTA per SM, n / sms environments per CTA are worked off in ceil(. / k) rounds of
+                             // k; the smallest k with the same number of rounds leaves fewer warps contending in every round
+        int ctas_per_sm = 1; { long per_cta = (long)sm_smem / 2 - 1024; if ((per_cta - mb) / wb >= k_sel) ctas_per_sm = 2; }
+        if (ctas_per_sm == 1) { const double per_cta = (double)n / sms; const int rounds = (int)std::ceil(per_cta / k_sel); if (rounds >= 1) { int kb = (int)std::ceil(per_cta / rounds); if (kb < 1) kb = 1; if (kb < k_sel) k_sel = kb; } }
+      }
       cfg[ext].wpb = k_sel; cfg[ext].smem = model_bytes<real>() + (size_t)k_sel * wb;
       int per_sm = 0;
       if (ext) { CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));

@@ -20,6 +20,7 @@
 #ifdef CASSIE_EMU
 #define CFN inline
 #define DECL_LANE
+#define STAGE_SYNC(on)
 #define LANES for (int l = 0; l < 32; ++l) {
 #define ENDL }
 #define LANES_NS for (int l = 0; l < 32; ++l) {
@@ -37,6 +38,9 @@
 #else
 #define CFN __device__ __forceinline__
 #define DECL_LANE const int l = threadIdx.x & 31;
+// optional CTA-wide rendezvous between stages: the warps of a CTA (one environment each) then walk the code together and share
+// instruction-cache lines; `on` is uniform over the CTA
+#define STAGE_SYNC(on) do { if (on) __syncthreads(); } while (0)
 #define LANES {
 #define ENDL } __syncwarp();
 #define LANES_NS {
@@ -68,6 +72,7 @@ template <typename real> struct EnvPtrs {
   real *aux;          // [AUX_W] derived-quantity row or null
   real *cenv;         // [CE_W] per-environment model constants (domain randomisation) or null: then the shared model block's values apply
   int *counters;      // [8]
+  int cta_sync;       // 1: the CTA's warps rendezvous at the stage boundaries (STAGE_SYNC); only the step / forward modes
 };
 
 // ------------------------------------------------------------------ scalar math on float / double
@@ -435,6 +440,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   const real root_mass_inv = ce ? ce[CE_ROOT_MINV] : cm.root_mass_inv, total_mass_inv = ce ? ce[CE_TOT_MINV] : cm.total_mass_inv, pgs_scale = ce ? ce[CE_PGS_SCALE] : cm.pgs_scale;
   const real xb_dsqi_t = (ce && cm.xb >= 0) ? real(1) / msqrt(bmass[cm.xb]) : cm.xb_dsqi[0];   // the extra free body's mass acts at once, like every body_mass entry
   DECL_LANE
+  const bool csync = E.cta_sync != 0;   // set by the kernel wrapper for multi-tick step launches only
+  STAGE_SYNC(csync);
   const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
   real *qpos = sm + S_QPOS, *qM = E.qM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
@@ -792,6 +799,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
+  STAGE_SYNC(csync);
   // ================= collision (lane = candidate geom pair) =================
   real *geom = sm + S_Y + T_GEOM;   // the smooth-dynamics temporaries below it are dead; the constraint rows are written after the contact list
   LANES
@@ -982,6 +990,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
+  STAGE_SYNC(csync);
   LV(real, qacc); LV(real, qfrc_con);
   LV(real, f0); LV(real, f1);    // constraint forces: lane (r & 31) owns rows r and r + 32
   int iters = 0;
@@ -1180,6 +1189,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       ENDL
     }
   }
+  STAGE_SYNC(csync);
   if (counters) { LANES if (l == 0) counters[3] = iters; ENDL }
   // ================= derived quantities, part 3: contact forces (mj_contactForce -> world frame), foot / toe / heel sums, collision flags
   // (cassie_sim_foot_forces :1812-1854, cassie_sim_heeltoe_forces :1856-1898, check_*_collision :1586-1606, geom_collision :1944-1961)
@@ -1252,6 +1262,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     if (auxr) { LANES if (l < nv) vecs[l] = L(qvel); ENDL aux_foot_velocities(cm, sm, auxr); }
     return;
   }
+  STAGE_SYNC(csync);
   // ================= Euler with implicit joint damping (mj_Euler) + mj_advance =================
   // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
