@@ -498,6 +498,7 @@ bool compile_mjcf(const std::string &xml_path, HostModel &m, std::string &err) {
     else if (x->tag == "gyro") { t = SENS_GYRO; obj = m.site_id(x->get("site") ? x->get("site") : ""); }
     else if (x->tag == "accelerometer") { t = SENS_ACCEL; obj = m.site_id(x->get("site") ? x->get("site") : ""); }
     else if (x->tag == "magnetometer") { t = SENS_MAG; obj = m.site_id(x->get("site") ? x->get("site") : ""); }
+    else if (x->tag == "rangefinder") continue;   // cassie_no_grav.xml: six rangefinders after the 29 numbers the hot path reads; not modelled
     else { err = "unsupported sensor <" + x->tag + ">"; return false; }
     if (obj < 0) { err = "sensor <" + x->tag + "> refers to an unknown object"; return false; }
     m.sensor_type.push_back(t); m.sensor_objid.push_back(obj);

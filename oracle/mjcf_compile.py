@@ -523,6 +523,8 @@ def compile_mjcf(path):
     actnames = [m_.get('name') for m_ in (an if an is not None else [])]
     for s in (sn if sn is not None else []):
         # type codes private to this table: 0 actuatorpos, 1 jointpos, 2 framequat, 3 gyro, 4 accelerometer, 5 magnetometer
+        if s.tag == 'rangefinder':
+            continue      # cassie_no_grav.xml: six rangefinders AFTER the 29 numbers the hot path reads (src/cassiemujoco.c:754-773); not modelled
         t = {'actuatorpos': 0, 'jointpos': 1, 'framequat': 2, 'gyro': 3, 'accelerometer': 4, 'magnetometer': 5}[s.tag]
         if t == 0:
             obj = actnames.index(s.get('actuator'))

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(REPO, 'oracle'))
 import mjcf_compile as mc  # noqa: E402
 
 REF = os.environ.get('CASSIE_REFERENCE', '/root/reference')
-MODELS = ['cassie', 'cassie_hfield', 'cassie_tray_box']
+MODELS = ['cassie', 'cassie_hfield', 'cassie_tray_box', 'cassie_no_grav']
 
 
 def main():
