@@ -154,6 +154,8 @@ def lib():
     for n in ('cassie_batch_enable_aux',):
         getattr(L, n).argtypes = [vp, ci]
         getattr(L, n).restype = ci
+    L.cassie_batch_set_task_pd.argtypes = [vp, cd]
+    L.cassie_batch_set_task_pd.restype = ci
     L.cassie_batch_get_aux.argtypes = [vp, cd]
     L.cassie_batch_get_aux.restype = ci
     L.cassie_batch_query.argtypes = [vp]
@@ -258,6 +260,16 @@ class CassieBatch:
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         assert rows.shape == (self.n, PD_WIDTH)
         self.L.cassie_batch_set_pd(self.h, self._dp(rows))
+
+    def set_task_pd(self, rows):
+        """taskPd rows [n, 60] (per leg torque, pTarget, dTarget, pGain, dGain [6]) or None to switch the branch off."""
+        if rows is None:
+            rc = self.L.cassie_batch_set_task_pd(self.h, None)
+        else:
+            a = np.ascontiguousarray(rows, dtype=np.float64).reshape(self.n, 60)
+            rc = self.L.cassie_batch_set_task_pd(self.h, self._dp(a))
+        if rc != 0:
+            raise RuntimeError(_last_error())
 
     def step(self, nticks=1):
         self.L.cassie_batch_step(self.h, int(nticks))

@@ -25,7 +25,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     if (A.xb >= 0 && l < 6) { xqvel = A.qvel[(size_t)env * vw + 32 + l]; xqacc_ws = A.qacc_ws[(size_t)env * vw + 32 + l]; }
     __syncwarp();
     EnvPtrs<real> E;
-    E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W;
+    E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W; E.task = A.task ? A.task + (size_t)env * TASK_W : nullptr;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
     E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on;
@@ -199,6 +199,7 @@ struct BatchBase {
   virtual bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) = 0;
   virtual bool set_hfield(const float *data, int n_terrains) = 0;
   virtual bool enable_aux(bool on) = 0;
+  virtual bool set_task_pd(const double *rows) = 0;   // [n][60] or null (off)
   virtual bool set_model_rows(const char *what, const double *rows, int width) = 0;   // per-env model constants (domain randomisation)
   virtual bool get_model_rows(const char *what, double *rows, int width) = 0;
   virtual bool set_const(const unsigned char *mask, bool reset_state) = 0;
@@ -210,12 +211,12 @@ template <typename real> struct Batch : BatchBase {
   DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; int QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
   struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[2];   // [0] plain instance, [1] extended instance
   std::vector<real> h_tmp;
-  real *pin_pd = nullptr, *pin_obs = nullptr;   // pinned staging for the AoS entry point
+  real *pin_pd = nullptr, *pin_obs = nullptr, *pin_task = nullptr;   // pinned staging for the AoS entry point
   float *d_hfield = nullptr; unsigned char *d_mask = nullptr; DevModel<real> h_model_copy{}; int geom_dev[256]; void *d_row = nullptr;
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(d_mask); cudaFree(d_row);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(A.task); if (pin_task) cudaFreeHost(pin_task); cudaFree(d_mask); cudaFree(d_row);
     if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -374,6 +375,22 @@ template <typename real> struct Batch : BatchBase {
       }
       row[50] = row[51] = 0;
     }
+    {  // taskPd branch of pd_in_t: rows are uploaded only while some environment uses it
+      int any = 0;
+#pragma omp parallel for schedule(static) num_threads(aos_threads) reduction(| : any) if (n >= 512)
+      for (int e = 0; e < n; e++) { const pd_task_in_t *t[2] = {&pd_in[e].leftLeg.taskPd, &pd_in[e].rightLeg.taskPd};
+        for (int sd = 0; sd < 2; sd++) for (int k = 0; k < 6; k++) any |= (t[sd]->torque[k] != 0 || t[sd]->pGain[k] != 0 || t[sd]->dGain[k] != 0); }
+      if (any) {
+        if (!pin_task) CUDA_OK(cudaMallocHost(&pin_task, sizeof(real) * n * TASK_W));
+        if (!A.task) CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W));
+#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
+        for (int e = 0; e < n; e++) { real *row = pin_task + (size_t)e * TASK_W;
+          for (int sd = 0; sd < 2; sd++) { const pd_task_in_t *t = sd ? &pd_in[e].rightLeg.taskPd : &pd_in[e].leftLeg.taskPd; real *r = row + 30 * sd;
+            for (int k = 0; k < 6; k++) { r[k] = (real)t->torque[k]; r[6 + k] = (real)t->pTarget[k]; r[12 + k] = (real)t->dTarget[k]; r[18 + k] = (real)t->pGain[k]; r[24 + k] = (real)t->dGain[k]; } }
+          for (int i = 60; i < TASK_W; i++) row[i] = 0; }
+        CUDA_OK(cudaMemcpyAsync(A.task, pin_task, sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream));
+      } else if (A.task) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; }
+    }
     CUDA_OK(cudaMemcpyAsync(A.pd, pin_pd, sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));
     if (!step(1, 0)) return false;
     if (!state_out) return sync();
@@ -418,13 +435,23 @@ template <typename real> struct Batch : BatchBase {
     return true;
   }
   bool has_aux() const override { return A.aux != nullptr; }
+  // task-space PD rows (pd_in_t taskPd of both legs); NULL switches the branch off again
+  bool set_task_pd(const double *rows) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (!rows) { if (A.task) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; } return true; }
+    if (!A.task) CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W));
+    h_tmp.assign((size_t)n * TASK_W, 0);
+    for (int e = 0; e < n; e++) for (int i = 0; i < 60; i++) h_tmp[(size_t)e * TASK_W + i] = (real)rows[(size_t)e * 60 + i];
+    CUDA_OK(cudaMemcpyAsync(A.task, h_tmp.data(), sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
-    const LaunchCfg &c = cfg[(A.cenv || A.aux) ? 1 : 0];
+    const LaunchCfg &c = cfg[(A.cenv || A.aux || A.task) ? 1 : 0];
     int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
-    if (A.cenv || A.aux) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
+    if (A.cenv || A.aux || A.task) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
     else cassie_step_kernel<real, false><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
     launches++;
     CUDA_OK(cudaGetLastError());
@@ -484,7 +511,7 @@ template <typename real> struct Batch : BatchBase {
   }
   void *dev_ptr(const char *f) override {
     if (!strcmp(f, "qpos")) return A.qpos; if (!strcmp(f, "qvel")) return A.qvel; if (!strcmp(f, "pd")) return A.pd; if (!strcmp(f, "obs")) return A.obs;
-    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux;
+    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux; if (!strcmp(f, "task")) return A.task;
     return nullptr;
   }
   bool get_counters(int *out) override {
@@ -565,6 +592,7 @@ int cassie_batch_get_body_ipos(cassie_batch_t *b, double *ipos) { return b->impl
 int cassie_batch_get_dof_damping(cassie_batch_t *b, double *damp) { return b->impl->get_model_rows("dof_damping", damp, b->impl->hm.nv) ? 0 : -1; }
 int cassie_batch_get_geom_friction(cassie_batch_t *b, double *fric) { return b->impl->get_model_rows("geom_friction", fric, 3 * b->impl->hm.ngeom) ? 0 : -1; }
 int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int reset_state) { return b->impl->set_const(mask, reset_state != 0) ? 0 : -1; }
+int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows) { return b->impl->set_task_pd(rows) ? 0 : -1; }
 int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
 int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
 int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }

@@ -82,6 +82,7 @@ constexpr int QPOS_W_XB = 44, QVEL_W_XB = 40;       // with an extra free body (
 constexpr int CST_W = 192;      // controller / sensor state, layout below
 constexpr int DFILT_W = 96;     // int32 drive FIR taps [10][9] padded
 constexpr int PD_W = 52;        // torque, pTarget, dTarget, pGain, dGain for the 10 motors (+2 pad)
+constexpr int TASK_W = 64;      // optional task-space PD rows: per leg torque, pTarget, dTarget, pGain, dGain [6] each (left 0..29, right 30..59)
 constexpr int XFRC_W = 8;       // force xyz, torque xyz, body id (as real), pad
 constexpr int OBS_W = 96;       // the dynamic subset of cassie_out_t copied out at src/cassiemujoco.c:1127 + the decoded estimator outputs
 // CST offsets

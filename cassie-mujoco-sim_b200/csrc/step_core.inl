@@ -65,6 +65,7 @@ template <typename real> struct EnvPtrs {
   int *dfilt;         // [DFILT_W] drive FIR taps
   const real *pd;     // [PD_W] motor-PD row held for the launch
   const real *xfrc;   // [XFRC_W]
+  const real *task;   // [TASK_W] task-space PD rows (pd_in_t taskPd of both legs) or null
   real *obs;          // [OBS_W] or null
   real *qM;           // [NM_MAX] mass-matrix scratch (written by CRB, read back by the Euler stage)
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
@@ -78,6 +79,10 @@ template <typename real> struct EnvPtrs {
 // ------------------------------------------------------------------ scalar math on float / double
 CFN float msqrt(float x) { return sqrtf(x); }
 CFN double msqrt(double x) { return sqrt(x); }
+CFN float matan2(float y, float x) { return atan2f(y, x); }
+CFN double matan2(double y, double x) { return atan2(y, x); }
+CFN float masin(float x) { return asinf(x); }
+CFN double masin(double x) { return asin(x); }
 CFN float mabs(float x) { return fabsf(x); }
 CFN double mabs(double x) { return fabs(x); }
 CFN float mmax(float a, float b) { return fmaxf(a, b); }
@@ -1304,7 +1309,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
 // translational velocity (3 + 3) in the reported foot frame.  Offsets: model/cassie.xml:96-152; the foot point and the 40 degree frame
 // offset are the estimator's own constants.
 template <typename real>
-CFN void est_foot(int side, const real *sc, const real *rate, real *out) {
+CFN void est_foot(int side, const real *sc, const real *rate, real *out, real *jac = (real *)0) {   // jac (optional): [5][6] columns of [Jw; Jv] for the five motor angles
   const real sg = side ? real(-1) : real(1);
   // A = frame of the hip-pitch link in the pelvis frame (row-major), built from the three quarter-turn link frames and the joint turns
   const real s0 = sc[0], c0 = sc[1], s1 = sc[2], c1 = sc[3], s2 = sc[4], c2 = sc[5];
@@ -1359,6 +1364,17 @@ CFN void est_foot(int side, const real *sc, const real *rate, real *out) {
     out[3] = q[0]; out[4] = q[1]; out[5] = q[2]; out[6] = q[3];
   }
   matT_vec(out + 7, Rf, w); matT_vec(out + 10, Rf, vl);
+  if (jac) {   // pelvis-frame Jacobian of the foot point: hip roll, hip yaw, then hip pitch / knee / foot about the common z of the hip-pitch frame
+    d[0] = pos[0] - anchor0[0]; d[1] = pos[1] - anchor0[1]; d[2] = pos[2] - anchor0[2]; cross3(cr, axis0, d);
+    for (int k = 0; k < 3; ++k) { jac[k] = axis0[k]; jac[3 + k] = cr[k]; }
+    d[0] = pos[0] - anchor1[0]; d[1] = pos[1] - anchor1[1]; d[2] = pos[2] - anchor1[2]; cross3(cr, axis1, d);
+    for (int k = 0; k < 3; ++k) { jac[6 + k] = axis1[k]; jac[9 + k] = cr[k]; }
+    const real bx[3] = {0, ax[0], ax[3]}, by[3] = {0, ay[0], ay[3]};   // anchors of hip pitch (frame origin), knee, foot in the plane
+    for (int j = 0; j < 3; ++j) {
+      const real pj[3] = {-(u[1] - by[j]), u[0] - bx[j], 0}; mat_vec(v, A2, pj);
+      for (int k = 0; k < 3; ++k) { jac[12 + 6 * j + k] = A2[3 * k + 2]; jac[15 + 6 * j + k] = v[k]; }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ one control tick (cassie_sim_step_pd)
@@ -1398,6 +1414,32 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         L(tq) = u; L(ctrl) = add; L(scale_part) = sc;
       }
     ENDL
+    // ---- pd_input_step, taskPd branch (closed, decoded): task-space PD on the foot point through the leg Jacobian; extended instance only
+    if (DR && E.task) {
+      const real *tk = E.task;
+      LANES  // lanes 0..13: sin / cos of the 14 chain angles from LAST tick's cassie_out
+        if (l < 14) {
+          const int i = l, sd = i / 7, k = i % 7; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd;
+          real a = k < 3 ? mp[k] : mp[3];
+          if (k >= 4) a += jp[0]; if (k >= 5) a += jp[1]; if (k >= 6) a += mp[4];
+          real sn, cs; msincos(a, &sn, &cs); vecs[32 + 2 * i] = sn; vecs[33 + 2 * i] = cs;
+        }
+      ENDL
+      LANES
+        if (l < 2) {
+          const int sd = l; const real *mv = cst + CS_DVEL + 5 * sd, *jv = cst + CS_JVEL + 3 * sd, *t = tk + 30 * sd;
+          const real rate[7] = {mv[0], mv[1], mv[2], mv[3], jv[0], jv[1], mv[4]};
+          real fo[13], jac[30], x[6], w[6];
+          est_foot<real>(sd, vecs + 32 + 14 * sd, rate, fo, jac);
+          const real qw = fo[3], qx = fo[4], qy = fo[5], qz = fo[6];
+          x[0] = fo[0]; x[1] = fo[1]; x[2] = fo[2];
+          x[3] = matan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz)); x[4] = masin(2 * (qw * qy - qz * qx)); x[5] = matan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy));
+          for (int k = 0; k < 6; ++k) { const real vk = k < 3 ? fo[10 + k] : fo[7 + k - 3]; w[k] = t[k] + t[18 + k] * (t[6 + k] - x[k]) + t[24 + k] * (t[12 + k] - vk); }
+          for (int j = 0; j < 5; ++j) { real acc = 0; for (int k = 0; k < 6; ++k) acc += jac[6 * j + k] * w[k]; vecs[64 + 5 * sd + j] = acc; }
+        }
+      ENDL
+      LANES if (l < 10) L(tq) += vecs[64 + l]; ENDL
+    }
     // product of the per-row scale factors over all 10 motors (log-free: multiply through shared memory)
     LANES vecs[l] = L(scale_part); ENDL
     LANES
@@ -1436,7 +1478,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         int y = 0; for (int k = 0; k < 9; ++k) y += x[k] * b[k];
         cst[CS_DVEL + l] = (real)(y * scale / 3.141592653589793);
       } else if (l < 16) {  // joint encoder, IIR (:596-635)
-        const int i = l - 10, s = i < 3 ? 5 + i : 10 + i, bits = cm.enc_bits[s]; real *x = cst + CS_JFX + 4 * i, *y = cst + CS_JFY + 3 * i;
+        const int i = l - 10, s = i < 3 ? 5 + i : 10 + i, bits = cm.enc_bits[s]; real *x = cst + (CS_JFX - 40) + 4 * l, *y = cst + (CS_JFY - 30) + 3 * l;   // = CS_JFX + 4 i, CS_JFY + 3 i, written with non-negative terms only
         const double TWO_PI = 6.283185307179586;
         const int enc = (int)((double)cst[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
         const real p = (real)(enc * (TWO_PI / (double)(1 << bits)));
@@ -1460,20 +1502,20 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         if (l == 13) obs[OB_TIME] = cst[CS_TIME];
       ENDL
       // ---- state_output_step, stateless part (closed source, decoded): pelvis orientation / acceleration, foot poses and velocities
-      LANES  // lanes 16..29: sin / cos of the 14 chain angles (3 hip angles + 4 cumulative planar angles per leg)
-        if (l >= 16 && l < 30) {
-          const int i = l - 16, sd = i / 7, k = i % 7; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd;
+      LANES  // lanes 0..13: sin / cos of the 14 chain angles (3 hip angles + 4 cumulative planar angles per leg)
+        if (l < 14) {
+          const int i = l, sd = i / 7, k = i % 7; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd;
           real a = k < 3 ? mp[k] : mp[3];
           if (k >= 4) a += jp[0]; if (k >= 5) a += jp[1]; if (k >= 6) a += mp[4];
           real sn, cs; msincos(a, &sn, &cs); vecs[32 + 2 * i] = sn; vecs[33 + 2 * i] = cs;
         }
       ENDL
       LANES
-        if (l == 16 || l == 17) {
-          const int sd = l - 16; const real *mv = cst + CS_DVEL + 5 * sd, *jv = cst + CS_JVEL + 3 * sd;
+        if (l < 2) {
+          const int sd = l; const real *mv = cst + CS_DVEL + 5 * sd, *jv = cst + CS_JVEL + 3 * sd;
           const real rate[7] = {mv[0], mv[1], mv[2], mv[3], jv[0], jv[1], mv[4]};
           est_foot<real>(sd, vecs + 32 + 14 * sd, rate, obs + OB_FOOT + 13 * sd);
-        } else if (l == 18) {
+        } else if (l == 2) {
           const real *q = cst + CS_SENSOR + 16, *w = cst + CS_SENSOR + 20, *a = cst + CS_SENSOR + 23; const real sgq = q[0] < 0 ? real(-1) : real(1);
           for (int k = 0; k < 4; ++k) obs[OB_EST_QUAT + k] = sgq * q[k];
           real R[9], wr[3], wwr[3]; const real r[3] = {real(0.03155), 0, real(-0.079996)};

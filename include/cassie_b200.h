@@ -137,6 +137,11 @@ void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_
 /* throughput path: compact rows.  pd: host [n_env][CASSIE_PD_WIDTH] doubles, copied to the device (and converted to the batch
  * precision) on the batch stream; step: `nticks` control ticks per launch with the PD rows held; asynchronous. */
 void cassie_batch_set_pd(cassie_batch_t *b, const double *pd);
+/* the taskPd branch of pd_in_t (include/pd_in_t.h:32-38) for the throughput path: host [n_env][60] doubles = per leg (left, right)
+ * torque[6] pTarget[6] dTarget[6] pGain[6] dGain[6]; NULL switches the branch off.  Task coordinates as the reference's closed
+ * pd_input_step uses them (decoded, pinned to the archive): foot position in the pelvis frame, then yaw / pitch / roll of the foot
+ * frame; rates in the foot frame.  cassie_sim_step_pd(_batch) forward pd_in_t's taskPd fields automatically.  0 / -1. */
+int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows);
 void cassie_batch_step(cassie_batch_t *b, int nticks);
 void cassie_batch_sync(cassie_batch_t *b);
 /* host copies (synchronous): qpos [n][35], qvel [n][32], time [n], obs [n][CASSIE_OBS_WIDTH] =

@@ -1030,11 +1030,19 @@ static void cassie_out_init_(cassie_out_t *o) { /* :695-734 and :666-692 */
 }
 
 /* ---- Agility-block twins (closed source in the reference; semantics from SURVEY.md 8a-2 / 8a-3) */
+static void o_task_pd_leg(int side, const pd_task_in_t *t, const double ang[7], const double rate[7], double tq[5]);
 void o_pd_input_step(const pd_in_t *u, const cassie_out_t *o, double torque[10]) {
   for (int i = 0; i < 10; i++) {
     const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; int k = i % 5;
     const elmo_out_t *e = drive_ptr((cassie_out_t *)o, i);
     torque[i] = p->torque[k] + p->pGain[k] * (p->pTarget[k] - e->position) + p->dGain[k] * (p->dTarget[k] - e->velocity);
+  }
+  for (int s = 0; s < 2; s++) {
+    double ang[7], rate[7]; cassie_out_t *oo = (cassie_out_t *)o;
+    for (int i = 0; i < 4; i++) { ang[i] = drive_ptr(oo, 5 * s + i)->position; rate[i] = drive_ptr(oo, 5 * s + i)->velocity; }
+    ang[4] = joint_ptr(oo, 3 * s)->position; rate[4] = joint_ptr(oo, 3 * s)->velocity; ang[5] = joint_ptr(oo, 3 * s + 1)->position; rate[5] = joint_ptr(oo, 3 * s + 1)->velocity;
+    ang[6] = drive_ptr(oo, 5 * s + 4)->position; rate[6] = drive_ptr(oo, 5 * s + 4)->velocity;
+    o_task_pd_leg(s, s ? &u->rightLeg.taskPd : &u->leftLeg.taskPd, ang, rate, torque + 5 * s);
   }
 }
 /* soft joint limits = hard limits shrunk by W = 0.15 rad; order hipRoll hipYaw hipPitch knee foot, left leg then right.
@@ -1082,13 +1090,13 @@ static void est_mat2quat(double *q, const double *R) { /* R row-major */
   else if (R[4] > R[8]) { double s = sqrt(1 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
   else { double s = sqrt(1 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
 }
-void o_est_foot(int side, const double ang[7], const double rate[7], double pos[3], double quat[4], double rotvel[3], double linvel[3]) {
-  /* ang / rate: hipRoll, hipYaw, hipPitch, knee, shin, tarsus, foot */
+static void o_leg_chain(int side, const double ang[7], double pos[3], double Rf[9], double axis[7][3], double anchor[7][3]) {
+  /* ang: hipRoll, hipYaw, hipPitch, knee, shin, tarsus, foot; pelvis frame */
   const double sg = side ? -1.0 : 1.0;
   const double off[7][3] = {{0.021, 0.135 * sg, 0}, {0, 0, -0.07}, {0, 0, -0.09}, {0.12, 0, 0.0045 * sg}, {0.06068, 0.04741, 0}, {0.43476, 0.02, 0}, {0.408, -0.04, 0}};
   /* fixed frame of each link in its parent (columns = x, y, z axes): quarter turns for the three hip links, identity below */
   static const double F[3][9] = {{0, 0, 1, 0, 1, 0, -1, 0, 0}, {0, 0, -1, 0, 1, 0, 1, 0, 0}, {0, 1, 0, 0, 0, -1, -1, 0, 0}};
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}, anchor[7][3], axis[7][3];
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
   for (int i = 0; i < 7; i++) {
     double v[3], T[9], c = cos(ang[i]), s = sin(ang[i]);
     mulMatVec3(v, R, off[i]); for (int k = 0; k < 3; k++) p[k] += v[k];
@@ -1098,8 +1106,12 @@ void o_est_foot(int side, const double ang[7], const double rate[7], double pos[
     copyv(anchor[i], p, 3); axis[i][0] = R[2]; axis[i][1] = R[5]; axis[i][2] = R[8];
   }
   const double c40 = cos(40 * M_PI / 180), s40 = sin(40 * M_PI / 180), Roff[9] = {-c40, 0, -s40, s40, 0, -c40, 0, -1, 0}, loc[3] = {0.01762, 0.05219, 0};
-  double Rf[9], v[3], w[3] = {0, 0, 0}, vl[3] = {0, 0, 0};
+  double v[3];
   mulMatMat3(Rf, R, Roff); mulMatVec3(v, R, loc); for (int k = 0; k < 3; k++) pos[k] = p[k] + v[k];
+}
+void o_est_foot(int side, const double ang[7], const double rate[7], double pos[3], double quat[4], double rotvel[3], double linvel[3]) {
+  double Rf[9], axis[7][3], anchor[7][3], w[3] = {0, 0, 0}, vl[3] = {0, 0, 0};
+  o_leg_chain(side, ang, pos, Rf, axis, anchor);
   est_mat2quat(quat, Rf);
   for (int i = 0; i < 7; i++) {
     double d[3] = {pos[0] - anchor[i][0], pos[1] - anchor[i][1], pos[2] - anchor[i][2]}, cr[3];
@@ -1107,6 +1119,30 @@ void o_est_foot(int side, const double ang[7], const double rate[7], double pos[
     for (int k = 0; k < 3; k++) { w[k] += axis[i][k] * rate[i]; vl[k] += cr[k] * rate[i]; }
   }
   mulMatTVec3(rotvel, Rf, w); mulMatTVec3(linvel, Rf, vl);
+}
+/* pd_input_step, taskPd branch (closed; decoded by probing the archive, oracle/probe_estimator.c probe_pd; pinned in tests/test_agility_twins.py).
+ * Per leg, six task coordinates x = [foot position (pelvis frame, the estimator's point), yaw, pitch, roll of the estimator's foot frame (ZYX Euler
+ * angles of its quaternion)], their rates v = [footTranslationalVelocity, footRotationalVelocity] exactly as the estimator reports them (foot
+ * frame), w_k = torque_k + pGain_k (pTarget_k - x_k) + dGain_k (dTarget_k - v_k), and motor torques += A' w with A = [Jw; Jv], the angular then the
+ * linear Jacobian of the foot point (pelvis frame) with respect to the five MOTOR angles, shin / tarsus held at their measured values.  (Component
+ * k of w multiplies row k of A -- position errors meet the angular rows; that is what the archive computes.) */
+static void o_task_pd_leg(int side, const pd_task_in_t *t, const double ang[7], const double rate[7], double tq[5]) {
+  double pos[3], Rf[9], axis[7][3], anchor[7][3], quat[4], rot[3], lin[3], x[6], v[6];
+  static const int mot[5] = {0, 1, 2, 3, 6};
+  int any = 0; for (int k = 0; k < 6; k++) any |= (t->torque[k] != 0 || t->pGain[k] != 0 || t->dGain[k] != 0);
+  if (!any) return;
+  o_leg_chain(side, ang, pos, Rf, axis, anchor);
+  o_est_foot(side, ang, rate, pos, quat, rot, lin);
+  const double qw = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
+  x[0] = pos[0]; x[1] = pos[1]; x[2] = pos[2];
+  x[3] = atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz)); x[4] = asin(2 * (qw * qy - qz * qx)); x[5] = atan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy));
+  for (int k = 0; k < 3; k++) { v[k] = lin[k]; v[3 + k] = rot[k]; }
+  double w[6]; for (int k = 0; k < 6; k++) w[k] = t->torque[k] + t->pGain[k] * (t->pTarget[k] - x[k]) + t->dGain[k] * (t->dTarget[k] - v[k]);
+  for (int j = 0; j < 5; j++) {
+    const int i = mot[j]; double d[3] = {pos[0] - anchor[i][0], pos[1] - anchor[i][1], pos[2] - anchor[i][2]}, cr[3];
+    cross(cr, axis[i], d);
+    tq[j] += axis[i][0] * w[0] + axis[i][1] * w[1] + axis[i][2] * w[2] + cr[0] * w[3] + cr[1] * w[4] + cr[2] * w[5];
+  }
 }
 void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
   cassie_out_t out = *o;

@@ -33,7 +33,11 @@ int main(int argc, char **argv) {
       e->position = mid + half * w * urand(-1, 1); if (i >= 5 && k == 0) e->position = -e->position;
       e->velocity = urand(-8, 8); e->torqueLimit = tl[k]; e->gearRatio = 1; e->statusWord = 0x0637;
     }
+    { cassie_joint_out_t *jj[6] = {&o.leftLeg.shinJoint, &o.leftLeg.tarsusJoint, &o.leftLeg.footJoint, &o.rightLeg.shinJoint, &o.rightLeg.tarsusJoint, &o.rightLeg.footJoint};
+      for (int i = 0; i < 6; i++) { jj[i]->position = (i % 3 == 0) ? urand(-0.2, 0.2) : (i % 3 == 1 ? urand(0.8, 2.6) : urand(-2.4, -0.6)); jj[i]->velocity = urand(-6, 6); } }
     pd_in_t u; memset(&u, 0, sizeof u);
+    if (it % 3) for (int sd = 0; sd < 2; sd++) { pd_task_in_t *t = sd ? &u.rightLeg.taskPd : &u.leftLeg.taskPd;   /* taskPd branch: two thirds of the cases */
+      for (int k = 0; k < 6; k++) { t->torque[k] = urand(-30, 30); t->pTarget[k] = urand(-1, 1); t->dTarget[k] = urand(-2, 2); t->pGain[k] = (rand() % 4) ? urand(0, 300) : 0; t->dGain[k] = (rand() % 4) ? urand(0, 10) : 0; } }
     for (int i = 0; i < 10; i++) { pd_motor_in_t *p = i < 5 ? &u.leftLeg.motorPd : &u.rightLeg.motorPd; int k = i % 5;
       p->torque[k] = urand(-50, 50); p->pTarget[k] = urand(-2, 2); p->dTarget[k] = urand(-3, 3); p->pGain[k] = urand(0, 200); p->dGain[k] = urand(0, 10); }
     cassie_user_in_t ui; pd_input_step(pd, &u, &o, &ui);

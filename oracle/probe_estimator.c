@@ -45,3 +45,20 @@ void probe_est_seq(const double *in, int T, double *out) {
   for (int t = 0; t < T; t++) { fill(&o, in + 45 * t); state_output_step(e, &o, &y); flat(&y, out + 105 * t); }
   state_output_free(e);
 }
+
+/* pd_input_step probe: in[45] as above (cassie_out), task[60] = left-leg taskPd {torque, pTarget, dTarget, pGain, dGain}[6] then the right leg's;
+ * out[10] = cassie_user_in_t.torque after ncalls calls on a fresh block */
+typedef struct PdInput pd_input_t;
+pd_input_t *pd_input_alloc(void); void pd_input_setup(pd_input_t *); void pd_input_free(pd_input_t *);
+void pd_input_step(pd_input_t *, const pd_in_t *, const cassie_out_t *, cassie_user_in_t *);
+void probe_pd(const double *in, const double *task, int ncalls, double *out) {
+  cassie_out_t o; fill(&o, in);
+  pd_in_t u; memset(&u, 0, sizeof u);
+  for (int s = 0; s < 2; s++) { pd_task_in_t *t = s ? &u.rightLeg.taskPd : &u.leftLeg.taskPd; const double *p = task + 30 * s;
+    for (int k = 0; k < 6; k++) { t->torque[k] = p[k]; t->pTarget[k] = p[6 + k]; t->dTarget[k] = p[12 + k]; t->pGain[k] = p[18 + k]; t->dGain[k] = p[24 + k]; } }
+  cassie_user_in_t ui; memset(&ui, 0, sizeof ui);
+  pd_input_t *pd = pd_input_alloc(); pd_input_setup(pd);
+  for (int i = 0; i < ncalls; i++) pd_input_step(pd, &u, &o, &ui);
+  for (int i = 0; i < 10; i++) out[i] = ui.torque[i];
+  pd_input_free(pd);
+}

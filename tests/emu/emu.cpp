@@ -13,8 +13,8 @@ using namespace cassie;
 
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; BuildInfo info; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX], aux[AUX_W], cenv[CE_W]; int counters[8]; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
-  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
+  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX], aux[AUX_W], cenv[CE_W], task[TASK_W]; int counters[8]; bool use_task = false; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.task = use_task ? task : nullptr; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
@@ -70,6 +70,9 @@ int emu_model_set(void *p, const char *what, const double *v, int n) { Handle *h
 void emu_set_const(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.set_const(); else h->d.set_const(); }
 void emu_plain(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.use_ext = false; else h->d.use_ext = false; }   // run the plain instance from now on
 void emu_enable_cenv(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.enable_cenv(); else h->d.enable_cenv(); }
+void emu_set_task(void *p, const double *rows60) { Handle *h = (Handle *)p;
+  if (h->fp32) { h->f.use_task = rows60 != nullptr; if (rows60) for (int i = 0; i < 60; i++) h->f.task[i] = (float)rows60[i]; }
+  else { h->d.use_task = rows60 != nullptr; if (rows60) for (int i = 0; i < 60; i++) h->d.task[i] = rows60[i]; } }
 void emu_query(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.query(); else h->d.query(); }
 void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward(); else h->d.forward(); }
 // generic get/set of named state as doubles.  names: qpos qvel qacc_ws cst obs dbg xfrc ; ints: dfilt counters

@@ -78,6 +78,16 @@ class EmuSim:
         """switch to the plain kernel instance (no derived-quantity rows, no per-env constants), the one the throughput path runs."""
         self.L.emu_plain(self.h)
 
+    def set_task(self, rows60):
+        """taskPd rows (left then right leg: torque, pTarget, dTarget, pGain, dGain [6] each) or None; runs on the extended instance."""
+        self.L.emu_set_task.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        if rows60 is None:
+            self.L.emu_set_task(self.h, None)
+        else:
+            a = np.ascontiguousarray(rows60, dtype=np.float64)
+            assert a.size == 60
+            self.L.emu_set_task(self.h, a.ctypes.data_as(C.POINTER(C.c_double)))
+
     def enable_cenv(self):
         self.L.emu_enable_cenv(self.h)
 

@@ -66,14 +66,17 @@ def test_batch_every_env_its_own_constants(P, oracle_mod, model):
 
 
 def test_rows_off_equals_rows_on_with_defaults(P):
-    a, b = P.CassieBatch(3), P.CassieBatch(3)
-    rows = P.pd_rows(3, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
-    a.set_pd(rows)
-    b.set_pd(rows)
-    b.set_model('dof_damping', b.get_model('dof_damping'))      # allocates the constant rows, values unchanged
-    a.step(300)
-    b.step(300)
-    assert np.array_equal(a.qpos(), b.qpos())
+    """the extended kernel instance reading default constant rows follows the plain instance (two separately compiled instances: equal up to
+    the compiler's choice of fused multiply-adds, so a tolerance rather than bit equality; the host emulation checks bit equality)"""
+    for prec, tol in ((P.FP64, 1e-11), (P.FP32, 1e-5)):
+        a, b = P.CassieBatch(3, precision=prec), P.CassieBatch(3, precision=prec)
+        rows = P.pd_rows(3, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+        a.set_pd(rows)
+        b.set_pd(rows)
+        b.set_model('dof_damping', b.get_model('dof_damping'))      # allocates the constant rows, values unchanged
+        a.step(300)
+        b.step(300)
+        assert np.abs(a.qpos() - b.qpos()).max() < tol
 
 
 def test_free_body_ipos_is_rejected(P):
