@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     EnvPtrs<real> E;
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W; E.task = A.task ? A.task + (size_t)env * TASK_W : nullptr;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
-    E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
+    E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * 2 * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
     E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on;
     step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
@@ -233,7 +233,7 @@ template <typename real> struct Batch : BatchBase {
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QW)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * VW)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * VW));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
-    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * NM_MAX)); CUDA_OK(cudaMalloc(&A.ticket, sizeof(int)));
+    CUDA_OK(cudaMalloc(&A.obs, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMalloc(&A.dfilt, sizeof(int) * n * DFILT_W)); CUDA_OK(cudaMalloc(&A.counters, sizeof(int) * n * 8)); CUDA_OK(cudaMalloc(&A.qM, sizeof(real) * n * 2 * NM_MAX)); CUDA_OK(cudaMalloc(&A.ticket, sizeof(int)));
     CUDA_OK(cudaMemset(A.pd, 0, sizeof(real) * n * PD_W)); CUDA_OK(cudaMemset(A.obs, 0, sizeof(real) * n * OBS_W)); CUDA_OK(cudaMemset(A.counters, 0, sizeof(int) * n * 8));
     if (debug) { CUDA_OK(cudaMalloc(&A.dbg, sizeof(real) * n * D_SIZE)); CUDA_OK(cudaMemset(A.dbg, 0, sizeof(real) * n * D_SIZE)); }
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true;

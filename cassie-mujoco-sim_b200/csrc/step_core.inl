@@ -67,7 +67,7 @@ template <typename real> struct EnvPtrs {
   const real *xfrc;   // [XFRC_W]
   const real *task;   // [TASK_W] task-space PD rows (pd_in_t taskPd of both legs) or null
   real *obs;          // [OBS_W] or null
-  real *qM;           // [NM_MAX] mass-matrix scratch (written by CRB, read back by the Euler stage)
+  real *qM;           // [2 NM_MAX] scratch: M (debug dump / set_const only), then the factor of M + h B carried from the CRB stage to the Euler stage
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
   real *dbg;          // [D_SIZE] or null
   real *aux;          // [AUX_W] derived-quantity row or null
@@ -182,35 +182,48 @@ template <typename real> CFN void make_frame(real *f) {
 
 // ------------------------------------------------------------------ sparse L'DL on the dof tree (lane = dof where it matters)
 // in-place factorisation of sm[S_QLD..] (already holding M); writes 1/D and 1/sqrt(D)
-template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm) {
+// q2 (optional): a second matrix of the same sparsity (M + h B for the implicit-damping Euler step) factored in the same pass: the schedule
+// decode and the loop overhead are shared; every entry sees exactly the operations a separate factorisation would apply
+template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm, real *q2 = (real *)0) {
   DECL_LANE
-  real *qLD = sm + S_QLD, *ftmp = sm + S_VEC + 128;
-  LV(real, tmp);
+  real *qLD = sm + S_QLD, *ftmp = sm + S_VEC + 128, *ftmp2 = sm + S_VEC + 144;
+  LV(real, tmp); LV(real, tmp2);
   for (int k = cm.nv - 1; k >= 0; --k) {
     const int dk = cm.dof_depth[k];
     if (dk == 0) continue;
     const int kk = cm.dof_Madr[k];
     if (cm.nfac > 0) {
       // balanced schedule: the dk(dk+1)/2 independent updates  M(anc_t, .)[c] -= M(k, .)[t+c] * f_t  are dealt round-robin to the lanes
-      LANES L(tmp) = 0; if (l >= 1 && l <= dk) { L(tmp) = qLD[kk + l] * mrcp(qLD[kk]); ftmp[l] = L(tmp); } ENDL
+      LANES L(tmp) = 0; L(tmp2) = 0; if (l >= 1 && l <= dk) { L(tmp) = qLD[kk + l] * mrcp(qLD[kk]); ftmp[l] = L(tmp); if (q2) { L(tmp2) = q2[kk + l] * mrcp(q2[kk]); ftmp2[l] = L(tmp2); } } ENDL
       const int p0 = cm.fac_start[k], p1 = cm.fac_start[k + 1];
-      LANES
-        for (int p = p0 + l; p < p1; p += 32) { const uint32_t e = cm.fac_pairs[p]; qLD[e & 0xfffu] -= qLD[(e >> 12) & 0xfffu] * ftmp[e >> 24]; }
-      ENDL
-      LANES if (l >= 1 && l <= dk) qLD[kk + l] = L(tmp); ENDL
+      if (q2) {
+        LANES
+          for (int p = p0 + l; p < p1; p += 32) { const uint32_t e = cm.fac_pairs[p]; const int dst = e & 0xfffu, src = (e >> 12) & 0xfffu, t = e >> 24;
+            qLD[dst] -= qLD[src] * ftmp[t]; q2[dst] -= q2[src] * ftmp2[t]; }
+        ENDL
+        LANES if (l >= 1 && l <= dk) { qLD[kk + l] = L(tmp); q2[kk + l] = L(tmp2); } ENDL
+      } else {
+        LANES
+          for (int p = p0 + l; p < p1; p += 32) { const uint32_t e = cm.fac_pairs[p]; qLD[e & 0xfffu] -= qLD[(e >> 12) & 0xfffu] * ftmp[e >> 24]; }
+        ENDL
+        LANES if (l >= 1 && l <= dk) qLD[kk + l] = L(tmp); ENDL
+      }
     } else {
       const uint32_t anc = cm.dof_ancmask[k];
-      LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
-        L(tmp) = 0;
-        if ((anc >> l) & 1u) {
-          const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
-          const real f = qLD[kk + t] / qLD[kk];
-          const real *rk = qLD + kk + t; real *ri = qLD + ia;
-          for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
-          L(tmp) = f;
-        }
-      ENDL
-      LANES if ((anc >> l) & 1u) qLD[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
+      for (int pass = 0; pass < (q2 ? 2 : 1); ++pass) {
+        real *Q = pass ? q2 : qLD;
+        LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
+          L(tmp) = 0;
+          if ((anc >> l) & 1u) {
+            const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
+            const real f = Q[kk + t] / Q[kk];
+            const real *rk = Q + kk + t; real *ri = Q + ia;
+            for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
+            L(tmp) = f;
+          }
+        ENDL
+        LANES if ((anc >> l) & 1u) Q[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
+      }
     }
   }
   LANES if (l < cm.nv) { const real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = mrcp(d); sm[S_DSQI + l] = mrcp(msqrt(d)); } ENDL
@@ -442,6 +455,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
                                                  // sub-step of a launch fills it (what a query after the launch would see)
   const real *bmass = ce ? ce + CE_MASS : cm.body_mass, *bipos = ce ? ce + CE_IPOS : &cm.body_ipos[0][0], *ddamp = ce ? ce + CE_DAMP : cm.dof_damping;
   const real *binvw = ce ? ce + CE_BINVW : cm.body_invw, *dinvw = ce ? ce + CE_DINVW : cm.dof_invweight0;
+  const bool use2 = advance && (cm.has_damping || ce);   // the Euler stage needs the factor of M + h B: produced together with M's
+  const bool keep_qM = dbg || mode == 3;                 // the unfactored M itself is only wanted by the debug dump and by set_const
   const real root_mass_inv = ce ? ce[CE_ROOT_MINV] : cm.root_mass_inv, total_mass_inv = ce ? ce[CE_TOT_MINV] : cm.total_mass_inv, pgs_scale = ce ? ce[CE_PGS_SCALE] : cm.pgs_scale;
   const real xb_dsqi_t = (ce && cm.xb >= 0) ? real(1) / msqrt(bmass[cm.xb]) : cm.xb_dsqi[0];   // the extra free body's mass acts at once, like every body_mass entry
   DECL_LANE
@@ -450,6 +465,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
   real *qpos = sm + S_QPOS, *qM = E.qM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
+  real *qLD2 = sm + S_Y + T_CVEL;   // second matrix of the fused factorisation: the velocity-stage temporaries are not live yet
   const real *xfrc = E.xfrc; int *counters = E.counters;
   // temporaries of the smooth-dynamics stages live in the (not yet used) constraint-matrix region
   real *cinert = sm + S_Y + T_CINERT, *cdofd = sm + S_Y + T_CDOFD;
@@ -579,12 +595,16 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           const real *cj = cdof + 6 * j;
           real s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
           if (j == l) s += cm.dof_armature[l];
-          qM[a] = s; qLD[a] = s; ++a;
+          qLD[a] = s; if (keep_qM) qM[a] = s;
+          if (use2) qLD2[a] = (j == l) ? s + cm.timestep * ddamp[l] : s;
+          ++a;
         }
       }
     ENDL
   }
-  factor_ld(cm, sm);
+  factor_ld(cm, sm, use2 ? qLD2 : (real *)0);
+  // the factor of M + h B waits in the env's global scratch row until the Euler stage (the constraint stage needs this shared memory)
+  if (use2) { LANES for (int k = l; k < cm.nM; k += 32) qM[NM_MAX + k] = qLD2[k]; ENDL }
   if (dbg) { LANES for (int a = l; a < cm.nM; a += 32) { dbg[D_QM + a] = qM[a]; dbg[D_QLD + a] = qLD[a]; } ENDL }
 
   // ================= mode 3: mj_setConst for this env (src/cassiemujoco.c:949-977 -> set0 / setStat [M]) =================
@@ -1272,9 +1292,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
   if (cm.has_damping || ce) {
-    LANES for (int k = l; k < cm.nM; k += 32) qLD[k] = qM[k]; ENDL          // the inverse factor of M is dead: reuse its buffer
-    LANES if (l < nv) qLD[cm.dof_Madr[l]] += cm.timestep * ddamp[l]; ENDL
-    factor_ld(cm, sm);
+    LANES for (int k = l; k < cm.nM; k += 32) qLD[k] = qM[NM_MAX + k]; ENDL   // the factor of M is dead: its buffer takes the factor of M + h B
+    LANES if (l < nv) sm[S_DINV + l] = mrcp(qLD[cm.dof_Madr[l]]); ENDL
     LANES L(a) = (l < nv) ? cm.timestep * ddamp[l] * L(qacc) : real(0); ENDL
     solve_m(cm, sm, a);
     LANES L(a) = L(qacc) - L(a); ENDL

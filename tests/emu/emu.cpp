@@ -13,7 +13,7 @@ using namespace cassie;
 
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; BuildInfo info; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[NM_MAX], aux[AUX_W], cenv[CE_W], task[TASK_W]; int counters[8]; bool use_task = false; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
+  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[2 * NM_MAX], aux[AUX_W], cenv[CE_W], task[TASK_W]; int counters[8]; bool use_task = false; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
   EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.task = use_task ? task : nullptr; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
