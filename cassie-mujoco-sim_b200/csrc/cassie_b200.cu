@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   // persistent CTAs: a CTA draws one environment per warp from a global ticket counter until the batch is exhausted; its warps walk the
   // stages together (STAGE_SYNC) so that they share instruction-cache lines -- the kernel is ~250 KB of code, eight times the L1.5
   __shared__ int cta_base;
-  const int nwarps = blockDim.x >> 5, sync_on = A.cta_sync && mode == 0 && nticks > 1;   // a single tick starts in step and stays close enough
+  const int nwarps = blockDim.x >> 5, sync_on = (mode == 0 && nticks > 1) ? A.cta_sync : 0;   // a single tick starts in step and stays close enough
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) cta_base = atomicAdd(A.ticket, nwarps);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     const int env = base + warp;
     const bool active = env < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
     if (!active) {   // keep the rendezvous count of the working warps
-      if (sync_on) { for (int i = 0; i < nticks * cm.nsub * 5; ++i) __syncthreads(); }
+      if (sync_on) { const int per = __popc(sync_on); for (int i = 0; i < nticks * cm.nsub * per; ++i) __syncthreads(); }
       continue;
     }
     // warm the L2/L1 path of the rows that are addressed in place later (controller state, PD row, FIR taps)
@@ -229,7 +229,7 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
     h_model_copy = *hmodel; memcpy(geom_dev, info.geom_dev, sizeof geom_dev);
     const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
-    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : 1;
+    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; { const char *e = getenv("CASSIE_B200_SYNCMASK"); A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : (e ? (atoi(e) & 31) : 10); }   // which of the five per-sub-step rendezvous are on
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QW)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * VW)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * VW));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));

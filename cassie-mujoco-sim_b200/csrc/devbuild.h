@@ -216,6 +216,21 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = (real)solimp[k];
     }
   }
+  // mirror symmetry of the dof tree: a base chain 0..f-1, then two blocks of n dofs with identical relative structure hanging off dof f-1
+  d.sym_on = 0;
+  { const int nv2 = d.nv;
+    for (int j = 2; j < nv2 && !d.sym_on; j++) {   // candidate root of the second leg: a dof whose parent p is not its predecessor
+      const int p = m.dof_parentid[j]; if (p < 0 || p >= j - 1) continue;
+      const int first = p + 1, n = j - first; if (n < 1 || j + n != nv2) continue;
+      bool ok = m.dof_parentid[first] == p;
+      for (int i = 1; i < first && ok; i++) ok = m.dof_parentid[i] == i - 1;                       // the base is a chain
+      for (int r = 1; r < n && ok; r++) { const int pa = m.dof_parentid[first + r], pb = m.dof_parentid[j + r]; ok = pa >= first && pb == pa + n; }
+      if (ok && first == 6 && n == 13 && !std::getenv("CASSIE_B200_NOSYM")) { d.sym_on = 1; d.sym_first = first; d.sym_n = n; d.sym_madr = m.dof_Madr[j] - m.dof_Madr[first]; }   // the unrolled products are written for the Cassie tree (6 + 13 + 13)
+    }
+    for (int b = 0; b < m.nbody; b++) { int sd = 0; const int ld = d.body_lastdof[b];
+      if (d.sym_on && ld >= d.sym_first) sd = ld < d.sym_first + d.sym_n ? 1 : 2;
+      d.body_side[b] = (unsigned char)sd; }
+  }
   // feet: bodies `left-foot` / `right-foot`; toe and heel points = the named sites when the model has them (model/cassie.xml:153-154,
   // 219-220), else the end points of the foot capsule (where cassie.xml puts those sites; cassie_hfield.xml / cassie_tray_box.xml lack them)
   d.foot_offset = (real)std::sqrt(0.01762 * 0.01762 + 0.05219 * 0.05219);   // src/cassiemujoco.c:1618

@@ -45,6 +45,10 @@ struct DevModel {
   int body_parent[MB], body_depth[MB], body_jntadr[MB], body_jntnum[MB], body_lastdof[MB], body_subtree_end[MB];
   uint32_t body_dofmask[MB];
   real body_pos[MB][3], body_quat[MB][4], body_ipos[MB][3], body_imat[MB][9], body_mass[MB], body_inertia[MB][3], body_invw[MB];
+  // mirror symmetry of the dof tree (two identical legs below a common base chain): lets the row transform and the A = Y Y' products skip the
+  // leg a constraint row does not touch.  body_side: 0 base / world / extra body, 1 first leg, 2 second leg
+  int sym_on, sym_first, sym_n, sym_madr;
+  unsigned char body_side[MB];
   // ---- joints
   int jnt_type[MJ], jnt_qposadr[MJ], jnt_dofadr[MJ], jnt_body[MJ], jnt_limited[MJ];
   real jnt_pos[MJ][3], jnt_axis[MJ][3], jnt_stiffness[MJ], jnt_range[MJ][2], jnt_qpos0[MJ], jnt_qspring[MJ], jnt_solref[MJ][2], jnt_solimp[MJ][5];
@@ -149,7 +153,7 @@ constexpr int T_GEOM = 1216;                    // [16][12] geom world poses (po
 static_assert(T_GEOM + 192 <= NEFC * YSTRIDE_MAIN, "temporaries must fit in the constraint-matrix region");
 static_assert(NEFC >= 48 && 16 * YSTRIDE_MAX <= S_QLD - S_XPOS, "the dense solver path keeps A in rows 32..47 of Y and in the kinematics buffers");
 // slots of a row's 4 scalars while the rows are being built (overwritten by the solver constants afterwards)
-constexpr int E_POS = 0, E_SRC = 1, E_INEQ = 2;
+constexpr int E_POS = 0, E_SRC = 1, E_INEQ = 2, E_SIDE = 3;   // E_SIDE: 0 / 1 the row touches the base and at most the first leg, 2 ... the second leg, 3 both legs
 
 
 // ---- debug dump (tests only; one block per env, in `real`)

@@ -83,6 +83,7 @@ CFN float matan2(float y, float x) { return atan2f(y, x); }
 CFN double matan2(double y, double x) { return atan2(y, x); }
 CFN float masin(float x) { return asinf(x); }
 CFN double masin(double x) { return asin(x); }
+CFN int mmax(int a, int b) { return a > b ? a : b; }
 CFN float mabs(float x) { return fabsf(x); }
 CFN double mabs(double x) { return fabs(x); }
 CFN float mmax(float a, float b) { return fmaxf(a, b); }
@@ -422,6 +423,27 @@ CFN real half_solve_row(const DevModel<real> &cm, const real *sm, real *yy, int 
   return ad;
 }
 
+// the same transform for a row that touches the base chain and ONE of the two mirrored legs (off = 0: first leg, off = sym_n: second leg): the
+// leg's dofs are walked through the first leg's tables with a per-lane offset, the other leg's entries (exact zeros) are left alone
+template <typename real>
+CFN real half_solve_row_sym(const DevModel<real> &cm, const real *sm, real *yy, int off) {
+  const real *qLD = sm + S_QLD; const int f = cm.sym_first, n = cm.sym_n, moff = off ? cm.sym_madr : 0;
+  for (int r = n - 1; r >= 0; --r) {
+    const int i0 = f + r, di = cm.dof_depth[i0];
+    const real xi = yy[i0 + off]; const real *Li = qLD + cm.dof_Madr[i0] + moff; const unsigned char *an = cm.dof_anc[i0];
+    for (int t = 1; t <= di; ++t) { int a = an[t]; if (a >= f) a += off; yy[a] -= Li[t] * xi; }
+  }
+  for (int i = f - 1; i > 0; --i) {
+    const int di = cm.dof_depth[i]; const real xi = yy[i]; const real *Li = qLD + cm.dof_Madr[i]; const unsigned char *an = cm.dof_anc[i];
+    for (int t = 1; t <= di; ++t) yy[an[t]] -= Li[t] * xi;
+  }
+  real ad = 0;
+  for (int d = 0; d < f; ++d) { const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
+  for (int r = 0; r < n; ++r) { const int d = f + r + off; const real v = yy[d] * sm[S_DSQI + d]; yy[d] = v; ad += v * v; }
+  return ad;
+}
+CFN int side_of(int s1, int s2) { return s1 == 0 ? s2 : (s2 == 0 || s2 == s1 ? s1 : 3); }
+
 // cassie_sim_foot_velocities (src/cassiemujoco.c:1623-1631): mj_comVel of the two foot bodies = sum over the dof chain, root first, of
 // cdof * qvel; qvel is read from vecs[0..nv), cdof from the copy the derived-quantity stage left in the geom buffer
 template <typename real>
@@ -460,8 +482,8 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   const real root_mass_inv = ce ? ce[CE_ROOT_MINV] : cm.root_mass_inv, total_mass_inv = ce ? ce[CE_TOT_MINV] : cm.total_mass_inv, pgs_scale = ce ? ce[CE_PGS_SCALE] : cm.pgs_scale;
   const real xb_dsqi_t = (ce && cm.xb >= 0) ? real(1) / msqrt(bmass[cm.xb]) : cm.xb_dsqi[0];   // the extra free body's mass acts at once, like every body_mass entry
   DECL_LANE
-  const bool csync = E.cta_sync != 0;   // set by the kernel wrapper for multi-tick step launches only
-  STAGE_SYNC(csync);
+  const int csync = E.cta_sync;   // bit k: rendezvous k of the sub-step is on (set by the kernel wrapper for multi-tick step launches only)
+  STAGE_SYNC(csync & 1);
   const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
   real *qpos = sm + S_QPOS, *qM = E.qM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
@@ -824,7 +846,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
-  STAGE_SYNC(csync);
+  STAGE_SYNC(csync & 2);
   // ================= collision (lane = candidate geom pair) =================
   real *geom = sm + S_Y + T_GEOM;   // the smooth-dynamics temporaries below it are dead; the constraint rows are written after the contact list
   LANES
@@ -935,7 +957,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       for (int k = 0; k < 3; ++k) {
         Y[(nefc + k) * ys + l] = j1[k] - j2[k];
         if (xb >= 0 && l < 6) Y[(nefc + k) * ys + 32 + l] = 0;
-        if (l == 0) { efc[4 * (nefc + k) + E_POS] = p1[k] - p2[k]; efc[4 * (nefc + k) + E_SRC] = (real)e; efc[4 * (nefc + k) + E_INEQ] = 0; }
+        if (l == 0) { efc[4 * (nefc + k) + E_POS] = p1[k] - p2[k]; efc[4 * (nefc + k) + E_SRC] = (real)e; efc[4 * (nefc + k) + E_INEQ] = 0; efc[4 * (nefc + k) + E_SIDE] = (real)side_of(cm.body_side[b1], cm.body_side[b2]); }
       }
     ENDL
     nefc += 3;
@@ -956,7 +978,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         if (dist < 0 && r < NEFC) {
           for (int d = 0; d < ys - 1; ++d) Y[r * ys + d] = 0;
           Y[r * ys + cm.jnt_dofadr[l]] = side ? real(-1) : real(1);
-          efc[4 * r + E_POS] = dist; efc[4 * r + E_SRC] = (real)(64 + l); efc[4 * r + E_INEQ] = 1; ++r;
+          efc[4 * r + E_POS] = dist; efc[4 * r + E_SRC] = (real)(64 + l); efc[4 * r + E_INEQ] = 1; efc[4 * r + E_SIDE] = (real)cm.body_side[cm.jnt_body[l]]; ++r;
         }
       }
     }
@@ -994,7 +1016,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           Y[(nefc + 2) * ys + 32 + l] = xn + mu * xt2; Y[(nefc + 3) * ys + 32 + l] = xn - mu * xt2;
         }
       }
-      if (l < rows) { efc[4 * (nefc + l) + E_POS] = o[12]; efc[4 * (nefc + l) + E_SRC] = (real)(128 + p); efc[4 * (nefc + l) + E_INEQ] = 1; }
+      if (l < rows) { efc[4 * (nefc + l) + E_POS] = o[12]; efc[4 * (nefc + l) + E_SRC] = (real)(128 + p); efc[4 * (nefc + l) + E_INEQ] = 1; efc[4 * (nefc + l) + E_SIDE] = (real)side_of(cm.body_side[b1], cm.body_side[b2]); }
       if (l == 0) con[16 * c + 14] = (real)nefc;   // first row of this contact (read back by the contact-force stage)
     ENDL
     nefc += rows; ++ncon_used;
@@ -1015,7 +1037,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
   }
 
-  STAGE_SYNC(csync);
+  STAGE_SYNC(csync & 4);
   LV(real, qacc); LV(real, qfrc_con);
   LV(real, f0); LV(real, f1);    // constraint forces: lane (r & 31) owns rows r and r + 32
   int iters = 0;
@@ -1026,10 +1048,18 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     LANES if (l < nv) { vecs[l] = L(qvel); vecs[32 + l] = L(qacc_smooth); vecs[64 + l] = L(qacc_ws); } L(f0) = L(f1) = 0;
       if (xb >= 0 && l < 6) { vecs[160 + l] = L(xqvel); vecs[166 + l] = L(xqacc_smooth); vecs[172 + l] = L(xqacc_ws); } ENDL
     if (dbg) { LANES for (int r = 0; r < nefc; ++r) dbg[D_J + 32 * r + l] = Y[r * ys + l]; ENDL }
+    LV(int, side);   // lane r: which leg row r touches (E_SIDE), kept for the products below
+    LANES L(side) = 0; ENDL
     for (int pass = 0; pass * 32 < nefc; ++pass) {
+      // rows that touch a single leg take the mirrored-leg transform; one row over both legs (leg-leg contact) sends the whole pass the long way
+      LV(int, anyb);
+      LANES { const int r = l + 32 * pass; L(anyb) = (r < nefc && (int)efc[4 * r + E_SIDE] == 3) ? 1 : 0; } ENDL
+      ALLMAX(anyb);
+      const bool symrows = cm.sym_on && LANE0(anyb) == 0;
       LANES
         const int r = l + 32 * pass;
         if (r < nefc) {
+          const int sd = (int)efc[4 * r + E_SIDE]; if (pass == 0) L(side) = symrows ? sd : 3;
           real *yy = Y + r * ys; real jv = 0, ja = 0, jw = 0;
           for (int d = 0; d < nv; ++d) { const real y = yy[d]; jv += y * vecs[d]; ja += y * vecs[32 + d]; jw += y * vecs[64 + d]; }
           if (xb >= 0) for (int d = 0; d < 6; ++d) { const real y = yy[32 + d]; jv += y * vecs[160 + d]; ja += y * vecs[166 + d]; jw += y * vecs[172 + d]; }
@@ -1053,7 +1083,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (pass == 0) L(f0) = f; else L(f1) = f;
           if (dbg) { dbg[D_EFC_AREF + r] = aref; dbg[D_EFC_R + r] = Rr; dbg[D_EFC_B + r] = ja - aref; }
           // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place; all lanes (rows) walk the same (i, ancestor) sequence
-          real ad = half_solve_row(cm, sm, yy, nv);
+          real ad = symrows ? half_solve_row_sym(cm, sm, yy, sd == 2 ? cm.sym_n : 0) : half_solve_row(cm, sm, yy, nv);
           if (xb >= 0) for (int d = 0; d < 6; ++d) { const real v = yy[32 + d] * (d < 3 ? xb_dsqi_t : cm.xb_dsqi[d]); yy[32 + d] = v; ad += v * v; }
           // packed row constants for the solver: b, 1/A, A, +-R (sign bit set = inequality row)
           real *rc = efc + 4 * r; const real Ad = ad + Rr;
@@ -1074,11 +1104,23 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
 #pragma unroll
           for (int d = 0; d < 32; ++d) LA(yreg, d) = (l < nefc) ? Y[l * ys + d] : real(0);
         ENDL_NS
+        LV(int, sc);
         for (int c = 0; c < nefc; ++c) {
+          BCAST(sc, side, c);   // column c touches the base and one leg only: its entries on the other leg are exact zeros
           LANES_NS
             const real *yc = Y + c * ys; real sacc = 0;
+            if (LANE0(sc) == 3) {
 #pragma unroll
-            for (int d = 0; d < 32; ++d) sacc += LA(yreg, d) * yc[d];
+              for (int d = 0; d < 32; ++d) sacc += LA(yreg, d) * yc[d];
+            } else if (LANE0(sc) == 2) {
+#pragma unroll
+              for (int d = 0; d < 6; ++d) sacc += LA(yreg, d) * yc[d];
+#pragma unroll
+              for (int d = 19; d < 32; ++d) sacc += LA(yreg, d) * yc[d];
+            } else {
+#pragma unroll
+              for (int d = 0; d < 19; ++d) sacc += LA(yreg, d) * yc[d];
+            }
             if (xb >= 0 && l < nefc) for (int d = 32; d < 38; ++d) sacc += Y[l * ys + d] * yc[d];
             if (c == l) sacc += mabs(efc[4 * c + 3]);
             AM(c)[l] = sacc;
@@ -1214,7 +1256,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       ENDL
     }
   }
-  STAGE_SYNC(csync);
+  STAGE_SYNC(csync & 8);
   if (counters) { LANES if (l == 0) counters[3] = iters; ENDL }
   // ================= derived quantities, part 3: contact forces (mj_contactForce -> world frame), foot / toe / heel sums, collision flags
   // (cassie_sim_foot_forces :1812-1854, cassie_sim_heeltoe_forces :1856-1898, check_*_collision :1586-1606, geom_collision :1944-1961)
@@ -1287,7 +1329,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     if (auxr) { LANES if (l < nv) vecs[l] = L(qvel); ENDL aux_foot_velocities(cm, sm, auxr); }
     return;
   }
-  STAGE_SYNC(csync);
+  STAGE_SYNC(csync & 16);
   // ================= Euler with implicit joint damping (mj_Euler) + mj_advance =================
   // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
