@@ -39,7 +39,7 @@ sys.path.insert(0, os.path.join(REPO, 'oracle'))
 PD_TARGET = [0.0045, 0, 0.4973, -1.1997, -1.5968, -0.0045, 0, 0.4973, -1.1997, -1.5968]
 PD_PGAIN = [70, 70, 100, 100, 50] * 2
 PD_DGAIN = [7, 7, 8, 8, 5] * 2
-STATE_BYTES_FP32 = 4 * ((36 + 32 + 32 + 192 + 52 + 8 + 96) + (36 + 32 + 32 + 192 + 96 + 64))   # rows read + rows written per env per launch
+STATE_BYTES_FP32 = 4 * ((36 + 32 + 32 + 192 + 52 + 8 + 96) + (36 + 32 + 32 + 192 + 96 + 96))   # rows read + rows written per env per launch
 WORKLOAD = 'config2: 4096 envs/GPU cassie.xml flat floor, fixed motor-PD targets, pelvis z/yaw jitter U(-0.01,0.01) seed 0'
 
 
@@ -355,7 +355,7 @@ def gpu_arm(args, rank, local_rank, world):
                         'api': 'cassie_sim_step_pd_batch(envs, pd_in_t[n] host, state_out_t[n] host), %d steps, host AoS pack/unpack included%s' % (
                             e2e_steps, ''), 'obs_allgather_ms': ms_gather},
                 'gpu_launches': launches, 'per_rank': per_rank,
-                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': 9.07e6,   # dram__bytes_read.sum + write.sum per launch, profiles/r1_step_kernel_v3_ncu_summary.md
+                'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': 9.29e6,   # dram__bytes_read.sum + write.sum of a single-tick launch, profiles/r1_step_kernel_v6_ncu_summary.md
                              'peak_source': peak_src, 'bytes_per_env_per_launch': STATE_BYTES_FP32, 'ticks_per_launch': T,
                              'note': 'latency/issue-bound by design (SURVEY 8d): algorithmic HBM traffic is only the persistent state rows in+out'},
                 'single_tick_launches': {'ms_per_step': ms_single, 'env_steps_per_s_this_rank': n / (ms_single * 1e-3), 'note': 'the same K steps as K launches of one tick'},
