@@ -1,7 +1,7 @@
 """dev aid: a short tour of every kernel instance / mode, meant to be run under compute-sanitizer (not a pytest file)"""
 import importlib, os, sys
 import numpy as np
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
 from conftest import PD_TARGET, PD_PGAIN, PD_DGAIN
 from test_task_pd import task_rows

@@ -1,7 +1,7 @@
 """quick GPU sanity + timing used during development (not a pytest file)"""
 import importlib, os, sys, time
 import numpy as np
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
 from conftest import PD_TARGET, PD_PGAIN, PD_DGAIN
 P = importlib.import_module('cassie-mujoco-sim_b200')

@@ -1,7 +1,7 @@
 """GPU soak (development aid, not a pytest file): random PD targets re-drawn every 50 ticks, pushes, 16384 envs, 4000 ticks; everything must stay finite."""
 import importlib, os, sys
 import numpy as np
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
 from conftest import PD_TARGET, PD_PGAIN, PD_DGAIN
 P = importlib.import_module('cassie-mujoco-sim_b200')

@@ -1,6 +1,6 @@
 """dev aid: step time vs warps per CTA for a few batch sizes (not a pytest file)"""
 import importlib, os, subprocess, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == 'child':
     import numpy as np, torch
     sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
