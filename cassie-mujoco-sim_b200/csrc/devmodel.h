@@ -104,7 +104,7 @@ constexpr int OB_MPOS = 0, OB_MVEL = 10, OB_MTORQUE = 20, OB_JPOS = 30, OB_JVEL 
 // stateless part of the reference's estimator (state_output_step, closed source; semantics recovered by probing the archive):
 constexpr int OB_EST_ACC = 56;    // [3] pelvis.translationalAcceleration
 constexpr int OB_FOOT = 60;       // [2][13] per foot: position 3, orientation 4 (pelvis frame), rotational velocity 3, translational velocity 3 (foot frame)
-constexpr int OB_EST_QUAT = 86;   // [4] pelvis.orientation (IMU quaternion with w >= 0)
+constexpr int OB_EST_QUAT = 86;   // [4] pelvis.orientation (IMU quaternion through its rotation matrix and back: +-q)
 
 // derived-quantity row (optional, cassie_batch_enable_aux): the reference's read-only queries (src/cassiemujoco.c:1586-1961) as by-products
 constexpr int AUX_W = 64;

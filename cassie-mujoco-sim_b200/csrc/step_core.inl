@@ -1363,6 +1363,16 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   ENDL
 }
 
+// rotation matrix (row-major) -> quaternion with MuJoCo's mat2quat branches; the estimator's quaternion signs follow them
+template <typename real>
+CFN void est_mat2quat(real *q, const real *R) {
+  const real t = R[0] + R[4] + R[8];
+  if (t > 0) { const real s = msqrt(t + 1) * 2; q[0] = real(0.25) * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { const real s = msqrt(1 + R[0] - R[4] - R[8]) * 2; q[0] = (R[7] - R[5]) / s; q[1] = real(0.25) * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { const real s = msqrt(1 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = real(0.25) * s; q[3] = (R[5] + R[7]) / s; }
+  else { const real s = msqrt(1 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = real(0.25) * s; }
+}
+
 // ------------------------------------------------------------------ estimator, stateless part (state_output_step [closed], decoded)
 // Foot pose and velocity of one leg from the MEASURED angles: chain pelvis -> hipRoll -> hipYaw -> hipPitch, then the planar part knee ->
 // shin -> tarsus -> foot (parallel axes: angles add up).  sc = {sin, cos} of hipRoll, hipYaw, hipPitch and of the four cumulative planar
@@ -1416,14 +1426,7 @@ CFN void est_foot(int side, const real *sc, const real *rate, real *out, real *j
   const real pl[3] = {px, py, 0}; mat_vec(v, A2, pl);
   vl[0] += v[0]; vl[1] += v[1]; vl[2] += v[2];
   out[0] = pos[0]; out[1] = pos[1]; out[2] = pos[2];
-  {  // mat2quat with MuJoCo's branches (the estimator's signs follow them)
-    real q[4]; const real t = Rf[0] + Rf[4] + Rf[8];
-    if (t > 0) { const real s = msqrt(t + 1) * 2; q[0] = real(0.25) * s; q[1] = (Rf[7] - Rf[5]) / s; q[2] = (Rf[2] - Rf[6]) / s; q[3] = (Rf[3] - Rf[1]) / s; }
-    else if (Rf[0] > Rf[4] && Rf[0] > Rf[8]) { const real s = msqrt(1 + Rf[0] - Rf[4] - Rf[8]) * 2; q[0] = (Rf[7] - Rf[5]) / s; q[1] = real(0.25) * s; q[2] = (Rf[1] + Rf[3]) / s; q[3] = (Rf[2] + Rf[6]) / s; }
-    else if (Rf[4] > Rf[8]) { const real s = msqrt(1 + Rf[4] - Rf[0] - Rf[8]) * 2; q[0] = (Rf[2] - Rf[6]) / s; q[1] = (Rf[1] + Rf[3]) / s; q[2] = real(0.25) * s; q[3] = (Rf[5] + Rf[7]) / s; }
-    else { const real s = msqrt(1 + Rf[8] - Rf[0] - Rf[4]) * 2; q[0] = (Rf[3] - Rf[1]) / s; q[1] = (Rf[2] + Rf[6]) / s; q[2] = (Rf[5] + Rf[7]) / s; q[3] = real(0.25) * s; }
-    out[3] = q[0]; out[4] = q[1]; out[5] = q[2]; out[6] = q[3];
-  }
+  est_mat2quat(out + 3, Rf);
   matT_vec(out + 7, Rf, w); matT_vec(out + 10, Rf, vl);
   if (jac) {   // pelvis-frame Jacobian of the foot point: hip roll, hip yaw, then hip pitch / knee / foot about the common z of the hip-pitch frame
     d[0] = pos[0] - anchor0[0]; d[1] = pos[1] - anchor0[1]; d[2] = pos[2] - anchor0[2]; cross3(cr, axis0, d);
@@ -1577,10 +1580,10 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
           const real rate[7] = {mv[0], mv[1], mv[2], mv[3], jv[0], jv[1], mv[4]};
           est_foot<real>(sd, vecs + 32 + 14 * sd, rate, obs + OB_FOOT + 13 * sd);
         } else if (l == 2) {
-          const real *q = cst + CS_SENSOR + 16, *w = cst + CS_SENSOR + 20, *a = cst + CS_SENSOR + 23; const real sgq = q[0] < 0 ? real(-1) : real(1);
-          for (int k = 0; k < 4; ++k) obs[OB_EST_QUAT + k] = sgq * q[k];
+          const real *q = cst + CS_SENSOR + 16, *w = cst + CS_SENSOR + 20, *a = cst + CS_SENSOR + 23;
           real R[9], wr[3], wwr[3]; const real r[3] = {real(0.03155), 0, real(-0.079996)};
           quat2mat(R, q); cross3(wr, w, r); cross3(wwr, w, wr);
+          est_mat2quat(obs + OB_EST_QUAT, R);   // pelvis.orientation: the IMU quaternion through its matrix and back (+-q, mat2quat's sign)
           for (int k = 0; k < 3; ++k) obs[OB_EST_ACC + k] = a[k] - R[6 + k] * real(9.806) - wwr[k];
         }
       ENDL

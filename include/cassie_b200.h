@@ -129,7 +129,7 @@ void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask);
 /* cassie_sim_step_pd for every environment: pd_in[n_env] host AoS in, state_out[n_env] host AoS out (may be NULL).
  * Replaces n_env calls of src/cassiemujoco.c:1147-1157.  Synchronous.  state_out carries the stateless part of the reference's
  * state_output_step, decoded from the closed archive and checked equal to it to 1e-11: motor / joint position + velocity + torque,
- * pelvis.orientation (w >= 0), rotationalVelocity, translationalAcceleration, both feet's position / orientation (pelvis frame) and
+ * pelvis.orientation (+-q, mat2quat's sign), rotationalVelocity, translationalAcceleration, both feet's position / orientation (pelvis frame) and
  * footRotationalVelocity / footTranslationalVelocity (foot frame), radio, battery.  The stateful outputs (pelvis.position,
  * translationalVelocity, externalForce / externalMoment, toe / heel forces, terrain) are zero (scope). */
 void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_out_t *state_out);
@@ -147,7 +147,7 @@ void cassie_batch_sync(cassie_batch_t *b);
 /* host copies (synchronous): qpos [n][35], qvel [n][32], time [n], obs [n][CASSIE_OBS_WIDTH] =
  * motor pos[10] vel[10] torque[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3] mag[3], time (0..55);
  * estimator: translationalAcceleration[3] (56), pad, per foot {position 3, orientation 4, rotational velocity 3, translational
- * velocity 3} left (60..72) right (73..85), pelvis.orientation[4] (86..89), pad */
+ * velocity 3} left (60..72) right (73..85), pelvis.orientation[4] (86..89; the IMU quaternion up to sign), pad */
 void cassie_batch_get_qpos(cassie_batch_t *b, double *out);
 void cassie_batch_set_qpos(cassie_batch_t *b, const double *in);
 void cassie_batch_get_qvel(cassie_batch_t *b, double *out);

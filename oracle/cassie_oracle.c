@@ -1074,7 +1074,8 @@ void o_core_sim_step(const double u[10], const cassie_out_t *o, double out[10]) 
 /* ---- state_output_step: the STATELESS part of the closed estimator, decoded by probing the archive (oracle/probe_estimator.c,
  * oracle/probe_est_tools.py; agreement with the archive 1e-14 over random inputs, tests/test_agility_twins.py):
  *  - pass-through: motor / joint position, velocity, torque, radio, battery, IMU gyro;
- *  - pelvis.orientation = IMU quaternion with its sign chosen so that w >= 0;
+ *  - pelvis.orientation = the IMU quaternion sent through its rotation matrix and back (mat2quat with MuJoCo's branches): +q or -q, the sign
+ *    being the one that makes w positive when the trace is positive, else the largest-diagonal component positive;
  *  - pelvis.translationalAcceleration = accelerometer - R(q)' (0, 0, 9.806) - w x (w x r)   (body frame, gravity removed, moved from the
  *    IMU site to the pelvis origin without the angular-acceleration term);
  *  - per foot: forward kinematics of a 7-link chain pelvis -> hipRoll -> hipYaw -> hipPitch -> knee -> shin -> tarsus -> foot with the MJCF's
@@ -1149,8 +1150,8 @@ void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
   memset(y, 0, sizeof *y);
   for (int i = 0; i < 10; i++) { elmo_out_t *e = drive_ptr(&out, i); y->motor.position[i] = e->position; y->motor.velocity[i] = e->velocity; y->motor.torque[i] = e->torque; }
   for (int i = 0; i < 6; i++) { cassie_joint_out_t *j = joint_ptr(&out, i); y->joint.position[i] = j->position; y->joint.velocity[i] = j->velocity; }
-  const double *q = out.pelvis.vectorNav.orientation, sgn = q[0] < 0 ? -1.0 : 1.0;
-  for (int k = 0; k < 4; k++) y->pelvis.orientation[k] = sgn * q[k];
+  const double *q = out.pelvis.vectorNav.orientation;
+  { double Rq[9]; quat2Mat(Rq, q); est_mat2quat(y->pelvis.orientation, Rq); }   /* through the rotation matrix: +-q with mat2quat's sign choice */
   copyv(y->pelvis.rotationalVelocity, out.pelvis.vectorNav.angularVelocity, 3);
   { /* accelerometer moved from the IMU (r = (0.03155, 0, -0.079996) from the pelvis origin; the MJCF site has -0.07996, model/cassie.xml:87) to the pelvis origin, centripetal part only: a - w x (w x r) */
     double R[9], wr[3], wwr[3]; const double r[3] = {0.03155, 0, -0.079996}, *w = out.pelvis.vectorNav.angularVelocity;
@@ -1427,6 +1428,16 @@ double *osim_model_array(OSim *c, const char *key, int *n) {
   MARR("body_subtreemass", m->body_subtreemass, m->nbody) MARR("meaninertia", &m->meaninertia, 1) MARR("body_pos", m->body_pos, 3 * m->nbody)
   *n = 0; return NULL;
 }
+
+/* cassie_out_t image from the flat probe layout (oracle/probe_estimator.c): motor pos[10] vel[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3] mag[3] */
+void osim_fill_cassie_out(cassie_out_t *o, const double *in) {
+  cassie_out_init_(o);
+  for (int i = 0; i < 10; i++) { elmo_out_t *e = drive_ptr(o, i); e->position = in[i]; e->velocity = in[10 + i]; }
+  for (int i = 0; i < 6; i++) { joint_ptr(o, i)->position = in[20 + i]; joint_ptr(o, i)->velocity = in[26 + i]; }
+  for (int k = 0; k < 4; k++) o->pelvis.vectorNav.orientation[k] = in[32 + k];
+  for (int k = 0; k < 3; k++) { o->pelvis.vectorNav.angularVelocity[k] = in[36 + k]; o->pelvis.vectorNav.linearAcceleration[k] = in[39 + k]; o->pelvis.vectorNav.magneticField[k] = in[42 + k]; }
+}
+void osim_set_radio8(cassie_out_t *o, double v) { o->pelvis.radio.channel[8] = v; }
 
 /* ---------------- accessors for the test harness (ctypes) */
 OModel *osim_model(OSim *c) { return c->m; }

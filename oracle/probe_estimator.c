@@ -62,3 +62,17 @@ void probe_pd(const double *in, const double *task, int ncalls, double *out) {
   for (int i = 0; i < 10; i++) out[i] = ui.torque[i];
   pd_input_free(pd);
 }
+
+/* cassie_core_sim_step probe: in[45] (cassie_out), u[10] commanded torques, radio channel 8 -> out[10] torques of cassie_in_t */
+typedef struct CassieCoreSim cassie_core_sim_t;
+cassie_core_sim_t *cassie_core_sim_alloc(void); void cassie_core_sim_setup(cassie_core_sim_t *); void cassie_core_sim_free(cassie_core_sim_t *);
+void cassie_core_sim_step(cassie_core_sim_t *, const cassie_user_in_t *, const cassie_out_t *, cassie_in_t *);
+void probe_core(const double *in, const double *u, double ch8, double *out) {
+  cassie_out_t o; fill(&o, in); o.pelvis.radio.channel[8] = ch8;
+  cassie_user_in_t ui; memset(&ui, 0, sizeof ui); for (int i = 0; i < 10; i++) ui.torque[i] = u[i];
+  cassie_in_t ci; memset(&ci, 0, sizeof ci);
+  cassie_core_sim_t *c = cassie_core_sim_alloc(); cassie_core_sim_setup(c);
+  cassie_core_sim_step(c, &ui, &o, &ci);
+  for (int i = 0; i < 10; i++) { const cassie_leg_in_t *l = i < 5 ? &ci.leftLeg : &ci.rightLeg; const elmo_in_t *t[5] = {&l->hipRollDrive, &l->hipYawDrive, &l->hipPitchDrive, &l->kneeDrive, &l->footDrive}; out[i] = t[i % 5]->torque; }
+  cassie_core_sim_free(c);
+}

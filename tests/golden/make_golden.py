@@ -4,8 +4,8 @@ Runs ONLY in the build container (needs /root/reference); the GPU box uses the c
 
   *.omodel   oracle model tables: oracle/mjcf_compile.py applied to /root/reference/model/<name>.xml
              (derived numeric tables, not a copy of the XML)
-  agility_vectors.npz   input/output pairs of the reference's closed Agility blocks
-             (pd_input_step, cassie_core_sim_step from src/libagilitycassie.a via oracle/_ref/liboracle_ref.so)
+  agility_vectors.npz   input/output pairs of the reference's closed Agility blocks (pd_input_step incl. taskPd, cassie_core_sim_step,
+             state_output_step from src/libagilitycassie.a via oracle/_ref/liboracle_ref.so; layout: oracle/probe_estimator.c)
 """
 import os
 import sys
@@ -18,7 +18,45 @@ REF = os.environ.get('CASSIE_REFERENCE', '/root/reference')
 MODELS = ['cassie', 'cassie_hfield', 'cassie_tray_box', 'cassie_no_grav']
 
 
+def agility_vectors(n=300, seed=123):
+    """random cassie_out / pd_in_t inputs -> outputs of the REAL closed blocks (src/libagilitycassie.a through oracle/_ref/liboracle_ref.so)"""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    subprocess.check_call(['make', '-s', '-C', os.path.join(REPO, 'oracle'), 'ref', 'REF=' + REF])
+    L = C.CDLL(os.path.join(REPO, 'oracle', '_ref', 'liboracle_ref.so'))
+    dp = C.POINTER(C.c_double)
+    L.probe_est.argtypes = [dp, C.c_int, dp]
+    L.probe_pd.argtypes = [dp, dp, C.c_int, dp]
+    L.probe_core.argtypes = [dp, dp, C.c_double, dp]
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array([-0.3, -0.4, -0.9, -2.9, -2.5] * 2), np.array([0.4, 0.4, 1.4, -0.6, -0.5] * 2)
+    X, T, U, CH, EST, PD, CORE = [], [], [], [], [], [], []
+    for i in range(n):
+        x = np.zeros(45)
+        x[0:10] = rng.uniform(lo, hi) if i % 4 else rng.uniform(-3, 3, 10)
+        x[10:20] = rng.uniform(-8, 8, 10)
+        x[20:26] = [rng.uniform(-0.2, 0.2), rng.uniform(0.8, 2.6), rng.uniform(-2.4, -0.6)] * 2
+        x[26:32] = rng.uniform(-6, 6, 6)
+        q = rng.normal(size=4)
+        x[32:36] = q / np.linalg.norm(q)
+        x[36:39], x[39:42] = rng.uniform(-3, 3, 3), rng.uniform(-12, 12, 3)
+        t = np.zeros(60)
+        if i % 3:
+            t[:] = np.concatenate([np.concatenate([rng.uniform(-30, 30, 6), rng.uniform(-1, 1, 6), rng.uniform(-2, 2, 6), rng.uniform(0, 300, 6), rng.uniform(0, 10, 6)]) for _ in range(2)])
+        u, ch = rng.uniform(-250, 250, 10), (1.0 if i % 7 else 0.0)
+        e, p, c = np.zeros(123), np.zeros(10), np.zeros(10)
+        L.probe_est(x.ctypes.data_as(dp), 1, e.ctypes.data_as(dp))
+        L.probe_pd(x.ctypes.data_as(dp), t.ctypes.data_as(dp), 1, p.ctypes.data_as(dp))
+        L.probe_core(x.ctypes.data_as(dp), u.ctypes.data_as(dp), ch, c.ctypes.data_as(dp))
+        X.append(x); T.append(t); U.append(u); CH.append(ch); EST.append(e[:105]); PD.append(p); CORE.append(c)
+    np.savez_compressed(os.path.join(HERE, 'agility_vectors.npz'), cassie_out=np.array(X), task=np.array(T), u=np.array(U), ch8=np.array(CH),
+                        state_out=np.array(EST), pd_torque=np.array(PD), core_torque=np.array(CORE))
+    print('wrote agility_vectors.npz', n)
+
+
 def main():
+    agility_vectors()
     for name in MODELS:
         m = mc.compile_mjcf(os.path.join(REF, 'model', name + '.xml'))
         mc.write_omodel(m, os.path.join(HERE, name + '.omodel'))

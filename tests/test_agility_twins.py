@@ -158,3 +158,49 @@ def test_archive_kinematics_pin_the_mjcf_compiler(oracle_mod):
             p = xm[pel].T @ (xp[fb] + xm[fb] @ np.array([0.01762, 0.05219, 0]) - xp[pel])
             worst = max(worst, np.abs(p - e[22 + 19 * sd:25 + 19 * sd]).max())
     assert worst < 5e-7, worst
+
+
+def test_twins_against_committed_archive_vectors(oracle_mod, pkg):
+    """tests/golden/agility_vectors.npz holds outputs of the REAL closed blocks on 300 random inputs (tests/golden/make_golden.py); the oracle's
+    twins reproduce them with no archive present -- this is what pins the twins on the GPU box"""
+    import ctypes as C
+    V = np.load(os.path.join(GOLDEN, 'agility_vectors.npz'))
+    L = oracle_mod.load()
+    dp = C.POINTER(C.c_double)
+    L.o_est_foot.argtypes = [C.c_int] + [dp] * 6
+    L.o_pd_input_step.argtypes = [C.c_void_p, C.c_void_p, dp]
+    L.o_core_sim_step.argtypes = [dp, C.c_void_p, dp]
+    L.o_state_output_step.argtypes = [C.c_void_p, C.c_void_p]
+    # build cassie_out_t / pd_in_t images with ctypes mirrors of the bus structs: use the product's mirrors for pd_in_t and a raw
+    # buffer + the oracle's own accessor layout for cassie_out_t (offsets from include/cassie_bus.h via a tiny C helper)
+    L.osim_fill_cassie_out.argtypes = [C.c_void_p, dp]
+    worst = dict(est=0.0, pd=0.0, core=0.0)
+    for x, t, u, ch, est, pdq, core in zip(V['cassie_out'], V['task'], V['u'], V['ch8'], V['state_out'], V['pd_torque'], V['core_torque']):
+        co = (C.c_char * 1336)()
+        xx = np.ascontiguousarray(x)
+        L.osim_fill_cassie_out(co, xx.ctypes.data_as(dp))
+        y = pkg.state_out_t()
+        L.o_state_output_step(co, C.byref(y))
+        got = np.concatenate([[0, 0, 0], field(y, 'pelvis.orientation'), field(y, 'pelvis.rotationalVelocity'), [0, 0, 0], field(y, 'pelvis.translationalAcceleration')])
+        want = est[:16].copy()
+        want[0:3] = 0
+        want[10:13] = 0                                  # pelvis position / translational velocity: stateful, not decoded
+        worst['est'] = max(worst['est'], np.abs(got - want).max())
+        for sd, name in enumerate(('leftFoot', 'rightFoot')):
+            g = np.concatenate([field(y, name + '.position'), field(y, name + '.orientation'), field(y, name + '.footRotationalVelocity'), field(y, name + '.footTranslationalVelocity')])
+            worst['est'] = max(worst['est'], np.abs(g - est[22 + 19 * sd:35 + 19 * sd]).max())
+        pu = pkg.pd_in_t()
+        for sd, leg in enumerate((pu.leftLeg, pu.rightLeg)):
+            r = t[30 * sd:30 * sd + 30]
+            for k in range(6):
+                leg.taskPd.torque[k], leg.taskPd.pTarget[k], leg.taskPd.dTarget[k], leg.taskPd.pGain[k], leg.taskPd.dGain[k] = r[k], r[6 + k], r[12 + k], r[18 + k], r[24 + k]
+        tq = (C.c_double * 10)()
+        L.o_pd_input_step(C.byref(pu), co, tq)
+        worst['pd'] = max(worst['pd'], np.abs(np.array(tq[:]) - pdq).max() / max(1.0, np.abs(pdq).max()))
+        co2 = (C.c_char * 1336)()
+        L.osim_fill_cassie_out(co2, xx.ctypes.data_as(dp))
+        L.osim_set_radio8(co2, C.c_double(float(ch)))
+        uu, out = np.ascontiguousarray(u), (C.c_double * 10)()
+        L.o_core_sim_step(uu.ctypes.data_as(dp), co2, out)
+        worst['core'] = max(worst['core'], np.abs(np.array(out[:]) - core).max())
+    assert worst['est'] < 1e-11 and worst['pd'] < 1e-12 and worst['core'] < 1e-9, worst
