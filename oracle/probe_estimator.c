@@ -76,3 +76,12 @@ void probe_core(const double *in, const double *u, double ch8, double *out) {
   for (int i = 0; i < 10; i++) { const cassie_leg_in_t *l = i < 5 ? &ci.leftLeg : &ci.rightLeg; const elmo_in_t *t[5] = {&l->hipRollDrive, &l->hipYawDrive, &l->hipPitchDrive, &l->kneeDrive, &l->footDrive}; out[i] = t[i % 5]->torque; }
   cassie_core_sim_free(c);
 }
+
+/* as probe_est, plus the drives' measured torques: in[45..54] */
+void probe_est_tq(const double *in, int ncalls, double *out) {
+  cassie_out_t o; state_out_t y; fill(&o, in);
+  for (int i = 0; i < 10; i++) drv(&o, i)->torque = in[45 + i];
+  state_output_t *e = state_output_alloc(); state_output_setup(e);
+  for (int i = 0; i < ncalls; i++) state_output_step(e, &o, &y);
+  flat(&y, out); state_output_free(e);
+}
