@@ -52,6 +52,9 @@ def jittered_qpos(q0, n, seed=0):
     return q
 
 
+REF_TICKS = 250   # control ticks per reference-arm step
+
+
 # ------------------------------------------------------------------------------ CPU arm (oracle)
 def cpu_arm(n_threads, envs_per_thread, ticks, warm_ticks=0):
     """aggregate env-steps/s of the CPU oracle with one thread per core, each owning private sims."""
@@ -89,13 +92,15 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    ept = 16 if args.steps >= 100 else 64           # private sims per thread; enough work that thread start-up does not dominate
-    val, dt, ref = cpu_arm(cores, ept, args.steps, warm_ticks=args.warmup)
+    # one private sim per host thread (the reference's own threading model; more sims per thread only thrash the caches), one bench
+    # "step" = REF_TICKS control ticks of all of them
+    ept, ticks = 1, REF_TICKS * args.steps
+    val, dt, ref = cpu_arm(cores, ept, ticks, warm_ticks=REF_TICKS * min(args.warmup, 4))
     kind = 'port'
-    sample = '%d envs (%d threads x %d private sims) x %d ticks of %s; physics = oracle/cassie_oracle.c (fp64 restatement of MuJoCo 2.1.0 semantics), Agility blocks = %s' % (
-        cores * ept, cores, ept, args.steps, WORKLOAD, 'the reference archive libagilitycassie.a incl. state_output_step' if ref else 'oracle twins')
+    sample = '%d envs (%d threads x %d private sim) x %d ticks (%d per step) of %s; physics = oracle/cassie_oracle.c (fp64 restatement of MuJoCo 2.1.0 semantics), Agility blocks = %s' % (
+        cores * ept, cores, ept, ticks, REF_TICKS, WORKLOAD, 'the reference archive libagilitycassie.a incl. state_output_step' if ref else 'oracle twins')
     line = {'impl': 'reference', 'metric': 'Cassie env-steps/s', 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'ms_per_step': 1e3 * dt / args.steps,   # one step = REF_TICKS ticks of `cores` environments 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'parallelism': 'cpu x%d threads' % cores},
             'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
@@ -335,10 +340,10 @@ def gpu_arm(args, rank, local_rank, world):
     if rank == 0:
         cores = os.cpu_count() or 1
         try:
-            cpu_val, cpu_dt, ref = cpu_arm(cores, 16, 1500, warm_ticks=50)
+            cpu_val, cpu_dt, ref = cpu_arm(cores, 1, 30000, warm_ticks=500)
             cpu = {'value': cpu_val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                   'sample': '%d envs (%d threads x 16 private sims) x 1500 ticks of the same workload (~1 s per core); oracle/cassie_oracle.c fp64 + %s' % (
-                       16 * cores, cores, 'reference Agility archive' if ref else 'Agility twins')}
+                   'sample': '%d envs (%d threads x 1 private sim) x 30000 ticks of the same workload (~1-2 s per core); oracle/cassie_oracle.c fp64 + %s' % (
+                       cores, cores, 'reference Agility archive' if ref else 'Agility twins')}
         except Exception as ex:   # the oracle is a checker; its absence must not void the GPU number
             cpu = {'value': None, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': 'unavailable: %r' % (ex,)}
         ms_step = ms_kernel / args.steps

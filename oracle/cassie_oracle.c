@@ -75,6 +75,7 @@ typedef struct {
   /* ids looked up by name at init (src/cassiemujoco.c:861-866); -1 when the model has no such site */
   int left_foot_body, right_foot_body, left_heel, left_toe, right_heel, right_toe;
   double toe_local[2][3], heel_local[2][3]; /* toe / heel points in the foot body frames (sites, else the foot capsule's end points) */
+  int ncand, cand_ready; short cand[1024][2]; /* geom pairs that pass the static filters (weld / parent-child / contype-conaffinity), in MuJoCo's order */
 } OModel;
 
 typedef struct {
@@ -673,20 +674,27 @@ static void collide_geoms(const OModel *m, OData *d, int g1, int g2) {
   }
 }
 
-static void o_collision(const OModel *m, OData *d) {
+static void o_collision(const OModel *m_, OData *d) {
+  OModel *m = (OModel *)m_;
   d->ncon = 0;
-  /* body pairs in ascending (b1,b2) order == MuJoCo's sorted broadphase output; the AABB sweep itself only
-     prunes pairs that the bounding-sphere / narrow phase would reject anyway */
-  for (int b1 = 0; b1 < m->nbody; b1++) for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
-    int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
-    if (w1 == w2) continue;
-    if (w1 && w2 && (m->body_weldid[m->body_parentid[w1]] == w2 || m->body_weldid[m->body_parentid[w2]] == w1)) continue;
-    for (int g1 = 0; g1 < m->ngeom; g1++) if (m->geom_bodyid[g1] == b1)
-      for (int g2 = 0; g2 < m->ngeom; g2++) if (m->geom_bodyid[g2] == b2) collide_geoms(m, d, g1, g2);
+  /* body pairs in ascending (b1,b2) order == MuJoCo's sorted broadphase output; the AABB sweep itself only prunes pairs that the
+     bounding-sphere / narrow phase would reject anyway.  The pairs that survive the STATIC filters are listed once per model. */
+  if (!m->cand_ready) {
+    m->ncand = 0;
+    for (int b1 = 0; b1 < m->nbody; b1++) for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
+      int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
+      if (w1 == w2) continue;
+      if (w1 && w2 && (m->body_weldid[m->body_parentid[w1]] == w2 || m->body_weldid[m->body_parentid[w2]] == w1)) continue;
+      for (int g1 = 0; g1 < m->ngeom; g1++) if (m->geom_bodyid[g1] == b1)
+        for (int g2 = 0; g2 < m->ngeom; g2++) if (m->geom_bodyid[g2] == b2) {
+          if (!((m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]))) continue;
+          if (m->ncand < 1024) { m->cand[m->ncand][0] = (short)g1; m->cand[m->ncand][1] = (short)g2; m->ncand++; }
+        }
+    }
+    m->cand_ready = 1;
   }
+  for (int i = 0; i < m->ncand; i++) collide_geoms(m, d, m->cand[i][0], m->cand[i][1]);
 }
-
-/* ---------------- constraints (mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint) */
 static int add_row(OData *d, const double *J, int nv, double pos, double margin, int type, int id) {
   if (d->nefc >= MAXEFC) return -1;
   int r = d->nefc++;
