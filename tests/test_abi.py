@@ -73,3 +73,22 @@ def test_env_shard_partitions(pkg):
             for (s0, c0), (s1, _) in zip(spans, spans[1:]):
                 assert s0 + c0 == s1
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """examples/cassietest_b200.c (the reference's cassietest.c verbs) compiles as C against include/cassie_b200.h, links the product library,
+    and -- on a box without a CUDA device -- exits 1 with the no-fallback message instead of computing anything"""
+    import subprocess
+    pkg.build()
+    exe = str(tmp_path / 'cassietest_b200')
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(['gcc', '-std=c11', '-Wall', '-Werror', '-I', os.path.join(REPO, 'include'), os.path.join(REPO, 'examples', 'cassietest_b200.c'),
+                           '-L', libdir, '-lcassie_b200', '-Wl,-rpath,' + libdir, '-o', exe])
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip('a GPU is visible here: the run-time half of this test is for CPU-only boxes')
+    except ImportError:
+        pass
+    r = subprocess.run([exe, os.path.join(REPO, 'cassie-mujoco-sim_b200', 'models', 'cassie.cmodel')], capture_output=True, text=True, cwd=REPO)
+    assert r.returncode == 1 and 'no CUDA device' in r.stderr, (r.returncode, r.stderr)
