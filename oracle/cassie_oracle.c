@@ -1091,7 +1091,8 @@ void o_core_sim_step(const double u[10], const cassie_out_t *o, double out[10]) 
  *    encoders for shin and tarsus; the foot joint encoder is not used).  position = the point (0.01762, 0.05219, 0) of the foot frame in
  *    the pelvis frame; orientation = foot frame turned by a fixed rotation (40 degrees), as a quaternion (mat2quat branches as MuJoCo's);
  *    footRotationalVelocity / footTranslationalVelocity = Jacobian times the measured rates, expressed in THAT FOOT FRAME.
- * Not decoded (left zero): pelvis.position / translationalVelocity / externalForce / externalMoment, toe / heel forces, terrain (stateful). */
+ *  - toeForce = heelForce: o_est_leg_force below (spring torques through the closed four-bar; single-precision agreement only).
+ * Not decoded (left zero): pelvis.position / translationalVelocity / externalForce / externalMoment, terrain (stateful filters). */
 static void est_mat2quat(double *q, const double *R) { /* R row-major */
   double t = R[0] + R[4] + R[8];
   if (t > 0) { double s = sqrt(t + 1) * 2; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
@@ -1153,6 +1154,57 @@ static void o_task_pd_leg(int side, const pd_task_in_t *t, const double ang[7], 
     tq[j] += axis[i][0] * w[0] + axis[i][1] * w[1] + axis[i][2] * w[2] + cr[0] * w[3] + cr[1] * w[4] + cr[2] * w[5];
   }
 }
+/* toe / heel force of one leg (state_output_step, closed; decoded by fitting the archive, oracle/probe_fit_forces.py): the two leaf springs'
+ * torques mapped to a force at the foot point through the closed four-bar.  Both outputs are the same vector:
+ *   toeForce = heelForce = Rz(yaw)' R(q) [f_x, 0, f_z],   (f_x, f_z) = -1/2 J_c^-T [1500 shin; 1250 (H - 2.586e-6)]
+ * H = heel-spring angle that closes the achilles rod: |A - B(knee, shin, tarsus, H)| = 0.5012 with A = (0, 0, 0.045) on the hip-pitch link, the
+ * heel spring mounted on the tarsus as in the MJCF (model/cassie.xml:132) and the rod end at (0.11877, -0.01, 0) of the heel-spring frame;
+ * J_c = [p_s - p_t b/a, p_t / a] (pelvis x and z rows), p_s / p_t the serial-chain partials of the foot point w.r.t. shin / tarsus and
+ * a = dH/dtarsus, b = dH/dshin from the closure; q the IMU quaternion, yaw its ZYX heading.  The archive evaluates this in single precision:
+ * agreement is 4e-3 N on forces of 150 N, not the 1e-12 of the kinematic outputs. */
+void o_est_leg_force(int side, const double ang[7], const double quat[4], double force[3]) {
+  const double sg = side ? -1.0 : 1.0, kn = ang[3], sh = ang[4], ta = ang[5];
+  /* planar chain in the hip-pitch frame (z = the common joint axis) */
+  const double A[3] = {0, 0, 0.045 * sg}, k0[3] = {0.12, 0, 0.0045 * sg}, hsp[3] = {-0.01269, -0.03059, 0.00092 * sg}, Bl[3] = {0.11877, -0.01, 0};
+  double hx[3] = {-0.91211, 0.40829, 0.036948 * sg}, hy[3] = {-0.40992, -0.90952, -0.068841 * sg}, hz[3];
+  { double n = sqrt(dot3(hx, hx)); for (int k = 0; k < 3; k++) hx[k] /= n; double d = dot3(hx, hy); for (int k = 0; k < 3; k++) hy[k] -= d * hx[k];
+    n = sqrt(dot3(hy, hy)); for (int k = 0; k < 3; k++) hy[k] /= n; cross(hz, hx, hy); }      /* xyaxes -> frame, as the MJCF compiler does */
+  const double c1 = cos(kn), s1 = sin(kn), c2 = cos(kn + sh), s2 = sin(kn + sh), c3 = cos(kn + sh + ta), s3 = sin(kn + sh + ta);
+  const double s0[3] = {k0[0] + c1 * 0.06068 - s1 * 0.04741, k0[1] + s1 * 0.06068 + c1 * 0.04741, k0[2]};
+  const double t0[3] = {s0[0] + c2 * 0.43476 - s2 * 0.02, s0[1] + s2 * 0.43476 + c2 * 0.02, s0[2]};
+  const double R3[9] = {c3, -s3, 0, s3, c3, 0, 0, 0, 1};
+  double hs0[3], v[3], HF[9] = {hx[0], hy[0], hz[0], hx[1], hy[1], hz[1], hx[2], hy[2], hz[2]}, RH[9], axh[3];
+  mulMatVec3(v, R3, hsp); for (int k = 0; k < 3; k++) hs0[k] = t0[k] + v[k];
+  mulMatMat3(RH, R3, HF); axh[0] = RH[2]; axh[1] = RH[5]; axh[2] = RH[8];                      /* heel-spring joint axis */
+  double H = 0, B[3], dB[3], gd = 1;
+  for (int it = 0; it < 8; it++) {                                                              /* Newton on g(H) = |B - A|^2 - L^2 */
+    const double ch = cos(H), shh = sin(H), Zl[3] = {ch * Bl[0] - shh * Bl[1], shh * Bl[0] + ch * Bl[1], Bl[2]};
+    mulMatVec3(v, RH, Zl); for (int k = 0; k < 3; k++) { B[k] = hs0[k] + v[k]; dB[k] = B[k] - A[k]; }
+    double r[3] = {B[0] - hs0[0], B[1] - hs0[1], B[2] - hs0[2]}, dBd[3]; cross(dBd, axh, r);
+    const double g = dot3(dB, dB) - 0.5012 * 0.5012; gd = 2 * dot3(dB, dBd);
+    H -= g / gd;
+  }
+  { const double ch = cos(H), shh = sin(H), Zl[3] = {ch * Bl[0] - shh * Bl[1], shh * Bl[0] + ch * Bl[1], Bl[2]};
+    mulMatVec3(v, RH, Zl); for (int k = 0; k < 3; k++) { B[k] = hs0[k] + v[k]; dB[k] = B[k] - A[k]; }
+    double r[3] = {B[0] - hs0[0], B[1] - hs0[1], B[2] - hs0[2]}, dBd[3]; cross(dBd, axh, r); gd = 2 * dot3(dB, dBd); }
+  const double ez[3] = {0, 0, 1}; double rs[3] = {B[0] - s0[0], B[1] - s0[1], B[2] - s0[2]}, rt[3] = {B[0] - t0[0], B[1] - t0[1], B[2] - t0[2]}, dBs[3], dBt[3];
+  cross(dBs, ez, rs); cross(dBt, ez, rt);
+  const double a = -2 * dot3(dB, dBt) / gd, b = -2 * dot3(dB, dBs) / gd;
+  /* foot-point partials in the pelvis frame from the serial chain */
+  double pos[3], Rf[9], axis[7][3], anchor[7][3], d4[3], d5[3], ps[3], pt[3];
+  o_leg_chain(side, ang, pos, Rf, axis, anchor);
+  for (int k = 0; k < 3; k++) { d4[k] = pos[k] - anchor[4][k]; d5[k] = pos[k] - anchor[5][k]; }
+  cross(ps, axis[4], d4); cross(pt, axis[5], d5);
+  /* J_c' f = tau with J_c = [ps - pt b/a, pt/a] (x and z rows) */
+  const double j00 = ps[0] - pt[0] * b / a, j10 = ps[2] - pt[2] * b / a, j01 = pt[0] / a, j11 = pt[2] / a;
+  const double t0_ = 1500.0 * sh, t1_ = 1250.0 * (H - 2.586e-6), det = j00 * j11 - j10 * j01;
+  const double fx = -0.5 * (t0_ * j11 - t1_ * j10) / det, fz = -0.5 * (-t0_ * j01 + t1_ * j00) / det;
+  /* heading-free world frame */
+  double R[9]; quat2Mat(R, quat);
+  const double yaw = atan2(2 * (quat[0] * quat[3] + quat[1] * quat[2]), 1 - 2 * (quat[2] * quat[2] + quat[3] * quat[3])), cy = cos(yaw), sy = sin(yaw);
+  const double wv[3] = {R[0] * fx + R[2] * fz, R[3] * fx + R[5] * fz, R[6] * fx + R[8] * fz};
+  force[0] = cy * wv[0] + sy * wv[1]; force[1] = -sy * wv[0] + cy * wv[1]; force[2] = wv[2];
+}
 void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
   cassie_out_t out = *o;
   memset(y, 0, sizeof *y);
@@ -1171,6 +1223,7 @@ void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
     ang[4] = y->joint.position[3 * s]; rate[4] = y->joint.velocity[3 * s]; ang[5] = y->joint.position[3 * s + 1]; rate[5] = y->joint.velocity[3 * s + 1];
     ang[6] = y->motor.position[5 * s + 4]; rate[6] = y->motor.velocity[5 * s + 4];
     o_est_foot(s, ang, rate, f->position, f->orientation, f->footRotationalVelocity, f->footTranslationalVelocity);
+    o_est_leg_force(s, ang, q, f->toeForce); copyv(f->heelForce, f->toeForce, 3);
   }
   copyv(y->radio.channel, out.pelvis.radio.channel, 16); y->radio.signalGood = true; y->battery.stateOfCharge = out.pelvis.battery.stateOfCharge;
 }

@@ -18,7 +18,7 @@ REF = os.environ.get('CASSIE_REFERENCE', '/root/reference')
 MODELS = ['cassie', 'cassie_hfield', 'cassie_tray_box', 'cassie_no_grav']
 
 
-def agility_vectors(n=300, seed=123):
+def agility_vectors(n=400, seed=123):
     """random cassie_out / pd_in_t inputs -> outputs of the REAL closed blocks (src/libagilitycassie.a through oracle/_ref/liboracle_ref.so)"""
     import ctypes as C
     import subprocess
@@ -37,6 +37,11 @@ def agility_vectors(n=300, seed=123):
         x[0:10] = rng.uniform(lo, hi) if i % 4 else rng.uniform(-3, 3, 10)
         x[10:20] = rng.uniform(-8, 8, 10)
         x[20:26] = [rng.uniform(-0.2, 0.2), rng.uniform(0.8, 2.6), rng.uniform(-2.4, -0.6)] * 2
+        if i % 2:   # every other sample inside the leg's working range (small spring deflections): what the toe / heel force model is pinned on
+            x[0:10] = rng.uniform(np.array([-0.2, -0.3, -0.6, -2.2, -2.2] * 2), np.array([0.3, 0.3, 1.0, -0.9, -0.8] * 2))
+            for sd in range(2):
+                x[20 + 3 * sd] = rng.uniform(-0.05, 0.05)
+                x[21 + 3 * sd] = np.deg2rad(13) - x[5 * sd + 3] - x[20 + 3 * sd] + rng.uniform(-0.05, 0.05)
         x[26:32] = rng.uniform(-6, 6, 6)
         q = rng.normal(size=4)
         x[32:36] = q / np.linalg.norm(q)

@@ -204,3 +204,45 @@ def test_twins_against_committed_archive_vectors(oracle_mod, pkg):
         L.o_core_sim_step(uu.ctypes.data_as(dp), co2, out)
         worst['core'] = max(worst['core'], np.abs(np.array(out[:]) - core).max())
     assert worst['est'] < 1e-11 and worst['pd'] < 1e-12 and worst['core'] < 1e-9, worst
+
+
+def test_toe_heel_force_twin(oracle_mod, pkg):
+    """toeForce / heelForce: the decoded spring-force model against the real estimator.  The archive evaluates it in single precision, so the
+    bar is its own rounding noise (a few mN on forces of ~100 N), not 1e-12: |twin - archive| <= 2e-2 N + 2e-4 |F| in closed loop and on the
+    committed random vectors whose deflections are physically plausible"""
+    import ctypes as C
+    import oracle as O
+    V = np.load(os.path.join(GOLDEN, 'agility_vectors.npz'))
+    L = oracle_mod.load()
+    dp = C.POINTER(C.c_double)
+    L.o_est_leg_force.argtypes = [C.c_int, dp, dp, dp]
+    checked = 0
+    for x, est in zip(V['cassie_out'], V['state_out']):
+        for sd in range(2):
+            m, sh, ta = x[5 * sd:5 * sd + 5], x[20 + 3 * sd], x[21 + 3 * sd]
+            if abs(sh) > 0.1 or abs(m[3] + sh + ta - np.deg2rad(13)) > 0.1 or not (-2.5 < m[3] < -0.7) or abs(m[0]) > 0.5 or abs(m[1]) > 0.5 or abs(m[2]) > 1.3:
+                continue                                    # outside the leg's working range (the four-bar flips, the x-z solve degenerates)
+            ang, q, f = (C.c_double * 7)(m[0], m[1], m[2], m[3], sh, ta, m[4]), (C.c_double * 4)(*x[32:36]), (C.c_double * 3)()
+            L.o_est_leg_force(sd, ang, q, f)
+            want = est[35 + 19 * sd:38 + 19 * sd]
+            assert np.abs(np.array(f[:]) - want).max() <= 2e-2 + 2e-4 * np.abs(want).max(), (sd, f[:], want)
+            assert np.array_equal(want, est[38 + 19 * sd:41 + 19 * sd])        # the archive reports the same vector for toe and heel
+            checked += 1
+    if os.path.exists(O.lib_path(ref=True)):   # closed loop against the live archive
+        o = O.OracleSim(os.path.join(GOLDEN, 'cassie.omodel'), ref=True)
+        Lr = O.load(ref=True)
+        Lr.o_state_output_step.argtypes = [C.c_void_p, C.c_void_p]
+        y, y2, co = pkg.state_out_t(), pkg.state_out_t(), (C.c_char * 1336)()
+        u = O.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+        big = 0.0
+        for k in range(800):
+            o.step_pd(u, y, co)
+            Lr.o_state_output_step(C.byref(co), C.byref(y2))
+            for name in ('leftFoot', 'rightFoot'):
+                for fld in ('toeForce', 'heelForce'):
+                    a, b = field(y, name + '.' + fld), field(y2, name + '.' + fld)
+                    assert np.abs(a - b).max() <= 2e-2 + 2e-4 * np.abs(a).max(), (k, name, fld, a, b)
+                    big = max(big, np.abs(a).max())
+        assert big > 30                                       # standing: the springs carry the weight
+        checked += 1
+    assert checked > 0
