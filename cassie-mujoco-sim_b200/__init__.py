@@ -154,6 +154,8 @@ def lib():
     for n in ('cassie_batch_enable_aux',):
         getattr(L, n).argtypes = [vp, ci]
         getattr(L, n).restype = ci
+    L.cassie_batch_enable_estimator_forces.argtypes = [vp, ci]
+    L.cassie_batch_enable_estimator_forces.restype = ci
     L.cassie_batch_set_task_pd.argtypes = [vp, cd]
     L.cassie_batch_set_task_pd.restype = ci
     L.cassie_batch_get_aux.argtypes = [vp, cd]

@@ -16,6 +16,7 @@
 
 #include "../../include/cassie_b200.h"
 #include "devbuild.h"
+#include "estimator_host.h"
 #include "step_core.inl"
 
 namespace cassie {
@@ -184,6 +185,7 @@ __global__ void fill_rows_kernel(T *__restrict__ dst, const T *__restrict__ row,
 // ------------------------------------------------------------------ host side
 struct BatchBase {
   virtual ~BatchBase() {}
+  bool est_forces = false;   // fill toeForce / heelForce of state_out_t on the host (cassie_batch_enable_estimator_forces)
   HostModel hm; int n = 0, device = 0, precision = 0, wpb = 4; cudaStream_t stream = nullptr; bool own_stream = false; long launches = 0; bool debug = false;
   virtual bool init() = 0;
   virtual bool reset(const unsigned char *mask) = 0;
@@ -408,6 +410,12 @@ template <typename real> struct Batch : BatchBase {
         state_foot_out_t *f = sd ? &y->rightFoot : &y->leftFoot; const real *fo = o + OB_FOOT + 13 * sd;
         for (int i = 0; i < 3; i++) { f->position[i] = fo[i]; f->footRotationalVelocity[i] = fo[7 + i]; f->footTranslationalVelocity[i] = fo[10 + i]; }
         for (int i = 0; i < 4; i++) f->orientation[i] = fo[3 + i];
+        if (est_forces) {   // toe / heel force: host-side part of the decoded estimator (opt-in for batches: it costs host time per environment)
+          const double ang[7] = {o[OB_MPOS + 5 * sd], o[OB_MPOS + 5 * sd + 1], o[OB_MPOS + 5 * sd + 2], o[OB_MPOS + 5 * sd + 3], o[OB_JPOS + 3 * sd], o[OB_JPOS + 3 * sd + 1], o[OB_MPOS + 5 * sd + 4]};
+          const double qd[4] = {o[OB_QUAT], o[OB_QUAT + 1], o[OB_QUAT + 2], o[OB_QUAT + 3]};
+          estimator_leg_force(sd, ang, qd, f->toeForce);
+          for (int i = 0; i < 3; i++) f->heelForce[i] = f->toeForce[i];
+        }
       }
       for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
       y->radio.signalGood = true; y->battery.stateOfCharge = 1;
@@ -593,6 +601,8 @@ int cassie_batch_get_dof_damping(cassie_batch_t *b, double *damp) { return b->im
 int cassie_batch_get_geom_friction(cassie_batch_t *b, double *fric) { return b->impl->get_model_rows("geom_friction", fric, 3 * b->impl->hm.ngeom) ? 0 : -1; }
 int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int reset_state) { return b->impl->set_const(mask, reset_state != 0) ? 0 : -1; }
 int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows) { return b->impl->set_task_pd(rows) ? 0 : -1; }
+int cassie_batch_enable_estimator_forces(cassie_batch_t *b, int on) { b->impl->est_forces = on != 0; return 0; }
+void cassie_b200_estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) { estimator_leg_force(side, ang, quat, force); }
 int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
 int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
 int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }
@@ -647,6 +657,7 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   if (!b) return nullptr;
   cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b;
   b->impl->enable_aux(true); b->impl->step(0, 1);   // a single environment always carries the derived-quantity row; populate it like the sensordata
+  b->impl->est_forces = true;                       // ... and the host-side toe / heel forces of the estimator
   sim_pull(c);
   { const HostModel &hm = b->impl->hm; c->m_mass = hm.body_mass; c->m_ipos = hm.body_ipos; c->m_damp = hm.dof_damping; c->m_fric = hm.geom_friction;
     c->m_mass_dev = c->m_mass; c->m_ipos_dev = c->m_ipos; c->m_damp_dev = c->m_damp; c->m_fric_dev = c->m_fric; }

@@ -130,8 +130,9 @@ void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask);
  * Replaces n_env calls of src/cassiemujoco.c:1147-1157.  Synchronous.  state_out carries the stateless part of the reference's
  * state_output_step, decoded from the closed archive and checked equal to it to 1e-11: motor / joint position + velocity + torque,
  * pelvis.orientation (+-q, mat2quat's sign), rotationalVelocity, translationalAcceleration, both feet's position / orientation (pelvis frame) and
- * footRotationalVelocity / footTranslationalVelocity (foot frame), radio, battery.  The stateful outputs (pelvis.position,
- * translationalVelocity, externalForce / externalMoment, toe / heel forces, terrain) are zero (scope). */
+ * footRotationalVelocity / footTranslationalVelocity (foot frame), radio, battery; toeForce / heelForce when enabled (see
+ * cassie_batch_enable_estimator_forces).  The stateful outputs (pelvis.position, translationalVelocity, externalForce / externalMoment,
+ * terrain) are zero (scope). */
 void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_out_t *state_out);
 
 /* throughput path: compact rows.  pd: host [n_env][CASSIE_PD_WIDTH] doubles, copied to the device (and converted to the batch
@@ -179,6 +180,12 @@ int cassie_batch_get_body_ipos(cassie_batch_t *b, double *ipos);
 int cassie_batch_get_dof_damping(cassie_batch_t *b, double *damp);
 int cassie_batch_get_geom_friction(cassie_batch_t *b, double *fric);
 int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int reset_state);
+/* toeForce / heelForce of state_out_t (the estimator's spring-force model, decoded; single-precision agreement with the archive): computed
+ * on the host while cassie_sim_step_pd_batch unpacks its rows; off by default for batches (host time per environment), always on for a
+ * cassie_sim_t.  The pure function behind it is exported for callers that keep observations on the device:
+ * ang = hipRoll, hipYaw, hipPitch, knee (motor positions), shin, tarsus (joint encoders), foot (motor position); quat = IMU quaternion. */
+int cassie_batch_enable_estimator_forces(cassie_batch_t *b, int on);
+void cassie_b200_estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]);
 /* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
 void cassie_batch_forward(cassie_batch_t *b);
 /* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */

@@ -72,3 +72,29 @@ def test_observation_row_matches_estimator_twin(oracle_mod, pkg, fp32):
             # the twin applied to the row's OWN measured angles and rates
             row_vs_twin(oracle_mod, row, 2e-5 if fp32 else 1e-12)
     assert y.pelvis.orientation[0] > 0 and o.arr('sensordata')[16] < 0
+
+
+def test_host_side_leg_force_function(oracle_mod, pkg):
+    """the product's host-side toe / heel force (csrc/estimator_host.h, exported as a pure C function: no GPU needed) against the oracle's twin
+    (same model, written independently: <= 1e-9 relative) and against the committed outputs of the real archive (its single-precision noise)"""
+    L, O = pkg.lib(), oracle_mod.load()
+    dp = C.POINTER(C.c_double)
+    L.cassie_b200_estimator_leg_force.argtypes = [C.c_int, dp, dp, dp]
+    L.cassie_b200_estimator_leg_force.restype = None
+    O.o_est_leg_force.argtypes = [C.c_int, dp, dp, dp]
+    V = np.load(os.path.join(GOLDEN, 'agility_vectors.npz'))
+    n = 0
+    for x, est in zip(V['cassie_out'], V['state_out']):
+        for sd in range(2):
+            m, sh, ta = x[5 * sd:5 * sd + 5], x[20 + 3 * sd], x[21 + 3 * sd]
+            if abs(sh) > 0.1 or abs(m[3] + sh + ta - np.deg2rad(13)) > 0.1 or not (-2.5 < m[3] < -0.7) or abs(m[0]) > 0.5 or abs(m[1]) > 0.5 or abs(m[2]) > 1.3:
+                continue
+            ang, q = (C.c_double * 7)(m[0], m[1], m[2], m[3], sh, ta, m[4]), (C.c_double * 4)(*x[32:36])
+            f, g = (C.c_double * 3)(), (C.c_double * 3)()
+            L.cassie_b200_estimator_leg_force(sd, ang, q, f)
+            O.o_est_leg_force(sd, ang, q, g)
+            f, g, want = np.array(f[:]), np.array(g[:]), est[35 + 19 * sd:38 + 19 * sd]
+            assert np.abs(f - g).max() <= 1e-9 * max(1.0, np.abs(g).max()), (f, g)
+            assert np.abs(f - want).max() <= 2e-2 + 2e-4 * np.abs(want).max(), (f, want)
+            n += 1
+    assert n > 300

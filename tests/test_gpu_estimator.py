@@ -40,6 +40,12 @@ def test_state_out_matches_real_estimator(P, oracle_mod):
     for f, w in worst.items():
         assert w < 1e-8, (f, w)
     assert abs(yc.leftFoot.position[2] + 0.9) < 0.2 and yc.pelvis.translationalAcceleration[2] != 0
+    # toe / heel forces (host-side part, always on for a cassie_sim_t): the archive's single-precision noise is the bar
+    for name in ('leftFoot', 'rightFoot'):
+        for fld in ('toeForce', 'heelForce'):
+            a, b = field(y, name + '.' + fld), field(yc, name + '.' + fld)
+            assert np.abs(a - b).max() <= 2e-2 + 2e-4 * np.abs(a).max(), (name, fld, a, b)
+    assert abs(yc.leftFoot.toeForce[2]) > 10
 
 
 def test_batch_rows_and_aos(P, oracle_mod):
@@ -52,6 +58,10 @@ def test_batch_rows_and_aos(P, oracle_mod):
     rows = b.obs()
     for e in (0, n - 1):
         row_vs_state_out(rows[e], ys[e], 1e-12)
+    assert ys[0].leftFoot.toeForce[2] == 0                      # batches: off by default
+    P.lib().cassie_batch_enable_estimator_forces(b.h, 1)
+    ys = b.step_pd(pin)
+    assert abs(ys[0].leftFoot.toeForce[2]) > 10 and ys[0].leftFoot.toeForce[2] == ys[0].leftFoot.heelForce[2]
     b32 = P.CassieBatch(n, precision=P.FP32)
     b32.set_pd(P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
     b32.step(300)
