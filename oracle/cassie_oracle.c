@@ -104,6 +104,9 @@ typedef struct {
       qfrc_constraint[MAXV], cacc[MAXB][6], subtree_linvel[MAXB][3], subtree_angmom[MAXB][3];
   double sensordata[40];
   int solver_iter, unsupported_pairs, dropped_contacts;
+  int cap_con, cap_rows; /* optional: the product's capacities (12 contacts, 48 rows; 0 = MuJoCo-like, unlimited up to MAXCON / MAXEFC), so that overflow
+                            situations can be compared too.  Contacts beyond the cap are dropped in contact order; limit rows beyond the row cap
+                            are dropped; the first contact whose rows do not fit ends the contact rows. */
 } OData;
 
 /* ------------------------------------------------------------------ small vector math */
@@ -665,7 +668,7 @@ static void collide_geoms(const OModel *m, OData *d, int g1, int g2) {
   }
   for (int i = 0; i < num; i++) {
     if (con[i].dist >= margin) continue; /* only penetrating (dist < margin) contacts are kept */
-    if (d->ncon >= MAXCON) { d->dropped_contacts++; continue; }
+    if (d->ncon >= MAXCON || (d->cap_con && d->ncon >= d->cap_con)) { d->dropped_contacts++; continue; }
     OContact *c = &d->contact[d->ncon++];
     *c = con[i]; c->geom1 = g1; c->geom2 = g2; c->dim = dim; c->includemargin = margin - gap;
     c->friction[0] = c->friction[1] = fr[0]; c->friction[2] = fr[1]; c->friction[3] = c->friction[4] = fr[2];
@@ -732,12 +735,13 @@ static void o_makeConstraint(const OModel *m, OData *d) {
     double value = d->qpos[m->jnt_qposadr[j]], margin = m->jnt_margin[j];
     for (int side = -1; side <= 1; side += 2) {
       double dist = side * (m->jnt_range[j][(side + 1) / 2] - value);
-      if (dist < margin) { zero(J[0], nv); J[0][m->jnt_dofadr[j]] = -(double)side; add_row(d, J[0], nv, dist, margin, C_LIMIT, j); d->nl++; }
+      if (dist < margin && !(d->cap_rows && d->nefc >= d->cap_rows)) { zero(J[0], nv); J[0][m->jnt_dofadr[j]] = -(double)side; add_row(d, J[0], nv, dist, margin, C_LIMIT, j); d->nl++; }
     }
   }
   /* contacts */
   for (int c = 0; c < d->ncon; c++) {
     OContact *con = &d->contact[c]; int b1 = m->geom_bodyid[con->geom1], b2 = m->geom_bodyid[con->geom2];
+    if (d->cap_rows && d->nefc + (con->dim > 1 ? 2 * (con->dim - 1) : 1) > d->cap_rows) { d->dropped_contacts += d->ncon - c; d->ncon = c; break; }
     con->efc_address = d->nefc;
     o_jac(m, d, jp1, NULL, con->pos, b1); o_jac(m, d, jp2, NULL, con->pos, b2);
     int nr = con->dim > 1 ? 3 : 1;
@@ -1510,6 +1514,7 @@ double *osim_joint_filter_y(OSim *c) { return &c->joint_filter_y[0][0]; }
 double *osim_torque_delay(OSim *c) { return &c->torque_delay[0][0]; }
 float *osim_hfield_data(OSim *c) { return c->m->hfield_data; }
 void osim_forward(OSim *c) { o_forward(c->m, c->d); }
+void osim_set_caps(OSim *c, int max_contacts, int max_rows) { c->d->cap_con = max_contacts; c->d->cap_rows = max_rows; }
 void osim_mj_step(OSim *c) { o_step(c->m, c->d); }
 #define ARR(name, ptr, cnt) if (!strcmp(key, name)) { *n = (cnt); return (double *)(ptr); }
 double *osim_array(OSim *c, const char *key, int *n) {

@@ -131,6 +131,11 @@ class OracleSim:
     def forward(self):
         self.L.osim_forward(self.h)
 
+    def set_caps(self, max_contacts=12, max_rows=48):
+        """apply the product's capacity limits so that overflow situations can be compared; (0, 0) = unlimited."""
+        self.L.osim_set_caps.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.L.osim_set_caps(self.h, max_contacts, max_rows)
+
     def mj_step(self):
         self.L.osim_mj_step(self.h)
 

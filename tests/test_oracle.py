@@ -152,3 +152,17 @@ def test_golden_trajectory(oracle_mod, name):
             i = ticks.index(k)
             assert np.abs(o.arr('qpos') - g['qpos'][i]).max() < 1e-7, k
             assert np.abs(o.arr('qvel') - g['qvel'][i]).max() < 1e-5, k
+
+
+def test_capacity_option_of_the_checker(oracle_mod):
+    """the oracle can be given the product's capacity limits (12 contacts / 48 rows in the product; tiny ones here) so that overflow situations stay
+    comparable: contacts beyond the cap are dropped in contact order and counted, the row count never exceeds the cap"""
+    o = oracle_mod.OracleSim(os.path.join(GOLDEN, 'cassie.omodel'))
+    o.set_caps(2, 20)
+    u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    most = 0
+    for _ in range(600):
+        o.step_pd(u)
+        assert o.get_int('ncon') <= 2 and o.get_int('nefc') <= 20
+        most = max(most, o.get_int('ncon'))
+    assert most == 2 and o.get_int('dropped_contacts') > 0 and np.isfinite(o.arr('qpos')).all()
