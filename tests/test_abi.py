@@ -92,3 +92,34 @@ def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(pkg,
         pass
     r = subprocess.run([exe, os.path.join(REPO, 'cassie-mujoco-sim_b200', 'models', 'cassie.cmodel')], capture_output=True, text=True, cwd=REPO)
     assert r.returncode == 1 and 'no CUDA device' in r.stderr, (r.returncode, r.stderr)
+
+
+def test_bus_struct_offsets_equal_the_reference_headers(tmp_path):
+    """field offsets of every bus struct: include/cassie_bus.h against the reference's own headers, both compiled by gcc (two programs, same probes)"""
+    import subprocess
+    if not have_reference():
+        pytest.skip('reference checkout not present')
+    probes = r'''
+#include <stdio.h>
+#include <stddef.h>
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("sizes %zu %zu %zu %zu %zu\n", sizeof(pd_in_t), sizeof(state_out_t), sizeof(cassie_out_t), sizeof(cassie_in_t), sizeof(cassie_user_in_t));
+  P(pd_in_t, leftLeg.taskPd.pGain); P(pd_in_t, leftLeg.motorPd.torque); P(pd_in_t, rightLeg.motorPd.dGain); P(pd_in_t, telemetry);
+  P(state_out_t, pelvis.orientation); P(state_out_t, pelvis.translationalAcceleration); P(state_out_t, leftFoot.toeForce); P(state_out_t, rightFoot.position);
+  P(state_out_t, terrain.slope); P(state_out_t, motor.torque); P(state_out_t, joint.velocity); P(state_out_t, radio.channel); P(state_out_t, battery.stateOfCharge);
+  P(cassie_out_t, pelvis.vectorNav.orientation); P(cassie_out_t, pelvis.radio.channel); P(cassie_out_t, leftLeg.kneeDrive.position); P(cassie_out_t, rightLeg.footDrive.torque);
+  P(cassie_out_t, leftLeg.tarsusJoint.position); P(cassie_out_t, rightLeg.footJoint.velocity); P(cassie_out_t, isCalibrated);
+  P(cassie_in_t, leftLeg.hipPitchDrive.torque); P(cassie_in_t, rightLeg.footDrive.torque); P(cassie_user_in_t, torque); P(cassie_user_in_t, telemetry);
+  return 0;
+}
+'''
+    outs = []
+    for tag, hdrs, inc in (('mine', ['cassie_bus.h'], os.path.join(REPO, 'include')),
+                           ('ref', ['pd_in_t.h', 'state_out_t.h', 'cassie_out_t.h', 'cassie_in_t.h', 'cassie_user_in_t.h'], os.path.join(REFERENCE, 'include'))):
+        src = tmp_path / (tag + '.c')
+        src.write_text('#include <stdbool.h>\n' + ''.join('#include "%s"\n' % h for h in hdrs) + probes)
+        exe = str(tmp_path / tag)
+        subprocess.check_call(['gcc', '-std=c11', '-I', inc, str(src), '-o', exe])
+        outs.append(subprocess.check_output([exe], text=True))
+    assert outs[0] == outs[1] and 'sizes 952 992 1336' in outs[0], outs
