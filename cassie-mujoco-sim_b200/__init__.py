@@ -156,6 +156,10 @@ def lib():
         getattr(L, n).restype = ci
     L.cassie_batch_enable_estimator_forces.argtypes = [vp, ci]
     L.cassie_batch_enable_estimator_forces.restype = ci
+    L.cassie_batch_enable_estimator_filter.argtypes = [vp, ci]
+    L.cassie_batch_enable_estimator_filter.restype = ci
+    L.cassie_batch_reset_estimator.argtypes = [vp, C.c_void_p]
+    L.cassie_batch_reset_estimator.restype = ci
     L.cassie_batch_set_task_pd.argtypes = [vp, cd]
     L.cassie_batch_set_task_pd.restype = ci
     L.cassie_batch_get_aux.argtypes = [vp, cd]
@@ -315,6 +319,16 @@ class CassieBatch:
 
     def obs(self):
         return self._get(self.L.cassie_batch_get_obs, OBS_WIDTH)
+
+    # ---- the estimator's host-side part for step_pd(): toe / heel forces, and the filters behind pelvis.position / translationalVelocity /
+    # externalForce and terrain.height (one filter per environment, advanced once per step_pd call as the reference's 2 kHz estimator is)
+    def enable_estimator(self, forces=True, filters=True):
+        self.L.cassie_batch_enable_estimator_forces(self.h, 1 if (forces or filters) else 0)
+        self.L.cassie_batch_enable_estimator_filter(self.h, 1 if filters else 0)
+
+    def reset_estimator(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.L.cassie_batch_reset_estimator(self.h, None if m is None else m.ctypes.data)
 
     # ---- derived quantities (reference: the read-only queries of example/cassiemujoco.py:214-306, 815-819), one row per environment
     def enable_aux(self, on=True):

@@ -186,6 +186,9 @@ __global__ void fill_rows_kernel(T *__restrict__ dst, const T *__restrict__ row,
 struct BatchBase {
   virtual ~BatchBase() {}
   bool est_forces = false;   // fill toeForce / heelForce of state_out_t on the host (cassie_batch_enable_estimator_forces)
+  bool est_filter = false;   // run the estimator's filters on the host, one per environment (cassie_batch_enable_estimator_filter; needs est_forces)
+  std::vector<cassie::EstimatorFilter> est_state;
+  void reset_estimator(const unsigned char *mask) { for (size_t e = 0; e < est_state.size(); e++) if (!mask || mask[e]) est_state[e].reset(); }
   HostModel hm; int n = 0, device = 0, precision = 0, wpb = 4; cudaStream_t stream = nullptr; bool own_stream = false; long launches = 0; bool debug = false;
   virtual bool init() = 0;
   virtual bool reset(const unsigned char *mask) = 0;
@@ -398,6 +401,7 @@ template <typename real> struct Batch : BatchBase {
     if (!state_out) return sync();
     CUDA_OK(cudaMemcpyAsync(pin_obs, A.obs, sizeof(real) * n * OBS_W, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+    if (est_filter && est_state.size() != (size_t)n) est_state.assign((size_t)n, cassie::EstimatorFilter());
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
     for (int e = 0; e < n; e++) {
       const real *o = pin_obs + (size_t)e * OBS_W; state_out_t *y = state_out + e;
@@ -416,6 +420,12 @@ template <typename real> struct Batch : BatchBase {
           estimator_leg_force(sd, ang, qd, f->toeForce);
           for (int i = 0; i < 3; i++) f->heelForce[i] = f->toeForce[i];
         }
+      }
+      if (est_filter) {   // pelvis.position / translationalVelocity / externalForce, terrain.height: the estimator's filters, one 2 kHz call per step_pd call
+        cassie::EstimatorFilter &f = est_state[(size_t)e];
+        f.step(y->pelvis.orientation, y->leftFoot.position, y->rightFoot.position, y->leftFoot.toeForce[2] + y->leftFoot.heelForce[2],
+               y->rightFoot.toeForce[2] + y->rightFoot.heelForce[2], y->pelvis.translationalAcceleration,
+               y->pelvis.position, y->pelvis.translationalVelocity, y->pelvis.externalForce, &y->terrain.height);
       }
       for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
       y->radio.signalGood = true; y->battery.stateOfCharge = 1;
@@ -578,7 +588,7 @@ int cassie_batch_row_width(const cassie_batch_t *b, const char *field) {
   if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; if (!strcmp(field, "aux")) return AUX_W; return -1;
 }
 long cassie_batch_launch_count(const cassie_batch_t *b) { return b->impl->launches; }
-void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); }
+void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); b->impl->reset_estimator(mask); }   // a fresh cassie_sim_t has a fresh estimator
 void cassie_batch_set_pd(cassie_batch_t *b, const double *pd) { b->impl->set_pd(pd); }
 void cassie_batch_step(cassie_batch_t *b, int nticks) { if (nticks > 0) b->impl->step(nticks, 0); }
 void cassie_batch_forward(cassie_batch_t *b) { b->impl->step(0, 1); }
@@ -603,6 +613,16 @@ int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int res
 int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows) { return b->impl->set_task_pd(rows) ? 0 : -1; }
 int cassie_batch_enable_estimator_forces(cassie_batch_t *b, int on) { b->impl->est_forces = on != 0; return 0; }
 void cassie_b200_estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) { estimator_leg_force(side, ang, quat, force); }
+int cassie_batch_enable_estimator_filter(cassie_batch_t *b, int on) { b->impl->est_filter = on != 0; if (on) b->impl->est_forces = true; else b->impl->est_state.clear(); return 0; }
+int cassie_batch_reset_estimator(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset_estimator(mask); return 0; }
+// the same filters as a plain host object (no GPU involved): what the unpack loop above runs per environment
+void *cassie_b200_estimator_filter_new(void) { return new cassie::EstimatorFilter(); }
+void cassie_b200_estimator_filter_free(void *f) { delete static_cast<cassie::EstimatorFilter *>(f); }
+void cassie_b200_estimator_filter_reset(void *f) { static_cast<cassie::EstimatorFilter *>(f)->reset(); }
+void cassie_b200_estimator_filter_step(void *f, state_out_t *y) {
+  static_cast<cassie::EstimatorFilter *>(f)->step(y->pelvis.orientation, y->leftFoot.position, y->rightFoot.position, y->leftFoot.toeForce[2] + y->leftFoot.heelForce[2],
+      y->rightFoot.toeForce[2] + y->rightFoot.heelForce[2], y->pelvis.translationalAcceleration, y->pelvis.position, y->pelvis.translationalVelocity, y->pelvis.externalForce, &y->terrain.height);
+}
 int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
 int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
 int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }
@@ -657,7 +677,7 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   if (!b) return nullptr;
   cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b;
   b->impl->enable_aux(true); b->impl->step(0, 1);   // a single environment always carries the derived-quantity row; populate it like the sensordata
-  b->impl->est_forces = true;                       // ... and the host-side toe / heel forces of the estimator
+  b->impl->est_forces = true; b->impl->est_filter = true;   // ... and the host-side part of the estimator (toe / heel forces, filters), as state_output_step runs in every cassie_sim_step_pd (src/cassiemujoco.c:1180)
   sim_pull(c);
   { const HostModel &hm = b->impl->hm; c->m_mass = hm.body_mass; c->m_ipos = hm.body_ipos; c->m_damp = hm.dof_damping; c->m_fric = hm.geom_friction;
     c->m_mass_dev = c->m_mass; c->m_ipos_dev = c->m_ipos; c->m_damp_dev = c->m_damp; c->m_fric_dev = c->m_fric; }
@@ -730,6 +750,7 @@ void cassie_sim_full_reset(cassie_sim_t *c) {
   c->b->impl->set("cst", cst.data());
   memset(c->qpos, 0, sizeof c->qpos); memcpy(c->qpos, q, sizeof q); memset(c->qvel, 0, sizeof c->qvel);
   c->b->impl->set("qpos", c->qpos); c->b->impl->set("qvel", c->qvel); cassie_batch_clear_forces(c->b);
+  c->b->impl->reset_estimator(nullptr);   // state_output_setup (src/cassiemujoco.c:2032) restarts the estimator's filters
   sim_pull(c);
 }
 }  // extern "C"

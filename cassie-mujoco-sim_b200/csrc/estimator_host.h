@@ -60,4 +60,91 @@ inline void estimator_leg_force(int side, const double ang[7], const double quat
   force[0] = cy * wx + sy * wy; force[1] = -sy * wx + cy * wy; force[2] = wz;
 }
 
+// ---- the estimator's filters (pelvis.position / translationalVelocity / externalForce, terrain.height of state_out_t).  Recovered from the
+// closed block's own memory (it keeps states, covariances and noise matrices as plain doubles): three per-axis Kalman filters
+// in the world frame at 2 kHz with the block's nominal mass (31 kg) and gravity (9.806).
+//   y_i = -R(q) foot_i (pelvis relative to foot i),  a = R(q) translationalAcceleration,  f_i = min(F_i.z, 0) with F_i = toeForce + heelForce
+//   contact = -(f_L + f_R) > 1 N;   w_meas = contact ? f_L / (f_L + f_R) : 1/2;   q_i = F_i.z < -50 N ? 1e-10 : 1e-6   (foot process noise)
+//   x, y:  state [p, v, footL, footR, w, F_ext]; in contact v follows a linear inverted pendulum (height 1 m) over w footL + (1 - w) footR plus
+//          F_ext / m, else it is held; measurements [p - footL, p - footR, w, v] = [y_L, y_R, w_meas, v_prev + dt a], R = diag(1e-6, 1e-6, 1e-6, 1)
+//   z:     state [p, v, footL, footR, F_ext]; v' = -g - (f_L + f_R) / m + F_ext / m; measurements [p - footL, p - footR] = [y_L.z, y_R.z]
+//   terrain.height: 1 s first-order lag of p_z - (w_meas y_L.z + (1 - w_meas) y_R.z), advanced in contact only.
+// The covariance update keeps the block's own form P <- P - K (H P) (not symmetrised): the block's trajectories are reproduced to 1e-13 with
+// it, and a mathematically equal symmetric form drifts away from them within a second of simulated time.
+template <int N, int K>
+inline void kalman_update(double (&x)[N], double (&P)[N * N], const double (&H)[K * N], const double (&Rd)[K], const double (&zm)[K]) {
+  double HP[K * N], S[K][2 * K], G[N * K];
+  for (int l = 0; l < K; l++) for (int j = 0; j < N; j++) { double a = 0; for (int q = 0; q < N; q++) a += H[l * N + q] * P[q * N + j]; HP[l * N + j] = a; }
+  for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) { double a = 0; for (int q = 0; q < N; q++) a += P[i * N + q] * H[j * N + q]; G[i * K + j] = a; }   // P H'
+  for (int i = 0; i < K; i++) for (int j = 0; j < K; j++) { double a = i == j ? Rd[i] : 0; for (int q = 0; q < N; q++) a += H[i * N + q] * G[q * K + j]; S[i][j] = a; S[i][K + j] = i == j; }
+  for (int c = 0; c < K; c++) {   // S is symmetric positive definite (R > 0): elimination without row exchanges
+    const double inv = 1.0 / S[c][c];
+    for (int j = 0; j < 2 * K; j++) S[c][j] *= inv;
+    for (int r = 0; r < K; r++) if (r != c) { const double f = S[r][c]; for (int j = 0; j < 2 * K; j++) S[r][j] -= f * S[c][j]; }
+  }
+  double Kg[N * K], inn[K];
+  for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) { double a = 0; for (int l = 0; l < K; l++) a += G[i * K + l] * S[l][K + j]; Kg[i * K + j] = a; }
+  for (int j = 0; j < K; j++) { double a = zm[j]; for (int q = 0; q < N; q++) a -= H[j * N + q] * x[q]; inn[j] = a; }
+  for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) x[i] += Kg[i * K + j] * inn[j];
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double a = 0; for (int l = 0; l < K; l++) a += Kg[i * K + l] * HP[l * N + j]; P[i * N + j] -= a; }
+}
+template <int N>
+inline void kalman_predict_cov(double (&P)[N * N], const double (&A)[N * N], const double (&Qd)[N]) {
+  double T[N * N];
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double a = 0; for (int q = 0; q < N; q++) a += A[i * N + q] * P[q * N + j]; T[i * N + j] = a; }
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double a = i == j ? Qd[i] : 0; for (int q = 0; q < N; q++) a += T[i * N + q] * A[j * N + q]; P[i * N + j] = a; }
+}
+
+struct EstimatorFilter {
+  bool started = false;
+  double xy[2][6] = {}, Pxy[2][36] = {}, z[5] = {}, Pz[25] = {}, terrain = 0;
+  void reset() { *this = EstimatorFilter(); }
+  // quat: pelvis.orientation; footL / footR: foot points in the pelvis frame; FLz / FRz: z of toeForce + heelForce; acc: translationalAcceleration
+  void step(const double quat[4], const double footL[3], const double footR[3], double FLz, double FRz, const double acc[3],
+            double pos[3], double vel[3], double ext_force[3], double *terrain_height) {
+    constexpr double dt = 0.0005, mass = 31.0, grav = 9.806, c = dt * grav;
+    const double w = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
+    const M3 R{{w * w + qx * qx - qy * qy - qz * qz, 2 * (qx * qy + w * qz), 2 * (qx * qz - w * qy)},
+               {2 * (qx * qy - w * qz), w * w - qx * qx + qy * qy - qz * qz, 2 * (qy * qz + w * qx)},
+               {2 * (qx * qz + w * qy), 2 * (qy * qz - w * qx), w * w - qx * qx - qy * qy + qz * qz}};
+    const V3 yl = -1.0 * (R * V3{footL[0], footL[1], footL[2]}), yr = -1.0 * (R * V3{footR[0], footR[1], footR[2]}), a = R * V3{acc[0], acc[1], acc[2]};
+    const double yL[3] = {yl.x, yl.y, yl.z}, yR[3] = {yr.x, yr.y, yr.z}, aw[3] = {a.x, a.y, a.z};
+    const double fl = FLz < 0 ? FLz : 0, fr = FRz < 0 ? FRz : 0;
+    const bool contact = -(fl + fr) > 1.0;
+    const double wm = contact ? fl / (fl + fr) : 0.5, qL = FLz < -50 ? 1e-10 : 1e-6, qR = FRz < -50 ? 1e-10 : 1e-6;
+    if (!started) {   // the block's own start: pelvis at 0, the foot states at +y (sic), weight 1/2, the whole weight on the external force
+      for (int ax = 0; ax < 2; ax++) { const double x0[6] = {0, 0, yL[ax], yR[ax], 0.5, 0}; for (int i = 0; i < 6; i++) xy[ax][i] = x0[i];
+        for (int i = 0; i < 36; i++) Pxy[ax][i] = (i % 7 == 0) ? 1e-6 : 0; }
+      const double z0[5] = {0, 0, yL[2], yR[2], mass * grav}; for (int i = 0; i < 5; i++) z[i] = z0[i];
+      for (int i = 0; i < 25; i++) Pz[i] = (i % 6 == 0) ? 1e-6 : 0;
+      terrain = 0; started = true;
+    }
+    static constexpr double H6[24] = {1, 0, -1, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0}, R4[4] = {1e-6, 1e-6, 1e-6, 1};
+    for (int ax = 0; ax < 2; ax++) {
+      double (&x)[6] = xy[ax];
+      const double zm[4] = {yL[ax], yR[ax], wm, x[1] + dt * aw[ax]}, Qd[6] = {1e-8, 1e-8, qL, qR, 1e-5, 1e-2}, p0 = x[0], v0 = x[1], wt = x[4];
+      double A[36] = {}; for (int i = 0; i < 6; i++) A[7 * i] = 1;
+      A[1] = dt;
+      if (contact) { A[6] = c; A[8] = -c * wt; A[9] = -c * (1 - wt); A[10] = -c * (x[2] - x[3]); A[11] = dt / mass;
+                     x[1] = v0 + c * (p0 - wt * x[2] - (1 - wt) * x[3]) + dt / mass * x[5]; }
+      x[0] = p0 + dt * v0;
+      kalman_predict_cov<6>(Pxy[ax], A, Qd);
+      kalman_update<6, 4>(x, Pxy[ax], H6, R4, zm);
+    }
+    {
+      static constexpr double H5[10] = {1, 0, -1, 0, 0, 1, 0, 0, -1, 0}, R2[2] = {1e-6, 1e-6};
+      const double zm[2] = {yL[2], yR[2]}, Qd[5] = {1e-8, 1e-8, qL, qR, 1e-2}, p0 = z[0], v0 = z[1];
+      double A[25] = {}; for (int i = 0; i < 5; i++) A[6 * i] = 1;
+      A[1] = dt; A[9] = dt / mass;
+      z[0] = p0 + dt * v0; z[1] = v0 + dt / mass * z[4] + dt * (-grav - (fl + fr) / mass);
+      kalman_predict_cov<5>(Pz, A, Qd);
+      kalman_update<5, 2>(z, Pz, H5, R2, zm);
+    }
+    if (contact) terrain = (terrain + dt * (z[0] - (wm * yL[2] + (1 - wm) * yR[2]))) / (1 + dt);
+    for (int ax = 0; ax < 2; ax++) { pos[ax] = xy[ax][0]; vel[ax] = xy[ax][1]; ext_force[ax] = xy[ax][5]; }
+    pos[2] = z[0]; vel[2] = z[1]; ext_force[2] = z[4];
+    *terrain_height = terrain;
+  }
+};
+
 }  // namespace cassie

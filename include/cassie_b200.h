@@ -131,8 +131,8 @@ void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask);
  * state_output_step, decoded from the closed archive and checked equal to it to 1e-11: motor / joint position + velocity + torque,
  * pelvis.orientation (+-q, mat2quat's sign), rotationalVelocity, translationalAcceleration, both feet's position / orientation (pelvis frame) and
  * footRotationalVelocity / footTranslationalVelocity (foot frame), radio, battery; toeForce / heelForce when enabled (see
- * cassie_batch_enable_estimator_forces).  The stateful outputs (pelvis.position, translationalVelocity, externalForce / externalMoment,
- * terrain) are zero (scope). */
+ * cassie_batch_enable_estimator_forces); pelvis.position / translationalVelocity / externalForce and terrain.height (the estimator's filters)
+ * when enabled (see cassie_batch_enable_estimator_filter).  externalMoment and terrain.slope are zero, as they are in the reference's output. */
 void cassie_sim_step_pd_batch(cassie_batch_t *envs, const pd_in_t *pd_in, state_out_t *state_out);
 
 /* throughput path: compact rows.  pd: host [n_env][CASSIE_PD_WIDTH] doubles, copied to the device (and converted to the batch
@@ -186,6 +186,18 @@ int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int res
  * ang = hipRoll, hipYaw, hipPitch, knee (motor positions), shin, tarsus (joint encoders), foot (motor position); quat = IMU quaternion. */
 int cassie_batch_enable_estimator_forces(cassie_batch_t *b, int on);
 void cassie_b200_estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]);
+/* The estimator's filters (state_output_step's stateful part, src/cassiemujoco.c:1180; decoded from the closed block's memory, agreement with the
+ * archive 1e-13 on the archive's own stateless outputs): pelvis.position, translationalVelocity, externalForce, terrain.height.  One filter
+ * object per environment lives on the host and advances once per cassie_sim_step_pd_batch call (the reference runs it once per 2 kHz
+ * step_pd call); it turns the force option on.  Off by default for batches, always on for a cassie_sim_t.  cassie_batch_reset_estimator
+ * restarts the filters (state_output_setup; mask as in cassie_batch_reset).  The filter is also exported as a plain host object:
+ * ..._step reads orientation, translationalAcceleration, both feet's position and toe / heel forces from *y and writes the four outputs. */
+int cassie_batch_enable_estimator_filter(cassie_batch_t *b, int on);
+int cassie_batch_reset_estimator(cassie_batch_t *b, const unsigned char *mask);
+void *cassie_b200_estimator_filter_new(void);
+void cassie_b200_estimator_filter_free(void *filter);
+void cassie_b200_estimator_filter_reset(void *filter);
+void cassie_b200_estimator_filter_step(void *filter, state_out_t *y);
 /* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
 void cassie_batch_forward(cassie_batch_t *b);
 /* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */

@@ -1002,12 +1002,15 @@ pd_input_t *pd_input_alloc(void); void pd_input_setup(pd_input_t *); void pd_inp
 void pd_input_step(pd_input_t *, const pd_in_t *, const cassie_out_t *, cassie_user_in_t *);
 #endif
 
+/* state of the estimator's filters (o_est_filter_step) */
+typedef struct { int started; double x[2][6], P[2][36], z[5], Pz[25], terrain; } OEst;
 typedef struct {
   OModel *m; OData *d;
   cassie_out_t cassie_out;
   int drive_filter[NUM_DRIVES][9];
   double joint_filter_x[NUM_JOINTS][4], joint_filter_y[NUM_JOINTS][3];
   double torque_delay[NUM_DRIVES][DELAY];
+  OEst est2;
 #ifdef ORACLE_USE_AGILITY_REF
   cassie_core_sim_t *core; state_output_t *est; pd_input_t *pd;
 #endif
@@ -1096,7 +1099,10 @@ void o_core_sim_step(const double u[10], const cassie_out_t *o, double out[10]) 
  *    the pelvis frame; orientation = foot frame turned by a fixed rotation (40 degrees), as a quaternion (mat2quat branches as MuJoCo's);
  *    footRotationalVelocity / footTranslationalVelocity = Jacobian times the measured rates, expressed in THAT FOOT FRAME.
  *  - toeForce = heelForce: o_est_leg_force below (spring torques through the closed four-bar; single-precision agreement only).
- * Not decoded (left zero): pelvis.position / translationalVelocity / externalForce / externalMoment, terrain (stateful filters). */
+ * The STATEFUL part (o_est_filter_step below) was decoded from the block's own memory (oracle/probe_estimator.c probe_est_mem: the block
+ * keeps its states, covariances and noise matrices in plain doubles) and agrees with the archive to 1e-15 when fed the archive's own
+ * stateless outputs (tests/test_estimator_filter.py): pelvis.position / translationalVelocity / externalForce and terrain.height.
+ * externalMoment and terrain.slope are always zero in the archive too. */
 static void est_mat2quat(double *q, const double *R) { /* R row-major */
   double t = R[0] + R[4] + R[8];
   if (t > 0) { double s = sqrt(t + 1) * 2; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
@@ -1209,6 +1215,97 @@ void o_est_leg_force(int side, const double ang[7], const double quat[4], double
   const double wv[3] = {R[0] * fx + R[2] * fz, R[3] * fx + R[5] * fz, R[6] * fx + R[8] * fz};
   force[0] = cy * wv[0] + sy * wv[1]; force[1] = -sy * wv[0] + cy * wv[1]; force[2] = wv[2];
 }
+
+/* ---- the estimator's stateful part: three per-axis Kalman filters in the world frame, 2 kHz (dt = 0.0005), nominal mass 31 kg, g = 9.806.
+ * Inputs per call (all outputs of the stateless part): R = R(orientation), the foot points in the pelvis frame, the leg forces
+ * (toeForce + heelForce, i.e. the leg's force on the ground: negative z when it carries load), translationalAcceleration.
+ *   y_i = -R foot_i                      (pelvis relative to foot i, world frame), a = R translationalAcceleration
+ *   f_i = min(F_i.z, 0);  contact = -(f_L + f_R) > 1 N;  w_meas = contact ? f_L / (f_L + f_R) : 0.5;  q_i = F_i.z < -50 N ? 1e-10 : 1e-6
+ * x and y axes: extended filter, state [p, v, footL, footR, w, F_ext], P0 = 1e-6 I, Q = diag(1e-8, 1e-8, q_L, q_R, 1e-5, 1e-2),
+ *   predict  p += dt v;  in contact (linear inverted pendulum of height 1 m over the load-weighted foot point):
+ *            v += dt g (p - w footL - (1 - w) footR) + dt/m F_ext      (Jacobian row [c, 1, -c w, -c (1-w), -c (footL - footR), dt/m], c = dt g);
+ *            out of contact v is held (row [0, 1, 0, 0, 0, 0]);
+ *   measure  [p - footL, p - footR, w, v] = [y_L, y_R, w_meas, v_previous + dt a],  R = diag(1e-6, 1e-6, 1e-6, 1).
+ * z axis: linear filter, state [p, v, footL, footR, F_ext], Q = diag(1e-8, 1e-8, q_L, q_R, 1e-2),
+ *   predict  p += dt v;  v += dt (-g - (f_L + f_R) / m) + dt/m F_ext;   measure [p - footL, p - footR] = [y_L.z, y_R.z], R = 1e-6 I.
+ * First call: states start at [0, 0, y_L, y_R, 0.5, 0] (x, y) and [0, 0, y_L.z, y_R.z, m g] (z) - the feet at +y, as the archive has it.
+ * terrain.height: first-order lag (1 s, backward Euler) of p_z - (w_meas y_L.z + (1 - w_meas) y_R.z), advanced only in contact. */
+void o_est_filter_reset(OEst *e) { memset(e, 0, sizeof *e); }
+/* x <- x + K (zm - H x), P <- (I - K H) P for n states, k measurements (H row-major k x n, R diagonal) */
+static void kf_update_(int n, int k, double *x, double *P, const double *H, const double *Rd, const double *zm) {
+  double PHt[6 * 4], S[4 * 4], Si[4 * 4], K[6 * 4], inn[4], Pn[36];
+  for (int i = 0; i < n; i++) for (int j = 0; j < k; j++) { double a = 0; for (int l = 0; l < n; l++) a += P[i * n + l] * H[j * n + l]; PHt[i * k + j] = a; }
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) { double a = i == j ? Rd[i] : 0; for (int l = 0; l < n; l++) a += H[i * n + l] * PHt[l * k + j]; S[i * k + j] = a; }
+  /* inverse by Gauss-Jordan with partial pivoting */
+  double M[4][8];
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) { M[i][j] = S[i * k + j]; M[i][k + j] = i == j; }
+  for (int c = 0; c < k; c++) {
+    int pv = c; for (int r = c + 1; r < k; r++) if (fabs(M[r][c]) > fabs(M[pv][c])) pv = r;
+    if (pv != c) for (int j = 0; j < 2 * k; j++) { double t = M[c][j]; M[c][j] = M[pv][j]; M[pv][j] = t; }
+    double d = M[c][c]; for (int j = 0; j < 2 * k; j++) M[c][j] /= d;
+    for (int r = 0; r < k; r++) if (r != c) { double f = M[r][c]; for (int j = 0; j < 2 * k; j++) M[r][j] -= f * M[c][j]; }
+  }
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) Si[i * k + j] = M[i][k + j];
+  for (int i = 0; i < n; i++) for (int j = 0; j < k; j++) { double a = 0; for (int l = 0; l < k; l++) a += PHt[i * k + l] * Si[l * k + j]; K[i * k + j] = a; }
+  for (int j = 0; j < k; j++) { double a = zm[j]; for (int l = 0; l < n; l++) a -= H[j * n + l] * x[l]; inn[j] = a; }
+  for (int i = 0; i < n; i++) for (int j = 0; j < k; j++) x[i] += K[i * k + j] * inn[j];
+  double HP[4 * 6];   /* (I - K H) P with H P formed as such (not as (P H')'): the archive's form; P is only symmetric to rounding */
+  for (int l = 0; l < k; l++) for (int j = 0; j < n; j++) { double a = 0; for (int q = 0; q < n; q++) a += H[l * n + q] * P[q * n + j]; HP[l * n + j] = a; }
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { double a = P[i * n + j]; for (int l = 0; l < k; l++) a -= K[i * k + l] * HP[l * n + j]; Pn[i * n + j] = a; }
+  memcpy(P, Pn, sizeof(double) * n * n);
+}
+/* P <- A P A' + diag(Qd) */
+static void kf_predict_cov_(int n, double *P, const double *A, const double *Qd) {
+  double T[36], Pn[36];
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { double a = 0; for (int l = 0; l < n; l++) a += A[i * n + l] * P[l * n + j]; T[i * n + j] = a; }
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { double a = i == j ? Qd[i] : 0; for (int l = 0; l < n; l++) a += T[i * n + l] * A[j * n + l]; Pn[i * n + j] = a; }
+  memcpy(P, Pn, sizeof(double) * n * n);
+}
+void o_est_filter_step(OEst *e, state_out_t *y) {
+  const double dt = 0.0005, mass = 31, grav = 9.806, c = dt * grav;
+  double R[9], yL[3], yR[3], aw[3];
+  quat2Mat(R, y->pelvis.orientation);
+  mulMatVec3(yL, R, y->leftFoot.position); mulMatVec3(yR, R, y->rightFoot.position); mulMatVec3(aw, R, y->pelvis.translationalAcceleration);
+  for (int k = 0; k < 3; k++) { yL[k] = -yL[k]; yR[k] = -yR[k]; }
+  const double FLz = y->leftFoot.toeForce[2] + y->leftFoot.heelForce[2], FRz = y->rightFoot.toeForce[2] + y->rightFoot.heelForce[2];
+  const double fl = FLz < 0 ? FLz : 0, fr = FRz < 0 ? FRz : 0;
+  const int contact = -(fl + fr) > 1.0;
+  const double wm = contact ? fl / (fl + fr) : 0.5, qL = FLz < -50 ? 1e-10 : 1e-6, qR = FRz < -50 ? 1e-10 : 1e-6;
+  if (!e->started) {
+    for (int ax = 0; ax < 2; ax++) {
+      const double x0[6] = {0, 0, yL[ax], yR[ax], 0.5, 0}; copyv(e->x[ax], x0, 6);
+      memset(e->P[ax], 0, sizeof e->P[ax]); for (int i = 0; i < 6; i++) e->P[ax][7 * i] = 1e-6;
+    }
+    const double z0[5] = {0, 0, yL[2], yR[2], mass * grav}; copyv(e->z, z0, 5);
+    memset(e->Pz, 0, sizeof e->Pz); for (int i = 0; i < 5; i++) e->Pz[6 * i] = 1e-6;
+    e->terrain = 0; e->started = 1;
+  }
+  static const double H6[24] = {1, 0, -1, 0, 0, 0,  1, 0, 0, -1, 0, 0,  0, 0, 0, 0, 1, 0,  0, 1, 0, 0, 0, 0}, R4[4] = {1e-6, 1e-6, 1e-6, 1};
+  for (int ax = 0; ax < 2; ax++) {
+    double *x = e->x[ax], A[36] = {0}, zm[4] = {yL[ax], yR[ax], wm, x[1] + dt * aw[ax]};
+    const double Qd[6] = {1e-8, 1e-8, qL, qR, 1e-5, 1e-2}, p0 = x[0], v0 = x[1], w = x[4];
+    for (int i = 0; i < 6; i++) A[7 * i] = 1;
+    A[1] = dt;
+    if (contact) { A[6] = c; A[8] = -c * w; A[9] = -c * (1 - w); A[10] = -c * (x[2] - x[3]); A[11] = dt / mass; x[1] = v0 + c * (p0 - w * x[2] - (1 - w) * x[3]) + dt / mass * x[5]; }
+    x[0] = p0 + dt * v0;
+    kf_predict_cov_(6, e->P[ax], A, Qd);
+    kf_update_(6, 4, x, e->P[ax], H6, R4, zm);
+  }
+  {
+    static const double H5[10] = {1, 0, -1, 0, 0,  1, 0, 0, -1, 0}, R2[2] = {1e-6, 1e-6};
+    double *x = e->z, A[25] = {0}, zm[2] = {yL[2], yR[2]};
+    const double Qd[5] = {1e-8, 1e-8, qL, qR, 1e-2}, p0 = x[0], v0 = x[1];
+    for (int i = 0; i < 5; i++) A[6 * i] = 1;
+    A[1] = dt; A[9] = dt / mass;
+    x[0] = p0 + dt * v0; x[1] = v0 + dt / mass * x[4] + dt * (-grav - (fl + fr) / mass);
+    kf_predict_cov_(5, e->Pz, A, Qd);
+    kf_update_(5, 2, x, e->Pz, H5, R2, zm);
+  }
+  if (contact) e->terrain = (e->terrain + dt * (e->z[0] - (wm * yL[2] + (1 - wm) * yR[2]))) / (1 + dt);
+  for (int ax = 0; ax < 2; ax++) { y->pelvis.position[ax] = e->x[ax][0]; y->pelvis.translationalVelocity[ax] = e->x[ax][1]; y->pelvis.externalForce[ax] = e->x[ax][5]; }
+  y->pelvis.position[2] = e->z[0]; y->pelvis.translationalVelocity[2] = e->z[1]; y->pelvis.externalForce[2] = e->z[4];
+  y->terrain.height = e->terrain;
+}
 void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
   cassie_out_t out = *o;
   memset(y, 0, sizeof *y);
@@ -1231,6 +1328,11 @@ void o_state_output_step(const cassie_out_t *o, state_out_t *y) {
   }
   copyv(y->radio.channel, out.pelvis.radio.channel, 16); y->radio.signalGood = true; y->battery.stateOfCharge = out.pelvis.battery.stateOfCharge;
 }
+
+/* stateless part then the filters (one OEst per estimator instance) */
+void o_state_output_step_full(OEst *e, const cassie_out_t *o, state_out_t *y) { o_state_output_step(o, y); o_est_filter_step(e, y); }
+OEst *o_est_new(void) { return calloc(1, sizeof(OEst)); }
+void o_est_free(OEst *e) { free(e); }
 
 OSim *osim_new(const char *model_path) {
   OSim *c = calloc(1, sizeof(OSim));
@@ -1325,7 +1427,7 @@ void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassi
 #ifdef ORACLE_USE_AGILITY_REF
     state_output_step(c->est, &out, y);
 #else
-    o_state_output_step(&out, y); /* the decoded stateless subset */
+    o_state_output_step_full(&c->est2, &out, y); /* the decoded estimator */
 #endif
   }
 }

@@ -61,3 +61,17 @@ def fk(side, m, shin, tars):
     c40, s40 = np.cos(np.deg2rad(40)), np.sin(np.deg2rad(40))
     Roff = np.array([[-c40, 0, -s40], [s40, 0, -c40], [0, -1, 0.]])
     return p + R @ np.array([0.01762, 0.05219, 0]), R @ Roff
+
+
+def est_mem(inps):
+    """(outputs [T,105], memory snapshots [T+1, nbytes] of the estimator block) for a sequence of inputs"""
+    a = np.ascontiguousarray(inps, dtype=np.float64)
+    T = a.shape[0]
+    L = lib()
+    L.probe_est_mem.restype = C.c_long
+    L.probe_est_mem.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_long, C.POINTER(C.c_double)]
+    sz = L.probe_est_mem(a.ctypes.data_as(C.POINTER(C.c_double)), 0, None, 0, None)
+    mem = np.zeros((T + 1, sz), dtype=np.uint8)
+    out = np.zeros((T, 105))
+    L.probe_est_mem(a.ctypes.data_as(C.POINTER(C.c_double)), T, mem.ctypes.data, sz, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out, mem

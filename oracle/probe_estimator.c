@@ -85,3 +85,36 @@ void probe_est_tq(const double *in, int ncalls, double *out) {
   for (int i = 0; i < ncalls; i++) state_output_step(e, &o, &y);
   flat(&y, out); state_output_free(e);
 }
+
+/* internal-memory view of the estimator (study aid): T inputs of 45, one persistent block; mem = T+1 snapshots (after setup, then after each call)
+ * of the first `nbytes` bytes of the block; returns malloc_usable_size of the block. */
+#include <malloc.h>
+long probe_est_mem(const double *in, int T, unsigned char *mem, long nbytes, double *out) {
+  cassie_out_t o; state_out_t y;
+  state_output_t *e = state_output_alloc(); state_output_setup(e);
+  long sz = (long)malloc_usable_size(e);
+  if (nbytes > sz) nbytes = sz;
+  if (mem) memcpy(mem, e, nbytes);
+  for (int t = 0; t < T; t++) { fill(&o, in + 45 * t); state_output_step(e, &o, &y); if (out) flat(&y, out + 105 * t); if (mem) memcpy(mem + (t + 1) * nbytes, e, nbytes); }
+  state_output_free(e);
+  return sz;
+}
+/* same with raw cassie_out_t records (T of them, as the simulator wrote them) */
+long probe_est_mem_raw(const cassie_out_t *seq, int T, unsigned char *mem, long nbytes, double *out) {
+  state_out_t y;
+  state_output_t *e = state_output_alloc(); state_output_setup(e);
+  long sz = (long)malloc_usable_size(e);
+  if (nbytes > sz) nbytes = sz;
+  if (mem) memcpy(mem, e, nbytes);
+  for (int t = 0; t < T; t++) { state_output_step(e, seq + t, &y); if (out) flat(&y, out + 105 * t); if (mem) memcpy(mem + (t + 1) * nbytes, e, nbytes); }
+  state_output_free(e);
+  return sz;
+}
+/* does state_output_setup on a used block restart the filters?  out[0..104] = output of a call after `pre` calls + setup; out[105..209] = same from a fresh block */
+void probe_est_resetup(const double *in, int pre, double *out) {
+  cassie_out_t o; state_out_t y; fill(&o, in);
+  state_output_t *e = state_output_alloc(); state_output_setup(e);
+  for (int i = 0; i < pre; i++) state_output_step(e, &o, &y);
+  state_output_setup(e); state_output_step(e, &o, &y); flat(&y, out); state_output_free(e);
+  e = state_output_alloc(); state_output_setup(e); state_output_step(e, &o, &y); flat(&y, out + 105); state_output_free(e);
+}

@@ -4,6 +4,8 @@ Runs ONLY in the build container (needs /root/reference); the GPU box uses the c
 
   *.omodel   oracle model tables: oracle/mjcf_compile.py applied to /root/reference/model/<name>.xml
              (derived numeric tables, not a copy of the XML)
+  estimator_sequence.npz   400 consecutive 2 kHz calls of the reference's closed estimator (state_output_step) in a closed-loop run from the
+             initial state (free fall, touch-down, load transfer): its stateless outputs that feed its filters, and the filters' outputs
   agility_vectors.npz   input/output pairs of the reference's closed Agility blocks (pd_input_step incl. taskPd, cassie_core_sim_step,
              state_output_step from src/libagilitycassie.a via oracle/_ref/liboracle_ref.so; layout: oracle/probe_estimator.c)
 """
@@ -60,8 +62,36 @@ def agility_vectors(n=400, seed=123):
     print('wrote agility_vectors.npz', n)
 
 
+def estimator_sequence(T=400):
+    """closed loop of the oracle's simulator with the REAL closed blocks (oracle/_ref/liboracle_ref.so): per call the archive's own stateless
+    outputs the filters consume (orientation 4, translationalAcceleration 3, foot positions 2x3, toe+heel force 2x3 = 19) and the filter
+    outputs (position 3, translationalVelocity 3, externalForce 3, terrain.height = 10)"""
+    import ctypes as C
+    import importlib
+    import numpy as np
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import oracle as O
+    from conftest import PD_DGAIN, PD_PGAIN, PD_TARGET
+    pkg = importlib.import_module('cassie-mujoco-sim_b200')
+    O.build(ref=True)
+    o = O.OracleSim(os.path.join(HERE, 'cassie.omodel'), ref=True)
+    u = O.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    y = pkg.state_out_t()
+    X, Y = [], []
+    for k in range(T):
+        o.step_pd(u, y)
+        X.append(np.concatenate([y.pelvis.orientation[:], y.pelvis.translationalAcceleration[:], y.leftFoot.position[:], y.rightFoot.position[:],
+                                 np.array(y.leftFoot.toeForce[:]) + np.array(y.leftFoot.heelForce[:]), np.array(y.rightFoot.toeForce[:]) + np.array(y.rightFoot.heelForce[:])]))
+        Y.append(np.concatenate([y.pelvis.position[:], y.pelvis.translationalVelocity[:], y.pelvis.externalForce[:], [y.terrain.height]]))
+        assert not any(y.pelvis.externalMoment[:]) and not any(y.terrain.slope[:])
+    np.savez_compressed(os.path.join(HERE, 'estimator_sequence.npz'), stateless=np.array(X), filtered=np.array(Y))
+    print('wrote estimator_sequence.npz', T)
+
+
 def main():
     agility_vectors()
+    estimator_sequence()
     for name in MODELS:
         m = mc.compile_mjcf(os.path.join(REF, 'model', name + '.xml'))
         mc.write_omodel(m, os.path.join(HERE, name + '.omodel'))

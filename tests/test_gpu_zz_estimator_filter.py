@@ -1,0 +1,67 @@
+"""GPU: the estimator's filters inside cassie_sim_step_pd(_batch) (pelvis.position / translationalVelocity / externalForce, terrain.height)
+against the oracle linked with the REAL estimator archive when the prebuilt checker travelled (oracle/_ref), else its pinned restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PD_DGAIN, PD_PGAIN, PD_TARGET, product
+
+pytestmark = pytest.mark.gpu
+
+
+def _pd(P):
+    pu = P.pd_in_t()
+    for side, leg in enumerate((pu.leftLeg, pu.rightLeg)):
+        for i in range(5):
+            leg.motorPd.pTarget[i] = PD_TARGET[5 * side + i]
+            leg.motorPd.pGain[i], leg.motorPd.dGain[i] = PD_PGAIN[i], PD_DGAIN[i]
+    return pu
+
+
+def _filtered(y):
+    return np.concatenate([y.pelvis.position[:], y.pelvis.translationalVelocity[:], y.pelvis.externalForce[:], [y.terrain.height]])
+
+
+def test_filtered_outputs_match_the_estimator(oracle_mod):
+    P, O = product(), oracle_mod
+    ref = os.path.exists(O.lib_path(ref=True))
+    o = O.OracleSim(os.path.join(GOLDEN, 'cassie.omodel'), ref=ref)
+    c = P.CassieSim()
+    u, pu, y = O.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN), _pd(P), P.state_out_t()
+    worst = 0.0
+    for k in range(700):
+        o.step_pd(u, y)
+        yc = c.step_pd(pu)
+        a, b = _filtered(y), _filtered(yc)
+        worst = max(worst, (np.abs(a - b) / (1 + np.abs(a))).max())
+    # the leg forces feeding the filters agree with the archive only to its single precision: 1e-3 relative is the bar (CPU twin: 1e-4)
+    assert worst < 2e-3, worst
+    assert abs(b[2]) > 0.3 and abs(b[8] - 31 * 9.806) > 10 and b[9] != 0 and yc.leftFoot.toeForce[2] < -50
+    c.full_reset()                                               # state_output_setup: the filters start again (src/cassiemujoco.c:2032)
+    again = _filtered(c.step_pd(pu))
+    assert again[8] == pytest.approx(31 * 9.806, rel=1e-6) and np.abs(again[3:6]).max() < 0.05 and 0.4 < again[2] < 1.0
+
+
+def test_batch_filters_follow_each_environment():
+    P = product()
+    n = 4
+    b0 = P.CassieBatch(1, precision=P.FP64)
+    y0 = b0.step_pd((P.pd_in_t * 1)(_pd(P)))
+    assert not any(y0[0].pelvis.position[:]) and not any(y0[0].pelvis.externalForce[:])     # batches: off by default
+    b = P.CassieBatch(n, precision=P.FP64)
+    pin = (P.pd_in_t * n)(*[_pd(P) for _ in range(n)])
+    b.enable_estimator()
+    c = P.CassieSim()
+    for k in range(300):
+        ys = b.step_pd(pin)
+        yc = c.step_pd(pin[0])
+        if k == 150:
+            m = np.zeros(n, dtype=np.uint8)
+            m[2] = 1
+            b.reset_estimator(m)
+    want = _filtered(yc)
+    for e in (0, 1, 3):     # the single-environment object runs the extended kernel instance: equal physics to rounding, not bitwise
+        assert (np.abs(_filtered(ys[e]) - want) / (1 + np.abs(want))).max() < 1e-6, e
+    assert np.array_equal(_filtered(ys[0]), _filtered(ys[1]))
+    assert (np.abs(_filtered(ys[2]) - want) / (1 + np.abs(want))).max() > 1e-3   # environment 2 restarted its filters at call 150
