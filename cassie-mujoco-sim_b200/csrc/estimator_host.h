@@ -1,6 +1,7 @@
 // estimator_host.h -- host-side part of the reference's estimator (state_output_step, closed source; semantics recovered by probing the
-// archive): the toe / heel force of one leg.  Pure function of the measured angles and the IMU quaternion; runs on the host while
-// state_out_t rows are unpacked (the kernel's observation row does not carry it in this round).
+// archive): the toe / heel force of one leg (a pure function of the measured angles and the IMU quaternion) and, further down, the
+// Kalman filters behind pelvis.position / translationalVelocity / externalForce and terrain.height.  Both run on the host while state_out_t
+// rows are unpacked (the kernel's observation row does not carry them in this round).
 //
 //   toeForce = heelForce = Rz(yaw)' R(q) [f_x, 0, f_z],   (f_x, f_z) = -1/2 J^-T [k_s shin; k_h (H - H0)],   k = (1500, 1250) N m / rad
 //

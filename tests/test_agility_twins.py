@@ -184,7 +184,7 @@ def test_twins_against_committed_archive_vectors(oracle_mod, pkg):
         got = np.concatenate([[0, 0, 0], field(y, 'pelvis.orientation'), field(y, 'pelvis.rotationalVelocity'), [0, 0, 0], field(y, 'pelvis.translationalAcceleration')])
         want = est[:16].copy()
         want[0:3] = 0
-        want[10:13] = 0                                  # pelvis position / translational velocity: stateful, not decoded
+        want[10:13] = 0                                  # pelvis position / translational velocity: the filters, checked in tests/test_estimator_filter.py
         worst['est'] = max(worst['est'], np.abs(got - want).max())
         for sd, name in enumerate(('leftFoot', 'rightFoot')):
             g = np.concatenate([field(y, name + '.position'), field(y, name + '.orientation'), field(y, name + '.footRotationalVelocity'), field(y, name + '.footTranslationalVelocity')])
