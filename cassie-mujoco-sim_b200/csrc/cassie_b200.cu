@@ -414,7 +414,7 @@ template <typename real> struct Batch : BatchBase {
         state_foot_out_t *f = sd ? &y->rightFoot : &y->leftFoot; const real *fo = o + OB_FOOT + 13 * sd;
         for (int i = 0; i < 3; i++) { f->position[i] = fo[i]; f->footRotationalVelocity[i] = fo[7 + i]; f->footTranslationalVelocity[i] = fo[10 + i]; }
         for (int i = 0; i < 4; i++) f->orientation[i] = fo[3 + i];
-        if (est_forces) {   // toe / heel force: host-side part of the decoded estimator (opt-in for batches: it costs host time per environment)
+        if (est_forces || est_filter) {   // toe / heel force: host-side part of the decoded estimator (opt-in for batches: it costs host time per environment)
           const double ang[7] = {o[OB_MPOS + 5 * sd], o[OB_MPOS + 5 * sd + 1], o[OB_MPOS + 5 * sd + 2], o[OB_MPOS + 5 * sd + 3], o[OB_JPOS + 3 * sd], o[OB_JPOS + 3 * sd + 1], o[OB_MPOS + 5 * sd + 4]};
           const double qd[4] = {o[OB_QUAT], o[OB_QUAT + 1], o[OB_QUAT + 2], o[OB_QUAT + 3]};
           estimator_leg_force(sd, ang, qd, f->toeForce);
