@@ -72,12 +72,14 @@ inline void estimator_leg_force(int side, const double ang[7], const double quat
 //   terrain.height: 1 s first-order lag of p_z - (w_meas y_L.z + (1 - w_meas) y_R.z), advanced in contact only.
 // The covariance update keeps the block's own form P <- P - K (H P) (not symmetrised): the block's trajectories are reproduced to 1e-13 with
 // it, and a mathematically equal symmetric form drifts away from them within a second of simulated time.
+// Measurement rows are differences of two states or single states: row l = e_plus[l] - e_minus[l] (minus < 0: none), R diagonal.  The sums keep the
+// term order of the dense products, so dropping the structural zeros changes no bit.
 template <int N, int K>
-inline void kalman_update(double (&x)[N], double (&P)[N * N], const double (&H)[K * N], const double (&Rd)[K], const double (&zm)[K]) {
+inline void kalman_update(double (&x)[N], double (&P)[N * N], const int (&plus)[K], const int (&minus)[K], const double (&Rd)[K], const double (&zm)[K]) {
   double HP[K * N], S[K][2 * K], G[N * K];
-  for (int l = 0; l < K; l++) for (int j = 0; j < N; j++) { double a = 0; for (int q = 0; q < N; q++) a += H[l * N + q] * P[q * N + j]; HP[l * N + j] = a; }
-  for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) { double a = 0; for (int q = 0; q < N; q++) a += P[i * N + q] * H[j * N + q]; G[i * K + j] = a; }   // P H'
-  for (int i = 0; i < K; i++) for (int j = 0; j < K; j++) { double a = i == j ? Rd[i] : 0; for (int q = 0; q < N; q++) a += H[i * N + q] * G[q * K + j]; S[i][j] = a; S[i][K + j] = i == j; }
+  for (int l = 0; l < K; l++) for (int j = 0; j < N; j++) HP[l * N + j] = minus[l] < 0 ? P[plus[l] * N + j] : P[plus[l] * N + j] - P[minus[l] * N + j];
+  for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) G[i * K + j] = minus[j] < 0 ? P[i * N + plus[j]] : P[i * N + plus[j]] - P[i * N + minus[j]];   // P H'
+  for (int i = 0; i < K; i++) for (int j = 0; j < K; j++) { double a = (i == j ? Rd[i] : 0) + G[plus[i] * K + j]; if (minus[i] >= 0) a -= G[minus[i] * K + j]; S[i][j] = a; S[i][K + j] = i == j; }
   for (int c = 0; c < K; c++) {   // S is symmetric positive definite (R > 0): elimination without row exchanges
     const double inv = 1.0 / S[c][c];
     for (int j = 0; j < 2 * K; j++) S[c][j] *= inv;
@@ -85,15 +87,23 @@ inline void kalman_update(double (&x)[N], double (&P)[N * N], const double (&H)[
   }
   double Kg[N * K], inn[K];
   for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) { double a = 0; for (int l = 0; l < K; l++) a += G[i * K + l] * S[l][K + j]; Kg[i * K + j] = a; }
-  for (int j = 0; j < K; j++) { double a = zm[j]; for (int q = 0; q < N; q++) a -= H[j * N + q] * x[q]; inn[j] = a; }
+  for (int j = 0; j < K; j++) { double a = zm[j] - x[plus[j]]; if (minus[j] >= 0) a += x[minus[j]]; inn[j] = a; }
   for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) x[i] += Kg[i * K + j] * inn[j];
   for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double a = 0; for (int l = 0; l < K; l++) a += Kg[i * K + l] * HP[l * N + j]; P[i * N + j] -= a; }
 }
+// P <- A P A' + diag(Qd) for A = identity except A[0][1] = dt and row 1 = a1 (a1[1] = 1)
 template <int N>
-inline void kalman_predict_cov(double (&P)[N * N], const double (&A)[N * N], const double (&Qd)[N]) {
-  double T[N * N];
-  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double a = 0; for (int q = 0; q < N; q++) a += A[i * N + q] * P[q * N + j]; T[i * N + j] = a; }
-  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) { double a = i == j ? Qd[i] : 0; for (int q = 0; q < N; q++) a += T[i * N + q] * A[j * N + q]; P[i * N + j] = a; }
+inline void kalman_predict_cov(double (&P)[N * N], double dt, const double (&a1)[N], const double (&Qd)[N]) {
+  double T0[N], T1[N];   // rows 0 and 1 of A P; the other rows are P's
+  for (int j = 0; j < N; j++) { T0[j] = P[j] + dt * P[N + j]; double a = 0; for (int q = 0; q < N; q++) a += a1[q] * P[q * N + j]; T1[j] = a; }
+  for (int j = 0; j < N; j++) { P[j] = T0[j]; P[N + j] = T1[j]; }
+  for (int i = 0; i < N; i++) {   // (A P) A': columns 0 and 1 mix, the others only receive Q on the diagonal
+    const double *T = P + i * N;
+    double c1 = i == 1 ? Qd[1] : 0; for (int q = 0; q < N; q++) c1 += T[q] * a1[q];
+    const double c0 = ((i == 0 ? Qd[0] : 0) + T[0]) + T[1] * dt;
+    P[i * N] = c0; P[i * N + 1] = c1;
+    if (i >= 2) P[i * N + i] = Qd[i] + T[i];
+  }
 }
 
 struct EstimatorFilter {
@@ -120,26 +130,25 @@ struct EstimatorFilter {
       for (int i = 0; i < 25; i++) Pz[i] = (i % 6 == 0) ? 1e-6 : 0;
       terrain = 0; started = true;
     }
-    static constexpr double H6[24] = {1, 0, -1, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0}, R4[4] = {1e-6, 1e-6, 1e-6, 1};
+    static constexpr int plus6[4] = {0, 0, 4, 1}, minus6[4] = {2, 3, -1, -1};   // measurements p - footL, p - footR, w, v
+    static constexpr double R4[4] = {1e-6, 1e-6, 1e-6, 1};
     for (int ax = 0; ax < 2; ax++) {
       double (&x)[6] = xy[ax];
       const double zm[4] = {yL[ax], yR[ax], wm, x[1] + dt * aw[ax]}, Qd[6] = {1e-8, 1e-8, qL, qR, 1e-5, 1e-2}, p0 = x[0], v0 = x[1], wt = x[4];
-      double A[36] = {}; for (int i = 0; i < 6; i++) A[7 * i] = 1;
-      A[1] = dt;
-      if (contact) { A[6] = c; A[8] = -c * wt; A[9] = -c * (1 - wt); A[10] = -c * (x[2] - x[3]); A[11] = dt / mass;
+      double a1[6] = {0, 1, 0, 0, 0, 0};   // row 1 of the Jacobian
+      if (contact) { a1[0] = c; a1[2] = -c * wt; a1[3] = -c * (1 - wt); a1[4] = -c * (x[2] - x[3]); a1[5] = dt / mass;
                      x[1] = v0 + c * (p0 - wt * x[2] - (1 - wt) * x[3]) + dt / mass * x[5]; }
       x[0] = p0 + dt * v0;
-      kalman_predict_cov<6>(Pxy[ax], A, Qd);
-      kalman_update<6, 4>(x, Pxy[ax], H6, R4, zm);
+      kalman_predict_cov<6>(Pxy[ax], dt, a1, Qd);
+      kalman_update<6, 4>(x, Pxy[ax], plus6, minus6, R4, zm);
     }
     {
-      static constexpr double H5[10] = {1, 0, -1, 0, 0, 1, 0, 0, -1, 0}, R2[2] = {1e-6, 1e-6};
+      static constexpr int plus5[2] = {0, 0}, minus5[2] = {2, 3};
+      static constexpr double R2[2] = {1e-6, 1e-6}, a1[5] = {0, 1, 0, 0, dt / mass};
       const double zm[2] = {yL[2], yR[2]}, Qd[5] = {1e-8, 1e-8, qL, qR, 1e-2}, p0 = z[0], v0 = z[1];
-      double A[25] = {}; for (int i = 0; i < 5; i++) A[6 * i] = 1;
-      A[1] = dt; A[9] = dt / mass;
       z[0] = p0 + dt * v0; z[1] = v0 + dt / mass * z[4] + dt * (-grav - (fl + fr) / mass);
-      kalman_predict_cov<5>(Pz, A, Qd);
-      kalman_update<5, 2>(z, Pz, H5, R2, zm);
+      kalman_predict_cov<5>(Pz, dt, a1, Qd);
+      kalman_update<5, 2>(z, Pz, plus5, minus5, R2, zm);
     }
     if (contact) terrain = (terrain + dt * (z[0] - (wm * yL[2] + (1 - wm) * yR[2]))) / (1 + dt);
     for (int ax = 0; ax < 2; ax++) { pos[ax] = xy[ax][0]; vel[ax] = xy[ax][1]; ext_force[ax] = xy[ax][5]; }
