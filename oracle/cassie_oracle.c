@@ -14,11 +14,12 @@
  *     limit, pyramidal contact), PGS with warm start, sensors, implicit-damping Euler.
  *     This is a restatement of MuJoCo's published algorithm (Computation chapter + the
  *     open-sourced engine_*.c), specialised to the features the Cassie models use.
- *   - the closed Agility blocks pd_input_step (motor-PD branch) and cassie_core_sim_step
- *     (safety layer), include/pd_input.h:34, include/cassie_core_sim.h:34, from black-box
- *     probing.  With -DORACLE_USE_AGILITY_REF the real archive
- *     src/libagilitycassie.a is linked instead (oracle/_ref/liboracle_ref.so) and
- *     state_output_step is the real one.
+ *   - the closed Agility blocks pd_input_step (motor-PD and task-PD branches), cassie_core_sim_step
+ *     (safety layer) and state_output_step (estimator: leg kinematics, spring-force model, Kalman
+ *     filters), include/pd_input.h:34, include/cassie_core_sim.h:34, include/state_output.h:33-34,
+ *     from black-box probing and, for the filters, the block's own memory (SURVEY.md section
+ *     8a-2/8a-3/8a-8).  With -DORACLE_USE_AGILITY_REF the real archive src/libagilitycassie.a is
+ *     linked instead (oracle/_ref/liboracle_ref.so) and the three blocks are the real ones.
  *
  * PARITY STATUS: physics parity vs MuJoCo 2.1.0 is UNPINNED -- MuJoCo is absent from the build
  * container, the reference ships no golden trajectories.  The Agility-block
