@@ -166,3 +166,40 @@ def test_capacity_option_of_the_checker(oracle_mod):
         assert o.get_int('ncon') <= 2 and o.get_int('nefc') <= 20
         most = max(most, o.get_int('ncon'))
     assert most == 2 and o.get_int('dropped_contacts') > 0 and np.isfinite(o.arr('qpos')).all()
+
+
+def test_free_flight_conserves_momentum(oracle_mod):
+    """no gravity, no contact (model/cassie_no_grav.xml lifted off the floor): springs, joint limits, loop closures, rotor inertias, damping and
+    the PD motors are all internal forces, so the centre-of-mass velocity and the angular momentum about it stay put while the joints thrash.
+    A physics invariant that needs no reference trajectory; the queries mix one-sub-step-old kinematics with new velocities, hence O(h) noise."""
+    import emu_harness as E
+    rng = np.random.default_rng(1)
+    for pd in (False, True):
+        o = oracle_mod.OracleSim(os.path.join(GOLDEN, 'cassie_no_grav.omodel'))
+        e = E.EmuSim(os.path.join(REPO, 'cassie-mujoco-sim_b200', 'models', 'cassie_no_grav.cmodel'))
+        q, v = o.arr('qpos'), o.arr('qvel')
+        q[2] = 3.0
+        v[:] = rng.normal(0, 0.7, 32)
+        e.set('qpos', np.concatenate([q, np.zeros(len(e.get('qpos')) - 35)]))
+        e.set('qvel', v)
+        o.forward()
+        e.forward()
+        u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN) if pd else oracle_mod.make_pd()
+        row = np.concatenate([np.zeros(10), PD_TARGET, np.zeros(10), PD_PGAIN, PD_DGAIN]) if pd else np.zeros(50)
+        o.step_pd(u)
+        e.step(row)
+        cm0, L0, dev, dev_e = o.cm_velocity().copy(), o.angular_momentum().copy(), np.zeros(2), np.zeros(2)
+        j0, jpeak = o.arr('qpos')[7:35].copy(), 0.0
+        for k in range(400):
+            o.step_pd(u)
+            e.step(row)
+            dev = np.maximum(dev, [np.abs(o.cm_velocity() - cm0).max(), np.abs(o.angular_momentum() - L0).max()])
+            jpeak = max(jpeak, np.abs(o.arr('qpos')[7:35] - j0).max())
+            if k % 50 == 49:    # the kernel source's derived-quantity row says the same
+                e.query()
+                a = e.get('aux')
+                dev_e = np.maximum(dev_e, [np.abs(a[45:48] - cm0).max(), np.abs(a[48:51] - L0).max()])
+        assert len(o.contacts()) == 0 and jpeak > 0.05      # free flight, and the joints did move
+        assert np.abs(L0).max() > 0.5 and dev[0] < 2e-4 and dev[1] < 5e-3, (pd, cm0, L0, dev)
+        assert dev_e[0] < 2e-4 and dev_e[1] < 5e-3, (pd, dev_e)
+        e.close()
