@@ -203,3 +203,68 @@ def test_free_flight_conserves_momentum(oracle_mod):
         assert np.abs(L0).max() > 0.5 and dev[0] < 2e-4 and dev[1] < 5e-3, (pd, cm0, L0, dev)
         assert dev_e[0] < 2e-4 and dev_e[1] < 5e-3, (pd, dev_e)
         e.close()
+
+
+def test_half_and_quarter_turn_invariance(oracle_mod):
+    """the same start turned about the vertical by 180 or 90 degrees gives the same trajectory turned back (flat floor; the friction pyramid has
+    exactly that symmetry, an arbitrary heading does not): kinematics, Jacobians, collision frames, constraint rows and sensors agree on what
+    a rotation is.  Sliding touch-down under PD control, oracle and kernel source."""
+    import emu_harness as E
+
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+    u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    row = np.concatenate([np.zeros(10), PD_TARGET, np.zeros(10), PD_PGAIN, PD_DGAIN])
+
+    def run(yaw, n, emu):
+        c, s = np.cos(yaw), np.sin(yaw)
+        Rz, qz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]]), np.array([np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)])
+        o = oracle_mod.OracleSim(OMODEL)
+        q, v = o.arr('qpos').copy(), o.arr('qvel').copy()
+        q[0:3], q[3:7], v[0:3] = Rz @ [0.3, -0.2, q[2]], qmul(qz, q[3:7]), Rz @ [0.4, 0.1, 0.0]     # free joint: linear velocity in the world frame
+        if emu:
+            e = E.EmuSim(os.path.join(REPO, 'cassie-mujoco-sim_b200', 'models', 'cassie.cmodel'))
+            e.set('qpos', q)
+            e.set('qvel', v)
+            e.forward()
+            for k in range(n):
+                e.step(row)
+            q, v, ncon = e.get('qpos')[:35].copy(), e.get('qvel')[:32].copy(), int(e.get('counters')[1])
+            e.close()
+        else:
+            o.arr('qpos')[:], o.arr('qvel')[:] = q, v
+            o.forward()
+            for k in range(n):
+                o.step_pd(u)
+            q, v, ncon = o.arr('qpos').copy(), o.arr('qvel').copy(), len(o.contacts())
+        q[0:3], q[3:7], v[0:3] = Rz.T @ q[0:3], qmul(qz * [1, 1, 1, -1], q[3:7]), Rz.T @ v[0:3]
+        return q, v, ncon
+    for emu in (False, True):
+        q0, v0, ncon = run(0.0, 400, emu)
+        assert ncon >= 2 and abs(q0[0] - 0.3) > 0.01                      # it landed and slid
+        for yaw, tol in ((np.pi, 1e-11), (np.pi / 2, 1e-6)):               # the quarter turn permutes the pyramid's rows: Gauss-Seidel order noise
+            q1, v1, _ = run(yaw, 400, emu)
+            assert np.abs(q1 - q0).max() < tol and np.abs(v1 - v0).max() < 100 * tol, (emu, yaw, np.abs(q1 - q0).max(), np.abs(v1 - v0).max())
+
+
+def test_free_fall_is_ballistic(oracle_mod):
+    """gravity on, no contact: the centre of mass falls with g (MuJoCo's default 9.81, model/cassie.xml sets none) whatever the joints do, its
+    horizontal velocity and the angular momentum about it stay put"""
+    rng = np.random.default_rng(2)
+    o = oracle_mod.OracleSim(OMODEL)
+    q, v = o.arr('qpos'), o.arr('qvel')
+    q[2] = 4.0
+    v[:] = rng.normal(0, 0.7, 32)
+    o.forward()
+    u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    o.step_pd(u)
+    cm0, L0, t0 = o.cm_velocity().copy(), o.angular_momentum().copy(), float(o.arr('time')[0])
+    worst = np.zeros(3)
+    for k in range(300):
+        o.step_pd(u)
+        t = float(o.arr('time')[0]) - t0
+        cm = o.cm_velocity()
+        worst = np.maximum(worst, [np.abs(cm[:2] - cm0[:2]).max(), abs(cm[2] - (cm0[2] - 9.81 * t)), np.abs(o.angular_momentum() - L0).max()])
+    assert len(o.contacts()) == 0 and t == pytest.approx(0.15)
+    assert worst[0] < 2e-4 and worst[1] < 2e-4 and worst[2] < 5e-3, worst
