@@ -65,3 +65,39 @@ def test_batch_filters_follow_each_environment():
         assert (np.abs(_filtered(ys[e]) - want) / (1 + np.abs(want))).max() < 1e-6, e
     assert np.array_equal(_filtered(ys[0]), _filtered(ys[1]))
     assert (np.abs(_filtered(ys[2]) - want) / (1 + np.abs(want))).max() > 1e-3   # environment 2 restarted its filters at call 150
+
+
+def test_turn_invariance_at_full_size():
+    """BASELINE config 2 size, fp64: every environment starts from the same sliding touch-down turned about the vertical by a multiple of 90
+    degrees; turned back, all trajectories coincide (exactly the symmetry group of the friction pyramid; CPU twin of this property for the
+    oracle and the kernel source: tests/test_oracle.py::test_half_and_quarter_turn_invariance)"""
+    P = product()
+    n = 4096
+    b = P.CassieBatch(n, precision=P.FP64)
+    q, v = b.qpos(), b.qvel()
+    k = np.arange(n) % 4
+    yaw = k * (np.pi / 2)
+    c, s = np.round(np.cos(yaw)), np.round(np.sin(yaw))                       # exact quarter turns
+    p0, v0 = np.array([0.3, -0.2]), np.array([0.4, 0.1])
+    q[:, 0], q[:, 1] = c * p0[0] - s * p0[1], s * p0[0] + c * p0[1]
+    v[:, 0], v[:, 1] = c * v0[0] - s * v0[1], s * v0[0] + c * v0[1]
+    qz = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], axis=1)
+
+    def qmul(a, r):
+        return np.stack([a[:, 0] * r[:, 0] - a[:, 1] * r[:, 1] - a[:, 2] * r[:, 2] - a[:, 3] * r[:, 3], a[:, 0] * r[:, 1] + a[:, 1] * r[:, 0] + a[:, 2] * r[:, 3] - a[:, 3] * r[:, 2],
+                         a[:, 0] * r[:, 2] - a[:, 1] * r[:, 3] + a[:, 2] * r[:, 0] + a[:, 3] * r[:, 1], a[:, 0] * r[:, 3] + a[:, 1] * r[:, 2] - a[:, 2] * r[:, 1] + a[:, 3] * r[:, 0]], axis=1)
+    q[:, 3:7] = qmul(qz, q[:, 3:7])
+    b.set_qpos(q)
+    b.set_qvel(v)
+    b.forward()
+    b.set_pd(P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
+    b.step(400)
+    q = b.qpos()
+    x, y = q[:, 0].copy(), q[:, 1].copy()
+    q[:, 0], q[:, 1] = c * x + s * y, -s * x + c * y                          # turned back
+    q[:, 3:7] = qmul(qz * [1, 1, 1, -1], q[:, 3:7])
+    ref = q[0]
+    assert abs(ref[0] - 0.3) > 0.01 and (b.counters()[:, 1] >= 2).all()       # it landed and slid, everywhere
+    for kk, tol in ((0, 0.0), (2, 1e-10), (1, 1e-6), (3, 1e-6)):              # same heading: bitwise; half turn: rounding; quarter turns: row-order noise
+        d = np.abs(q[k == kk] - ref).max()
+        assert d <= tol, (kk, d)
