@@ -268,3 +268,27 @@ def test_free_fall_is_ballistic(oracle_mod):
         worst = np.maximum(worst, [np.abs(cm[:2] - cm0[:2]).max(), abs(cm[2] - (cm0[2] - 9.81 * t)), np.abs(o.angular_momentum() - L0).max()])
     assert len(o.contacts()) == 0 and t == pytest.approx(0.15)
     assert worst[0] < 2e-4 and worst[1] < 2e-4 and worst[2] < 5e-3, worst
+
+
+def test_constraint_forces_satisfy_the_kkt_conditions(oracle_mod):
+    """the constraint solve minimises 1/2 f'(A + R) f + f'b with f free on the equality rows and f >= 0 on limit and pyramid rows (MuJoCo's dual
+    problem).  At the solver's exit the gradient g = (A + R) f + b vanishes on equality rows and active rows and is non-negative on rows at
+    zero force -- to the solver's own stopping tolerance, relative to |b|.  Independent of how the solution was reached."""
+    o = oracle_mod.OracleSim(OMODEL)
+    u = oracle_mod.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    seen_contact = seen_inactive = 0
+    for k in range(450):
+        o.step_pd(u)
+        if k % 25 != 24:
+            continue
+        n, ne = o.get_int('nefc'), o.get_int('ne')
+        AR, b, f = o.arr('efc_AR')[:n * n].reshape(n, n), o.arr('efc_b')[:n], o.arr('efc_force')[:n]
+        g, scale = AR @ f + b, np.abs(b).max()
+        assert np.abs(AR - AR.T).max() < 1e-9 * np.abs(AR).max() and np.linalg.eigvalsh(AR).min() > 0      # A + R symmetric positive definite
+        assert np.abs(g[:ne]).max() < 2e-4 * scale, (k, np.abs(g[:ne]).max(), scale)
+        if n > ne:
+            fi, gi = f[ne:], g[ne:]
+            assert fi.min() >= 0 and gi.min() > -2e-4 * scale and np.abs(gi[fi > 0]).max(initial=0.0) < 2e-4 * scale, (k, fi.min(), gi.min(), scale)
+            seen_contact += 1
+            seen_inactive += int((fi == 0).any())
+    assert seen_contact >= 10
