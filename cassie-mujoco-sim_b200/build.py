@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcassie_b200.so')
 SRCS = [os.path.join(CSRC, 'cassie_b200.cu'), os.path.join(CSRC, 'mjcf.cpp')]
-DEPS = SRCS + [os.path.join(CSRC, f) for f in ('step_core.inl', 'devmodel.h', 'devbuild.h', 'model.h')] + [
+DEPS = SRCS + [os.path.join(CSRC, f) for f in ('step_core.inl', 'devmodel.h', 'devbuild.h', 'model.h', 'estimator_host.h', 'legacy_stubs.inc')] + [
     os.path.join(HERE, '..', 'include', 'cassie_b200.h'), os.path.join(HERE, '..', 'include', 'cassie_bus.h')]
 
 

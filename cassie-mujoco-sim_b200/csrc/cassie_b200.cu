@@ -753,4 +753,13 @@ void cassie_sim_full_reset(cassie_sim_t *c) {
   c->b->impl->reset_estimator(nullptr);   // state_output_setup (src/cassiemujoco.c:2032) restarts the estimator's filters
   sim_pull(c);
 }
+// sizes the reference's Python wrapper asks for (src/cassiemujoco.c:1038-1060)
+int cassie_sim_nbody(const cassie_sim_t *c) { return c->b->impl->hm.nbody; }
+int cassie_sim_ngeom(const cassie_sim_t *c) { return c->b->impl->hm.ngeom; }
+int cassie_sim_njnt(const cassie_sim_t *c) { return c->b->impl->hm.njnt; }
+int cassie_sim_nu(const cassie_sim_t *c) { return c->b->impl->hm.nu; }
+// src/cassiemujoco.c:1183-1189: qpos += h * qvel on the joint manifold; the reference then feeds an uninitialised cassie_out_t to its estimator,
+// so *y carries no information there -- it is zeroed here
+void cassie_integrate_pos(cassie_sim_t *c, state_out_t *y) { sim_push(c); cassie_batch_integrate_pos(c->b); c->b->impl->sync(); sim_pull(c); if (y) memset(y, 0, sizeof *y); }
+#include "legacy_stubs.inc"
 }  // extern "C"

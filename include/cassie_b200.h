@@ -46,6 +46,17 @@ void cassie_sim_apply_force(cassie_sim_t *sim, double xfrc[6], const char *name)
 void cassie_sim_clear_forces(cassie_sim_t *sim);
 /* include/cassiemujoco.h:281 (src/cassiemujoco.c:2008-2033) */
 void cassie_sim_full_reset(cassie_sim_t *sim);
+/* sizes the reference's Python wrapper asks for (src/cassiemujoco.c:1038-1060) and qpos += h qvel (src/cassiemujoco.c:1183-1189; *y is zeroed: the
+ * reference runs its estimator on an uninitialised cassie_out_t there) */
+int cassie_sim_nbody(const cassie_sim_t *sim);
+int cassie_sim_ngeom(const cassie_sim_t *sim);
+int cassie_sim_njnt(const cassie_sim_t *sim);
+int cassie_sim_nu(const cassie_sim_t *sim);
+void cassie_integrate_pos(cassie_sim_t *sim, state_out_t *y);
+/* Import compatibility: the library also exports, as stubs, the 133 further names example/cassiemujoco_ctypes.py resolves at import time
+ * (cassie_vis_*, UDP, pack / unpack, pd_input_* / cassie_core_sim_* / state_output_* host objects, mjModel / mjData accessors, ...;
+ * csrc/legacy_stubs.inc, list in tests/golden/ctypes_bound_names.txt).  They are outside the accelerated path: a call records an error
+ * (cassie_b200_last_error), prints it and returns 0 / NULL.  They are deliberately not declared here. */
 /* include/cassiemujoco.h:317-329 (src/cassiemujoco.c:2050-2080): height-field terrain of cassie_hfield.xml; nrow*ncol floats in [0,1],
  * row-major, row <-> y, column <-> x.  cassie_sim_hfielddata returns a borrowed read-write host mirror uploaded before the next step. */
 int cassie_sim_get_hfield_nrow(cassie_sim_t *sim);

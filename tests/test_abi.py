@@ -123,3 +123,29 @@ int main(void) {
         subprocess.check_call(['gcc', '-std=c11', '-I', inc, str(src), '-o', exe])
         outs.append(subprocess.check_output([exe], text=True))
     assert outs[0] == outs[1] and 'sizes 952 992 1336' in outs[0], outs
+
+
+def test_every_name_the_reference_binding_resolves_is_exported(tmp_path):
+    """example/cassiemujoco_ctypes.py resolves 187 names at import time; a missing one makes `import cassiemujoco` raise.  The
+    list is committed (tests/golden/ctypes_bound_names.txt, tools/gen_legacy_stubs.py); with the reference checkout present the binding module
+    itself is imported against the product library.  Names outside the accelerated path are stubs that fail at the call, loudly."""
+    import ctypes as C
+    import subprocess
+    import sys
+    names = open(os.path.join(REPO, 'tests', 'golden', 'ctypes_bound_names.txt')).read().split()
+    assert len(names) == 187
+    lib = os.path.join(REPO, 'cassie-mujoco-sim_b200', 'libcassie_b200.so')
+    exported = {ln.split()[-1] for ln in subprocess.check_output(['nm', '-D', '--defined-only', lib], text=True).splitlines()}
+    assert not [n for n in names if n not in exported]
+    L = C.CDLL(lib)
+    L.cassie_vis_init.restype = C.c_void_p
+    L.cassie_b200_last_error.restype = C.c_char_p
+    assert L.cassie_vis_init(None, b'x') is None and b'cassie_vis_init' in L.cassie_b200_last_error()      # a stub: NULL and a recorded error
+    L.cassie_vis_free(None)                                                                                # releasing nothing stays silent
+    if have_reference():
+        for f in ('cassiemujoco_ctypes.py',):
+            (tmp_path / f).write_text(open(os.path.join(REFERENCE, 'example', f)).read())
+        os.symlink(lib, tmp_path / 'libcassiemujoco.so')
+        code = 'import cassiemujoco_ctypes as m; print(len([n for n in dir(m) if n.startswith("cassie_sim_")]))'
+        out = subprocess.check_output([sys.executable, '-c', code], cwd=tmp_path, text=True)
+        assert int(out.strip()) > 90
