@@ -21,9 +21,12 @@
  *     8a-2/8a-3/8a-8).  With -DORACLE_USE_AGILITY_REF the real archive src/libagilitycassie.a is
  *     linked instead (oracle/_ref/liboracle_ref.so) and the three blocks are the real ones.
  *
- * PARITY STATUS: physics parity vs MuJoCo 2.1.0 is UNPINNED -- MuJoCo is absent from the build
- * container, the reference ships no golden trajectories.  The Agility-block
- * twins ARE pinned against the archive (tests/test_agility_twins.py).
+ * PARITY STATUS: "parity unpinned" for the physics -- no MuJoCo of any version is reachable on the
+ * build container or on the GPU box (tools/probe_reference.py; committed logs
+ * profiles/r2_probe_reference_{build_container,gpu_box}.json), and the reference ships no golden
+ * trajectories.  tests/test_mujoco_parity.py diffs this file stage by stage
+ * against a real MuJoCo the day one is importable.  The Agility-block twins ARE pinned against the
+ * archive (tests/test_agility_twins.py).
  */
 #include <math.h>
 #include <stdio.h>
