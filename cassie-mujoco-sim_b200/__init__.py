@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcassie_b200.so')
 MODEL_DIR = os.path.join(_HERE, 'models')
 FP32, FP64 = 0, 1
-PD_WIDTH, OBS_WIDTH, AUX_WIDTH = 52, 96, 64
+PD_WIDTH, OBS_WIDTH, AUX_WIDTH, EST_WIDTH = 52, 96, 64, 16
 # slices of a derived-quantity row (CASSIE_AUX_* in include/cassie_b200.h)
 AUX = dict(foot_force=slice(0, 12), toe_force=slice(12, 18), heel_force=slice(18, 24), foot_pos=slice(24, 30), foot_vel=slice(30, 42),
            cm_pos=slice(42, 45), cm_vel=slice(45, 48), angmom=slice(48, 51), obstacle=51, self_collision=52, group_mask=53, ncon=54)
@@ -160,6 +160,10 @@ def lib():
     L.cassie_batch_enable_estimator_filter.restype = ci
     L.cassie_batch_reset_estimator.argtypes = [vp, C.c_void_p]
     L.cassie_batch_reset_estimator.restype = ci
+    L.cassie_batch_enable_estimator_device.argtypes = [vp, ci]
+    L.cassie_batch_enable_estimator_device.restype = ci
+    L.cassie_batch_get_estimator.argtypes = [vp, cd]
+    L.cassie_batch_get_estimator.restype = ci
     L.cassie_batch_set_task_pd.argtypes = [vp, cd]
     L.cassie_batch_set_task_pd.restype = ci
     L.cassie_batch_get_aux.argtypes = [vp, cd]
@@ -325,6 +329,18 @@ class CassieBatch:
     def enable_estimator(self, forces=True, filters=True):
         self.L.cassie_batch_enable_estimator_forces(self.h, 1 if (forces or filters) else 0)
         self.L.cassie_batch_enable_estimator_filter(self.h, 1 if filters else 0)
+
+    def enable_estimator_device(self, on=True):
+        """the estimator inside the step kernel: estimator() rows follow every tick of every launch"""
+        if self.L.cassie_batch_enable_estimator_device(self.h, 1 if on else 0) != 0:
+            raise RuntimeError(_last_error())
+
+    def estimator(self):
+        """[n, 16]: position 3, translationalVelocity 3, externalForce 3, terrain.height, toeForce L 3, R 3"""
+        out = np.zeros((self.n, EST_WIDTH))
+        if self.L.cassie_batch_get_estimator(self.h, self._dp(out)) != 0:
+            raise RuntimeError(_last_error())
+        return out
 
     def reset_estimator(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)

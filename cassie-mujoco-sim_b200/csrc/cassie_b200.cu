@@ -26,7 +26,7 @@ static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *est_out; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * 2 * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
     E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on;
+    E.est = A.est ? A.est + (size_t)env * EST_W : nullptr; E.est_out = A.est ? A.est_out + (size_t)env * EO_W : nullptr;
     step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
     if (mode >= 2) continue;   // query / set_const: only the aux row / the constant row is written
@@ -204,6 +205,8 @@ struct BatchBase {
   virtual bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) = 0;
   virtual bool set_hfield(const float *data, int n_terrains) = 0;
   virtual bool enable_aux(bool on) = 0;
+  virtual bool enable_estimator_device(bool on) = 0;   // leg forces + filters inside the step kernel (extended instance), every 2 kHz tick
+  virtual bool reset_estimator_device(const unsigned char *mask) = 0;
   virtual bool set_task_pd(const double *rows) = 0;   // [n][60] or null (off)
   virtual bool set_model_rows(const char *what, const double *rows, int width) = 0;   // per-env model constants (domain randomisation)
   virtual bool get_model_rows(const char *what, double *rows, int width) = 0;
@@ -221,7 +224,7 @@ template <typename real> struct Batch : BatchBase {
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(A.task); if (pin_task) cudaFreeHost(pin_task); cudaFree(d_mask); cudaFree(d_row);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(A.task); cudaFree(A.est); cudaFree(A.est_out); if (pin_task) cudaFreeHost(pin_task); cudaFree(d_mask); cudaFree(d_row);
     if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -453,6 +456,23 @@ template <typename real> struct Batch : BatchBase {
     return true;
   }
   bool has_aux() const override { return A.aux != nullptr; }
+  bool enable_estimator_device(bool on) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (on && !A.est) {
+      CUDA_OK(cudaMalloc(&A.est, sizeof(double) * n * EST_W)); CUDA_OK(cudaMalloc(&A.est_out, sizeof(real) * n * EO_W));
+      CUDA_OK(cudaMemsetAsync(A.est, 0, sizeof(double) * n * EST_W, stream)); CUDA_OK(cudaMemsetAsync(A.est_out, 0, sizeof(real) * n * EO_W, stream));
+    }
+    if (!on && A.est) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.est)); CUDA_OK(cudaFree(A.est_out)); A.est = nullptr; A.est_out = nullptr; }
+    return true;
+  }
+  bool reset_estimator_device(const unsigned char *mask) override {   // started flag (and everything else) back to zero: the filters start again at the next tick
+    if (!A.est) return true;
+    CUDA_OK(cudaSetDevice(device));
+    if (!mask) { CUDA_OK(cudaMemsetAsync(A.est, 0, sizeof(double) * n * EST_W, stream)); return true; }
+    if (!upload_mask(mask)) return false;
+    const std::vector<double> zero(EST_W, 0.0);
+    return fill_masked(A.est, zero.data(), EST_W);
+  }
   // task-space PD rows (pd_in_t taskPd of both legs); NULL switches the branch off again
   bool set_task_pd(const double *rows) override {
     CUDA_OK(cudaSetDevice(device));
@@ -469,7 +489,7 @@ template <typename real> struct Batch : BatchBase {
     const LaunchCfg &c = cfg[(A.cenv || A.aux || A.task) ? 1 : 0];
     int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
-    if (A.cenv || A.aux || A.task) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
+    if (A.cenv || A.aux || A.task || A.est) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
     else cassie_step_kernel<real, false><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
     launches++;
     CUDA_OK(cudaGetLastError());
@@ -501,6 +521,7 @@ template <typename real> struct Batch : BatchBase {
     if (!strcmp(f, "time")) return d2h(A.cst, CST_W, 1, CS_TIME, out);
     if (!strcmp(f, "obs")) return d2h(A.obs, OBS_W, OBS_W, 0, out);
     if (!strcmp(f, "cst")) return d2h(A.cst, CST_W, CST_W, 0, out);
+    if (!strcmp(f, "est_out")) { if (!A.est) { set_err("the in-kernel estimator is not enabled (cassie_batch_enable_estimator_device)"); return false; } return d2h(A.est_out, EO_W, EO_W, 0, out); }
     if (!strcmp(f, "aux")) { if (!A.aux) { set_err("derived quantities are not enabled (cassie_batch_enable_aux)"); return false; } return d2h(A.aux, AUX_W, AUX_W, 0, out); }
     set_err(std::string("unknown field ") + f); return false;
   }
@@ -529,7 +550,7 @@ template <typename real> struct Batch : BatchBase {
   }
   void *dev_ptr(const char *f) override {
     if (!strcmp(f, "qpos")) return A.qpos; if (!strcmp(f, "qvel")) return A.qvel; if (!strcmp(f, "pd")) return A.pd; if (!strcmp(f, "obs")) return A.obs;
-    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux; if (!strcmp(f, "task")) return A.task;
+    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux; if (!strcmp(f, "task")) return A.task; if (!strcmp(f, "est_out")) return A.est_out;
     return nullptr;
   }
   bool get_counters(int *out) override {
@@ -585,10 +606,10 @@ int cassie_batch_nv(const cassie_batch_t *b) { return b->impl->hm.nv; }
 int cassie_batch_precision(const cassie_batch_t *b) { return b->impl->precision; }
 int cassie_batch_row_width(const cassie_batch_t *b, const char *field) {
   if (!strcmp(field, "qpos")) return b->impl->hm.nq > 36 ? QPOS_W_XB : QPOS_W_MAIN; if (!strcmp(field, "qvel")) return b->impl->hm.nv > 32 ? QVEL_W_XB : QVEL_W_MAIN;
-  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; if (!strcmp(field, "aux")) return AUX_W; return -1;
+  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; if (!strcmp(field, "aux")) return AUX_W; if (!strcmp(field, "est_out")) return EO_W; return -1;
 }
 long cassie_batch_launch_count(const cassie_batch_t *b) { return b->impl->launches; }
-void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); b->impl->reset_estimator(mask); }   // a fresh cassie_sim_t has a fresh estimator
+void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); b->impl->reset_estimator(mask); b->impl->reset_estimator_device(mask); }   // a fresh cassie_sim_t has a fresh estimator
 void cassie_batch_set_pd(cassie_batch_t *b, const double *pd) { b->impl->set_pd(pd); }
 void cassie_batch_step(cassie_batch_t *b, int nticks) { if (nticks > 0) b->impl->step(nticks, 0); }
 void cassie_batch_forward(cassie_batch_t *b) { b->impl->step(0, 1); }
@@ -614,7 +635,7 @@ int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows) { return b->
 int cassie_batch_enable_estimator_forces(cassie_batch_t *b, int on) { b->impl->est_forces = on != 0; return 0; }
 void cassie_b200_estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) { estimator_leg_force(side, ang, quat, force); }
 int cassie_batch_enable_estimator_filter(cassie_batch_t *b, int on) { b->impl->est_filter = on != 0; if (on) b->impl->est_forces = true; else b->impl->est_state.clear(); return 0; }
-int cassie_batch_reset_estimator(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset_estimator(mask); return 0; }
+int cassie_batch_reset_estimator(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset_estimator(mask); return b->impl->reset_estimator_device(mask) ? 0 : -1; }
 // the same filters as a plain host object (no GPU involved): what the unpack loop above runs per environment
 void *cassie_b200_estimator_filter_new(void) { return new cassie::EstimatorFilter(); }
 void cassie_b200_estimator_filter_free(void *f) { delete static_cast<cassie::EstimatorFilter *>(f); }
@@ -625,6 +646,8 @@ void cassie_b200_estimator_filter_step(void *f, state_out_t *y) {
 }
 int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
 int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
+int cassie_batch_enable_estimator_device(cassie_batch_t *b, int on) { return b->impl->enable_estimator_device(on != 0) ? 0 : -1; }
+int cassie_batch_get_estimator(cassie_batch_t *b, double *out) { return b->impl->get("est_out", out) ? 0 : -1; }
 int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }
 int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *body_name) {
   int id = body_name ? b->impl->hm.body_id(body_name) : -1;

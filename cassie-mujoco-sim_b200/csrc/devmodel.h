@@ -107,6 +107,12 @@ constexpr int OB_FOOT = 60;       // [2][13] per foot: position 3, orientation 4
 constexpr int OB_EST_QUAT = 86;   // [4] pelvis.orientation (IMU quaternion through its rotation matrix and back: +-q)
 
 // derived-quantity row (optional, cassie_batch_enable_aux): the reference's read-only queries (src/cassiemujoco.c:1586-1961) as by-products
+// in-kernel estimator (optional, extended instance): per environment a row of doubles with the filter state (doubles in every precision: the
+// covariance recursion is the reference's unsymmetrised one and needs them) and a row of reals with its outputs
+constexpr int EST_W = 128;      // doubles: [0] started, [1..42] x axis (state 6, covariance 36), [43..84] y axis, [85..89] z state, [90..114] z covariance,
+constexpr int ES_X = 1, ES_Z = 85, ES_PZ = 90, ES_TERRAIN = 115, ES_FORCE = 116;   // [115] terrain, [116..121] leg forces (toeForce of each foot, double)
+constexpr int EO_W = 16;        // reals: pelvis.position 3, translationalVelocity 3, externalForce 3, terrain.height 1, toeForce (= heelForce) L 3, R 3
+constexpr int EO_POS = 0, EO_VEL = 3, EO_EXTF = 6, EO_TERRAIN = 9, EO_TOE = 10;
 constexpr int AUX_W = 64;
 constexpr int AX_FOOT_FORCE = 0;                    // [12] cassie_sim_foot_forces: left xyz, 3 zeros, right xyz, 3 zeros
 constexpr int AX_TOE_FORCE = 12, AX_HEEL_FORCE = 18; // [6] [6] cassie_sim_heeltoe_forces: left xyz, right xyz

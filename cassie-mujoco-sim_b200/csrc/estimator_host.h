@@ -10,22 +10,27 @@
 // foot point w.r.t. the two spring deflections under that closure.  The archive evaluates this in single precision; agreement ~1e-4 relative.
 #pragma once
 #include <cmath>
+#ifdef __CUDACC__
+#define CASSIE_HD __host__ __device__
+#else
+#define CASSIE_HD
+#endif
 
 namespace cassie {
 
 struct V3 { double x, y, z; };
-inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
-inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline V3 crs(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+CASSIE_HD inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+CASSIE_HD inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+CASSIE_HD inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+CASSIE_HD inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+CASSIE_HD inline V3 crs(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 struct M3 { V3 c0, c1, c2; };   // columns
-inline V3 operator*(const M3 &m, V3 v) { return v.x * m.c0 + v.y * m.c1 + v.z * m.c2; }
-inline M3 operator*(const M3 &a, const M3 &b) { return {a * b.c0, a * b.c1, a * b.c2}; }
-inline M3 rotz(double t) { const double c = std::cos(t), s = std::sin(t); return {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; }
+CASSIE_HD inline V3 operator*(const M3 &m, V3 v) { return v.x * m.c0 + v.y * m.c1 + v.z * m.c2; }
+CASSIE_HD inline M3 operator*(const M3 &a, const M3 &b) { return {a * b.c0, a * b.c1, a * b.c2}; }
+CASSIE_HD inline M3 rotz(double t) { const double c = std::cos(t), s = std::sin(t); return {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; }
 
 // ang: hipRoll, hipYaw, hipPitch, knee (motor positions), shin, tarsus (joint encoders), foot (motor position); quat: IMU quaternion (w, x, y, z)
-inline void estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) {
+CASSIE_HD inline void estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) {
   const double sg = side ? -1.0 : 1.0, kn = ang[3], sh = ang[4], ta = ang[5];
   // ---- planar part in the hip-pitch frame (z = common axis of knee, shin, tarsus): the four-bar closure
   const V3 A{0, 0, 0.045 * sg}, k0{0.12, 0, 0.0045 * sg}, o4{0.06068, 0.04741, 0}, o5{0.43476, 0.02, 0}, hsp{-0.01269, -0.03059, 0.00092 * sg}, Bl{0.11877, -0.01, 0}, ez{0, 0, 1};
@@ -75,7 +80,7 @@ inline void estimator_leg_force(int side, const double ang[7], const double quat
 // Measurement rows are differences of two states or single states: row l = e_plus[l] - e_minus[l] (minus < 0: none), R diagonal.  The sums keep the
 // term order of the dense products, so dropping the structural zeros changes no bit.
 template <int N, int K>
-inline void kalman_update(double (&x)[N], double (&P)[N * N], const int (&plus)[K], const int (&minus)[K], const double (&Rd)[K], const double (&zm)[K]) {
+CASSIE_HD inline void kalman_update(double *x, double *P, const int *plus, const int *minus, const double *Rd, const double *zm) {
   double HP[K * N], S[K][2 * K], G[N * K];
   for (int l = 0; l < K; l++) for (int j = 0; j < N; j++) HP[l * N + j] = minus[l] < 0 ? P[plus[l] * N + j] : P[plus[l] * N + j] - P[minus[l] * N + j];
   for (int i = 0; i < N; i++) for (int j = 0; j < K; j++) G[i * K + j] = minus[j] < 0 ? P[i * N + plus[j]] : P[i * N + plus[j]] - P[i * N + minus[j]];   // P H'
@@ -93,7 +98,7 @@ inline void kalman_update(double (&x)[N], double (&P)[N * N], const int (&plus)[
 }
 // P <- A P A' + diag(Qd) for A = identity except A[0][1] = dt and row 1 = a1 (a1[1] = 1)
 template <int N>
-inline void kalman_predict_cov(double (&P)[N * N], double dt, const double (&a1)[N], const double (&Qd)[N]) {
+CASSIE_HD inline void kalman_predict_cov(double *P, double dt, const double *a1, const double *Qd) {
   double T0[N], T1[N];   // rows 0 and 1 of A P; the other rows are P's
   for (int j = 0; j < N; j++) { T0[j] = P[j] + dt * P[N + j]; double a = 0; for (int q = 0; q < N; q++) a += a1[q] * P[q * N + j]; T1[j] = a; }
   for (int j = 0; j < N; j++) { P[j] = T0[j]; P[N + j] = T1[j]; }
@@ -106,6 +111,47 @@ inline void kalman_predict_cov(double (&P)[N * N], double dt, const double (&a1)
   }
 }
 
+// One call of the three filters is written axis by axis: an axis only touches its own state, so on the device three lanes run them side by side.
+// The contact terms derived from the two leg forces are shared.
+struct EstimatorContact { bool contact; double fl, fr, wm, qL, qR; };
+CASSIE_HD inline EstimatorContact estimator_contact(double FLz, double FRz) {
+  EstimatorContact k; k.fl = FLz < 0 ? FLz : 0; k.fr = FRz < 0 ? FRz : 0; k.contact = -(k.fl + k.fr) > 1.0;
+  k.wm = k.contact ? k.fl / (k.fl + k.fr) : 0.5; k.qL = FLz < -50 ? 1e-10 : 1e-6; k.qR = FRz < -50 ? 1e-10 : 1e-6; return k;
+}
+constexpr double EST_DT = 0.0005, EST_MASS = 31.0, EST_GRAV = 9.806;
+CASSIE_HD inline void estimator_axis_start_xy(double *x, double *P, double yL, double yR) {   // the block's own start: pelvis at 0, the foot states at +y (sic), weight 1/2
+  const double x0[6] = {0, 0, yL, yR, 0.5, 0}; for (int i = 0; i < 6; i++) x[i] = x0[i];
+  for (int i = 0; i < 36; i++) P[i] = (i % 7 == 0) ? 1e-6 : 0;
+}
+CASSIE_HD inline void estimator_axis_start_z(double *z, double *P, double yL, double yR) {    // ... and the whole weight on the external force
+  const double z0[5] = {0, 0, yL, yR, EST_MASS * EST_GRAV}; for (int i = 0; i < 5; i++) z[i] = z0[i];
+  for (int i = 0; i < 25; i++) P[i] = (i % 6 == 0) ? 1e-6 : 0;
+}
+CASSIE_HD inline void estimator_axis_xy(double *x, double *P, double yL, double yR, double a, const EstimatorContact &k) {
+  const double dt = EST_DT, c = EST_DT * EST_GRAV;
+  const int plus6[4] = {0, 0, 4, 1}, minus6[4] = {2, 3, -1, -1};   // measurements p - footL, p - footR, w, v
+  const double R4[4] = {1e-6, 1e-6, 1e-6, 1};
+  const double zm[4] = {yL, yR, k.wm, x[1] + dt * a}, Qd[6] = {1e-8, 1e-8, k.qL, k.qR, 1e-5, 1e-2}, p0 = x[0], v0 = x[1], wt = x[4];
+  double a1[6] = {0, 1, 0, 0, 0, 0};   // row 1 of the Jacobian
+  if (k.contact) { a1[0] = c; a1[2] = -c * wt; a1[3] = -c * (1 - wt); a1[4] = -c * (x[2] - x[3]); a1[5] = dt / EST_MASS;
+                   x[1] = v0 + c * (p0 - wt * x[2] - (1 - wt) * x[3]) + dt / EST_MASS * x[5]; }
+  x[0] = p0 + dt * v0;
+  kalman_predict_cov<6>(P, dt, a1, Qd);
+  kalman_update<6, 4>(x, P, plus6, minus6, R4, zm);
+}
+CASSIE_HD inline void estimator_axis_z(double *z, double *P, double yL, double yR, const EstimatorContact &k) {
+  const double dt = EST_DT;
+  const int plus5[2] = {0, 0}, minus5[2] = {2, 3};
+  const double R2[2] = {1e-6, 1e-6}, a1[5] = {0, 1, 0, 0, dt / EST_MASS};
+  const double zm[2] = {yL, yR}, Qd[5] = {1e-8, 1e-8, k.qL, k.qR, 1e-2}, p0 = z[0], v0 = z[1];
+  z[0] = p0 + dt * v0; z[1] = v0 + dt / EST_MASS * z[4] + dt * (-EST_GRAV - (k.fl + k.fr) / EST_MASS);
+  kalman_predict_cov<5>(P, dt, a1, Qd);
+  kalman_update<5, 2>(z, P, plus5, minus5, R2, zm);
+}
+CASSIE_HD inline double estimator_terrain(double terrain, double pz, double yLz, double yRz, const EstimatorContact &k) {
+  return k.contact ? (terrain + EST_DT * (pz - (k.wm * yLz + (1 - k.wm) * yRz))) / (1 + EST_DT) : terrain;
+}
+
 struct EstimatorFilter {
   bool started = false;
   double xy[2][6] = {}, Pxy[2][36] = {}, z[5] = {}, Pz[25] = {}, terrain = 0;
@@ -113,44 +159,18 @@ struct EstimatorFilter {
   // quat: pelvis.orientation; footL / footR: foot points in the pelvis frame; FLz / FRz: z of toeForce + heelForce; acc: translationalAcceleration
   void step(const double quat[4], const double footL[3], const double footR[3], double FLz, double FRz, const double acc[3],
             double pos[3], double vel[3], double ext_force[3], double *terrain_height) {
-    constexpr double dt = 0.0005, mass = 31.0, grav = 9.806, c = dt * grav;
     const double w = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
     const M3 R{{w * w + qx * qx - qy * qy - qz * qz, 2 * (qx * qy + w * qz), 2 * (qx * qz - w * qy)},
                {2 * (qx * qy - w * qz), w * w - qx * qx + qy * qy - qz * qz, 2 * (qy * qz + w * qx)},
                {2 * (qx * qz + w * qy), 2 * (qy * qz - w * qx), w * w - qx * qx - qy * qy + qz * qz}};
     const V3 yl = -1.0 * (R * V3{footL[0], footL[1], footL[2]}), yr = -1.0 * (R * V3{footR[0], footR[1], footR[2]}), a = R * V3{acc[0], acc[1], acc[2]};
     const double yL[3] = {yl.x, yl.y, yl.z}, yR[3] = {yr.x, yr.y, yr.z}, aw[3] = {a.x, a.y, a.z};
-    const double fl = FLz < 0 ? FLz : 0, fr = FRz < 0 ? FRz : 0;
-    const bool contact = -(fl + fr) > 1.0;
-    const double wm = contact ? fl / (fl + fr) : 0.5, qL = FLz < -50 ? 1e-10 : 1e-6, qR = FRz < -50 ? 1e-10 : 1e-6;
-    if (!started) {   // the block's own start: pelvis at 0, the foot states at +y (sic), weight 1/2, the whole weight on the external force
-      for (int ax = 0; ax < 2; ax++) { const double x0[6] = {0, 0, yL[ax], yR[ax], 0.5, 0}; for (int i = 0; i < 6; i++) xy[ax][i] = x0[i];
-        for (int i = 0; i < 36; i++) Pxy[ax][i] = (i % 7 == 0) ? 1e-6 : 0; }
-      const double z0[5] = {0, 0, yL[2], yR[2], mass * grav}; for (int i = 0; i < 5; i++) z[i] = z0[i];
-      for (int i = 0; i < 25; i++) Pz[i] = (i % 6 == 0) ? 1e-6 : 0;
-      terrain = 0; started = true;
-    }
-    static constexpr int plus6[4] = {0, 0, 4, 1}, minus6[4] = {2, 3, -1, -1};   // measurements p - footL, p - footR, w, v
-    static constexpr double R4[4] = {1e-6, 1e-6, 1e-6, 1};
-    for (int ax = 0; ax < 2; ax++) {
-      double (&x)[6] = xy[ax];
-      const double zm[4] = {yL[ax], yR[ax], wm, x[1] + dt * aw[ax]}, Qd[6] = {1e-8, 1e-8, qL, qR, 1e-5, 1e-2}, p0 = x[0], v0 = x[1], wt = x[4];
-      double a1[6] = {0, 1, 0, 0, 0, 0};   // row 1 of the Jacobian
-      if (contact) { a1[0] = c; a1[2] = -c * wt; a1[3] = -c * (1 - wt); a1[4] = -c * (x[2] - x[3]); a1[5] = dt / mass;
-                     x[1] = v0 + c * (p0 - wt * x[2] - (1 - wt) * x[3]) + dt / mass * x[5]; }
-      x[0] = p0 + dt * v0;
-      kalman_predict_cov<6>(Pxy[ax], dt, a1, Qd);
-      kalman_update<6, 4>(x, Pxy[ax], plus6, minus6, R4, zm);
-    }
-    {
-      static constexpr int plus5[2] = {0, 0}, minus5[2] = {2, 3};
-      static constexpr double R2[2] = {1e-6, 1e-6}, a1[5] = {0, 1, 0, 0, dt / mass};
-      const double zm[2] = {yL[2], yR[2]}, Qd[5] = {1e-8, 1e-8, qL, qR, 1e-2}, p0 = z[0], v0 = z[1];
-      z[0] = p0 + dt * v0; z[1] = v0 + dt / mass * z[4] + dt * (-grav - (fl + fr) / mass);
-      kalman_predict_cov<5>(Pz, dt, a1, Qd);
-      kalman_update<5, 2>(z, Pz, plus5, minus5, R2, zm);
-    }
-    if (contact) terrain = (terrain + dt * (z[0] - (wm * yL[2] + (1 - wm) * yR[2]))) / (1 + dt);
+    const EstimatorContact k = estimator_contact(FLz, FRz);
+    if (!started) { for (int ax = 0; ax < 2; ax++) estimator_axis_start_xy(xy[ax], Pxy[ax], yL[ax], yR[ax]);
+                    estimator_axis_start_z(z, Pz, yL[2], yR[2]); terrain = 0; started = true; }
+    for (int ax = 0; ax < 2; ax++) estimator_axis_xy(xy[ax], Pxy[ax], yL[ax], yR[ax], aw[ax], k);
+    estimator_axis_z(z, Pz, yL[2], yR[2], k);
+    terrain = estimator_terrain(terrain, z[0], yL[2], yR[2], k);
     for (int ax = 0; ax < 2; ax++) { pos[ax] = xy[ax][0]; vel[ax] = xy[ax][1]; ext_force[ax] = xy[ax][5]; }
     pos[2] = z[0]; vel[2] = z[1]; ext_force[2] = z[4];
     *terrain_height = terrain;

@@ -72,6 +72,8 @@ template <typename real> struct EnvPtrs {
   real *dbg;          // [D_SIZE] or null
   real *aux;          // [AUX_W] derived-quantity row or null
   real *cenv;         // [CE_W] per-environment model constants (domain randomisation) or null: then the shared model block's values apply
+  double *est;        // [EST_W] in-kernel estimator state or null (extended instance only)
+  real *est_out;      // [EO_W] its outputs
   int *counters;      // [8]
   int cta_sync;       // 1: the CTA's warps rendezvous at the stage boundaries (STAGE_SYNC); only the step / forward modes
 };
@@ -1558,7 +1560,9 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       }
     ENDL
     // ---- *y = cassie_out (:1127): the observation of this tick
-    if (obs && tick == nticks - 1) {
+    bool est_on = false;
+    if constexpr (DR) est_on = E.est != (double *)0;   // the filters advance every 2 kHz tick, so the stateless part runs every tick too
+    if (obs && (tick == nticks - 1 || est_on)) {
       LANES
         if (l < 10) { obs[OB_MPOS + l] = cst[CS_DPOS + l]; obs[OB_MVEL + l] = cst[CS_DVEL + l]; obs[OB_MTORQUE + l] = cst[CS_DTORQUE + l]; }
         if (l < 6) { obs[OB_JPOS + l] = cst[CS_JPOS + l]; obs[OB_JVEL + l] = cst[CS_JVEL + l]; }
@@ -1587,6 +1591,45 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
           for (int k = 0; k < 3; ++k) obs[OB_EST_ACC + k] = a[k] - R[6 + k] * real(9.806) - wwr[k];
         }
       ENDL
+      // ---- state_output_step, spring-force model and filters (csrc/estimator_host.h: the same functions run here and on the host)
+      if constexpr (DR) { if (est_on) {
+        LANES  // lanes 0, 1: leg force from the measured angles and the IMU quaternion
+          if (l < 2) {
+            const int sd = l; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd, *q = cst + CS_SENSOR + 16;
+            const double ang[7] = {(double)mp[0], (double)mp[1], (double)mp[2], (double)mp[3], (double)jp[0], (double)jp[1], (double)mp[4]}, qd[4] = {(double)q[0], (double)q[1], (double)q[2], (double)q[3]};
+            double f[3]; estimator_leg_force(sd, ang, qd, f);
+            for (int k = 0; k < 3; ++k) { E.est[ES_FORCE + 3 * sd + k] = f[k]; E.est_out[EO_TOE + 3 * sd + k] = (real)f[k]; }
+          }
+        ENDL
+        LANES  // lanes 0, 1, 2: the x, y, z filters side by side (each reads row `ax` of R(q) only)
+          if (l < 3) {
+            const int ax = l; double *st = E.est;
+            const real *q = obs + OB_EST_QUAT, *pl = obs + OB_FOOT, *pr = obs + OB_FOOT + 13, *ac = obs + OB_EST_ACC;
+            const double w = q[0], x = q[1], y = q[2], z = q[3];
+            const double r0 = ax == 0 ? w * w + x * x - y * y - z * z : ax == 1 ? 2 * (x * y + w * z) : 2 * (x * z - w * y);
+            const double r1 = ax == 0 ? 2 * (x * y - w * z) : ax == 1 ? w * w - x * x + y * y - z * z : 2 * (y * z + w * x);
+            const double r2 = ax == 0 ? 2 * (x * z + w * y) : ax == 1 ? 2 * (y * z - w * x) : w * w - x * x - y * y + z * z;
+            const double yL = -(pl[0] * r0 + pl[1] * r1 + pl[2] * r2), yR = -(pr[0] * r0 + pr[1] * r1 + pr[2] * r2), aw = ac[0] * r0 + ac[1] * r1 + ac[2] * r2;
+            const EstimatorContact k = estimator_contact(st[ES_FORCE + 2] + st[ES_FORCE + 2], st[ES_FORCE + 5] + st[ES_FORCE + 5]);   // toeForce + heelForce
+            const bool started = st[0] != 0;
+            if (ax < 2) {
+              double *xs = st + ES_X + 42 * ax, *P = xs + 6;
+              if (!started) estimator_axis_start_xy(xs, P, yL, yR);
+              estimator_axis_xy(xs, P, yL, yR, aw, k);
+              E.est_out[EO_POS + ax] = (real)xs[0]; E.est_out[EO_VEL + ax] = (real)xs[1]; E.est_out[EO_EXTF + ax] = (real)xs[5];
+            } else {
+              double *zs = st + ES_Z, *P = st + ES_PZ;
+              if (!started) { estimator_axis_start_z(zs, P, yL, yR); st[ES_TERRAIN] = 0; }
+              estimator_axis_z(zs, P, yL, yR, k);
+              st[ES_TERRAIN] = estimator_terrain(st[ES_TERRAIN], zs[0], yL, yR, k);
+              E.est_out[EO_POS + 2] = (real)zs[0]; E.est_out[EO_VEL + 2] = (real)zs[1]; E.est_out[EO_EXTF + 2] = (real)zs[4]; E.est_out[EO_TERRAIN] = (real)st[ES_TERRAIN];
+            }
+          }
+        ENDL
+        LANES
+          if (l == 0) E.est[0] = 1;
+        ENDL
+      } }
     }
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)

@@ -204,6 +204,13 @@ void cassie_b200_estimator_leg_force(int side, const double ang[7], const double
  * restarts the filters (state_output_setup; mask as in cassie_batch_reset).  The filter is also exported as a plain host object:
  * ..._step reads orientation, translationalAcceleration, both feet's position and toe / heel forces from *y and writes the four outputs. */
 int cassie_batch_enable_estimator_filter(cassie_batch_t *b, int on);
+/* The same estimator inside the step kernel (leg forces + filters, every 2 kHz tick of a launch, so multi-tick launches keep it exact and
+ * device-resident observations are complete): one [n][CASSIE_EST_WIDTH] row per environment, device pointer "est_out" --
+ * pelvis.position 3, translationalVelocity 3, externalForce 3, terrain.height 1, toeForce (= heelForce) left 3, right 3.
+ * The filter state is held in doubles in every batch precision.  cassie_batch_reset(_estimator) restarts it. */
+#define CASSIE_EST_WIDTH 16
+int cassie_batch_enable_estimator_device(cassie_batch_t *b, int on);
+int cassie_batch_get_estimator(cassie_batch_t *b, double *out /* [n][CASSIE_EST_WIDTH] */);
 int cassie_batch_reset_estimator(cassie_batch_t *b, const unsigned char *mask);
 void *cassie_b200_estimator_filter_new(void);
 void cassie_b200_estimator_filter_free(void *filter);

@@ -16,7 +16,7 @@ D = dict(XPOS=0, XQUAT=96, CDOF=224, QM=416, QLD=736, BIAS=1056, PASSIVE=1088, S
 
 def build(force=False):
     srcs = [os.path.join(HERE, 'emu', 'emu.cpp'), os.path.join(CSRC, 'mjcf.cpp'), os.path.join(CSRC, 'step_core.inl'),
-            os.path.join(CSRC, 'devmodel.h'), os.path.join(CSRC, 'devbuild.h'), os.path.join(CSRC, 'model.h')]
+            os.path.join(CSRC, 'devmodel.h'), os.path.join(CSRC, 'devbuild.h'), os.path.join(CSRC, 'model.h'), os.path.join(CSRC, 'estimator_host.h')]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -87,6 +87,11 @@ class EmuSim:
             a = np.ascontiguousarray(rows60, dtype=np.float64)
             assert a.size == 60
             self.L.emu_set_task(self.h, a.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def enable_est(self, on=True):
+        """in-kernel estimator (forces + filters) of the extended instance; enabling restarts it"""
+        self.L.emu_enable_est.argtypes = [C.c_void_p, C.c_int]
+        self.L.emu_enable_est(self.h, 1 if on else 0)
 
     def enable_cenv(self):
         self.L.emu_enable_cenv(self.h)

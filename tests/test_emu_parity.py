@@ -107,3 +107,31 @@ def test_no_gravity_variant(oracle_mod):
         e.step(PD_ROW)
     assert np.abs(e.get('qpos')[:35] - o.arr('qpos')).max() < 1e-10
     assert abs(o.arr('qpos')[2] - 1.01) < 0.01 and int(e.get('counters')[1]) == 0      # still floating, no contacts
+
+
+def test_in_kernel_estimator_matches_oracle(oracle_mod, pkg):
+    """the estimator stage of the extended instance (leg forces + filters, every tick of a launch) against the oracle's restated estimator:
+    fp64 to rounding, also when several ticks run per launch"""
+    import os
+    import numpy as np
+    from conftest import GOLDEN, PD_DGAIN, PD_PGAIN, PD_TARGET
+    from emu_harness import EmuSim
+    O = oracle_mod
+
+    def rows(y):
+        return np.concatenate([y.pelvis.position[:], y.pelvis.translationalVelocity[:], y.pelvis.externalForce[:], [y.terrain.height], y.leftFoot.toeForce[:], y.rightFoot.toeForce[:]])
+    u = O.make_pd(pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    row = np.zeros(50)
+    row[10:20], row[30:40], row[40:50] = PD_TARGET, PD_PGAIN, PD_DGAIN
+    for nt in (1, 4):
+        o, e, y = O.OracleSim(os.path.join(GOLDEN, 'cassie.omodel')), EmuSim(pkg.model_path('cassie')), pkg.state_out_t()
+        e.enable_est()
+        worst = 0.0
+        for k in range(0, 600, nt):
+            for _ in range(nt):
+                o.step_pd(u, y)
+            e.step(row, nt)
+            a = rows(y)
+            worst = max(worst, (np.abs(a - e.get('est_out')) / (1 + np.abs(a))).max())
+        assert worst < 1e-10 and abs(a[8]) > 1 and a[12] < -50, (nt, worst)
+        e.close()

@@ -101,3 +101,28 @@ def test_turn_invariance_at_full_size():
     for kk, tol in ((0, 0.0), (2, 1e-10), (1, 1e-6), (3, 1e-6)):              # same heading: bitwise; half turn: rounding; quarter turns: row-order noise
         d = np.abs(q[k == kk] - ref).max()
         assert d <= tol, (kk, d)
+
+
+def test_in_kernel_estimator_rows():
+    """the estimator inside the step kernel: rows equal the host-side filters of the one-tick AoS path, and stay exact over multi-tick launches"""
+    P = product()
+    n = 3
+    a, b = P.CassieBatch(n, precision=P.FP64), P.CassieBatch(n, precision=P.FP64)
+    pin = (P.pd_in_t * n)(*[_pd(P) for _ in range(n)])
+    rows = P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN)
+    a.enable_estimator()                       # host filters
+    b.enable_estimator_device()                # kernel stage
+    b.set_pd(rows)
+    for k in range(60):
+        for _ in range(5):
+            ys = a.step_pd(pin)
+        b.step(5)                              # five ticks per launch
+    want = np.concatenate([_filtered(ys[1]), ys[1].leftFoot.toeForce[:], ys[1].rightFoot.toeForce[:]])
+    got = b.estimator()[1]
+    assert (np.abs(got - want) / (1 + np.abs(want))).max() < 1e-8, (got, want)
+    m = np.zeros(n, dtype=np.uint8)
+    m[0] = 1
+    b.reset_estimator(m)
+    b.step(1)
+    r = b.estimator()
+    assert r[0, 8] == pytest.approx(31 * 9.806, rel=1e-6) and abs(r[1, 8] - 31 * 9.806) > 1
