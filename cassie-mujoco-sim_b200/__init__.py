@@ -14,13 +14,18 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcassie_b200.so')
 MODEL_DIR = os.path.join(_HERE, 'models')
 FP32, FP64 = 0, 1
-PD_WIDTH, OBS_WIDTH, AUX_WIDTH, EST_WIDTH = 52, 96, 64, 16
+PD_WIDTH, OBS_WIDTH, AUX_WIDTH, EST_WIDTH = 52, 112, 64, 16
 # slices of a derived-quantity row (CASSIE_AUX_* in include/cassie_b200.h)
 AUX = dict(foot_force=slice(0, 12), toe_force=slice(12, 18), heel_force=slice(18, 24), foot_pos=slice(24, 30), foot_vel=slice(30, 42),
            cm_pos=slice(42, 45), cm_vel=slice(45, 48), angmom=slice(48, 51), obstacle=51, self_collision=52, group_mask=53, ncon=54)
 # observation row layout (cassie_batch_get_obs)
 OBS = dict(motor_pos=slice(0, 10), motor_vel=slice(10, 20), motor_torque=slice(20, 30), joint_pos=slice(30, 36), joint_vel=slice(36, 42),
-           quat=slice(42, 46), gyro=slice(46, 49), accel=slice(49, 52), mag=slice(52, 55), time=55)
+           quat=slice(42, 46), gyro=slice(46, 49), accel=slice(49, 52), mag=slice(52, 55), time=55,
+           # decoded estimator (state_output_step): stateless part ...
+           est_accel=slice(56, 59), left_foot=slice(60, 73), right_foot=slice(73, 86), est_quat=slice(86, 90),
+           # ... and, once the in-kernel estimator is on, the force model and the filters
+           est_position=slice(96, 99), est_velocity=slice(99, 102), est_external_force=slice(102, 105), est_terrain_height=105,
+           est_left_toe_force=slice(106, 109), est_right_toe_force=slice(109, 112))
 
 
 # ---------------------------------------------------------------- ctypes mirrors of the bus structs (include/cassie_bus.h)
@@ -164,6 +169,8 @@ def lib():
     L.cassie_batch_enable_estimator_device.restype = ci
     L.cassie_batch_get_estimator.argtypes = [vp, cd]
     L.cassie_batch_get_estimator.restype = ci
+    L.cassie_batch_set_pd_gait.argtypes = [vp, cd, cd, cd]
+    L.cassie_batch_set_pd_gait.restype = ci
     L.cassie_batch_set_task_pd.argtypes = [vp, cd]
     L.cassie_batch_set_task_pd.restype = ci
     L.cassie_batch_get_aux.argtypes = [vp, cd]
@@ -281,6 +288,19 @@ class CassieBatch:
         if rc != 0:
             raise RuntimeError(_last_error())
 
+    def set_pd_gait(self, amp=None, freq=None, phase=None):
+        """open-loop gait on the motor-PD targets: pTarget_i(t) = row pTarget_i + amp[e, i] sin(2 pi freq[e] t + phase[e, i]), evaluated inside the kernel
+        every control tick (t = ticks since reset / since this call x 0.5 ms); amp=None switches it off."""
+        if amp is None:
+            rc = self.L.cassie_batch_set_pd_gait(self.h, None, None, None)
+        else:
+            a = np.ascontiguousarray(np.broadcast_to(amp, (self.n, 10)), dtype=np.float64)
+            f = np.ascontiguousarray(np.broadcast_to(freq, (self.n,)), dtype=np.float64)
+            p = np.ascontiguousarray(np.broadcast_to(phase, (self.n, 10)), dtype=np.float64)
+            rc = self.L.cassie_batch_set_pd_gait(self.h, self._dp(a), self._dp(f), self._dp(p))
+        if rc != 0:
+            raise RuntimeError(_last_error())
+
     def step(self, nticks=1):
         self.L.cassie_batch_step(self.h, int(nticks))
 
@@ -327,11 +347,14 @@ class CassieBatch:
     # ---- the estimator's host-side part for step_pd(): toe / heel forces, and the filters behind pelvis.position / translationalVelocity /
     # externalForce and terrain.height (one filter per environment, advanced once per step_pd call as the reference's 2 kHz estimator is)
     def enable_estimator(self, forces=True, filters=True):
+        """HOST-side checker of the estimator (one filter object per environment, advanced per step_pd call); the product path is the
+        in-kernel estimator (enable_estimator_device), which step_pd switches on by itself"""
         self.L.cassie_batch_enable_estimator_forces(self.h, 1 if (forces or filters) else 0)
         self.L.cassie_batch_enable_estimator_filter(self.h, 1 if filters else 0)
 
     def enable_estimator_device(self, on=True):
-        """the estimator inside the step kernel: estimator() rows follow every tick of every launch"""
+        """the estimator inside the step kernel: columns 96..111 of obs() / estimator() follow every tick of every launch; step_pd switches it
+        on by itself at its first call, enable_estimator_device(False) keeps it off"""
         if self.L.cassie_batch_enable_estimator_device(self.h, 1 if on else 0) != 0:
             raise RuntimeError(_last_error())
 
@@ -431,7 +454,10 @@ class CassieBatch:
         self.L.cassie_batch_set_stream(self.h, C.c_void_p(cuda_stream_ptr))
 
     def torch_view(self, field):
-        """zero-copy torch tensor over a device state array (qpos [n,36], qvel [n,32], pd [n,52], obs [n,96])."""
+        """zero-copy torch tensor over a device state array (qpos [n,36], qvel [n,32], pd [n,52], obs [n,112]).
+
+        The arrays are written on the batch's stream.  Unless that stream is torch's current stream (set_stream(torch.cuda.current_stream().cuda_stream)),
+        call sync() before reading the view: torch ops on another stream are not ordered after an in-flight step."""
         import torch
         self.L.cassie_batch_row_width.argtypes = [C.c_void_p, C.c_char_p]
         width = self.L.cassie_batch_row_width(self.h, field.encode())

@@ -25,8 +25,21 @@ static thread_local std::string g_err;
 static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b200: %s\n", e.c_str()); }
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return false; } } while (0)
 
+// CPUs this process may actually use: the affinity mask clipped by the cgroup CPU quota (a container on a 128-thread host may own 16)
+static int effective_cpus() {
+  int hw = omp_get_num_procs();
+  long quota = -1, period = 0;
+  if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) { char q[64]; if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max")) quota = atol(q); fclose(f); }
+  else {
+    if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(g, "%ld", &quota) != 1) quota = -1; fclose(g); }
+    if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(g, "%ld", &period) != 1) period = 0; fclose(g); }
+  }
+  if (quota > 0 && period > 0) { const int c = (int)((quota + period - 1) / period); if (c >= 1 && c < hw) hw = c; }
+  return hw < 1 ? 1 : hw;
+}
+
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *est_out; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,11 +101,11 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     if (A.xb >= 0 && l < 6) { xqvel = A.qvel[(size_t)env * vw + 32 + l]; xqacc_ws = A.qacc_ws[(size_t)env * vw + 32 + l]; }
     __syncwarp();
     EnvPtrs<real> E;
-    E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W; E.task = A.task ? A.task + (size_t)env * TASK_W : nullptr;
+    E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W; E.task = A.task ? A.task + (size_t)env * TASK_W : nullptr; E.gait = A.gait ? A.gait + (size_t)env * GAIT_W : nullptr;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * 2 * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
     E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on;
-    E.est = A.est ? A.est + (size_t)env * EST_W : nullptr; E.est_out = A.est ? A.est_out + (size_t)env * EO_W : nullptr;
+    E.est = A.est ? A.est + (size_t)env * EST_W : nullptr; E.est_out = E.obs + OB_EST_OUT;
     step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
     if (mode >= 2) continue;   // query / set_const: only the aux row / the constant row is written
@@ -178,16 +191,17 @@ __global__ void __launch_bounds__(256) cassie_integrate_kernel(const DevModel<re
 
 // rows of the selected environments <- one template row (masked reset / set_const)
 template <typename T>
-__global__ void fill_rows_kernel(T *__restrict__ dst, const T *__restrict__ row, int w, const unsigned char *__restrict__ mask, int n) {
-  const size_t total = (size_t)n * w;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) { const size_t e = i / w; if (!mask || mask[e]) dst[i] = row[i - e * w]; }
+__global__ void fill_rows_kernel(T *__restrict__ dst, const T *__restrict__ row, int w, const unsigned char *__restrict__ mask, int n, int ncols) {
+  const size_t total = (size_t)n * w;   // only the first ncols columns of a row are rewritten
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) { const size_t e = i / w; if ((!mask || mask[e]) && (int)(i - e * w) < ncols) dst[i] = row[i - e * w]; }
 }
 
 // ------------------------------------------------------------------ host side
 struct BatchBase {
   virtual ~BatchBase() {}
   bool est_forces = false;   // fill toeForce / heelForce of state_out_t on the host (cassie_batch_enable_estimator_forces)
-  bool est_filter = false;   // run the estimator's filters on the host, one per environment (cassie_batch_enable_estimator_filter; needs est_forces)
+  bool est_filter = false;   // run the estimator's filters on the host, one per environment (cassie_batch_enable_estimator_filter; needs est_forces): the checker of the in-kernel estimator
+  bool est_auto = true;      // cassie_sim_step_pd_batch switches the in-kernel estimator on by itself (cassie_batch_enable_estimator_device(b, 0) clears this)
   std::vector<cassie::EstimatorFilter> est_state;
   void reset_estimator(const unsigned char *mask) { for (size_t e = 0; e < est_state.size(); e++) if (!mask || mask[e]) est_state[e].reset(); }
   HostModel hm; int n = 0, device = 0, precision = 0, wpb = 4; cudaStream_t stream = nullptr; bool own_stream = false; long launches = 0; bool debug = false;
@@ -208,6 +222,7 @@ struct BatchBase {
   virtual bool enable_estimator_device(bool on) = 0;   // leg forces + filters inside the step kernel (extended instance), every 2 kHz tick
   virtual bool reset_estimator_device(const unsigned char *mask) = 0;
   virtual bool set_task_pd(const double *rows) = 0;   // [n][60] or null (off)
+  virtual bool set_pd_gait(const double *amp, const double *freq, const double *phase) = 0;   // [n][10], [n], [n][10] or all null (off)
   virtual bool set_model_rows(const char *what, const double *rows, int width) = 0;   // per-env model constants (domain randomisation)
   virtual bool get_model_rows(const char *what, double *rows, int width) = 0;
   virtual bool set_const(const unsigned char *mask, bool reset_state) = 0;
@@ -220,11 +235,12 @@ template <typename real> struct Batch : BatchBase {
   struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[2];   // [0] plain instance, [1] extended instance
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr, *pin_task = nullptr;   // pinned staging for the AoS entry point
+  bool task_from_aos = false;   // the task-PD rows were created by the AoS entry point's forwarding (not by cassie_batch_set_task_pd)
   float *d_hfield = nullptr; unsigned char *d_mask = nullptr; DevModel<real> h_model_copy{}; int geom_dev[256]; void *d_row = nullptr;
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
-    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(A.task); cudaFree(A.est); cudaFree(A.est_out); if (pin_task) cudaFreeHost(pin_task); cudaFree(d_mask); cudaFree(d_row);
+    cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(A.task); cudaFree(A.gait); cudaFree(A.est); if (pin_task) cudaFreeHost(pin_task); cudaFree(d_mask); cudaFree(d_row);
     if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -304,10 +320,10 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemcpyAsync(d_mask, mask, n, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
     return true;
   }
-  template <typename T> bool fill_masked(T *dst, const T *row, int w) {   // uses d_mask
+  template <typename T> bool fill_masked(T *dst, const T *row, int w, int ncols = 1 << 30) {   // uses d_mask
     if (!d_row) CUDA_OK(cudaMalloc(&d_row, 4096));
     CUDA_OK(cudaMemcpyAsync(d_row, row, sizeof(T) * w, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
-    fill_rows_kernel<T><<<256, 256, 0, stream>>>(dst, (const T *)d_row, w, d_mask, n);
+    fill_rows_kernel<T><<<256, 256, 0, stream>>>(dst, (const T *)d_row, w, d_mask, n, ncols);
     CUDA_OK(cudaGetLastError()); CUDA_OK(cudaStreamSynchronize(stream));
     return true;
   }
@@ -354,7 +370,7 @@ template <typename real> struct Batch : BatchBase {
     // src/cassiemujoco.c:955-971: qpos <- the init constants, qvel <- 0, time <- 0, mj_forward (filters, delay line, cassie_out keep their values)
     std::vector<real> qpos(QPOS_W_XB), qvel(QVEL_W_XB), qa(QVEL_W_XB), cst(CST_W), xf(XFRC_W); std::vector<int> df(DFILT_W);
     init_env_rows(hm, qpos.data(), qvel.data(), qa.data(), cst.data(), df.data(), xf.data());
-    if (!fill_masked(A.qpos, qpos.data(), QW) || !fill_masked(A.qvel, qvel.data(), VW)) return false;
+    if (!fill_masked(A.qpos, qpos.data(), QW, 35) || !fill_masked(A.qvel, qvel.data(), VW)) return false;   // the reference copies 35 qpos entries (:967): an extra free body keeps its pose
     { std::vector<real> all((size_t)n * CST_W);
       CUDA_OK(cudaMemcpyAsync(all.data(), A.cst, sizeof(real) * n * CST_W, cudaMemcpyDeviceToHost, stream)); CUDA_OK(cudaStreamSynchronize(stream));
       for (int e = 0; e < n; e++) if (mask[e]) all[(size_t)e * CST_W + CS_TIME] = 0;
@@ -372,7 +388,7 @@ template <typename real> struct Batch : BatchBase {
   // cassie_sim_step_pd for every env with host AoS buffers: pack pd_in_t[] -> pinned rows -> H2D, one tick, D2H rows -> state_out_t[]
   bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) override {
     CUDA_OK(cudaSetDevice(device));
-    static const int aos_threads = [] { const char *e = getenv("CASSIE_B200_AOS_THREADS"); int t = e ? atoi(e) : 32; const int hw = omp_get_num_procs(); if (t > hw) t = hw; return t < 1 ? 1 : t; }();   // host pack / unpack threads
+    static const int aos_threads = [] { const char *e = getenv("CASSIE_B200_AOS_THREADS"); int t = e ? atoi(e) : 32; const int hw = effective_cpus(); if (t > hw) t = hw; return t < 1 ? 1 : t; }();   // host pack / unpack threads
     if (!pin_pd) { CUDA_OK(cudaMallocHost(&pin_pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMallocHost(&pin_obs, sizeof(real) * n * OBS_W)); }
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
     for (int e = 0; e < n; e++) {
@@ -390,48 +406,57 @@ template <typename real> struct Batch : BatchBase {
         for (int sd = 0; sd < 2; sd++) for (int k = 0; k < 6; k++) any |= (t[sd]->torque[k] != 0 || t[sd]->pGain[k] != 0 || t[sd]->dGain[k] != 0); }
       if (any) {
         if (!pin_task) CUDA_OK(cudaMallocHost(&pin_task, sizeof(real) * n * TASK_W));
-        if (!A.task) CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W));
+        if (!A.task) { CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W)); task_from_aos = true; }
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
         for (int e = 0; e < n; e++) { real *row = pin_task + (size_t)e * TASK_W;
           for (int sd = 0; sd < 2; sd++) { const pd_task_in_t *t = sd ? &pd_in[e].rightLeg.taskPd : &pd_in[e].leftLeg.taskPd; real *r = row + 30 * sd;
             for (int k = 0; k < 6; k++) { r[k] = (real)t->torque[k]; r[6 + k] = (real)t->pTarget[k]; r[12 + k] = (real)t->dTarget[k]; r[18 + k] = (real)t->pGain[k]; r[24 + k] = (real)t->dGain[k]; } }
           for (int i = 60; i < TASK_W; i++) row[i] = 0; }
         CUDA_OK(cudaMemcpyAsync(A.task, pin_task, sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream));
-      } else if (A.task) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; }
+      } else if (A.task && task_from_aos) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; task_from_aos = false; }   // rows installed with cassie_batch_set_task_pd stay
     }
     CUDA_OK(cudaMemcpyAsync(A.pd, pin_pd, sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));
+    // cassie_sim_step_pd runs state_output_step in every call (src/cassiemujoco.c:1156): so does the batched entry point, inside the kernel,
+    // from the first call that asks for state_out_t rows (unless the caller switched it off or runs the host-side checker instead)
+    if (state_out && est_auto && !A.est && !est_filter && !enable_estimator_device(true)) return false;
     if (!step(1, 0)) return false;
     if (!state_out) return sync();
     CUDA_OK(cudaMemcpyAsync(pin_obs, A.obs, sizeof(real) * n * OBS_W, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     if (est_filter && est_state.size() != (size_t)n) est_state.assign((size_t)n, cassie::EstimatorFilter());
+    const bool dev_est = A.est != nullptr;   // the estimator ran inside the kernel: its outputs are columns of the observation row
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
     for (int e = 0; e < n; e++) {
-      const real *o = pin_obs + (size_t)e * OBS_W; state_out_t *y = state_out + e;
-      memset(y, 0, sizeof *y);
+      // every field of state_out_t is written exactly once (no memset pass): what the reference's block never writes (externalMoment,
+      // terrain.slope, battery.current) is zero, as in a freshly set-up state_output_t
+      const real *o = pin_obs + (size_t)e * OBS_W; state_out_t *y = state_out + e; const real *eo = o + OB_EST_OUT;
+      for (int i = 0; i < 3; i++) { y->pelvis.position[i] = dev_est ? (double)eo[EO_POS + i] : 0.0; y->pelvis.translationalVelocity[i] = dev_est ? (double)eo[EO_VEL + i] : 0.0;
+                                    y->pelvis.externalForce[i] = dev_est ? (double)eo[EO_EXTF + i] : 0.0; y->pelvis.externalMoment[i] = 0;
+                                    y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_EST_ACC + i]; }
+      for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_EST_QUAT + i];
+      y->terrain.height = dev_est ? (double)eo[EO_TERRAIN] : 0.0; y->terrain.slope[0] = y->terrain.slope[1] = 0;
       for (int i = 0; i < 10; i++) { y->motor.position[i] = o[OB_MPOS + i]; y->motor.velocity[i] = o[OB_MVEL + i]; y->motor.torque[i] = o[OB_MTORQUE + i]; }
       for (int i = 0; i < 6; i++) { y->joint.position[i] = o[OB_JPOS + i]; y->joint.velocity[i] = o[OB_JVEL + i]; }
-      for (int i = 0; i < 4; i++) y->pelvis.orientation[i] = o[OB_EST_QUAT + i];
-      for (int i = 0; i < 3; i++) { y->pelvis.rotationalVelocity[i] = o[OB_GYRO + i]; y->pelvis.translationalAcceleration[i] = o[OB_EST_ACC + i]; }
-      for (int sd = 0; sd < 2; sd++) {   // decoded stateless part of the estimator: foot pose (pelvis frame) and velocities (foot frame)
+      for (int sd = 0; sd < 2; sd++) {   // decoded estimator: foot pose (pelvis frame), velocities (foot frame), toe / heel force
         state_foot_out_t *f = sd ? &y->rightFoot : &y->leftFoot; const real *fo = o + OB_FOOT + 13 * sd;
         for (int i = 0; i < 3; i++) { f->position[i] = fo[i]; f->footRotationalVelocity[i] = fo[7 + i]; f->footTranslationalVelocity[i] = fo[10 + i]; }
         for (int i = 0; i < 4; i++) f->orientation[i] = fo[3 + i];
-        if (est_forces || est_filter) {   // toe / heel force: host-side part of the decoded estimator (opt-in for batches: it costs host time per environment)
+        if (est_forces || est_filter) {   // host-side checker path (cassie_batch_enable_estimator_forces / _filter): the same functions the kernel runs
           const double ang[7] = {o[OB_MPOS + 5 * sd], o[OB_MPOS + 5 * sd + 1], o[OB_MPOS + 5 * sd + 2], o[OB_MPOS + 5 * sd + 3], o[OB_JPOS + 3 * sd], o[OB_JPOS + 3 * sd + 1], o[OB_MPOS + 5 * sd + 4]};
           const double qd[4] = {o[OB_QUAT], o[OB_QUAT + 1], o[OB_QUAT + 2], o[OB_QUAT + 3]};
           estimator_leg_force(sd, ang, qd, f->toeForce);
-          for (int i = 0; i < 3; i++) f->heelForce[i] = f->toeForce[i];
-        }
+        } else for (int i = 0; i < 3; i++) f->toeForce[i] = dev_est ? (double)eo[EO_TOE + 3 * sd + i] : 0.0;
+        for (int i = 0; i < 3; i++) f->heelForce[i] = f->toeForce[i];
       }
-      if (est_filter) {   // pelvis.position / translationalVelocity / externalForce, terrain.height: the estimator's filters, one 2 kHz call per step_pd call
+      if (est_filter) {   // host-side checker path: one 2 kHz filter call per step_pd call, overwrites the four filtered outputs
         cassie::EstimatorFilter &f = est_state[(size_t)e];
         f.step(y->pelvis.orientation, y->leftFoot.position, y->rightFoot.position, y->leftFoot.toeForce[2] + y->leftFoot.heelForce[2],
                y->rightFoot.toeForce[2] + y->rightFoot.heelForce[2], y->pelvis.translationalAcceleration,
                y->pelvis.position, y->pelvis.translationalVelocity, y->pelvis.externalForce, &y->terrain.height);
       }
       for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
-      y->radio.signalGood = true; y->battery.stateOfCharge = 1;
+      memset(&y->radio.signalGood, 0, sizeof(double)); y->radio.signalGood = true;   // the bool and its padding
+      y->battery.stateOfCharge = 1; y->battery.current = 0;
     }
     return true;
   }
@@ -459,10 +484,11 @@ template <typename real> struct Batch : BatchBase {
   bool enable_estimator_device(bool on) override {
     CUDA_OK(cudaSetDevice(device));
     if (on && !A.est) {
-      CUDA_OK(cudaMalloc(&A.est, sizeof(double) * n * EST_W)); CUDA_OK(cudaMalloc(&A.est_out, sizeof(real) * n * EO_W));
-      CUDA_OK(cudaMemsetAsync(A.est, 0, sizeof(double) * n * EST_W, stream)); CUDA_OK(cudaMemsetAsync(A.est_out, 0, sizeof(real) * n * EO_W, stream));
+      CUDA_OK(cudaMalloc(&A.est, sizeof(double) * n * EST_W));
+      CUDA_OK(cudaMemsetAsync(A.est, 0, sizeof(double) * n * EST_W, stream));
     }
-    if (!on && A.est) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.est)); CUDA_OK(cudaFree(A.est_out)); A.est = nullptr; A.est_out = nullptr; }
+    if (!on && A.est) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.est)); A.est = nullptr;
+                        CUDA_OK(cudaMemset2DAsync(A.obs + OB_EST_OUT, sizeof(real) * OBS_W, 0, sizeof(real) * EO_W, n, stream)); }   // its columns of the observation row read zero again
     return true;
   }
   bool reset_estimator_device(const unsigned char *mask) override {   // started flag (and everything else) back to zero: the filters start again at the next tick
@@ -476,11 +502,24 @@ template <typename real> struct Batch : BatchBase {
   // task-space PD rows (pd_in_t taskPd of both legs); NULL switches the branch off again
   bool set_task_pd(const double *rows) override {
     CUDA_OK(cudaSetDevice(device));
+    task_from_aos = false;   // the caller owns the rows from here on: the AoS entry point no longer drops them
     if (!rows) { if (A.task) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; } return true; }
     if (!A.task) CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W));
     h_tmp.assign((size_t)n * TASK_W, 0);
     for (int e = 0; e < n; e++) for (int i = 0; i < 60; i++) h_tmp[(size_t)e * TASK_W + i] = (real)rows[(size_t)e * 60 + i];
     CUDA_OK(cudaMemcpyAsync(A.task, h_tmp.data(), sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  // open-loop sinusoidal gait on the motor-PD targets (BASELINE config 5 "random PD gaits"): evaluated in the kernel every control tick, so
+  // multi-tick launches follow it without a host round trip; installing it restarts the tick clock
+  bool set_pd_gait(const double *amp, const double *freq, const double *phase) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (!amp || !freq || !phase) { if (A.gait) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.gait)); A.gait = nullptr; } return true; }
+    if (!A.gait) CUDA_OK(cudaMalloc(&A.gait, sizeof(real) * n * GAIT_W));
+    h_tmp.assign((size_t)n * GAIT_W, 0);
+    for (int e = 0; e < n; e++) { real *r = &h_tmp[(size_t)e * GAIT_W]; for (int i = 0; i < 10; i++) { r[GA_AMP + i] = (real)amp[(size_t)e * 10 + i]; r[GA_PHASE + i] = (real)phase[(size_t)e * 10 + i]; } r[GA_FREQ] = (real)freq[e]; }
+    CUDA_OK(cudaMemcpyAsync(A.gait, h_tmp.data(), sizeof(real) * n * GAIT_W, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemset2DAsync(A.dfilt + DF_TICK, sizeof(int) * DFILT_W, 0, sizeof(int), n, stream)); CUDA_OK(cudaStreamSynchronize(stream));
     return true;
   }
   bool step(int nticks, int mode) override {
@@ -521,7 +560,7 @@ template <typename real> struct Batch : BatchBase {
     if (!strcmp(f, "time")) return d2h(A.cst, CST_W, 1, CS_TIME, out);
     if (!strcmp(f, "obs")) return d2h(A.obs, OBS_W, OBS_W, 0, out);
     if (!strcmp(f, "cst")) return d2h(A.cst, CST_W, CST_W, 0, out);
-    if (!strcmp(f, "est_out")) { if (!A.est) { set_err("the in-kernel estimator is not enabled (cassie_batch_enable_estimator_device)"); return false; } return d2h(A.est_out, EO_W, EO_W, 0, out); }
+    if (!strcmp(f, "est_out")) { if (!A.est) { set_err("the in-kernel estimator is not enabled (cassie_batch_enable_estimator_device)"); return false; } return d2h(A.obs, OBS_W, EO_W, OB_EST_OUT, out); }
     if (!strcmp(f, "aux")) { if (!A.aux) { set_err("derived quantities are not enabled (cassie_batch_enable_aux)"); return false; } return d2h(A.aux, AUX_W, AUX_W, 0, out); }
     set_err(std::string("unknown field ") + f); return false;
   }
@@ -550,7 +589,7 @@ template <typename real> struct Batch : BatchBase {
   }
   void *dev_ptr(const char *f) override {
     if (!strcmp(f, "qpos")) return A.qpos; if (!strcmp(f, "qvel")) return A.qvel; if (!strcmp(f, "pd")) return A.pd; if (!strcmp(f, "obs")) return A.obs;
-    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux; if (!strcmp(f, "task")) return A.task; if (!strcmp(f, "est_out")) return A.est_out;
+    if (!strcmp(f, "xfrc")) return A.xfrc; if (!strcmp(f, "cst")) return A.cst; if (!strcmp(f, "qacc_ws")) return A.qacc_ws; if (!strcmp(f, "aux")) return A.aux; if (!strcmp(f, "task")) return A.task;
     return nullptr;
   }
   bool get_counters(int *out) override {
@@ -606,7 +645,7 @@ int cassie_batch_nv(const cassie_batch_t *b) { return b->impl->hm.nv; }
 int cassie_batch_precision(const cassie_batch_t *b) { return b->impl->precision; }
 int cassie_batch_row_width(const cassie_batch_t *b, const char *field) {
   if (!strcmp(field, "qpos")) return b->impl->hm.nq > 36 ? QPOS_W_XB : QPOS_W_MAIN; if (!strcmp(field, "qvel")) return b->impl->hm.nv > 32 ? QVEL_W_XB : QVEL_W_MAIN;
-  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; if (!strcmp(field, "aux")) return AUX_W; if (!strcmp(field, "est_out")) return EO_W; return -1;
+  if (!strcmp(field, "pd")) return PD_W; if (!strcmp(field, "obs")) return OBS_W; if (!strcmp(field, "xfrc")) return XFRC_W; if (!strcmp(field, "aux")) return AUX_W; return -1;
 }
 long cassie_batch_launch_count(const cassie_batch_t *b) { return b->impl->launches; }
 void cassie_batch_reset(cassie_batch_t *b, const unsigned char *mask) { b->impl->reset(mask); b->impl->sync(); b->impl->reset_estimator(mask); b->impl->reset_estimator_device(mask); }   // a fresh cassie_sim_t has a fresh estimator
@@ -632,6 +671,7 @@ int cassie_batch_get_dof_damping(cassie_batch_t *b, double *damp) { return b->im
 int cassie_batch_get_geom_friction(cassie_batch_t *b, double *fric) { return b->impl->get_model_rows("geom_friction", fric, 3 * b->impl->hm.ngeom) ? 0 : -1; }
 int cassie_batch_set_const(cassie_batch_t *b, const unsigned char *mask, int reset_state) { return b->impl->set_const(mask, reset_state != 0) ? 0 : -1; }
 int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows) { return b->impl->set_task_pd(rows) ? 0 : -1; }
+int cassie_batch_set_pd_gait(cassie_batch_t *b, const double *amp, const double *freq, const double *phase) { return b->impl->set_pd_gait(amp, freq, phase) ? 0 : -1; }
 int cassie_batch_enable_estimator_forces(cassie_batch_t *b, int on) { b->impl->est_forces = on != 0; return 0; }
 void cassie_b200_estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) { estimator_leg_force(side, ang, quat, force); }
 int cassie_batch_enable_estimator_filter(cassie_batch_t *b, int on) { b->impl->est_filter = on != 0; if (on) b->impl->est_forces = true; else b->impl->est_state.clear(); return 0; }
@@ -646,7 +686,7 @@ void cassie_b200_estimator_filter_step(void *f, state_out_t *y) {
 }
 int cassie_batch_enable_aux(cassie_batch_t *b, int on) { return b->impl->enable_aux(on != 0) ? 0 : -1; }
 int cassie_batch_get_aux(cassie_batch_t *b, double *out) { return b->impl->get("aux", out) ? 0 : -1; }
-int cassie_batch_enable_estimator_device(cassie_batch_t *b, int on) { return b->impl->enable_estimator_device(on != 0) ? 0 : -1; }
+int cassie_batch_enable_estimator_device(cassie_batch_t *b, int on) { if (!on) b->impl->est_auto = false; return b->impl->enable_estimator_device(on != 0) ? 0 : -1; }
 int cassie_batch_get_estimator(cassie_batch_t *b, double *out) { return b->impl->get("est_out", out) ? 0 : -1; }
 int cassie_batch_query(cassie_batch_t *b) { if (!b->impl->has_aux() && !b->impl->enable_aux(true)) return -1; return b->impl->step(0, 2) ? 0 : -1; }
 int cassie_batch_apply_force(cassie_batch_t *b, const double *xfrc, const char *body_name) {
@@ -700,7 +740,7 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   if (!b) return nullptr;
   cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b;
   b->impl->enable_aux(true); b->impl->step(0, 1);   // a single environment always carries the derived-quantity row; populate it like the sensordata
-  b->impl->est_forces = true; b->impl->est_filter = true;   // ... and the host-side part of the estimator (toe / heel forces, filters), as state_output_step runs in every cassie_sim_step_pd (src/cassiemujoco.c:1180)
+  b->impl->enable_estimator_device(true);   // ... and the estimator (toe / heel forces, filters) inside the kernel, as state_output_step runs in every cassie_sim_step_pd (src/cassiemujoco.c:1156)
   sim_pull(c);
   { const HostModel &hm = b->impl->hm; c->m_mass = hm.body_mass; c->m_ipos = hm.body_ipos; c->m_damp = hm.dof_damping; c->m_fric = hm.geom_friction;
     c->m_mass_dev = c->m_mass; c->m_ipos_dev = c->m_ipos; c->m_damp_dev = c->m_damp; c->m_fric_dev = c->m_fric; }
@@ -771,9 +811,9 @@ void cassie_sim_full_reset(cassie_sim_t *c) {
   std::vector<double> cst(CST_W); c->b->impl->get("cst", cst.data());
   for (int i = 0; i < 60; i++) cst[CS_DELAY + i] = 0;
   c->b->impl->set("cst", cst.data());
-  memset(c->qpos, 0, sizeof c->qpos); memcpy(c->qpos, q, sizeof q); memset(c->qvel, 0, sizeof c->qvel);
+  memcpy(c->qpos, q, sizeof q); memset(c->qvel, 0, sizeof c->qvel);   // 35 entries only (:2025): qpos beyond them (the cup of cassie_tray_box.xml) keeps its values
   c->b->impl->set("qpos", c->qpos); c->b->impl->set("qvel", c->qvel); cassie_batch_clear_forces(c->b);
-  c->b->impl->reset_estimator(nullptr);   // state_output_setup (src/cassiemujoco.c:2032) restarts the estimator's filters
+  c->b->impl->reset_estimator(nullptr); c->b->impl->reset_estimator_device(nullptr);   // state_output_setup (src/cassiemujoco.c:2032) restarts the estimator's filters
   sim_pull(c);
 }
 // sizes the reference's Python wrapper asks for (src/cassiemujoco.c:1038-1060)

@@ -84,11 +84,14 @@ struct DevModel {
 constexpr int QPOS_W_MAIN = 36, QVEL_W_MAIN = 32;   // row widths for the nq 35 / nv 32 models (runtime values live in DevModel::qpos_w / qvel_w)
 constexpr int QPOS_W_XB = 44, QVEL_W_XB = 40;       // with an extra free body (nq 42 / nv 38)
 constexpr int CST_W = 192;      // controller / sensor state, layout below
-constexpr int DFILT_W = 96;     // int32 drive FIR taps [10][9] padded
+constexpr int DFILT_W = 96;     // int32 drive FIR taps [10][9], then DF_TICK
+constexpr int DF_TICK = 90;     // control ticks since the last reset (int32): the clock of the optional open-loop gait generator
+constexpr int GAIT_W = 24;      // optional per-env sinusoidal gait on the motor-PD targets: amplitude[10], phase[10], frequency (Hz), pad
+constexpr int GA_AMP = 0, GA_PHASE = 10, GA_FREQ = 20;
 constexpr int PD_W = 52;        // torque, pTarget, dTarget, pGain, dGain for the 10 motors (+2 pad)
 constexpr int TASK_W = 64;      // optional task-space PD rows: per leg torque, pTarget, dTarget, pGain, dGain [6] each (left 0..29, right 30..59)
 constexpr int XFRC_W = 8;       // force xyz, torque xyz, body id (as real), pad
-constexpr int OBS_W = 96;       // the dynamic subset of cassie_out_t copied out at src/cassiemujoco.c:1127 + the decoded estimator outputs
+constexpr int OBS_W = 112;      // the dynamic subset of cassie_out_t copied out at src/cassiemujoco.c:1127 + the decoded estimator outputs (stateless part, then the filtered part)
 // CST offsets
 constexpr int CS_SENSOR = 0;    // sensordata[29]
 constexpr int CS_ACTVEL = 32;   // actuator_velocity[10]
@@ -111,6 +114,7 @@ constexpr int OB_EST_QUAT = 86;   // [4] pelvis.orientation (IMU quaternion thro
 // covariance recursion is the reference's unsymmetrised one and needs them) and a row of reals with its outputs
 constexpr int EST_W = 128;      // doubles: [0] started, [1..42] x axis (state 6, covariance 36), [43..84] y axis, [85..89] z state, [90..114] z covariance,
 constexpr int ES_X = 1, ES_Z = 85, ES_PZ = 90, ES_TERRAIN = 115, ES_FORCE = 116;   // [115] terrain, [116..121] leg forces (toeForce of each foot, double)
+constexpr int OB_EST_OUT = 96;  // [EO_W] the estimator's force model and filters, columns of the observation row (zero until cassie_batch_enable_estimator_device)
 constexpr int EO_W = 16;        // reals: pelvis.position 3, translationalVelocity 3, externalForce 3, terrain.height 1, toeForce (= heelForce) L 3, R 3
 constexpr int EO_POS = 0, EO_VEL = 3, EO_EXTF = 6, EO_TERRAIN = 9, EO_TOE = 10;
 constexpr int AUX_W = 64;

@@ -66,6 +66,7 @@ template <typename real> struct EnvPtrs {
   const real *pd;     // [PD_W] motor-PD row held for the launch
   const real *xfrc;   // [XFRC_W]
   const real *task;   // [TASK_W] task-space PD rows (pd_in_t taskPd of both legs) or null
+  const real *gait;   // [GAIT_W] open-loop gait on the motor-PD targets: pTarget_i(t) = pd.pTarget_i + amp_i sin(2 pi f t + phase_i), t = ticks since reset x 0.5 ms; or null
   real *obs;          // [OBS_W] or null
   real *qM;           // [2 NM_MAX] scratch: M (debug dump / set_const only), then the factor of M + h B carried from the CRB stage to the Euler stage
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
@@ -94,6 +95,8 @@ CFN float mmin(float a, float b) { return fminf(a, b); }
 CFN double mmin(double a, double b) { return fmin(a, b); }
 CFN float mpow(float a, float b) { return powf(a, b); }
 CFN double mpow(double a, double b) { return pow(a, b); }
+CFN float msin(float x) { return sinf(x); }
+CFN double msin(double x) { return sin(x); }
 CFN void msincos(float x, float *s, float *c) { sincosf(x, s, c); }
 CFN void msincos(double x, double *s, double *c) { sincos(x, s, c); }
 CFN float mrcp(float x) {
@@ -1459,6 +1462,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
   // forward_only: a single mj_forward with zero ctrl (cassie_sim_init / reset, src/cassiemujoco.c:1029); it shares the one inlined copy of
   // mj_substep with the stepping path so the kernel's instruction footprint stays small
   if (forward_only) nticks = 1;
+  const real *gait = E.gait; const int tick0 = ism[DF_TICK];
   for (int tick = 0; tick < nticks; ++tick) {
     if (forward_only) { LANES L(ctrl) = 0; ENDL }
     else {
@@ -1468,7 +1472,9 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       L(tq) = 0; L(scale_part) = 1;
       if (l < 10) {
         const real pos = cst[CS_DPOS + l], vel = cst[CS_DVEL + l]; const int k = l % 5;
-        const real u = pd[l] + pd[30 + l] * (pd[10 + l] - pos) + pd[40 + l] * (pd[20 + l] - vel);
+        real pT = pd[10 + l];
+        if (gait) pT += gait[GA_AMP + l] * msin(real(6.283185307179586) * gait[GA_FREQ] * ((real)(tick0 + tick) * real(0.0005)) + gait[GA_PHASE + l]);   // open-loop gait (BASELINE config 5)
+        const real u = pd[l] + pd[30 + l] * (pT - pos) + pd[40 + l] * (pd[20 + l] - vel);
         real add = 0, sc = 1;
         const real dhi = pos - (core_hi_deg<real>(l) * DEG - W), dlo = (core_lo_deg<real>(l) * DEG + W) - pos;
         if (dhi > 0) { add -= core_K<real>(k) * dhi * (1 + dhi / W) + core_C<real>(k) * mmin(dhi / W, real(1)) * vel; sc *= mmax(real(0), 1 - dhi / W); }
@@ -1636,6 +1642,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     const int nsub = forward_only ? 1 : cm.nsub;
     for (int s = 0; s < nsub; ++s) mj_substep<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, (tick == nticks - 1 && s == nsub - 1) ? E.aux : (real *)0, mode);
   }
+  if (!forward_only) { LANES if (l == 0) ism[DF_TICK] = tick0 + nticks; ENDL }
 }
 
 }  // namespace cassie

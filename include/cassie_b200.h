@@ -111,7 +111,7 @@ void cassie_sim_radio(cassie_sim_t *sim, double channels[16]);
 #define CASSIE_B200_FP32 0 /* throughput build: state and arithmetic in fp32 */
 #define CASSIE_B200_FP64 1 /* parity build: state and arithmetic in fp64 */
 #define CASSIE_PD_WIDTH 52  /* compact motor-PD row: torque[10] pTarget[10] dTarget[10] pGain[10] dGain[10] pad[2] */
-#define CASSIE_OBS_WIDTH 96 /* compact observation row, see cassie_batch_get_obs */
+#define CASSIE_OBS_WIDTH 112 /* compact observation row, see cassie_batch_get_obs */
 #define CASSIE_AUX_WIDTH 64 /* derived-quantity row, see cassie_batch_get_aux */
 /* offsets inside a derived-quantity row */
 #define CASSIE_AUX_FOOT_FORCE 0   /* [12] cassie_sim_foot_forces layout: left xyz, 3 zeros, right xyz, 3 zeros */
@@ -154,12 +154,18 @@ void cassie_batch_set_pd(cassie_batch_t *b, const double *pd);
  * pd_input_step uses them (decoded, pinned to the archive): foot position in the pelvis frame, then yaw / pitch / roll of the foot
  * frame; rates in the foot frame.  cassie_sim_step_pd(_batch) forward pd_in_t's taskPd fields automatically.  0 / -1. */
 int cassie_batch_set_task_pd(cassie_batch_t *b, const double *rows);
+/* Open-loop gait on top of the motor-PD rows (BASELINE config 5 "random PD gaits"): in every control tick of every launch
+ * pTarget_i(t) = row.pTarget_i + amp_i sin(2 pi freq t + phase_i), t = control ticks since the last reset (or since this call) x 0.5 ms.
+ * amp [n][10], freq [n] (Hz), phase [n][10]; all NULL switches it off.  New verb: the reference moves its targets from the host every tick. */
+int cassie_batch_set_pd_gait(cassie_batch_t *b, const double *amp, const double *freq, const double *phase);
 void cassie_batch_step(cassie_batch_t *b, int nticks);
 void cassie_batch_sync(cassie_batch_t *b);
 /* host copies (synchronous): qpos [n][35], qvel [n][32], time [n], obs [n][CASSIE_OBS_WIDTH] =
  * motor pos[10] vel[10] torque[10], joint pos[6] vel[6], IMU quat[4] gyro[3] accel[3] mag[3], time (0..55);
  * estimator: translationalAcceleration[3] (56), pad, per foot {position 3, orientation 4, rotational velocity 3, translational
- * velocity 3} left (60..72) right (73..85), pelvis.orientation[4] (86..89; the IMU quaternion up to sign), pad */
+ * velocity 3} left (60..72) right (73..85), pelvis.orientation[4] (86..89; the IMU quaternion up to sign), pad;
+ * in-kernel estimator (cassie_batch_enable_estimator_device; zero while it is off): pelvis.position[3] (96), translationalVelocity[3] (99),
+ * externalForce[3] (102), terrain.height (105), toeForce = heelForce left[3] (106) right[3] (109) */
 void cassie_batch_get_qpos(cassie_batch_t *b, double *out);
 void cassie_batch_set_qpos(cassie_batch_t *b, const double *in);
 void cassie_batch_get_qvel(cassie_batch_t *b, double *out);
@@ -205,9 +211,12 @@ void cassie_b200_estimator_leg_force(int side, const double ang[7], const double
  * ..._step reads orientation, translationalAcceleration, both feet's position and toe / heel forces from *y and writes the four outputs. */
 int cassie_batch_enable_estimator_filter(cassie_batch_t *b, int on);
 /* The same estimator inside the step kernel (leg forces + filters, every 2 kHz tick of a launch, so multi-tick launches keep it exact and
- * device-resident observations are complete): one [n][CASSIE_EST_WIDTH] row per environment, device pointer "est_out" --
+ * device-resident observations are complete): columns 96..111 of the observation row ("obs"), also copied out by cassie_batch_get_estimator --
  * pelvis.position 3, translationalVelocity 3, externalForce 3, terrain.height 1, toeForce (= heelForce) left 3, right 3.
- * The filter state is held in doubles in every batch precision.  cassie_batch_reset(_estimator) restarts it. */
+ * The filter state is held in doubles in every batch precision.  cassie_batch_reset(_estimator) restarts it.
+ * cassie_sim_step_pd_batch switches it on by itself at the first call that asks for state_out_t rows, because cassie_sim_step_pd runs
+ * state_output_step in every call (src/cassiemujoco.c:1156); cassie_batch_enable_estimator_device(b, 0) keeps it off (the filtered fields,
+ * toeForce and heelForce of state_out_t are then zero).  A cassie_sim_t always runs it. */
 #define CASSIE_EST_WIDTH 16
 int cassie_batch_enable_estimator_device(cassie_batch_t *b, int on);
 int cassie_batch_get_estimator(cassie_batch_t *b, double *out /* [n][CASSIE_EST_WIDTH] */);
@@ -231,7 +240,7 @@ int cassie_batch_hfield_nrow(const cassie_batch_t *b);
 int cassie_batch_hfield_ncol(const cassie_batch_t *b);
 
 /* zero-copy access for a PyTorch / DLPack caller: device pointer of a state array ("qpos" [n][36], "qvel" [n][32],
- * "pd" [n][52], "obs" [n][96], "xfrc" [n][8], "aux" [n][64]) in the batch precision; the stream all work is enqueued on (cudaStream_t). */
+ * "pd" [n][52], "obs" [n][112], "xfrc" [n][8], "aux" [n][64]) in the batch precision; the stream all work is enqueued on (cudaStream_t). */
 void *cassie_batch_device_ptr(cassie_batch_t *b, const char *field);
 void cassie_batch_set_stream(cassie_batch_t *b, void *cuda_stream);
 void *cassie_batch_get_stream(cassie_batch_t *b);

@@ -14,8 +14,8 @@ using namespace cassie;
 
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; BuildInfo info; std::vector<real> sm; std::vector<int> ism;
-  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[2 * NM_MAX], aux[AUX_W], cenv[CE_W], task[TASK_W]; int counters[8]; double est[EST_W]; real est_out[EO_W]; bool use_est = false; bool use_task = false; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
-  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.task = use_task ? task : nullptr; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); E.est = use_est ? est : nullptr; E.est_out = est_out; return E; }
+  real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[2 * NM_MAX], aux[AUX_W], cenv[CE_W], task[TASK_W], gait[GAIT_W]; bool use_gait = false; int counters[8]; double est[EST_W]; bool use_est = false; bool use_task = false; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.task = use_task ? task : nullptr; E.gait = use_gait ? gait : nullptr; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); E.est = use_est ? est : nullptr; E.est_out = obs + OB_EST_OUT; return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
@@ -26,7 +26,7 @@ template <typename real> struct Emu {
     init_env_rows(hm, qpos.data(), qv.data(), qa.data(), cst, ism.data(), xfrc);
     for (int i = 0; i < 32; i++) { qvel[i] = qv[i]; qacc_ws[i] = qa[i]; xqvel[i] = 0; xqacc_ws[i] = 0; }
     for (int i = 0; i < QPOS_W_XB; i++) sm[S_QPOS + i] = qpos[i];
-    std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters); std::memset(aux, 0, sizeof aux); std::memset(est, 0, sizeof est); std::memset(est_out, 0, sizeof est_out);
+    std::memset(pd, 0, sizeof pd); std::memset(obs, 0, sizeof obs); std::memset(dbg, 0, sizeof dbg); std::memset(counters, 0, sizeof counters); std::memset(aux, 0, sizeof aux); std::memset(est, 0, sizeof est);
     forward();
     return true;
   }
@@ -74,6 +74,9 @@ void emu_enable_cenv(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.enabl
 void emu_set_task(void *p, const double *rows60) { Handle *h = (Handle *)p;
   if (h->fp32) { h->f.use_task = rows60 != nullptr; if (rows60) for (int i = 0; i < 60; i++) h->f.task[i] = (float)rows60[i]; }
   else { h->d.use_task = rows60 != nullptr; if (rows60) for (int i = 0; i < 60; i++) h->d.task[i] = rows60[i]; } }
+void emu_set_gait(void *p, const double *row21) { Handle *h = (Handle *)p;   // amp[10], phase[10], freq; null: off.  Restarts the tick clock.
+  if (h->fp32) { h->f.use_gait = row21 != nullptr; h->f.ism[DF_TICK] = 0; if (row21) for (int i = 0; i < 21; i++) h->f.gait[i] = (float)row21[i]; }
+  else { h->d.use_gait = row21 != nullptr; h->d.ism[DF_TICK] = 0; if (row21) for (int i = 0; i < 21; i++) h->d.gait[i] = row21[i]; } }
 void emu_enable_est(void *p, int on) { Handle *h = (Handle *)p; if (h->fp32) { h->f.use_est = on; std::memset(h->f.est, 0, sizeof h->f.est); } else { h->d.use_est = on; std::memset(h->d.est, 0, sizeof h->d.est); } }   // (re)start the in-kernel estimator
 void emu_query(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.query(); else h->d.query(); }
 void emu_forward(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.forward(); else h->d.forward(); }
@@ -83,7 +86,7 @@ int emu_get(void *p, const char *name, double *out, int n) {
 #define GET(T, E) { const T *src = nullptr; int cnt = 0; \
   if (k == "qpos") { src = E.sm.data() + S_QPOS; cnt = QPOS_W_XB; } else if (k == "xqvel") { src = E.xqvel; cnt = 6; } else if (k == "qvel") { src = E.qvel; cnt = 32; } else if (k == "qacc_ws") { src = E.qacc_ws; cnt = 32; } \
   else if (k == "cst") { src = E.cst; cnt = CST_W; } else if (k == "obs") { src = E.obs; cnt = OBS_W; } else if (k == "dbg") { src = E.dbg; cnt = D_SIZE; } \
-  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } else if (k == "aux") { src = E.aux; cnt = AUX_W; } else if (k == "cenv") { src = E.cenv; cnt = CE_W; } else if (k == "est_out") { src = E.est_out; cnt = EO_W; } \
+  else if (k == "xfrc") { src = E.xfrc; cnt = XFRC_W; } else if (k == "aux") { src = E.aux; cnt = AUX_W; } else if (k == "cenv") { src = E.cenv; cnt = CE_W; } else if (k == "est_out") { src = E.obs + OB_EST_OUT; cnt = EO_W; } \
   if (src) { if (cnt > n) cnt = n; for (int i = 0; i < cnt; i++) out[i] = (double)src[i]; return cnt; } \
   if (k == "dfilt") { int c2 = DFILT_W < n ? DFILT_W : n; for (int i = 0; i < c2; i++) out[i] = E.ism[i]; return c2; } \
   if (k == "counters") { int c2 = 8 < n ? 8 : n; for (int i = 0; i < c2; i++) out[i] = E.counters[i]; return c2; } }

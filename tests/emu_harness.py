@@ -88,6 +88,15 @@ class EmuSim:
             assert a.size == 60
             self.L.emu_set_task(self.h, a.ctypes.data_as(C.POINTER(C.c_double)))
 
+    def set_gait(self, amp, phase, freq):
+        """open-loop gait on the motor-PD targets (amp[10], phase[10], freq in Hz) or amp=None: off"""
+        self.L.emu_set_gait.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        if amp is None:
+            self.L.emu_set_gait(self.h, None)
+        else:
+            a = np.ascontiguousarray(np.concatenate([amp, phase, [freq]]), dtype=np.float64)
+            self.L.emu_set_gait(self.h, a.ctypes.data_as(C.POINTER(C.c_double)))
+
     def enable_est(self, on=True):
         """in-kernel estimator (forces + filters) of the extended instance; enabling restarts it"""
         self.L.emu_enable_est.argtypes = [C.c_void_p, C.c_int]

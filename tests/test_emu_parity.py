@@ -135,3 +135,24 @@ def test_in_kernel_estimator_matches_oracle(oracle_mod, pkg):
             worst = max(worst, (np.abs(a - e.get('est_out')) / (1 + np.abs(a))).max())
         assert worst < 1e-10 and abs(a[8]) > 1 and a[12] < -50, (nt, worst)
         e.close()
+
+
+def test_open_loop_gait_follows_per_tick_targets(oracle_mod):
+    """cassie_batch_set_pd_gait (BASELINE config 5's "random PD gaits"): the kernel moves pTarget itself every control tick of a multi-tick
+    launch; the oracle is handed the same targets from outside, one pd_in_t per tick, as a caller of the reference would"""
+    import emu_harness as E
+    amp, ph, f = np.array([0.05, 0.05, 0.3, 0.4, 0.3] * 2), np.array([0.3] * 5 + [0.3 + np.pi] * 5), 1.2
+    o, e = oracle_mod.OracleSim(OMODEL), E.EmuSim(CMODEL)
+    e.plain()
+    e.set_gait(amp, ph, f)
+    for k in range(450):
+        o.step_pd(oracle_mod.make_pd(pTarget=np.array(PD_TARGET) + amp * np.sin(2 * np.pi * f * k * 0.0005 + ph), pGain=PD_PGAIN, dGain=PD_DGAIN))
+        if k % 3 == 0:
+            e.step(PD_ROW, 3)
+        if k % 3 == 2:
+            assert np.abs(e.get('qpos')[:35] - o.arr('qpos')).max() < 1e-10, k
+    assert abs(o.arr('qpos')[14] - (-1.1997)) > 0.05      # the knees really moved
+    e.set_gait(None, None, None)
+    q = e.get('qpos').copy()
+    e.step(PD_ROW, 1)
+    assert np.abs(e.get('qpos') - q).max() > 0

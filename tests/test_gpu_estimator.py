@@ -58,10 +58,12 @@ def test_batch_rows_and_aos(P, oracle_mod):
     rows = b.obs()
     for e in (0, n - 1):
         row_vs_state_out(rows[e], ys[e], 1e-12)
-    assert ys[0].leftFoot.toeForce[2] == 0                      # batches: off by default
-    P.lib().cassie_batch_enable_estimator_forces(b.h, 1)
+    assert abs(ys[0].leftFoot.toeForce[2]) > 10 and ys[0].leftFoot.toeForce[2] == ys[0].leftFoot.heelForce[2]    # in-kernel estimator: on by default for the AoS entry point
+    assert rows[0][P.OBS['est_left_toe_force']][2] == ys[0].leftFoot.toeForce[2] and rows[0][P.OBS['est_position']][2] == ys[0].pelvis.position[2]
+    dev = ys[0].leftFoot.toeForce[2]
+    P.lib().cassie_batch_enable_estimator_forces(b.h, 1)        # host-side checker of the same function
     ys = b.step_pd(pin)
-    assert abs(ys[0].leftFoot.toeForce[2]) > 10 and ys[0].leftFoot.toeForce[2] == ys[0].leftFoot.heelForce[2]
+    assert abs(ys[0].leftFoot.toeForce[2] - dev) < 1e-3 * abs(dev)
     b32 = P.CassieBatch(n, precision=P.FP32)
     b32.set_pd(P.pd_rows(n, pTarget=PD_TARGET, pGain=PD_PGAIN, dGain=PD_DGAIN))
     b32.step(300)

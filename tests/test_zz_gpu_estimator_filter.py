@@ -47,12 +47,17 @@ def test_batch_filters_follow_each_environment():
     P = product()
     n = 4
     b0 = P.CassieBatch(1, precision=P.FP64)
-    y0 = b0.step_pd((P.pd_in_t * 1)(_pd(P)))
-    assert not any(y0[0].pelvis.position[:]) and not any(y0[0].pelvis.externalForce[:])     # batches: off by default
+    pin1 = (P.pd_in_t * 1)(_pd(P))
+    y0 = b0.step_pd(pin1)
+    # cassie_sim_step_pd_batch is output-equivalent to cassie_sim_step_pd: the in-kernel estimator comes on with the first call ...
+    assert y0[0].pelvis.externalForce[2] == pytest.approx(31 * 9.806, rel=1e-3) and y0[0].pelvis.position[2] != 0
+    b0.enable_estimator_device(False)      # ... unless the caller opts out: the filtered fields and the leg forces are then zero
+    y0 = b0.step_pd(pin1)
+    assert not any(y0[0].pelvis.position[:]) and not any(y0[0].pelvis.externalForce[:]) and not any(y0[0].leftFoot.toeForce[:])
     b = P.CassieBatch(n, precision=P.FP64)
     pin = (P.pd_in_t * n)(*[_pd(P) for _ in range(n)])
-    b.enable_estimator()
-    c = P.CassieSim()
+    b.enable_estimator()                   # the host-side checker (one filter object per environment); the kernel stage stays off
+    c = P.CassieSim()                       # runs the in-kernel estimator
     for k in range(300):
         ys = b.step_pd(pin)
         yc = c.step_pd(pin[0])
