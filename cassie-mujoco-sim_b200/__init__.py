@@ -434,6 +434,11 @@ class CassieBatch:
         if self.L.cassie_batch_set_hfielddata(self.h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0]) != 0:
             raise RuntimeError(_last_error())
 
+    def row_width(self, field):
+        """row width (elements) of a device array: qpos 36 (44 with the extra free body), qvel 32 (40), pd 52, obs 112, xfrc 8, aux 64"""
+        self.L.cassie_batch_row_width.argtypes = [C.c_void_p, C.c_char_p]
+        return int(self.L.cassie_batch_row_width(self.h, field.encode()))
+
     def counters(self):
         out = np.zeros((self.n, 8), dtype=np.int32)
         self.L.cassie_batch_get_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int)))

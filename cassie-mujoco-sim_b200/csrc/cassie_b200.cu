@@ -4,6 +4,7 @@
 // a TMA bulk copy (cp.async.bulk + mbarrier, SASS: UBLKCP), then every warp loads its environment's state rows from HBM
 // (coalesced, one row per array), advances `nticks` control ticks entirely on chip (step_core.inl) and writes the rows back.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -39,7 +40,7 @@ static int effective_cpus() {
 }
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,6 +96,9 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     else if (l < 9) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dfilt + (size_t)env * DFILT_W + 32 * (l - 6)));
     else if (l < 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pd + (size_t)env * PD_W + 32 * (l - 9)));
     else if (l == 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.xfrc + (size_t)env * XFRC_W));
+    // optional zero-copy input: this environment's motor-PD row straight from mapped host memory into its device row (the AoS entry point
+    // uses one DMA instead: 2 x 4096 small PCIe reads at kernel start were measured slower than the copy engine; kept for C2C-attached hosts)
+    if (A.pd_host) { for (int i = l; i < PD_W; i += 32) A.pd[(size_t)env * PD_W + i] = A.pd_host[(size_t)env * PD_W + i]; }
     // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
     for (int i = l; i < qw; i += 32) sm[S_QPOS + i] = (mode == 3) ? cm.qpos0[i] : A.qpos[(size_t)env * qw + i];   // set_const works at the reference configuration
     real qvel = A.qvel[(size_t)env * vw + l], qacc_ws = A.qacc_ws[(size_t)env * vw + l], xqvel = 0, xqacc_ws = 0;
@@ -112,6 +116,8 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     for (int i = l; i < qw; i += 32) A.qpos[(size_t)env * qw + i] = sm[S_QPOS + i];
     A.qvel[(size_t)env * vw + l] = qvel; A.qacc_ws[(size_t)env * vw + l] = qacc_ws;
     if (A.xb >= 0 && l < 6) { A.qvel[(size_t)env * vw + 32 + l] = xqvel; A.qacc_ws[(size_t)env * vw + 32 + l] = xqacc_ws; }
+    // ... and its observation row goes back the same way as soon as the environment is done, overlapped with the environments still stepping
+    if (A.obs_host) { for (int i = l; i < OBS_W; i += 32) A.obs_host[(size_t)env * OBS_W + i] = A.obs[(size_t)env * OBS_W + i]; }
     __syncwarp();
   }
 }
@@ -201,6 +207,8 @@ struct BatchBase {
   virtual ~BatchBase() {}
   bool est_forces = false;   // fill toeForce / heelForce of state_out_t on the host (cassie_batch_enable_estimator_forces)
   bool est_filter = false;   // run the estimator's filters on the host, one per environment (cassie_batch_enable_estimator_filter; needs est_forces): the checker of the in-kernel estimator
+  double aos_t[6] = {0, 0, 0, 0, 0, 0}; cudaEvent_t aos_ev[3] = {nullptr, nullptr, nullptr};   // [4] [5]: H2D and kernel milliseconds by CUDA events, only with CASSIE_B200_AOS_EVENTS set
+  double aos_unused[1] = {0};   // accumulated seconds of the AoS entry point: host pack, device (copies + kernel, as waited for), host unpack; [3] calls
   bool est_auto = true;      // cassie_sim_step_pd_batch switches the in-kernel estimator on by itself (cassie_batch_enable_estimator_device(b, 0) clears this)
   std::vector<cassie::EstimatorFilter> est_state;
   void reset_estimator(const unsigned char *mask) { for (size_t e = 0; e < est_state.size(); e++) if (!mask || mask[e]) est_state[e].reset(); }
@@ -235,6 +243,7 @@ template <typename real> struct Batch : BatchBase {
   struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[2];   // [0] plain instance, [1] extended instance
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr, *pin_task = nullptr;   // pinned staging for the AoS entry point
+  real *dpin_pd = nullptr, *dpin_obs = nullptr;                      // the same buffers as the device sees them (mapped)
   bool task_from_aos = false;   // the task-PD rows were created by the AoS entry point's forwarding (not by cassie_batch_set_task_pd)
   float *d_hfield = nullptr; unsigned char *d_mask = nullptr; DevModel<real> h_model_copy{}; int geom_dev[256]; void *d_row = nullptr;
   ~Batch() override {
@@ -248,7 +257,8 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaSetDevice(device));
     DevModel<real> *hmodel = (DevModel<real> *)calloc(1, model_bytes<real>()); std::string err; BuildInfo info;
     if (!build_dev_model(hm, *hmodel, err, &info)) { free(hmodel); set_err(err); return false; }
-    if (info.unsupported_pairs) fprintf(stderr, "cassie_b200: note: %d candidate geom pairs involve box/hfield geoms that this build does not collide (skipped)\n", info.unsupported_pairs);
+    static bool noted = false;   // once per process
+    if (info.unsupported_pairs && !noted) noted = true, fprintf(stderr, "cassie_b200: note: %d candidate geom pairs involve box/hfield geoms that this build does not collide (skipped)\n", info.unsupported_pairs);
     CUDA_OK(cudaMalloc(&d_model, model_bytes<real>()));
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
     h_model_copy = *hmodel; memcpy(geom_dev, info.geom_dev, sizeof geom_dev);
@@ -389,7 +399,11 @@ template <typename real> struct Batch : BatchBase {
   bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) override {
     CUDA_OK(cudaSetDevice(device));
     static const int aos_threads = [] { const char *e = getenv("CASSIE_B200_AOS_THREADS"); int t = e ? atoi(e) : 32; const int hw = effective_cpus(); if (t > hw) t = hw; return t < 1 ? 1 : t; }();   // host pack / unpack threads
-    if (!pin_pd) { CUDA_OK(cudaMallocHost(&pin_pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMallocHost(&pin_obs, sizeof(real) * n * OBS_W)); }
+    if (!pin_pd) {   // pinned AND mapped: the step kernel itself reads the PD rows from / writes the observation rows to these buffers
+      CUDA_OK(cudaHostAlloc(&pin_pd, sizeof(real) * n * PD_W, cudaHostAllocMapped)); CUDA_OK(cudaHostAlloc(&pin_obs, sizeof(real) * n * OBS_W, cudaHostAllocMapped));
+      CUDA_OK(cudaHostGetDevicePointer(&dpin_pd, pin_pd, 0)); CUDA_OK(cudaHostGetDevicePointer(&dpin_obs, pin_obs, 0));
+    }
+    const auto tp0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
     for (int e = 0; e < n; e++) {
       real *row = pin_pd + (size_t)e * PD_W; const pd_in_t *u = pd_in + e;
@@ -415,14 +429,22 @@ template <typename real> struct Batch : BatchBase {
         CUDA_OK(cudaMemcpyAsync(A.task, pin_task, sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream));
       } else if (A.task && task_from_aos) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; task_from_aos = false; }   // rows installed with cassie_batch_set_task_pd stay
     }
-    CUDA_OK(cudaMemcpyAsync(A.pd, pin_pd, sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));
+    const auto tp1 = std::chrono::steady_clock::now();
     // cassie_sim_step_pd runs state_output_step in every call (src/cassiemujoco.c:1156): so does the batched entry point, inside the kernel,
     // from the first call that asks for state_out_t rows (unless the caller switched it off or runs the host-side checker instead)
     if (state_out && est_auto && !A.est && !est_filter && !enable_estimator_device(true)) return false;
-    if (!step(1, 0)) return false;
+    static const bool aos_events = getenv("CASSIE_B200_AOS_EVENTS") != nullptr;
+    if (aos_events) { if (!aos_ev[0]) for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&aos_ev[i])); CUDA_OK(cudaEventRecord(aos_ev[0], stream)); }
+    CUDA_OK(cudaMemcpyAsync(A.pd, pin_pd, sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));   // one DMA: a burst of small PCIe reads from every warp at kernel start measured slower
+    A.pd_host = nullptr; A.obs_host = state_out ? dpin_obs : nullptr;
+    if (aos_events) CUDA_OK(cudaEventRecord(aos_ev[1], stream));
+    const bool launched = step(1, 0);
+    if (aos_events) CUDA_OK(cudaEventRecord(aos_ev[2], stream));
+    A.pd_host = nullptr; A.obs_host = nullptr;
+    if (!launched) return false;
     if (!state_out) return sync();
-    CUDA_OK(cudaMemcpyAsync(pin_obs, A.obs, sizeof(real) * n * OBS_W, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+    const auto tp2 = std::chrono::steady_clock::now();
     if (est_filter && est_state.size() != (size_t)n) est_state.assign((size_t)n, cassie::EstimatorFilter());
     const bool dev_est = A.est != nullptr;   // the estimator ran inside the kernel: its outputs are columns of the observation row
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
@@ -458,6 +480,9 @@ template <typename real> struct Batch : BatchBase {
       memset(&y->radio.signalGood, 0, sizeof(double)); y->radio.signalGood = true;   // the bool and its padding
       y->battery.stateOfCharge = 1; y->battery.current = 0;
     }
+    { const auto tp3 = std::chrono::steady_clock::now(); auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+      aos_t[0] += sec(tp0, tp1); aos_t[1] += sec(tp1, tp2); aos_t[2] += sec(tp2, tp3); aos_t[3] += 1;
+      if (aos_events) { float a = 0, b = 0; cudaEventElapsedTime(&a, aos_ev[0], aos_ev[1]); cudaEventElapsedTime(&b, aos_ev[1], aos_ev[2]); aos_t[4] += a; aos_t[5] += b; } }
     return true;
   }
   // K terrains of nrow*ncol normalised elevations; environment e stands on terrain e % K (cassie_sim_set_hfielddata, src/cassiemujoco.c:2076-2080)
@@ -525,10 +550,11 @@ template <typename real> struct Batch : BatchBase {
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
-    const LaunchCfg &c = cfg[(A.cenv || A.aux || A.task) ? 1 : 0];
+    const bool ext = A.cenv || A.aux || A.task || A.est;   // per-environment model constants / derived-quantity rows / task-space PD / in-kernel estimator: extended instance (its own scratch size and launch shape)
+    const LaunchCfg &c = cfg[ext ? 1 : 0];
     int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
-    if (A.cenv || A.aux || A.task || A.est) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);   // per-environment model constants / derived-quantity rows in use
+    if (ext) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
     else cassie_step_kernel<real, false><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
     launches++;
     CUDA_OK(cudaGetLastError());
@@ -705,6 +731,8 @@ void *cassie_batch_get_stream(cassie_batch_t *b) { return (void *)b->impl->strea
 void cassie_batch_get_counters(cassie_batch_t *b, int *out) { b->impl->get_counters(out); }
 int cassie_batch_debug_dump(cassie_batch_t *b, int env, double *out, int n) { return b->impl->debug_dump(env, out, n); }
 
+void cassie_batch_aos_timing(cassie_batch_t *b, double out[6], int reset) { for (int i = 0; i < 6; i++) out[i] = b->impl->aos_t[i]; if (reset) for (int i = 0; i < 6; i++) b->impl->aos_t[i] = 0; }
+int cassie_b200_effective_cpus(void) { return cassie::effective_cpus(); }
 void cassie_sim_step_pd_batch(cassie_batch_t *b, const pd_in_t *pd_in, state_out_t *state_out) {
   b->impl->step_pd_aos(pd_in, state_out, b->radio.data());
 }

@@ -18,53 +18,57 @@
 
 namespace cassie {
 
-struct V3 { double x, y, z; };
-CASSIE_HD inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-CASSIE_HD inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-CASSIE_HD inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
-CASSIE_HD inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-CASSIE_HD inline V3 crs(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-struct M3 { V3 c0, c1, c2; };   // columns
-CASSIE_HD inline V3 operator*(const M3 &m, V3 v) { return v.x * m.c0 + v.y * m.c1 + v.z * m.c2; }
-CASSIE_HD inline M3 operator*(const M3 &a, const M3 &b) { return {a * b.c0, a * b.c1, a * b.c2}; }
-CASSIE_HD inline M3 rotz(double t) { const double c = std::cos(t), s = std::sin(t); return {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; }
+template <typename T> struct V3T { T x, y, z; };
+template <typename T> CASSIE_HD inline V3T<T> operator+(V3T<T> a, V3T<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename T> CASSIE_HD inline V3T<T> operator-(V3T<T> a, V3T<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename T> CASSIE_HD inline V3T<T> operator*(T s, V3T<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename T> CASSIE_HD inline T dot(V3T<T> a, V3T<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> CASSIE_HD inline V3T<T> crs(V3T<T> a, V3T<T> b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+template <typename T> struct M3T { V3T<T> c0, c1, c2; };   // columns
+template <typename T> CASSIE_HD inline V3T<T> operator*(const M3T<T> &m, V3T<T> v) { return v.x * m.c0 + v.y * m.c1 + v.z * m.c2; }
+template <typename T> CASSIE_HD inline M3T<T> operator*(const M3T<T> &a, const M3T<T> &b) { return {a * b.c0, a * b.c1, a * b.c2}; }
+template <typename T> CASSIE_HD inline M3T<T> rotz(T t) { const T c = std::cos(t), s = std::sin(t); return {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; }
+using V3 = V3T<double>; using M3 = M3T<double>;
 
-// ang: hipRoll, hipYaw, hipPitch, knee (motor positions), shin, tarsus (joint encoders), foot (motor position); quat: IMU quaternion (w, x, y, z)
-CASSIE_HD inline void estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) {
-  const double sg = side ? -1.0 : 1.0, kn = ang[3], sh = ang[4], ta = ang[5];
+// ang: hipRoll, hipYaw, hipPitch, knee (motor positions), shin, tarsus (joint encoders), foot (motor position); quat: IMU quaternion (w, x, y, z).
+// T = double on the host and in fp64 batches; the fp32 kernel instance evaluates it in float, which is the archive's own precision for this block
+template <typename T>
+CASSIE_HD inline void estimator_leg_force_t(int side, const T ang[7], const T quat[4], T force[3]) {
+  typedef V3T<T> V; typedef M3T<T> M;
+  const T sg = side ? T(-1) : T(1), kn = ang[3], sh = ang[4], ta = ang[5];
   // ---- planar part in the hip-pitch frame (z = common axis of knee, shin, tarsus): the four-bar closure
-  const V3 A{0, 0, 0.045 * sg}, k0{0.12, 0, 0.0045 * sg}, o4{0.06068, 0.04741, 0}, o5{0.43476, 0.02, 0}, hsp{-0.01269, -0.03059, 0.00092 * sg}, Bl{0.11877, -0.01, 0}, ez{0, 0, 1};
-  V3 hx{-0.91211, 0.40829, 0.036948 * sg}, hy{-0.40992, -0.90952, -0.068841 * sg};
-  hx = (1.0 / std::sqrt(dot(hx, hx))) * hx; hy = hy - dot(hx, hy) * hx; hy = (1.0 / std::sqrt(dot(hy, hy))) * hy;
-  const M3 HF{hx, hy, crs(hx, hy)};
-  const V3 s0 = k0 + rotz(kn) * o4, t0 = s0 + rotz(kn + sh) * o5;
-  const M3 R3 = rotz(kn + sh + ta), RH = R3 * HF;
-  const V3 hs0 = t0 + R3 * hsp, axh = RH.c2;
-  double H = 0, gd = 1; V3 B{}, dB{};
+  const V A{0, 0, T(0.045) * sg}, k0{T(0.12), 0, T(0.0045) * sg}, o4{T(0.06068), T(0.04741), 0}, o5{T(0.43476), T(0.02), 0}, hsp{T(-0.01269), T(-0.03059), T(0.00092) * sg}, Bl{T(0.11877), T(-0.01), 0}, ez{0, 0, 1};
+  V hx{T(-0.91211), T(0.40829), T(0.036948) * sg}, hy{T(-0.40992), T(-0.90952), T(-0.068841) * sg};
+  hx = (T(1) / std::sqrt(dot(hx, hx))) * hx; hy = hy - dot(hx, hy) * hx; hy = (T(1) / std::sqrt(dot(hy, hy))) * hy;
+  const M HF{hx, hy, crs(hx, hy)};
+  const V s0 = k0 + rotz(kn) * o4, t0 = s0 + rotz(kn + sh) * o5;
+  const M R3 = rotz(kn + sh + ta), RH = R3 * HF;
+  const V hs0 = t0 + R3 * hsp, axh = RH.c2;
+  T H = 0, gd = 1; V B{}, dB{};
   for (int it = 0; it < 5; it++) {   // Newton on |B - A|^2 = L^2 (quadratic: 5 steps from 0 reach the last bit for |H| < 0.3)
     B = hs0 + RH * (rotz(H) * Bl); dB = B - A;
     gd = 2 * dot(dB, crs(axh, B - hs0));
-    if (it < 4) H -= (dot(dB, dB) - 0.5012 * 0.5012) / gd;
+    if (it < 4) H -= (dot(dB, dB) - T(0.5012) * T(0.5012)) / gd;
   }
-  const double a = -2 * dot(dB, crs(ez, B - t0)) / gd, b = -2 * dot(dB, crs(ez, B - s0)) / gd;   // dH/dtarsus, dH/dshin
-  // ---- serial chain pelvis -> hip roll -> hip yaw -> hip pitch: frame A2 and origin p2 of the hip-pitch link (exact quarter turns)
-  const M3 F0{{0, 0, -1}, {0, 1, 0}, {1, 0, 0}}, F1{{0, 0, 1}, {0, 1, 0}, {-1, 0, 0}}, F2{{0, 0, -1}, {1, 0, 0}, {0, -1, 0}};
-  const M3 A0 = F0 * rotz(ang[0]); const V3 p1 = V3{0.021, 0.135 * sg, 0} + A0 * V3{0, 0, -0.07};
-  const M3 A1 = A0 * F1 * rotz(ang[1]); const V3 p2 = p1 + A1 * V3{0, 0, -0.09};
-  const M3 A2 = A1 * F2 * rotz(ang[2]);
+  const T a = -2 * dot(dB, crs(ez, B - t0)) / gd, b = -2 * dot(dB, crs(ez, B - s0)) / gd;   // dH/dtarsus, dH/dshin
+  // ---- serial chain pelvis -> hip roll -> hip yaw -> hip pitch: frame A2 of the hip-pitch link (exact quarter turns)
+  const M F0{{0, 0, -1}, {0, 1, 0}, {1, 0, 0}}, F1{{0, 0, 1}, {0, 1, 0}, {-1, 0, 0}}, F2{{0, 0, -1}, {1, 0, 0}, {0, -1, 0}};
+  const M A0 = F0 * rotz(ang[0]);
+  const M A1 = A0 * F1 * rotz(ang[1]);
+  const M A2 = A1 * F2 * rotz(ang[2]);
   // foot point in the hip-pitch frame and its partials w.r.t. shin / tarsus (rotations about z through s0 / t0)
-  const V3 f0 = t0 + R3 * V3{0.408, -0.04, 0}, u = f0 + rotz(kn + sh + ta + ang[6]) * V3{0.01762, 0.05219, 0};
-  const V3 ps = A2 * crs(ez, u - s0), pt = A2 * crs(ez, u - t0);
-  (void)p2;
-  const double j00 = ps.x - pt.x * b / a, j10 = ps.z - pt.z * b / a, j01 = pt.x / a, j11 = pt.z / a, det = j00 * j11 - j10 * j01;
-  const double t0_ = 1500.0 * sh, t1_ = 1250.0 * (H - 2.586e-6);
-  const double fx = -0.5 * (t0_ * j11 - t1_ * j10) / det, fz = -0.5 * (-t0_ * j01 + t1_ * j00) / det;
+  const V f0 = t0 + R3 * V{T(0.408), T(-0.04), 0}, u = f0 + rotz(kn + sh + ta + ang[6]) * V{T(0.01762), T(0.05219), 0};
+  const V ps = A2 * crs(ez, u - s0), pt = A2 * crs(ez, u - t0);
+  const T j00 = ps.x - pt.x * b / a, j10 = ps.z - pt.z * b / a, j01 = pt.x / a, j11 = pt.z / a, det = j00 * j11 - j10 * j01;
+  const T t0_ = T(1500.0) * sh, t1_ = T(1250.0) * (H - T(2.586e-6));
+  const T fx = T(-0.5) * (t0_ * j11 - t1_ * j10) / det, fz = T(-0.5) * (-t0_ * j01 + t1_ * j00) / det;
   // ---- heading-free world frame
-  const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
-  const double wx = (1 - 2 * (y * y + z * z)) * fx + 2 * (x * z + w * y) * fz, wy = 2 * (x * y + w * z) * fx + 2 * (y * z - w * x) * fz, wz = 2 * (x * z - w * y) * fx + (1 - 2 * (x * x + y * y)) * fz;
-  const double yaw = std::atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z)), cy = std::cos(yaw), sy = std::sin(yaw);
+  const T w = quat[0], x = quat[1], y = quat[2], z = quat[3];
+  const T wx = (1 - 2 * (y * y + z * z)) * fx + 2 * (x * z + w * y) * fz, wy = 2 * (x * y + w * z) * fx + 2 * (y * z - w * x) * fz, wz = 2 * (x * z - w * y) * fx + (1 - 2 * (x * x + y * y)) * fz;
+  const T yaw = std::atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z)), cy = std::cos(yaw), sy = std::sin(yaw);
   force[0] = cy * wx + sy * wy; force[1] = -sy * wx + cy * wy; force[2] = wz;
 }
+CASSIE_HD inline void estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) { estimator_leg_force_t<double>(side, ang, quat, force); }
 
 // ---- the estimator's filters (pelvis.position / translationalVelocity / externalForce, terrain.height of state_out_t).  Recovered from the
 // closed block's own memory (it keeps states, covariances and noise matrices as plain doubles): three per-axis Kalman filters

@@ -19,6 +19,7 @@
 
 #ifdef CASSIE_EMU
 #define CFN inline
+#define CNOINLINE inline
 #define DECL_LANE
 #define STAGE_SYNC(on)
 #define LANES for (int l = 0; l < 32; ++l) {
@@ -37,6 +38,7 @@
 #define EXSCAN_INT(v, total) do { int a_ = 0; for (int i_ = 0; i_ < 32; ++i_) { int t_ = v[i_]; v[i_] = a_; a_ += t_; } total = a_; } while (0)
 #else
 #define CFN __device__ __forceinline__
+#define CNOINLINE __device__ __noinline__   // cold / register-hungry stages: their own register allocation, no pressure on the stepping loop
 #define DECL_LANE const int l = threadIdx.x & 31;
 // optional CTA-wide rendezvous between stages: the warps of a CTA (one environment each) then walk the code together and share
 // instruction-cache lines; `on` is uniform over the CTA
@@ -1446,6 +1448,169 @@ CFN void est_foot(int side, const real *sc, const real *rate, real *out, real *j
   }
 }
 
+// ------------------------------------------------------------------ estimator, force model + filters (state_output_step [closed], decoded)
+// The arithmetic is csrc/estimator_host.h's (the host-side checker runs those functions one environment per call); here the three per-axis Kalman
+// filters are spread over the warp: filter f = lane / 8 (x, y, z), index j = lane % 8 inside it, every covariance / gain entry is produced by one
+// lane with the host code's own term order.  All filter data sits in shared memory (the constraint-matrix region is idle between ticks) as
+// doubles in every batch precision -- the block's unsymmetrised covariance recursion needs them.  Called once per 2 kHz control tick.
+// ds layout (doubles): [0..121] the environment's estimator row (devmodel.h ES_*), [128 + 64 f ..] per-filter parameters a1[6] zm[4] Qd[6] misc,
+// [320 + 96 f ..] per-filter work: G[N][K] (24), HP[K][N] (24), S[K][2K] (32), (gain reuses G's slot after S is inverted: Kg[N][K] at +80, 16.. no: see offsets)
+template <typename real>
+CNOINLINE void est_stage(real *sm, const real *cst, real *obs, double *est) {
+  DECL_LANE
+  double *ds = reinterpret_cast<double *>(sm + S_Y);
+  real *eo = obs + OB_EST_OUT;
+  constexpr int PAR = 128, WRK = 320;   // per-filter parameter block (64 doubles each), per-filter work block (112 doubles each)
+  constexpr int W_G = 0, W_HP = 24, W_S = 48, W_KG = 80;
+  // ---- leg forces (lanes 0, 1), in the batch precision: the archive evaluates this block in single precision itself
+  LANES
+    if (l < 2) {
+      const int sd = l; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd, *q = cst + CS_SENSOR + 16;
+      const real ang[7] = {mp[0], mp[1], mp[2], mp[3], jp[0], jp[1], mp[4]}, qd[4] = {q[0], q[1], q[2], q[3]};
+      real f[3]; estimator_leg_force_t<real>(sd, ang, qd, f);
+      for (int k = 0; k < 3; ++k) { est[ES_FORCE + 3 * sd + k] = (double)f[k]; eo[EO_TOE + 3 * sd + k] = f[k]; }
+    }
+    // the environment's filter row -> shared memory (the force slots are rewritten above, read back from `est` below)
+    for (int i = l; i < ES_FORCE; i += 32) ds[i] = est[i];
+  ENDL
+  // ---- per-filter scalars (lane 0 of each filter): measurements, contact terms, state prediction, Jacobian row a1
+  LANES
+    const int f = l >> 3, j = l & 7;
+    if (f < 3 && j == 0) {
+      const real *q = obs + OB_EST_QUAT, *pl = obs + OB_FOOT, *pr = obs + OB_FOOT + 13, *ac = obs + OB_EST_ACC;
+      const double w = q[0], x = q[1], y = q[2], z = q[3];
+      const double r0 = f == 0 ? w * w + x * x - y * y - z * z : f == 1 ? 2 * (x * y + w * z) : 2 * (x * z - w * y);
+      const double r1 = f == 0 ? 2 * (x * y - w * z) : f == 1 ? w * w - x * x + y * y - z * z : 2 * (y * z + w * x);
+      const double r2 = f == 0 ? 2 * (x * z + w * y) : f == 1 ? 2 * (y * z - w * x) : w * w - x * x - y * y + z * z;
+      const double yL = -(pl[0] * r0 + pl[1] * r1 + pl[2] * r2), yR = -(pr[0] * r0 + pr[1] * r1 + pr[2] * r2), aw = ac[0] * r0 + ac[1] * r1 + ac[2] * r2;
+      const EstimatorContact k = estimator_contact(est[ES_FORCE + 2] + est[ES_FORCE + 2], est[ES_FORCE + 5] + est[ES_FORCE + 5]);   // toeForce + heelForce
+      const bool started = ds[0] != 0;
+      double *par = ds + PAR + 64 * f, *a1 = par, *zm = par + 6, *Qd = par + 10;
+      const double dt = EST_DT, c = EST_DT * EST_GRAV;
+      if (f < 2) {
+        double *xs = ds + ES_X + 42 * f, *P = xs + 6;
+        if (!started) estimator_axis_start_xy(xs, P, yL, yR);
+        const double p0 = xs[0], v0 = xs[1], wt = xs[4];
+        zm[0] = yL; zm[1] = yR; zm[2] = k.wm; zm[3] = xs[1] + dt * aw;
+        Qd[0] = 1e-8; Qd[1] = 1e-8; Qd[2] = k.qL; Qd[3] = k.qR; Qd[4] = 1e-5; Qd[5] = 1e-2;
+        a1[0] = 0; a1[1] = 1; a1[2] = 0; a1[3] = 0; a1[4] = 0; a1[5] = 0;
+        if (k.contact) { a1[0] = c; a1[2] = -c * wt; a1[3] = -c * (1 - wt); a1[4] = -c * (xs[2] - xs[3]); a1[5] = dt / EST_MASS;
+                         xs[1] = v0 + c * (p0 - wt * xs[2] - (1 - wt) * xs[3]) + dt / EST_MASS * xs[5]; }
+        xs[0] = p0 + dt * v0;
+      } else {
+        double *zs = ds + ES_Z, *P = ds + ES_PZ;
+        if (!started) { estimator_axis_start_z(zs, P, yL, yR); ds[ES_TERRAIN] = 0; }
+        const double p0 = zs[0], v0 = zs[1];
+        zm[0] = yL; zm[1] = yR; Qd[0] = 1e-8; Qd[1] = 1e-8; Qd[2] = k.qL; Qd[3] = k.qR; Qd[4] = 1e-2;
+        a1[0] = 0; a1[1] = 1; a1[2] = 0; a1[3] = 0; a1[4] = dt / EST_MASS;
+        zs[0] = p0 + dt * v0; zs[1] = v0 + dt / EST_MASS * zs[4] + dt * (-EST_GRAV - (k.fl + k.fr) / EST_MASS);
+        par[16] = yL; par[17] = yR; par[18] = k.contact ? 1.0 : 0.0; par[19] = k.wm;   // for the terrain lag at the end
+      }
+    }
+  ENDL
+  // ---- covariance prediction P <- A P A' + Q (kalman_predict_cov): rows 0 and 1 of A P, column by column ...
+  LANES
+    const int f = l >> 3, j = l & 7, N = f < 2 ? 6 : 5;
+    if (f < 3 && j < N) {
+      double *P = f < 2 ? ds + ES_X + 42 * f + 6 : ds + ES_PZ; const double *a1 = ds + PAR + 64 * f;
+      const double T0 = P[j] + EST_DT * P[N + j]; double T1 = 0;
+      for (int q = 0; q < N; ++q) T1 += a1[q] * P[q * N + j];
+      P[j] = T0; P[N + j] = T1;
+    }
+  ENDL
+  LANES  // ... then (A P) A' row by row: columns 0 and 1 mix, the other diagonal entries receive Q
+    const int f = l >> 3, i = l & 7, N = f < 2 ? 6 : 5;
+    if (f < 3 && i < N) {
+      double *P = f < 2 ? ds + ES_X + 42 * f + 6 : ds + ES_PZ; const double *a1 = ds + PAR + 64 * f, *Qd = a1 + 10; const double *T = P + i * N;
+      double c1 = i == 1 ? Qd[1] : 0; for (int q = 0; q < N; ++q) c1 += T[q] * a1[q];
+      const double c0 = ((i == 0 ? Qd[0] : 0) + T[0]) + T[1] * EST_DT;
+      const double dg = i >= 2 ? Qd[i] + T[i] : 0;
+      P[i * N] = c0; P[i * N + 1] = c1;
+      if (i >= 2) P[i * N + i] = dg;
+    }
+  ENDL
+  // ---- measurement update (kalman_update): rows are differences of two states or single states
+  LANES  // H P (lane = column), P H' (lane = row)
+    const int f = l >> 3, j = l & 7, N = f < 2 ? 6 : 5, K = f < 2 ? 4 : 2;
+    if (f < 3 && j < N) {
+      const double *P = f < 2 ? ds + ES_X + 42 * f + 6 : ds + ES_PZ; double *wk = ds + WRK + 112 * f;
+      const int plus[4] = {0, 0, f < 2 ? 4 : 0, f < 2 ? 1 : 0}, minus[4] = {2, 3, -1, -1};
+      for (int m = 0; m < K; ++m) {
+        wk[W_HP + m * N + j] = minus[m] < 0 ? P[plus[m] * N + j] : P[plus[m] * N + j] - P[minus[m] * N + j];
+        wk[W_G + j * K + m] = minus[m] < 0 ? P[j * N + plus[m]] : P[j * N + plus[m]] - P[j * N + minus[m]];
+      }
+    }
+  ENDL
+  LANES  // S = H (P H') + R, augmented with the identity (lane = column of [S | I])
+    const int f = l >> 3, j = l & 7, K = f < 2 ? 4 : 2;
+    if (f < 3 && j < 2 * K) {
+      double *wk = ds + WRK + 112 * f;
+      const int plus[4] = {0, 0, f < 2 ? 4 : 0, f < 2 ? 1 : 0}, minus[4] = {2, 3, -1, -1};
+      const double Rd[4] = {1e-6, 1e-6, 1e-6, 1};
+      for (int i = 0; i < K; ++i) {
+        double a;
+        if (j < K) { a = (i == j ? Rd[i] : 0) + wk[W_G + plus[i] * K + j]; if (minus[i] >= 0) a -= wk[W_G + minus[i] * K + j]; }
+        else a = (i == j - K) ? 1.0 : 0.0;
+        wk[W_S + i * 2 * K + j] = a;
+      }
+    }
+  ENDL
+  for (int c = 0; c < 4; ++c) {   // Gauss-Jordan without row exchanges (S is symmetric positive definite), one pivot per phase, lane = column
+    LV(double, pv); LVA(double, col, 4);
+    LANES
+      const int f = l >> 3, j = l & 7, K = f < 2 ? 4 : 2;
+      L(pv) = 0;
+      if (f < 3 && j < 2 * K && c < K) {
+        const double *S = ds + WRK + 112 * f + W_S;
+        const double inv = 1.0 / S[c * 2 * K + c];
+        L(pv) = S[c * 2 * K + j] * inv;
+        for (int r = 0; r < K; ++r) LA(col, r) = r == c ? L(pv) : S[r * 2 * K + j] - S[r * 2 * K + c] * L(pv);
+      }
+    ENDL
+    LANES
+      const int f = l >> 3, j = l & 7, K = f < 2 ? 4 : 2;
+      if (f < 3 && j < 2 * K && c < K) { double *S = ds + WRK + 112 * f + W_S; for (int r = 0; r < K; ++r) S[r * 2 * K + j] = LA(col, r); }
+    ENDL
+  }
+  LANES  // gain K = (P H') inv(S) (lane = row)
+    const int f = l >> 3, i = l & 7, N = f < 2 ? 6 : 5, K = f < 2 ? 4 : 2;
+    if (f < 3 && i < N) {
+      double *wk = ds + WRK + 112 * f;
+      for (int j = 0; j < K; ++j) { double a = 0; for (int m = 0; m < K; ++m) a += wk[W_G + i * K + m] * wk[W_S + m * 2 * K + K + j]; wk[W_KG + i * K + j] = a; }
+    }
+  ENDL
+  LV(double, xnew);
+  LANES  // state: x += K (z - H x), the innovation taken from the predicted state before any entry is updated (lane = state entry)
+    const int f = l >> 3, i = l & 7, N = f < 2 ? 6 : 5, K = f < 2 ? 4 : 2;
+    L(xnew) = 0;
+    if (f < 3 && i < N) {
+      const double *wk = ds + WRK + 112 * f, *zm = ds + PAR + 64 * f + 6; const double *x = f < 2 ? ds + ES_X + 42 * f : ds + ES_Z;
+      const int plus[4] = {0, 0, f < 2 ? 4 : 0, f < 2 ? 1 : 0}, minus[4] = {2, 3, -1, -1};
+      double xi = x[i];
+      for (int j = 0; j < K; ++j) { double inn = zm[j] - x[plus[j]]; if (minus[j] >= 0) inn += x[minus[j]]; xi += wk[W_KG + i * K + j] * inn; }
+      L(xnew) = xi;
+    }
+  ENDL
+  LANES  // covariance: P -= K (H P) (lane = column), and the new state
+    const int f = l >> 3, j = l & 7, N = f < 2 ? 6 : 5, K = f < 2 ? 4 : 2;
+    if (f < 3 && j < N) {
+      double *P = f < 2 ? ds + ES_X + 42 * f + 6 : ds + ES_PZ; const double *wk = ds + WRK + 112 * f; double *x = f < 2 ? ds + ES_X + 42 * f : ds + ES_Z;
+      for (int i = 0; i < N; ++i) { double a = 0; for (int m = 0; m < K; ++m) a += wk[W_KG + i * K + m] * wk[W_HP + m * N + j]; P[i * N + j] -= a; }
+      x[j] = L(xnew);
+    }
+  ENDL
+  // ---- terrain lag, outputs, filter row back to global memory
+  LANES
+    if (l == 16) { const double *par = ds + PAR + 128; const EstimatorContact k{par[18] != 0, 0, 0, par[19], 0, 0}; ds[ES_TERRAIN] = estimator_terrain(ds[ES_TERRAIN], ds[ES_Z], par[16], par[17], k); }
+    if (l == 0) ds[0] = 1;
+  ENDL
+  LANES
+    for (int i = l; i < ES_FORCE; i += 32) est[i] = ds[i];
+    if (l < 2) { const double *xs = ds + ES_X + 42 * l; eo[EO_POS + l] = (real)xs[0]; eo[EO_VEL + l] = (real)xs[1]; eo[EO_EXTF + l] = (real)xs[5]; }
+    if (l == 2) { const double *zs = ds + ES_Z; eo[EO_POS + 2] = (real)zs[0]; eo[EO_VEL + 2] = (real)zs[1]; eo[EO_EXTF + 2] = (real)zs[4]; eo[EO_TERRAIN] = (real)ds[ES_TERRAIN]; }
+  ENDL
+}
+
 // ------------------------------------------------------------------ one control tick (cassie_sim_step_pd)
 // soft-limit tables of the safety layer (cassie_core_sim_step), degrees; left leg then right leg
 template <typename real> CFN real core_lo_deg(int i) { const real t[10] = {-15, -22, -50, -156, -140, -20, -22, -50, -156, -140}; return t[i]; }
@@ -1597,45 +1762,8 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
           for (int k = 0; k < 3; ++k) obs[OB_EST_ACC + k] = a[k] - R[6 + k] * real(9.806) - wwr[k];
         }
       ENDL
-      // ---- state_output_step, spring-force model and filters (csrc/estimator_host.h: the same functions run here and on the host)
-      if constexpr (DR) { if (est_on) {
-        LANES  // lanes 0, 1: leg force from the measured angles and the IMU quaternion
-          if (l < 2) {
-            const int sd = l; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd, *q = cst + CS_SENSOR + 16;
-            const double ang[7] = {(double)mp[0], (double)mp[1], (double)mp[2], (double)mp[3], (double)jp[0], (double)jp[1], (double)mp[4]}, qd[4] = {(double)q[0], (double)q[1], (double)q[2], (double)q[3]};
-            double f[3]; estimator_leg_force(sd, ang, qd, f);
-            for (int k = 0; k < 3; ++k) { E.est[ES_FORCE + 3 * sd + k] = f[k]; E.est_out[EO_TOE + 3 * sd + k] = (real)f[k]; }
-          }
-        ENDL
-        LANES  // lanes 0, 1, 2: the x, y, z filters side by side (each reads row `ax` of R(q) only)
-          if (l < 3) {
-            const int ax = l; double *st = E.est;
-            const real *q = obs + OB_EST_QUAT, *pl = obs + OB_FOOT, *pr = obs + OB_FOOT + 13, *ac = obs + OB_EST_ACC;
-            const double w = q[0], x = q[1], y = q[2], z = q[3];
-            const double r0 = ax == 0 ? w * w + x * x - y * y - z * z : ax == 1 ? 2 * (x * y + w * z) : 2 * (x * z - w * y);
-            const double r1 = ax == 0 ? 2 * (x * y - w * z) : ax == 1 ? w * w - x * x + y * y - z * z : 2 * (y * z + w * x);
-            const double r2 = ax == 0 ? 2 * (x * z + w * y) : ax == 1 ? 2 * (y * z - w * x) : w * w - x * x - y * y + z * z;
-            const double yL = -(pl[0] * r0 + pl[1] * r1 + pl[2] * r2), yR = -(pr[0] * r0 + pr[1] * r1 + pr[2] * r2), aw = ac[0] * r0 + ac[1] * r1 + ac[2] * r2;
-            const EstimatorContact k = estimator_contact(st[ES_FORCE + 2] + st[ES_FORCE + 2], st[ES_FORCE + 5] + st[ES_FORCE + 5]);   // toeForce + heelForce
-            const bool started = st[0] != 0;
-            if (ax < 2) {
-              double *xs = st + ES_X + 42 * ax, *P = xs + 6;
-              if (!started) estimator_axis_start_xy(xs, P, yL, yR);
-              estimator_axis_xy(xs, P, yL, yR, aw, k);
-              E.est_out[EO_POS + ax] = (real)xs[0]; E.est_out[EO_VEL + ax] = (real)xs[1]; E.est_out[EO_EXTF + ax] = (real)xs[5];
-            } else {
-              double *zs = st + ES_Z, *P = st + ES_PZ;
-              if (!started) { estimator_axis_start_z(zs, P, yL, yR); st[ES_TERRAIN] = 0; }
-              estimator_axis_z(zs, P, yL, yR, k);
-              st[ES_TERRAIN] = estimator_terrain(st[ES_TERRAIN], zs[0], yL, yR, k);
-              E.est_out[EO_POS + 2] = (real)zs[0]; E.est_out[EO_VEL + 2] = (real)zs[1]; E.est_out[EO_EXTF + 2] = (real)zs[4]; E.est_out[EO_TERRAIN] = (real)st[ES_TERRAIN];
-            }
-          }
-        ENDL
-        LANES
-          if (l == 0) E.est[0] = 1;
-        ENDL
-      } }
+      // ---- state_output_step, spring-force model and filters: the warp-parallel stage above (extended instance only)
+      if constexpr (DR) { if (est_on) est_stage<real>(sm, cst, obs, E.est); }
     }
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)

@@ -225,6 +225,12 @@ void *cassie_b200_estimator_filter_new(void);
 void cassie_b200_estimator_filter_free(void *filter);
 void cassie_b200_estimator_filter_reset(void *filter);
 void cassie_b200_estimator_filter_step(void *filter, state_out_t *y);
+/* measurement aids: accumulated wall-clock seconds of cassie_sim_step_pd_batch since the last reset -- out[0] host pack of pd_in_t[], out[1] device part
+ * (H2D, kernel, D2H, as waited for), out[2] host unpack into state_out_t[], out[3] number of calls, out[4] / out[5] milliseconds of the H2D copy /
+ * of the kernel by CUDA events (only when the environment variable CASSIE_B200_AOS_EVENTS is set); CPUs this process may use (affinity mask
+ * clipped by the cgroup quota), which bounds the pack / unpack threads (CASSIE_B200_AOS_THREADS, default 32) */
+void cassie_batch_aos_timing(cassie_batch_t *b, double out[6], int reset);
+int cassie_b200_effective_cpus(void);
 /* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
 void cassie_batch_forward(cassie_batch_t *b);
 /* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */

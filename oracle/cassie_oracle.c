@@ -1586,7 +1586,7 @@ void osim_set_const(OSim *c) {                                             /* :9
   static const double qi[28] = {0.0045, 0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968,
                                 -0.0045, 0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997, 0, 1.4267, 0, -1.5244, 1.5244, -1.5968};
   o_setConst(c->m, c->d);
-  copyv(c->d->qpos, c->m->qpos0, c->m->nq); copyv(c->d->qpos + 7, qi, 28);  /* the 35 constants at :953-958 = qpos0[0..6] ++ these */
+  { static const double q7[7] = {0, 0, 1.01, 1, 0, 0, 0}; copyv(c->d->qpos, q7, 7); } copyv(c->d->qpos + 7, qi, 28);  /* exactly the 35 constants of :953-958, mju_copy(qpos, qpos_init, 35) at :967: qpos beyond them (cassie_tray_box.xml's cup) keeps its values */
   zero(c->d->qvel, c->m->nv); zero(c->d->qacc, c->m->nv);
   c->d->time = 0;
   o_forward(c->m, c->d);
