@@ -146,9 +146,21 @@ def lib():
     L.cassie_sim_init.restype = vp
     L.cassie_sim_free.argtypes = [vp]
     L.cassie_sim_step_pd.argtypes = [vp, C.POINTER(state_out_t), C.POINTER(pd_in_t)]
-    for n in ('cassie_sim_time', 'cassie_sim_qpos', 'cassie_sim_qvel'):
+    for n in ('cassie_sim_time', 'cassie_sim_qpos', 'cassie_sim_qvel', 'cassie_sim_timestep', 'cassie_state_time', 'cassie_state_qpos', 'cassie_state_qvel'):
         getattr(L, n).argtypes = [vp]
         getattr(L, n).restype = cd
+    L.cassie_sim_step.argtypes = [vp, vp, vp]
+    L.cassie_sim_step_pd_no2khz.argtypes = [vp, C.POINTER(state_out_t), C.POINTER(pd_in_t)]
+    L.cassie_sim_set_timestep.argtypes = [vp, C.c_double]
+    L.cassie_sim_forward.argtypes = [vp]
+    L.cassie_sim_forward.restype = ci
+    for n in ('cassie_sim_hold', 'cassie_sim_release', 'cassie_state_free'):
+        getattr(L, n).argtypes = [vp]
+    for n in ('cassie_get_state', 'cassie_set_state', 'cassie_sim_copy', 'cassie_state_copy'):
+        getattr(L, n).argtypes = [vp, vp]
+    L.cassie_state_alloc.restype = vp
+    L.cassie_sim_duplicate.argtypes = [vp]
+    L.cassie_sim_duplicate.restype = vp
     for n in ('cassie_sim_nv', 'cassie_sim_nq'):
         getattr(L, n).argtypes = [vp]
         getattr(L, n).restype = ci
@@ -434,6 +446,31 @@ class CassieBatch:
         if self.L.cassie_batch_set_hfielddata(self.h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0]) != 0:
             raise RuntimeError(_last_error())
 
+    def get_state(self, snap=None):
+        """device-resident snapshot of every row array (qpos, qvel, warm start, controller / sensor state, filters, forces, estimator, observation rows)"""
+        self.L.cassie_batch_state_alloc.restype = C.c_void_p
+        self.L.cassie_batch_state_alloc.argtypes = [C.c_void_p]
+        self.L.cassie_batch_get_state.argtypes = [C.c_void_p, C.c_void_p]
+        snap = snap or self.L.cassie_batch_state_alloc(self.h)
+        if not snap or self.L.cassie_batch_get_state(self.h, C.c_void_p(snap)) != 0:
+            raise RuntimeError(_last_error())
+        return snap
+
+    def set_state(self, snap, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.L.cassie_batch_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        if self.L.cassie_batch_set_state(self.h, C.c_void_p(snap), None if m is None else m.ctypes.data) != 0:
+            raise RuntimeError(_last_error())
+
+    def free_state(self, snap):
+        self.L.cassie_batch_state_free.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.cassie_batch_state_free(self.h, C.c_void_p(snap))
+
+    def set_timestep(self, dt):
+        self.L.cassie_batch_set_timestep.argtypes = [C.c_void_p, C.c_double]
+        if self.L.cassie_batch_set_timestep(self.h, float(dt)) != 0:
+            raise RuntimeError(_last_error())
+
     def row_width(self, field):
         """row width (elements) of a device array: qpos 36 (44 with the extra free body), qvel 32 (40), pd 52, obs 112, xfrc 8, aux 64"""
         self.L.cassie_batch_row_width.argtypes = [C.c_void_p, C.c_char_p]
@@ -473,6 +510,95 @@ class CassieBatch:
         a = _Arr()
         a.__cuda_array_interface__ = dict(shape=(self.n, width), typestr=ts, data=(self.device_ptr(field), False), version=2)
         return torch.as_tensor(a, device='cuda')
+
+
+class cassie_user_in_t(C.Structure):
+    _fields_ = [('torque', C.c_double * 10), ('telemetry', C.c_short * 9)]
+
+
+class elmo_out_t(C.Structure):
+    _fields_ = [('statusWord', C.c_ushort), ('position', C.c_double), ('velocity', C.c_double), ('torque', C.c_double), ('driveTemperature', C.c_double),
+                ('dcLinkVoltage', C.c_double), ('torqueLimit', C.c_double), ('gearRatio', C.c_double)]
+
+
+class cassie_joint_out_t(C.Structure):
+    _fields_ = [('position', C.c_double), ('velocity', C.c_double)]
+
+
+class cassie_leg_out_t(C.Structure):
+    _fields_ = [(n, elmo_out_t) for n in ('hipRollDrive', 'hipYawDrive', 'hipPitchDrive', 'kneeDrive', 'footDrive')] + \
+               [(n, cassie_joint_out_t) for n in ('shinJoint', 'tarsusJoint', 'footJoint')] + \
+               [('medullaCounter', C.c_ubyte), ('medullaCpuLoad', C.c_ushort), ('reedSwitchState', C.c_bool)]
+
+
+class battery_out_t(C.Structure):
+    _fields_ = [('dataGood', C.c_bool), ('stateOfCharge', C.c_double), ('voltage', C.c_double * 12), ('current', C.c_double), ('temperature', C.c_double * 4)]
+
+
+class radio_out_t(C.Structure):
+    _fields_ = [('radioReceiverSignalGood', C.c_bool), ('receiverMedullaSignalGood', C.c_bool), ('channel', C.c_double * 16)]
+
+
+class target_pc_out_t(C.Structure):
+    _fields_ = [('etherCatStatus', C.c_int * 6), ('etherCatNotifications', C.c_int * 21), ('taskExecutionTime', C.c_double), ('overloadCounter', C.c_uint), ('cpuTemperature', C.c_double)]
+
+
+class vectornav_out_t(C.Structure):
+    _fields_ = [('dataGood', C.c_bool), ('vpeStatus', C.c_ushort), ('pressure', C.c_double), ('temperature', C.c_double), ('magneticField', C.c_double * 3),
+                ('angularVelocity', C.c_double * 3), ('linearAcceleration', C.c_double * 3), ('orientation', C.c_double * 4)]
+
+
+class cassie_pelvis_out_t(C.Structure):
+    _fields_ = [('targetPc', target_pc_out_t), ('battery', battery_out_t), ('radio', radio_out_t), ('vectorNav', vectornav_out_t), ('medullaCounter', C.c_ubyte),
+                ('medullaCpuLoad', C.c_ushort), ('bleederState', C.c_bool), ('leftReedSwitchState', C.c_bool), ('rightReedSwitchState', C.c_bool), ('vtmTemperature', C.c_double)]
+
+
+class cassie_out_t(C.Structure):
+    _fields_ = [('pelvis', cassie_pelvis_out_t), ('leftLeg', cassie_leg_out_t), ('rightLeg', cassie_leg_out_t), ('isCalibrated', C.c_bool), ('messages', C.c_short * 4)]
+
+
+assert C.sizeof(cassie_out_t) == 1336 and C.sizeof(cassie_user_in_t) == 104
+
+
+class CassieState:
+    """cassie_state_t (reference: example/cassiemujoco.py CassieState): a full dynamic-state snapshot of a CassieSim"""
+
+    def __init__(self):
+        self.L = lib()
+        self.s = self.L.cassie_state_alloc()
+
+    def time(self):
+        return self.L.cassie_state_time(self.s)[0]
+
+    def qpos(self):
+        return np.array(self.L.cassie_state_qpos(self.s)[:35])
+
+    def qvel(self):
+        return np.array(self.L.cassie_state_qvel(self.s)[:32])
+
+    def set_time(self, t):
+        self.L.cassie_state_time(self.s)[0] = t
+
+    def set_qpos(self, q):
+        p = self.L.cassie_state_qpos(self.s)
+        for i in range(len(q)):
+            p[i] = q[i]
+
+    def set_qvel(self, v):
+        p = self.L.cassie_state_qvel(self.s)
+        for i in range(len(v)):
+            p[i] = v[i]
+
+    def close(self):
+        if getattr(self, 's', None):
+            self.L.cassie_state_free(self.s)
+            self.s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CassieSim:
@@ -522,6 +648,58 @@ class CassieSim:
 
     def full_reset(self):
         self.L.cassie_sim_full_reset(self.c)
+
+    # ---- the verbs around the hot path (reference: example/cassiemujoco.py:64-173)
+    def step(self, u):
+        """torque-level step: u = cassie_user_in_t; returns the cassie_out_t of this tick"""
+        y = cassie_out_t()
+        self.L.cassie_sim_step(self.c, C.addressof(y), C.addressof(u))
+        return y
+
+    def step_pd_no2khz(self, u):
+        y = state_out_t()
+        self.L.cassie_sim_step_pd_no2khz(self.c, C.byref(y), C.byref(u))
+        return y
+
+    def get_cassie_out(self):
+        self.L.cassie_sim_get_cassie_out.restype = cassie_out_t
+        self.L.cassie_sim_get_cassie_out.argtypes = [C.c_void_p]
+        return self.L.cassie_sim_get_cassie_out(self.c)
+
+    def timestep(self):
+        return self.L.cassie_sim_timestep(self.c)[0]
+
+    def set_timestep(self, dt):
+        self.L.cassie_sim_set_timestep(self.c, float(dt))
+
+    def forward(self):
+        return self.L.cassie_sim_forward(self.c)
+
+    def hold(self):
+        self.L.cassie_sim_hold(self.c)
+
+    def release(self):
+        self.L.cassie_sim_release(self.c)
+
+    def get_state(self, s=None):
+        s = s or CassieState()
+        self.L.cassie_get_state(self.c, s.s)
+        return s
+
+    def set_state(self, s):
+        self.L.cassie_set_state(self.c, s.s)
+
+    def duplicate(self):
+        d = CassieSim.__new__(CassieSim)
+        d.L = self.L
+        d.c = self.L.cassie_sim_duplicate(self.c)
+        if not d.c:
+            raise RuntimeError('cassie_sim_duplicate failed: ' + _last_error())
+        d.nq, d.nv = self.nq, self.nv
+        return d
+
+    def copy(self, src):
+        self.L.cassie_sim_copy(self.c, src.c)
 
     # ---- model constants, named as in the reference wrapper (example/cassiemujoco.py:380-610)
     def params(self):

@@ -40,7 +40,7 @@ static int effective_cpus() {
 }
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync, nsub, warp_stride; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
   tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
   const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
-  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + (size_t)warp * warp_bytes<real>(A.ystride, DR));
+  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + warp * A.warp_stride);   // warp_stride = warp_bytes(ystride, instance), precomputed on the host: cheap to rematerialise under register pressure
   const int qw = A.qpos_w, vw = A.qvel_w;
   const DevModel<real> &cm = *cmp;
   // persistent CTAs: a CTA draws one environment per warp from a global ticket counter until the batch is exhausted; its warps walk the
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     const int env = base + warp;
     const bool active = env < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
     if (!active) {   // keep the rendezvous count of the working warps
-      if (sync_on) { const int per = __popc(sync_on); for (int i = 0; i < nticks * cm.nsub * per; ++i) __syncthreads(); }
+      if (sync_on) { const int per = __popc(sync_on); for (int i = 0; i < nticks * (A.nsub > 0 ? A.nsub : cm.nsub) * per; ++i) __syncthreads(); }
       continue;
     }
     // warm the L2/L1 path of the rows that are addressed in place later (controller state, PD row, FIR taps)
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
     E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W; E.task = A.task ? A.task + (size_t)env * TASK_W : nullptr; E.gait = A.gait ? A.gait + (size_t)env * GAIT_W : nullptr;
     E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
     E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * 2 * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on;
+    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on; E.nsub = A.nsub;
     E.est = A.est ? A.est + (size_t)env * EST_W : nullptr; E.est_out = E.obs + OB_EST_OUT;
     step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
     __syncwarp();
@@ -202,6 +202,13 @@ __global__ void fill_rows_kernel(T *__restrict__ dst, const T *__restrict__ row,
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) { const size_t e = i / w; if ((!mask || mask[e]) && (int)(i - e * w) < ncols) dst[i] = row[i - e * w]; }
 }
 
+// rows of the selected environments <- the same rows of another array (snapshot restore of a subset)
+template <typename T>
+__global__ void copy_rows_kernel(T *__restrict__ dst, const T *__restrict__ src, int w, const unsigned char *__restrict__ mask, int n) {
+  const size_t total = (size_t)n * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) { const size_t e = i / w; if (!mask || mask[e]) dst[i] = src[i]; }
+}
+
 // ------------------------------------------------------------------ host side
 struct BatchBase {
   virtual ~BatchBase() {}
@@ -235,6 +242,16 @@ struct BatchBase {
   virtual bool get_model_rows(const char *what, double *rows, int width) = 0;
   virtual bool set_const(const unsigned char *mask, bool reset_state) = 0;
   virtual bool has_aux() const = 0;
+  // full dynamic state of every environment (cassie_get_state / cassie_set_state, src/cassiemujoco.c:3435-3452: mjData + the block objects +
+  // cassie_out + encoder filters + torque delay line): device-resident snapshots, restore of a masked subset
+  virtual void *snap_alloc() = 0;
+  virtual bool snap_get(void *snap) = 0;
+  virtual bool snap_set(const void *snap, const unsigned char *mask) = 0;
+  virtual bool snap_copy(void *dst, const void *src) = 0;
+  virtual void snap_free(void *snap) = 0;
+  virtual bool copy_model_from(BatchBase *src) = 0;     // per-environment constants, height fields, timestep (mj_copyModel in cassie_sim_copy, :1083-1091)
+  virtual bool rebuild_model() = 0;                     // after hm was edited (timestep, hold / release): rebuild and upload the constant block
+  int nsub_override = 0;                                // > 0: physics sub-steps per control tick of the next launches (cassie_sim_step_pd_no2khz)
   bool sync() { CUDA_OK(cudaStreamSynchronize(stream)); return true; }
 };
 
@@ -535,6 +552,74 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemcpyAsync(A.task, h_tmp.data(), sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
     return true;
   }
+  // ---- snapshots
+  struct Snap { real *qpos = nullptr, *qvel = nullptr, *qacc_ws = nullptr, *cst = nullptr, *xfrc = nullptr, *obs = nullptr, *aux = nullptr; int *dfilt = nullptr; double *est = nullptr; bool has_est = false, has_aux = false; };
+  void *snap_alloc() override {
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    Snap *k = new Snap();
+    if (cudaMalloc(&k->qpos, sizeof(real) * n * QW) != cudaSuccess || cudaMalloc(&k->qvel, sizeof(real) * n * VW) != cudaSuccess || cudaMalloc(&k->qacc_ws, sizeof(real) * n * VW) != cudaSuccess ||
+        cudaMalloc(&k->cst, sizeof(real) * n * CST_W) != cudaSuccess || cudaMalloc(&k->xfrc, sizeof(real) * n * XFRC_W) != cudaSuccess || cudaMalloc(&k->obs, sizeof(real) * n * OBS_W) != cudaSuccess ||
+        cudaMalloc(&k->dfilt, sizeof(int) * n * DFILT_W) != cudaSuccess) { snap_free(k); set_err("snapshot: out of device memory"); return nullptr; }
+    return k;
+  }
+  void snap_free(void *p) override { if (!p) return; Snap *k = (Snap *)p; cudaSetDevice(device); cudaFree(k->qpos); cudaFree(k->qvel); cudaFree(k->qacc_ws); cudaFree(k->cst); cudaFree(k->xfrc); cudaFree(k->obs); cudaFree(k->aux); cudaFree(k->dfilt); cudaFree(k->est); delete k; }
+  template <typename T> bool rows_copy(T *dst, const T *src, int w, const unsigned char *dmask) {
+    if (!dmask) { CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(T) * n * w, cudaMemcpyDeviceToDevice, stream)); return true; }
+    copy_rows_kernel<T><<<256, 256, 0, stream>>>(dst, src, w, dmask, n); CUDA_OK(cudaGetLastError()); return true;
+  }
+  bool snap_get(void *p) override {
+    Snap *k = (Snap *)p; CUDA_OK(cudaSetDevice(device));
+    if (!rows_copy(k->qpos, A.qpos, QW, nullptr) || !rows_copy(k->qvel, A.qvel, VW, nullptr) || !rows_copy(k->qacc_ws, A.qacc_ws, VW, nullptr) || !rows_copy(k->cst, A.cst, CST_W, nullptr) ||
+        !rows_copy(k->xfrc, A.xfrc, XFRC_W, nullptr) || !rows_copy(k->obs, A.obs, OBS_W, nullptr) || !rows_copy(k->dfilt, A.dfilt, DFILT_W, nullptr)) return false;
+    k->has_est = A.est != nullptr; k->has_aux = A.aux != nullptr;
+    if (k->has_est) { if (!k->est) CUDA_OK(cudaMalloc(&k->est, sizeof(double) * n * EST_W)); if (!rows_copy(k->est, A.est, EST_W, nullptr)) return false; }
+    if (k->has_aux) { if (!k->aux) CUDA_OK(cudaMalloc(&k->aux, sizeof(real) * n * AUX_W)); if (!rows_copy(k->aux, A.aux, AUX_W, nullptr)) return false; }
+    return sync();
+  }
+  bool snap_set(const void *p, const unsigned char *mask) override {
+    const Snap *k = (const Snap *)p; CUDA_OK(cudaSetDevice(device));
+    const unsigned char *dm = nullptr;
+    if (mask) { if (!upload_mask(mask)) return false; dm = d_mask; }
+    if (!rows_copy(A.qpos, (const real *)k->qpos, QW, dm) || !rows_copy(A.qvel, (const real *)k->qvel, VW, dm) || !rows_copy(A.qacc_ws, (const real *)k->qacc_ws, VW, dm) || !rows_copy(A.cst, (const real *)k->cst, CST_W, dm) ||
+        !rows_copy(A.xfrc, (const real *)k->xfrc, XFRC_W, dm) || !rows_copy(A.obs, (const real *)k->obs, OBS_W, dm) || !rows_copy(A.dfilt, (const int *)k->dfilt, DFILT_W, dm)) return false;
+    if (k->has_est) { if (!A.est && !enable_estimator_device(true)) return false; if (!rows_copy(A.est, (const double *)k->est, EST_W, dm)) return false; }
+    else if (A.est && !reset_estimator_device(mask)) return false;   // the snapshot was taken before the estimator ran: it starts afresh
+    if (k->has_aux && A.aux && !rows_copy(A.aux, (const real *)k->aux, AUX_W, dm)) return false;
+    return sync();
+  }
+  bool snap_copy(void *pd, const void *ps) override {
+    Snap *d = (Snap *)pd; const Snap *k = (const Snap *)ps; CUDA_OK(cudaSetDevice(device));
+    if (!rows_copy(d->qpos, (const real *)k->qpos, QW, nullptr) || !rows_copy(d->qvel, (const real *)k->qvel, VW, nullptr) || !rows_copy(d->qacc_ws, (const real *)k->qacc_ws, VW, nullptr) || !rows_copy(d->cst, (const real *)k->cst, CST_W, nullptr) ||
+        !rows_copy(d->xfrc, (const real *)k->xfrc, XFRC_W, nullptr) || !rows_copy(d->obs, (const real *)k->obs, OBS_W, nullptr) || !rows_copy(d->dfilt, (const int *)k->dfilt, DFILT_W, nullptr)) return false;
+    d->has_est = k->has_est; d->has_aux = k->has_aux;
+    if (k->has_est) { if (!d->est) CUDA_OK(cudaMalloc(&d->est, sizeof(double) * n * EST_W)); if (!rows_copy(d->est, (const double *)k->est, EST_W, nullptr)) return false; }
+    if (k->has_aux) { if (!d->aux) CUDA_OK(cudaMalloc(&d->aux, sizeof(real) * n * AUX_W)); if (!rows_copy(d->aux, (const real *)k->aux, AUX_W, nullptr)) return false; }
+    return sync();
+  }
+  bool rebuild_model() override {
+    CUDA_OK(cudaSetDevice(device));
+    DevModel<real> *hmodel = (DevModel<real> *)calloc(1, model_bytes<real>()); std::string err; BuildInfo info;
+    if (!build_dev_model(hm, *hmodel, err, &info)) { free(hmodel); set_err(err); return false; }
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
+    h_model_copy = *hmodel; free(hmodel);
+    return true;
+  }
+  bool copy_model_from(BatchBase *other) override {
+    Batch<real> *src = dynamic_cast<Batch<real> *>(other);
+    if (!src || src->n != n || src->hm.nq != hm.nq || src->hm.nbody != hm.nbody) { set_err("copy: the two simulators differ in model, size or precision"); return false; }
+    CUDA_OK(cudaSetDevice(device));
+    hm = src->hm;
+    if (!rebuild_model()) return false;
+    if (src->A.cenv) { if (!ensure_cenv()) return false; CUDA_OK(cudaMemcpyAsync(A.cenv, src->A.cenv, sizeof(real) * n * CE_W, cudaMemcpyDeviceToDevice, stream)); }
+    else if (A.cenv) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.cenv)); A.cenv = nullptr; }
+    if (src->d_hfield) {
+      const size_t cells = (size_t)hm.hfield_nrow[0] * hm.hfield_ncol[0] * src->A.n_terrain;
+      std::vector<float> tmp(cells); CUDA_OK(cudaMemcpy(tmp.data(), src->d_hfield, sizeof(float) * cells, cudaMemcpyDeviceToHost));
+      if (!set_hfield(tmp.data(), src->A.n_terrain)) return false;
+    }
+    return sync();
+  }
   // open-loop sinusoidal gait on the motor-PD targets (BASELINE config 5 "random PD gaits"): evaluated in the kernel every control tick, so
   // multi-tick launches follow it without a host round trip; installing it restarts the tick clock
   bool set_pd_gait(const double *amp, const double *freq, const double *phase) override {
@@ -550,6 +635,8 @@ template <typename real> struct Batch : BatchBase {
   bool step(int nticks, int mode) override {
     CUDA_OK(cudaSetDevice(device));
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
+    A.nsub = nsub_override;
+    A.warp_stride = (int)warp_bytes<real>(A.ystride, A.cenv || A.aux || A.task || A.est);
     const bool ext = A.cenv || A.aux || A.task || A.est;   // per-environment model constants / derived-quantity rows / task-space PD / in-kernel estimator: extended instance (its own scratch size and launch shape)
     const LaunchCfg &c = cfg[ext ? 1 : 0];
     int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
@@ -586,6 +673,7 @@ template <typename real> struct Batch : BatchBase {
     if (!strcmp(f, "time")) return d2h(A.cst, CST_W, 1, CS_TIME, out);
     if (!strcmp(f, "obs")) return d2h(A.obs, OBS_W, OBS_W, 0, out);
     if (!strcmp(f, "cst")) return d2h(A.cst, CST_W, CST_W, 0, out);
+    if (!strcmp(f, "xfrc")) return d2h(A.xfrc, XFRC_W, XFRC_W, 0, out);
     if (!strcmp(f, "est_out")) { if (!A.est) { set_err("the in-kernel estimator is not enabled (cassie_batch_enable_estimator_device)"); return false; } return d2h(A.obs, OBS_W, EO_W, OB_EST_OUT, out); }
     if (!strcmp(f, "aux")) { if (!A.aux) { set_err("derived quantities are not enabled (cassie_batch_enable_aux)"); return false; } return d2h(A.aux, AUX_W, AUX_W, 0, out); }
     set_err(std::string("unknown field ") + f); return false;
@@ -639,8 +727,12 @@ template <typename real> struct Batch : BatchBase {
 // ====================================================================== C-ABI
 using namespace cassie;
 struct cassie_batch { BatchBase *impl; std::vector<double> obs, radio; };
-struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev, aux[AUX_W]; std::vector<float> hfield, hfield_dev;
+struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev, aux[AUX_W]; std::vector<float> hfield, hfield_dev; std::string path; double timestep = 0, timestep_dev = 0;
   std::vector<double> m_mass, m_ipos, m_damp, m_fric, m_mass_dev, m_ipos_dev, m_damp_dev, m_fric_dev; };   // host mirrors of the model arrays handed out as borrowed pointers
+
+// cassie_state_t (include/cassiemujoco.h:434-463): a device-resident snapshot of one simulator's rows plus the host mirrors the reference hands out as
+// borrowed pointers (time, qpos, qvel); the snapshot is allocated by the first cassie_get_state, which also fixes the owning simulator's sizes
+struct cassie_state { BatchBase *owner = nullptr; void *snap = nullptr; double qpos[64], qvel[64], time = 0, qpos_snap[64], qvel_snap[64], time_snap = 0; };
 
 static std::mutex g_model_mutex;
 static std::string g_model_path;   // what cassie_mujoco_init cached (the reference caches the parsed model, src/cassiemujoco.c:48-59)
@@ -755,6 +847,7 @@ static void sim_push(cassie_sim_t *c) {  // upload whatever the caller wrote thr
   if (memcmp(c->qpos_dev, c->qpos, sizeof c->qpos)) c->b->impl->set("qpos", c->qpos);
   if (memcmp(c->qvel_dev, c->qvel, sizeof c->qvel)) c->b->impl->set("qvel", c->qvel);
   if (c->time_dev != c->time) c->b->impl->set("time", &c->time);
+  if (c->timestep != c->timestep_dev) { if (c->timestep > 0) { c->b->impl->hm.timestep = c->timestep; c->b->impl->rebuild_model(); } c->timestep_dev = c->timestep; }   // written through cassie_sim_timestep()
   if (!c->hfield.empty() && c->hfield != c->hfield_dev) { c->b->impl->set_hfield(c->hfield.data(), 1); c->hfield_dev = c->hfield; }
   if (c->m_mass != c->m_mass_dev) { cassie_batch_set_body_mass(c->b, c->m_mass.data()); c->m_mass_dev = c->m_mass; }
   if (c->m_ipos != c->m_ipos_dev) { cassie_batch_set_body_ipos(c->b, c->m_ipos.data()); c->m_ipos_dev = c->m_ipos; }
@@ -766,7 +859,7 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   { std::lock_guard<std::mutex> g(g_model_mutex); if (reinit || g_model_path.empty()) { if (!modelfile) { set_err("cassie_sim_init: model file required"); return nullptr; } path = modelfile; if (g_model_path.empty()) g_model_path = modelfile; } else path = g_model_path; }
   cassie_batch_t *b = cassie_batch_init(path.c_str(), 1, 0, CASSIE_B200_FP64);
   if (!b) return nullptr;
-  cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b;
+  cassie_sim_t *c = new cassie_sim(); memset(c->qpos, 0, sizeof c->qpos); memset(c->qvel, 0, sizeof c->qvel); memset(c->aux, 0, sizeof c->aux); c->b = b; c->path = path; c->timestep = c->timestep_dev = b->impl->hm.timestep;
   b->impl->enable_aux(true); b->impl->step(0, 1);   // a single environment always carries the derived-quantity row; populate it like the sensordata
   b->impl->enable_estimator_device(true);   // ... and the estimator (toe / heel forces, filters) inside the kernel, as state_output_step runs in every cassie_sim_step_pd (src/cassiemujoco.c:1156)
   sim_pull(c);
@@ -852,5 +945,116 @@ int cassie_sim_nu(const cassie_sim_t *c) { return c->b->impl->hm.nu; }
 // src/cassiemujoco.c:1183-1189: qpos += h * qvel on the joint manifold; the reference then feeds an uninitialised cassie_out_t to its estimator,
 // so *y carries no information there -- it is zeroed here
 void cassie_integrate_pos(cassie_sim_t *c, state_out_t *y) { sim_push(c); cassie_batch_integrate_pos(c->b); c->b->impl->sync(); sim_pull(c); if (y) memset(y, 0, sizeof *y); }
+
+// ---- legacy verbs RL wrappers call around cassie_sim_step_pd (src/cassiemujoco.c:1072-1093, 1137-1145, 1159-1181, 1196-1225, 1974-2000, 2086-2092, 3380-3452)
+// the dynamic subset of cassie_out_t from an observation row, the rest as cassie_out_init leaves it (:672-734)
+static void fill_cassie_out(const double *o, const double *radio, cassie_out_t *y) {
+  memset(y, 0, sizeof *y);
+  y->isCalibrated = true;
+  y->pelvis.medullaCounter = 1; y->pelvis.medullaCpuLoad = 159; y->pelvis.vtmTemperature = 40;
+  y->pelvis.targetPc.etherCatStatus[1] = 8; y->pelvis.targetPc.etherCatStatus[4] = 1; y->pelvis.targetPc.taskExecutionTime = 2e-4; y->pelvis.targetPc.cpuTemperature = 60;
+  y->pelvis.battery.dataGood = true; y->pelvis.battery.stateOfCharge = 1;
+  for (int i = 0; i < 4; i++) y->pelvis.battery.temperature[i] = 30;
+  for (int i = 0; i < 12; i++) y->pelvis.battery.voltage[i] = 4.2;
+  y->pelvis.radio.radioReceiverSignalGood = true; y->pelvis.radio.receiverMedullaSignalGood = true;
+  for (int i = 0; i < 16; i++) y->pelvis.radio.channel[i] = radio[i];
+  y->pelvis.vectorNav.dataGood = true; y->pelvis.vectorNav.pressure = 101.325; y->pelvis.vectorNav.temperature = 25;
+  for (int i = 0; i < 4; i++) y->pelvis.vectorNav.orientation[i] = o[OB_QUAT + i];
+  for (int i = 0; i < 3; i++) { y->pelvis.vectorNav.angularVelocity[i] = o[OB_GYRO + i]; y->pelvis.vectorNav.linearAcceleration[i] = o[OB_ACCEL + i]; y->pelvis.vectorNav.magneticField[i] = o[OB_MAG + i]; }
+  static const double tl[5] = {140.63, 140.63, 216.16, 216.16, 45.14}, gr[5] = {25, 25, 16, 16, 50};
+  for (int sd = 0; sd < 2; sd++) {
+    cassie_leg_out_t *leg = sd ? &y->rightLeg : &y->leftLeg; leg->medullaCounter = 1; leg->medullaCpuLoad = 94;
+    elmo_out_t *dr[5] = {&leg->hipRollDrive, &leg->hipYawDrive, &leg->hipPitchDrive, &leg->kneeDrive, &leg->footDrive};
+    for (int i = 0; i < 5; i++) { dr[i]->statusWord = 0x0637; dr[i]->dcLinkVoltage = 48; dr[i]->driveTemperature = 30; dr[i]->torqueLimit = tl[i]; dr[i]->gearRatio = gr[i];
+      dr[i]->position = o[OB_MPOS + 5 * sd + i]; dr[i]->velocity = o[OB_MVEL + 5 * sd + i]; dr[i]->torque = o[OB_MTORQUE + 5 * sd + i]; }
+    cassie_joint_out_t *jn[3] = {&leg->shinJoint, &leg->tarsusJoint, &leg->footJoint};
+    for (int i = 0; i < 3; i++) { jn[i]->position = o[OB_JPOS + 3 * sd + i]; jn[i]->velocity = o[OB_JVEL + 3 * sd + i]; }
+  }
+}
+// :2090-2092.  The observation row holds what `*y = c->cassie_out` copied out in the last step (:1127); before the first step it is the initial bus state
+cassie_out_t cassie_sim_get_cassie_out(cassie_sim_t *c) { double o[OBS_W]; cassie_out_t y; c->b->impl->get("obs", o); fill_cassie_out(o, c->b->radio.data(), &y); return y; }
+// :1137-1145: user torques -> safety layer -> motor model -> physics; y = the bus as the sensors filled it in this tick.  A pd_in_t that carries only
+// motorPd.torque makes pd_input_step the identity on the torques, so the launch is the same one cassie_sim_step_pd uses
+void cassie_sim_step(cassie_sim_t *c, cassie_out_t *y, const cassie_user_in_t *u) {
+  pd_in_t pd; memset(&pd, 0, sizeof pd);
+  for (int i = 0; i < 5; i++) { pd.leftLeg.motorPd.torque[i] = u->torque[i]; pd.rightLeg.motorPd.torque[i] = u->torque[5 + i]; }
+  state_out_t so; sim_push(c); cassie_sim_step_pd_batch(c->b, &pd, &so); sim_pull(c);
+  if (y) *y = cassie_sim_get_cassie_out(c);
+}
+// :1159-1181: the same tick with ONE physics step whatever the model's timestep is
+void cassie_sim_step_pd_no2khz(cassie_sim_t *c, state_out_t *y, const pd_in_t *u) { sim_push(c); c->b->impl->nsub_override = 1; cassie_sim_step_pd_batch(c->b, u, y); c->b->impl->nsub_override = 0; sim_pull(c); }
+// :1196-1204: the borrowed pointer is a host mirror, uploaded (constant block rebuilt) before the next launch
+double *cassie_sim_timestep(cassie_sim_t *c) { return &c->timestep; }
+void cassie_sim_set_timestep(cassie_sim_t *c, double dt) { c->timestep = dt; }
+int cassie_batch_set_timestep(cassie_batch_t *b, double dt) { if (!(dt > 0)) return -1; b->impl->hm.timestep = dt; return b->impl->rebuild_model() ? 0 : -1; }
+// :1221-1225
+int cassie_sim_forward(cassie_sim_t *c) { sim_push(c); c->b->impl->step(0, 1); sim_pull(c); return 0; }
+// :1974-2000: pin / free the pelvis with a stiff spring-damper on its three slides and damping on its ball joint
+static void sim_hold(cassie_sim_t *c, bool on) {
+  HostModel &hm = c->b->impl->hm; sim_push(c);
+  for (int i = 0; i < 3 && i < hm.njnt; i++) { hm.jnt_stiffness[i] = on ? 1e5 : 0; if (on) hm.qpos_spring[i] = c->qpos[i]; }
+  for (int i = 0; i < 6 && i < hm.nv; i++) { hm.dof_damping[i] = on ? (i < 3 ? 1e4 : 1e4) : 0; c->m_damp[i] = hm.dof_damping[i]; }
+  c->b->impl->rebuild_model(); sim_push(c);
+}
+void cassie_sim_hold(cassie_sim_t *c) { sim_hold(c, true); }
+void cassie_sim_release(cassie_sim_t *c) { sim_hold(c, false); }
+// :3380-3452
+cassie_state_t *cassie_state_alloc(void) { cassie_state *s = new cassie_state(); memset(s->qpos, 0, sizeof s->qpos); memset(s->qvel, 0, sizeof s->qvel); memset(s->qpos_snap, 0, sizeof s->qpos_snap); memset(s->qvel_snap, 0, sizeof s->qvel_snap); return s; }
+void cassie_state_free(cassie_state_t *s) { if (!s) return; if (s->snap && s->owner) s->owner->snap_free(s->snap); delete s; }
+double *cassie_state_time(cassie_state_t *s) { return &s->time; }
+double *cassie_state_qpos(cassie_state_t *s) { return s->qpos; }
+double *cassie_state_qvel(cassie_state_t *s) { return s->qvel; }
+void cassie_get_state(const cassie_sim_t *cc, cassie_state_t *s) {
+  cassie_sim_t *c = const_cast<cassie_sim_t *>(cc); BatchBase *impl = c->b->impl; sim_push(c);
+  if (s->snap && s->owner != impl) { s->owner->snap_free(s->snap); s->snap = nullptr; }   // (the batch object behind a cassie_sim_t outlives its states only if the caller frees them first, as with the reference's mjData)
+  if (!s->snap) { s->snap = impl->snap_alloc(); s->owner = impl; if (!s->snap) return; }
+  impl->snap_get(s->snap);
+  memcpy(s->qpos, c->qpos, sizeof s->qpos); memcpy(s->qvel, c->qvel, sizeof s->qvel); s->time = c->time;
+  memcpy(s->qpos_snap, s->qpos, sizeof s->qpos); memcpy(s->qvel_snap, s->qvel, sizeof s->qvel); s->time_snap = s->time;
+}
+void cassie_set_state(cassie_sim_t *c, const cassie_state_t *s) {
+  if (!s->snap) { set_err("cassie_set_state: the state object holds no snapshot (cassie_get_state first)"); return; }
+  BatchBase *impl = c->b->impl;
+  if (s->owner != impl) {   // a state taken from another simulator of the same model: through a snapshot of this one
+    void *t = impl->snap_alloc(); if (!t) return;
+    if (!impl->snap_copy(t, s->snap)) { impl->snap_free(t); return; }
+    impl->snap_set(t, nullptr); impl->snap_free(t);
+  } else impl->snap_set(s->snap, nullptr);
+  sim_pull(c);
+  // what the caller wrote through cassie_state_qpos / qvel / time after the snapshot was taken
+  if (memcmp(s->qpos, s->qpos_snap, sizeof s->qpos)) memcpy(c->qpos, s->qpos, sizeof s->qpos);
+  if (memcmp(s->qvel, s->qvel_snap, sizeof s->qvel)) memcpy(c->qvel, s->qvel, sizeof s->qvel);
+  if (s->time != s->time_snap) c->time = s->time;
+  sim_push(c);
+}
+void cassie_state_copy(cassie_state_t *dst, const cassie_state_t *src) {
+  if (!src->snap) return;
+  if (dst->snap && dst->owner != src->owner) { dst->owner->snap_free(dst->snap); dst->snap = nullptr; }
+  if (!dst->snap) { dst->snap = src->owner->snap_alloc(); dst->owner = src->owner; if (!dst->snap) return; }
+  src->owner->snap_copy(dst->snap, src->snap);
+  memcpy(dst->qpos, src->qpos, sizeof dst->qpos); memcpy(dst->qvel, src->qvel, sizeof dst->qvel); dst->time = src->time;
+  memcpy(dst->qpos_snap, src->qpos_snap, sizeof dst->qpos_snap); memcpy(dst->qvel_snap, src->qvel_snap, sizeof dst->qvel_snap); dst->time_snap = src->time_snap;
+}
+cassie_state_t *cassie_state_duplicate(const cassie_state_t *src) { cassie_state_t *s = cassie_state_alloc(); cassie_state_copy(s, src); return s; }
+// :1072-1093: model (per-environment constants, height field, timestep) and full dynamic state
+void cassie_sim_copy(cassie_sim_t *dst, const cassie_sim_t *csrc) {
+  cassie_sim_t *src = const_cast<cassie_sim_t *>(csrc); sim_push(src); sim_push(dst);
+  if (!dst->b->impl->copy_model_from(src->b->impl)) return;
+  dst->m_mass = src->m_mass; dst->m_ipos = src->m_ipos; dst->m_damp = src->m_damp; dst->m_fric = src->m_fric;
+  dst->m_mass_dev = dst->m_mass; dst->m_ipos_dev = dst->m_ipos; dst->m_damp_dev = dst->m_damp; dst->m_fric_dev = dst->m_fric;
+  dst->hfield = src->hfield; dst->hfield_dev = src->hfield_dev; dst->timestep = dst->timestep_dev = src->timestep;
+  for (int i = 0; i < 16; i++) dst->b->radio[i] = src->b->radio[i];
+  cassie_state_t *s = cassie_state_alloc(); cassie_get_state(src, s); cassie_set_state(dst, s); cassie_state_free(s);
+}
+cassie_sim_t *cassie_sim_duplicate(const cassie_sim_t *src) {
+  cassie_sim_t *c = cassie_sim_init(src->path.c_str(), true);
+  if (c) cassie_sim_copy(c, src);
+  return c;
+}
+// batched snapshots: an opaque handle per batch (cassie_batch_state_free before cassie_batch_free)
+void *cassie_batch_state_alloc(cassie_batch_t *b) { return b->impl->snap_alloc(); }
+void cassie_batch_state_free(cassie_batch_t *b, void *state) { b->impl->snap_free(state); }
+int cassie_batch_get_state(cassie_batch_t *b, void *state) { return state && b->impl->snap_get(state) ? 0 : -1; }
+int cassie_batch_set_state(cassie_batch_t *b, const void *state, const unsigned char *mask) { return state && b->impl->snap_set(state, mask) ? 0 : -1; }
 #include "legacy_stubs.inc"
 }  // extern "C"

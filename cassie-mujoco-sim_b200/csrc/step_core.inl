@@ -79,6 +79,7 @@ template <typename real> struct EnvPtrs {
   real *est_out;      // [EO_W] its outputs
   int *counters;      // [8]
   int cta_sync;       // 1: the CTA's warps rendezvous at the stage boundaries (STAGE_SYNC); only the step / forward modes
+  int nsub;           // > 0: physics sub-steps per control tick for this launch instead of round(5e-4 / timestep) (cassie_sim_step_pd_no2khz: 1)
 };
 
 // ------------------------------------------------------------------ scalar math on float / double
@@ -1767,7 +1768,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     }
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
-    const int nsub = forward_only ? 1 : cm.nsub;
+    const int nsub = forward_only ? 1 : (E.nsub > 0 ? E.nsub : cm.nsub);
     for (int s = 0; s < nsub; ++s) mj_substep<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, (tick == nticks - 1 && s == nsub - 1) ? E.aux : (real *)0, mode);
   }
   if (!forward_only) { LANES if (l == 0) ism[DF_TICK] = tick0 + nticks; ENDL }

@@ -19,6 +19,7 @@ extern "C" {
 #endif
 
 typedef struct cassie_sim cassie_sim_t;     /* include/cassiemujoco.h:31 */
+typedef struct cassie_state cassie_state_t; /* include/cassiemujoco.h:32 */
 typedef struct cassie_batch cassie_batch_t; /* new */
 
 /* ------------------------------------------------------------------ (1) legacy single-environment verbs */
@@ -53,6 +54,40 @@ int cassie_sim_ngeom(const cassie_sim_t *sim);
 int cassie_sim_njnt(const cassie_sim_t *sim);
 int cassie_sim_nu(const cassie_sim_t *sim);
 void cassie_integrate_pos(cassie_sim_t *sim, state_out_t *y);
+/* ---- the verbs RL wrappers call around the hot path
+ * include/cassiemujoco.h:85 (src/cassiemujoco.c:1137-1145): user torques -> safety layer -> motor model -> physics; *y = the bus of this tick.
+ * cassie_sim_step_ethercat (below the safety layer) stays a stub: the kernel always runs cassie_core_sim_step. */
+void cassie_sim_step(cassie_sim_t *sim, cassie_out_t *y, const cassie_user_in_t *u);
+/* src/cassiemujoco.c:1159-1181: cassie_sim_step_pd with ONE physics step per call whatever the model's timestep */
+void cassie_sim_step_pd_no2khz(cassie_sim_t *sim, state_out_t *y, const pd_in_t *u);
+/* src/cassiemujoco.c:2090-2092: the bus as the last step's sensors filled it (dynamic subset; the rest as cassie_out_init leaves it, :672-734) */
+cassie_out_t cassie_sim_get_cassie_out(cassie_sim_t *sim);
+/* include/cassiemujoco.h:108-112 (src/cassiemujoco.c:1196-1204): the physics timestep; control ticks stay 0.5 ms = round(5e-4 / timestep) sub-steps.
+ * The pointer is a host mirror: a write takes effect at the next step / forward.  cassie_batch_set_timestep: the same for a batch (0 / -1). */
+double *cassie_sim_timestep(cassie_sim_t *sim);
+void cassie_sim_set_timestep(cassie_sim_t *sim, double dt);
+int cassie_batch_set_timestep(cassie_batch_t *b, double dt);
+/* src/cassiemujoco.c:1221-1225: mj_forward on the current state; returns 0 */
+int cassie_sim_forward(cassie_sim_t *sim);
+/* include/cassiemujoco.h:271-275 (src/cassiemujoco.c:1974-2000): pin / free the pelvis (stiff spring-damper on its slides, damping on its ball joint) */
+void cassie_sim_hold(cassie_sim_t *sim);
+void cassie_sim_release(cassie_sim_t *sim);
+/* include/cassiemujoco.h:61-73 (src/cassiemujoco.c:1072-1093): model (per-environment constants, height field, timestep) + full dynamic state */
+cassie_sim_t *cassie_sim_duplicate(const cassie_sim_t *src);
+void cassie_sim_copy(cassie_sim_t *dst, const cassie_sim_t *src);
+/* include/cassiemujoco.h:434-463 (src/cassiemujoco.c:3380-3452): full dynamic state of a simulator -- qpos, qvel, warm start, time, sensor snapshot,
+ * cassie_out subset, encoder filters, torque delay line, applied forces, estimator filters, last observation row.  The borrowed time / qpos / qvel
+ * pointers are host mirrors: what the caller writes there after cassie_get_state is honoured by cassie_set_state.  A state is bound to the
+ * simulator (or one of the same model) it was taken from and must be freed before that simulator. */
+cassie_state_t *cassie_state_alloc(void);
+cassie_state_t *cassie_state_duplicate(const cassie_state_t *src);
+void cassie_state_copy(cassie_state_t *dst, const cassie_state_t *src);
+void cassie_state_free(cassie_state_t *state);
+double *cassie_state_time(cassie_state_t *state);
+double *cassie_state_qpos(cassie_state_t *state);
+double *cassie_state_qvel(cassie_state_t *state);
+void cassie_get_state(const cassie_sim_t *sim, cassie_state_t *state);
+void cassie_set_state(cassie_sim_t *sim, const cassie_state_t *state);
 /* Import compatibility: the library also exports, as stubs, the 133 further names example/cassiemujoco_ctypes.py resolves at import time
  * (cassie_vis_*, UDP, pack / unpack, pd_input_* / cassie_core_sim_* / state_output_* host objects, mjModel / mjData accessors, ...;
  * csrc/legacy_stubs.inc, list in tests/golden/ctypes_bound_names.txt).  They are outside the accelerated path: a call records an error
@@ -231,6 +266,12 @@ void cassie_b200_estimator_filter_step(void *filter, state_out_t *y);
  * clipped by the cgroup quota), which bounds the pack / unpack threads (CASSIE_B200_AOS_THREADS, default 32) */
 void cassie_batch_aos_timing(cassie_batch_t *b, double out[6], int reset);
 int cassie_b200_effective_cpus(void);
+/* Batched snapshots (new): every row array of the batch copied device-to-device into an opaque handle; restore all environments or the masked
+ * subset (mask as in cassie_batch_reset; e.g. return the fallen robots of an RL batch to a stored standing state).  0 / -1. */
+void *cassie_batch_state_alloc(cassie_batch_t *b);
+void cassie_batch_state_free(cassie_batch_t *b, void *state);
+int cassie_batch_get_state(cassie_batch_t *b, void *state);
+int cassie_batch_set_state(cassie_batch_t *b, const void *state, const unsigned char *mask);
 /* re-run mj_forward on the current state (after set_qpos / set_qvel), like cassie_sim_forward (src/cassiemujoco.c:1221-1225) */
 void cassie_batch_forward(cassie_batch_t *b);
 /* batched cassie_sim_apply_force / cassie_sim_clear_forces: xfrc [n][6]; one perturbed body per env */

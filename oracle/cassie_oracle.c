@@ -1408,6 +1408,7 @@ static void sensor_data_(OSim *c) { /* :737-774, 558-635 */
 
 /* cassie_sim_step_pd, src/cassiemujoco.c:1147-1157 (with :1137-1145 and :1115-1135 inlined).
  * y may be NULL.  cassie_out_copy (optional) receives the cassie_out_t the reference hands to the estimator. */
+static int g_no2khz = 0;   /* osim_step_pd_no2khz: one mj_step per call (src/cassiemujoco.c:1175) instead of round(5e-4 / timestep) */
 void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassie_out_copy) {
   double tq_user[10], tq_in[10];
 #ifdef ORACLE_USE_AGILITY_REF
@@ -1425,7 +1426,7 @@ void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassi
   sensor_data_(c);
   cassie_out_t out = c->cassie_out;
   if (cassie_out_copy) *cassie_out_copy = out;
-  int mjsteps = (int)round(5e-4 / c->m->timestep);
+  int mjsteps = g_no2khz ? 1 : (int)round(5e-4 / c->m->timestep);
   for (int i = 0; i < mjsteps; i++) o_step(c->m, c->d);
   if (y) {
 #ifdef ORACLE_USE_AGILITY_REF
@@ -1435,6 +1436,9 @@ void osim_step_pd(OSim *c, const pd_in_t *u, state_out_t *y, cassie_out_t *cassi
 #endif
   }
 }
+
+/* cassie_sim_step_pd_no2khz, src/cassiemujoco.c:1159-1181: the same blocks in the same order, ONE physics step */
+void osim_step_pd_no2khz(OSim *c, const pd_in_t *u, state_out_t *y) { g_no2khz = 1; osim_step_pd(c, u, y, NULL); g_no2khz = 0; }
 
 /* ------------------------------------------------------------------ derived-quantity queries (src/cassiemujoco.c:1586-1961)
  * Each function restates the reference function of the same name, INCLUDING which arrays it recomputes and which it reads stale:
@@ -1596,7 +1600,7 @@ double *osim_model_array(OSim *c, const char *key, int *n) {
 #define MARR(name, ptr, cnt) if (!strcmp(key, name)) { *n = (cnt); return (double *)(ptr); }
   MARR("body_mass", m->body_mass, m->nbody) MARR("body_ipos", m->body_ipos, 3 * m->nbody) MARR("dof_damping", m->dof_damping, m->nv)
   MARR("geom_friction", m->geom_friction, 3 * m->ngeom) MARR("body_invweight0", m->body_invweight0, 2 * m->nbody) MARR("dof_invweight0", m->dof_invweight0, m->nv)
-  MARR("body_subtreemass", m->body_subtreemass, m->nbody) MARR("meaninertia", &m->meaninertia, 1) MARR("body_pos", m->body_pos, 3 * m->nbody)
+  MARR("body_subtreemass", m->body_subtreemass, m->nbody) MARR("meaninertia", &m->meaninertia, 1) MARR("timestep", &m->timestep, 1) MARR("jnt_stiffness", m->jnt_stiffness, m->njnt) MARR("qpos_spring", m->qpos_spring, m->nq) MARR("body_pos", m->body_pos, 3 * m->nbody)
   *n = 0; return NULL;
 }
 

@@ -59,6 +59,7 @@ def load(ref=False):
     L.osim_new.argtypes = [C.c_char_p]
     L.osim_free.argtypes = [C.c_void_p]
     L.osim_step_pd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.osim_step_pd_no2khz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.osim_array.restype = C.POINTER(C.c_double)
     L.osim_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     L.osim_int.argtypes = [C.c_void_p, C.c_char_p]
@@ -127,6 +128,9 @@ class OracleSim:
     def step_pd(self, u, y=None, cassie_out=None):
         self.L.osim_step_pd(self.h, C.byref(u), C.byref(y) if y is not None else None,
                             C.byref(cassie_out) if cassie_out is not None else None)
+
+    def step_pd_no2khz(self, u, y=None):
+        self.L.osim_step_pd_no2khz(self.h, C.byref(u), C.byref(y) if y is not None else None)
 
     def forward(self):
         self.L.osim_forward(self.h)

@@ -15,7 +15,7 @@ using namespace cassie;
 template <typename real> struct Emu {
   HostModel hm; DevModel<real> dm; BuildInfo info; std::vector<real> sm; std::vector<int> ism;
   real qvel[32], qacc_ws[32], xqvel[32], xqacc_ws[32], pd[PD_W], xfrc[XFRC_W], obs[OBS_W], dbg[D_SIZE], cst[CST_W], qM[2 * NM_MAX], aux[AUX_W], cenv[CE_W], task[TASK_W], gait[GAIT_W]; bool use_gait = false; int counters[8]; double est[EST_W]; bool use_est = false; bool use_task = false; bool use_cenv = false, use_ext = true;   // use_ext: run the extended instance (derived-quantity rows on)
-  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.task = use_task ? task : nullptr; E.gait = use_gait ? gait : nullptr; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); E.est = use_est ? est : nullptr; E.est_out = obs + OB_EST_OUT; return E; }
+  EnvPtrs<real> ptrs() { EnvPtrs<real> E; E.cst = cst; E.dfilt = ism.data(); E.pd = pd; E.xfrc = xfrc; E.obs = obs; E.qM = qM; E.dbg = dbg; E.counters = counters; E.cta_sync = 0; E.nsub = 0; E.task = use_task ? task : nullptr; E.gait = use_gait ? gait : nullptr; E.aux = use_ext ? aux : nullptr; E.cenv = use_cenv ? cenv : nullptr; E.hfield = hfield.empty() ? nullptr : hfield.data(); E.est = use_est ? est : nullptr; E.est_out = obs + OB_EST_OUT; return E; }
   std::vector<float> hfield;
   bool init(const char *path, std::string &err) {
     if (!load_model_any(path, hm, err)) return false;
