@@ -18,9 +18,29 @@
 #include "../../include/cassie_b200.h"
 #include "devbuild.h"
 #include "estimator_host.h"
-#include "step_core.inl"
+#include "step_kernel.cuh"
+
+// the step-kernel instances live in their own translation units (step_inst.cu, one compilation per instance)
+#define CASSIE_STEP_ENTRY(tag) extern "C" const void *cassie_step_entry_##tag(void);
+CASSIE_STEP_ENTRY(f00) CASSIE_STEP_ENTRY(f10) CASSIE_STEP_ENTRY(f02) CASSIE_STEP_ENTRY(f12) CASSIE_STEP_ENTRY(f05) CASSIE_STEP_ENTRY(f15) CASSIE_STEP_ENTRY(f07) CASSIE_STEP_ENTRY(f17)
+CASSIE_STEP_ENTRY(d07) CASSIE_STEP_ENTRY(d17)
+#undef CASSIE_STEP_ENTRY
 
 namespace cassie {
+
+// the instance for (precision, plain / extended, model features): the smallest compiled feature set that covers the model's
+template <typename real> static const void *step_entry(bool ext, int feat, int *compiled_feat = nullptr) {
+  int f = F_ALL;
+  if (!std::is_same<real, double>::value) { if (feat == 0) f = 0; else if (feat == F_HFIELD) f = F_HFIELD; else if ((feat & ~(F_XB | F_BOX)) == 0) f = F_XB | F_BOX; }
+  if (compiled_feat) *compiled_feat = f;
+  if (std::is_same<real, double>::value) return ext ? cassie_step_entry_d17() : cassie_step_entry_d07();
+  switch (f) {
+    case 0: return ext ? cassie_step_entry_f10() : cassie_step_entry_f00();
+    case F_HFIELD: return ext ? cassie_step_entry_f12() : cassie_step_entry_f02();
+    case F_XB | F_BOX: return ext ? cassie_step_entry_f15() : cassie_step_entry_f05();
+    default: return ext ? cassie_step_entry_f17() : cassie_step_entry_f07();
+  }
+}
 
 static thread_local std::string g_err;
 static void set_err(const std::string &e) { g_err = e; fprintf(stderr, "cassie_b200: %s\n", e.c_str()); }
@@ -37,89 +57,6 @@ static int effective_cpus() {
   }
   if (quota > 0 && period > 0) { const int c = (int)((quota + period - 1) / period); if (c >= 1 && c < hw) hw = c; }
   return hw < 1 ? 1 : hw;
-}
-
-template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync, nsub, warp_stride; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy; all threads of the CTA return after it landed
-__device__ __forceinline__ void tma_stage(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  const uint32_t bar_a = smem_u32(bar), dst_a = smem_u32(dst_smem);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a), "l"(src_gmem), "r"(bytes), "r"(bar_a) : "memory");
-  }
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(bar_a), "r"(0) : "memory");
-}
-
-template <typename real> __host__ __device__ constexpr size_t model_bytes() { return (sizeof(DevModel<real>) + 127) / 128 * 128; }
-template <typename real> __host__ __device__ constexpr size_t warp_bytes(int ystride, bool ext) { return ((size_t)(ext ? scratch_reals_ext(ystride) : scratch_reals(ystride)) * sizeof(real) + 127) / 128 * 128; }
-
-// mode 0: step nticks; mode 1: mj_forward only
-template <typename real, bool DR>
-__global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *__restrict__ gmodel, EnvArrays<real> A, int nticks, int mode) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
-  DevModel<real> *cmp = reinterpret_cast<DevModel<real> *>(smem_raw);
-  tma_stage(cmp, gmodel, (uint32_t)model_bytes<real>(), &bar);
-  const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
-  real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + warp * A.warp_stride);   // warp_stride = warp_bytes(ystride, instance), precomputed on the host: cheap to rematerialise under register pressure
-  const int qw = A.qpos_w, vw = A.qvel_w;
-  const DevModel<real> &cm = *cmp;
-  // persistent CTAs: a CTA draws one environment per warp from a global ticket counter until the batch is exhausted; its warps walk the
-  // stages together (STAGE_SYNC) so that they share instruction-cache lines -- the kernel is ~250 KB of code, eight times the L1.5
-  __shared__ int cta_base;
-  const int nwarps = blockDim.x >> 5, sync_on = (mode == 0 && nticks > 1) ? A.cta_sync : 0;   // a single tick starts in step and stays close enough
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) cta_base = atomicAdd(A.ticket, nwarps);
-    __syncthreads();
-    const int base = cta_base;
-    if (base >= A.n) break;
-    const int env = base + warp;
-    const bool active = env < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
-    if (!active) {   // keep the rendezvous count of the working warps
-      if (sync_on) { const int per = __popc(sync_on); for (int i = 0; i < nticks * (A.nsub > 0 ? A.nsub : cm.nsub) * per; ++i) __syncthreads(); }
-      continue;
-    }
-    // warm the L2/L1 path of the rows that are addressed in place later (controller state, PD row, FIR taps)
-    if (l < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cst + (size_t)env * CST_W + 32 * l));
-    else if (l < 9) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dfilt + (size_t)env * DFILT_W + 32 * (l - 6)));
-    else if (l < 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pd + (size_t)env * PD_W + 32 * (l - 9)));
-    else if (l == 11) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.xfrc + (size_t)env * XFRC_W));
-    // optional zero-copy input: this environment's motor-PD row straight from mapped host memory into its device row (the AoS entry point
-    // uses one DMA instead: 2 x 4096 small PCIe reads at kernel start were measured slower than the copy engine; kept for C2C-attached hosts)
-    if (A.pd_host) { for (int i = l; i < PD_W; i += 32) A.pd[(size_t)env * PD_W + i] = A.pd_host[(size_t)env * PD_W + i]; }
-    // state rows: qpos to shared memory, qvel / warm start one value per lane; everything else is addressed in place
-    for (int i = l; i < qw; i += 32) sm[S_QPOS + i] = (mode == 3) ? cm.qpos0[i] : A.qpos[(size_t)env * qw + i];   // set_const works at the reference configuration
-    real qvel = A.qvel[(size_t)env * vw + l], qacc_ws = A.qacc_ws[(size_t)env * vw + l], xqvel = 0, xqacc_ws = 0;
-    if (A.xb >= 0 && l < 6) { xqvel = A.qvel[(size_t)env * vw + 32 + l]; xqacc_ws = A.qacc_ws[(size_t)env * vw + 32 + l]; }
-    __syncwarp();
-    EnvPtrs<real> E;
-    E.cst = A.cst + (size_t)env * CST_W; E.dfilt = A.dfilt + (size_t)env * DFILT_W; E.pd = A.pd + (size_t)env * PD_W; E.xfrc = A.xfrc + (size_t)env * XFRC_W; E.task = A.task ? A.task + (size_t)env * TASK_W : nullptr; E.gait = A.gait ? A.gait + (size_t)env * GAIT_W : nullptr;
-    E.hfield = A.hfield ? A.hfield + (size_t)(env % A.n_terrain) * A.hfield_stride : nullptr;
-    E.obs = A.obs + (size_t)env * OBS_W; E.qM = A.qM + (size_t)env * 2 * NM_MAX; E.dbg = A.dbg ? A.dbg + (size_t)env * D_SIZE : nullptr; E.counters = A.counters + (size_t)env * 8;
-    E.aux = A.aux ? A.aux + (size_t)env * AUX_W : nullptr; E.cenv = A.cenv ? A.cenv + (size_t)env * CE_W : nullptr; E.cta_sync = sync_on; E.nsub = A.nsub;
-    E.est = A.est ? A.est + (size_t)env * EST_W : nullptr; E.est_out = E.obs + OB_EST_OUT;
-    step_env<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode);
-    __syncwarp();
-    if (mode >= 2) continue;   // query / set_const: only the aux row / the constant row is written
-    for (int i = l; i < qw; i += 32) A.qpos[(size_t)env * qw + i] = sm[S_QPOS + i];
-    A.qvel[(size_t)env * vw + l] = qvel; A.qacc_ws[(size_t)env * vw + l] = qacc_ws;
-    if (A.xb >= 0 && l < 6) { A.qvel[(size_t)env * vw + 32 + l] = xqvel; A.qacc_ws[(size_t)env * vw + 32 + l] = xqacc_ws; }
-    // ... and its observation row goes back the same way as soon as the environment is done, overlapped with the environments still stepping
-    if (A.obs_host) { for (int i = l; i < OBS_W; i += 32) A.obs_host[(size_t)env * OBS_W + i] = A.obs[(size_t)env * OBS_W + i]; }
-    __syncwarp();
-  }
 }
 
 // cassie_integrate_pos for the whole batch (mj_integratePos, src/cassiemujoco.c:1183-1189): the HBM-bound kernel.
@@ -210,6 +147,34 @@ __global__ void copy_rows_kernel(T *__restrict__ dst, const T *__restrict__ src,
 }
 
 // ------------------------------------------------------------------ host side
+// device-resident copy of every per-environment row array of a batch (cassie_state_t / cassie_batch_get_state); it owns its memory and carries its own
+// sizes, so it can be copied, restored into any batch of the same shape and freed without the batch it was taken from
+struct Snap {
+  enum { R_QPOS, R_QVEL, R_QACC, R_CST, R_XFRC, R_OBS, R_DFILT, R_EST, R_AUX, NROWS };
+  int device = 0, n = 0, esz = 4, qw = 0, vw = 0; bool has_est = false, has_aux = false;
+  void *rows[NROWS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int width(int r) const { const int w[NROWS] = {qw, vw, vw, CST_W, XFRC_W, OBS_W, DFILT_W, EST_W, AUX_W}; return w[r]; }
+  int elem(int r) const { return r == R_DFILT ? 4 : (r == R_EST ? 8 : esz); }
+  size_t bytes(int r) const { return (size_t)n * width(r) * elem(r); }
+};
+static void snap_delete(Snap *k) { if (!k) return; cudaSetDevice(k->device); for (int r = 0; r < Snap::NROWS; r++) cudaFree(k->rows[r]); delete k; }
+static Snap *snap_new(int device, int n, int esz, int qw, int vw) {
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  Snap *k = new Snap(); k->device = device; k->n = n; k->esz = esz; k->qw = qw; k->vw = vw;
+  for (int r = 0; r < Snap::NROWS; r++) if (r != Snap::R_EST && r != Snap::R_AUX && cudaMalloc(&k->rows[r], k->bytes(r)) != cudaSuccess) { snap_delete(k); return nullptr; }
+  return k;
+}
+static bool snap_clone_into(Snap *d, const Snap *k) {   // same shape required
+  if (d->n != k->n || d->esz != k->esz || d->qw != k->qw || d->vw != k->vw || cudaSetDevice(d->device) != cudaSuccess) return false;
+  d->has_est = k->has_est; d->has_aux = k->has_aux;
+  for (int r = 0; r < Snap::NROWS; r++) {
+    if ((r == Snap::R_EST && !k->has_est) || (r == Snap::R_AUX && !k->has_aux)) continue;
+    if (!d->rows[r] && cudaMalloc(&d->rows[r], d->bytes(r)) != cudaSuccess) return false;
+    if (cudaMemcpy(d->rows[r], k->rows[r], k->bytes(r), cudaMemcpyDefault) != cudaSuccess) return false;
+  }
+  return true;
+}
+
 struct BatchBase {
   virtual ~BatchBase() {}
   bool est_forces = false;   // fill toeForce / heelForce of state_out_t on the host (cassie_batch_enable_estimator_forces)
@@ -244,11 +209,9 @@ struct BatchBase {
   virtual bool has_aux() const = 0;
   // full dynamic state of every environment (cassie_get_state / cassie_set_state, src/cassiemujoco.c:3435-3452: mjData + the block objects +
   // cassie_out + encoder filters + torque delay line): device-resident snapshots, restore of a masked subset
-  virtual void *snap_alloc() = 0;
-  virtual bool snap_get(void *snap) = 0;
-  virtual bool snap_set(const void *snap, const unsigned char *mask) = 0;
-  virtual bool snap_copy(void *dst, const void *src) = 0;
-  virtual void snap_free(void *snap) = 0;
+  virtual Snap *snap_alloc() = 0;
+  virtual bool snap_get(Snap *snap) = 0;
+  virtual bool snap_set(const Snap *snap, const unsigned char *mask) = 0;
   virtual bool copy_model_from(BatchBase *src) = 0;     // per-environment constants, height fields, timestep (mj_copyModel in cassie_sim_copy, :1083-1091)
   virtual bool rebuild_model() = 0;                     // after hm was edited (timestep, hold / release): rebuild and upload the constant block
   int nsub_override = 0;                                // > 0: physics sub-steps per control tick of the next launches (cassie_sim_step_pd_no2khz)
@@ -258,6 +221,7 @@ struct BatchBase {
 template <typename real> struct Batch : BatchBase {
   DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; int QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
   struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[2];   // [0] plain instance, [1] extended instance
+  int feat = F_ALL;   // model features (F_XB | F_HFIELD | F_BOX): selects the kernel instance
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr, *pin_task = nullptr;   // pinned staging for the AoS entry point
   real *dpin_pd = nullptr, *dpin_obs = nullptr;                      // the same buffers as the device sees them (mapped)
@@ -279,8 +243,10 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMalloc(&d_model, model_bytes<real>()));
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
     h_model_copy = *hmodel; memcpy(geom_dev, info.geom_dev, sizeof geom_dev);
+    feat = hmodel->xb >= 0 ? F_XB : 0;   // which kernel instance this model needs (step_inst.cu)
+    for (int p = 0; p < hmodel->npair; p++) { const int k = hmodel->pair_kind[p]; if (k == PAIR_HFIELD_SPHERE || k == PAIR_HFIELD_CAPSULE) feat |= F_HFIELD; else if (k >= PAIR_PLANE_BOX) feat |= F_BOX; }
     const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
-    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; { const char *e = getenv("CASSIE_B200_SYNCMASK"); A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : (e ? (atoi(e) & 31) : 10); }   // which of the five per-sub-step rendezvous are on
+    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; { const char *e = getenv("CASSIE_B200_WARP_TICKETS"); A.warp_tickets = e ? atoi(e) : 0; } { const char *e = getenv("CASSIE_B200_SYNCMASK"); A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : (e ? (atoi(e) & 31) : 10); }   // which of the five per-sub-step rendezvous are on
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QW)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * VW)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * VW));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));
@@ -316,10 +282,9 @@ template <typename real> struct Batch : BatchBase {
       }
       cfg[ext].wpb = k_sel; cfg[ext].smem = model_bytes<real>() + (size_t)k_sel * wb;
       int per_sm = 0;
-      if (ext) { CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));
-                 CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real, true>, 32 * k_sel, cfg[ext].smem)); }
-      else { CUDA_OK(cudaFuncSetAttribute(cassie_step_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));
-             CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cassie_step_kernel<real, false>, 32 * k_sel, cfg[ext].smem)); }
+      { const void *entry = step_entry<real>(ext != 0, feat);
+        CUDA_OK(cudaFuncSetAttribute(entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entry, 32 * k_sel, cfg[ext].smem)); }
       cfg[ext].resident_ctas = per_sm * sms < 1 ? 1 : per_sm * sms;
     }
     wpb = cfg[0].wpb;
@@ -552,48 +517,36 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemcpyAsync(A.task, h_tmp.data(), sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream)); CUDA_OK(cudaStreamSynchronize(stream));
     return true;
   }
-  // ---- snapshots
-  struct Snap { real *qpos = nullptr, *qvel = nullptr, *qacc_ws = nullptr, *cst = nullptr, *xfrc = nullptr, *obs = nullptr, *aux = nullptr; int *dfilt = nullptr; double *est = nullptr; bool has_est = false, has_aux = false; };
-  void *snap_alloc() override {
-    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
-    Snap *k = new Snap();
-    if (cudaMalloc(&k->qpos, sizeof(real) * n * QW) != cudaSuccess || cudaMalloc(&k->qvel, sizeof(real) * n * VW) != cudaSuccess || cudaMalloc(&k->qacc_ws, sizeof(real) * n * VW) != cudaSuccess ||
-        cudaMalloc(&k->cst, sizeof(real) * n * CST_W) != cudaSuccess || cudaMalloc(&k->xfrc, sizeof(real) * n * XFRC_W) != cudaSuccess || cudaMalloc(&k->obs, sizeof(real) * n * OBS_W) != cudaSuccess ||
-        cudaMalloc(&k->dfilt, sizeof(int) * n * DFILT_W) != cudaSuccess) { snap_free(k); set_err("snapshot: out of device memory"); return nullptr; }
-    return k;
-  }
-  void snap_free(void *p) override { if (!p) return; Snap *k = (Snap *)p; cudaSetDevice(device); cudaFree(k->qpos); cudaFree(k->qvel); cudaFree(k->qacc_ws); cudaFree(k->cst); cudaFree(k->xfrc); cudaFree(k->obs); cudaFree(k->aux); cudaFree(k->dfilt); cudaFree(k->est); delete k; }
-  template <typename T> bool rows_copy(T *dst, const T *src, int w, const unsigned char *dmask) {
-    if (!dmask) { CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(T) * n * w, cudaMemcpyDeviceToDevice, stream)); return true; }
-    copy_rows_kernel<T><<<256, 256, 0, stream>>>(dst, src, w, dmask, n); CUDA_OK(cudaGetLastError()); return true;
-  }
-  bool snap_get(void *p) override {
-    Snap *k = (Snap *)p; CUDA_OK(cudaSetDevice(device));
-    if (!rows_copy(k->qpos, A.qpos, QW, nullptr) || !rows_copy(k->qvel, A.qvel, VW, nullptr) || !rows_copy(k->qacc_ws, A.qacc_ws, VW, nullptr) || !rows_copy(k->cst, A.cst, CST_W, nullptr) ||
-        !rows_copy(k->xfrc, A.xfrc, XFRC_W, nullptr) || !rows_copy(k->obs, A.obs, OBS_W, nullptr) || !rows_copy(k->dfilt, A.dfilt, DFILT_W, nullptr)) return false;
+  // ---- snapshots (the Snap object owns its device memory and knows its own sizes: it may outlive this batch)
+  Snap *snap_alloc() override { Snap *k = snap_new(device, n, (int)sizeof(real), QW, VW); if (!k) set_err("snapshot: out of device memory"); return k; }
+  bool snap_compatible(const Snap *k) { if (k && k->n == n && k->esz == (int)sizeof(real) && k->qw == QW && k->vw == VW) return true; set_err("snapshot: taken from a batch of another size, precision or model"); return false; }
+  void *snap_src(int r) { void *t[Snap::NROWS] = {A.qpos, A.qvel, A.qacc_ws, A.cst, A.xfrc, A.obs, A.dfilt, A.est, A.aux}; return t[r]; }
+  bool snap_get(Snap *k) override {
+    if (!snap_compatible(k)) return false;
+    CUDA_OK(cudaSetDevice(device));
     k->has_est = A.est != nullptr; k->has_aux = A.aux != nullptr;
-    if (k->has_est) { if (!k->est) CUDA_OK(cudaMalloc(&k->est, sizeof(double) * n * EST_W)); if (!rows_copy(k->est, A.est, EST_W, nullptr)) return false; }
-    if (k->has_aux) { if (!k->aux) CUDA_OK(cudaMalloc(&k->aux, sizeof(real) * n * AUX_W)); if (!rows_copy(k->aux, A.aux, AUX_W, nullptr)) return false; }
+    for (int r = 0; r < Snap::NROWS; r++) {
+      if ((r == Snap::R_EST && !k->has_est) || (r == Snap::R_AUX && !k->has_aux)) continue;
+      if (!k->rows[r]) CUDA_OK(cudaMalloc(&k->rows[r], k->bytes(r)));
+      CUDA_OK(cudaMemcpyAsync(k->rows[r], snap_src(r), k->bytes(r), cudaMemcpyDeviceToDevice, stream));
+    }
     return sync();
   }
-  bool snap_set(const void *p, const unsigned char *mask) override {
-    const Snap *k = (const Snap *)p; CUDA_OK(cudaSetDevice(device));
+  bool snap_set(const Snap *k, const unsigned char *mask) override {
+    if (!snap_compatible(k)) return false;
+    CUDA_OK(cudaSetDevice(device));
     const unsigned char *dm = nullptr;
     if (mask) { if (!upload_mask(mask)) return false; dm = d_mask; }
-    if (!rows_copy(A.qpos, (const real *)k->qpos, QW, dm) || !rows_copy(A.qvel, (const real *)k->qvel, VW, dm) || !rows_copy(A.qacc_ws, (const real *)k->qacc_ws, VW, dm) || !rows_copy(A.cst, (const real *)k->cst, CST_W, dm) ||
-        !rows_copy(A.xfrc, (const real *)k->xfrc, XFRC_W, dm) || !rows_copy(A.obs, (const real *)k->obs, OBS_W, dm) || !rows_copy(A.dfilt, (const int *)k->dfilt, DFILT_W, dm)) return false;
-    if (k->has_est) { if (!A.est && !enable_estimator_device(true)) return false; if (!rows_copy(A.est, (const double *)k->est, EST_W, dm)) return false; }
-    else if (A.est && !reset_estimator_device(mask)) return false;   // the snapshot was taken before the estimator ran: it starts afresh
-    if (k->has_aux && A.aux && !rows_copy(A.aux, (const real *)k->aux, AUX_W, dm)) return false;
-    return sync();
-  }
-  bool snap_copy(void *pd, const void *ps) override {
-    Snap *d = (Snap *)pd; const Snap *k = (const Snap *)ps; CUDA_OK(cudaSetDevice(device));
-    if (!rows_copy(d->qpos, (const real *)k->qpos, QW, nullptr) || !rows_copy(d->qvel, (const real *)k->qvel, VW, nullptr) || !rows_copy(d->qacc_ws, (const real *)k->qacc_ws, VW, nullptr) || !rows_copy(d->cst, (const real *)k->cst, CST_W, nullptr) ||
-        !rows_copy(d->xfrc, (const real *)k->xfrc, XFRC_W, nullptr) || !rows_copy(d->obs, (const real *)k->obs, OBS_W, nullptr) || !rows_copy(d->dfilt, (const int *)k->dfilt, DFILT_W, nullptr)) return false;
-    d->has_est = k->has_est; d->has_aux = k->has_aux;
-    if (k->has_est) { if (!d->est) CUDA_OK(cudaMalloc(&d->est, sizeof(double) * n * EST_W)); if (!rows_copy(d->est, (const double *)k->est, EST_W, nullptr)) return false; }
-    if (k->has_aux) { if (!d->aux) CUDA_OK(cudaMalloc(&d->aux, sizeof(real) * n * AUX_W)); if (!rows_copy(d->aux, (const real *)k->aux, AUX_W, nullptr)) return false; }
+    if (k->has_est && !A.est && !enable_estimator_device(true)) return false;
+    if (!k->has_est && A.est && !reset_estimator_device(mask)) return false;   // the snapshot was taken before the estimator ran: it starts afresh
+    for (int r = 0; r < Snap::NROWS; r++) {
+      if ((r == Snap::R_EST && !k->has_est) || (r == Snap::R_AUX && (!k->has_aux || !A.aux))) continue;
+      if (!dm) { CUDA_OK(cudaMemcpyAsync(snap_src(r), k->rows[r], k->bytes(r), cudaMemcpyDeviceToDevice, stream)); continue; }
+      const int w = k->width(r);
+      if (k->elem(r) == 8) copy_rows_kernel<unsigned long long><<<256, 256, 0, stream>>>((unsigned long long *)snap_src(r), (const unsigned long long *)k->rows[r], w, dm, n);
+      else copy_rows_kernel<unsigned int><<<256, 256, 0, stream>>>((unsigned int *)snap_src(r), (const unsigned int *)k->rows[r], w, dm, n);
+      CUDA_OK(cudaGetLastError());
+    }
     return sync();
   }
   bool rebuild_model() override {
@@ -641,8 +594,8 @@ template <typename real> struct Batch : BatchBase {
     const LaunchCfg &c = cfg[ext ? 1 : 0];
     int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
     CUDA_OK(cudaMemsetAsync(A.ticket, 0, sizeof(int), stream));
-    if (ext) cassie_step_kernel<real, true><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
-    else cassie_step_kernel<real, false><<<grid, 32 * c.wpb, c.smem, stream>>>(d_model, A, nticks, mode);
+    { const DevModel<real> *dm = d_model; void *args[4] = {(void *)&dm, (void *)&A, (void *)&nticks, (void *)&mode};
+      CUDA_OK(cudaLaunchKernel(step_entry<real>(ext, feat), dim3(grid), dim3(32 * c.wpb), args, c.smem, stream)); }
     launches++;
     CUDA_OK(cudaGetLastError());
     return true;
@@ -732,7 +685,7 @@ struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[6
 
 // cassie_state_t (include/cassiemujoco.h:434-463): a device-resident snapshot of one simulator's rows plus the host mirrors the reference hands out as
 // borrowed pointers (time, qpos, qvel); the snapshot is allocated by the first cassie_get_state, which also fixes the owning simulator's sizes
-struct cassie_state { BatchBase *owner = nullptr; void *snap = nullptr; double qpos[64], qvel[64], time = 0, qpos_snap[64], qvel_snap[64], time_snap = 0; };
+struct cassie_state { cassie::Snap *snap = nullptr; double qpos[64], qvel[64], time = 0, qpos_snap[64], qvel_snap[64], time_snap = 0; };
 
 static std::mutex g_model_mutex;
 static std::string g_model_path;   // what cassie_mujoco_init cached (the reference caches the parsed model, src/cassiemujoco.c:48-59)
@@ -1000,26 +953,21 @@ void cassie_sim_hold(cassie_sim_t *c) { sim_hold(c, true); }
 void cassie_sim_release(cassie_sim_t *c) { sim_hold(c, false); }
 // :3380-3452
 cassie_state_t *cassie_state_alloc(void) { cassie_state *s = new cassie_state(); memset(s->qpos, 0, sizeof s->qpos); memset(s->qvel, 0, sizeof s->qvel); memset(s->qpos_snap, 0, sizeof s->qpos_snap); memset(s->qvel_snap, 0, sizeof s->qvel_snap); return s; }
-void cassie_state_free(cassie_state_t *s) { if (!s) return; if (s->snap && s->owner) s->owner->snap_free(s->snap); delete s; }
+void cassie_state_free(cassie_state_t *s) { if (!s) return; snap_delete(s->snap); delete s; }
 double *cassie_state_time(cassie_state_t *s) { return &s->time; }
 double *cassie_state_qpos(cassie_state_t *s) { return s->qpos; }
 double *cassie_state_qvel(cassie_state_t *s) { return s->qvel; }
 void cassie_get_state(const cassie_sim_t *cc, cassie_state_t *s) {
   cassie_sim_t *c = const_cast<cassie_sim_t *>(cc); BatchBase *impl = c->b->impl; sim_push(c);
-  if (s->snap && s->owner != impl) { s->owner->snap_free(s->snap); s->snap = nullptr; }   // (the batch object behind a cassie_sim_t outlives its states only if the caller frees them first, as with the reference's mjData)
-  if (!s->snap) { s->snap = impl->snap_alloc(); s->owner = impl; if (!s->snap) return; }
+  if (s->snap && !(s->snap->n == 1 && s->snap->qw == cassie_batch_row_width(c->b, "qpos") && s->snap->vw == cassie_batch_row_width(c->b, "qvel") && s->snap->device == impl->device)) { snap_delete(s->snap); s->snap = nullptr; }
+  if (!s->snap) { s->snap = impl->snap_alloc(); if (!s->snap) return; }
   impl->snap_get(s->snap);
   memcpy(s->qpos, c->qpos, sizeof s->qpos); memcpy(s->qvel, c->qvel, sizeof s->qvel); s->time = c->time;
   memcpy(s->qpos_snap, s->qpos, sizeof s->qpos); memcpy(s->qvel_snap, s->qvel, sizeof s->qvel); s->time_snap = s->time;
 }
 void cassie_set_state(cassie_sim_t *c, const cassie_state_t *s) {
   if (!s->snap) { set_err("cassie_set_state: the state object holds no snapshot (cassie_get_state first)"); return; }
-  BatchBase *impl = c->b->impl;
-  if (s->owner != impl) {   // a state taken from another simulator of the same model: through a snapshot of this one
-    void *t = impl->snap_alloc(); if (!t) return;
-    if (!impl->snap_copy(t, s->snap)) { impl->snap_free(t); return; }
-    impl->snap_set(t, nullptr); impl->snap_free(t);
-  } else impl->snap_set(s->snap, nullptr);
+  if (!c->b->impl->snap_set(s->snap, nullptr)) return;   // any simulator of the same model accepts it
   sim_pull(c);
   // what the caller wrote through cassie_state_qpos / qvel / time after the snapshot was taken
   if (memcmp(s->qpos, s->qpos_snap, sizeof s->qpos)) memcpy(c->qpos, s->qpos, sizeof s->qpos);
@@ -1029,9 +977,9 @@ void cassie_set_state(cassie_sim_t *c, const cassie_state_t *s) {
 }
 void cassie_state_copy(cassie_state_t *dst, const cassie_state_t *src) {
   if (!src->snap) return;
-  if (dst->snap && dst->owner != src->owner) { dst->owner->snap_free(dst->snap); dst->snap = nullptr; }
-  if (!dst->snap) { dst->snap = src->owner->snap_alloc(); dst->owner = src->owner; if (!dst->snap) return; }
-  src->owner->snap_copy(dst->snap, src->snap);
+  if (dst->snap && (dst->snap->n != src->snap->n || dst->snap->qw != src->snap->qw || dst->snap->vw != src->snap->vw || dst->snap->esz != src->snap->esz)) { snap_delete(dst->snap); dst->snap = nullptr; }
+  if (!dst->snap) { dst->snap = snap_new(src->snap->device, src->snap->n, src->snap->esz, src->snap->qw, src->snap->vw); if (!dst->snap) return; }
+  if (!snap_clone_into(dst->snap, src->snap)) { set_err("cassie_state_copy failed"); return; }
   memcpy(dst->qpos, src->qpos, sizeof dst->qpos); memcpy(dst->qvel, src->qvel, sizeof dst->qvel); dst->time = src->time;
   memcpy(dst->qpos_snap, src->qpos_snap, sizeof dst->qpos_snap); memcpy(dst->qvel_snap, src->qvel_snap, sizeof dst->qvel_snap); dst->time_snap = src->time_snap;
 }
@@ -1053,8 +1001,8 @@ cassie_sim_t *cassie_sim_duplicate(const cassie_sim_t *src) {
 }
 // batched snapshots: an opaque handle per batch (cassie_batch_state_free before cassie_batch_free)
 void *cassie_batch_state_alloc(cassie_batch_t *b) { return b->impl->snap_alloc(); }
-void cassie_batch_state_free(cassie_batch_t *b, void *state) { b->impl->snap_free(state); }
-int cassie_batch_get_state(cassie_batch_t *b, void *state) { return state && b->impl->snap_get(state) ? 0 : -1; }
-int cassie_batch_set_state(cassie_batch_t *b, const void *state, const unsigned char *mask) { return state && b->impl->snap_set(state, mask) ? 0 : -1; }
+void cassie_batch_state_free(cassie_batch_t *b, void *state) { (void)b; snap_delete((Snap *)state); }
+int cassie_batch_get_state(cassie_batch_t *b, void *state) { return state && b->impl->snap_get((Snap *)state) ? 0 : -1; }
+int cassie_batch_set_state(cassie_batch_t *b, const void *state, const unsigned char *mask) { return state && b->impl->snap_set((const Snap *)state, mask) ? 0 : -1; }
 #include "legacy_stubs.inc"
 }  // extern "C"

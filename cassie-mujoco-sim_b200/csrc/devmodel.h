@@ -26,6 +26,9 @@ constexpr int MAXCON = 12;    // contacts per env
 constexpr int YSTRIDE_MAIN = 33;  // row stride of the constraint matrix in shared memory: dofs + 1 (odd: bank-conflict free both ways)
 constexpr int YSTRIDE_MAX = 39;   // with the 6 dofs of an extra free body (cassie_tray_box.xml)
 
+// model features a kernel instance is compiled for (template parameter FEAT): an instance without a feature carries none of its code
+constexpr int F_XB = 1, F_HFIELD = 2, F_BOX = 4, F_ALL = 7;   // extra free body (cassie_tray_box.xml's cup), height field, box geoms
+
 // pair kinds handled by the narrow phase
 enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2, PAIR_HFIELD_SPHERE = 3, PAIR_HFIELD_CAPSULE = 4,
                 PAIR_PLANE_BOX = 5, PAIR_SPHERE_BOX = 6, PAIR_CAPSULE_BOX = 7, PAIR_BOX_BOX = 8 };

@@ -475,7 +475,7 @@ CFN void aux_foot_velocities(const DevModel<real> &cm, real *sm, real *aux) {
 // DR ("extended" instance): the batch carries per-environment model constants (domain randomisation) and / or derived-quantity rows.  A
 // compile-time flag so that the plain instance keeps its constants in the shared model block with no indirection and contains neither the
 // set_const stage nor the derived-quantity stages.
-template <typename real, bool DR>
+template <typename real, bool DR, int FEAT>
 CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), LP(real, ctrl), real *dbg, real *aux_row, int mode) {
   const bool advance = (mode == 0);   // mode: 0 step, 1 mj_forward only, 2 query (kinematics + velocities -> centre-of-mass slots of the aux row, nothing else written),
                                       //       3 set_const (invweights / masses / mean inertia at the reference configuration -> the env's constant row)
@@ -488,11 +488,13 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   const bool use2 = advance && (cm.has_damping || ce);   // the Euler stage needs the factor of M + h B: produced together with M's
   const bool keep_qM = dbg || mode == 3;                 // the unfactored M itself is only wanted by the debug dump and by set_const
   const real root_mass_inv = ce ? ce[CE_ROOT_MINV] : cm.root_mass_inv, total_mass_inv = ce ? ce[CE_TOT_MINV] : cm.total_mass_inv, pgs_scale = ce ? ce[CE_PGS_SCALE] : cm.pgs_scale;
-  const real xb_dsqi_t = (ce && cm.xb >= 0) ? real(1) / msqrt(bmass[cm.xb]) : cm.xb_dsqi[0];   // the extra free body's mass acts at once, like every body_mass entry
+  const real xb_dsqi_t = ((FEAT & F_XB) && ce && cm.xb >= 0) ? real(1) / msqrt(bmass[cm.xb]) : cm.xb_dsqi[0];   // the extra free body's mass acts at once, like every body_mass entry
   DECL_LANE
   const int csync = E.cta_sync;   // bit k: rendezvous k of the sub-step is on (set by the kernel wrapper for multi-tick step launches only)
   STAGE_SYNC(csync & 1);
-  const int nv = cm.nv, nb = cm.nbody, ys = cm.ystride, xb = cm.xb;   // nv: dofs of the main tree (one per lane); xb: extra free body or -1
+  // nv: dofs of the main tree (one per lane); xb: extra free body or -1.  An instance compiled without the extra-body feature sees xb = -1 and the
+  // narrow row stride as constants: every `xb >= 0` branch below and the stride arithmetic fold away
+  const int nv = cm.nv, nb = cm.nbody, ys = (FEAT & F_XB) ? cm.ystride : YSTRIDE_MAIN, xb = (FEAT & F_XB) ? cm.xb : -1;
   real *xpos = sm + S_XPOS, *xquat = sm + S_XQUAT, *xmat = sm + S_XMAT, *cdof = sm + S_CDOF;
   real *qpos = sm + S_QPOS, *qM = E.qM, *qLD = sm + S_QLD, *Y = sm + S_Y, *efc = sm + S_EFC, *con = sm + S_CON;
   real *qLD2 = sm + S_Y + T_CVEL;   // second matrix of the fused factorisation: the velocity-stage temporaries are not live yet
@@ -891,7 +893,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           }
         }
         if (kind == PAIR_PLANE_CAPSULE) { L(ch0) = a2[0]; L(ch1) = a2[1]; L(ch2) = a2[2]; }
-      } else if (kind == PAIR_HFIELD_SPHERE || kind == PAIR_HFIELD_CAPSULE) {
+      } else if ((FEAT & F_HFIELD) && (kind == PAIR_HFIELD_SPHERE || kind == PAIR_HFIELD_CAPSULE)) {
         const real r = cm.geom_size[g2][0], hl = (kind == PAIR_HFIELD_CAPSULE) ? cm.geom_size[g2][1] : real(0);
         const int ne = (kind == PAIR_HFIELD_CAPSULE) ? 2 : 1;
         if (E.hfield) for (int e = 0; e < ne; ++e) {
@@ -904,10 +906,10 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           }
         }
         if (kind == PAIR_HFIELD_CAPSULE) { L(ch0) = a2[0]; L(ch1) = a2[1]; L(ch2) = a2[2]; }
-      } else if (kind >= PAIR_PLANE_BOX) {
+      } else if ((FEAT & F_BOX) && kind >= PAIR_PLANE_BOX) {
         n = box_pair(kind, margin, p1, p2, cm.geom_size[g1], cm.geom_size[g2], cp, cn, cdst);
         if (kind == PAIR_CAPSULE_BOX && n) { L(ch0) = a1[0]; L(ch1) = a1[1]; L(ch2) = a1[2]; }
-      } else {  // capsule - capsule
+      } else if (kind == PAIR_CAPSULE_CAPSULE) {
         const real s1 = cm.geom_size[g1][1], s2 = cm.geom_size[g2][1], r1 = cm.geom_size[g1][0], r2 = cm.geom_size[g2][0];
         real dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
         const real ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif), det = ma * mc - mb * mb;
@@ -1619,7 +1621,7 @@ template <typename real> CFN real core_hi_deg(int i) { const real t[10] = {20, 2
 template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 1200, 1200, 100}; return t[k]; }
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
-template <typename real, bool DR>
+template <typename real, bool DR, int FEAT>
 CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), int nticks, int mode) {
   const bool forward_only = (mode != 0);
   DECL_LANE
@@ -1769,7 +1771,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
     const int nsub = forward_only ? 1 : (E.nsub > 0 ? E.nsub : cm.nsub);
-    for (int s = 0; s < nsub; ++s) mj_substep<real, DR>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, (tick == nticks - 1 && s == nsub - 1) ? E.aux : (real *)0, mode);
+    for (int s = 0; s < nsub; ++s) mj_substep<real, DR, FEAT>(cm, sm, E, qvel, qacc_ws, xqvel, xqacc_ws, ctrl, (tick == nticks - 1 && s == nsub - 1) ? E.dbg : (real *)0, (tick == nticks - 1 && s == nsub - 1) ? E.aux : (real *)0, mode);
   }
   if (!forward_only) { LANES if (l == 0) ism[DF_TICK] = tick0 + nticks; ENDL }
 }

@@ -77,8 +77,8 @@ cassie_sim_t *cassie_sim_duplicate(const cassie_sim_t *src);
 void cassie_sim_copy(cassie_sim_t *dst, const cassie_sim_t *src);
 /* include/cassiemujoco.h:434-463 (src/cassiemujoco.c:3380-3452): full dynamic state of a simulator -- qpos, qvel, warm start, time, sensor snapshot,
  * cassie_out subset, encoder filters, torque delay line, applied forces, estimator filters, last observation row.  The borrowed time / qpos / qvel
- * pointers are host mirrors: what the caller writes there after cassie_get_state is honoured by cassie_set_state.  A state is bound to the
- * simulator (or one of the same model) it was taken from and must be freed before that simulator. */
+ * pointers are host mirrors: what the caller writes there after cassie_get_state is honoured by cassie_set_state.  A state owns its (device)
+ * memory: it can be restored into any simulator of the same model and freed at any time, before or after the simulator it was taken from. */
 cassie_state_t *cassie_state_alloc(void);
 cassie_state_t *cassie_state_duplicate(const cassie_state_t *src);
 void cassie_state_copy(cassie_state_t *dst, const cassie_state_t *src);

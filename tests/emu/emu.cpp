@@ -30,7 +30,7 @@ template <typename real> struct Emu {
     forward();
     return true;
   }
-  void run(int nticks, int mode) { if (use_cenv || use_ext) step_env<real, true>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); else step_env<real, false>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); }
+  void run(int nticks, int mode) { if (use_cenv || use_ext) step_env<real, true, F_ALL>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); else step_env<real, false, F_ALL>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); }
   void forward() { run(1, 1); }
   // per-environment model constants + mj_setConst (mode 3 works at the reference configuration, like the kernel wrapper does)
   void enable_cenv() { if (!use_cenv) { init_cenv_row(dm, cenv); use_cenv = true; } }
