@@ -267,7 +267,8 @@ class Workload:
     def make_copy(self, k):
         P, n = self.P, self.n
         b = P.CassieBatch(n, modelfile=P.model_path(self.cfg['model']), device=self.device, precision=P.FP32)
-        b.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        if self.torch is not None:
+            b.set_stream(self.torch.cuda.current_stream().cuda_stream)
         if self.terrains is not None:
             b.set_hfield_data(self.terrains)
         q0 = b.qpos()[0]

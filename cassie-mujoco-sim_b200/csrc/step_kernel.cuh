@@ -11,7 +11,7 @@
 namespace cassie {
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync, nsub, warp_stride, warp_tickets; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync, nsub, warp_stride; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -46,25 +46,28 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   real *sm = reinterpret_cast<real *>(smem_raw + model_bytes<real>() + warp * A.warp_stride);   // warp_stride = warp_bytes(ystride, instance), precomputed on the host: cheap to rematerialise under register pressure
   const int qw = (FEAT & F_XB) ? A.qpos_w : QPOS_W_MAIN, vw = (FEAT & F_XB) ? A.qvel_w : QVEL_W_MAIN;
   const DevModel<real> &cm = *cmp;
-  // persistent CTAs: a CTA draws one environment per warp from a global ticket counter until the batch is exhausted; its warps walk the
-  // stages together (STAGE_SYNC) so that they share instruction-cache lines -- the kernel is ~250 KB of code, eight times the L1.5
-  __shared__ int cta_base;
-  const int nwarps = blockDim.x >> 5, sync_on = (mode == 0 && nticks > 1) ? A.cta_sync : 0;   // a single tick starts in step and stays close enough
-  const bool warp_tickets = A.warp_tickets && !sync_on;   // uniform over the grid
-  for (;;) {
-    int env;
-    if (warp_tickets) {   // every warp draws its own environment: no CTA-wide rendezvous per round, nobody waits for the CTA's slowest environment
-      int t = 0; if (l == 0) t = atomicAdd(A.ticket, 1);
-      env = __shfl_sync(0xffffffffu, t, 0);
-      if (env >= A.n) break;
-    } else {
-      __syncthreads();
-      if (threadIdx.x == 0) cta_base = atomicAdd(A.ticket, nwarps);
-      __syncthreads();
-      const int base = cta_base;
-      if (base >= A.n) break;
-      env = base + warp;
-    }
+  // persistent CTAs with a static round-robin schedule: in round r CTA b owns environments [(r gridDim + b) nwarps, ... + nwarps), one per warp.  The
+  // grid is sized to the resident CTAs, the environments cost about the same, and a static schedule lets every warp pull the rows of its NEXT
+  // environment towards L2 while it steps the current one.  (Multi-tick launches: the CTA's warps walk the stages together, STAGE_SYNC, so that
+  // they share instruction-cache lines -- the kernel is ~200 KB of code, several times the L1.5.)
+  const int nwarps = blockDim.x >> 5, sync_on = (mode == 0 && (nticks > 1 || (A.cta_sync & 32))) ? (A.cta_sync & 31) : 0;   // bit 5: also in single-tick launches
+  const int stride = gridDim.x * nwarps;
+  for (int base = blockIdx.x * nwarps; base < A.n; base += stride) {
+    const int env = base + warp;
+    __syncthreads();   // the warps of a CTA start every round together: they then share instruction-cache lines through the round (measured: 16 384
+                       // environments, 7 rounds, -20 % without it), and the multi-tick rendezvous counts below assume it
+    { const int nenv = env + stride;   // warm L2 with the next round's state rows of this warp (about 2 KB per environment, one 128-byte line per lane)
+      if (nenv < A.n && mode == 0) {
+        const char *p = nullptr;
+        if (l < 6) p = (const char *)(A.cst + (size_t)nenv * CST_W) + 128 * l * (sizeof(real) / 4);
+        else if (l < 9) p = (const char *)(A.dfilt + (size_t)nenv * DFILT_W) + 128 * (l - 6);
+        else if (l < 11) p = (const char *)(A.pd + (size_t)nenv * PD_W) + 128 * (l - 9) * (sizeof(real) / 4);
+        else if (l < 13) p = (const char *)(A.qpos + (size_t)nenv * qw) + 128 * (l - 11) * (sizeof(real) / 4);
+        else if (l < 15) p = (const char *)(A.qvel + (size_t)nenv * vw) + 128 * (l - 13) * (sizeof(real) / 4);
+        else if (l < 17) p = (const char *)(A.qacc_ws + (size_t)nenv * vw) + 128 * (l - 15) * (sizeof(real) / 4);
+        else if (l == 17) p = (const char *)(A.xfrc + (size_t)nenv * XFRC_W);
+        if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      } }
     const bool active = env < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
     if (!active) {   // keep the rendezvous count of the working warps
       if (sync_on) { const int per = __popc(sync_on); for (int i = 0; i < nticks * (A.nsub > 0 ? A.nsub : cm.nsub) * per; ++i) __syncthreads(); }
