@@ -22,7 +22,7 @@
 
 // the step-kernel instances live in their own translation units (step_inst.cu, one compilation per instance)
 #define CASSIE_STEP_ENTRY(tag) extern "C" const void *cassie_step_entry_##tag(void);
-CASSIE_STEP_ENTRY(f00) CASSIE_STEP_ENTRY(f10) CASSIE_STEP_ENTRY(f02) CASSIE_STEP_ENTRY(f12) CASSIE_STEP_ENTRY(f05) CASSIE_STEP_ENTRY(f15) CASSIE_STEP_ENTRY(f07) CASSIE_STEP_ENTRY(f17)
+CASSIE_STEP_ENTRY(f00) CASSIE_STEP_ENTRY(f10) CASSIE_STEP_ENTRY(f02) CASSIE_STEP_ENTRY(f12) CASSIE_STEP_ENTRY(f04) CASSIE_STEP_ENTRY(f14) CASSIE_STEP_ENTRY(f05) CASSIE_STEP_ENTRY(f15) CASSIE_STEP_ENTRY(f07) CASSIE_STEP_ENTRY(f17)
 CASSIE_STEP_ENTRY(d07) CASSIE_STEP_ENTRY(d17)
 #undef CASSIE_STEP_ENTRY
 
@@ -31,12 +31,13 @@ namespace cassie {
 // the instance for (precision, plain / extended, model features): the smallest compiled feature set that covers the model's
 template <typename real> static const void *step_entry(bool ext, int feat, int *compiled_feat = nullptr) {
   int f = F_ALL;
-  if (!std::is_same<real, double>::value) { if (feat == 0) f = 0; else if (feat == F_HFIELD) f = F_HFIELD; else if ((feat & ~(F_XB | F_BOX)) == 0) f = F_XB | F_BOX; }
+  if (!std::is_same<real, double>::value) { if (feat == 0) f = 0; else if (feat == F_HFIELD) f = F_HFIELD; else if (feat == F_BOX) f = F_BOX; else if ((feat & ~(F_XB | F_BOX)) == 0) f = F_XB | F_BOX; }
   if (compiled_feat) *compiled_feat = f;
   if (std::is_same<real, double>::value) return ext ? cassie_step_entry_d17() : cassie_step_entry_d07();
   switch (f) {
     case 0: return ext ? cassie_step_entry_f10() : cassie_step_entry_f00();
     case F_HFIELD: return ext ? cassie_step_entry_f12() : cassie_step_entry_f02();
+    case F_BOX: return ext ? cassie_step_entry_f14() : cassie_step_entry_f04();
     case F_XB | F_BOX: return ext ? cassie_step_entry_f15() : cassie_step_entry_f05();
     default: return ext ? cassie_step_entry_f17() : cassie_step_entry_f07();
   }
@@ -244,7 +245,7 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemcpy(d_model, hmodel, model_bytes<real>(), cudaMemcpyHostToDevice));
     h_model_copy = *hmodel; memcpy(geom_dev, info.geom_dev, sizeof geom_dev);
     feat = hmodel->xb >= 0 ? F_XB : 0;   // which kernel instance this model needs (step_inst.cu)
-    for (int p = 0; p < hmodel->npair; p++) { const int k = hmodel->pair_kind[p]; if (k == PAIR_HFIELD_SPHERE || k == PAIR_HFIELD_CAPSULE) feat |= F_HFIELD; else if (k >= PAIR_PLANE_BOX) feat |= F_BOX; }
+    for (int p = 0; p < hmodel->npair; p++) { const int k = pair_kind(hmodel->pair_code[p]); if (k == PAIR_HFIELD_SPHERE || k == PAIR_HFIELD_CAPSULE) feat |= F_HFIELD; else if (k >= PAIR_PLANE_BOX) feat |= F_BOX; }
     const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
     A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; { const char *e = getenv("CASSIE_B200_SYNCMASK"); A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : (e ? (atoi(e) & 63) : 10); }   // which of the five per-sub-step rendezvous are on
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
@@ -680,7 +681,8 @@ template <typename real> struct Batch : BatchBase {
 using namespace cassie;
 struct cassie_batch { BatchBase *impl; std::vector<double> obs, radio; };
 struct cassie_sim { cassie_batch *b; double qpos[64], qvel[64], time, qpos_dev[64], qvel_dev[64], time_dev, aux[AUX_W]; std::vector<float> hfield, hfield_dev; std::string path; double timestep = 0, timestep_dev = 0;
-  std::vector<double> m_mass, m_ipos, m_damp, m_fric, m_mass_dev, m_ipos_dev, m_damp_dev, m_fric_dev; };   // host mirrors of the model arrays handed out as borrowed pointers
+  std::vector<double> m_mass, m_ipos, m_damp, m_fric, m_mass_dev, m_ipos_dev, m_damp_dev, m_fric_dev;
+  std::vector<double> m_gpos, m_gquat, m_gsize, m_gpos_dev, m_gquat_dev, m_gsize_dev; };   // geom placement (stair boxes): host mirrors, the constant block is rebuilt when they change   // host mirrors of the model arrays handed out as borrowed pointers
 
 // cassie_state_t (include/cassiemujoco.h:434-463): a device-resident snapshot of one simulator's rows plus the host mirrors the reference hands out as
 // borrowed pointers (time, qpos, qvel); the snapshot is allocated by the first cassie_get_state, which also fixes the owning simulator's sizes
@@ -805,6 +807,9 @@ static void sim_push(cassie_sim_t *c) {  // upload whatever the caller wrote thr
   if (c->m_ipos != c->m_ipos_dev) { cassie_batch_set_body_ipos(c->b, c->m_ipos.data()); c->m_ipos_dev = c->m_ipos; }
   if (c->m_damp != c->m_damp_dev) { cassie_batch_set_dof_damping(c->b, c->m_damp.data()); c->m_damp_dev = c->m_damp; }
   if (c->m_fric != c->m_fric_dev) { cassie_batch_set_geom_friction(c->b, c->m_fric.data()); c->m_fric_dev = c->m_fric; }
+  if (c->m_gpos != c->m_gpos_dev || c->m_gquat != c->m_gquat_dev || c->m_gsize != c->m_gsize_dev) {   // a geom was moved / turned / resized (src/cassiemujoco.c:1438-1541)
+    HostModel &hm = c->b->impl->hm; hm.geom_pos = c->m_gpos; hm.geom_quat = c->m_gquat; hm.geom_size = c->m_gsize;
+    c->b->impl->rebuild_model(); c->m_gpos_dev = c->m_gpos; c->m_gquat_dev = c->m_gquat; c->m_gsize_dev = c->m_gsize; }
 }
 cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   std::string path;
@@ -816,7 +821,8 @@ cassie_sim_t *cassie_sim_init(const char *modelfile, bool reinit) {
   b->impl->enable_estimator_device(true);   // ... and the estimator (toe / heel forces, filters) inside the kernel, as state_output_step runs in every cassie_sim_step_pd (src/cassiemujoco.c:1156)
   sim_pull(c);
   { const HostModel &hm = b->impl->hm; c->m_mass = hm.body_mass; c->m_ipos = hm.body_ipos; c->m_damp = hm.dof_damping; c->m_fric = hm.geom_friction;
-    c->m_mass_dev = c->m_mass; c->m_ipos_dev = c->m_ipos; c->m_damp_dev = c->m_damp; c->m_fric_dev = c->m_fric; }
+    c->m_mass_dev = c->m_mass; c->m_ipos_dev = c->m_ipos; c->m_damp_dev = c->m_damp; c->m_fric_dev = c->m_fric;
+    c->m_gpos = hm.geom_pos; c->m_gquat = hm.geom_quat; c->m_gsize = hm.geom_size; c->m_gpos_dev = c->m_gpos; c->m_gquat_dev = c->m_gquat; c->m_gsize_dev = c->m_gsize; }
   if (b->impl->hm.nhfield) { c->hfield.assign((size_t)b->impl->hm.hfield_nrow[0] * b->impl->hm.hfield_ncol[0], 0.0f); c->hfield_dev = c->hfield; }
   return c;
 }
@@ -897,6 +903,30 @@ int cassie_sim_nu(const cassie_sim_t *c) { return c->b->impl->hm.nu; }
 // src/cassiemujoco.c:1183-1189: qpos += h * qvel on the joint manifold; the reference then feeds an uninitialised cassie_out_t to its estimator,
 // so *y carries no information there -- it is zeroed here
 void cassie_integrate_pos(cassie_sim_t *c, state_out_t *y) { sim_push(c); cassie_batch_integrate_pos(c->b); c->b->impl->sync(); sim_pull(c); if (y) memset(y, 0, sizeof *y); }
+
+// ---- geom placement (src/cassiemujoco.c:1466-1541; example/test_terrain.c:118-157 moves the stair boxes with these): borrowed pointers into host
+// mirrors in the reference's geom numbering; the constant block is rebuilt before the next launch.  As in MuJoCo a new size leaves geom_rbound alone.
+double *cassie_sim_geom_pos(cassie_sim_t *c) { return c->m_gpos.data(); }
+double *cassie_sim_geom_quat(cassie_sim_t *c) { return c->m_gquat.data(); }
+double *cassie_sim_geom_size(cassie_sim_t *c) { return c->m_gsize.data(); }
+double *cassie_sim_geom_name_pos(cassie_sim_t *c, const char *name) { const int g = c->b->impl->hm.geom_id(name ? name : ""); return g >= 0 ? &c->m_gpos[3 * g] : nullptr; }
+double *cassie_sim_geom_name_quat(cassie_sim_t *c, const char *name) { const int g = c->b->impl->hm.geom_id(name ? name : ""); return g >= 0 ? &c->m_gquat[4 * g] : nullptr; }
+double *cassie_sim_geom_name_size(cassie_sim_t *c, const char *name) { const int g = c->b->impl->hm.geom_id(name ? name : ""); return g >= 0 ? &c->m_gsize[3 * g] : nullptr; }
+void cassie_sim_set_geom_pos(cassie_sim_t *c, double *pos) { for (size_t i = 0; i < c->m_gpos.size(); i++) c->m_gpos[i] = pos[i]; }
+void cassie_sim_set_geom_quat(cassie_sim_t *c, double *quat) { for (size_t i = 0; i < c->m_gquat.size(); i++) c->m_gquat[i] = quat[i]; }
+void cassie_sim_set_geom_size(cassie_sim_t *c, double *size) { for (size_t i = 0; i < c->m_gsize.size(); i++) c->m_gsize[i] = size[i]; }
+void cassie_sim_set_geom_name_pos(cassie_sim_t *c, const char *name, double *pos) { double *p = cassie_sim_geom_name_pos(c, name); if (p) for (int k = 0; k < 3; k++) p[k] = pos[k]; }
+void cassie_sim_set_geom_name_quat(cassie_sim_t *c, const char *name, double *quat) { double *p = cassie_sim_geom_name_quat(c, name); if (p) for (int k = 0; k < 4; k++) p[k] = quat[k]; }
+void cassie_sim_set_geom_name_size(cassie_sim_t *c, const char *name, double *size) { double *p = cassie_sim_geom_name_size(c, name); if (p) for (int k = 0; k < 3; k++) p[k] = size[k]; }
+// the same for a batch: one placement shared by all its environments (pos / quat / size: NULL leaves that part alone); 0 / -1 (unknown geom)
+int cassie_batch_set_geom_pose(cassie_batch_t *b, const char *name, const double *pos, const double *quat, const double *size) {
+  HostModel &hm = b->impl->hm; const int g = hm.geom_id(name ? name : "");
+  if (g < 0) { set_err("cassie_batch_set_geom_pose: unknown geom"); return -1; }
+  if (pos) for (int k = 0; k < 3; k++) hm.geom_pos[3 * g + k] = pos[k];
+  if (quat) for (int k = 0; k < 4; k++) hm.geom_quat[4 * g + k] = quat[k];
+  if (size) for (int k = 0; k < 3; k++) hm.geom_size[3 * g + k] = size[k];
+  return b->impl->rebuild_model() ? 0 : -1;
+}
 
 // ---- legacy verbs RL wrappers call around cassie_sim_step_pd (src/cassiemujoco.c:1072-1093, 1137-1145, 1159-1181, 1196-1225, 1974-2000, 2086-2092, 3380-3452)
 // the dynamic subset of cassie_out_t from an observation row, the rest as cassie_out_init leaves it (:672-734)
@@ -989,6 +1019,7 @@ void cassie_sim_copy(cassie_sim_t *dst, const cassie_sim_t *csrc) {
   if (!dst->b->impl->copy_model_from(src->b->impl)) return;
   dst->m_mass = src->m_mass; dst->m_ipos = src->m_ipos; dst->m_damp = src->m_damp; dst->m_fric = src->m_fric;
   dst->m_mass_dev = dst->m_mass; dst->m_ipos_dev = dst->m_ipos; dst->m_damp_dev = dst->m_damp; dst->m_fric_dev = dst->m_fric;
+  dst->m_gpos = dst->m_gpos_dev = src->m_gpos; dst->m_gquat = dst->m_gquat_dev = src->m_gquat; dst->m_gsize = dst->m_gsize_dev = src->m_gsize;
   dst->hfield = src->hfield; dst->hfield_dev = src->hfield_dev; dst->timestep = dst->timestep_dev = src->timestep;
   for (int i = 0; i < 16; i++) dst->b->radio[i] = src->b->radio[i];
   cassie_state_t *s = cassie_state_alloc(); cassie_get_state(src, s); cassie_set_state(dst, s); cassie_state_free(s);

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <vector>
 #include "devmodel.h"
 #include "model.h"
 
@@ -151,15 +152,43 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     for (int k = 0; k < 2; k++) d.eq_solref[e][k] = (real)m.eq_solref[2 * e + k];
     for (int k = 0; k < 5; k++) d.eq_solimp[e][k] = (real)m.eq_solimp[5 * e + k];
   }
-  // candidate pairs in MuJoCo's order: body pairs ascending, geoms in id order; then type-sorted
+  // candidate pairs in MuJoCo's order: body pairs ascending, geoms in id order; then type-sorted.  Collision geoms get device ids: on moving
+  // bodies 0 .. MG-1 (world pose recomputed every step), static ones (world body and bodies welded to it) MG .. MG+MGS-1 with their world pose here
   int gmap[256]; for (int g = 0; g < 256; g++) gmap[g] = -1;
+  int n_dyn = 0, n_stat = 0, n_pc = 0;
+  std::vector<double> reach(m.nbody, 0.0);   // bound on the distance of a body's origin from the root body's origin, whatever the joint angles
+  { int root = -1; for (int b = 1; b < m.nbody; b++) if (m.body_weldid[b] != 0 && b != xb) { root = b; break; }
+    d.root_body = root < 0 ? 0 : root;
+    for (int b = 1; b < m.nbody; b++) if (m.body_weldid[b] != 0 && b != d.root_body && b != xb) {
+      const double *bp = &m.body_pos[3 * b]; reach[b] = reach[m.body_parentid[b]] + std::sqrt(bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]); } }
+  double robot_reach = 0;
   auto dev_geom = [&](int g) -> int {
     if (gmap[g] >= 0) return gmap[g];
-    if (d.ngeom >= MG) return -1;
-    int k = d.ngeom++; gmap[g] = k; d.geom_body[k] = m.geom_bodyid[g]; d.geom_type[k] = m.geom_type[g];
+    const int b = m.geom_bodyid[g]; const bool stat = m.body_weldid[b] == 0;
+    if ((stat && n_stat >= MGS) || (!stat && n_dyn >= MG)) return -1;
+    const int k = stat ? MG + n_stat++ : n_dyn++; gmap[g] = k; d.geom_body[k] = b; d.geom_type[k] = m.geom_type[g];
     double R[9]; detail::q2m_d(R, &m.geom_quat[4 * g]);
-    for (int c = 0; c < 3; c++) { d.geom_pos[k][c] = (real)m.geom_pos[3 * g + c]; d.geom_size[k][c] = (real)m.geom_size[3 * g + c]; }
-    for (int c = 0; c < 9; c++) d.geom_mat[k][c] = (real)R[c];
+    for (int c = 0; c < 3; c++) d.geom_size[k][c] = (real)m.geom_size[3 * g + c];
+    d.geom_rbound[k] = (real)m.geom_rbound[g]; d.geom_fric[k] = (real)m.geom_friction[3 * g];
+    if (!stat) {
+      for (int c = 0; c < 3; c++) d.geom_pos[k][c] = (real)m.geom_pos[3 * g + c];
+      for (int c = 0; c < 9; c++) d.geom_mat[k][c] = (real)R[c];
+      if (b != xb) { const double *gp = &m.geom_pos[3 * g]; robot_reach = std::max(robot_reach, reach[b] + std::sqrt(gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2]) + m.geom_rbound[g]); }
+    } else {   // world pose: compose the (constant) chain of static bodies
+      double bp[3] = {0, 0, 0}, bq[4] = {1, 0, 0, 0};
+      { std::vector<int> chain; for (int bb = b; bb > 0; bb = m.body_parentid[bb]) chain.push_back(bb);
+        for (int i = (int)chain.size() - 1; i >= 0; i--) { const int bb = chain[i]; double Rb[9], v[3]; detail::q2m_d(Rb, bq);
+          for (int r = 0; r < 3; r++) v[r] = Rb[3 * r] * m.body_pos[3 * bb] + Rb[3 * r + 1] * m.body_pos[3 * bb + 1] + Rb[3 * r + 2] * m.body_pos[3 * bb + 2];
+          for (int r = 0; r < 3; r++) bp[r] += v[r];
+          const double *q2 = &m.body_quat[4 * bb]; const double t[4] = {bq[0] * q2[0] - bq[1] * q2[1] - bq[2] * q2[2] - bq[3] * q2[3], bq[0] * q2[1] + bq[1] * q2[0] + bq[2] * q2[3] - bq[3] * q2[2],
+                                                                        bq[0] * q2[2] - bq[1] * q2[3] + bq[2] * q2[0] + bq[3] * q2[1], bq[0] * q2[3] + bq[1] * q2[2] - bq[2] * q2[1] + bq[3] * q2[0]};
+          for (int r = 0; r < 4; r++) bq[r] = t[r]; } }
+      double Rb[9], W[9], wp[3]; detail::q2m_d(Rb, bq);
+      for (int r = 0; r < 3; r++) { wp[r] = bp[r] + Rb[3 * r] * m.geom_pos[3 * g] + Rb[3 * r + 1] * m.geom_pos[3 * g + 1] + Rb[3 * r + 2] * m.geom_pos[3 * g + 2];
+        for (int c = 0; c < 3; c++) W[3 * r + c] = Rb[3 * r] * R[c] + Rb[3 * r + 1] * R[3 + c] + Rb[3 * r + 2] * R[6 + c]; }
+      real *w = d.geom_wpose[k - MG];
+      for (int r = 0; r < 3; r++) { w[r] = (real)wp[r]; w[3 + r] = (real)W[3 * r + 2]; w[6 + r] = (real)W[3 * r]; w[9 + r] = (real)W[3 * r + 1]; }   // position, z, x, y axes
+    }
     return k;
   };
   int unsupported = 0;
@@ -171,8 +200,6 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       int g1 = ga, g2 = gb; if (m.geom_type[g1] > m.geom_type[g2]) std::swap(g1, g2);
       if (!((m.geom_contype[g1] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g1]))) continue;
       int t1 = m.geom_type[g1], t2 = m.geom_type[g2], kind;
-      { int gw = m.geom_bodyid[g1] == 0 ? g1 : (m.geom_bodyid[g2] == 0 ? g2 : -1);   // the 15 stair boxes of cassie.xml are parked 20 m away: not collided
-        if (gw >= 0 && m.geom_type[gw] == GEOM_BOX && std::fabs(m.geom_pos[3 * gw + 1]) > 10.0) { unsupported++; continue; } }
       if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) kind = PAIR_PLANE_SPHERE;
       else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) kind = PAIR_PLANE_CAPSULE;
       else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) kind = PAIR_CAPSULE_CAPSULE;
@@ -183,17 +210,16 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) kind = PAIR_CAPSULE_BOX;
       else if (t1 == GEOM_BOX && t2 == GEOM_BOX) kind = PAIR_BOX_BOX;
       else { unsupported++; continue; }
-      if (d.npair >= MP) { err = "too many candidate geom pairs"; return false; }
+      if (d.npair >= MPAIR) { err = "too many candidate geom pairs"; return false; }
       if (t1 == GEOM_HFIELD) { const double *q = &m.geom_quat[4 * g1], *bq = &m.body_quat[4 * m.geom_bodyid[g1]];
         if (std::fabs(q[0]) < 1 - 1e-12 || std::fabs(bq[0]) < 1 - 1e-12 || m.body_weldid[m.geom_bodyid[g1]] != 0) { err = "the height field must be axis aligned and static"; return false; } }
-      int k1 = dev_geom(g1), k2 = dev_geom(g2); if (k1 < 0 || k2 < 0) { err = "too many collision geoms"; return false; }
-      int p = d.npair++; d.pair_g1[p] = k1; d.pair_g2[p] = k2; d.pair_kind[p] = kind;
-      { const int u1 = m.geom_user[g1], u2 = m.geom_user[g2], r1 = m.geom_group[g1], r2 = m.geom_group[g2]; int fl = 0;
+      int k1 = dev_geom(g1), k2 = dev_geom(g2); if (k1 < 0 || k2 < 0) { err = "too many collision geoms (16 on moving bodies, 16 static)"; return false; }
+      int fl = 0;
+      { const int u1 = m.geom_user[g1], u2 = m.geom_user[g2], r1 = m.geom_group[g1], r2 = m.geom_group[g2];
         if (u1 == 1 || u2 == 1) fl |= 1;
         if (u1 == 2 && u2 == 2) fl |= 2;
         if (r1 == 1 && r2 >= 0 && r2 < 16) fl |= 256 << r2;
-        if (r2 == 1 && r1 >= 0 && r1 < 16) fl |= 256 << r1;
-        d.pair_flags[p] = fl; }
+        if (r2 == 1 && r1 >= 0 && r1 < 16) fl |= 256 << r1; }
       // contact parameter mixing (mj_contactParam)
       double fr, solref[2], solimp[5]; int dim;
       if (m.geom_priority[g1] != m.geom_priority[g2]) {
@@ -208,14 +234,26 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
         for (int k = 0; k < 5; k++) solimp[k] = mix * m.geom_solimp[5 * g1 + k] + (1 - mix) * m.geom_solimp[5 * g2 + k];
       }
       if (dim != 1 && dim != 3) { err = "only condim 1 and 3 contacts are supported"; return false; }
-      d.pair_condim[p] = dim; d.pair_mu[p] = (real)(fr / std::sqrt(m.impratio));
-      d.pair_mu_src[p] = m.geom_priority[g1] == m.geom_priority[g2] ? 0 : (m.geom_priority[g1] > m.geom_priority[g2] ? 1 : 2);
-      d.geom_fric[k1] = (real)m.geom_friction[3 * g1]; d.geom_fric[k2] = (real)m.geom_friction[3 * g2];
-      d.pair_margin[p] = (real)std::max(m.geom_margin[g1], m.geom_margin[g2]); d.pair_gap[p] = (real)std::max(m.geom_gap[g1], m.geom_gap[g2]);
-      for (int k = 0; k < 2; k++) d.pair_solref[p][k] = (real)solref[k];
-      for (int k = 0; k < 5; k++) d.pair_solimp[p][k] = (real)solimp[k];
+      // the pair's parameter record: shared with every pair that mixes to the same values (all 135 box x robot pairs of cassie.xml share one)
+      const real mu = (real)(fr / std::sqrt(m.impratio)), mg = (real)std::max(m.geom_margin[g1], m.geom_margin[g2]), gp = (real)std::max(m.geom_gap[g1], m.geom_gap[g2]);
+      const int msrc = m.geom_priority[g1] == m.geom_priority[g2] ? 0 : (m.geom_priority[g1] > m.geom_priority[g2] ? 1 : 2);
+      int pc = -1;
+      for (int c = 0; c < n_pc && pc < 0; c++) {
+        bool same = d.pc_condim[c] == dim && d.pc_mu_src[c] == msrc && d.pc_flags[c] == fl && d.pc_mu[c] == mu && d.pc_margin[c] == mg && d.pc_gap[c] == gp;
+        for (int k = 0; k < 2; k++) same = same && d.pc_solref[c][k] == (real)solref[k];
+        for (int k = 0; k < 5; k++) same = same && d.pc_solimp[c][k] == (real)solimp[k];
+        if (same) pc = c;
+      }
+      if (pc < 0) {
+        if (n_pc >= NPC) { err = "too many distinct contact-parameter records"; return false; }
+        pc = n_pc++; d.pc_condim[pc] = dim; d.pc_mu_src[pc] = msrc; d.pc_flags[pc] = fl; d.pc_mu[pc] = mu; d.pc_margin[pc] = mg; d.pc_gap[pc] = gp;
+        for (int k = 0; k < 2; k++) d.pc_solref[pc][k] = (real)solref[k];
+        for (int k = 0; k < 5; k++) d.pc_solimp[pc][k] = (real)solimp[k];
+      }
+      d.pair_code[d.npair++] = (uint32_t)k1 | ((uint32_t)k2 << 6) | ((uint32_t)kind << 12) | ((uint32_t)pc << 16);
     }
   }
+  d.ngeom = n_dyn; d.ngeom_static = n_stat; d.robot_reach = (real)(robot_reach * 1.05 + 0.05);
   // mirror symmetry of the dof tree: a base chain 0..f-1, then two blocks of n dofs with identical relative structure hanging off dof f-1
   d.sym_on = 0;
   { const int nv2 = d.nv;
@@ -246,7 +284,7 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       for (int k = 0; k < 3; k++) { d.toe_local[s][k] = (real)(m.geom_pos[3 * g + k] + R[3 * k + 2] * m.geom_size[3 * g + 1]); d.heel_local[s][k] = (real)(m.geom_pos[3 * g + k] - R[3 * k + 2] * m.geom_size[3 * g + 1]); }
     }
   }
-  if (info) { info->unsupported_pairs = unsupported; info->collision_geoms = d.ngeom; for (int g = 0; g < 256; g++) info->geom_dev[g] = gmap[g]; }
+  if (info) { info->unsupported_pairs = unsupported; info->collision_geoms = d.ngeom + d.ngeom_static; for (int g = 0; g < 256; g++) info->geom_dev[g] = gmap[g]; }
   return true;
 }
 
@@ -268,7 +306,7 @@ void init_cenv_row(const DevModel<real> &d, real *row) {
   for (int i = 0; i < CE_W; i++) row[i] = 0;
   for (int b = 0; b < d.nbody; b++) { row[CE_MASS + b] = d.body_mass[b]; for (int k = 0; k < 3; k++) row[CE_IPOS + 3 * b + k] = d.body_ipos[b][k]; row[CE_BINVW + b] = d.body_invw[b]; }
   for (int i = 0; i < d.nv; i++) { row[CE_DAMP + i] = d.dof_damping[i]; row[CE_DINVW + i] = d.dof_invweight0[i]; }
-  for (int g = 0; g < d.ngeom; g++) row[CE_FRIC + g] = d.geom_fric[g];
+  for (int g = 0; g < MGT; g++) row[CE_FRIC + g] = d.geom_fric[g];
   row[CE_ROOT_MINV] = d.root_mass_inv; row[CE_TOT_MINV] = d.total_mass_inv; row[CE_PGS_SCALE] = d.pgs_scale;
 }
 

@@ -14,8 +14,11 @@ namespace cassie {
 constexpr int MB = 32;        // bodies (nbody <= 32: one lane per body)
 constexpr int MJ = 32;        // joints
 constexpr int MV = 32;        // dofs   (nv <= 32: one lane per dof)
-constexpr int MG = 16;        // collision geoms
-constexpr int MP = 32;        // candidate geom pairs (one lane per pair)
+constexpr int MG = 16;        // collision geoms on moving bodies (world pose recomputed every step)
+constexpr int MGS = 16;       // static collision geoms (world body or bodies welded to it: floor plane, height field, the 15 stair boxes of cassie.xml): device ids MG .. MG + MGS - 1
+constexpr int MGT = MG + MGS;
+constexpr int MPAIR = 192;    // candidate geom pairs in MuJoCo's order (cassie.xml: 9 floor + 9 x 15 box + 9 leg-leg = 153), 32 per collision pass
+constexpr int NPC = 8;        // distinct contact-parameter records among the pairs (mj_contactParam results)
 constexpr int ME = 4;         // connect equalities
 constexpr int MU = 10;        // motors
 constexpr int NM_MAX = 320;   // sparse mass-matrix entries (307 for Cassie)
@@ -28,6 +31,11 @@ constexpr int YSTRIDE_MAX = 39;   // with the 6 dofs of an extra free body (cass
 
 // model features a kernel instance is compiled for (template parameter FEAT): an instance without a feature carries none of its code
 constexpr int F_XB = 1, F_HFIELD = 2, F_BOX = 4, F_ALL = 7;   // extra free body (cassie_tray_box.xml's cup), height field, box geoms
+
+CASSIE_HD inline int pair_g1(uint32_t c) { return (int)(c & 63u); }
+CASSIE_HD inline int pair_g2(uint32_t c) { return (int)((c >> 6) & 63u); }
+CASSIE_HD inline int pair_kind(uint32_t c) { return (int)((c >> 12) & 15u); }
+CASSIE_HD inline int pair_pc(uint32_t c) { return (int)((c >> 16) & 15u); }
 
 // pair kinds handled by the narrow phase
 enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2, PAIR_HFIELD_SPHERE = 3, PAIR_HFIELD_CAPSULE = 4,
@@ -64,14 +72,18 @@ struct DevModel {
   int nfac, fac_start[MV + 1], padf[2];
   uint32_t fac_pairs[NFAC_MAX];  // (t << 24) | (src << 12) | dst: qLD[dst] -= qLD[src] * f_t, grouped by eliminated dof k
   // ---- collision geoms and pairs
-  int geom_body[MG], geom_type[MG];
-  real geom_pos[MG][3], geom_mat[MG][9], geom_size[MG][3];   // geom frame in its body (row-major rotation), sizes
-  int pair_g1[MP], pair_g2[MP], pair_kind[MP], pair_condim[MP];
-  real pair_mu[MP], pair_margin[MP], pair_gap[MP], pair_solref[MP][2], pair_solimp[MP][5];
-  int pair_mu_src[MP];  // how the pair's sliding friction follows from the geoms': 0 max of both (equal priority), 1 geom 1, 2 geom 2
-  real geom_fric[MG], qpos0[44];   // sliding friction per collision geom; the reference configuration (mj_setConst works there)
-  int pair_flags[MP];   // derived-quantity flags of a pair: bit 0 obstacle geom involved (geom user == 1), bit 1 robot-robot (both user == 2),
+  int geom_body[MGT], geom_type[MGT], ngeom_static, root_body;
+  real geom_pos[MG][3], geom_mat[MG][9];   // moving geoms: frame in their body (row-major rotation)
+  real geom_wpose[MGS][12];                // static geoms: world pose as the collision stage wants it (position, z axis, x axis, y axis)
+  real geom_size[MGT][3], geom_rbound[MGT], geom_fric[MGT];   // sizes, bounding-sphere radius (0: plane / height field), sliding friction
+  real robot_reach, padg[3];               // no robot collision geom reaches farther than this from the root body's origin (obstacle broad phase)
+  // candidate pairs in MuJoCo's order: (g1 | g2 << 6 | kind << 12 | parameter record << 16); records = distinct mj_contactParam results
+  uint32_t pair_code[MPAIR];
+  int pc_condim[NPC], pc_mu_src[NPC];   // mu_src: how the sliding friction follows from the geoms': 0 max of both (equal priority), 1 geom 1, 2 geom 2
+  int pc_flags[NPC];    // derived-quantity flags: bit 0 obstacle geom involved (geom user == 1), bit 1 robot-robot (both user == 2),
                         // bits 8.. : geom groups g met by a group-1 geom (cassie_sim_geom_collision, src/cassiemujoco.c:1944-1961)
+  real pc_mu[NPC], pc_margin[NPC], pc_gap[NPC], pc_solref[NPC][2], pc_solimp[NPC][5];
+  real qpos0[44];       // the reference configuration (mj_setConst works there)
   // ---- feet (src/cassiemujoco.c:861-866): body ids, toe / heel points in the foot frames, total mass including the extra free body
   int foot_body[2], padfb[2];
   real toe_local[2][3], heel_local[2][3], foot_offset, total_mass_inv, padft[2];
@@ -131,14 +143,14 @@ constexpr int AX_TMP = 56;                          // [8] toe / heel world xy o
 
 // per-environment model constants (optional, domain randomisation: src/cassiemujoco.c:1303-1436 setters + mj_setConst :949-977).
 // When a batch carries these rows the step kernel reads the listed constants from the env's row instead of the shared model block.
-constexpr int CE_W = 256;
+constexpr int CE_W = 288;
 constexpr int CE_MASS = 0;       // [32] body_mass
 constexpr int CE_IPOS = 32;      // [32][3] body_ipos
 constexpr int CE_DAMP = 128;     // [32] dof_damping (main tree)
-constexpr int CE_FRIC = 160;     // [16] sliding friction per collision geom (device geom order)
-constexpr int CE_BINVW = 176;    // [32] body_invweight0 (translational)  -- written by the set_const launch
-constexpr int CE_DINVW = 208;    // [32] dof_invweight0                    -- written by the set_const launch
-constexpr int CE_ROOT_MINV = 240, CE_TOT_MINV = 241, CE_PGS_SCALE = 242;   // 1 / main-tree mass, 1 / total mass, 1 / (meaninertia * nv)
+constexpr int CE_FRIC = 160;     // [32] sliding friction per collision geom (device geom ids: moving 0..15, static 16..31)
+constexpr int CE_BINVW = 192;    // [32] body_invweight0 (translational)  -- written by the set_const launch
+constexpr int CE_DINVW = 224;    // [32] dof_invweight0                    -- written by the set_const launch
+constexpr int CE_ROOT_MINV = 256, CE_TOT_MINV = 257, CE_PGS_SCALE = 258;   // 1 / main-tree mass, 1 / total mass, 1 / (meaninertia * nv)
 
 // ---- per-warp scratch (in units of `real`)
 constexpr int S_XPOS = 0;                       // [32][3]

@@ -235,11 +235,12 @@ struct Compiler {
       vec p = nums(b->get("pos") ? b->get("pos") : "0 0 0"); memcpy(B.pos, p.data(), sizeof B.pos);
       orientation(b->attr, B.quat); B.iquat[0] = 1;
       if (const XNode *in = b->child("inertial")) {
-        B.explicit_inertial = true; vec ip = nums(in->get("pos")); memcpy(B.ipos, ip.data(), sizeof B.ipos); B.mass = atof(in->get("mass"));
+        B.explicit_inertial = true; vec ip = nums(in->get("pos") ? in->get("pos") : "0 0 0"); ip.resize(3, 0.0); memcpy(B.ipos, ip.data(), sizeof B.ipos); B.mass = in->get("mass") ? atof(in->get("mass")) : 0.0;
         if (in->has("fullinertia")) {
           vec f = nums(in->get("fullinertia")); double I[9] = {f[0], f[3], f[4], f[3], f[1], f[5], f[4], f[5], f[2]}, V[9];
           eig3(I, B.inertia, V); m2q(B.iquat, V);
-        } else { vec d = nums(in->get("diaginertia")); memcpy(B.inertia, d.data(), sizeof B.inertia); orientation(in->attr, B.iquat); }
+        } else { vec d = nums(in->get("diaginertia")); for (size_t i = 0; i < 3; i++) B.inertia[i] = i < d.size() ? d[i] : 0.0;   // a point mass (model/cassie_mass.xml:88) carries no inertia of its own
+                 orientation(in->attr, B.iquat); }
       }
       bodies.push_back(B);
       for (auto &jn : b->kids) if (jn->tag == "joint" || jn->tag == "freejoint") {

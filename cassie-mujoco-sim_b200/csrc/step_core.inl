@@ -36,6 +36,7 @@
 #define ALLMAX(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ = s_ > v[i_] ? s_ : v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
 #define BCAST(dst, src, lane) do { auto s_ = src[lane]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = s_; } while (0)
 #define EXSCAN_INT(v, total) do { int a_ = 0; for (int i_ = 0; i_ < 32; ++i_) { int t_ = v[i_]; v[i_] = a_; a_ += t_; } total = a_; } while (0)
+#define BALLOT(mask, v) do { uint32_t m_ = 0; for (int i_ = 0; i_ < 32; ++i_) if (v[i_]) m_ |= 1u << i_; mask = m_; } while (0)
 #else
 #define CFN __device__ __forceinline__
 #define CNOINLINE __device__ __noinline__   // cold / register-hungry stages: their own register allocation, no pressure on the stepping loop
@@ -56,6 +57,7 @@
 #define ALLSUM(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o_); } while (0)
 #define ALLMAX(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v = mmax(v, __shfl_xor_sync(0xffffffffu, v, o_)); } while (0)
 #define BCAST(dst, src, lane) dst = __shfl_sync(0xffffffffu, src, lane)
+#define BALLOT(mask, v) mask = __ballot_sync(0xffffffffu, v)
 #define EXSCAN_INT(v, total) do { int x_ = v; for (int o_ = 1; o_ < 32; o_ <<= 1) { int y_ = __shfl_up_sync(0xffffffffu, x_, o_); if (l >= o_) x_ += y_; } total = __shfl_sync(0xffffffffu, x_, 31); v = x_ - v; } while (0)
 #endif
 
@@ -413,8 +415,9 @@ template <typename real> CFN void jac_col(const DevModel<real> &cm, int l, int b
 // higher priority wins, else the larger coefficient)
 template <typename real>
 CFN real pair_friction(const DevModel<real> &cm, const real *ce, int p) {
-  if (!ce) return cm.pair_mu[p];
-  const real f1 = ce[CE_FRIC + cm.pair_g1[p]], f2 = ce[CE_FRIC + cm.pair_g2[p]]; const int src = cm.pair_mu_src[p];
+  const uint32_t code = cm.pair_code[p]; const int pc = pair_pc(code);
+  if (!ce) return cm.pc_mu[pc];
+  const real f1 = ce[CE_FRIC + pair_g1(code)], f2 = ce[CE_FRIC + pair_g2(code)]; const int src = cm.pc_mu_src[pc];
   return src == 0 ? mmax(f1, f2) : (src == 1 ? f1 : f2);
 }
 // one row of J  ->  D^-1/2 L^-T J' in place (mj_solveM2 on a single vector, main-tree dofs); returns its squared norm = J inv(M) J'
@@ -859,7 +862,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   STAGE_SYNC(csync & 2);
   // ================= collision (lane = candidate geom pair) =================
   real *geom = sm + S_Y + T_GEOM;   // the smooth-dynamics temporaries below it are dead; the constraint rows are written after the contact list
-  LANES
+  LANES   // world poses of the geoms on moving bodies (static geoms carry theirs in the model block)
     if (l < cm.ngeom) {
       const int b = cm.geom_body[l]; real v[3];
       mat_vec(v, xmat + 9 * b, cm.geom_pos[l]);
@@ -869,14 +872,38 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         const int o = c == 2 ? 3 : (c == 0 ? 6 : 9); geom[12 * l + o] = v[0]; geom[12 * l + o + 1] = v[1]; geom[12 * l + o + 2] = v[2]; }
     }
   ENDL
+  // broad phase for static obstacle boxes (the 15 stair boxes of model/cassie.xml:232-246, parked 20 m away unless a caller places them): a box
+  // farther from the robot's root body than the robot can reach cannot touch it, so its 9 candidate pairs are skipped without a narrow phase
+  uint32_t box_near = 0xffffffffu;
+  if ((FEAT & F_BOX) && cm.ngeom_static > 1) {
+    LV(int, nearb);
+    LANES
+      L(nearb) = 1;
+      if (l < cm.ngeom_static && cm.geom_type[MG + l] == 6) {
+        const real *w = cm.geom_wpose[l], *rp = xpos + 3 * cm.root_body; const real dx = w[0] - rp[0], dy = w[1] - rp[1], dz = w[2] - rp[2], rr = cm.robot_reach + cm.geom_rbound[MG + l];
+        L(nearb) = (dx * dx + dy * dy + dz * dz <= rr * rr) ? 1 : 0;
+      }
+    ENDL
+    BALLOT(box_near, nearb);
+  }
+  int ncon_total = 0;
+  for (int pass = 0; pass * 32 < cm.npair; ++pass) {   // 32 candidate pairs per pass, one per lane, in MuJoCo's pair order
   LV(int, ccount); LV(int, coff);
   LVA(real, cb, 28);   // up to 4 contacts of this lane's pair: [pos3 normal3 dist] each
   LV(real, ch0); LV(real, ch1); LV(real, ch2);
   LANES
     L(ccount) = 0; L(ch0) = L(ch1) = L(ch2) = 0;
-    if (l < cm.npair) {
-      const int g1 = cm.pair_g1[l], g2 = cm.pair_g2[l], kind = cm.pair_kind[l]; const real margin = cm.pair_margin[l];
-      const real *p1 = geom + 12 * g1, *a1 = p1 + 3, *p2 = geom + 12 * g2, *a2 = p2 + 3;
+    const int pidx = 32 * pass + l;
+    bool go = pidx < cm.npair;
+    const uint32_t code = go ? cm.pair_code[pidx] : 0u;
+    const int g1 = pair_g1(code), g2 = pair_g2(code), kind = pair_kind(code);
+    if ((FEAT & F_BOX) && go && kind >= PAIR_SPHERE_BOX) {   // a static box out of the robot's reach (pairs with the extra free body are always tested)
+      if (g1 >= MG && !((box_near >> (g1 - MG)) & 1u) && cm.geom_body[g2] != xb) go = false;
+      if (g2 >= MG && !((box_near >> (g2 - MG)) & 1u) && cm.geom_body[g1] != xb) go = false;
+    }
+    if (go) {
+      const real margin = cm.pc_margin[pair_pc(code)];
+      const real *p1 = g1 < MG ? geom + 12 * g1 : cm.geom_wpose[g1 - MG], *a1 = p1 + 3, *p2 = g2 < MG ? geom + 12 * g2 : cm.geom_wpose[g2 - MG], *a2 = p2 + 3;
       real cp[4][3], cn[4][3], cdst[4]; int n = 0;
       if (kind == PAIR_PLANE_SPHERE || kind == PAIR_PLANE_CAPSULE) {
         const real r = cm.geom_size[g2][0], hl = (kind == PAIR_PLANE_CAPSULE) ? cm.geom_size[g2][1] : real(0);
@@ -938,21 +965,23 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     }
     L(coff) = L(ccount);
   ENDL
-  int ncon_total = 0;
-  EXSCAN_INT(coff, ncon_total);
+  int pass_total = 0;
+  EXSCAN_INT(coff, pass_total);
   LANES  // write contacts in pair order: [pos3 frame9 dist pair]
     for (int e = 0; e < L(ccount); ++e) {
-      const int c = L(coff) + e;
+      const int c = ncon_total + L(coff) + e;
       if (c < MAXCON) {
         real *o = con + 16 * c;
         o[0] = LA(cb, 7 * e); o[1] = LA(cb, 7 * e + 1); o[2] = LA(cb, 7 * e + 2);
         real f[9] = {LA(cb, 7 * e + 3), LA(cb, 7 * e + 4), LA(cb, 7 * e + 5), L(ch0), L(ch1), L(ch2), 0, 0, 0};
         make_frame(f);
         for (int k = 0; k < 9; ++k) o[3 + k] = f[k];
-        o[12] = LA(cb, 7 * e + 6); o[13] = (real)l;
+        o[12] = LA(cb, 7 * e + 6); o[13] = (real)(32 * pass + l);
       }
     }
   ENDL
+  ncon_total += pass_total;
+  }
   int ncon = ncon_total < MAXCON ? ncon_total : MAXCON;
 
   // ================= constraint rows: J (into Y), pos, source; order = equality, limits, contacts =================
@@ -997,9 +1026,9 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   const int nefc_before_contacts = nefc;
   int ncon_used = 0;
   for (int c = 0; c < ncon; ++c) {
-    const real *o = con + 16 * c; const int p = (int)o[13]; const int rows = cm.pair_condim[p] > 1 ? 4 : 1;
+    const real *o = con + 16 * c; const int p = (int)o[13]; const uint32_t pcode = cm.pair_code[p]; const int rows = cm.pc_condim[pair_pc(pcode)] > 1 ? 4 : 1;
     if (nefc + rows > NEFC) break;
-    const int b1 = cm.geom_body[cm.pair_g1[p]], b2 = cm.geom_body[cm.pair_g2[p]];
+    const int b1 = cm.geom_body[pair_g1(pcode)], b2 = cm.geom_body[pair_g2(pcode)];
     LANES  // lane = dof
       real j1[3], j2[3], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, cm3[3] = {L(com0), L(com1), L(com2)};
       jac_col(cm, l, b1, cd, o, cm3, j1); jac_col(cm, l, b2, cd, o, cm3, j2);
@@ -1078,9 +1107,10 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (src < 64) { solref = cm.eq_solref[src]; solimp = cm.eq_solimp[src]; dA = binvw[cm.eq_b1[src]] + binvw[cm.eq_b2[src]]; }
           else if (src < 128) { const int j = src - 64; solref = cm.jnt_solref[j]; solimp = cm.jnt_solimp[j]; dA = dinvw[cm.jnt_dofadr[j]]; }
           else {
-            const int p = src - 128; solref = cm.pair_solref[p]; solimp = cm.pair_solimp[p]; margin = cm.pair_margin[p] - cm.pair_gap[p];
-            dA = binvw[cm.geom_body[cm.pair_g1[p]]] + binvw[cm.geom_body[cm.pair_g2[p]]];
-            if (cm.pair_condim[p] > 1) { const real mu = pair_friction(cm, ce, p); dA += mu * mu * dA; rscale = 2 * mu * mu; }
+            const int p = src - 128; const uint32_t pcode = cm.pair_code[p]; const int pc = pair_pc(pcode);
+            solref = cm.pc_solref[pc]; solimp = cm.pc_solimp[pc]; margin = cm.pc_margin[pc] - cm.pc_gap[pc];
+            dA = binvw[cm.geom_body[pair_g1(pcode)]] + binvw[cm.geom_body[pair_g2(pcode)]];
+            if (cm.pc_condim[pc] > 1) { const real mu = pair_friction(cm, ce, p); dA += mu * mu * dA; rscale = 2 * mu * mu; }
           }
           const real imp = impedance(solimp, pos, margin);
           const real Rr = rscale * mmax(minval<real>(), (1 - imp) * dA / imp);
@@ -1275,12 +1305,12 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     if (nefc > 0) { LANES if (l < nefc) efc[4 * l] = L(f0); if (l + 32 < nefc) efc[4 * (l + 32)] = L(f1); ENDL }   // slot 0 (b) is dead: keep the row forces
     LANES  // lane = contact: decode the pyramid, rotate into the world frame, classify
       if (l < ncon_used) {
-        real *o = con + 16 * l; const int p = (int)o[13], r0 = (int)o[14];
+        real *o = con + 16 * l; const int p = (int)o[13], r0 = (int)o[14]; const uint32_t pcode = cm.pair_code[p];
         real fn, t1 = 0, t2 = 0;
-        if (cm.pair_condim[p] == 1) fn = efc[4 * r0];
+        if (cm.pc_condim[pair_pc(pcode)] == 1) fn = efc[4 * r0];
         else { const real a = efc[4 * r0], b = efc[4 * (r0 + 1)], c = efc[4 * (r0 + 2)], d = efc[4 * (r0 + 3)], mu = pair_friction(cm, ce, p); fn = a + b + c + d; t1 = (a - b) * mu; t2 = (c - d) * mu; }
         real F[3]; for (int k = 0; k < 3; ++k) F[k] = o[3 + k] * fn + o[6 + k] * t1 + o[9 + k] * t2;
-        const int b1 = cm.geom_body[cm.pair_g1[p]], b2 = cm.geom_body[cm.pair_g2[p]], lf = cm.foot_body[0], rf = cm.foot_body[1];
+        const int b1 = cm.geom_body[pair_g1(pcode)], b2 = cm.geom_body[pair_g2(pcode)], lf = cm.foot_body[0], rf = cm.foot_body[1];
         const bool f1 = (b1 == lf || b1 == rf), anyf = f1 || b2 == lf || b2 == rf; const int id = (b1 == rf || b2 == rf) ? 1 : 0;
         real toe = 0;
         if (anyf) {
@@ -1304,7 +1334,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         if (l < 6) { aux[AX_FOOT_FORCE + 6 * (l / 3) + l % 3] = acc; aux[AX_FOOT_FORCE + 6 * (l / 3) + 3 + l % 3] = 0; }
         else aux[AX_TOE_FORCE + (l - 6)] = acc;
       } else if (l == 18) {
-        int fl = 0; for (int c = 0; c < ncon_used; ++c) fl |= cm.pair_flags[(int)con[16 * c + 13]];
+        int fl = 0; for (int c = 0; c < ncon_used; ++c) fl |= cm.pc_flags[pair_pc(cm.pair_code[(int)con[16 * c + 13]])];
         aux[AX_OBSTACLE] = (fl & 1) ? real(1) : real(0); aux[AX_SELF] = (fl & 2) ? real(1) : real(0); aux[AX_GROUPMASK] = (real)(fl >> 8); aux[AX_NCON] = (real)ncon_used;
       }
     ENDL

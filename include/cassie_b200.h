@@ -72,6 +72,23 @@ int cassie_sim_forward(cassie_sim_t *sim);
 /* include/cassiemujoco.h:271-275 (src/cassiemujoco.c:1974-2000): pin / free the pelvis (stiff spring-damper on its slides, damping on its ball joint) */
 void cassie_sim_hold(cassie_sim_t *sim);
 void cassie_sim_release(cassie_sim_t *sim);
+/* src/cassiemujoco.c:1466-1541 (example/test_terrain.c:118-157 builds stairs out of the 15 boxes of model/cassie.xml:232-246 with them): geom position /
+ * orientation / size in the reference's geom numbering; borrowed pointers are host mirrors, a change takes effect at the next step / forward.
+ * All 135 box x robot candidate pairs are collided (contact rules for boxes: DESIGN.md section 3); a box out of the robot's reach costs one
+ * distance test per step.  cassie_batch_set_geom_pose: the same for a batch, one placement shared by its environments (NULL: leave that part). */
+double *cassie_sim_geom_pos(cassie_sim_t *sim);
+double *cassie_sim_geom_quat(cassie_sim_t *sim);
+double *cassie_sim_geom_size(cassie_sim_t *sim);
+double *cassie_sim_geom_name_pos(cassie_sim_t *sim, const char *name);
+double *cassie_sim_geom_name_quat(cassie_sim_t *sim, const char *name);
+double *cassie_sim_geom_name_size(cassie_sim_t *sim, const char *name);
+void cassie_sim_set_geom_pos(cassie_sim_t *sim, double *pos);
+void cassie_sim_set_geom_quat(cassie_sim_t *sim, double *quat);
+void cassie_sim_set_geom_size(cassie_sim_t *sim, double *size);
+void cassie_sim_set_geom_name_pos(cassie_sim_t *sim, const char *name, double *pos);
+void cassie_sim_set_geom_name_quat(cassie_sim_t *sim, const char *name, double *quat);
+void cassie_sim_set_geom_name_size(cassie_sim_t *sim, const char *name, double *size);
+int cassie_batch_set_geom_pose(cassie_batch_t *b, const char *name, const double *pos, const double *quat, const double *size);
 /* include/cassiemujoco.h:61-73 (src/cassiemujoco.c:1072-1093): model (per-environment constants, height field, timestep) + full dynamic state */
 cassie_sim_t *cassie_sim_duplicate(const cassie_sim_t *src);
 void cassie_sim_copy(cassie_sim_t *dst, const cassie_sim_t *src);

@@ -1600,7 +1600,7 @@ double *osim_model_array(OSim *c, const char *key, int *n) {
 #define MARR(name, ptr, cnt) if (!strcmp(key, name)) { *n = (cnt); return (double *)(ptr); }
   MARR("body_mass", m->body_mass, m->nbody) MARR("body_ipos", m->body_ipos, 3 * m->nbody) MARR("dof_damping", m->dof_damping, m->nv)
   MARR("geom_friction", m->geom_friction, 3 * m->ngeom) MARR("body_invweight0", m->body_invweight0, 2 * m->nbody) MARR("dof_invweight0", m->dof_invweight0, m->nv)
-  MARR("body_subtreemass", m->body_subtreemass, m->nbody) MARR("meaninertia", &m->meaninertia, 1) MARR("timestep", &m->timestep, 1) MARR("jnt_stiffness", m->jnt_stiffness, m->njnt) MARR("qpos_spring", m->qpos_spring, m->nq) MARR("body_pos", m->body_pos, 3 * m->nbody)
+  MARR("body_subtreemass", m->body_subtreemass, m->nbody) MARR("meaninertia", &m->meaninertia, 1) MARR("timestep", &m->timestep, 1) MARR("geom_pos", m->geom_pos, 3 * m->ngeom) MARR("geom_quat", m->geom_quat, 4 * m->ngeom) MARR("geom_size", m->geom_size, 3 * m->ngeom) MARR("jnt_stiffness", m->jnt_stiffness, m->njnt) MARR("qpos_spring", m->qpos_spring, m->nq) MARR("body_pos", m->body_pos, 3 * m->nbody)
   *n = 0; return NULL;
 }
 

@@ -243,7 +243,7 @@ def compile_mjcf(path):
                     bd['inertia'] = w
                     bd['iquat'] = mat2quat(V)
                 else:
-                    bd['inertia'] = fl(ine.get('diaginertia'))
+                    bd['inertia'] = fl(ine.get('diaginertia')) if ine.get('diaginertia') else np.zeros(3)   # a point mass (model/cassie_mass.xml:88)
                     bd['iquat'] = orientation(ine.attrib)
             bodies.append(bd)
             for j in list(b.findall('joint')) + list(b.findall('freejoint')):

@@ -53,6 +53,16 @@ template <typename real> struct Emu {
 
 struct Handle { int fp32; Emu<float> f; Emu<double> d; };
 
+// move / turn / resize a geom (host geom numbering = the reference's) and rebuild the constant block, like cassie_sim_set_geom_name_pos & co.
+template <typename E> static int emu_geom_set_(E &e, int g, const double *pos, const double *quat, const double *size) {
+  if (g < 0 || g >= e.hm.ngeom) return -1;
+  if (pos) for (int k = 0; k < 3; k++) e.hm.geom_pos[3 * g + k] = pos[k];
+  if (quat) for (int k = 0; k < 4; k++) e.hm.geom_quat[4 * g + k] = quat[k];
+  if (size) for (int k = 0; k < 3; k++) e.hm.geom_size[3 * g + k] = size[k];
+  std::string err; return build_dev_model(e.hm, e.dm, err, &e.info) ? 0 : -2;
+}
+
+
 extern "C" {
 void *emu_new(const char *path, int fp32) {
   Handle *h = new Handle(); h->fp32 = fp32; std::string err;
@@ -66,6 +76,8 @@ void emu_step(void *p, const double *pd50, int nticks) {
   if (h->fp32) { for (int i = 0; i < 50; i++) h->f.pd[i] = (float)pd50[i]; h->f.step(nticks); }
   else { for (int i = 0; i < 50; i++) h->d.pd[i] = pd50[i]; h->d.step(nticks); }
 }
+int emu_set_geom(void *p, int g, const double *pos, const double *quat, const double *size) { Handle *h = (Handle *)p; return h->fp32 ? emu_geom_set_(h->f, g, pos, quat, size) : emu_geom_set_(h->d, g, pos, quat, size); }
+int emu_geom_id(void *p, const char *name) { Handle *h = (Handle *)p; return (h->fp32 ? h->f.hm : h->d.hm).geom_id(name); }
 void emu_set_hfield(void *p, const float *data, int n) { Handle *h = (Handle *)p; std::vector<float> &dst = h->fp32 ? h->f.hfield : h->d.hfield; for (int i = 0; i < n && i < (int)dst.size(); i++) dst[i] = data[i]; }
 int emu_model_set(void *p, const char *what, const double *v, int n) { Handle *h = (Handle *)p; return h->fp32 ? h->f.model_set(what, v, n) : h->d.model_set(what, v, n); }
 void emu_set_const(void *p) { Handle *h = (Handle *)p; if (h->fp32) h->f.set_const(); else h->d.set_const(); }

@@ -97,6 +97,16 @@ class EmuSim:
             a = np.ascontiguousarray(np.concatenate([amp, phase, [freq]]), dtype=np.float64)
             self.L.emu_set_gait(self.h, a.ctypes.data_as(C.POINTER(C.c_double)))
 
+    def set_geom(self, name, pos=None, quat=None, size=None):
+        """move / turn / resize a named geom (cassie_sim_set_geom_name_pos / quat / size) and rebuild the constant block"""
+        dp = C.POINTER(C.c_double)
+        self.L.emu_set_geom.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+        self.L.emu_geom_id.argtypes = [C.c_void_p, C.c_char_p]
+        g = self.L.emu_geom_id(self.h, name.encode())
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (pos, quat, size)]
+        assert self.L.emu_set_geom(self.h, g, *[None if a is None else a.ctypes.data_as(dp) for a in arrs]) == 0, name
+        return g
+
     def enable_est(self, on=True):
         """in-kernel estimator (forces + filters) of the extended instance; enabling restarts it"""
         self.L.emu_enable_est.argtypes = [C.c_void_p, C.c_int]

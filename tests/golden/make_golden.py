@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(REPO, 'oracle'))
 import mjcf_compile as mc  # noqa: E402
 
 REF = os.environ.get('CASSIE_REFERENCE', '/root/reference')
-MODELS = ['cassie', 'cassie_hfield', 'cassie_tray_box', 'cassie_no_grav']
+MODELS = ['cassie', 'cassie_hfield', 'cassie_tray_box', 'cassie_no_grav', 'cassie_mass', 'cassie_depth']
 
 
 def agility_vectors(n=400, seed=123):

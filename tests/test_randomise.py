@@ -8,7 +8,7 @@ import pytest
 from conftest import GOLDEN, PD_DGAIN, PD_PGAIN, PD_TARGET, REPO
 
 PD_ROW = np.concatenate([np.zeros(10), PD_TARGET, np.zeros(10), PD_PGAIN, PD_DGAIN])
-CE_BINVW, CE_DINVW, CE_ROOT, CE_TOT, CE_PGS = 176, 208, 240, 241, 242     # devmodel.h CE_*
+CE_BINVW, CE_DINVW, CE_ROOT, CE_TOT, CE_PGS = 192, 224, 256, 257, 258     # devmodel.h CE_*
 
 
 def randomise(o, rng, free_body=None):
