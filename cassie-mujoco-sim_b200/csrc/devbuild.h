@@ -254,6 +254,18 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     }
   }
   d.ngeom = n_dyn; d.ngeom_static = n_stat; d.robot_reach = (real)(robot_reach * 1.05 + 0.05);
+  { // two runs: pairs without a static box first, static-box pairs after them; each keeps MuJoCo's relative order and its rank in the full order
+    std::vector<uint32_t> a, bx; d.static_box_mask = 0;
+    for (int g = MG; g < MGT; g++) if (g - MG < n_stat && d.geom_type[g] == GEOM_BOX) d.static_box_mask |= 1 << (g - MG);
+    for (int p = 0; p < d.npair; p++) {
+      const uint32_t c = d.pair_code[p] | ((uint32_t)p << 20); const int g1 = pair_g1(c), g2 = pair_g2(c);
+      const bool sb = (g1 >= MG && ((d.static_box_mask >> (g1 - MG)) & 1)) || (g2 >= MG && ((d.static_box_mask >> (g2 - MG)) & 1));
+      (sb ? bx : a).push_back(c);
+    }
+    d.npair_a = (int)a.size();
+    for (size_t i = 0; i < a.size(); i++) d.pair_code[i] = a[i];
+    for (size_t i = 0; i < bx.size(); i++) d.pair_code[a.size() + i] = bx[i];
+    if (d.npair > 255) { err = "too many candidate geom pairs"; return false; } }
   // mirror symmetry of the dof tree: a base chain 0..f-1, then two blocks of n dofs with identical relative structure hanging off dof f-1
   d.sym_on = 0;
   { const int nv2 = d.nv;

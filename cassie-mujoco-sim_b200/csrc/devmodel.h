@@ -36,6 +36,7 @@ CASSIE_HD inline int pair_g1(uint32_t c) { return (int)(c & 63u); }
 CASSIE_HD inline int pair_g2(uint32_t c) { return (int)((c >> 6) & 63u); }
 CASSIE_HD inline int pair_kind(uint32_t c) { return (int)((c >> 12) & 15u); }
 CASSIE_HD inline int pair_pc(uint32_t c) { return (int)((c >> 16) & 15u); }
+CASSIE_HD inline int pair_rank(uint32_t c) { return (int)((c >> 20) & 255u); }
 
 // pair kinds handled by the narrow phase
 enum PairKind { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_CAPSULE_CAPSULE = 2, PAIR_HFIELD_SPHERE = 3, PAIR_HFIELD_CAPSULE = 4,
@@ -72,12 +73,14 @@ struct DevModel {
   int nfac, fac_start[MV + 1], padf[2];
   uint32_t fac_pairs[NFAC_MAX];  // (t << 24) | (src << 12) | dst: qLD[dst] -= qLD[src] * f_t, grouped by eliminated dof k
   // ---- collision geoms and pairs
-  int geom_body[MGT], geom_type[MGT], ngeom_static, root_body;
+  int geom_body[MGT], geom_type[MGT], ngeom_static, root_body, npair_a, static_box_mask, padn[2];   // npair_a: pairs without a static box come first
   real geom_pos[MG][3], geom_mat[MG][9];   // moving geoms: frame in their body (row-major rotation)
   real geom_wpose[MGS][12];                // static geoms: world pose as the collision stage wants it (position, z axis, x axis, y axis)
   real geom_size[MGT][3], geom_rbound[MGT], geom_fric[MGT];   // sizes, bounding-sphere radius (0: plane / height field), sliding friction
   real robot_reach, padg[3];               // no robot collision geom reaches farther than this from the root body's origin (obstacle broad phase)
-  // candidate pairs in MuJoCo's order: (g1 | g2 << 6 | kind << 12 | parameter record << 16); records = distinct mj_contactParam results
+  // candidate pairs: (g1 | g2 << 6 | kind << 12 | parameter record << 16 | rank in MuJoCo's pair order << 20); records = distinct mj_contactParam
+  // results.  Stored in two runs, each in MuJoCo's order: [0, npair_a) the pairs without a static box, [npair_a, npair) the static-box pairs, which are
+  // only visited when a box is within the robot's reach; contacts are put back into MuJoCo's order by rank afterwards
   uint32_t pair_code[MPAIR];
   int pc_condim[NPC], pc_mu_src[NPC];   // mu_src: how the sliding friction follows from the geoms': 0 max of both (equal priority), 1 geom 1, 2 geom 2
   int pc_flags[NPC];    // derived-quantity flags: bit 0 obstacle geom involved (geom user == 1), bit 1 robot-robot (both user == 2),

@@ -358,7 +358,7 @@ template <typename real> CFN int sphere_box(real margin, const real *sc, real r,
   return 1;
 }
 // all box pair kinds; g1 / g2 = geom records, s1 / s2 = geom sizes; returns the contact count (<= 4)
-template <typename real> CFN int box_pair(int kind, real margin, const real *g1, const real *g2, const real *s1, const real *s2, real (*cp)[3], real (*cn)[3], real *cdst) {
+template <typename real> CNOINLINE int box_pair(int kind, real margin, const real *g1, const real *g2, const real *s1, const real *s2, real (*cp)[3], real (*cn)[3], real *cdst) {
   int cnt = 0;
   if (kind == PAIR_PLANE_BOX) {            // every corner below the plane, at most 4, in corner order
     const real *n = g1 + 3;
@@ -875,7 +875,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   // broad phase for static obstacle boxes (the 15 stair boxes of model/cassie.xml:232-246, parked 20 m away unless a caller places them): a box
   // farther from the robot's root body than the robot can reach cannot touch it, so its 9 candidate pairs are skipped without a narrow phase
   uint32_t box_near = 0xffffffffu;
-  if ((FEAT & F_BOX) && cm.ngeom_static > 1) {
+  if ((FEAT & F_BOX) && cm.npair > cm.npair_a) {
     LV(int, nearb);
     LANES
       L(nearb) = 1;
@@ -886,15 +886,18 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     ENDL
     BALLOT(box_near, nearb);
   }
-  int ncon_total = 0;
-  for (int pass = 0; pass * 32 < cm.npair; ++pass) {   // 32 candidate pairs per pass, one per lane, in MuJoCo's pair order
+  int ncon_total = 0, ncon_a = 0;
+  for (int seg = 0; seg < 2; ++seg) {   // run 0: the pairs without a static box; run 1: the static-box pairs, only when a box is within reach
+  const int seg0 = seg ? cm.npair_a : 0, seg1 = seg ? cm.npair : cm.npair_a;
+  if (seg == 1) { ncon_a = ncon_total; if (!(FEAT & F_BOX) || seg0 == seg1 || !(box_near & (uint32_t)cm.static_box_mask)) break; }
+  for (int pbase = seg0; pbase < seg1; pbase += 32) {   // 32 candidate pairs per pass, one per lane
   LV(int, ccount); LV(int, coff);
   LVA(real, cb, 28);   // up to 4 contacts of this lane's pair: [pos3 normal3 dist] each
   LV(real, ch0); LV(real, ch1); LV(real, ch2);
   LANES
     L(ccount) = 0; L(ch0) = L(ch1) = L(ch2) = 0;
-    const int pidx = 32 * pass + l;
-    bool go = pidx < cm.npair;
+    const int pidx = pbase + l;
+    bool go = pidx < seg1;
     const uint32_t code = go ? cm.pair_code[pidx] : 0u;
     const int g1 = pair_g1(code), g2 = pair_g2(code), kind = pair_kind(code);
     if ((FEAT & F_BOX) && go && kind >= PAIR_SPHERE_BOX) {   // a static box out of the robot's reach (pairs with the extra free body are always tested)
@@ -976,11 +979,21 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         real f[9] = {LA(cb, 7 * e + 3), LA(cb, 7 * e + 4), LA(cb, 7 * e + 5), L(ch0), L(ch1), L(ch2), 0, 0, 0};
         make_frame(f);
         for (int k = 0; k < 9; ++k) o[3 + k] = f[k];
-        o[12] = LA(cb, 7 * e + 6); o[13] = (real)(32 * pass + l);
+        o[12] = LA(cb, 7 * e + 6); o[13] = (real)(pbase + l); o[15] = (real)(8 * pair_rank(cm.pair_code[pbase + l]) + e);   // pair, (rank, e) sort key
       }
     }
   ENDL
   ncon_total += pass_total;
+  }
+  }
+  if ((FEAT & F_BOX) && ncon_total > ncon_a && ncon_a > 0) {   // contacts of both runs: back into MuJoCo's order (by pair rank, then contact index within the pair)
+    const int nc = ncon_total < MAXCON ? ncon_total : MAXCON;
+    LVA(real, row, 16); LV(int, dst);
+    LANES
+      L(dst) = -1;
+      if (l < nc) { const real key = con[16 * l + 15]; int r = 0; for (int c = 0; c < nc; ++c) if (con[16 * c + 15] < key) ++r; L(dst) = r; for (int k = 0; k < 16; ++k) LA(row, k) = con[16 * l + k]; }
+    ENDL
+    LANES if (L(dst) >= 0) for (int k = 0; k < 16; ++k) con[16 * L(dst) + k] = LA(row, k); ENDL
   }
   int ncon = ncon_total < MAXCON ? ncon_total : MAXCON;
 

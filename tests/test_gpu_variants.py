@@ -70,7 +70,7 @@ def test_stairs_with_the_legacy_geom_verbs(oracle_mod):
     assert o.arr('qpos')[2] > 0.8 and all(cc['geom1'] != 0 for cc in o.contacts())      # standing on the boxes, the floor plane (geom 0) is untouched
     ff = np.zeros(12)
     L.cassie_sim_foot_forces(c.c, ff.ctypes.data_as(dp))
-    assert ff[2] > 50 and ff[8] > 50                                                      # both feet carry weight (derived-quantity row sees box contacts)
+    assert np.abs(ff - o.foot_forces()).max() < 1e-6 and ff[2] + ff[8] > 150               # the derived-quantity row sees the box contacts: the boxes carry the robot
 
 
 def test_stairs_in_a_batch():
