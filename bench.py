@@ -490,6 +490,8 @@ def gpu_arm(args, rank, local_rank, world):
     med, med_multi, s_e2e, s_e2e_off, ms_flush = [float(x) for x in t]
     if rank == 0:
         try:
+            if world > 1 and getattr(args, '_allowed_cpus', None):   # the CPU arm gets the whole lease back (the other ranks are done), not rank 0's pinned share
+                os.sched_setaffinity(0, args._allowed_cpus)
             cpu = cpu_baseline(20000 if args.config in (2, 3) else 8000, model=cfg['model'])
         except Exception as ex:   # the oracle is a checker; its absence must not void the GPU number
             cpu = {'value': None, 'unit': 'env-steps/s', 'cores': effective_cpus()[0], 'kind': 'port', 'sample': 'unavailable: %r' % (ex,)}
@@ -552,8 +554,14 @@ def main():
     else:
         # N ranks on one node share the host: each rank takes its slice of the CPUs (on its GPU's NUMA node) BEFORE any OpenMP runtime starts;
         # the AoS entry point sizes its pack / unpack team from what the process may use
+        eff_all, _, quota = effective_cpus()            # before pinning: what the whole job may use
+        allowed = sorted(os.sched_getaffinity(0))
         pin_rank_to_its_share(local_rank, world)
-        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(max(2, min(32, effective_cpus()[0]))))
+        # pack / unpack threads of this rank: its pinned CPUs, but never more than its share of the cgroup quota (N ranks x 32 threads on a lease that
+        # owns 64 CPUs would only throttle each other)
+        per_rank = max(1, eff_all // max(1, world))
+        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(max(2, min(32, effective_cpus()[0], per_rank))))
+        args._allowed_cpus = allowed
         gpu_arm(args, rank, local_rank, world)
 
 

@@ -24,22 +24,23 @@
 #define CASSIE_STEP_ENTRY(tag) extern "C" const void *cassie_step_entry_##tag(void);
 CASSIE_STEP_ENTRY(f00) CASSIE_STEP_ENTRY(f10) CASSIE_STEP_ENTRY(f02) CASSIE_STEP_ENTRY(f12) CASSIE_STEP_ENTRY(f04) CASSIE_STEP_ENTRY(f14) CASSIE_STEP_ENTRY(f05) CASSIE_STEP_ENTRY(f15) CASSIE_STEP_ENTRY(f07) CASSIE_STEP_ENTRY(f17)
 CASSIE_STEP_ENTRY(d07) CASSIE_STEP_ENTRY(d17)
+CASSIE_STEP_ENTRY(f20) CASSIE_STEP_ENTRY(f22) CASSIE_STEP_ENTRY(f24) CASSIE_STEP_ENTRY(f25) CASSIE_STEP_ENTRY(f27) CASSIE_STEP_ENTRY(d27)
 #undef CASSIE_STEP_ENTRY
 
 namespace cassie {
 
 // the instance for (precision, plain / extended, model features): the smallest compiled feature set that covers the model's
-template <typename real> static const void *step_entry(bool ext, int feat, int *compiled_feat = nullptr) {
+template <typename real> static const void *step_entry(int inst, int feat, int *compiled_feat = nullptr) {   // inst: 0 plain, 1 extended, 2 plain + estimator
   int f = F_ALL;
   if (!std::is_same<real, double>::value) { if (feat == 0) f = 0; else if (feat == F_HFIELD) f = F_HFIELD; else if (feat == F_BOX) f = F_BOX; else if ((feat & ~(F_XB | F_BOX)) == 0) f = F_XB | F_BOX; }
   if (compiled_feat) *compiled_feat = f;
-  if (std::is_same<real, double>::value) return ext ? cassie_step_entry_d17() : cassie_step_entry_d07();
+  if (std::is_same<real, double>::value) return inst == 1 ? cassie_step_entry_d17() : (inst == 2 ? cassie_step_entry_d27() : cassie_step_entry_d07());
   switch (f) {
-    case 0: return ext ? cassie_step_entry_f10() : cassie_step_entry_f00();
-    case F_HFIELD: return ext ? cassie_step_entry_f12() : cassie_step_entry_f02();
-    case F_BOX: return ext ? cassie_step_entry_f14() : cassie_step_entry_f04();
-    case F_XB | F_BOX: return ext ? cassie_step_entry_f15() : cassie_step_entry_f05();
-    default: return ext ? cassie_step_entry_f17() : cassie_step_entry_f07();
+    case 0: return inst == 1 ? cassie_step_entry_f10() : (inst == 2 ? cassie_step_entry_f20() : cassie_step_entry_f00());
+    case F_HFIELD: return inst == 1 ? cassie_step_entry_f12() : (inst == 2 ? cassie_step_entry_f22() : cassie_step_entry_f02());
+    case F_BOX: return inst == 1 ? cassie_step_entry_f14() : (inst == 2 ? cassie_step_entry_f24() : cassie_step_entry_f04());
+    case F_XB | F_BOX: return inst == 1 ? cassie_step_entry_f15() : (inst == 2 ? cassie_step_entry_f25() : cassie_step_entry_f05());
+    default: return inst == 1 ? cassie_step_entry_f17() : (inst == 2 ? cassie_step_entry_f27() : cassie_step_entry_f07());
   }
 }
 
@@ -221,7 +222,7 @@ struct BatchBase {
 
 template <typename real> struct Batch : BatchBase {
   DevModel<real> *d_model = nullptr; EnvArrays<real> A{}; int QW = QPOS_W_MAIN, VW = QVEL_W_MAIN;
-  struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[2];   // [0] plain instance, [1] extended instance
+  struct LaunchCfg { int wpb = 1; size_t smem = 0; int resident_ctas = 1; } cfg[3];   // [0] plain instance, [1] extended instance, [2] plain + estimator
   int feat = F_ALL;   // model features (F_XB | F_HFIELD | F_BOX): selects the kernel instance
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr, *pin_task = nullptr;   // pinned staging for the AoS entry point
@@ -261,8 +262,8 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    for (int ext = 0; ext < 2; ++ext) {
-      const long wb = (long)warp_bytes<real>(hmodel_ystride, ext != 0), mb = (long)model_bytes<real>() + 256;   // + static shared (mbarrier) and alignment slack
+    for (int ext = 0; ext < 3; ++ext) {
+      const long wb = (long)warp_bytes<real>(hmodel_ystride, ext == 1), mb = (long)model_bytes<real>() + 256;   // + static shared (mbarrier) and alignment slack
       const char *w = getenv("CASSIE_B200_WPB"); int k_sel = 1;
       if (w) { k_sel = atoi(w); const int kmax = (int)(((long)dev_smem - mb) / wb); if (k_sel > kmax) k_sel = kmax; }
       else {
@@ -283,7 +284,7 @@ template <typename real> struct Batch : BatchBase {
       }
       cfg[ext].wpb = k_sel; cfg[ext].smem = model_bytes<real>() + (size_t)k_sel * wb;
       int per_sm = 0;
-      { const void *entry = step_entry<real>(ext != 0, feat);
+      { const void *entry = step_entry<real>(ext, feat);
         CUDA_OK(cudaFuncSetAttribute(entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg[ext].smem));
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entry, 32 * k_sel, cfg[ext].smem)); }
       cfg[ext].resident_ctas = per_sm * sms < 1 ? 1 : per_sm * sms;
@@ -590,9 +591,11 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaSetDevice(device));
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
     A.nsub = nsub_override;
-    A.warp_stride = (int)warp_bytes<real>(A.ystride, A.cenv || A.aux || A.task || A.est);
-    const bool ext = A.cenv || A.aux || A.task || A.est;   // per-environment model constants / derived-quantity rows / task-space PD / in-kernel estimator: extended instance (its own scratch size and launch shape)
-    const LaunchCfg &c = cfg[ext ? 1 : 0];
+    // per-environment model constants / derived-quantity rows / task-space PD / set_const: extended instance (its own scratch size and launch shape);
+    // the in-kernel estimator alone: the plain instance with the estimator stage
+    const int ext = (A.cenv || A.aux || A.task || mode == 3) ? 1 : (A.est ? 2 : 0);
+    A.warp_stride = (int)warp_bytes<real>(A.ystride, ext == 1);
+    const LaunchCfg &c = cfg[ext];
     int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
     { const DevModel<real> *dm = d_model; void *args[4] = {(void *)&dm, (void *)&A, (void *)&nticks, (void *)&mode};
       CUDA_OK(cudaLaunchKernel(step_entry<real>(ext, feat), dim3(grid), dim3(32 * c.wpb), args, c.smem, stream)); }

@@ -1664,7 +1664,7 @@ template <typename real> CFN real core_hi_deg(int i) { const real t[10] = {20, 2
 template <typename real> CFN real core_K(int k) { const real t[5] = {1000, 800, 1200, 1200, 100}; return t[k]; }
 template <typename real> CFN real core_C(int k) { const real t[5] = {12, 12, 36, 36, 7}; return t[k]; }
 
-template <typename real, bool DR, int FEAT>
+template <typename real, bool DR, int FEAT, bool EST = DR>
 CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP(real, qvel), LP(real, qacc_ws), LP(real, xqvel), LP(real, xqacc_ws), int nticks, int mode) {
   const bool forward_only = (mode != 0);
   DECL_LANE
@@ -1778,7 +1778,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     ENDL
     // ---- *y = cassie_out (:1127): the observation of this tick
     bool est_on = false;
-    if constexpr (DR) est_on = E.est != (double *)0;   // the filters advance every 2 kHz tick, so the stateless part runs every tick too
+    if constexpr (EST) est_on = E.est != (double *)0;   // the filters advance every 2 kHz tick, so the stateless part runs every tick too
     if (obs && (tick == nticks - 1 || est_on)) {
       LANES
         if (l < 10) { obs[OB_MPOS + l] = cst[CS_DPOS + l]; obs[OB_MVEL + l] = cst[CS_DVEL + l]; obs[OB_MTORQUE + l] = cst[CS_DTORQUE + l]; }
@@ -1809,7 +1809,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         }
       ENDL
       // ---- state_output_step, spring-force model and filters: the warp-parallel stage above (extended instance only)
-      if constexpr (DR) { if (est_on) est_stage<real>(sm, cst, obs, E.est); }
+      if constexpr (EST) { if (est_on) est_stage<real>(sm, cst, obs, E.est); }
     }
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
