@@ -57,7 +57,7 @@ CONFIGS = {
     5: dict(envs=8192, model='cassie_tray_box', name='config5: 8192 envs/GPU cassie_tray_box.xml (5 kg cup on the pelvis tray), random PD gaits f ~ U(0.5,1.5) Hz, A = (.05,.05,.3,.4,.3) rad, L/R phase offset pi, Philox seed 99'),
 }
 # warp instructions per env-step of the dominant kernel, from the committed ncu captures (static: ncu cannot run inside a timed bench)
-INST_PER_ENV_STEP = {2: (26971, 'profiles/r1_step_kernel_v6_ncu_summary.md')}
+INST_PER_ENV_STEP = {2: (26996, 'profiles/r2_step_kernel_plain_ncu_summary.md')}
 
 
 # ------------------------------------------------------------------------------ host CPUs
@@ -523,7 +523,7 @@ def gpu_arm(args, rank, local_rank, world):
                         'obs_allgather_ms': ms_gather},
                 'gpu_launches': launches, 'per_rank': per_rank,
                 'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                             'traffic': 9.29e6 if args.config == 2 else None, 'traffic_source': 'static: dram__bytes_read.sum + write.sum of a single-tick 4096-env launch, profiles/r1_step_kernel_v6_ncu_summary.md',
+                             'traffic': 9.27e6 if args.config == 2 else None, 'traffic_source': 'static: dram__bytes_read.sum + write.sum of a single-tick 4096-env launch, profiles/r2_step_kernel_plain_ncu_summary.md',
                              'peak_source': peak_src, 'bytes_per_env_per_launch': row_bytes, 'ticks_per_launch': 1,
                              'issue': issue,
                              'note': 'issue / latency bound by design (SURVEY 8d): the algorithmic HBM traffic is only the persistent state rows in + out, so the HBM fraction is tiny; the issue-slot fraction is the figure that says how far the kernel is from its bound'},
