@@ -8,6 +8,7 @@
 #include <vector>
 #include "devmodel.h"
 #include "model.h"
+#include "cassie_tree_gen.inc"
 
 namespace cassie {
 
@@ -277,6 +278,10 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
       for (int r = 1; r < n && ok; r++) { const int pa = m.dof_parentid[first + r], pb = m.dof_parentid[j + r]; ok = pa >= first && pb == pa + n; }
       if (ok && first == 6 && n == 13 && !std::getenv("CASSIE_B200_NOSYM")) { d.sym_on = 1; d.sym_first = first; d.sym_n = n; d.sym_madr = m.dof_Madr[j] - m.dof_Madr[first]; }   // the unrolled products are written for the Cassie tree (6 + 13 + 13)
     }
+    { static const int sigp[32] = CT19_SIG_PARENT, sigm[32] = CT19_SIG_MADR;   // the tree the straight-line row transform was generated for
+      bool same = d.sym_on && nv2 == 32 && d.sym_first == 6 && d.sym_n == 13;
+      for (int i = 0; i < 32 && same; i++) same = m.dof_parentid[i] == sigp[i] && m.dof_Madr[i] == sigm[i];
+      d.spec19 = (same && !std::getenv("CASSIE_B200_NOSPEC")) ? 1 : 0; }
     for (int b = 0; b < m.nbody; b++) { int sd = 0; const int ld = d.body_lastdof[b];
       if (d.sym_on && ld >= d.sym_first) sd = ld < d.sym_first + d.sym_n ? 1 : 2;
       d.body_side[b] = (unsigned char)sd; }

@@ -60,6 +60,7 @@ struct DevModel {
   // mirror symmetry of the dof tree (two identical legs below a common base chain): lets the row transform and the A = Y Y' products skip the
   // leg a constraint row does not touch.  body_side: 0 base / world / extra body, 1 first leg, 2 second leg
   int sym_on, sym_first, sym_n, sym_madr;
+  int spec19, padsp[3];   // the dof tree is the one csrc/cassie_tree_gen.inc was generated for: single-leg rows take the straight-line transform
   unsigned char body_side[MB];
   // ---- joints
   int jnt_type[MJ], jnt_qposadr[MJ], jnt_dofadr[MJ], jnt_body[MJ], jnt_limited[MJ];

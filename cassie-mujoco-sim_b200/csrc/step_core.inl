@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "devmodel.h"
+#include "cassie_tree_gen.inc"
 
 #ifdef CASSIE_EMU
 #define CFN inline
@@ -36,6 +37,7 @@
 #define ALLMAX(v) do { auto s_ = v[0]; for (int i_ = 1; i_ < 32; ++i_) s_ = s_ > v[i_] ? s_ : v[i_]; for (int i_ = 0; i_ < 32; ++i_) v[i_] = s_; } while (0)
 #define BCAST(dst, src, lane) do { auto s_ = src[lane]; for (int i_ = 0; i_ < 32; ++i_) dst[i_] = s_; } while (0)
 #define EXSCAN_INT(v, total) do { int a_ = 0; for (int i_ = 0; i_ < 32; ++i_) { int t_ = v[i_]; v[i_] = a_; a_ += t_; } total = a_; } while (0)
+#define SHFLV(dst, src, idx) do { auto t0_ = src[0]; decltype(t0_) t_[32]; for (int l = 0; l < 32; ++l) t_[l] = src[(idx)]; for (int l = 0; l < 32; ++l) dst[l] = t_[l]; } while (0)
 #define BALLOT(mask, v) do { uint32_t m_ = 0; for (int i_ = 0; i_ < 32; ++i_) if (v[i_]) m_ |= 1u << i_; mask = m_; } while (0)
 #else
 #define CFN __device__ __forceinline__
@@ -57,6 +59,7 @@
 #define ALLSUM(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o_); } while (0)
 #define ALLMAX(v) do { for (int o_ = 16; o_ > 0; o_ >>= 1) v = mmax(v, __shfl_xor_sync(0xffffffffu, v, o_)); } while (0)
 #define BCAST(dst, src, lane) dst = __shfl_sync(0xffffffffu, src, lane)
+#define SHFLV(dst, src, idx) dst = __shfl_sync(0xffffffffu, src, idx)
 #define BALLOT(mask, v) mask = __ballot_sync(0xffffffffu, v)
 #define EXSCAN_INT(v, total) do { int x_ = v; for (int o_ = 1; o_ < 32; o_ <<= 1) { int y_ = __shfl_up_sync(0xffffffffu, x_, o_); if (l >= o_) x_ += y_; } total = __shfl_sync(0xffffffffu, x_, 31); v = x_ - v; } while (0)
 #endif
@@ -263,12 +266,27 @@ template <typename real> CFN void sweep_l(const DevModel<real> &cm, const real *
     LANES_NS if ((L(ancl) >> j) & 1u) { L(x) -= sm[L(ptr)] * L(xi); L(ptr) -= 1; } ENDL_NS
   }
 }
+// the same two sweeps for the tree csrc/cassie_tree_gen.inc was generated for: straight-line steps with the two mirrored legs walked side by side
+// (19 dependent steps instead of 31: leg lanes take their own leg's value through a per-lane shuffle source, base lanes take both)
+#define LNAME_(v) L(v)
+template <typename real> CFN void sweep_lt_spec(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+  DECL_LANE
+  LV(real, xi); LV(real, xj); LV(uint32_t, qbit); LV(int, lsel); LV(int, po);
+  LANES_NS { const int leg2 = l >= 19 ? 1 : 0; L(lsel) = leg2 ? 13 : 0; L(qbit) = l < 6 ? 0x80000000u : 1u << (l - 6 - L(lsel)); L(po) = S_QLD - cm.dof_depth[l] + (leg2 ? CT19_SYM_MADR : 0); } ENDL_NS
+  CT19_SWEEP_LT(x, xi, xj, SHFLV, BCAST, LANES_NS, ENDL_NS, LNAME_, sm, L(qbit), L(lsel), L(po), S_QLD);
+}
+template <typename real> CFN void sweep_l_spec(const DevModel<real> &cm, const real *sm, LP(real, x)) {
+  DECL_LANE
+  LV(real, xi); LV(uint32_t, qbit); LV(int, lsel); LV(int, pr);
+  LANES_NS { const int leg2 = l >= 19 ? 1 : 0; L(lsel) = leg2 ? 13 : 0; L(qbit) = l < 6 ? 0u : 1u << (l - 6 - L(lsel)); L(pr) = S_QLD + cm.dof_Mrow[l]; } ENDL_NS
+  CT19_SWEEP_L(x, xi, SHFLV, BCAST, LANES_NS, ENDL_NS, LNAME_, sm, L(qbit), L(lsel), L(pr));
+}
 // x <- inv(L'DL) x
 template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *sm, LP(real, x)) {
   DECL_LANE
-  sweep_lt(cm, sm, x);
+  if (cm.spec19) sweep_lt_spec(cm, sm, x); else sweep_lt(cm, sm, x);
   LANES_NS if (l < cm.nv) L(x) *= sm[S_DINV + l]; ENDL_NS
-  sweep_l(cm, sm, x);
+  if (cm.spec19) sweep_l_spec(cm, sm, x); else sweep_l(cm, sm, x);
 }
 
 // closest point on triangle abc to p (Ericson, Real-Time Collision Detection 5.1.5); true when it lies strictly inside the face
@@ -1113,6 +1131,19 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
         if (r < nefc) {
           const int sd = (int)efc[4 * r + E_SIDE]; if (pass == 0) L(side) = symrows ? sd : 3;
           real *yy = Y + r * ys; real jv = 0, ja = 0, jw = 0;
+          // single-leg rows on the tree csrc/cassie_tree_gen.inc was generated for: the row's 19 possibly non-zero entries (base chain + its leg) are held in
+          // registers from here to the end of the transform; the other leg's entries are exact zeros and stay untouched in shared memory
+          const bool spec = symrows && cm.spec19;
+          const int loff = sd == 2 ? 13 : 0;
+          real y19[19];
+          if (spec) {
+#pragma unroll
+            for (int d = 0; d < 6; ++d) y19[d] = yy[d];
+#pragma unroll
+            for (int d = 0; d < 13; ++d) y19[6 + d] = yy[6 + loff + d];
+#pragma unroll
+            for (int d = 0; d < 19; ++d) { const int dd = d < 6 ? d : d + loff; const real y = y19[d]; jv += y * vecs[dd]; ja += y * vecs[32 + dd]; jw += y * vecs[64 + dd]; }
+          } else
           for (int d = 0; d < nv; ++d) { const real y = yy[d]; jv += y * vecs[d]; ja += y * vecs[32 + d]; jw += y * vecs[64 + d]; }
           if (xb >= 0) for (int d = 0; d < 6; ++d) { const real y = yy[32 + d]; jv += y * vecs[160 + d]; ja += y * vecs[166 + d]; jw += y * vecs[172 + d]; }
           const int src = (int)efc[4 * r + E_SRC]; const real pos = efc[4 * r + E_POS]; const bool ineq = efc[4 * r + E_INEQ] != 0;
@@ -1136,7 +1167,20 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
           if (pass == 0) L(f0) = f; else L(f1) = f;
           if (dbg) { dbg[D_EFC_AREF + r] = aref; dbg[D_EFC_R + r] = Rr; dbg[D_EFC_B + r] = ja - aref; }
           // ---- Y row <- sqrt(inv(D)) inv(L') J row  (mj_solveM2), in place; all lanes (rows) walk the same (i, ancestor) sequence
-          real ad = symrows ? half_solve_row_sym(cm, sm, yy, sd == 2 ? cm.sym_n : 0) : half_solve_row(cm, sm, yy, nv);
+          real ad;
+          if (spec) {
+            const real *qLb = sm + S_QLD, *qLl = sm + S_QLD + (sd == 2 ? cm.sym_madr : 0);
+#define Y19_(i) y19[i]
+#define LB19_(a) qLb[a]
+#define LL19_(a) qLl[a]
+            CT19_TRANSFORM(Y19_, LB19_, LL19_, real);
+#undef Y19_
+#undef LB19_
+#undef LL19_
+            ad = 0;
+#pragma unroll
+            for (int d = 0; d < 19; ++d) { const int dd = d < 6 ? d : d + loff; const real v = y19[d] * sm[S_DSQI + dd]; yy[dd] = v; ad += v * v; }
+          } else ad = symrows ? half_solve_row_sym(cm, sm, yy, sd == 2 ? cm.sym_n : 0) : half_solve_row(cm, sm, yy, nv);
           if (xb >= 0) for (int d = 0; d < 6; ++d) { const real v = yy[32 + d] * (d < 3 ? xb_dsqi_t : cm.xb_dsqi[d]); yy[32 + d] = v; ad += v * v; }
           // packed row constants for the solver: b, 1/A, A, +-R (sign bit set = inequality row)
           real *rc = efc + 4 * r; const real Ad = ad + Rr;
@@ -1295,7 +1339,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     // ---- qacc = qacc_smooth + inv(L) D^-1/2 z ;  qfrc_constraint = J'f = L' D^1/2 z
     LV(real, w);
     LANES L(w) = (l < nv) ? L(z) * sm[S_DSQI + l] : real(0); ENDL
-    sweep_l(cm, sm, w);
+    if (cm.spec19) sweep_l_spec(cm, sm, w); else sweep_l(cm, sm, w);
     LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; if (xb >= 0 && l < 6) L(xqacc) = L(xqacc_smooth) + L(xz) * (l < 3 ? xb_dsqi_t : cm.xb_dsqi[l]); ENDL
     if (dbg) {  // qfrc_constraint = M (qacc - qacc_smooth); only the debug dump wants it (the Euler stage below does not)
       LANES vecs[128 + l] = L(w); ENDL

@@ -16,7 +16,7 @@ D = dict(XPOS=0, XQUAT=96, CDOF=224, QM=416, QLD=736, BIAS=1056, PASSIVE=1088, S
 
 def build(force=False):
     srcs = [os.path.join(HERE, 'emu', 'emu.cpp'), os.path.join(CSRC, 'mjcf.cpp'), os.path.join(CSRC, 'step_core.inl'),
-            os.path.join(CSRC, 'devmodel.h'), os.path.join(CSRC, 'devbuild.h'), os.path.join(CSRC, 'model.h'), os.path.join(CSRC, 'estimator_host.h')]
+            os.path.join(CSRC, 'devmodel.h'), os.path.join(CSRC, 'devbuild.h'), os.path.join(CSRC, 'model.h'), os.path.join(CSRC, 'estimator_host.h'), os.path.join(CSRC, 'cassie_tree_gen.inc')]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
