@@ -227,12 +227,16 @@ template <typename real> struct Batch : BatchBase {
   std::vector<real> h_tmp;
   real *pin_pd = nullptr, *pin_obs = nullptr, *pin_task = nullptr;   // pinned staging for the AoS entry point
   real *dpin_pd = nullptr, *dpin_obs = nullptr;                      // the same buffers as the device sees them (mapped)
+  static constexpr int AOS_MAXC = 4;
+  cudaEvent_t aos_done[AOS_MAXC] = {}, aos_start = nullptr;            // the AoS entry point's chunk launches: completion events,
+  cudaStream_t aos_stream[AOS_MAXC] = {};                              // their streams
   bool task_from_aos = false;   // the task-PD rows were created by the AoS entry point's forwarding (not by cassie_batch_set_task_pd)
   float *d_hfield = nullptr; unsigned char *d_mask = nullptr; DevModel<real> h_model_copy{}; int geom_dev[256]; void *d_row = nullptr;
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_model); cudaFree(A.qpos); cudaFree(A.qvel); cudaFree(A.qacc_ws); cudaFree(A.cst); cudaFree(A.pd); cudaFree(A.xfrc); cudaFree(A.obs); cudaFree(A.dbg);
     cudaFree(A.dfilt); cudaFree(A.counters); cudaFree(A.qM); cudaFree(A.ticket); cudaFree(A.aux); cudaFree(A.cenv); cudaFree(A.task); cudaFree(A.gait); cudaFree(A.est); if (pin_task) cudaFreeHost(pin_task); cudaFree(d_mask); cudaFree(d_row);
+    for (int i = 0; i < AOS_MAXC; i++) { if (aos_done[i]) cudaEventDestroy(aos_done[i]); if (aos_stream[i]) cudaStreamDestroy(aos_stream[i]); } if (aos_start) cudaEventDestroy(aos_start);
     if (pin_pd) cudaFreeHost(pin_pd); if (pin_obs) cudaFreeHost(pin_obs); if (d_hfield) cudaFree(d_hfield);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -383,21 +387,20 @@ template <typename real> struct Batch : BatchBase {
   bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) override {
     CUDA_OK(cudaSetDevice(device));
     static const int aos_threads = [] { const char *e = getenv("CASSIE_B200_AOS_THREADS"); int t = e ? atoi(e) : 32; const int hw = effective_cpus(); if (t > hw) t = hw; return t < 1 ? 1 : t; }();   // host pack / unpack threads
-    if (!pin_pd) {   // pinned AND mapped: the step kernel itself reads the PD rows from / writes the observation rows to these buffers
+    static const bool aos_events = getenv("CASSIE_B200_AOS_EVENTS") != nullptr;
+    static const bool aos_obs_dma = [] { const char *e = getenv("CASSIE_B200_AOS_OBS_DMA"); return e && atoi(e) != 0; }();
+    static const int aos_chunks = [] { const char *e = getenv("CASSIE_B200_AOS_CHUNKS"); int t = e ? atoi(e) : 2; return t < 1 ? 1 : (t > AOS_MAXC ? AOS_MAXC : t); }();   // launches per call for batches of up to two rounds
+    if (!pin_pd) {   // pinned AND mapped: the step kernel itself writes the observation rows into pin_obs
       CUDA_OK(cudaHostAlloc(&pin_pd, sizeof(real) * n * PD_W, cudaHostAllocMapped)); CUDA_OK(cudaHostAlloc(&pin_obs, sizeof(real) * n * OBS_W, cudaHostAllocMapped));
       CUDA_OK(cudaHostGetDevicePointer(&dpin_pd, pin_pd, 0)); CUDA_OK(cudaHostGetDevicePointer(&dpin_obs, pin_obs, 0));
+      for (int i = 0; i < AOS_MAXC; i++) { CUDA_OK(cudaEventCreateWithFlags(&aos_done[i], cudaEventDisableTiming)); CUDA_OK(cudaStreamCreateWithFlags(&aos_stream[i], cudaStreamNonBlocking)); }
+      CUDA_OK(cudaEventCreateWithFlags(&aos_start, cudaEventDisableTiming));
     }
-    const auto tp0 = std::chrono::steady_clock::now();
-#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
-    for (int e = 0; e < n; e++) {
-      real *row = pin_pd + (size_t)e * PD_W; const pd_in_t *u = pd_in + e;
-      for (int i = 0; i < 10; i++) {
-        const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; const int k = i % 5;
-        row[i] = (real)p->torque[k]; row[10 + i] = (real)p->pTarget[k]; row[20 + i] = (real)p->dTarget[k]; row[30 + i] = (real)p->pGain[k]; row[40 + i] = (real)p->dGain[k];
-      }
-      row[50] = row[51] = 0;
-    }
-    {  // taskPd branch of pd_in_t: rows are uploaded only while some environment uses it
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    double t_pack = 0, t_wait = 0, t_unpack = 0;
+    auto tq = now();
+    {  // taskPd branch of pd_in_t: rows are uploaded only while some environment uses it (whole batch, before the first launch)
       int any = 0;
 #pragma omp parallel for schedule(static) num_threads(aos_threads) reduction(| : any) if (n >= 512)
       for (int e = 0; e < n; e++) { const pd_task_in_t *t[2] = {&pd_in[e].leftLeg.taskPd, &pd_in[e].rightLeg.taskPd};
@@ -413,26 +416,59 @@ template <typename real> struct Batch : BatchBase {
         CUDA_OK(cudaMemcpyAsync(A.task, pin_task, sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream));
       } else if (A.task && task_from_aos) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; task_from_aos = false; }   // rows installed with cassie_batch_set_task_pd stay
     }
-    const auto tp1 = std::chrono::steady_clock::now();
     // cassie_sim_step_pd runs state_output_step in every call (src/cassiemujoco.c:1156): so does the batched entry point, inside the kernel,
     // from the first call that asks for state_out_t rows (unless the caller switched it off or runs the host-side checker instead)
     if (state_out && est_auto && !A.est && !est_filter && !enable_estimator_device(true)) return false;
-    static const bool aos_events = getenv("CASSIE_B200_AOS_EVENTS") != nullptr;
-    if (aos_events) { if (!aos_ev[0]) for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&aos_ev[i])); CUDA_OK(cudaEventRecord(aos_ev[0], stream)); }
-    CUDA_OK(cudaMemcpyAsync(A.pd, pin_pd, sizeof(real) * n * PD_W, cudaMemcpyHostToDevice, stream));   // one DMA: a burst of small PCIe reads from every warp at kernel start measured slower
-    A.pd_host = nullptr; A.obs_host = state_out ? dpin_obs : nullptr;
-    if (aos_events) CUDA_OK(cudaEventRecord(aos_ev[1], stream));
-    const bool launched = step(1, 0);
-    if (aos_events) CUDA_OK(cudaEventRecord(aos_ev[2], stream));
-    A.pd_host = nullptr; A.obs_host = nullptr;
-    if (!launched) return false;
-    if (!state_out) return sync();
-    CUDA_OK(cudaStreamSynchronize(stream));
-    const auto tp2 = std::chrono::steady_clock::now();
     if (est_filter && est_state.size() != (size_t)n) est_state.assign((size_t)n, cassie::EstimatorFilter());
-    const bool dev_est = A.est != nullptr;   // the estimator ran inside the kernel: its outputs are columns of the observation row
+    const bool dev_est = A.est != nullptr;   // the estimator runs inside the kernel: its outputs are columns of the observation row
+    // The batch is stepped as up to AOS_MAXC independent launches ("chunks") on their own streams: the host packs chunk c + 1 while chunk c is copied in
+    // and stepping, and unpacks chunk c while the later ones are stepping; the kernels of consecutive chunks overlap at their edges (a chunk's CTAs start
+    // on the SMs the previous chunk's CTAs have left, while its last observation rows are still draining over PCIe).  Chunks are whole rounds of the
+    // resident warps when the batch is worked off in more than two rounds, equal parts otherwise.
+    const int inst = (A.cenv || A.aux || A.task) ? 1 : (A.est ? 2 : 0), slots = cfg[inst].resident_ctas * cfg[inst].wpb;
+    int nchunk = 1, c0[AOS_MAXC + 1] = {0};
+    if (state_out && n >= 1024 && aos_chunks > 1) {
+      if (n <= 2 * slots) { nchunk = aos_chunks; for (int c = 1; c < nchunk; c++) c0[c] = (int)((size_t)n * c / nchunk + 31) / 32 * 32; }
+      else { const int rounds = (n + slots - 1) / slots; nchunk = rounds < AOS_MAXC ? rounds : AOS_MAXC; const int per = (rounds + nchunk - 1) / nchunk * slots;
+        for (int c = 1; c < nchunk; c++) c0[c] = per * c < n ? per * c : n; }
+    }
+    c0[nchunk] = n;
+    CUDA_OK(cudaEventRecord(aos_start, stream));   // everything enqueued on the batch's stream so far happens before the chunks
+    t_pack += sec(tq, now());
+    for (int c = 0; c < nchunk; c++) {
+      const int e0 = c0[c], e1 = c0[c + 1], cnt = e1 - e0; if (cnt <= 0) { CUDA_OK(cudaEventRecord(aos_done[c], stream)); continue; }
+      tq = now();
 #pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
-    for (int e = 0; e < n; e++) {
+      for (int e = e0; e < e1; e++) {
+        real *row = pin_pd + (size_t)e * PD_W; const pd_in_t *u = pd_in + e;
+        for (int i = 0; i < 10; i++) {
+          const pd_motor_in_t *p = i < 5 ? &u->leftLeg.motorPd : &u->rightLeg.motorPd; const int k = i % 5;
+          row[i] = (real)p->torque[k]; row[10 + i] = (real)p->pTarget[k]; row[20 + i] = (real)p->dTarget[k]; row[30 + i] = (real)p->pGain[k]; row[40 + i] = (real)p->dGain[k];
+        }
+        row[50] = row[51] = 0;
+      }
+      t_pack += sec(tq, now());
+      const size_t off = (size_t)e0 * PD_W; cudaStream_t cs = nchunk > 1 ? aos_stream[c] : stream;
+      if (nchunk > 1) CUDA_OK(cudaStreamWaitEvent(cs, aos_start, 0));
+      if (aos_events && c == 0) { if (!aos_ev[0]) for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&aos_ev[i])); CUDA_OK(cudaEventRecord(aos_ev[0], cs)); }
+      CUDA_OK(cudaMemcpyAsync(A.pd + off, pin_pd + off, sizeof(real) * cnt * PD_W, cudaMemcpyHostToDevice, cs));   // one DMA per launch: a burst of small PCIe reads from every warp at kernel start measured no faster
+      if (aos_events && c == 0) CUDA_OK(cudaEventRecord(aos_ev[1], cs));
+      A.pd_host = nullptr; A.obs_host = (state_out && !aos_obs_dma) ? dpin_obs : nullptr;   // observation rows return by zero-copy stores as each environment finishes ...
+      const bool launched = step_range(1, 0, e0, cnt, cs);
+      A.obs_host = nullptr;
+      if (!launched) return false;
+      if (state_out && aos_obs_dma) CUDA_OK(cudaMemcpyAsync(pin_obs + (size_t)e0 * OBS_W, A.obs + (size_t)e0 * OBS_W, sizeof(real) * cnt * OBS_W, cudaMemcpyDeviceToHost, cs));   // ... or by one DMA per chunk
+      CUDA_OK(cudaEventRecord(aos_done[c], cs));
+      if (nchunk > 1) CUDA_OK(cudaStreamWaitEvent(stream, aos_done[c], 0));   // later work on the batch's stream sees the stepped rows
+      if (aos_events && c == nchunk - 1) CUDA_OK(cudaEventRecord(aos_ev[2], cs));
+    }
+    if (!state_out) return sync();
+    for (int c = 0; c < nchunk; c++) {
+      tq = now();
+      CUDA_OK(cudaEventSynchronize(aos_done[c]));
+      t_wait += sec(tq, now()); tq = now();
+#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
+      for (int e = c0[c]; e < c0[c + 1]; e++) {
       // every field of state_out_t is written exactly once (no memset pass): what the reference's block never writes (externalMoment,
       // terrain.slope, battery.current) is zero, as in a freshly set-up state_output_t
       const real *o = pin_obs + (size_t)e * OBS_W; state_out_t *y = state_out + e; const real *eo = o + OB_EST_OUT;
@@ -463,10 +499,11 @@ template <typename real> struct Batch : BatchBase {
       for (int i = 0; i < 16; i++) y->radio.channel[i] = radio[(size_t)e * 16 + i];
       memset(&y->radio.signalGood, 0, sizeof(double)); y->radio.signalGood = true;   // the bool and its padding
       y->battery.stateOfCharge = 1; y->battery.current = 0;
+      }
+      t_unpack += sec(tq, now());
     }
-    { const auto tp3 = std::chrono::steady_clock::now(); auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
-      aos_t[0] += sec(tp0, tp1); aos_t[1] += sec(tp1, tp2); aos_t[2] += sec(tp2, tp3); aos_t[3] += 1;
-      if (aos_events) { float a = 0, b = 0; cudaEventElapsedTime(&a, aos_ev[0], aos_ev[1]); cudaEventElapsedTime(&b, aos_ev[1], aos_ev[2]); aos_t[4] += a; aos_t[5] += b; } }
+    aos_t[0] += t_pack; aos_t[1] += t_wait; aos_t[2] += t_unpack; aos_t[3] += 1;
+    if (aos_events) { float a = 0, b = 0; cudaEventElapsedTime(&a, aos_ev[0], aos_ev[1]); cudaEventElapsedTime(&b, aos_ev[1], aos_ev[2]); aos_t[4] += a; aos_t[5] += b; }
     return true;
   }
   // K terrains of nrow*ncol normalised elevations; environment e stands on terrain e % K (cassie_sim_set_hfielddata, src/cassiemujoco.c:2076-2080)
@@ -587,7 +624,8 @@ template <typename real> struct Batch : BatchBase {
     CUDA_OK(cudaMemset2DAsync(A.dfilt + DF_TICK, sizeof(int) * DFILT_W, 0, sizeof(int), n, stream)); CUDA_OK(cudaStreamSynchronize(stream));
     return true;
   }
-  bool step(int nticks, int mode) override {
+  bool step(int nticks, int mode) override { return step_range(nticks, mode, 0, n, stream); }
+  bool step_range(int nticks, int mode, int env0, int count, cudaStream_t on) {   // the launch covers environments [env0, env0 + count)
     CUDA_OK(cudaSetDevice(device));
     if (mode == 2 && !A.aux) { set_err("query needs the derived-quantity rows (cassie_batch_enable_aux)"); return false; }
     A.nsub = nsub_override;
@@ -596,9 +634,10 @@ template <typename real> struct Batch : BatchBase {
     const int ext = (A.cenv || A.aux || A.task || mode == 3) ? 1 : (A.est ? 2 : 0);
     A.warp_stride = (int)warp_bytes<real>(A.ystride, ext == 1);
     const LaunchCfg &c = cfg[ext];
-    int grid = (n + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
-    { const DevModel<real> *dm = d_model; void *args[4] = {(void *)&dm, (void *)&A, (void *)&nticks, (void *)&mode};
-      CUDA_OK(cudaLaunchKernel(step_entry<real>(ext, feat), dim3(grid), dim3(32 * c.wpb), args, c.smem, stream)); }
+    int grid = (count + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
+    EnvArrays<real> La = A; La.env0 = env0; La.n = count;   // the argument block of this launch
+    { const DevModel<real> *dm = d_model; void *args[4] = {(void *)&dm, (void *)&La, (void *)&nticks, (void *)&mode};
+      CUDA_OK(cudaLaunchKernel(step_entry<real>(ext, feat), dim3(grid), dim3(32 * c.wpb), args, c.smem, on)); }
     launches++;
     CUDA_OK(cudaGetLastError());
     return true;

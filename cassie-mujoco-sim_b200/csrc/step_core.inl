@@ -198,6 +198,18 @@ template <typename real> CFN void make_frame(real *f) {
 // in-place factorisation of sm[S_QLD..] (already holding M); writes 1/D and 1/sqrt(D)
 // q2 (optional): a second matrix of the same sparsity (M + h B for the implicit-damping Euler step) factored in the same pass: the schedule
 // decode and the loop overhead are shared; every entry sees exactly the operations a separate factorisation would apply
+// four consecutive reals of a 16-byte aligned shared-memory record in one (fp32) or two (fp64) 128-bit loads
+template <typename real> struct Row4 { real x, y, z, w; };
+template <typename real> CFN Row4<real> load_row4(const real *p) {
+#ifdef CASSIE_EMU
+  return Row4<real>{p[0], p[1], p[2], p[3]};
+#else
+  Row4<real> r;
+  if (sizeof(real) == 4) { const float4 v = *reinterpret_cast<const float4 *>(p); r.x = (real)v.x; r.y = (real)v.y; r.z = (real)v.z; r.w = (real)v.w; }
+  else { const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2); r.x = (real)a.x; r.y = (real)a.y; r.z = (real)b.x; r.w = (real)b.y; }
+  return r;
+#endif
+}
 template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm, real *q2 = (real *)0) {
   DECL_LANE
   real *qLD = sm + S_QLD, *ftmp = sm + S_VEC + 128, *ftmp2 = sm + S_VEC + 144;
@@ -1235,45 +1247,38 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
       ENDL_NS
       ALLSUM(t0);
       if (LANE0(t0) > 0) { LANES_NS L(f0) = 0; L(res) = L(t1); ENDL_NS }
+      // solver constants repacked for the sweep: slot 2 <- A_ii / 2, slot 3 <- the row's lower bound (0: inequality, -inf: equality)
+      LANES_NS if (l < nefc) { real *rc = efc + 4 * l; rc[2] = real(0.5) * rc[2]; rc[3] = rc[3] < 0 ? real(0) : -(real)INFINITY; } ENDL_NS
+      // One row update = a scalar chain every lane runs redundantly (f_i, its change, the cost change) + one FMA per lane (res += A(.,i) delta).  The
+      // residual of the NEXT row is not fetched from its lane after this row's update (a shuffle on the critical path) but rebuilt by every lane from the
+      // value broadcast one row earlier plus this row's contribution -- the same FMA on the same operands as that lane performs itself.
+      LV(real, rs); LV(real, fs);   // fs: the forces as they stood at the start of the sweep (row i is the only writer of f_i, so f_i is still that value when row i reads it)
+#define PGS_ROW_(i, Ac)                                                                                                              \
+  BCAST(rs, res, (i) + 1 < 32 ? (i) + 1 : 31); BCAST(fb, fs, i);                                                                     \
+  LANES_NS                                                                                                                           \
+    const Row4<real> rc = load_row4(efc + 4 * (i));                                                                                  \
+    const real ainv = rc.y, hAd = rc.z, lo = rc.w, fold = L(fb), resi = L(ri);                                                       \
+    real fnew = mmax(fold - resi * ainv, lo);                                                                                        \
+    real delta = fnew - fold;                                                                                                        \
+    const real change = delta * (hAd * delta + resi);                                                                                \
+    if (change > real(1e-10)) { delta = 0; fnew = fold; } else L(impr) -= change;                                                    \
+    L(res) += (Ac)[l] * delta;                                                                                                       \
+    L(ri) = L(rs) + (Ac)[(i) + 1] * delta;                                                                                           \
+    if (l == (i)) L(f0) = fnew;                                                                                                      \
+  ENDL_NS
       while (iters < cm.iterations) {
-        LANES_NS L(impr) = 0; ENDL_NS
+        LANES_NS L(impr) = 0; L(fs) = L(f0); ENDL_NS
+        BCAST(ri, res, 0);
         {
           const real *Ac = Y + 32 * ys; const int n0 = nefc < 16 ? nefc : 16;
-          for (int i = 0; i < n0; ++i, Ac += ys) {
-          BCAST(ri, res, i); BCAST(fb, f0, i);
-            LANES_NS
-              const real *rc = efc + 4 * i;
-              const real ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb), resi = L(ri);
-              real fnew = fold - resi * ainv;
-              if (Rs < 0) fnew = mmax(fnew, real(0));
-              real delta = fnew - fold;
-              real change = delta * (real(0.5) * delta * Ad + resi);
-              if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
-              L(impr) -= change;
-              L(res) += Ac[l] * delta;
-              if (l == i) L(f0) = fnew;
-            ENDL_NS
-          }
+          for (int i = 0; i < n0; ++i, Ac += ys) { PGS_ROW_(i, Ac) }
           Ac = sm + S_XPOS;
-          for (int i = 16; i < nefc; ++i, Ac += ys) {
-          BCAST(ri, res, i); BCAST(fb, f0, i);
-            LANES_NS
-              const real *rc = efc + 4 * i;
-              const real ainv = rc[1], Ad = rc[2], Rs = rc[3], fold = L(fb), resi = L(ri);
-              real fnew = fold - resi * ainv;
-              if (Rs < 0) fnew = mmax(fnew, real(0));
-              real delta = fnew - fold;
-              real change = delta * (real(0.5) * delta * Ad + resi);
-              if (change > real(1e-10)) { delta = 0; change = 0; fnew = fold; }
-              L(impr) -= change;
-              L(res) += Ac[l] * delta;
-              if (l == i) L(f0) = fnew;
-            ENDL_NS
-          }
+          for (int i = 16; i < nefc; ++i, Ac += ys) { PGS_ROW_(i, Ac) }
         }
         ++iters;
         if (LANE0(impr) * pgs_scale < cm.tolerance) break;
       }
+#undef PGS_ROW_
       LANES_NS L(z) = 0; ENDL_NS
       for (int r = 0; r < nefc; ++r) { BCAST(fb, f0, r); LANES_NS if (l < nv) L(z) += Y[r * ys + l] * L(fb); if (xb >= 0 && l < 6) L(xz) += Y[r * ys + 32 + l] * L(fb); ENDL_NS }
     } else {

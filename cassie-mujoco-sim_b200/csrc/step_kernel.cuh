@@ -11,7 +11,7 @@
 namespace cassie {
 
 template <typename real> struct EnvArrays {
-  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync, nsub, warp_stride; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
+  real *qpos, *qvel, *qacc_ws, *cst, *pd, *xfrc, *obs, *dbg, *qM, *aux, *cenv, *task, *gait; const real *pd_host; real *obs_host; double *est; int *dfilt, *counters, *ticket; const float *hfield; const unsigned char *mask; int cta_sync, nsub, warp_stride, env0; int n, n_terrain, qpos_w, qvel_w, ystride, xb; size_t hfield_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,11 +54,11 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   const int nwarps = blockDim.x >> 5, sync_on = (mode == 0 && (nticks > 1 || (A.cta_sync & 32))) ? (A.cta_sync & 31) : 0;   // bit 5: also in single-tick launches
   const int stride = gridDim.x * nwarps;
   for (int base = blockIdx.x * nwarps; base < A.n; base += stride) {
-    const int env = base + warp;
+    const int env = A.env0 + base + warp;   // a launch covers environments [env0, env0 + n)
     __syncthreads();   // the warps of a CTA start every round together: they then share instruction-cache lines through the round (measured: 16 384
                        // environments, 7 rounds, -20 % without it), and the multi-tick rendezvous counts below assume it
-    { const int nenv = env + stride;   // warm L2 with the next round's state rows of this warp (about 2 KB per environment, one 128-byte line per lane)
-      if (nenv < A.n && mode == 0) {
+    { const int nenv = base + warp + stride < A.n ? env + stride : 0x7fffffff;   // warm L2 with the next round's state rows of this warp (about 2 KB per environment, one 128-byte line per lane)
+      if (nenv != 0x7fffffff && mode == 0) {
         const char *p = nullptr;
         if (l < 6) p = (const char *)(A.cst + (size_t)nenv * CST_W) + 128 * l * (sizeof(real) / 4);
         else if (l < 9) p = (const char *)(A.dfilt + (size_t)nenv * DFILT_W) + 128 * (l - 6);
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
         else if (l == 17) p = (const char *)(A.xfrc + (size_t)nenv * XFRC_W);
         if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
       } }
-    const bool active = env < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
+    const bool active = base + warp < A.n && !(A.mask && !A.mask[env]);   // masked launches (reset / set_const of a subset)
     if (!active) {   // keep the rendezvous count of the working warps
       if (sync_on) { const int per = __popc(sync_on); for (int i = 0; i < nticks * (A.nsub > 0 ? A.nsub : cm.nsub) * per; ++i) __syncthreads(); }
       continue;

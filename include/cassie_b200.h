@@ -42,6 +42,9 @@ double *cassie_sim_qvel(cassie_sim_t *sim);
 int cassie_sim_nv(const cassie_sim_t *sim);
 int cassie_sim_nq(const cassie_sim_t *sim);
 /* include/cassiemujoco.h:263 (src/cassiemujoco.c:1963-1967): xfrc = force xyz, torque xyz in the world frame; unknown name: no-op */
+/* LIMIT of this library: an environment carries ONE (wrench, body) slot.  A call that names another body REPLACES the earlier wrench (the reference
+ * keeps xfrc_applied per body, so several bodies can be pushed at once); cassie_sim_clear_forces empties the slot.  The BASELINE configurations push the
+ * pelvis only. */
 void cassie_sim_apply_force(cassie_sim_t *sim, double xfrc[6], const char *name);
 /* include/cassiemujoco.h:268 (src/cassiemujoco.c:1969-1972) */
 void cassie_sim_clear_forces(cassie_sim_t *sim);

@@ -198,3 +198,28 @@ def test_integrate_pos_kernel(P, prec):
         else:
             want[:, qi] = q[:, qi] + h * v[:, di]; qi += 1; di += 1
     assert np.abs(q1 - want).max() < (1e-12 if prec == 'fp64' else 2e-6)
+
+
+@pytest.mark.parametrize('n', [2085, 5000])
+def test_aos_chunked_launches_equal_one_launch(P, n):
+    """cassie_sim_step_pd_batch steps large batches as several launches on their own streams (host pack / unpack overlapped with the kernels); the result
+    must be, bit for bit, what one launch over the compact rows gives.  2085: two ragged halves; 5000: more than two rounds, chunks of whole rounds."""
+    rng = np.random.default_rng(n)
+    tgt = np.array(PD_TARGET) + rng.uniform(-0.05, 0.05, (n, 10))
+    pd = (P.pd_in_t * n)()
+    for e in range(n):
+        for i in range(5):
+            for leg, off in ((pd[e].leftLeg, 0), (pd[e].rightLeg, 5)):
+                leg.motorPd.pTarget[i] = tgt[e, off + i]; leg.motorPd.pGain[i] = PD_PGAIN[i]; leg.motorPd.dGain[i] = PD_DGAIN[i]
+    a, b = P.CassieBatch(n, precision=P.FP32), P.CassieBatch(n, precision=P.FP32)
+    b.enable_estimator_device(True)      # the AoS entry point switches the in-kernel estimator on by itself: same kernel instance on both sides
+    b.set_pd(P.pd_rows(n, pTarget=tgt, pGain=PD_PGAIN, dGain=PD_DGAIN))
+    for _ in range(25):
+        y = a.step_pd(pd)
+        b.step(1)
+    assert np.array_equal(a.qpos(), b.qpos()) and np.array_equal(a.qvel(), b.qvel())
+    ob = b.obs()
+    for e in (0, n // 2 - 1, n // 2, n // 2 + 1, n - 1, 2071, 2072):
+        assert np.array_equal(np.array(y[e].motor.position, dtype=np.float32), ob[e, P.OBS['motor_pos']].astype(np.float32)), e
+        assert np.array_equal(np.array(y[e].pelvis.orientation, dtype=np.float32), ob[e, P.OBS['est_quat']].astype(np.float32)), e
+    assert np.unique(np.round(a.qpos()[:, 9], 6)).size > n // 4
