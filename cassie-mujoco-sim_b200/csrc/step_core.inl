@@ -212,44 +212,55 @@ template <typename real> CFN Row4<real> load_row4(const real *p) {
 }
 template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm, real *q2 = (real *)0) {
   DECL_LANE
-  real *qLD = sm + S_QLD, *ftmp = sm + S_VEC + 128, *ftmp2 = sm + S_VEC + 144;
-  LV(real, tmp); LV(real, tmp2);
+  real *qLD = sm + S_QLD, *dinv2 = sm + S_VEC + 128;
+  if (cm.nfac > 0) {
+    // Balanced schedule: eliminating dof k means dk(dk+1)/2 independent updates  M(anc_t, .)[c] -= M(k, .)[t + c] * f_t,  f_t = M(k, anc_t) / D_k;  a
+    // precomputed table deals them round-robin to the lanes, two per lane and trip so that their loads overlap.  f_t is formed on the fly from the
+    // still un-normalised row k, which is never written again: the rows are normalised (L = M(k, .) / D_k) in one parallel pass after the last step.
+    // One warp rendezvous per step (the next dof's row must have seen this step's updates).
+    for (int k = cm.nv - 1; k >= 0; --k) {
+      if (cm.dof_depth[k] == 0) continue;
+      const int kk = cm.dof_Madr[k], p0 = cm.fac_start[k], p1 = cm.fac_start[k + 1];
+      const real rinv = mrcp(qLD[kk]), rinv2 = q2 ? mrcp(q2[kk]) : real(0);
+      LANES
+        for (int p = p0 + l; p < p1; p += 64) {
+          const bool two = p + 32 < p1;
+          const uint32_t ea = cm.fac_pairs[p], eb = two ? cm.fac_pairs[p + 32] : ea;
+          const int da = ea & 0xfffu, sa = (ea >> 12) & 0xfffu, ta = kk + (int)(ea >> 24), db = eb & 0xfffu, sb = (eb >> 12) & 0xfffu, tb = kk + (int)(eb >> 24);
+          const real va = qLD[da] - qLD[sa] * (qLD[ta] * rinv), vb = qLD[db] - qLD[sb] * (qLD[tb] * rinv);
+          if (q2) {
+            const real wa = q2[da] - q2[sa] * (q2[ta] * rinv2), wb = q2[db] - q2[sb] * (q2[tb] * rinv2);
+            q2[da] = wa; if (two) q2[db] = wb;
+          }
+          qLD[da] = va; if (two) qLD[db] = vb;
+        }
+      ENDL
+    }
+    LANES if (l < cm.nv) { const real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = mrcp(d); sm[S_DSQI + l] = mrcp(msqrt(d)); if (q2) dinv2[l] = mrcp(q2[cm.dof_Madr[l]]); } ENDL
+    LANES
+      for (int p = l; p < cm.ntri; p += 32) { const uint32_t e = cm.tri[p]; const int i = e >> 24, a = e & 0xffffu; qLD[a] *= sm[S_DINV + i]; if (q2) q2[a] *= dinv2[i]; }
+    ENDL
+    return;
+  }
+  LV(real, tmp);
   for (int k = cm.nv - 1; k >= 0; --k) {
     const int dk = cm.dof_depth[k];
     if (dk == 0) continue;
     const int kk = cm.dof_Madr[k];
-    if (cm.nfac > 0) {
-      // balanced schedule: the dk(dk+1)/2 independent updates  M(anc_t, .)[c] -= M(k, .)[t+c] * f_t  are dealt round-robin to the lanes
-      LANES L(tmp) = 0; L(tmp2) = 0; if (l >= 1 && l <= dk) { L(tmp) = qLD[kk + l] * mrcp(qLD[kk]); ftmp[l] = L(tmp); if (q2) { L(tmp2) = q2[kk + l] * mrcp(q2[kk]); ftmp2[l] = L(tmp2); } } ENDL
-      const int p0 = cm.fac_start[k], p1 = cm.fac_start[k + 1];
-      if (q2) {
-        LANES
-          for (int p = p0 + l; p < p1; p += 32) { const uint32_t e = cm.fac_pairs[p]; const int dst = e & 0xfffu, src = (e >> 12) & 0xfffu, t = e >> 24;
-            qLD[dst] -= qLD[src] * ftmp[t]; q2[dst] -= q2[src] * ftmp2[t]; }
-        ENDL
-        LANES if (l >= 1 && l <= dk) { qLD[kk + l] = L(tmp); q2[kk + l] = L(tmp2); } ENDL
-      } else {
-        LANES
-          for (int p = p0 + l; p < p1; p += 32) { const uint32_t e = cm.fac_pairs[p]; qLD[e & 0xfffu] -= qLD[(e >> 12) & 0xfffu] * ftmp[e >> 24]; }
-        ENDL
-        LANES if (l >= 1 && l <= dk) qLD[kk + l] = L(tmp); ENDL
-      }
-    } else {
-      const uint32_t anc = cm.dof_ancmask[k];
-      for (int pass = 0; pass < (q2 ? 2 : 1); ++pass) {
-        real *Q = pass ? q2 : qLD;
-        LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
-          L(tmp) = 0;
-          if ((anc >> l) & 1u) {
-            const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
-            const real f = Q[kk + t] / Q[kk];
-            const real *rk = Q + kk + t; real *ri = Q + ia;
-            for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
-            L(tmp) = f;
-          }
-        ENDL
-        LANES if ((anc >> l) & 1u) Q[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
-      }
+    const uint32_t anc = cm.dof_ancmask[k];
+    for (int pass = 0; pass < (q2 ? 2 : 1); ++pass) {
+      real *Q = pass ? q2 : qLD;
+      LANES  // lane i (an ancestor of k): row_i -= row_k[t..] * (M(k,i)/M(k,k)),  t = depth(k) - depth(i)
+        L(tmp) = 0;
+        if ((anc >> l) & 1u) {
+          const int di = cm.dof_depth[l], t = dk - di, ia = cm.dof_Madr[l];
+          const real f = Q[kk + t] / Q[kk];
+          const real *rk = Q + kk + t; real *ri = Q + ia;
+          for (int c = 0; c <= di; ++c) ri[c] -= rk[c] * f;
+          L(tmp) = f;
+        }
+      ENDL
+      LANES if ((anc >> l) & 1u) Q[kk + dk - cm.dof_depth[l]] = L(tmp); ENDL
     }
   }
   LANES if (l < cm.nv) { const real d = qLD[cm.dof_Madr[l]]; sm[S_DINV + l] = mrcp(d); sm[S_DSQI + l] = mrcp(msqrt(d)); } ENDL
@@ -1436,7 +1447,13 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   // (M + hB) a = qfrc_smooth + qfrc_constraint = M qacc   =>   a = qacc - c  with  (M + hB) c = hB qacc  (exact; no J'f needed).
   LV(real, a);
   if (cm.has_damping || ce) {
-    LANES for (int k = l; k < cm.nM; k += 32) qLD[k] = qM[NM_MAX + k]; ENDL   // the factor of M is dead: its buffer takes the factor of M + h B
+    LANES   // the factor of M is dead: its buffer takes the factor of M + h B.  All loads first, then the stores: one L2 round trip instead of nM / 32 dependent ones
+      real t[NM_MAX / 32];
+#pragma unroll
+      for (int j = 0; j < NM_MAX / 32; ++j) { const int k = l + 32 * j; t[j] = k < cm.nM ? qM[NM_MAX + k] : real(0); }
+#pragma unroll
+      for (int j = 0; j < NM_MAX / 32; ++j) { const int k = l + 32 * j; if (k < cm.nM) qLD[k] = t[j]; }
+    ENDL
     LANES if (l < nv) sm[S_DINV + l] = mrcp(qLD[cm.dof_Madr[l]]); ENDL
     LANES L(a) = (l < nv) ? cm.timestep * ddamp[l] * L(qacc) : real(0); ENDL
     solve_m(cm, sm, a);
@@ -1726,21 +1743,44 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
   for (int tick = 0; tick < nticks; ++tick) {
     if (forward_only) { LANES L(ctrl) = 0; ENDL }
     else {
+    // ---- the controller stage works on a shared-memory copy of the environment's controller rows (sensor / filter state, FIR taps, PD row, observation row):
+    // one burst of independent loads instead of a dozen dependent L2 round trips through the stage's phases.  The copy lives in the kinematics buffers,
+    // which are dead between ticks; the estimator's filter data sits in the constraint-matrix region.
+    real *cs = sm + S_XPOS, *ps = sm + S_XPOS + CST_W + DFILT_W, *os = sm + S_XPOS + CST_W + DFILT_W + 64; int *is = reinterpret_cast<int *>(sm + S_XPOS + CST_W);
+    LANES
+      real t[6], o[4] = {0, 0, 0, 0}; int u[3];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) t[j] = cst[l + 32 * j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) u[j] = ism[l + 32 * j];
+      const real p0 = pd[l], p1 = l + 32 < PD_W ? pd[l + 32] : real(0);
+      if (obs) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (l + 32 * j < OBS_W) o[j] = obs[l + 32 * j];
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) cs[l + 32 * j] = t[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) is[l + 32 * j] = u[j];
+      ps[l] = p0; if (l + 32 < 64) ps[l + 32] = p1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (l + 32 * j < OBS_W) os[l + 32 * j] = o[j];
+    ENDL
     // ---- pd_input_step (motor-PD branch) + cassie_core_sim_step, lane = motor; both read LAST tick's cassie_out
     const real W = real(0.15), DEG = real(0.017453292519943295);
     LANES
       L(tq) = 0; L(scale_part) = 1;
       if (l < 10) {
-        const real pos = cst[CS_DPOS + l], vel = cst[CS_DVEL + l]; const int k = l % 5;
-        real pT = pd[10 + l];
+        const real pos = cs[CS_DPOS + l], vel = cs[CS_DVEL + l]; const int k = l % 5;
+        real pT = ps[10 + l];
         if (gait) pT += gait[GA_AMP + l] * msin(real(6.283185307179586) * gait[GA_FREQ] * ((real)(tick0 + tick) * real(0.0005)) + gait[GA_PHASE + l]);   // open-loop gait (BASELINE config 5)
-        const real u = pd[l] + pd[30 + l] * (pT - pos) + pd[40 + l] * (pd[20 + l] - vel);
+        const real u = ps[l] + ps[30 + l] * (pT - pos) + ps[40 + l] * (ps[20 + l] - vel);
         real add = 0, sc = 1;
         const real dhi = pos - (core_hi_deg<real>(l) * DEG - W), dlo = (core_lo_deg<real>(l) * DEG + W) - pos;
         if (dhi > 0) { add -= core_K<real>(k) * dhi * (1 + dhi / W) + core_C<real>(k) * mmin(dhi / W, real(1)) * vel; sc *= mmax(real(0), 1 - dhi / W); }
         if (dlo > 0) { add += core_K<real>(k) * dlo * (1 + dlo / W) - core_C<real>(k) * mmin(dlo / W, real(1)) * vel; sc *= mmax(real(0), 1 - dlo / W); }
         if (k == 2 || k == 3) {  // coupled row hipPitch + knee >= -135 deg, evaluated by both lanes of the pair
-          const int a = l - k + 2; const real dsum = -135 * DEG - (cst[CS_DPOS + a] + cst[CS_DPOS + a + 1]);
+          const int a = l - k + 2; const real dsum = -135 * DEG - (cs[CS_DPOS + a] + cs[CS_DPOS + a + 1]);
           if (dsum > 0) { add += 1200 * dsum * (1 + dsum / W) - 36 * mmin(dsum / W, real(1)) * vel; if (k == 2) sc *= mmax(real(0), 1 - dsum / W); }
         }
         L(tq) = u; L(ctrl) = add; L(scale_part) = sc;
@@ -1751,7 +1791,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       const real *tk = E.task;
       LANES  // lanes 0..13: sin / cos of the 14 chain angles from LAST tick's cassie_out
         if (l < 14) {
-          const int i = l, sd = i / 7, k = i % 7; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd;
+          const int i = l, sd = i / 7, k = i % 7; const real *mp = cs + CS_DPOS + 5 * sd, *jp = cs + CS_JPOS + 3 * sd;
           real a = k < 3 ? mp[k] : mp[3];
           if (k >= 4) a += jp[0]; if (k >= 5) a += jp[1]; if (k >= 6) a += mp[4];
           real sn, cs; msincos(a, &sn, &cs); vecs[32 + 2 * i] = sn; vecs[33 + 2 * i] = cs;
@@ -1759,7 +1799,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       ENDL
       LANES
         if (l < 2) {
-          const int sd = l; const real *mv = cst + CS_DVEL + 5 * sd, *jv = cst + CS_JVEL + 3 * sd, *t = tk + 30 * sd;
+          const int sd = l; const real *mv = cs + CS_DVEL + 5 * sd, *jv = cs + CS_JVEL + 3 * sd, *t = tk + 30 * sd;
           const real rate[7] = {mv[0], mv[1], mv[2], mv[3], jv[0], jv[1], mv[4]};
           real fo[13], jac[30], x[6], w[6];
           est_foot<real>(sd, vecs + 32 + 14 * sd, rate, fo, jac);
@@ -1777,44 +1817,44 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
     LANES
       if (l < 10) {
         real sc = 1; for (int i = 0; i < 10; ++i) sc *= vecs[i];
-        const bool sto = !(cst[CS_STO] >= 1);
+        const bool sto = !(cs[CS_STO] >= 1);
         real t = sto ? real(0) : L(tq) * sc + L(ctrl);
         const real lim = cm.act_torque_limit[l];
         t = clampr(t, -lim, lim);
         // ---- motor(): torque-speed curve, STO, 6-tick delay line (src/cassiemujoco.c:638-664)
-        const real ratio = cm.act_gear[l], tmax = cm.act_ctrl_hi[l], w = cst[CS_ACTVEL + l];
+        const real ratio = cm.act_gear[l], tmax = cm.act_ctrl_hi[l], w = cs[CS_ACTVEL + l];
         real tlim = 2 * tmax * (1 - mabs(w) / cm.act_wmax[l]); tlim = mmax(mmin(tlim, tmax), real(0));
         if (sto) t = 0;
         real tau = mmin(mabs(t / ratio), tlim); if (t < 0) tau = -tau;
-        real *dl = cst + CS_DELAY + 6 * l;
+        real *dl = cs + CS_DELAY + 6 * l;
         const real c = dl[5];
         for (int k = 5; k > 0; --k) dl[k] = dl[k - 1];
         dl[0] = tau;
         L(ctrl) = c;
-        cst[CS_DTORQUE + l] = c * ratio;
+        cs[CS_DTORQUE + l] = c * ratio;
       } else L(ctrl) = 0;
     ENDL
     // ---- cassie_sensor_data(): encoders + filters from the sensordata of the PREVIOUS physics step (:737-774)
     LANES
       if (l < 10) {  // drive encoder, integer FIR (:558-593)
-        const int s = l < 5 ? l : l + 3, bits = cm.enc_bits[s]; int *x = ism + 9 * l;
+        const int s = l < 5 ? l : l + 3, bits = cm.enc_bits[s]; int *x = is + 9 * l;
         const double TWO_PI = 6.283185307179586;
-        const int enc = (int)((double)cst[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
+        const int enc = (int)((double)cs[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
         const double scale = TWO_PI / (double)(1 << bits) / (double)cm.act_gear[l];
-        cst[CS_DPOS + l] = (real)(enc * scale);
+        cs[CS_DPOS + l] = (real)(enc * scale);
         bool allzero = true; for (int k = 0; k < 9; ++k) allzero &= (x[k] == 0);
         if (allzero) for (int k = 0; k < 9; ++k) x[k] = enc;
         for (int k = 8; k > 0; --k) x[k] = x[k - 1];
         x[0] = enc;
         const int b[9] = {2727, 534, -2658, -795, 72, 110, 19, -6, -3};
         int y = 0; for (int k = 0; k < 9; ++k) y += x[k] * b[k];
-        cst[CS_DVEL + l] = (real)(y * scale / 3.141592653589793);
+        cs[CS_DVEL + l] = (real)(y * scale / 3.141592653589793);
       } else if (l < 16) {  // joint encoder, IIR (:596-635)
-        const int i = l - 10, s = i < 3 ? 5 + i : 10 + i, bits = cm.enc_bits[s]; real *x = cst + (CS_JFX - 40) + 4 * l, *y = cst + (CS_JFY - 30) + 3 * l;   // = CS_JFX + 4 i, CS_JFY + 3 i, written with non-negative terms only
+        const int i = l - 10, s = i < 3 ? 5 + i : 10 + i, bits = cm.enc_bits[s]; real *x = cs + (CS_JFX - 40) + 4 * l, *y = cs + (CS_JFY - 30) + 3 * l;   // = CS_JFX + 4 i, CS_JFY + 3 i, written with non-negative terms only
         const double TWO_PI = 6.283185307179586;
-        const int enc = (int)((double)cst[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
+        const int enc = (int)((double)cs[CS_SENSOR + s] / TWO_PI * (double)(1 << bits));
         const real p = (real)(enc * (TWO_PI / (double)(1 << bits)));
-        cst[CS_JPOS + i] = p;
+        cs[CS_JPOS + i] = p;
         bool allzero = true; for (int k = 0; k < 4; ++k) allzero &= (x[k] == 0);
         if (allzero) for (int k = 0; k < 4; ++k) x[k] = p;
         for (int k = 3; k > 0; --k) x[k] = x[k - 1];
@@ -1822,23 +1862,24 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         for (int k = 2; k > 0; --k) y[k] = y[k - 1];
         real y0 = real(12.348) * (x[0] + x[1] - x[2] - x[3]);
         y0 -= y[1] * real(-1.7658) + y[2] * real(0.79045);
-        y[0] = y0; cst[CS_JVEL + i] = y0;
+        y[0] = y0; cs[CS_JVEL + i] = y0;
       }
     ENDL
     // ---- *y = cassie_out (:1127): the observation of this tick
     bool est_on = false;
     if constexpr (EST) est_on = E.est != (double *)0;   // the filters advance every 2 kHz tick, so the stateless part runs every tick too
-    if (obs && (tick == nticks - 1 || est_on)) {
+    const bool wrote_obs = obs && (tick == nticks - 1 || est_on);
+    if (wrote_obs) {
       LANES
-        if (l < 10) { obs[OB_MPOS + l] = cst[CS_DPOS + l]; obs[OB_MVEL + l] = cst[CS_DVEL + l]; obs[OB_MTORQUE + l] = cst[CS_DTORQUE + l]; }
-        if (l < 6) { obs[OB_JPOS + l] = cst[CS_JPOS + l]; obs[OB_JVEL + l] = cst[CS_JVEL + l]; }
-        if (l < 13) obs[OB_QUAT + l] = cst[CS_SENSOR + 16 + l];
-        if (l == 13) obs[OB_TIME] = cst[CS_TIME];
+        if (l < 10) { os[OB_MPOS + l] = cs[CS_DPOS + l]; os[OB_MVEL + l] = cs[CS_DVEL + l]; os[OB_MTORQUE + l] = cs[CS_DTORQUE + l]; }
+        if (l < 6) { os[OB_JPOS + l] = cs[CS_JPOS + l]; os[OB_JVEL + l] = cs[CS_JVEL + l]; }
+        if (l < 13) os[OB_QUAT + l] = cs[CS_SENSOR + 16 + l];
+        if (l == 13) os[OB_TIME] = cs[CS_TIME];
       ENDL
       // ---- state_output_step, stateless part (closed source, decoded): pelvis orientation / acceleration, foot poses and velocities
       LANES  // lanes 0..13: sin / cos of the 14 chain angles (3 hip angles + 4 cumulative planar angles per leg)
         if (l < 14) {
-          const int i = l, sd = i / 7, k = i % 7; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd;
+          const int i = l, sd = i / 7, k = i % 7; const real *mp = cs + CS_DPOS + 5 * sd, *jp = cs + CS_JPOS + 3 * sd;
           real a = k < 3 ? mp[k] : mp[3];
           if (k >= 4) a += jp[0]; if (k >= 5) a += jp[1]; if (k >= 6) a += mp[4];
           real sn, cs; msincos(a, &sn, &cs); vecs[32 + 2 * i] = sn; vecs[33 + 2 * i] = cs;
@@ -1846,20 +1887,30 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       ENDL
       LANES
         if (l < 2) {
-          const int sd = l; const real *mv = cst + CS_DVEL + 5 * sd, *jv = cst + CS_JVEL + 3 * sd;
+          const int sd = l; const real *mv = cs + CS_DVEL + 5 * sd, *jv = cs + CS_JVEL + 3 * sd;
           const real rate[7] = {mv[0], mv[1], mv[2], mv[3], jv[0], jv[1], mv[4]};
-          est_foot<real>(sd, vecs + 32 + 14 * sd, rate, obs + OB_FOOT + 13 * sd);
+          est_foot<real>(sd, vecs + 32 + 14 * sd, rate, os + OB_FOOT + 13 * sd);
         } else if (l == 2) {
-          const real *q = cst + CS_SENSOR + 16, *w = cst + CS_SENSOR + 20, *a = cst + CS_SENSOR + 23;
+          const real *q = cs + CS_SENSOR + 16, *w = cs + CS_SENSOR + 20, *a = cs + CS_SENSOR + 23;
           real R[9], wr[3], wwr[3]; const real r[3] = {real(0.03155), 0, real(-0.079996)};
           quat2mat(R, q); cross3(wr, w, r); cross3(wwr, w, wr);
-          est_mat2quat(obs + OB_EST_QUAT, R);   // pelvis.orientation: the IMU quaternion through its matrix and back (+-q, mat2quat's sign)
-          for (int k = 0; k < 3; ++k) obs[OB_EST_ACC + k] = a[k] - R[6 + k] * real(9.806) - wwr[k];
+          est_mat2quat(os + OB_EST_QUAT, R);   // pelvis.orientation: the IMU quaternion through its matrix and back (+-q, mat2quat's sign)
+          for (int k = 0; k < 3; ++k) os[OB_EST_ACC + k] = a[k] - R[6 + k] * real(9.806) - wwr[k];
         }
       ENDL
       // ---- state_output_step, spring-force model and filters: the warp-parallel stage above (extended instance only)
-      if constexpr (EST) { if (est_on) est_stage<real>(sm, cst, obs, E.est); }
+      if constexpr (EST) { if (est_on) est_stage<real>(sm, cs, os, E.est); }
     }
+    // ---- flush: the rows' modified ranges go back to their HBM rows before the physics (which writes sensordata / actuator_velocity / time there)
+    LANES
+      for (int i = CS_DPOS + l; i < CS_TIME; i += 32) cst[i] = cs[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { const int i = l + 32 * j; if (i < DF_TICK) ism[i] = is[i]; }
+      if (wrote_obs) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int i = l + 32 * j; if (i < OBS_W) obs[i] = os[i]; }
+      }
+    ENDL
     }
     // ---- mj_step1 + mj_step2, round(5e-4 / timestep) times with ctrl held (:1130-1134)
     const int nsub = forward_only ? 1 : (E.nsub > 0 ? E.nsub : cm.nsub);
