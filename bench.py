@@ -56,8 +56,17 @@ CONFIGS = {
     4: dict(envs=8192, model='cassie_hfield', name='config4: 8192 envs/GPU cassie_hfield.xml, 64 terrains shared round-robin (seed 7, U(0,1) x 0.25 of the 0.2 m scale = 5 cm, flat centre patch), fixed motor-PD targets'),
     5: dict(envs=8192, model='cassie_tray_box', name='config5: 8192 envs/GPU cassie_tray_box.xml (5 kg cup on the pelvis tray), random PD gaits f ~ U(0.5,1.5) Hz, A = (.05,.05,.3,.4,.3) rad, L/R phase offset pi, Philox seed 99'),
 }
-# warp instructions per env-step of the dominant kernel, from the committed ncu captures (static: ncu cannot run inside a timed bench)
-INST_PER_ENV_STEP = {2: (26996, 'profiles/r2_step_kernel_plain_ncu_summary.md')}
+# warp instructions per env-step and DRAM bytes per launch of the dominant kernel, from the committed ncu capture (static: ncu cannot run inside a
+# timed bench).  profiles/r2_step_kernel_counts.json is written by tools/ncu_counts.py from the .ncu-rep the summary next to it was made from.
+def _kernel_counts():
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_step_kernel_counts.json')) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+KERNEL_COUNTS = _kernel_counts()
 
 
 # ------------------------------------------------------------------------------ host CPUs
@@ -500,7 +509,7 @@ def gpu_arm(args, rank, local_rank, world):
         ach = row_bytes * n / (ms_step * 1e-3) / 1e9     # algorithmic bytes of one single-tick launch / its duration
         sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
         issue_peak = 148 * 4 * sm_mhz * 1e6              # warp instructions / s: 148 SMs x 4 schedulers x clock
-        inst, inst_src = INST_PER_ENV_STEP.get(args.config, (None, None))
+        kc = KERNEL_COUNTS.get(str(args.config), {}); inst, inst_src = kc.get('warp_inst_per_env_step'), kc.get('source', 'profiles/r2_step_kernel_counts.json')
         issue = None if inst is None else {'warp_inst_per_env_step': inst, 'source': 'static: ' + inst_src, 'achieved_inst_per_s': inst * value / world, 'peak_inst_per_s': issue_peak,
                                            'frac': inst * value / world / issue_peak, 'sm_mhz': sm_mhz}
         eff = effective_cpus()
@@ -523,7 +532,7 @@ def gpu_arm(args, rank, local_rank, world):
                         'obs_allgather_ms': ms_gather},
                 'gpu_launches': launches, 'per_rank': per_rank,
                 'roofline': {'kernel': 'cassie_step_kernel<float>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                             'traffic': 9.27e6 if args.config == 2 else None, 'traffic_source': 'static: dram__bytes_read.sum + write.sum of a single-tick 4096-env launch, profiles/r2_step_kernel_plain_ncu_summary.md',
+                             'traffic': kc.get('dram_bytes_per_launch'), 'traffic_source': 'static: dram__bytes_read.sum + write.sum of one single-tick launch of this config under ncu --set full (cold caches), ' + str(inst_src),
                              'peak_source': peak_src, 'bytes_per_env_per_launch': row_bytes, 'ticks_per_launch': 1,
                              'issue': issue,
                              'note': 'issue / latency bound by design (SURVEY 8d): the algorithmic HBM traffic is only the persistent state rows in + out, so the HBM fraction is tiny; the issue-slot fraction is the figure that says how far the kernel is from its bound'},

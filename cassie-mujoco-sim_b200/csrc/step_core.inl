@@ -222,6 +222,16 @@ template <typename real> CFN void factor_ld(const DevModel<real> &cm, real *sm, 
       if (cm.dof_depth[k] == 0) continue;
       const int kk = cm.dof_Madr[k], p0 = cm.fac_start[k], p1 = cm.fac_start[k + 1];
       const real rinv = mrcp(qLD[kk]), rinv2 = q2 ? mrcp(q2[kk]) : real(0);
+      if (p1 - p0 <= 32) {   // the shallow dofs: one update per lane
+        LANES
+          if (p0 + l < p1) {
+            const uint32_t ea = cm.fac_pairs[p0 + l]; const int da = ea & 0xfffu, sa = (ea >> 12) & 0xfffu, ta = kk + (int)(ea >> 24);
+            if (q2) q2[da] -= q2[sa] * (q2[ta] * rinv2);
+            qLD[da] -= qLD[sa] * (qLD[ta] * rinv);
+          }
+        ENDL
+        continue;
+      }
       LANES
         for (int p = p0 + l; p < p1; p += 64) {
           const bool two = p + 32 < p1;
