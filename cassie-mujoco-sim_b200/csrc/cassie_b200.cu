@@ -400,21 +400,29 @@ template <typename real> struct Batch : BatchBase {
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     double t_pack = 0, t_wait = 0, t_unpack = 0;
     auto tq = now();
-    {  // taskPd branch of pd_in_t: rows are uploaded only while some environment uses it (whole batch, before the first launch)
+    // taskPd branch of pd_in_t: task rows are uploaded only while some environment uses that branch.  While task rows exist, the whole batch is
+    // scanned before the first launch (and the rows are dropped again when no environment uses them); otherwise -- the common case, motor PD only --
+    // the scan rides along with the chunks' pack loops, and the first chunk that finds a task entry installs the rows for itself and the later chunks
+    // (the earlier chunks, by their own scan, had none).
+    auto uses_task = [](const pd_in_t &u) { int any = 0; const pd_task_in_t *t[2] = {&u.leftLeg.taskPd, &u.rightLeg.taskPd};
+      for (int sd = 0; sd < 2; sd++) for (int k = 0; k < 6; k++) any |= (t[sd]->torque[k] != 0 || t[sd]->pGain[k] != 0 || t[sd]->dGain[k] != 0); return any; };
+    auto install_task_rows = [&](cudaStream_t on) -> bool {
+      if (!pin_task) CUDA_OK(cudaMallocHost(&pin_task, sizeof(real) * n * TASK_W));
+      if (!A.task) { CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W)); task_from_aos = true; }
+#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
+      for (int e = 0; e < n; e++) { real *row = pin_task + (size_t)e * TASK_W;
+        for (int sd = 0; sd < 2; sd++) { const pd_task_in_t *t = sd ? &pd_in[e].rightLeg.taskPd : &pd_in[e].leftLeg.taskPd; real *r = row + 30 * sd;
+          for (int k = 0; k < 6; k++) { r[k] = (real)t->torque[k]; r[6 + k] = (real)t->pTarget[k]; r[12 + k] = (real)t->dTarget[k]; r[18 + k] = (real)t->pGain[k]; r[24 + k] = (real)t->dGain[k]; } }
+        for (int i = 60; i < TASK_W; i++) row[i] = 0; }
+      CUDA_OK(cudaMemcpyAsync(A.task, pin_task, sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, on));
+      return true; };
+    bool scan_in_chunks = (A.task == nullptr);
+    if (!scan_in_chunks) {
       int any = 0;
 #pragma omp parallel for schedule(static) num_threads(aos_threads) reduction(| : any) if (n >= 512)
-      for (int e = 0; e < n; e++) { const pd_task_in_t *t[2] = {&pd_in[e].leftLeg.taskPd, &pd_in[e].rightLeg.taskPd};
-        for (int sd = 0; sd < 2; sd++) for (int k = 0; k < 6; k++) any |= (t[sd]->torque[k] != 0 || t[sd]->pGain[k] != 0 || t[sd]->dGain[k] != 0); }
-      if (any) {
-        if (!pin_task) CUDA_OK(cudaMallocHost(&pin_task, sizeof(real) * n * TASK_W));
-        if (!A.task) { CUDA_OK(cudaMalloc(&A.task, sizeof(real) * n * TASK_W)); task_from_aos = true; }
-#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
-        for (int e = 0; e < n; e++) { real *row = pin_task + (size_t)e * TASK_W;
-          for (int sd = 0; sd < 2; sd++) { const pd_task_in_t *t = sd ? &pd_in[e].rightLeg.taskPd : &pd_in[e].leftLeg.taskPd; real *r = row + 30 * sd;
-            for (int k = 0; k < 6; k++) { r[k] = (real)t->torque[k]; r[6 + k] = (real)t->pTarget[k]; r[12 + k] = (real)t->dTarget[k]; r[18 + k] = (real)t->pGain[k]; r[24 + k] = (real)t->dGain[k]; } }
-          for (int i = 60; i < TASK_W; i++) row[i] = 0; }
-        CUDA_OK(cudaMemcpyAsync(A.task, pin_task, sizeof(real) * n * TASK_W, cudaMemcpyHostToDevice, stream));
-      } else if (A.task && task_from_aos) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; task_from_aos = false; }   // rows installed with cassie_batch_set_task_pd stay
+      for (int e = 0; e < n; e++) any |= uses_task(pd_in[e]);
+      if (any) { if (!install_task_rows(stream)) return false; }
+      else if (task_from_aos) { CUDA_OK(cudaStreamSynchronize(stream)); CUDA_OK(cudaFree(A.task)); A.task = nullptr; task_from_aos = false; }   // rows installed with cassie_batch_set_task_pd stay
     }
     // cassie_sim_step_pd runs state_output_step in every call (src/cassiemujoco.c:1156): so does the batched entry point, inside the kernel,
     // from the first call that asks for state_out_t rows (unless the caller switched it off or runs the host-side checker instead)
@@ -438,7 +446,8 @@ template <typename real> struct Batch : BatchBase {
     for (int c = 0; c < nchunk; c++) {
       const int e0 = c0[c], e1 = c0[c + 1], cnt = e1 - e0; if (cnt <= 0) { CUDA_OK(cudaEventRecord(aos_done[c], stream)); continue; }
       tq = now();
-#pragma omp parallel for schedule(static) num_threads(aos_threads) if (n >= 512)
+      int any_task = 0;
+#pragma omp parallel for schedule(static) num_threads(aos_threads) reduction(| : any_task) if (n >= 512)
       for (int e = e0; e < e1; e++) {
         real *row = pin_pd + (size_t)e * PD_W; const pd_in_t *u = pd_in + e;
         for (int i = 0; i < 10; i++) {
@@ -446,10 +455,15 @@ template <typename real> struct Batch : BatchBase {
           row[i] = (real)p->torque[k]; row[10 + i] = (real)p->pTarget[k]; row[20 + i] = (real)p->dTarget[k]; row[30 + i] = (real)p->pGain[k]; row[40 + i] = (real)p->dGain[k];
         }
         row[50] = row[51] = 0;
+        if (scan_in_chunks) any_task |= uses_task(*u);
       }
-      t_pack += sec(tq, now());
       const size_t off = (size_t)e0 * PD_W; cudaStream_t cs = nchunk > 1 ? aos_stream[c] : stream;
       if (nchunk > 1) CUDA_OK(cudaStreamWaitEvent(cs, aos_start, 0));
+      if (any_task) {   // first task entry of this call: rows for the whole batch, in place before this chunk's (and every later chunk's) launch
+        if (!install_task_rows(cs)) return false;
+        CUDA_OK(cudaStreamSynchronize(cs)); scan_in_chunks = false;
+      }
+      t_pack += sec(tq, now());
       if (aos_events && c == 0) { if (!aos_ev[0]) for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&aos_ev[i])); CUDA_OK(cudaEventRecord(aos_ev[0], cs)); }
       CUDA_OK(cudaMemcpyAsync(A.pd + off, pin_pd + off, sizeof(real) * cnt * PD_W, cudaMemcpyHostToDevice, cs));   // one DMA per launch: a burst of small PCIe reads from every warp at kernel start measured no faster
       if (aos_events && c == 0) CUDA_OK(cudaEventRecord(aos_ev[1], cs));

@@ -105,6 +105,20 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     d.dof_cvelsrc[i] = (m.jnt_type[j] == JNT_BALL) ? m.dof_parentid[m.jnt_dofadr[j]] : m.dof_parentid[i];
   }
   for (int i = nvm - 1; i >= 0; i--) { int a = m.dof_Madr[i] + 1; for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) { if (d.ntri >= NTRI_MAX) { err = "too many factor entries"; return false; } d.tri[d.ntri++] = ((uint32_t)i << 24) | ((uint32_t)j << 16) | (uint32_t)a; a++; } }
+  // two-level subtree sums: a body whose subtree has more than 13 bodies (the pelvis) takes its own term plus the finished sums of its direct children,
+  // provided there are at most 4 of them, each carries a dof (its first dof's lane holds the child's sum in the bias stage) and none is large itself
+  d.any_big = 0;
+  for (int b = 0; b < MB; b++) d.body_kid_dofs[b] = 0;
+  if (!std::getenv("CASSIE_B200_NOKIDS")) for (int b = 1; b < m.nbody; b++) {
+    if (d.body_subtree_end[b] - b <= 13 || b == xb) continue;
+    uint32_t packed = 0; int nk = 0; bool ok = true;
+    for (int c = b + 1; c < d.body_subtree_end[b] && ok; c++) {
+      if (m.body_parentid[c] != b) continue;
+      if (m.body_dofnum[c] == 0 || nk == 4 || d.body_subtree_end[c] - c > 13 || m.body_dofadr[c] >= nvm) { ok = false; break; }
+      packed |= (uint32_t)(m.body_dofadr[c] + 1) << (8 * nk++);
+    }
+    if (ok && nk > 0) { d.body_kid_dofs[b] = packed; d.any_big = 1; }
+  }
   // balanced factorisation schedule (falls back to the per-ancestor loop when the table would not fit)
   { int total = 0; for (int k = 0; k < nvm; k++) total += d.dof_depth[k] * (d.dof_depth[k] + 1) / 2;
     d.nfac = 0;

@@ -55,6 +55,8 @@ struct DevModel {
   real xb_mass, xb_inertia[3], xb_dsqi[6], padxb[2];  // extra free body: mass, principal inertia (inertial frame = body frame), 1/sqrt of its diagonal mass matrix
   // ---- bodies
   int body_parent[MB], body_depth[MB], body_jntadr[MB], body_jntnum[MB], body_lastdof[MB], body_subtree_end[MB];
+  uint32_t body_kid_dofs[MB];   // bodies with a large subtree: (first dof + 1) of up to 4 direct children, 8 bits each, 0 = none; their subtree sums are composed from the children's (0: summed directly)
+  int any_big, padb[3];
   uint32_t body_dofmask[MB];
   real body_pos[MB][3], body_quat[MB][4], body_ipos[MB][3], body_imat[MB][9], body_mass[MB], body_inertia[MB][3], body_invw[MB];
   // mirror symmetry of the dof tree (two identical legs below a common base chain): lets the row transform and the A = Y Y' products skip the

@@ -668,10 +668,17 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     LANES  // lane = body: composite inertia = sum of cinert over the (contiguous, depth-first) subtree
       if (l < nb) {
         real acc[10]; for (int k = 0; k < 10; ++k) acc[k] = 0;
-        if (l >= 1) for (int b = l; b < cm.body_subtree_end[l]; ++b) for (int k = 0; k < 10; ++k) acc[k] += cinert[10 * b + k];
+        if (l >= 1) { const int end = cm.body_kid_dofs[l] ? l + 1 : cm.body_subtree_end[l]; for (int b = l; b < end; ++b) for (int k = 0; k < 10; ++k) acc[k] += cinert[10 * b + k]; }
         for (int k = 0; k < 10; ++k) crb[10 * l + k] = acc[k];
       }
     ENDL
+    if (cm.any_big) {   // a body with a large subtree (the pelvis): its own term + the finished sums of its direct children (mj_crb's own order of accumulation)
+      LANES
+        if (l < nb && cm.body_kid_dofs[l]) {
+          for (uint32_t kd = cm.body_kid_dofs[l]; kd; kd >>= 8) { const int c = cm.dof_body[(kd & 255u) - 1]; for (int k = 0; k < 10; ++k) crb[10 * l + k] += crb[10 * c + k]; }
+        }
+      ENDL
+    }
     LANES  // lane = dof i: M(i, ancestors)
       if (l < nv) {
         real buf[6], cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)};
@@ -787,13 +794,30 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   ENDL
   LANES { const int ld = cm.body_lastdof[cm.imu_body]; if (l < 6) vecs[96 + l] = (ld >= 0) ? S[6 * ld + l] : real(0); } ENDL
   LV(real, qfrc_smooth); LV(real, qacc_smooth); LV(real, bias);
-  LANES  // lane = dof: bias = cdof . (sum of cfrc over the subtree of the dof's body); passive; actuation; applied
+  // lane = dof: the sum of cfrc over the subtree of the dof's body (a body with a large subtree: its own term, then the sums its children's first dof lanes hold)
+  LV(real, sf0); LV(real, sf1); LV(real, sf2); LV(real, sf3); LV(real, sf4); LV(real, sf5);
+  LANES
+    real acc[6] = {0, 0, 0, 0, 0, 0};
+    if (l < nv) { const int b = cm.dof_body[l], end = cm.body_kid_dofs[b] ? b + 1 : cm.body_subtree_end[b]; for (int d = b; d < end; ++d) for (int k = 0; k < 6; ++k) acc[k] += cfrc[6 * d + k]; }
+    L(sf0) = acc[0]; L(sf1) = acc[1]; L(sf2) = acc[2]; L(sf3) = acc[3]; L(sf4) = acc[4]; L(sf5) = acc[5];
+  ENDL
+  if (cm.any_big) {
+    LV(uint32_t, kd); LV(int, ksrc); LV(int, more); LV(real, g);
+    LANES_NS L(kd) = l < nv ? cm.body_kid_dofs[cm.dof_body[l]] : 0u; ENDL_NS
+    for (int j = 0; j < 4; ++j) {
+      LANES_NS L(ksrc) = (L(kd) & 255u) ? (int)(L(kd) & 255u) - 1 : l; ENDL_NS
+#define KID_ADD_(v) SHFLV(g, v, L(ksrc)); LANES_NS if (L(kd) & 255u) L(v) += L(g); ENDL_NS
+      KID_ADD_(sf0) KID_ADD_(sf1) KID_ADD_(sf2) KID_ADD_(sf3) KID_ADD_(sf4) KID_ADD_(sf5)
+#undef KID_ADD_
+      LANES_NS L(kd) >>= 8; L(more) = L(kd) != 0u; ENDL_NS
+      uint32_t anymore; BALLOT(anymore, more); if (!anymore) break;   // the Cassie pelvis has two such children
+    }
+  }
+  LANES  // lane = dof: bias = cdof . (that sum); passive; actuation; applied
     L(qfrc_smooth) = 0; L(bias) = 0;
     if (l < nv) {
       const int b = cm.dof_body[l];
-      real acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int d = b; d < cm.body_subtree_end[b]; ++d) for (int k = 0; k < 6; ++k) acc[k] += cfrc[6 * d + k];
-      const real bs = L(cd0) * acc[0] + L(cd1) * acc[1] + L(cd2) * acc[2] + L(cd3) * acc[3] + L(cd4) * acc[4] + L(cd5) * acc[5];
+      const real bs = L(cd0) * L(sf0) + L(cd1) * L(sf1) + L(cd2) * L(sf2) + L(cd3) * L(sf3) + L(cd4) * L(sf4) + L(cd5) * L(sf5);
       const int j = cm.dof_jnt[l];
       real passive = -ddamp[l] * L(qvel);
       if (cm.jnt_stiffness[j] != 0 && cm.jnt_type[j] >= 2) passive -= cm.jnt_stiffness[j] * (qpos[cm.jnt_qposadr[j]] - cm.jnt_qspring[j]);

@@ -42,3 +42,28 @@ def test_task_pd_all_entry_points(oracle_mod):
     d = P.CassieBatch(3, precision=P.FP64)
     d.set_qpos(b.qpos())
     d.set_qvel(b.qvel())
+
+
+def test_task_entry_found_in_a_later_chunk():
+    """cassie_sim_step_pd_batch scans for taskPd entries while it packs each chunk of a large batch: an entry that first shows up in the second chunk
+    installs the task rows for that chunk and the later ones (the first chunk has already been launched without them).  Against the compact path."""
+    P = product()
+    n, who = 2085, 1800                                   # two chunks (1056 + 1029); only environment 1800 uses the task branch
+    rows = task_rows(np.random.default_rng(5))
+    pd = (P.pd_in_t * n)()
+    for e in range(n):
+        for side, leg in enumerate((pd[e].leftLeg, pd[e].rightLeg)):
+            for i in range(5):
+                leg.motorPd.pTarget[i], leg.motorPd.pGain[i], leg.motorPd.dGain[i] = PD_TARGET[5 * side + i], PD_PGAIN[i] * 0.3, PD_DGAIN[i]
+    fill_task(pd[who], rows)
+    a, b = P.CassieBatch(n, precision=P.FP64), P.CassieBatch(n, precision=P.FP64)
+    b.set_pd(P.pd_rows(n, pTarget=PD_TARGET, pGain=np.array(PD_PGAIN) * 0.3, dGain=PD_DGAIN))
+    tr = np.zeros((n, 60)); tr[who] = rows
+    b.set_task_pd(tr)
+    for _ in range(40):
+        a.step_pd(pd)
+        b.step(1)
+    qa, qb = a.qpos(), b.qpos()
+    assert np.abs(qa - qb).max() < 1e-9
+    assert np.abs(qa[who] - qa[who - 1]).max() > 1e-4     # the task controller did act on that environment only
+    assert np.abs(qa[0] - qa[who - 1]).max() < 1e-12
