@@ -184,7 +184,7 @@ bool build_dev_model(const HostModel &m, DevModel<real> &d, std::string &err, Bu
     const int k = stat ? MG + n_stat++ : n_dyn++; gmap[g] = k; d.geom_body[k] = b; d.geom_type[k] = m.geom_type[g];
     double R[9]; detail::q2m_d(R, &m.geom_quat[4 * g]);
     for (int c = 0; c < 3; c++) d.geom_size[k][c] = (real)m.geom_size[3 * g + c];
-    d.geom_rbound[k] = (real)m.geom_rbound[g]; d.geom_fric[k] = (real)m.geom_friction[3 * g];
+    d.geom_rbound[k] = (real)m.geom_rbound[g];
     if (!stat) {
       for (int c = 0; c < 3; c++) d.geom_pos[k][c] = (real)m.geom_pos[3 * g + c];
       for (int c = 0; c < 9; c++) d.geom_mat[k][c] = (real)R[c];
@@ -333,11 +333,11 @@ inline int cenv_slot(const HostModel &hm, int nv_main, const int *geom_dev, cons
 
 // default row of per-environment model constants (CE_* layout): the shared model's own values
 template <typename real>
-void init_cenv_row(const DevModel<real> &d, real *row) {
+void init_cenv_row(const DevModel<real> &d, real *row, const HostModel &hm, const int *geom_dev) {
   for (int i = 0; i < CE_W; i++) row[i] = 0;
   for (int b = 0; b < d.nbody; b++) { row[CE_MASS + b] = d.body_mass[b]; for (int k = 0; k < 3; k++) row[CE_IPOS + 3 * b + k] = d.body_ipos[b][k]; row[CE_BINVW + b] = d.body_invw[b]; }
   for (int i = 0; i < d.nv; i++) { row[CE_DAMP + i] = d.dof_damping[i]; row[CE_DINVW + i] = d.dof_invweight0[i]; }
-  for (int g = 0; g < MGT; g++) row[CE_FRIC + g] = d.geom_fric[g];
+  for (int g = 0; g < hm.ngeom && g < 256; g++) if (geom_dev[g] >= 0 && geom_dev[g] < MGT) row[CE_FRIC + geom_dev[g]] = (real)hm.geom_friction[3 * g];   // collision geoms only, in the kernel's numbering
   row[CE_ROOT_MINV] = d.root_mass_inv; row[CE_TOT_MINV] = d.total_mass_inv; row[CE_PGS_SCALE] = d.pgs_scale;
 }
 

@@ -17,13 +17,13 @@ constexpr int MV = 32;        // dofs   (nv <= 32: one lane per dof)
 constexpr int MG = 16;        // collision geoms on moving bodies (world pose recomputed every step)
 constexpr int MGS = 16;       // static collision geoms (world body or bodies welded to it: floor plane, height field, the 15 stair boxes of cassie.xml): device ids MG .. MG + MGS - 1
 constexpr int MGT = MG + MGS;
-constexpr int MPAIR = 192;    // candidate geom pairs in MuJoCo's order (cassie.xml: 9 floor + 9 x 15 box + 9 leg-leg = 153), 32 per collision pass
+constexpr int MPAIR = 160;    // candidate geom pairs in MuJoCo's order (cassie.xml: 9 floor + 9 x 15 box + 9 leg-leg = 153), 32 per collision pass
 constexpr int NPC = 8;        // distinct contact-parameter records among the pairs (mj_contactParam results)
 constexpr int ME = 4;         // connect equalities
 constexpr int MU = 10;        // motors
 constexpr int NM_MAX = 320;   // sparse mass-matrix entries (307 for Cassie)
-constexpr int NTRI_MAX = 288; // off-diagonal entries of the sparse factor (275 for Cassie)
-constexpr int NFAC_MAX = 1600; // rank-1 update pairs of the factorisation schedule (1519 for Cassie)
+constexpr int NTRI_MAX = 276; // off-diagonal entries of the sparse factor (275 for Cassie)
+constexpr int NFAC_MAX = 1520; // rank-1 update pairs of the factorisation schedule (1519 for Cassie)
 constexpr int NEFC = 48;      // constraint rows per env (12 equality + limits + 4 per floor contact); excess contacts are dropped and counted
 constexpr int MAXCON = 12;    // contacts per env
 constexpr int YSTRIDE_MAIN = 33;  // row stride of the constraint matrix in shared memory: dofs + 1 (odd: bank-conflict free both ways)
@@ -79,7 +79,7 @@ struct DevModel {
   int geom_body[MGT], geom_type[MGT], ngeom_static, root_body, npair_a, static_box_mask, padn[2];   // npair_a: pairs without a static box come first
   real geom_pos[MG][3], geom_mat[MG][9];   // moving geoms: frame in their body (row-major rotation)
   real geom_wpose[MGS][12];                // static geoms: world pose as the collision stage wants it (position, z axis, x axis, y axis)
-  real geom_size[MGT][3], geom_rbound[MGT], geom_fric[MGT];   // sizes, bounding-sphere radius (0: plane / height field), sliding friction
+  real geom_size[MGT][3], geom_rbound[MGT];   // sizes, bounding-sphere radius (0: plane / height field)
   real robot_reach, padg[3];               // no robot collision geom reaches farther than this from the root body's origin (obstacle broad phase)
   // candidate pairs: (g1 | g2 << 6 | kind << 12 | parameter record << 16 | rank in MuJoCo's pair order << 20); records = distinct mj_contactParam
   // results.  Stored in two runs, each in MuJoCo's order: [0, npair_a) the pairs without a static box, [npair_a, npair) the static-box pairs, which are

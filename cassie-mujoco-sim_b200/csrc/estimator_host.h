@@ -28,21 +28,28 @@ template <typename T> struct M3T { V3T<T> c0, c1, c2; };   // columns
 template <typename T> CASSIE_HD inline V3T<T> operator*(const M3T<T> &m, V3T<T> v) { return v.x * m.c0 + v.y * m.c1 + v.z * m.c2; }
 template <typename T> CASSIE_HD inline M3T<T> operator*(const M3T<T> &a, const M3T<T> &b) { return {a * b.c0, a * b.c1, a * b.c2}; }
 template <typename T> CASSIE_HD inline M3T<T> rotz(T t) { const T c = std::cos(t), s = std::sin(t); return {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; }
+template <typename T> CASSIE_HD inline M3T<T> rotz_sc(T s, T c) { return {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; }   // the same rotation from a sine / cosine pair the caller already has
 using V3 = V3T<double>; using M3 = M3T<double>;
 
 // ang: hipRoll, hipYaw, hipPitch, knee (motor positions), shin, tarsus (joint encoders), foot (motor position); quat: IMU quaternion (w, x, y, z).
 // T = double on the host and in fp64 batches; the fp32 kernel instance evaluates it in float, which is the archive's own precision for this block
+// sc (optional): {sin, cos} pairs of hipRoll, hipYaw, hipPitch, knee, knee + shin, knee + shin + tarsus, knee + shin + tarsus + foot -- the kernel has
+// them from the foot-pose stage of the same tick (same inputs, same sums), so the seven rotations below are not evaluated a second time
 template <typename T>
-CASSIE_HD inline void estimator_leg_force_t(int side, const T ang[7], const T quat[4], T force[3]) {
+CASSIE_HD inline void estimator_leg_force_t(int side, const T ang[7], const T quat[4], T force[3], const T *sc = nullptr) {
   typedef V3T<T> V; typedef M3T<T> M;
+  T scl[14];
+  if (sc) { for (int i = 0; i < 14; i++) scl[i] = sc[i]; }
+  else { const T a[7] = {ang[0], ang[1], ang[2], ang[3], ang[3] + ang[4], ang[3] + ang[4] + ang[5], ang[3] + ang[4] + ang[5] + ang[6]}; for (int i = 0; i < 7; i++) { scl[2 * i] = std::sin(a[i]); scl[2 * i + 1] = std::cos(a[i]); } }
+#define RZ_(i) rotz_sc(scl[2 * (i)], scl[2 * (i) + 1])
   const T sg = side ? T(-1) : T(1), kn = ang[3], sh = ang[4], ta = ang[5];
   // ---- planar part in the hip-pitch frame (z = common axis of knee, shin, tarsus): the four-bar closure
   const V A{0, 0, T(0.045) * sg}, k0{T(0.12), 0, T(0.0045) * sg}, o4{T(0.06068), T(0.04741), 0}, o5{T(0.43476), T(0.02), 0}, hsp{T(-0.01269), T(-0.03059), T(0.00092) * sg}, Bl{T(0.11877), T(-0.01), 0}, ez{0, 0, 1};
   V hx{T(-0.91211), T(0.40829), T(0.036948) * sg}, hy{T(-0.40992), T(-0.90952), T(-0.068841) * sg};
   hx = (T(1) / std::sqrt(dot(hx, hx))) * hx; hy = hy - dot(hx, hy) * hx; hy = (T(1) / std::sqrt(dot(hy, hy))) * hy;
   const M HF{hx, hy, crs(hx, hy)};
-  const V s0 = k0 + rotz(kn) * o4, t0 = s0 + rotz(kn + sh) * o5;
-  const M R3 = rotz(kn + sh + ta), RH = R3 * HF;
+  const V s0 = k0 + RZ_(3) * o4, t0 = s0 + RZ_(4) * o5;
+  const M R3 = RZ_(5), RH = R3 * HF;
   const V hs0 = t0 + R3 * hsp, axh = RH.c2;
   T H = 0, gd = 1; V B{}, dB{};
   for (int it = 0; it < 5; it++) {   // Newton on |B - A|^2 = L^2 (quadratic: 5 steps from 0 reach the last bit for |H| < 0.3)
@@ -53,11 +60,11 @@ CASSIE_HD inline void estimator_leg_force_t(int side, const T ang[7], const T qu
   const T a = -2 * dot(dB, crs(ez, B - t0)) / gd, b = -2 * dot(dB, crs(ez, B - s0)) / gd;   // dH/dtarsus, dH/dshin
   // ---- serial chain pelvis -> hip roll -> hip yaw -> hip pitch: frame A2 of the hip-pitch link (exact quarter turns)
   const M F0{{0, 0, -1}, {0, 1, 0}, {1, 0, 0}}, F1{{0, 0, 1}, {0, 1, 0}, {-1, 0, 0}}, F2{{0, 0, -1}, {1, 0, 0}, {0, -1, 0}};
-  const M A0 = F0 * rotz(ang[0]);
-  const M A1 = A0 * F1 * rotz(ang[1]);
-  const M A2 = A1 * F2 * rotz(ang[2]);
+  const M A0 = F0 * RZ_(0);
+  const M A1 = A0 * F1 * RZ_(1);
+  const M A2 = A1 * F2 * RZ_(2);
   // foot point in the hip-pitch frame and its partials w.r.t. shin / tarsus (rotations about z through s0 / t0)
-  const V f0 = t0 + R3 * V{T(0.408), T(-0.04), 0}, u = f0 + rotz(kn + sh + ta + ang[6]) * V{T(0.01762), T(0.05219), 0};
+  const V f0 = t0 + R3 * V{T(0.408), T(-0.04), 0}, u = f0 + RZ_(6) * V{T(0.01762), T(0.05219), 0};
   const V ps = A2 * crs(ez, u - s0), pt = A2 * crs(ez, u - t0);
   const T j00 = ps.x - pt.x * b / a, j10 = ps.z - pt.z * b / a, j01 = pt.x / a, j11 = pt.z / a, det = j00 * j11 - j10 * j01;
   const T t0_ = T(1500.0) * sh, t1_ = T(1250.0) * (H - T(2.586e-6));
@@ -65,8 +72,10 @@ CASSIE_HD inline void estimator_leg_force_t(int side, const T ang[7], const T qu
   // ---- heading-free world frame
   const T w = quat[0], x = quat[1], y = quat[2], z = quat[3];
   const T wx = (1 - 2 * (y * y + z * z)) * fx + 2 * (x * z + w * y) * fz, wy = 2 * (x * y + w * z) * fx + 2 * (y * z - w * x) * fz, wz = 2 * (x * z - w * y) * fx + (1 - 2 * (x * x + y * y)) * fz;
-  const T yaw = std::atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z)), cy = std::cos(yaw), sy = std::sin(yaw);
+  // heading: cos / sin of yaw = atan2(a, b) are b / |(a, b)| and a / |(a, b)|
+  const T ya = 2 * (w * z + x * y), yb = 1 - 2 * (y * y + z * z), yn = std::sqrt(ya * ya + yb * yb), cy = yn > 0 ? yb / yn : T(1), sy = yn > 0 ? ya / yn : T(0);
   force[0] = cy * wx + sy * wy; force[1] = -sy * wx + cy * wy; force[2] = wz;
+#undef RZ_
 }
 CASSIE_HD inline void estimator_leg_force(int side, const double ang[7], const double quat[4], double force[3]) { estimator_leg_force_t<double>(side, ang, quat, force); }
 

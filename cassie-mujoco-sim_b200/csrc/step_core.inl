@@ -75,6 +75,7 @@ template <typename real> struct EnvPtrs {
   const real *task;   // [TASK_W] task-space PD rows (pd_in_t taskPd of both legs) or null
   const real *gait;   // [GAIT_W] open-loop gait on the motor-PD targets: pTarget_i(t) = pd.pTarget_i + amp_i sin(2 pi f t + phase_i), t = ticks since reset x 0.5 ms; or null
   real *obs;          // [OBS_W] or null
+  real *obs_host = nullptr;   // [OBS_W] or null: the environment's observation row in mapped host memory (the AoS entry point); written as soon as the row is final
   real *qM;           // [2 NM_MAX] scratch: M (debug dump / set_const only), then the factor of M + h B carried from the CRB stage to the Euler stage
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
   real *dbg;          // [D_SIZE] or null
@@ -1602,7 +1603,7 @@ CFN void est_foot(int side, const real *sc, const real *rate, real *out, real *j
 // ds layout (doubles): [0..121] the environment's estimator row (devmodel.h ES_*), [128 + 64 f ..] per-filter parameters a1[6] zm[4] Qd[6] misc,
 // [320 + 96 f ..] per-filter work: G[N][K] (24), HP[K][N] (24), S[K][2K] (32), (gain reuses G's slot after S is inverted: Kg[N][K] at +80, 16.. no: see offsets)
 template <typename real>
-CNOINLINE void est_stage(real *sm, const real *cst, real *obs, double *est) {
+CNOINLINE void est_stage(real *sm, const real *cst, real *obs, double *est, const real *sc) {   // sc: {sin, cos} of the 2 x 7 chain angles (foot-pose stage of this tick)
   DECL_LANE
   double *ds = reinterpret_cast<double *>(sm + S_Y);
   real *eo = obs + OB_EST_OUT;
@@ -1613,7 +1614,7 @@ CNOINLINE void est_stage(real *sm, const real *cst, real *obs, double *est) {
     if (l < 2) {
       const int sd = l; const real *mp = cst + CS_DPOS + 5 * sd, *jp = cst + CS_JPOS + 3 * sd, *q = cst + CS_SENSOR + 16;
       const real ang[7] = {mp[0], mp[1], mp[2], mp[3], jp[0], jp[1], mp[4]}, qd[4] = {q[0], q[1], q[2], q[3]};
-      real f[3]; estimator_leg_force_t<real>(sd, ang, qd, f);
+      real f[3]; estimator_leg_force_t<real>(sd, ang, qd, f, sc + 14 * sd);
       for (int k = 0; k < 3; ++k) { est[ES_FORCE + 3 * sd + k] = (double)f[k]; eo[EO_TOE + 3 * sd + k] = f[k]; }
     }
     // the environment's filter row -> shared memory (the force slots are rewritten above, read back from `est` below)
@@ -1933,7 +1934,7 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
         }
       ENDL
       // ---- state_output_step, spring-force model and filters: the warp-parallel stage above (extended instance only)
-      if constexpr (EST) { if (est_on) est_stage<real>(sm, cs, os, E.est); }
+      if constexpr (EST) { if (est_on) est_stage<real>(sm, cs, os, E.est, vecs + 32); }
     }
     // ---- flush: the rows' modified ranges go back to their HBM rows before the physics (which writes sensordata / actuator_velocity / time there)
     LANES
@@ -1943,6 +1944,12 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       if (wrote_obs) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int i = l + 32 * j; if (i < OBS_W) obs[i] = os[i]; }
+        // the observation of a tick is final BEFORE its physics: the row of the last tick leaves for the host now (zero-copy stores), and crosses
+        // PCIe while the sub-steps run
+        if (E.obs_host && tick == nticks - 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const int i = l + 32 * j; if (i < OBS_W) E.obs_host[i] = os[i]; }
+        }
       }
     ENDL
     }

@@ -33,7 +33,7 @@ template <typename real> struct Emu {
   void run(int nticks, int mode) { if (use_cenv || use_ext) step_env<real, true, F_ALL>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); else step_env<real, false, F_ALL>(dm, sm.data(), ptrs(), qvel, qacc_ws, xqvel, xqacc_ws, nticks, mode); }
   void forward() { run(1, 1); }
   // per-environment model constants + mj_setConst (mode 3 works at the reference configuration, like the kernel wrapper does)
-  void enable_cenv() { if (!use_cenv) { init_cenv_row(dm, cenv); use_cenv = true; } }
+  void enable_cenv() { if (!use_cenv) { init_cenv_row(dm, cenv, hm, info.geom_dev); use_cenv = true; } }
   int model_set(const char *what, const double *v, int n) {   // same slot mapping as the product's cassie_batch_set_* verbs
     enable_cenv(); int w = 0; cenv_slot(hm, dm.nv, info.geom_dev, what, 0, w);
     if (w < 0 || w != n) return -1;
