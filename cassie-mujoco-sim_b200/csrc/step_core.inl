@@ -75,7 +75,6 @@ template <typename real> struct EnvPtrs {
   const real *task;   // [TASK_W] task-space PD rows (pd_in_t taskPd of both legs) or null
   const real *gait;   // [GAIT_W] open-loop gait on the motor-PD targets: pTarget_i(t) = pd.pTarget_i + amp_i sin(2 pi f t + phase_i), t = ticks since reset x 0.5 ms; or null
   real *obs;          // [OBS_W] or null
-  real *obs_host = nullptr;   // [OBS_W] or null: the environment's observation row in mapped host memory (the AoS entry point); written as soon as the row is final
   real *qM;           // [2 NM_MAX] scratch: M (debug dump / set_const only), then the factor of M + h B carried from the CRB stage to the Euler stage
   const float *hfield; // [nrow*ncol] normalised elevations of this env's terrain, or null
   real *dbg;          // [D_SIZE] or null
@@ -1944,12 +1943,6 @@ CFN void step_env(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, LP
       if (wrote_obs) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int i = l + 32 * j; if (i < OBS_W) obs[i] = os[i]; }
-        // the observation of a tick is final BEFORE its physics: the row of the last tick leaves for the host now (zero-copy stores), and crosses
-        // PCIe while the sub-steps run
-        if (E.obs_host && tick == nticks - 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { const int i = l + 32 * j; if (i < OBS_W) E.obs_host[i] = os[i]; }
-        }
       }
     ENDL
     }
