@@ -527,7 +527,7 @@ def gpu_arm(args, rank, local_rank, world):
                 'clocks': clocks,
                 'e2e': {'value': world * n / s_e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n * P.PD_WIDTH * 4, 'd2h_bytes_per_step': n * P.OBS_WIDTH * 4,
                         'api': 'cassie_sim_step_pd_batch(envs, pd_in_t[n] host, state_out_t[n] host): whole state_out_t incl. the estimator (in-kernel leg-force model + Kalman filters), %d steps, host AoS pack/unpack included' % e2e_steps,
-                        'state_out_complete': full, 'split_this_rank_ms': e2e_split, 'host_threads': min(int(os.environ.get('CASSIE_B200_AOS_THREADS', 32)), eff[0]),
+                        'state_out_complete': full, 'split_this_rank_ms': e2e_split, 'host_threads': int(P.lib().cassie_b200_aos_threads()),
                         'estimator_off_variant': {'value': world * n / s_e2e_off, 'note': 'cassie_batch_enable_estimator_device(b, 0): pelvis.position / translationalVelocity / externalForce, terrain.height, toe / heel forces come back zero (partial output)'},
                         'obs_allgather_ms': ms_gather},
                 'gpu_launches': launches, 'per_rank': per_rank,
@@ -569,7 +569,10 @@ def main():
         # pack / unpack threads of this rank: its pinned CPUs, but never more than its share of the cgroup quota (N ranks x 32 threads on a lease that
         # owns 64 CPUs would only throttle each other)
         per_rank = max(1, eff_all // max(1, world))
-        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(max(2, min(32, effective_cpus()[0], per_rank))))
+        # ... and two CPUs of the share stay free for the rank's CUDA driver / NCCL / sampler threads: the OpenMP team busy-waits through the whole
+        # call, and a job whose teams add up to the quota gets throttled as a whole (8 x 12 threads on a 96-CPU lease: e2e 4 x slower)
+        share = min(32, effective_cpus()[0], per_rank)
+        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(max(2, share - 2 if share > 4 else share)))
         args._allowed_cpus = allowed
         gpu_arm(args, rank, local_rank, world)
 

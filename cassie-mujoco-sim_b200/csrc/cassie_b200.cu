@@ -60,6 +60,13 @@ static int effective_cpus() {
   if (quota > 0 && period > 0) { const int c = (int)((quota + period - 1) / period); if (c >= 1 && c < hw) hw = c; }
   return hw < 1 ? 1 : hw;
 }
+// host pack / unpack threads of the AoS entry point.  The OpenMP workers busy-wait between the call's parallel regions, so the team burns its CPUs for the
+// whole call: by default two of the CPUs the process may use (affinity mask clipped by the cgroup quota) are left to the CUDA driver's and the caller's
+// own threads -- a team as large as the quota gets the whole cgroup throttled (measured on an 8-GPU lease: 8 x 12 threads on 96 CPUs, 4 x slower loops)
+static int aos_thread_count() {
+  const char *e = getenv("CASSIE_B200_AOS_THREADS"); const int hw = effective_cpus();
+  int t = e ? atoi(e) : (hw > 4 ? hw - 2 : hw); if (t > 32) t = 32; if (t > hw) t = hw; return t < 1 ? 1 : t;
+}
 
 // cassie_integrate_pos for the whole batch (mj_integratePos, src/cassiemujoco.c:1183-1189): the HBM-bound kernel.
 // A tile of ITILE consecutive environments is one contiguous chunk of the qpos array and one of the qvel array.  Persistent CTAs
@@ -392,7 +399,7 @@ template <typename real> struct Batch : BatchBase {
   // cassie_sim_step_pd for every env with host AoS buffers: pack pd_in_t[] -> pinned rows -> H2D, one tick, D2H rows -> state_out_t[]
   bool step_pd_aos(const pd_in_t *pd_in, state_out_t *state_out, const double *radio) override {
     CUDA_OK(cudaSetDevice(device));
-    static const int aos_threads = [] { const char *e = getenv("CASSIE_B200_AOS_THREADS"); int t = e ? atoi(e) : 32; const int hw = effective_cpus(); if (t > hw) t = hw; return t < 1 ? 1 : t; }();   // host pack / unpack threads
+    static const int aos_threads = aos_thread_count();
     static const bool aos_events = getenv("CASSIE_B200_AOS_EVENTS") != nullptr;
     static const bool aos_obs_dma = [] { const char *e = getenv("CASSIE_B200_AOS_OBS_DMA"); return e && atoi(e) != 0; }();
     static const int aos_chunks = [] { const char *e = getenv("CASSIE_B200_AOS_CHUNKS"); int t = e ? atoi(e) : 2; return t < 1 ? 1 : (t > AOS_MAXC ? AOS_MAXC : t); }();   // launches per call for batches of up to two rounds
@@ -840,6 +847,7 @@ void cassie_batch_get_counters(cassie_batch_t *b, int *out) { b->impl->get_count
 int cassie_batch_debug_dump(cassie_batch_t *b, int env, double *out, int n) { return b->impl->debug_dump(env, out, n); }
 
 void cassie_batch_aos_timing(cassie_batch_t *b, double out[6], int reset) { for (int i = 0; i < 6; i++) out[i] = b->impl->aos_t[i]; if (reset) for (int i = 0; i < 6; i++) b->impl->aos_t[i] = 0; }
+int cassie_b200_aos_threads(void) { return cassie::aos_thread_count(); }
 int cassie_b200_effective_cpus(void) { return cassie::effective_cpus(); }
 void cassie_sim_step_pd_batch(cassie_batch_t *b, const pd_in_t *pd_in, state_out_t *state_out) {
   b->impl->step_pd_aos(pd_in, state_out, b->radio.data());

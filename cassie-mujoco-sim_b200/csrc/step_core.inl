@@ -315,12 +315,30 @@ template <typename real> CFN void sweep_l_spec(const DevModel<real> &cm, const r
   CT19_SWEEP_L(x, xi, SHFLV, BCAST, LANES_NS, ENDL_NS, LNAME_, sm, L(qbit), L(lsel), L(pr));
 }
 // x <- inv(L'DL) x
+#ifdef CASSIE_EMU
 template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *sm, LP(real, x)) {
   DECL_LANE
   if (cm.spec19) sweep_lt_spec(cm, sm, x); else sweep_lt(cm, sm, x);
   LANES_NS if (l < cm.nv) L(x) *= sm[S_DINV + l]; ENDL_NS
   if (cm.spec19) sweep_l_spec(cm, sm, x); else sweep_l(cm, sm, x);
 }
+template <typename real> CFN void solve_l(const DevModel<real> &cm, const real *sm, LP(real, x)) { if (cm.spec19) sweep_l_spec(cm, sm, x); else sweep_l(cm, sm, x); }
+#else
+// The three solves of a sub-step (qacc_smooth, the constraint correction, the implicit-damping Euler step) share ONE copy of the sweeps' code: the
+// kernel's hot instruction footprint is larger than the instruction cache, and the generated sweeps are ~700 instructions of straight-line code per copy.
+// l_only: x <- inv(L) x (the second sweep alone)
+template <typename real> CNOINLINE real solve_shared(const DevModel<real> &cm, const real *sm, real x, int l_only) {
+  DECL_LANE
+  if (!l_only) {
+    if (cm.spec19) sweep_lt_spec(cm, sm, x); else sweep_lt(cm, sm, x);
+    if (l < cm.nv) x *= sm[S_DINV + l];
+  }
+  if (cm.spec19) sweep_l_spec(cm, sm, x); else sweep_l(cm, sm, x);
+  return x;
+}
+template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *sm, real &x) { x = solve_shared(cm, sm, x, 0); }
+template <typename real> CFN void solve_l(const DevModel<real> &cm, const real *sm, real &x) { x = solve_shared(cm, sm, x, 1); }
+#endif
 
 // closest point on triangle abc to p (Ericson, Real-Time Collision Detection 5.1.5); true when it lies strictly inside the face
 template <typename real> CFN bool closest_pt_tri(const real *p, const real *a, const real *b, const real *c, real *q) {
@@ -1389,7 +1407,7 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
     // ---- qacc = qacc_smooth + inv(L) D^-1/2 z ;  qfrc_constraint = J'f = L' D^1/2 z
     LV(real, w);
     LANES L(w) = (l < nv) ? L(z) * sm[S_DSQI + l] : real(0); ENDL
-    if (cm.spec19) sweep_l_spec(cm, sm, w); else sweep_l(cm, sm, w);
+    solve_l(cm, sm, w);
     LANES L(qacc) = L(qacc_smooth) + L(w); L(qfrc_con) = 0; if (xb >= 0 && l < 6) L(xqacc) = L(xqacc_smooth) + L(xz) * (l < 3 ? xb_dsqi_t : cm.xb_dsqi[l]); ENDL
     if (dbg) {  // qfrc_constraint = M (qacc - qacc_smooth); only the debug dump wants it (the Euler stage below does not)
       LANES vecs[128 + l] = L(w); ENDL

@@ -286,6 +286,8 @@ void cassie_b200_estimator_filter_step(void *filter, state_out_t *y);
  * clipped by the cgroup quota), which bounds the pack / unpack threads (CASSIE_B200_AOS_THREADS, default 32) */
 void cassie_batch_aos_timing(cassie_batch_t *b, double out[6], int reset);
 int cassie_b200_effective_cpus(void);
+/* OpenMP threads cassie_sim_step_pd_batch packs / unpacks with: CASSIE_B200_AOS_THREADS, else the CPUs above minus two (at most 32) */
+int cassie_b200_aos_threads(void);
 /* Batched snapshots (new): every row array of the batch copied device-to-device into an opaque handle; restore all environments or the masked
  * subset (mask as in cassie_batch_reset; e.g. return the fallen robots of an RL batch to a stored standing state).  0 / -1. */
 void *cassie_batch_state_alloc(cassie_batch_t *b);
