@@ -315,7 +315,7 @@ template <typename real> CFN void sweep_l_spec(const DevModel<real> &cm, const r
   CT19_SWEEP_L(x, xi, SHFLV, BCAST, LANES_NS, ENDL_NS, LNAME_, sm, L(qbit), L(lsel), L(pr));
 }
 // x <- inv(L'DL) x
-#ifdef CASSIE_EMU
+#if defined(CASSIE_EMU) || !defined(CASSIE_SHARED_SOLVES)
 template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *sm, LP(real, x)) {
   DECL_LANE
   if (cm.spec19) sweep_lt_spec(cm, sm, x); else sweep_lt(cm, sm, x);
@@ -324,8 +324,9 @@ template <typename real> CFN void solve_m(const DevModel<real> &cm, const real *
 }
 template <typename real> CFN void solve_l(const DevModel<real> &cm, const real *sm, LP(real, x)) { if (cm.spec19) sweep_l_spec(cm, sm, x); else sweep_l(cm, sm, x); }
 #else
-// The three solves of a sub-step (qacc_smooth, the constraint correction, the implicit-damping Euler step) share ONE copy of the sweeps' code: the
-// kernel's hot instruction footprint is larger than the instruction cache, and the generated sweeps are ~700 instructions of straight-line code per copy.
+// -DCASSIE_SHARED_SOLVES: the three solves of a sub-step (qacc_smooth, the constraint correction, the implicit-damping Euler step) share ONE copy of the
+// sweeps' code (-1.6 k static instructions; the hot footprint is larger than the instruction cache).  Measured A/B on config 2: 25.6 vs 25.9 M with the
+// inlined copies, same end to end -- so the inlined copies are the default.
 // l_only: x <- inv(L) x (the second sweep alone)
 template <typename real> CNOINLINE real solve_shared(const DevModel<real> &cm, const real *sm, real x, int l_only) {
   DECL_LANE
