@@ -772,13 +772,21 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   real *cfrc = sm + S_Y + T_CFRC;  // [32][6]
   real *vecs = sm + S_VEC;
   LANES if (l < nv) vecs[l] = L(qvel); ENDL
+  // chain sums over a dof's ancestors: with two legs below a common base chain (sym_on) a leg dof walks its own leg only and then takes the base chain's
+  // finished sum (the base's last dof), which is also the root-first order mj_comVel accumulates in
+#ifdef CASSIE_NO_CHAIN_CUT
+  const int chain_cut = -1;
+#else
+  const int chain_cut = cm.sym_on ? cm.sym_first - 1 : -1;
+#endif
   LANES  // lane = dof: S_d = sum over the chain root..d of cdof_a * qvel_a
     if (l < nv) {
-      real acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int a = l; a >= 0; a = cm.dof_parent[a]) { const real q = vecs[a]; const real *c = cdof + 6 * a; for (int k = 0; k < 6; ++k) acc[k] += c[k] * q; }
+      real acc[6] = {0, 0, 0, 0, 0, 0}; const int stop = l > chain_cut ? chain_cut : -1;
+      for (int a = l; a > stop; a = cm.dof_parent[a]) { const real q = vecs[a]; const real *c = cdof + 6 * a; for (int k = 0; k < 6; ++k) acc[k] += c[k] * q; }
       for (int k = 0; k < 6; ++k) S[6 * l + k] = acc[k];
     }
   ENDL
+  if (chain_cut >= 0) { LANES if (l < nv && l > chain_cut) for (int k = 0; k < 6; ++k) S[6 * l + k] += S[6 * chain_cut + k]; ENDL }
   LANES  // cdof_dot = (velocity before this joint) x cdof ; body velocities
     if (l < nv) {
       real vb[6] = {0, 0, 0, 0, 0, 0}, cd[6] = {L(cd0), L(cd1), L(cd2), L(cd3), L(cd4), L(cd5)}, r[6];
@@ -791,11 +799,12 @@ CFN void mj_substep(const DevModel<real> &cm, real *sm, const EnvPtrs<real> &E, 
   ENDL
   LANES  // T_d = chain sums of cdof_dot * qvel (overwrites S; nobody reads S in this phase)
     if (l < nv) {
-      real acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int a = l; a >= 0; a = cm.dof_parent[a]) { const real q = vecs[a]; const real *c = cdofd + 6 * a; for (int k = 0; k < 6; ++k) acc[k] += c[k] * q; }
+      real acc[6] = {0, 0, 0, 0, 0, 0}; const int stop = l > chain_cut ? chain_cut : -1;
+      for (int a = l; a > stop; a = cm.dof_parent[a]) { const real q = vecs[a]; const real *c = cdofd + 6 * a; for (int k = 0; k < 6; ++k) acc[k] += c[k] * q; }
       for (int k = 0; k < 6; ++k) S[6 * l + k] = acc[k];
     }
   ENDL
+  if (chain_cut >= 0) { LANES if (l < nv && l > chain_cut) for (int k = 0; k < 6; ++k) S[6 * l + k] += S[6 * chain_cut + k]; ENDL }
   LANES  // lane = body: cfrc = cinert * cacc + cvel x* (cinert * cvel), cacc = (0; -g) + T[lastdof]
     if (l < nb) {
       real f[6] = {0, 0, 0, 0, 0, 0};
