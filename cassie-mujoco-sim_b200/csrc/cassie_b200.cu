@@ -259,7 +259,7 @@ template <typename real> struct Batch : BatchBase {
     feat = hmodel->xb >= 0 ? F_XB : 0;   // which kernel instance this model needs (step_inst.cu)
     for (int p = 0; p < hmodel->npair; p++) { const int k = pair_kind(hmodel->pair_code[p]); if (k == PAIR_HFIELD_SPHERE || k == PAIR_HFIELD_CAPSULE) feat |= F_HFIELD; else if (k >= PAIR_PLANE_BOX) feat |= F_BOX; }
     const int hmodel_ystride = hmodel->ystride; QW = hmodel->qpos_w; VW = hmodel->qvel_w; A.qpos_w = QW; A.qvel_w = VW; A.ystride = hmodel_ystride; A.xb = hmodel->xb; free(hmodel);
-    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; { const char *e = getenv("CASSIE_B200_SYNCMASK"); A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : (e ? (atoi(e) & 63) : 10); }   // which of the five per-sub-step rendezvous are on
+    A.n = n; A.hfield = nullptr; A.n_terrain = 1; A.hfield_stride = 0; { const char *e = getenv("CASSIE_B200_SYNCMASK"); A.cta_sync = getenv("CASSIE_B200_NOSYNC") ? 0 : (e ? (atoi(e) & 127) : 10); }   // which of the five per-sub-step rendezvous are on
     if (hm.nhfield == 1 && !set_hfield(nullptr, 1)) return false;
     CUDA_OK(cudaMalloc(&A.qpos, sizeof(real) * n * QW)); CUDA_OK(cudaMalloc(&A.qvel, sizeof(real) * n * VW)); CUDA_OK(cudaMalloc(&A.qacc_ws, sizeof(real) * n * VW));
     CUDA_OK(cudaMalloc(&A.cst, sizeof(real) * n * CST_W)); CUDA_OK(cudaMalloc(&A.pd, sizeof(real) * n * PD_W)); CUDA_OK(cudaMalloc(&A.xfrc, sizeof(real) * n * XFRC_W));

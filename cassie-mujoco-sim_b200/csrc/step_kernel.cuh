@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(512) cassie_step_kernel(const DevModel<real> *
   const int stride = gridDim.x * nwarps;
   for (int base = blockIdx.x * nwarps; base < A.n; base += stride) {
     const int env = A.env0 + base + warp;   // a launch covers environments [env0, env0 + n)
-    __syncthreads();   // the warps of a CTA start every round together: they then share instruction-cache lines through the round (measured: 16 384
+    if (!(A.cta_sync & 64)) __syncthreads();   // the warps of a CTA start every round together: they then share instruction-cache lines through the round (measured: 16 384
                        // environments, 7 rounds, -20 % without it), and the multi-tick rendezvous counts below assume it
     { const int nenv = base + warp + stride < A.n ? env + stride : 0x7fffffff;   // warm L2 with the next round's state rows of this warp (about 2 KB per environment, one 128-byte line per lane)
       if (nenv != 0x7fffffff && mode == 0) {
