@@ -447,7 +447,7 @@ template <typename real> struct Batch : BatchBase {
     // and stepping, and unpacks chunk c while the later ones are stepping; the kernels of consecutive chunks overlap at their edges (a chunk's CTAs start
     // on the SMs the previous chunk's CTAs have left, while its last observation rows are still draining over PCIe).  Chunks are whole rounds of the
     // resident warps when the batch is worked off in more than two rounds, equal parts otherwise.
-    const int inst = (A.cenv || A.aux || A.task) ? 1 : (A.est ? 2 : 0), slots = cfg[inst].resident_ctas * cfg[inst].wpb;
+    const int inst = (A.cenv || A.aux || A.task || (A.dbg && !DBG_IN_ALL_INSTANCES)) ? 1 : (A.est ? 2 : 0), slots = cfg[inst].resident_ctas * cfg[inst].wpb;
     int nchunk = 1, c0[AOS_MAXC + 1] = {0};
     if (state_out && n >= 1024 && aos_chunks > 1) {
       if (n <= 2 * slots) { nchunk = aos_chunks; for (int c = 1; c < nchunk; c++) c0[c] = (int)((size_t)n * c / nchunk + 31) / 32 * 32; }
@@ -659,7 +659,7 @@ template <typename real> struct Batch : BatchBase {
     A.nsub = nsub_override;
     // per-environment model constants / derived-quantity rows / task-space PD / set_const: extended instance (its own scratch size and launch shape);
     // the in-kernel estimator alone: the plain instance with the estimator stage
-    const int ext = (A.cenv || A.aux || A.task || mode == 3) ? 1 : (A.est ? 2 : 0);
+    const int ext = (A.cenv || A.aux || A.task || (A.dbg && !DBG_IN_ALL_INSTANCES) || mode == 3) ? 1 : (A.est ? 2 : 0);   // debug batches: the stage dumps live in the extended instance
     A.warp_stride = (int)warp_bytes<real>(A.ystride, ext == 1);
     const LaunchCfg &c = cfg[ext];
     int grid = (count + c.wpb - 1) / c.wpb; if (grid > c.resident_ctas) grid = c.resident_ctas;
