@@ -156,3 +156,25 @@ def test_open_loop_gait_follows_per_tick_targets(oracle_mod):
     q = e.get('qpos').copy()
     e.step(PD_ROW, 1)
     assert np.abs(e.get('qpos') - q).max() > 0
+
+
+def test_table_free_shortcuts_change_nothing_beyond_rounding(pkg):
+    """The stepper takes model-specific shortcuts that must not change the mathematics: the pelvis' subtree sums composed from its children's sums
+    (CASSIE_B200_NOKIDS switches them off) and the code generated for the Cassie dof tree (CASSIE_B200_NOSPEC).  The environment variables are read
+    when a model is built, so the same emulation library runs all three variants; 300 ticks of the standing controller, fp64."""
+    import subprocess, sys
+    code = (
+        "import sys, importlib, numpy as np; sys.path.insert(0, %r); import emu_harness as E; from conftest import PD_TARGET, PD_PGAIN, PD_DGAIN\n"
+        "P = importlib.import_module('cassie-mujoco-sim_b200')\n"
+        "pd = np.zeros(50); pd[10:20] = PD_TARGET; pd[30:40] = (list(PD_PGAIN) * 2)[:10]; pd[40:50] = (list(PD_DGAIN) * 2)[:10]\n"
+        "s = E.EmuSim(P.model_path('cassie')); s.step(pd, 300); print(' '.join(repr(float(x)) for x in s.get('qpos', 35)))\n" % os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {'CASSIE_B200_NOKIDS': '1'}, {'CASSIE_B200_NOSPEC': '1'}):
+        env = dict(os.environ); env.update(extra)
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.array([float(x) for x in r.stdout.strip().split()]))
+    assert outs[0].size == 35 and np.isfinite(outs[0]).all() and outs[0][2] > 0.8
+    for o in outs[1:]:
+        d = np.abs(o - outs[0]).max()
+        assert d < 1e-11, d
