@@ -70,6 +70,13 @@ KERNEL_COUNTS = _kernel_counts()
 
 
 # ------------------------------------------------------------------------------ host CPUs
+def aos_threads_for_rank(cpus_now, per_rank_share):
+    """pack / unpack threads of one rank: its pinned CPUs, never more than its share of the job's CPU quota, at most 32, minus two (kept free for the
+    rank's CUDA driver / NCCL / sampler threads: the OpenMP team busy-waits, and teams that add up to the quota get the whole cgroup throttled)"""
+    share = min(32, cpus_now, per_rank_share)
+    return max(2, share - 2 if share > 4 else share)
+
+
 def effective_cpus():
     """CPUs this process may really use: affinity mask clipped by the cgroup CPU quota (a 1-GPU lease on a 128-thread host may own 16)."""
     try:
@@ -571,8 +578,7 @@ def main():
         per_rank = max(1, eff_all // max(1, world))
         # ... and two CPUs of the share stay free for the rank's CUDA driver / NCCL / sampler threads: the OpenMP team busy-waits through the whole
         # call, and a job whose teams add up to the quota gets throttled as a whole (8 x 12 threads on a 96-CPU lease: e2e 4 x slower)
-        share = min(32, effective_cpus()[0], per_rank)
-        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(max(2, share - 2 if share > 4 else share)))
+        os.environ.setdefault('CASSIE_B200_AOS_THREADS', str(aos_threads_for_rank(effective_cpus()[0], per_rank)))
         args._allowed_cpus = allowed
         gpu_arm(args, rank, local_rank, world)
 

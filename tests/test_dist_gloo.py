@@ -38,3 +38,14 @@ def test_shard_and_gather_world2(n_total):
         p.join(timeout=60)
     assert all(r[1] for r in res), res
     assert sum(r[3] for r in res) == n_total
+
+
+def test_aos_thread_team_leaves_headroom_in_the_cpu_quota():
+    """N ranks x their AoS thread teams must stay below the job's CPU quota (the teams busy-wait; at the quota the whole cgroup is throttled: measured on
+    the 8-GPU lease, 8 x 12 threads on 96 CPUs)"""
+    import bench
+    for quota, world, pinned in ((96, 8, 12), (48, 4, 12), (24, 2, 12), (16, 1, 128), (128, 8, 16), (4, 2, 2)):
+        t = bench.aos_threads_for_rank(pinned, quota // world)
+        assert 2 <= t <= 32 and t <= pinned
+        if quota // world > 4:
+            assert t * world <= quota - 2 * world
